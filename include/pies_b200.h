@@ -1,0 +1,205 @@
+/* pies_b200.h — C ABI of the B200-native Pies solver loop.
+ *
+ * Drop-in boundary: every entry point below replaces one member of the
+ * reference's only public class, Pies::Solver (reference Include/Pies/Solver.h:40-199),
+ * or is an additive extension the reference has no public API for (marked
+ * [additive]).  The header-only C++ class in Include/Pies/Solver.h of
+ * this repo forwards the reference's glm-typed signatures to these functions, so
+ * a host application that used the reference recompiles unchanged and links
+ * libpies_b200.so.  No torch / STL / glm types cross this boundary: plain
+ * pointers, sizes and PODs only.  All functions return 0 on success and a
+ * negative PIES_B200_E* code on failure; pies_b200_last_error() gives the text.
+ * Nothing here falls back to the CPU: without a CUDA device create() fails.
+ *
+ * Threading: one caller thread per solver (same as the reference); tick() is
+ * synchronous — it returns after the vertex mirror has been refreshed.
+ */
+#ifndef PIES_B200_H
+#define PIES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIES_B200_OK 0
+#define PIES_B200_EINVAL -1   /* bad argument */
+#define PIES_B200_ECUDA -2    /* CUDA runtime / launch failure (also latches simFailed) */
+#define PIES_B200_ENODEV -3   /* no usable sm_100 device: there is no CPU fallback */
+#define PIES_B200_ERANGE -4   /* a scene exceeds a documented limit */
+
+/* Mirrors Pies::SolverOptions field for field, same defaults
+ * (reference Include/Pies/Solver.h:23-38); solver: 0 = PBD, 1 = PD
+ * (SolverName, Solver.h:21). */
+typedef struct PiesB200Options {
+  float fixedTimestepSize;                   /* 0.012 */
+  uint32_t timeSubsteps;                     /* 1 */
+  uint32_t iterations;                       /* 4 */
+  uint32_t collisionStabilizationIterations; /* 4 */
+  float collisionThresholdDistance;          /* 0.1 */
+  float collisionThickness;                  /* 0.05 */
+  float gravity;                             /* 10 */
+  float damping;                             /* 0.006 */
+  float friction;                            /* 0.01 */
+  float staticFrictionThreshold;             /* 0 */
+  float floorHeight;                         /* 0 */
+  float gridSpacing;                         /* 2 */
+  uint32_t threadCount;                      /* 8: fixes the canonical order of the collision lists */
+  uint32_t solver;                           /* 1 = PD */
+} PiesB200Options;
+
+/* Mirrors Pies::Solver::Vertex (reference Include/Pies/Solver.h:42-49), 36 bytes. */
+typedef struct PiesB200Vertex {
+  float position[3];
+  float radius;
+  float baseColor[3];
+  float roughness;
+  float metallic;
+} PiesB200Vertex;
+
+/* Solver knobs the reference does not have (its global step is a direct sparse
+ * Cholesky, Solver.cpp:213-215,258-262,356; ours is a preconditioned CG). */
+typedef struct PiesB200Tuning {
+  float pcgTolerance;        /* stop when ||r||_2 <= tol * ||b||_2 per coordinate column; default 1e-7 */
+  uint32_t pcgMaxIterations; /* default 200 */
+  uint32_t pcgCheckEvery;    /* host polls the device convergence flag every k iterations; default 1 */
+  uint32_t reserved;
+} PiesB200Tuning;
+
+/* Counters and device-side phase timings of the most recent tick ([additive]). */
+typedef struct PiesB200Stats {
+  uint64_t staticProjections;    /* static constraint projections per PD iteration (shape/goal count one per member) */
+  uint64_t collisionProjections; /* live point-triangle + floor constraints of the last substep */
+  uint64_t projectionsLastTick;  /* sum over substeps and iterations of (static + live collision) */
+  uint64_t pcgIterationsLastTick;
+  uint64_t kernelLaunchesLastTick;
+  uint32_t triCollisions;
+  uint32_t staticCollisions;
+  uint32_t substepsLastTick;
+  uint32_t simFailed;
+  float msTick;        /* CUDA-event time of the whole tick on the solver stream */
+  float msLocal;       /* local projections + RHS gather (sum over iterations) */
+  float msGlobal;      /* PCG global solve */
+  float msDetect;      /* spatial hash + CCD */
+  float msContact;     /* stabilisation + friction */
+  float msOther;
+  float pcgLastRelResidual;
+  float reserved;
+} PiesB200Stats;
+
+typedef struct PiesB200Solver PiesB200Solver;
+
+/* ---- lifetime (Solver::Solver(const SolverOptions&), ~Solver; Solver.cpp:11-23) ---- */
+void pies_b200_default_options(PiesB200Options* out);
+void pies_b200_default_tuning(PiesB200Tuning* out);
+/* options == NULL behaves like the reference's Solver(SolverOptions{}) (deliberate fix of the
+ * default-ctor hazard).  device < 0 selects the current CUDA device. */
+int pies_b200_create(const PiesB200Options* options, int device, PiesB200Solver** out);
+void pies_b200_destroy(PiesB200Solver* s);
+const char* pies_b200_last_error(const PiesB200Solver* s); /* s may be NULL: last create() error */
+int pies_b200_set_tuning(PiesB200Solver* s, const PiesB200Tuning* t);
+/* Run on a caller-owned CUDA stream (cudaStream_t as void*), e.g. torch's current stream. */
+int pies_b200_set_stream(PiesB200Solver* s, void* cudaStream);
+int pies_b200_get_options(const PiesB200Solver* s, PiesB200Options* out); /* Solver::getOptions, Solver.h:71 */
+
+/* ---- stepping (Solver::tick / tickPD / tickPBD; Solver.cpp:25-486; dt is ignored like the reference) ---- */
+int pies_b200_tick(PiesB200Solver* s, float deltaTime);
+int pies_b200_tick_pd(PiesB200Solver* s, float deltaTime);
+int pies_b200_tick_pbd(PiesB200Solver* s, float deltaTime);
+/* n ticks back to back with a single vertex-mirror refresh at the end [additive]. */
+int pies_b200_tick_n(PiesB200Solver* s, uint32_t n);
+int pies_b200_set_release_hinge(PiesB200Solver* s, int release); /* public member releaseHinge, Solver.h:52 */
+int pies_b200_get_render_state_dirty(const PiesB200Solver* s);   /* public member renderStateDirty, Solver.h:51 */
+int pies_b200_set_render_state_dirty(PiesB200Solver* s, int dirty);
+int pies_b200_sim_failed(const PiesB200Solver* s);               /* the _simFailed latch, Solver.cpp:26-28,852-856 */
+int pies_b200_clear(PiesB200Solver* s);                          /* Solver::clear, Solver.cpp:488-507 */
+
+/* ---- readback (Solver::getVertices/getLines/getTriangles; Solver.h:65-69) ---- */
+uint32_t pies_b200_vertex_count(const PiesB200Solver* s);
+uint32_t pies_b200_line_index_count(const PiesB200Solver* s);
+uint32_t pies_b200_triangle_count(const PiesB200Solver* s);
+/* Pointers stay valid until the next mutating call, like the reference's const refs. */
+const PiesB200Vertex* pies_b200_get_vertices(const PiesB200Solver* s);
+const uint32_t* pies_b200_get_lines(const PiesB200Solver* s);
+const uint32_t* pies_b200_get_triangles(const PiesB200Solver* s); /* 3 per triangle */
+
+/* ---- scene construction: the reference's factories (Src/PrimitiveUtilities.cpp) ---- */
+int pies_b200_add_nodes(PiesB200Solver* s, uint32_t n, const float* xyz);                      /* :42-75 */
+int pies_b200_create_box(PiesB200Solver* s, const float t[3], float scale, float w);           /* :620-847 */
+int pies_b200_create_tet_box(PiesB200Solver* s, const float t[3], float scale, const float v0[3],
+                             float w, float mass, int hinged);                                   /* :330-618 */
+int pies_b200_create_sheet(PiesB200Solver* s, const float t[3], float scale, float mass, float k); /* :849-976 */
+int pies_b200_create_shape_matching_box(PiesB200Solver* s, const float t[3], uint32_t countX,
+                                        uint32_t countY, uint32_t countZ, float scale,
+                                        const float v0[3], float w);                             /* :985-1048 */
+int pies_b200_create_shape_matching_sheet(PiesB200Solver* s, const float t[3], float scale,
+                                          const float v0[3], float w);                           /* :1050-1125 */
+int pies_b200_create_bend_sheet(PiesB200Solver* s, const float t[3], float scale, float w);    /* :1127-1289 */
+/* The post-TetGen half of Solver::addTriMeshVolume (:243-327): the caller runs TetGen (a host-side,
+ * setup-time dependency the reference vendors; the C++ wrapper does it when <tetgen.h> is available)
+ * and passes its output: points, tetrahedra (4 indices each) and the boundary faces already
+ * filtered and re-wound as at :249-267 (3 indices each, local to this mesh). */
+int pies_b200_add_tet_mesh_volume(PiesB200Solver* s, uint32_t nPoints, const float* xyz,
+                                  uint32_t nTets, const uint32_t* tetIdx, uint32_t nTris,
+                                  const uint32_t* triIdx, const float v0[3], float density,
+                                  float strainStiffness, float minStrain, float maxStrain,
+                                  float volumeStiffness, float compression, float stretching);
+/* 4x4 matrices are 16 floats, column-major (glm::mat4 memory layout). */
+int pies_b200_add_fixed_regions(PiesB200Solver* s, uint32_t n, const float* mats, float w);    /* :77-112 */
+int pies_b200_update_fixed_regions(PiesB200Solver* s, uint32_t n, const float* mats);          /* :114-128 */
+int pies_b200_add_linked_regions(PiesB200Solver* s, uint32_t n, const float* mats, float w);   /* :130-162 */
+
+/* ---- [additive] bulk builders: what a white-box host does with createXConstraint
+ *      (reference Include/Pies/Constraints.h:155-230); rest data is taken from the
+ *      current node positions exactly like those factories do. ---- */
+int pies_b200_append_nodes(PiesB200Solver* s, uint32_t n, const float* pos, const float* vel,
+                           const float* radius, const float* invMass, uint32_t* firstId);
+int pies_b200_append_distance_constraints(PiesB200Solver* s, uint32_t n, const uint32_t* ids2, float w);
+int pies_b200_append_position_constraints(PiesB200Solver* s, uint32_t n, const uint32_t* ids, float w);
+int pies_b200_append_tet_constraints(PiesB200Solver* s, uint32_t n, const uint32_t* ids4, float w,
+                                     float minStrain, float maxStrain);
+int pies_b200_append_volume_constraints(PiesB200Solver* s, uint32_t n, const uint32_t* ids4, float w,
+                                        float compression, float stretching);
+int pies_b200_append_bend_constraints(PiesB200Solver* s, uint32_t n, const uint32_t* ids4, float w);
+int pies_b200_append_shape_constraint(PiesB200Solver* s, uint32_t n, const uint32_t* ids, float w);
+int pies_b200_append_triangles(PiesB200Solver* s, uint32_t n, const uint32_t* ids3);
+
+/* ---- [additive] state access for parity tests and hosts that need more than getVertices ---- */
+int pies_b200_get_positions(PiesB200Solver* s, float* xyz);
+int pies_b200_get_prev_positions(PiesB200Solver* s, float* xyz);
+int pies_b200_get_velocities(PiesB200Solver* s, float* xyz);
+/* Any of pos/prev/vel may be NULL (left untouched). */
+int pies_b200_set_state(PiesB200Solver* s, const float* pos, const float* prev, const float* vel);
+/* Runs only the once-per-substep detection pass (reference Solver.cpp:240, :680-875) on the current state. */
+int pies_b200_detect(PiesB200Solver* s);
+uint32_t pies_b200_tri_collision_count(const PiesB200Solver* s);
+uint32_t pies_b200_static_collision_count(const PiesB200Solver* s);
+int pies_b200_get_tri_collisions(PiesB200Solver* s, uint32_t* ids4);   /* canonical reference order */
+int pies_b200_get_static_collisions(PiesB200Solver* s, uint32_t* ids); /* canonical reference order */
+/* Triangle-hash occupancy of the last detect(): cells sorted by (x,y,z), members ascending. */
+int pies_b200_tri_occupancy_counts(PiesB200Solver* s, uint64_t* nCells, uint64_t* nMembers);
+int pies_b200_get_tri_occupancy(PiesB200Solver* s, int64_t* cellsXYZ, uint32_t* counts, uint32_t* members);
+int pies_b200_get_stats(const PiesB200Solver* s, PiesB200Stats* out);
+
+/* ---- [additive] per-kernel probes: run the device functions of the hot kernels on caller data ---- */
+/* Tet strain / volume projections (reference Constraints.cpp:76-128, :205-255): pos 12 floats,
+ * qinv 9 floats column-major per tet; out 12 floats (projected[0..3]). */
+int pies_b200_probe_tet_projection(uint32_t n, const float* pos, const float* qinv, float minStrain,
+                                   float maxStrain, float* out);
+int pies_b200_probe_volume_projection(uint32_t n, const float* pos, const float* qinv, float minOmega,
+                                      float maxOmega, float* out);
+/* pointTriangleCCD (reference CollisionDetection.cpp:227-302): in 18 floats per query. */
+int pies_b200_probe_ccd(uint32_t n, const float* in18, float threshold, int32_t* hit, float* t);
+/* TriCompRange / NodeCompRange (reference Solver.cpp:942-979, :877-901). */
+int pies_b200_probe_tri_range(uint32_t n, const float* pos9, const float* prev9, int64_t* mins, uint32_t* lens);
+int pies_b200_probe_node_range(uint32_t n, const float* pos3, const float* radius, float gridScale,
+                               int64_t* mins, uint32_t* lens);
+/* Stable LSD radix sort used by the cell tables (64-bit keys, 32-bit payload). */
+int pies_b200_probe_sort_pairs(uint64_t n, uint64_t* keys, uint32_t* vals, int keyBits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIES_B200_H */

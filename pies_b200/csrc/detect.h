@@ -1,0 +1,41 @@
+// detect.h — work buffers and entry point of the once-per-substep collision detection.
+#pragma once
+
+#include <algorithm>
+
+#include "engine.h"
+
+namespace pies {
+
+struct DetectInput {
+  const uint32_t* tri;   // 3 node ids per triangle (device)
+  const float4* q;       // current positions
+  const float4* prev;    // positions at the start of the substep
+  uint32_t nTri, nNodes, threadCount;
+  float threshold;       // collisionThresholdDistance
+  float floorLimit;      // floorHeight + collisionThickness
+};
+
+struct DetectWork {
+  DevBuf<int4> triMin;
+  DevBuf<uint32_t> triLen, cnt, hitCount, floorCount, scanScratch;
+  DevBuf<float4> aabbLo, aabbHi;
+  DevBuf<int> bbox;
+  DevBuf<uint64_t> keys, tmpKeys, incKeys, incTmpKeys;
+  DevBuf<uint32_t> vals, tmpVals, pairTri, posOf, memberTri, heads, cellStart, sortHist, incVals, incTmpVals;
+  DevBuf<uint4> triList;
+  DevBuf<uint32_t> floorList, incPtr, floorMult;
+  DevBuf<float> floorW;
+  int* host = nullptr;   // pinned, 16 ints
+  uint64_t nPairs = 0, scanCap = 0;
+  uint32_t nCells = 0;
+  int keyPack[5] = {0, 0, 0, 0, 0};  // minX, minY, minZ, bitsY, bitsZ of the last detection
+  bool failed = false, badInput = false;
+  cudaError_t lastError = cudaSuccess;
+};
+
+// Fills `out` (device pointers owned by `w`) with the point-triangle and floor lists in the
+// reference's canonical order plus the node->entry incidence table.  Returns 0, or -1 on a CUDA error.
+int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, ContactLists& out, int* launches);
+
+}  // namespace pies

@@ -1,0 +1,353 @@
+// engine.cu — device-state management and the per-timestep loops of the B200 solver.
+//
+// tickPD follows reference Solver::tickPD (Src/Solver.cpp:162-486) phase by phase; each
+// phase is one or a few kernels on the solver's stream.  There is no CPU path: if CUDA
+// fails the solver latches simFailed (the reference's only failure mode, Solver.cpp:26-28)
+// and reports the error.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+
+#include "common.cuh"
+#include "contact.h"
+#include "detect.h"
+
+namespace pies {
+
+int fail(PiesB200Solver* s, int code, const char* msg) {
+  if (s) s->err = msg;
+  return code;
+}
+
+int failCuda(PiesB200Solver* s, cudaError_t e, const char* what, int line) {
+  char buf[512];
+  std::snprintf(buf, sizeof(buf), "CUDA error %d (%s) at engine.cu:%d: %s", (int)e, cudaGetErrorString(e), line, what);
+  if (s) { s->err = buf; s->simFailed = true; }
+  return PIES_B200_ECUDA;
+}
+
+// pack kernel for the readback path: float4 (x,y,z,*) -> 3 contiguous floats
+__global__ void __launch_bounds__(kThreads) k_pack3(uint32_t n, const float4* __restrict__ src, float* __restrict__ dst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 v = src[i];
+  dst[3ull * i] = v.x; dst[3ull * i + 1] = v.y; dst[3ull * i + 2] = v.z;
+}
+
+static int gridFor(uint64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+template <typename T, typename U>
+static cudaError_t uploadVec(DevBuf<T>& d, const std::vector<U>& h, cudaStream_t s) {
+  static_assert(sizeof(T) % sizeof(U) == 0, "element packing");
+  return d.upload(reinterpret_cast<const T*>(h.data()), h.size() * sizeof(U) / sizeof(T), s);
+}
+
+int downloadVec3(PiesB200Solver* s, const float4* src, float* dstXYZ) {
+  uint32_t n = s->n;
+  if (!n) return PIES_B200_OK;
+  PIES_CHECK(s, s->packed.reserve(3ull * n));
+  if (s->hostPackedCap < 3ull * n) {
+    if (s->hostPacked) cudaFreeHost(s->hostPacked);
+    s->hostPacked = nullptr; s->hostPackedCap = 0;
+    PIES_CHECK(s, cudaMallocHost(&s->hostPacked, (3ull * n + 64) * sizeof(float)));
+    s->hostPackedCap = 3ull * n + 64;
+  }
+  k_pack3<<<gridFor(n, kThreads), kThreads, 0, s->stream>>>(n, src, s->packed.p);
+  ++s->launches;
+  PIES_CHECK(s, cudaMemcpyAsync(s->hostPacked, s->packed.p, 3ull * n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  PIES_CHECK(s, cudaStreamSynchronize(s->stream));
+  std::memcpy(dstXYZ, s->hostPacked, 3ull * n * sizeof(float));
+  return PIES_B200_OK;
+}
+
+int downloadState(PiesB200Solver* s) {
+  if (!s->deviceNewer || !s->n) { s->deviceNewer = false; return PIES_B200_OK; }
+  int rc;
+  if ((rc = downloadVec3(s, s->q.p, s->scene.pos.data()))) return rc;
+  if ((rc = downloadVec3(s, s->prev.p, s->scene.prev.data()))) return rc;
+  if ((rc = downloadVec3(s, s->vel.p, s->scene.vel.data()))) return rc;
+  if (s->scene.shapeQuat.size() && s->shapeQuat.p)
+    PIES_CHECK(s, cudaMemcpy(s->scene.shapeQuat.data(), s->shapeQuat.p,
+                             std::min(s->scene.shapeQuat.size(), s->shapeQuat.cap) * sizeof(double), cudaMemcpyDeviceToHost));
+  s->deviceNewer = false;
+  return PIES_B200_OK;
+}
+
+static int uploadState(PiesB200Solver* s) {
+  const HostScene& sc = s->scene;
+  uint32_t n = sc.nodeCount();
+  std::vector<float4> q(n), pv(n), vl(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    q[i] = make_float4(sc.pos[3 * i], sc.pos[3 * i + 1], sc.pos[3 * i + 2], sc.invMass[i]);
+    pv[i] = make_float4(sc.prev[3 * i], sc.prev[3 * i + 1], sc.prev[3 * i + 2], sc.radius[i]);
+    vl[i] = make_float4(sc.vel[3 * i], sc.vel[3 * i + 1], sc.vel[3 * i + 2], 0.0f);
+  }
+  PIES_CHECK(s, s->q.upload(q.data(), n, s->stream));
+  PIES_CHECK(s, s->prev.upload(pv.data(), n, s->stream));
+  PIES_CHECK(s, s->vel.upload(vl.data(), n, s->stream));
+  PIES_CHECK(s, cudaStreamSynchronize(s->stream));  // staging vectors die here
+  return PIES_B200_OK;
+}
+
+// Rebuild the device-side topology when the scene changed.  The reference rebuilds only when
+// the NODE count changes (Solver.cpp:168-169, SURVEY F2 — constraints added later never reach
+// its system matrix); here any scene mutation triggers the rebuild, which is identical for hosts
+// that add whole bodies and strictly safer otherwise.
+int ensureBuilt(PiesB200Solver* s) {
+  HostScene& sc = s->scene;
+  if (s->builtVersion == sc.topologyVersion) {
+    if (s->hostStateDirty) {
+      int rcu = uploadState(s);
+      if (rcu) return rcu;
+      s->hostStateDirty = false;
+    }
+    if (sc.goalXformDirty && sc.goalXform.size()) {
+      PIES_CHECK(s, s->goalXform.upload(reinterpret_cast<const float*>(sc.goalXform.data()), sc.goalXform.size() * 16, s->stream));
+      PIES_CHECK(s, cudaStreamSynchronize(s->stream));
+      sc.goalXformDirty = false;
+    }
+    return PIES_B200_OK;
+  }
+  int rc = downloadState(s);
+  if (rc) return rc;
+  const uint32_t n = sc.nodeCount();
+  s->n = n;
+  float h = s->opt.fixedTimestepSize / (float)s->opt.timeSubsteps;
+  unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  buildSystem(sc, h, s->sys, hw);
+  const HostSystem& y = s->sys;
+  cudaStream_t st = s->stream;
+  if ((rc = uploadState(s))) return rc;
+  PIES_CHECK(s, s->msn.reserve(n)); PIES_CHECK(s, s->rhs.reserve(n)); PIES_CHECK(s, s->snap.reserve(n));
+  PIES_CHECK(s, s->pr.reserve(n)); PIES_CHECK(s, s->pp.reserve(n)); PIES_CHECK(s, s->pz.reserve(n)); PIES_CHECK(s, s->pap.reserve(n)); PIES_CHECK(s, s->pdelta.reserve(n));
+  PIES_CHECK(s, s->partials.reserve((size_t)kReduceBlocks * 16)); PIES_CHECK(s, s->scalars.reserve(16)); PIES_CHECK(s, s->flag.reserve(4));
+  PIES_CHECK(s, cudaMemsetAsync(s->partials.p, 0, (size_t)kReduceBlocks * 16 * sizeof(float), st));
+  PIES_CHECK(s, cudaMemsetAsync(s->flag.p, 0, 4 * sizeof(int), st));
+  PIES_CHECK(s, cudaMemsetAsync(s->snap.p, 0, (size_t)n * sizeof(float4), st));
+  PIES_CHECK(s, s->contrib.reserve(y.nContrib + 1));
+  PIES_CHECK(s, cudaMemsetAsync(s->contrib.p, 0, (y.nContrib + 1) * sizeof(float4), st));
+  if (y.posContrib.size())
+    PIES_CHECK(s, cudaMemcpyAsync(s->contrib.p + y.basePos, y.posContrib.data(), y.posContrib.size() * sizeof(float),
+                                  cudaMemcpyHostToDevice, st));
+  PIES_CHECK(s, uploadVec(s->elemIds, y.elemIds, st));
+  PIES_CHECK(s, uploadVec(s->elemQa, y.elemQa, st)); PIES_CHECK(s, uploadVec(s->elemQb, y.elemQb, st));
+  PIES_CHECK(s, uploadVec(s->elemPc, y.elemPc, st)); PIES_CHECK(s, uploadVec(s->elemPd, y.elemPd, st));
+  PIES_CHECK(s, uploadVec(s->distIds, sc.distId, st));
+  {
+    std::vector<float2> rw(sc.distW.size());
+    for (size_t i = 0; i < rw.size(); ++i) rw[i] = make_float2(sc.distRest[i], sc.distW[i]);
+    PIES_CHECK(s, s->distRestW.upload(rw.data(), rw.size(), st));
+    std::vector<float2> aw(sc.bendW.size());
+    for (size_t i = 0; i < aw.size(); ++i) aw[i] = make_float2(sc.bendAngle[i], sc.bendW[i]);
+    PIES_CHECK(s, s->bendAngleW.upload(aw.data(), aw.size(), st));
+    std::vector<float4> pt(sc.posW.size());
+    for (size_t i = 0; i < pt.size(); ++i) pt[i] = make_float4(sc.posTarget[3 * i], sc.posTarget[3 * i + 1], sc.posTarget[3 * i + 2], sc.posW[i]);
+    PIES_CHECK(s, s->posTargetW.upload(pt.data(), pt.size(), st));
+    PIES_CHECK(s, cudaStreamSynchronize(st));
+  }
+  PIES_CHECK(s, uploadVec(s->posIds, sc.posId, st));
+  PIES_CHECK(s, uploadVec(s->bendIds, sc.bendId, st));
+  PIES_CHECK(s, uploadVec(s->shapeOff, sc.shapeOff, st)); PIES_CHECK(s, uploadVec(s->shapeIds, sc.shapeId, st));
+  PIES_CHECK(s, uploadVec(s->shapeMat, sc.shapeMat, st)); PIES_CHECK(s, uploadVec(s->shapeQinv, sc.shapeQinv, st));
+  PIES_CHECK(s, uploadVec(s->shapeQuat, sc.shapeQuat, st)); PIES_CHECK(s, uploadVec(s->shapeW, sc.shapeW, st));
+  PIES_CHECK(s, uploadVec(s->goalOff, sc.goalOff, st)); PIES_CHECK(s, uploadVec(s->goalIds, sc.goalId, st));
+  PIES_CHECK(s, uploadVec(s->goalMat, sc.goalMat, st)); PIES_CHECK(s, uploadVec(s->goalW, sc.goalW, st));
+  PIES_CHECK(s, s->goalXform.upload(reinterpret_cast<const float*>(sc.goalXform.data()), sc.goalXform.size() * 16, st));
+  sc.goalXformDirty = false;
+  PIES_CHECK(s, uploadVec(s->incPtr, y.incPtr, st)); PIES_CHECK(s, uploadVec(s->inc, y.inc, st));
+  PIES_CHECK(s, uploadVec(s->rowPtr, y.rowPtr, st)); PIES_CHECK(s, uploadVec(s->col, y.col, st)); PIES_CHECK(s, uploadVec(s->val, y.val, st));
+  PIES_CHECK(s, uploadVec(s->blockNodes, y.blockNodes, st)); PIES_CHECK(s, uploadVec(s->blockInv, y.blockInv, st));
+  PIES_CHECK(s, uploadVec(s->triIds, sc.triangles, st));
+  PIES_CHECK(s, cudaStreamSynchronize(st));
+  s->builtVersion = sc.topologyVersion;
+  s->hostStateDirty = false;
+  s->stats.staticProjections = y.staticProjections;
+  s->lastPcgIters = 1;
+  return PIES_B200_OK;
+}
+
+int refreshVertexMirror(PiesB200Solver* s) {
+  if (!s->n) return PIES_B200_OK;
+  uint32_t n = s->n;
+  PIES_CHECK(s, s->packed.reserve(3ull * n));
+  if (s->hostPackedCap < 3ull * n) {
+    if (s->hostPacked) cudaFreeHost(s->hostPacked);
+    s->hostPacked = nullptr; s->hostPackedCap = 0;
+    PIES_CHECK(s, cudaMallocHost(&s->hostPacked, (3ull * n + 64) * sizeof(float)));
+    s->hostPackedCap = 3ull * n + 64;
+  }
+  k_pack3<<<gridFor(n, kThreads), kThreads, 0, s->stream>>>(n, s->q.p, s->packed.p);
+  ++s->launches;
+  PIES_CHECK(s, cudaMemcpyAsync(s->hostPacked, s->packed.p, 3ull * n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  PIES_CHECK(s, cudaStreamSynchronize(s->stream));
+  PiesB200Vertex* v = s->scene.vertices.data();
+  const float* p = s->hostPacked;
+  for (uint32_t i = 0; i < n; ++i) { v[i].position[0] = p[3 * i]; v[i].position[1] = p[3 * i + 1]; v[i].position[2] = p[3 * i + 2]; }
+  return PIES_B200_OK;
+}
+
+namespace {
+struct PhaseTimer {
+  PiesB200Solver* s;
+  bool on;
+  cudaEvent_t ev[2];
+  explicit PhaseTimer(PiesB200Solver* s_) : s(s_), on(s_->tune.reserved != 0) {
+    if (on) { cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]); }
+  }
+  ~PhaseTimer() { if (on) { cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); } }
+  void begin() { if (on) cudaEventRecord(ev[0], s->stream); }
+  void end(float& acc) {
+    if (!on) return;
+    cudaEventRecord(ev[1], s->stream);
+    cudaEventSynchronize(ev[1]);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]);
+    acc += ms;
+  }
+};
+}  // namespace
+
+int runDetection(PiesB200Solver* s, ContactLists& lists) {
+  if (!s->detect) {
+    s->detect = new DetectWork();
+    PIES_CHECK(s, cudaMallocHost(&s->detect->host, 16 * sizeof(int)));
+  }
+  if (!s->contact) s->contact = new ContactWork();
+  DetectInput in{s->triIds.p, s->q.p, s->prev.p, s->scene.triCount(), s->n, s->opt.threadCount,
+                 s->opt.collisionThresholdDistance, s->opt.floorHeight + s->opt.collisionThickness};
+  int L = 0;
+  lists = ContactLists{};
+  if (detectTriangles(*s->detect, s->stream, in, lists, &L) != 0)
+    return failCuda(s, s->detect->lastError, "detectTriangles", __LINE__);
+  s->launches += L;
+  PIES_CHECK(s, cudaGetLastError());
+  if (s->detect->badInput) { s->simFailed = true; return fail(s, PIES_B200_ERANGE, "non-finite or out-of-range (|x| >= 2^30) positions reached collision detection"); }
+  if (s->detect->failed) { s->simFailed = true; lists.nTri = lists.nFloor = 0; }  // Solver.cpp:852-856
+  int L2 = buildContactComponents(*s->contact, s->stream, s->n, lists);
+  if (L2 < 0) return failCuda(s, cudaErrorMemoryAllocation, "buildContactComponents", __LINE__);
+  s->launches += L2;
+  if (lists.nTri) PIES_CHECK(s, s->contact->contribC.reserve(4ull * lists.nTri));
+  s->stats.triCollisions = lists.nTri;
+  s->stats.staticCollisions = lists.nFloor;
+  return PIES_B200_OK;
+}
+
+int tickPD(PiesB200Solver* s, bool refreshMirror) {
+  int rc = ensureBuilt(s);
+  if (rc) return rc;
+  const uint32_t n = s->n;
+  s->stats.substepsLastTick = 0;
+  s->stats.projectionsLastTick = 0;
+  s->stats.pcgIterationsLastTick = 0;
+  s->stats.msLocal = s->stats.msGlobal = s->stats.msDetect = s->stats.msContact = s->stats.msOther = 0.0f;
+  uint64_t launches0 = s->launches;
+  if (!n) return PIES_B200_OK;
+  cudaStream_t st = s->stream;
+  const PiesB200Options& o = s->opt;
+  const HostSystem& y = s->sys;
+  const float h = o.fixedTimestepSize / (float)o.timeSubsteps;
+  PhaseTimer timer(s);
+  cudaEvent_t tick0, tick1;
+  cudaEventCreate(&tick0); cudaEventCreate(&tick1);
+  cudaEventRecord(tick0, st);
+
+  TetElems te{s->elemIds.p, s->elemQa.p, s->elemQb.p, s->elemPc.p, s->elemPd.p, y.nElems};
+  DistanceElems de{s->distIds.p, s->distRestW.p, (uint32_t)s->scene.distW.size()};
+  BendElems be{s->bendIds.p, s->bendAngleW.p, (uint32_t)s->scene.bendW.size()};
+  ClusterElems sh{s->shapeOff.p, s->shapeIds.p, (uint32_t)s->scene.shapeW.size(), (uint32_t)s->scene.shapeId.size()};
+  ClusterElems go{s->goalOff.p, s->goalIds.p, (uint32_t)s->scene.goalW.size(), (uint32_t)s->scene.goalId.size()};
+  CsrMatrix A{s->rowPtr.p, s->col.p, s->val.p, n, (uint64_t)y.col.size()};
+  PcgWork pw{s->pr.p, s->pp.p, s->pz.p, s->pap.p, s->pdelta.p, s->partials.p, s->scalars.p, s->flag.p, s->blockNodes.p, s->blockInv.p, y.nBlocks};
+
+  for (uint32_t sub = 0; sub < o.timeSubsteps; ++sub) {
+    timer.begin();
+    s->launches += launchPredict(st, n, s->q.p, s->vel.p, s->msn.p, h);
+    timer.end(s->stats.msOther);
+
+    timer.begin();
+    ContactLists lists;
+    if ((rc = runDetection(s, lists))) { cudaEventDestroy(tick0); cudaEventDestroy(tick1); return rc; }
+    timer.end(s->stats.msDetect);
+    float4* contribC = s->contact ? s->contact->contribC.p : nullptr;
+
+    for (uint32_t it = 0; it < o.iterations; ++it) {
+      timer.begin();
+      s->launches += launchTetElems(st, te, s->q.p, s->contrib.p + y.baseTet);
+      s->launches += launchDistance(st, de, s->q.p, s->contrib.p + y.baseDist);
+      s->launches += launchBend(st, be, s->q.p, s->contrib.p + y.baseBend);
+      s->launches += launchShape(st, sh, s->shapeMat.p, s->shapeQinv.p, s->shapeQuat.p, s->shapeW.p, s->q.p, s->contrib.p + y.baseShape);
+      s->launches += launchGoal(st, go, s->goalMat.p, s->goalXform.p, s->goalW.p, s->contrib.p + y.baseGoal);
+      s->launches += launchContactProject(st, lists, s->q.p, o.collisionThickness, contribC, s->snap.p);
+      s->launches += launchGatherRhs(st, n, s->msn.p, s->incPtr.p, s->inc.p, s->contrib.p, s->rhs.p);
+      s->launches += launchGatherContacts(st, n, lists, contribC, s->snap.p, s->rhs.p);
+      timer.end(s->stats.msLocal);
+
+      timer.begin();
+      s->launches += launchPcgInit(st, A, lists, pw, s->rhs.p, s->q.p, s->tune.pcgTolerance);
+      uint32_t done = 0, burst = std::max(1u, s->lastPcgIters);
+      bool converged = false;
+      while (!converged && done < s->tune.pcgMaxIterations) {
+        uint32_t todo = std::min(burst, s->tune.pcgMaxIterations - done);
+        for (uint32_t k = 0; k < todo; ++k) s->launches += launchPcgIteration(st, A, lists, pw, s->tune.pcgTolerance, (int)((done + k) & 1u));
+        done += todo;
+        PIES_CHECK(s, cudaMemcpyAsync(s->hostFlag, s->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        PIES_CHECK(s, cudaStreamSynchronize(st));
+        converged = s->hostFlag[0] != 0;
+        burst = std::max(1u, s->tune.pcgCheckEvery);
+      }
+      s->launches += launchPcgFinish(st, pw, n, s->q.p);
+      uint32_t used = (uint32_t)s->hostFlag[1];
+      s->lastPcgIters = std::max(1u, used);
+      s->stats.pcgIterationsLastTick += used;
+      timer.end(s->stats.msGlobal);
+      s->stats.projectionsLastTick += y.staticProjections + lists.nTri + lists.nFloor;
+    }
+
+    timer.begin();
+    if (s->contact)
+      s->launches += launchStabilize(st, *s->contact, lists, s->q.p, s->prev.p, s->snap.p, o.collisionThickness,
+                                     o.collisionStabilizationIterations);
+    timer.end(s->stats.msContact);
+    timer.begin();
+    s->launches += launchVelocityUpdate(st, n, s->q.p, s->prev.p, s->vel.p, h, o.damping, o.gravity);
+    timer.end(s->stats.msOther);
+    timer.begin();
+    if (s->contact) s->launches += launchFriction(st, *s->contact, lists, n, s->q.p, s->vel.p, o.friction, o.staticFrictionThreshold);
+    timer.end(s->stats.msContact);
+    s->stats.collisionProjections = lists.nTri + lists.nFloor;
+    ++s->stats.substepsLastTick;
+  }
+  s->deviceNewer = true;
+  cudaEventRecord(tick1, st);
+  PIES_CHECK(s, cudaEventSynchronize(tick1));
+  cudaEventElapsedTime(&s->stats.msTick, tick0, tick1);
+  cudaEventDestroy(tick0); cudaEventDestroy(tick1);
+  PIES_CHECK(s, cudaGetLastError());
+  {
+    float rel = 0.0f;
+    cudaMemcpy(&rel, s->scalars.p, sizeof(float), cudaMemcpyDeviceToHost);
+    s->stats.pcgLastRelResidual = rel;
+  }
+  if (refreshMirror && (rc = refreshVertexMirror(s))) return rc;
+  s->stats.kernelLaunchesLastTick = s->launches - launches0;
+  s->stats.simFailed = s->simFailed ? 1u : 0u;
+  return PIES_B200_OK;
+}
+
+int tickPBD(PiesB200Solver* s, bool) {
+  return fail(s, PIES_B200_EINVAL, "PBD path (reference Solver::tickPBD, Solver.cpp:40-160) is not built yet in this round");
+}
+
+}  // namespace pies
+
+PiesB200Solver::~PiesB200Solver() {
+  if (detect) { if (detect->host) cudaFreeHost(detect->host); delete detect; }
+  delete contact;
+  if (hostPacked) cudaFreeHost(hostPacked);
+  if (hostFlag) cudaFreeHost(hostFlag);
+  if (ownStream && stream) cudaStreamDestroy(stream);
+}

@@ -1,0 +1,109 @@
+// engine.h — the solver object behind the C ABI: host scene + device state + tick loops.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "scene.h"
+#include "system.h"
+
+namespace pies {
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  // grow-only; contents are NOT preserved
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    release();
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want; else p = nullptr;
+    return e;
+  }
+  cudaError_t upload(const T* src, size_t n, cudaStream_t s) {
+    cudaError_t e = reserve(n);
+    if (e != cudaSuccess || !n) return e;
+    return cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+
+struct DetectWork;   // detect.cu
+struct ContactWork;  // contact.cu
+
+}  // namespace pies
+
+struct PiesB200Solver {
+  pies::HostScene scene;
+  PiesB200Options opt{};
+  PiesB200Tuning tune{};
+  PiesB200Stats stats{};
+  bool releaseHinge = false, renderStateDirty = true, simFailed = false;
+  std::string err;
+
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+
+  // ---- device state ----
+  uint64_t builtVersion = ~0ull;
+  bool deviceNewer = false;   // device q/prev/vel are ahead of scene.pos/prev/vel
+  bool hostStateDirty = false; // scene.pos/prev/vel were overwritten (set_state) and must be re-uploaded
+  uint32_t n = 0;
+  pies::HostSystem sys;
+  pies::DevBuf<float4> q, prev, vel, msn, rhs, contrib, snap;
+  pies::DevBuf<float4> pr, pp, pz, pap, pdelta;
+  pies::DevBuf<float> partials, scalars;
+  pies::DevBuf<int> flag;
+  pies::DevBuf<uint4> elemIds;
+  pies::DevBuf<float4> elemQa, elemQb, elemPc, elemPd;
+  pies::DevBuf<uint2> distIds; pies::DevBuf<float2> distRestW;
+  pies::DevBuf<uint4> bendIds; pies::DevBuf<float2> bendAngleW;
+  pies::DevBuf<uint32_t> shapeOff, shapeIds, goalOff, goalIds;
+  pies::DevBuf<double> shapeMat, shapeQinv, shapeQuat;
+  pies::DevBuf<float> shapeW, goalMat, goalXform, goalW;
+  pies::DevBuf<int> incPtr; pies::DevBuf<uint32_t> inc;
+  pies::DevBuf<int> rowPtr, col; pies::DevBuf<float> val;
+  pies::DevBuf<int> blockNodes; pies::DevBuf<float> blockInv;
+  pies::DevBuf<uint32_t> triIds;  // 3 per triangle
+  pies::DevBuf<float> packed;     // 3 floats per node, readback staging
+  // PBD
+  pies::DevBuf<uint32_t> posIds; pies::DevBuf<float4> posTargetW;
+
+  pies::DetectWork* detect = nullptr;
+  pies::ContactWork* contact = nullptr;
+
+  float* hostPacked = nullptr;  // pinned, 3 floats per node
+  size_t hostPackedCap = 0;
+  int* hostFlag = nullptr;      // pinned, 4 ints
+  uint32_t lastPcgIters = 1;
+  uint64_t launches = 0;
+
+  ~PiesB200Solver();
+};
+
+namespace pies {
+int failCuda(PiesB200Solver* s, cudaError_t e, const char* what, int line);
+int fail(PiesB200Solver* s, int code, const char* msg);
+int ensureBuilt(PiesB200Solver* s);
+int downloadState(PiesB200Solver* s);  // device -> scene.pos/prev/vel
+int tickPD(PiesB200Solver* s, bool refreshMirror);
+int tickPBD(PiesB200Solver* s, bool refreshMirror);
+int refreshVertexMirror(PiesB200Solver* s);
+int runDetection(PiesB200Solver* s, ContactLists& lists);
+}  // namespace pies
+
+#define PIES_CHECK(s, expr)                                                        \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) return pies::failCuda((s), _e, #expr, __LINE__);        \
+  } while (0)

@@ -1,0 +1,99 @@
+// kernels.h — launch wrappers of the sm_100a kernels (host-callable).
+// Every wrapper enqueues on the given stream and returns the number of kernel
+// launches it made (so the engine can report gpu_launches honestly).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pies {
+
+// ---------------------------------------------------------------- layouts ----
+// Node state, one float4 per node so a constraint gathers a node with one 16 B load:
+//   q    = (x, y, z, invMass)         current position
+//   prev = (x, y, z, radius)          Node::prevPosition
+//   vel  = (vx, vy, vz, 0)
+//   msn  = M s_n / h^2 (Solver.cpp:234-237), rhs = right-hand side of the global step.
+//
+// Fused tet elements: a strain constraint and a volume constraint on the same tet share
+// ids and Qinv, so they are stored (and their SVD computed) once.  Five 16 B planes:
+struct TetElems {
+  uint4* ids = nullptr;      // node ids
+  float4* qa = nullptr;      // Qinv[0..3]   (glm column-major)
+  float4* qb = nullptr;      // Qinv[4..7]
+  float4* pc = nullptr;      // Qinv[8], wStrain, minStrain, maxStrain
+  float4* pd = nullptr;      // wVolume, minOmega, maxOmega, unused
+  uint32_t n = 0;
+};
+
+struct DistanceElems { uint2* ids = nullptr; float2* restW = nullptr; uint32_t n = 0; };
+struct BendElems { uint4* ids = nullptr; float2* angleW = nullptr; uint32_t n = 0; };
+struct ClusterElems {  // shape- and goal-matching clusters (CSR over members)
+  uint32_t* off = nullptr;   // nClusters + 1
+  uint32_t* ids = nullptr;   // member node ids
+  uint32_t nClusters = 0, nMembers = 0;
+};
+
+// CSR of S = M/h^2 + sum w A^T A (Solver.cpp:174-210), both triangles.
+struct CsrMatrix { int* rowPtr = nullptr; int* col = nullptr; float* val = nullptr; uint32_t n = 0; uint64_t nnz = 0; };
+
+// Per-substep collision lists in the reference's canonical order.
+struct ContactLists {
+  uint4* tri = nullptr;        // (a, b, c, d): point a against triangle (b, c, d)
+  uint32_t* floorNode = nullptr;
+  uint32_t nTri = 0, nFloor = 0;
+  // node -> incident point-triangle entries, CSR (value = 4 * entry + slot), entries ascending
+  int* incPtr = nullptr; uint32_t* inc = nullptr;
+  float* floorW = nullptr;     // per node: sum of floor-contact weights (multiplicity * 1e4)
+  uint32_t* floorMult = nullptr;
+};
+
+// ------------------------------------------------------------- PD kernels ----
+int launchPredict(cudaStream_t s, uint32_t n, float4* q, const float4* vel, float4* msn, float h);
+int launchTetElems(cudaStream_t s, const TetElems& e, const float4* q, float4* contrib);
+int launchDistance(cudaStream_t s, const DistanceElems& e, const float4* q, float4* contrib);
+int launchBend(cudaStream_t s, const BendElems& e, const float4* q, float4* contrib);
+int launchGoal(cudaStream_t s, const ClusterElems& c, const float* material /*3 per member*/,
+               const float* xform /*16 per cluster*/, const float* w, float4* contrib);
+int launchShape(cudaStream_t s, const ClusterElems& c, const double* material, const double* qinv,
+                double* quat /*4 per cluster, state*/, const float* w, const float4* q, float4* contrib);
+int launchGatherRhs(cudaStream_t s, uint32_t n, const float4* msn, const int* incPtr, const uint32_t* inc,
+                    const float4* contrib, float4* rhs);
+int launchVelocityUpdate(cudaStream_t s, uint32_t n, const float4* q, float4* prev, float4* vel, float h,
+                         float damping, float gravity);
+
+// ------------------------------------------------------------------ PCG -----
+struct PcgWork {
+  float4 *r = nullptr, *p = nullptr, *z = nullptr, *ap = nullptr, *delta = nullptr;
+  float* partials = nullptr;   // kReduceBlocks * 16 floats
+  float* scalars = nullptr;    // see pcg.cu
+  int* flag = nullptr;         // [0] converged, [1] iterations done
+  // block-Jacobi preconditioner: blocks of <= 32 nodes, dense inverse of S restricted to the block
+  int* blockNodes = nullptr;   // nBlocks * 32 node ids (-1 = padding)
+  float* blockInv = nullptr;   // nBlocks * 1024, symmetric, [j*32 + i]
+  uint32_t nBlocks = 0;
+};
+// Solves A (x + delta) = b for the correction delta, starting from delta = 0 with the start
+// residual b - A x accumulated in fp64.
+int launchPcgInit(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w,
+                  const float4* b, const float4* x, float tol);
+// parity = iteration index & 1 (selects the double-buffered r.z partial slot)
+int launchPcgIteration(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, float tol,
+                       int parity);
+// x += delta: the correction is accumulated separately and added with a single rounding
+int launchPcgFinish(cudaStream_t s, const PcgWork& w, uint32_t n, float4* x);
+
+// ----------------------------------------------------------------- scan -----
+// In-place exclusive scan of data[0..n); scratch holds scanScratchElems(n) uint32.
+size_t scanScratchElems(uint64_t n);
+int launchExclusiveScan(cudaStream_t s, uint32_t* data, uint64_t n, uint32_t* scratch);
+
+// ----------------------------------------------------------------- sort -----
+// Stable LSD radix sort of (64-bit key, 32-bit value) pairs on keyBits low bits.
+// keys/vals are sorted in place; tmpKeys/tmpVals are same-size scratch; hist is
+// scratch of sortHistBytes(n) bytes.
+size_t sortHistBytes(uint64_t n);
+int launchSortPairs(cudaStream_t s, uint64_t n, uint64_t* keys, uint32_t* vals, uint64_t* tmpKeys,
+                    uint32_t* tmpVals, void* hist, int keyBits);
+
+}  // namespace pies
