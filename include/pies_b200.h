@@ -12,7 +12,7 @@
  * Nothing here falls back to the CPU: without a CUDA device create() fails.
  *
  * Threading: one caller thread per solver (same as the reference); tick() is
- * synchronous — it returns after the vertex mirror has been refreshed.
+ * synchronous — it returns after the device has finished the tick.
  */
 #ifndef PIES_B200_H
 #define PIES_B200_H
@@ -65,7 +65,7 @@ typedef struct PiesB200Tuning {
   float pcgTolerance;        /* stop when ||r||_2 <= tol * ||b||_2 per coordinate column; default 1e-7 */
   uint32_t pcgMaxIterations; /* default 200 */
   uint32_t pcgCheckEvery;    /* host polls the device convergence flag every k iterations; default 1 */
-  uint32_t reserved;
+  uint32_t reserved;         /* 1 = record per-phase CUDA-event timings into PiesB200Stats (no extra syncs) */
 } PiesB200Tuning;
 
 /* Counters and device-side phase timings of the most recent tick ([additive]). */
@@ -86,7 +86,9 @@ typedef struct PiesB200Stats {
   float msContact;     /* stabilisation + friction */
   float msOther;
   float pcgLastRelResidual;
-  float reserved;
+  float msTetKernel;           /* time inside the fused tet strain+volume projection kernel alone */
+  uint32_t tetKernelLaunches;  /* its launches in the last tick */
+  uint32_t reserved;
 } PiesB200Stats;
 
 typedef struct PiesB200Solver PiesB200Solver;
@@ -108,7 +110,7 @@ int pies_b200_get_options(const PiesB200Solver* s, PiesB200Options* out); /* Sol
 int pies_b200_tick(PiesB200Solver* s, float deltaTime);
 int pies_b200_tick_pd(PiesB200Solver* s, float deltaTime);
 int pies_b200_tick_pbd(PiesB200Solver* s, float deltaTime);
-/* n ticks back to back with a single vertex-mirror refresh at the end [additive]. */
+/* n ticks back to back [additive]. */
 int pies_b200_tick_n(PiesB200Solver* s, uint32_t n);
 int pies_b200_set_release_hinge(PiesB200Solver* s, int release); /* public member releaseHinge, Solver.h:52 */
 int pies_b200_get_render_state_dirty(const PiesB200Solver* s);   /* public member renderStateDirty, Solver.h:51 */
@@ -120,7 +122,8 @@ int pies_b200_clear(PiesB200Solver* s);                          /* Solver::clea
 uint32_t pies_b200_vertex_count(const PiesB200Solver* s);
 uint32_t pies_b200_line_index_count(const PiesB200Solver* s);
 uint32_t pies_b200_triangle_count(const PiesB200Solver* s);
-/* Pointers stay valid until the next mutating call, like the reference's const refs. */
+/* Pointers stay valid until the next mutating call, like the reference's const refs.  The position
+ * mirror is brought up to date (one D2H copy) by the first get_vertices() after a tick. */
 const PiesB200Vertex* pies_b200_get_vertices(const PiesB200Solver* s);
 const uint32_t* pies_b200_get_lines(const PiesB200Solver* s);
 const uint32_t* pies_b200_get_triangles(const PiesB200Solver* s); /* 3 per triangle */

@@ -383,6 +383,20 @@ void pref_get_static_collisions(void* h, uint32_t* ids) {
   for (size_t i = 0; i < s->_staticCollisions.size(); ++i) ids[i] = s->_staticCollisions[i].nodeId;
 }
 int64_t pref_stiffness_nnz(void* h) { return (int64_t)S(h)->_stiffnessMatrix.nonZeros(); }
+// The system of the last global step, white-box: S + C_t in triplet form, the last right-hand side
+// (_forceVector, N x 3 column-major) and the solver's answer (_stateVector).  Used to measure the
+// reference's own fp32 solve error against an fp64 solve of the same float system.
+int64_t pref_system_nnz(void* h) { return (int64_t)S(h)->_stiffnessAndCollisionMatrix.nonZeros(); }
+void pref_get_system(void* h, int32_t* rows, int32_t* cols, float* vals, float* rhs, float* state) {
+  Solver* s = S(h);
+  const Eigen::SparseMatrix<float>& m = s->_stiffnessAndCollisionMatrix;
+  int64_t k = 0;
+  for (int c = 0; c < m.outerSize(); ++c)
+    for (Eigen::SparseMatrix<float>::InnerIterator it(m, c); it; ++it) { rows[k] = (int32_t)it.row(); cols[k] = (int32_t)it.col(); vals[k] = it.value(); ++k; }
+  size_t n = s->_nodes.size();
+  for (size_t i = 0; i < n; ++i)
+    for (int c = 0; c < 3; ++c) { rhs[3 * i + c] = s->_forceVector(i, c); state[3 * i + c] = s->_stateVector(i, c); }
+}
 
 // ---- per-function probes ----------------------------------------------------
 namespace {

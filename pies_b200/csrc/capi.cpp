@@ -133,12 +133,13 @@ int pies_b200_get_options(const PiesB200Solver* s, PiesB200Options* out) {
 static int tickOnce(PiesB200Solver* s, int which, bool refresh) {
   if (s->simFailed) return PIES_B200_OK;  // Solver.cpp:26-28: silent no-op once failed
   cudaSetDevice(s->device);
-  if (which == 0) return pies::tickPBD(s, refresh);
-  return pies::tickPD(s, refresh);
+  (void)refresh;  // the vertex mirror is refreshed lazily by pies_b200_get_vertices
+  if (which == 0) return pies::tickPBD(s, false);
+  return pies::tickPD(s, false);
 }
 int pies_b200_tick(PiesB200Solver* s, float) { return guarded(s, [&]() { return tickOnce(s, (int)s->opt.solver, true); }); }
-int pies_b200_tick_pd(PiesB200Solver* s, float) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::tickPD(s, true); }); }
-int pies_b200_tick_pbd(PiesB200Solver* s, float) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::tickPBD(s, true); }); }
+int pies_b200_tick_pd(PiesB200Solver* s, float) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::tickPD(s, false); }); }
+int pies_b200_tick_pbd(PiesB200Solver* s, float) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::tickPBD(s, false); }); }
 int pies_b200_tick_n(PiesB200Solver* s, uint32_t n) {
   return guarded(s, [&]() {
     for (uint32_t i = 0; i < n; ++i) {
@@ -160,7 +161,15 @@ int pies_b200_clear(PiesB200Solver* s) {
 uint32_t pies_b200_vertex_count(const PiesB200Solver* s) { return s ? (uint32_t)s->scene.vertices.size() : 0; }
 uint32_t pies_b200_line_index_count(const PiesB200Solver* s) { return s ? (uint32_t)s->scene.lines.size() : 0; }
 uint32_t pies_b200_triangle_count(const PiesB200Solver* s) { return s ? s->scene.triCount() : 0; }
-const PiesB200Vertex* pies_b200_get_vertices(const PiesB200Solver* s) { return s ? s->scene.vertices.data() : nullptr; }
+const PiesB200Vertex* pies_b200_get_vertices(const PiesB200Solver* cs) {
+  if (!cs) return nullptr;
+  PiesB200Solver* s = const_cast<PiesB200Solver*>(cs);
+  // The reference refreshes its mirror at the end of every substep (Solver.cpp:157,393); here the D2H copy
+  // is deferred to the first getVertices() after a tick, which is observably the same and free for hosts
+  // that do not read every tick.
+  if (s->mirrorStale && !s->simFailed) { cudaSetDevice(s->device); if (pies::refreshVertexMirror(s) != 0) return nullptr; }
+  return s->scene.vertices.data();
+}
 const uint32_t* pies_b200_get_lines(const PiesB200Solver* s) { return s ? s->scene.lines.data() : nullptr; }
 const uint32_t* pies_b200_get_triangles(const PiesB200Solver* s) { return s ? s->scene.triangles.data() : nullptr; }
 
@@ -289,6 +298,11 @@ int pies_b200_get_velocities(PiesB200Solver* s, float* xyz) { return getVec(s, 2
 int pies_b200_set_state(PiesB200Solver* s, const float* pos, const float* prev, const float* vel) {
   return guarded(s, [&]() {
     cudaSetDevice(s->device);
+    if (s->builtVersion == s->scene.topologyVersion && s->n == s->scene.nodeCount() && !s->hostStateDirty) {
+      // device state is live: copy straight into it (DMA when the caller's buffers are pinned)
+      if (pos) s->mirrorStale = true;
+      return pies::uploadStateArrays(s, pos, prev, vel);
+    }
     int rc = pies::downloadState(s);
     if (rc) return rc;
     size_t bytes = 3ull * s->scene.nodeCount() * sizeof(float);

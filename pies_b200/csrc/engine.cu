@@ -38,6 +38,15 @@ __global__ void __launch_bounds__(kThreads) k_pack3(uint32_t n, const float4* __
   dst[3ull * i] = v.x; dst[3ull * i + 1] = v.y; dst[3ull * i + 2] = v.z;
 }
 
+// inverse of k_pack3 for the set_state path; keeps .w (invMass / radius)
+__global__ void __launch_bounds__(kThreads) k_unpack3(uint32_t n, const float* __restrict__ src, float4* __restrict__ dst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 v = dst[i];
+  v.x = src[3ull * i]; v.y = src[3ull * i + 1]; v.z = src[3ull * i + 2];
+  dst[i] = v;
+}
+
 static int gridFor(uint64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
 template <typename T, typename U>
@@ -61,6 +70,25 @@ int downloadVec3(PiesB200Solver* s, const float4* src, float* dstXYZ) {
   PIES_CHECK(s, cudaMemcpyAsync(s->hostPacked, s->packed.p, 3ull * n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
   PIES_CHECK(s, cudaStreamSynchronize(s->stream));
   std::memcpy(dstXYZ, s->hostPacked, 3ull * n * sizeof(float));
+  return PIES_B200_OK;
+}
+
+// Host arrays (pinned or pageable) -> device state, without touching the topology.
+int uploadStateArrays(PiesB200Solver* s, const float* pos, const float* prev, const float* vel) {
+  uint32_t n = s->n;
+  if (!n) return PIES_B200_OK;
+  PIES_CHECK(s, s->packed.reserve(9ull * n));
+  const float* src[3] = {pos, prev, vel};
+  float4* dst[3] = {s->q.p, s->prev.p, s->vel.p};
+  for (int k = 0; k < 3; ++k) {
+    if (!src[k]) continue;
+    float* stage = s->packed.p + 3ull * n * k;
+    PIES_CHECK(s, cudaMemcpyAsync(stage, src[k], 3ull * n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    k_unpack3<<<gridFor(n, kThreads), kThreads, 0, s->stream>>>(n, stage, dst[k]);
+    ++s->launches;
+  }
+  PIES_CHECK(s, cudaStreamSynchronize(s->stream));
+  s->deviceNewer = true;
   return PIES_B200_OK;
 }
 
@@ -187,28 +215,35 @@ int refreshVertexMirror(PiesB200Solver* s) {
   PiesB200Vertex* v = s->scene.vertices.data();
   const float* p = s->hostPacked;
   for (uint32_t i = 0; i < n; ++i) { v[i].position[0] = p[3 * i]; v[i].position[1] = p[3 * i + 1]; v[i].position[2] = p[3 * i + 2]; }
+  s->mirrorStale = false;
   return PIES_B200_OK;
 }
 
 namespace {
+// Phase timing with CUDA event pairs recorded on the solver stream and resolved after the
+// tick's final synchronisation (no extra syncs inside the tick).  Enabled by tuning.reserved.
+enum Phase { kPhOther = 0, kPhDetect, kPhLocal, kPhGlobal, kPhContact, kPhTetKernel, kPhCount };
 struct PhaseTimer {
   PiesB200Solver* s;
   bool on;
-  cudaEvent_t ev[2];
-  explicit PhaseTimer(PiesB200Solver* s_) : s(s_), on(s_->tune.reserved != 0) {
-    if (on) { cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]); }
+  std::vector<cudaEvent_t>& pool;
+  std::vector<std::pair<int, size_t>> spans;  // (phase, index of the start event)
+  size_t used = 0;
+  explicit PhaseTimer(PiesB200Solver* s_, std::vector<cudaEvent_t>& pool_) : s(s_), on(s_->tune.reserved != 0), pool(pool_) {}
+  cudaEvent_t next() {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
   }
-  ~PhaseTimer() { if (on) { cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); } }
-  void begin() { if (on) cudaEventRecord(ev[0], s->stream); }
-  void end(float& acc) {
-    if (!on) return;
-    cudaEventRecord(ev[1], s->stream);
-    cudaEventSynchronize(ev[1]);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev[0], ev[1]);
-    acc += ms;
+  void begin(int phase) { if (on) { spans.emplace_back(phase, used); cudaEventRecord(next(), s->stream); next(); } }
+  void end() { if (on) cudaEventRecord(pool[spans.back().second + 1], s->stream); }
+  void resolve(float (&acc)[kPhCount], uint32_t (&cnt)[kPhCount]) {
+    for (auto& sp : spans) {
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, pool[sp.second], pool[sp.second + 1]) == cudaSuccess) { acc[sp.first] += ms; ++cnt[sp.first]; }
+    }
   }
 };
+std::vector<cudaEvent_t> g_eventPool;
 }  // namespace
 
 int runDetection(PiesB200Solver* s, ContactLists& lists) {
@@ -244,13 +279,14 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
   s->stats.projectionsLastTick = 0;
   s->stats.pcgIterationsLastTick = 0;
   s->stats.msLocal = s->stats.msGlobal = s->stats.msDetect = s->stats.msContact = s->stats.msOther = 0.0f;
+  s->stats.msTetKernel = 0.0f; s->stats.tetKernelLaunches = 0;
   uint64_t launches0 = s->launches;
   if (!n) return PIES_B200_OK;
   cudaStream_t st = s->stream;
   const PiesB200Options& o = s->opt;
   const HostSystem& y = s->sys;
   const float h = o.fixedTimestepSize / (float)o.timeSubsteps;
-  PhaseTimer timer(s);
+  PhaseTimer timer(s, g_eventPool);
   cudaEvent_t tick0, tick1;
   cudaEventCreate(&tick0); cudaEventCreate(&tick1);
   cudaEventRecord(tick0, st);
@@ -264,19 +300,21 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
   PcgWork pw{s->pr.p, s->pp.p, s->pz.p, s->pap.p, s->pdelta.p, s->partials.p, s->scalars.p, s->flag.p, s->blockNodes.p, s->blockInv.p, y.nBlocks};
 
   for (uint32_t sub = 0; sub < o.timeSubsteps; ++sub) {
-    timer.begin();
+    timer.begin(kPhOther);
     s->launches += launchPredict(st, n, s->q.p, s->vel.p, s->msn.p, h);
-    timer.end(s->stats.msOther);
+    timer.end();
 
-    timer.begin();
+    timer.begin(kPhDetect);
     ContactLists lists;
     if ((rc = runDetection(s, lists))) { cudaEventDestroy(tick0); cudaEventDestroy(tick1); return rc; }
-    timer.end(s->stats.msDetect);
+    timer.end();
     float4* contribC = s->contact ? s->contact->contribC.p : nullptr;
 
     for (uint32_t it = 0; it < o.iterations; ++it) {
-      timer.begin();
+      timer.begin(kPhTetKernel);
       s->launches += launchTetElems(st, te, s->q.p, s->contrib.p + y.baseTet);
+      timer.end();
+      timer.begin(kPhLocal);
       s->launches += launchDistance(st, de, s->q.p, s->contrib.p + y.baseDist);
       s->launches += launchBend(st, be, s->q.p, s->contrib.p + y.baseBend);
       s->launches += launchShape(st, sh, s->shapeMat.p, s->shapeQinv.p, s->shapeQuat.p, s->shapeW.p, s->q.p, s->contrib.p + y.baseShape);
@@ -284,9 +322,9 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
       s->launches += launchContactProject(st, lists, s->q.p, o.collisionThickness, contribC, s->snap.p);
       s->launches += launchGatherRhs(st, n, s->msn.p, s->incPtr.p, s->inc.p, s->contrib.p, s->rhs.p);
       s->launches += launchGatherContacts(st, n, lists, contribC, s->snap.p, s->rhs.p);
-      timer.end(s->stats.msLocal);
+      timer.end();
 
-      timer.begin();
+      timer.begin(kPhGlobal);
       s->launches += launchPcgInit(st, A, lists, pw, s->rhs.p, s->q.p, s->tune.pcgTolerance);
       uint32_t done = 0, burst = std::max(1u, s->lastPcgIters);
       bool converged = false;
@@ -303,21 +341,21 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
       uint32_t used = (uint32_t)s->hostFlag[1];
       s->lastPcgIters = std::max(1u, used);
       s->stats.pcgIterationsLastTick += used;
-      timer.end(s->stats.msGlobal);
+      timer.end();
       s->stats.projectionsLastTick += y.staticProjections + lists.nTri + lists.nFloor;
     }
 
-    timer.begin();
+    timer.begin(kPhContact);
     if (s->contact)
       s->launches += launchStabilize(st, *s->contact, lists, s->q.p, s->prev.p, s->snap.p, o.collisionThickness,
                                      o.collisionStabilizationIterations);
-    timer.end(s->stats.msContact);
-    timer.begin();
+    timer.end();
+    timer.begin(kPhOther);
     s->launches += launchVelocityUpdate(st, n, s->q.p, s->prev.p, s->vel.p, h, o.damping, o.gravity);
-    timer.end(s->stats.msOther);
-    timer.begin();
+    timer.end();
+    timer.begin(kPhContact);
     if (s->contact) s->launches += launchFriction(st, *s->contact, lists, n, s->q.p, s->vel.p, o.friction, o.staticFrictionThreshold);
-    timer.end(s->stats.msContact);
+    timer.end();
     s->stats.collisionProjections = lists.nTri + lists.nFloor;
     ++s->stats.substepsLastTick;
   }
@@ -326,12 +364,21 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
   PIES_CHECK(s, cudaEventSynchronize(tick1));
   cudaEventElapsedTime(&s->stats.msTick, tick0, tick1);
   cudaEventDestroy(tick0); cudaEventDestroy(tick1);
+  {
+    float acc[kPhCount] = {0, 0, 0, 0, 0, 0};
+    uint32_t cnt[kPhCount] = {0, 0, 0, 0, 0, 0};
+    timer.resolve(acc, cnt);
+    s->stats.msOther = acc[kPhOther]; s->stats.msDetect = acc[kPhDetect]; s->stats.msLocal = acc[kPhLocal] + acc[kPhTetKernel];
+    s->stats.msGlobal = acc[kPhGlobal]; s->stats.msContact = acc[kPhContact];
+    s->stats.msTetKernel = acc[kPhTetKernel]; s->stats.tetKernelLaunches = cnt[kPhTetKernel];
+  }
   PIES_CHECK(s, cudaGetLastError());
   {
     float rel = 0.0f;
     cudaMemcpy(&rel, s->scalars.p, sizeof(float), cudaMemcpyDeviceToHost);
     s->stats.pcgLastRelResidual = rel;
   }
+  s->mirrorStale = true;
   if (refreshMirror && (rc = refreshVertexMirror(s))) return rc;
   s->stats.kernelLaunchesLastTick = s->launches - launches0;
   s->stats.simFailed = s->simFailed ? 1u : 0u;

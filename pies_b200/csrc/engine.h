@@ -57,6 +57,7 @@ struct PiesB200Solver {
   // ---- device state ----
   uint64_t builtVersion = ~0ull;
   bool deviceNewer = false;   // device q/prev/vel are ahead of scene.pos/prev/vel
+  bool mirrorStale = false;     // scene.vertices[].position is behind the device; refreshed lazily by get_vertices
   bool hostStateDirty = false; // scene.pos/prev/vel were overwritten (set_state) and must be re-uploaded
   uint32_t n = 0;
   pies::HostSystem sys;
@@ -99,6 +100,7 @@ int downloadState(PiesB200Solver* s);  // device -> scene.pos/prev/vel
 int tickPD(PiesB200Solver* s, bool refreshMirror);
 int tickPBD(PiesB200Solver* s, bool refreshMirror);
 int refreshVertexMirror(PiesB200Solver* s);
+int uploadStateArrays(PiesB200Solver* s, const float* pos, const float* prev, const float* vel);
 int runDetection(PiesB200Solver* s, ContactLists& lists);
 }  // namespace pies
 

@@ -46,7 +46,8 @@ class Stats(C.Structure):
         ("substepsLastTick", C.c_uint32), ("simFailed", C.c_uint32),
         ("msTick", C.c_float), ("msLocal", C.c_float), ("msGlobal", C.c_float),
         ("msDetect", C.c_float), ("msContact", C.c_float), ("msOther", C.c_float),
-        ("pcgLastRelResidual", C.c_float), ("reserved", C.c_float),
+        ("pcgLastRelResidual", C.c_float), ("msTetKernel", C.c_float),
+        ("tetKernelLaunches", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 

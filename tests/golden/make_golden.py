@@ -1,0 +1,226 @@
+"""Generates the golden fixtures under tests/golden/ from the UNMODIFIED reference (oracle/_ref).
+
+Run where /root/reference exists:   make -C oracle ref && python tests/golden/make_golden.py
+The fixtures travel with the repo, so the parity tests do not need /root/reference (nor oracle/_ref)
+at run time.  Every array comes out of the reference's own functions (through oracle/ref_driver.cpp).
+"""
+import contextlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle.refapi import RefSolver, lib  # noqa: E402
+from pies_b200 import scenes  # noqa: E402
+
+
+@contextlib.contextmanager
+def quiet():  # TetGen prints its statistics to stdout
+    sys.stdout.flush()
+    fd = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        yield
+    finally:
+        os.dup2(fd, 1)
+        os.close(devnull)
+        os.close(fd)
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("%-28s %7.1f KiB" % (name + ".npz", os.path.getsize(path) / 1024.0))
+
+
+def projections():
+    rng = np.random.default_rng(7)
+    n = 768
+    rest = rng.normal(size=(n, 4, 3)).astype(np.float32)
+    # keep the rest tets well conditioned (like mesh elements): reject slivers
+    vol = np.abs(np.linalg.det(rest[:, 1:] - rest[:, :1]))
+    rest[vol < 0.3] = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+    qinv = np.empty((n, 9), np.float32)
+    lib().pref_probe_qinv(n, np.ascontiguousarray(rest.reshape(n, 12)), qinv)
+    defo = (rest + 0.25 * rng.normal(size=rest.shape)).astype(np.float32)
+    defo[:64] = rest[:64]                                   # rest state
+    defo[64:128] = rest[64:128] * 1.3                      # uniform stretch (repeated sigma)
+    # inverted, with distinct singular values (a pure reflection has sigma1=sigma2=sigma3 and det<0, where the
+    # axis the reference un-inverts is an artefact of Eigen's sweep order — SURVEY App. A)
+    defo[128:192] = rest[128:192] * np.array([1.1, -0.9, 0.7], np.float32)
+    defo[192:256, 3] = defo[192:256, 0] + 0.3 * (defo[192:256, 1] - defo[192:256, 0]) + 0.4 * (defo[192:256, 2] - defo[192:256, 0])  # flat
+    defo[256:320] = rest[256:320] * 0.5                    # compressed
+    strain = np.empty((n, 12), np.float32)
+    volume = np.empty((n, 12), np.float32)
+    lib().pref_probe_tet(n, np.ascontiguousarray(defo.reshape(n, 12)), qinv, 0.8, 1.0, strain)
+    lib().pref_probe_volume(n, np.ascontiguousarray(defo.reshape(n, 12)), qinv, 1.0, 1.0, volume)
+    volume2 = np.empty((n, 12), np.float32)
+    lib().pref_probe_volume(n, np.ascontiguousarray(defo.reshape(n, 12)), qinv, 0.9, 1.1, volume2)
+    save("projections", pos=defo.reshape(n, 12), qinv=qinv, strain=strain, volume=volume, volume_09_11=volume2,
+         flat=np.arange(192, 256))
+
+
+def ccd_and_ranges():
+    rng = np.random.default_rng(11)
+    m = 6000
+    q = rng.normal(scale=0.5, size=(m, 18)).astype(np.float32)
+    q[:, 9:] = q[:, :9] + 0.12 * rng.normal(size=(m, 9)).astype(np.float32)
+    q[:500, 9:] = q[:500, :9]                              # static configurations
+    q[500:520, :] = 0.0                                    # fully degenerate
+    hit = np.empty(m, np.int32); t = np.empty(m, np.float32)
+    lib().pref_probe_ccd(m, q, 0.1, hit, t)
+    n = 3000
+    base = rng.uniform(-40, 40, size=(n, 1, 3))
+    tri = base + rng.normal(scale=1.0, size=(n, 3, 3))
+    tri[16:24] = base[16:24] + rng.normal(scale=60.0, size=(8, 3, 3))   # longer than the 50-cell cap
+    swept = tri + rng.normal(scale=0.3, size=tri.shape)
+    tri[:16, :, 0] = np.round(base[:16, :, 0]); swept[:16, :, 0] = tri[:16, :, 0]  # in an integer plane (F6): length 0
+    p = np.ascontiguousarray(tri.reshape(n, 9).astype(np.float32))
+    o = np.ascontiguousarray(swept.reshape(n, 9).astype(np.float32))
+    tm = np.empty((n, 3), np.int64); tl = np.empty((n, 3), np.uint32)
+    lib().pref_probe_tri_range(n, p, o, tm, tl)
+    pn = rng.uniform(-40, 40, size=(n, 3)).astype(np.float32)
+    rad = rng.uniform(0.05, 1.0, n).astype(np.float32)
+    rad[:8] = 200.0                                        # over the 50-cell cap
+    nm = np.empty((n, 3), np.int64); nl = np.empty((n, 3), np.uint32)
+    lib().pref_probe_node_range(n, pn, rad, 2.0, nm, nl)
+    save("ccd", queries=q, hit=hit, t=t)
+    save("ranges", tri_pos=p, tri_prev=o, tri_min=tm, tri_len=tl, node_pos=pn, node_radius=rad, node_min=nm, node_len=nl)
+
+
+FACTORIES = {
+    "tetbox": lambda s: s.createTetBox((0.25, 3.0, -1.5), 1.0, (0.5, 0.0, -0.25), 1000.0, 2.0, False),
+    "tetbox_hinged": lambda s: s.createTetBox((0.0, 1.0, 0.0), 0.5, (0, 0, 0), 500.0, 1.0, True),
+    "box": lambda s: s.createBox((1.0, 2.0, 3.0), 0.5, 100.0),
+    "sheet": lambda s: s.createSheet((0.0, 5.0, 0.0), 0.25, 0.5, 200.0),
+    "bendsheet": lambda s: s.createBendSheet((0.0, 4.0, 0.0), 0.5, 50.0),
+    "shapebox": lambda s: s.createShapeMatchingBox((0.0, 2.0, 0.0), 3, 4, 5, 1.0, (0, 0, 0), 800.0),
+    "shapesheet": lambda s: s.createShapeMatchingSheet((0.0, 6.0, 0.0), 0.2, (0, 0, 0), 300.0),
+}
+
+
+def factories():
+    """Topology + rest data every factory produces, then a short trajectory (PD, default options)."""
+    out = {}
+    for name, fn in FACTORIES.items():
+        r = RefSolver()
+        fn(r)
+        rad, im = r.nodeScalars()
+        out[name + "_pos"] = r.positions; out[name + "_vel"] = r.velocities
+        out[name + "_radius"] = rad; out[name + "_invmass"] = im
+        out[name + "_tris"] = r.getTriangles(); out[name + "_lines"] = r.getLines()
+        out[name + "_counts"] = np.array([r.count(k) for k in ("position", "distance", "tet", "volume", "bend", "shape", "goal")])
+        traj = []
+        for _ in range(10):
+            r.tick()
+            traj.append(r.positions)
+        out[name + "_traj"] = np.stack(traj)
+        out[name + "_vel10"] = r.velocities
+    save("factories", **out)
+
+
+def two_box(s):
+    s.createTetBox((0.1, 0.3, 0.1), 1.0, (0, 0, 0), 1000.0, 1.0, False)
+    s.createTetBox((0.4, 2.6, 0.3), 1.0, (0, -5, 0), 1000.0, 1.0, False)
+
+
+def collisions():
+    """SURVEY Appendix B scene: states fed to detection + the lists/occupancy the reference finds."""
+    r = RefSolver(iterations=10)
+    two_box(r)
+    out = {}
+    counts = []
+    for t in range(40):
+        # state entering tick t: detection inside the tick sees pos + h*v against prev
+        if t in (3, 10, 14, 30):
+            pos, prev, vel = r.positions, r.prevPositions, r.velocities
+        r.tick()
+        counts.append((r.count("tri_collision"), r.count("static_collision")))
+        if t in (3, 10, 14, 30):
+            # reproduce the detection input: positions after the inertia step (Solver.cpp:229-238)
+            h = np.float32(0.012)
+            out["t%d_pos" % t] = (pos + h * vel).astype(np.float32)
+            out["t%d_prev" % t] = prev
+            out["t%d_tri" % t] = r.triCollisions()
+            out["t%d_floor" % t] = r.staticCollisions()
+        if t in (0, 9, 39):
+            out["traj%d_pos" % (t + 1)] = r.positions
+            out["traj%d_vel" % (t + 1)] = r.velocities
+    out["counts"] = np.asarray(counts)
+    # occupancy of the triangle hash for the final state
+    r2 = RefSolver(iterations=10)
+    two_box(r2)
+    r2.tick(12)
+    cells, cnts, members = r2.triOccupancy()
+    out["occ_pos"] = r2.positions; out["occ_prev"] = r2.prevPositions
+    out["occ_cells"] = cells; out["occ_counts"] = cnts; out["occ_members"] = members
+    save("collisions", **out)
+
+
+def tetgen_cube():
+    """S1 at reduced size (config 1): TetGen cube falling on the floor, PD, strain + volume."""
+    with quiet():
+        r = RefSolver()
+        pts, tets, faces = scenes.add_tetgen_cube(r, n=6, origin=(0.0, 0.4, 0.0))
+    out = dict(points=pts, tets=tets, faces=faces)
+    traj = {}
+    for t in range(1, 61):
+        r.tick()
+        if t in (1, 10, 30, 60):
+            traj["pos%d" % t] = r.positions; traj["vel%d" % t] = r.velocities
+            traj["ncoll%d" % t] = np.array([r.count("tri_collision"), r.count("static_collision")])
+    out.update(traj)
+    save("tetgen_cube", **out)
+
+
+def stack():
+    """Reduced S3 (config 3 at 2x2 columns x 4 layers = 16 bodies), iterations=10: positions at K = 1, 10, 100."""
+    r = RefSolver(**scenes.S3_OPTIONS)
+    scenes.build_s3(r, bodies=16, nx=2, nz=2)
+    out = {}
+    for t in range(1, 101):
+        r.tick()
+        if t in (1, 10, 50, 100):
+            out["pos%d" % t] = r.positions; out["vel%d" % t] = r.velocities
+            out["ncoll%d" % t] = np.array([r.count("tri_collision"), r.count("static_collision")])
+    save("stack16", **out)
+
+
+def clusters():
+    """Shape matching + goal matching (config 4 ingredients): regions driven by a scripted transform."""
+    r = RefSolver(iterations=6)
+    for k in range(3):
+        r.createShapeMatchingBox((3.0 * k, 1.0 + 0.1 * k, 0.0), 3, 3, 3, 1.0, (0, 0, 0), 1000.0)
+    region = np.eye(4, dtype=np.float32)
+    region[3, :3] = (0.5, 1.5, 0.5)          # column-major: translation in the 4th column
+    r.addFixedRegions(region.reshape(1, 16), 1000.0)
+    lr = np.eye(4, dtype=np.float32)
+    lr[3, :3] = (3.5, 1.6, 0.5)
+    r.addLinkedRegions(lr.reshape(1, 16), 500.0)
+    out = {"goal_ids": r.goal(0)[0], "shape_count": np.array([r.count("shape")])}
+    xforms = []
+    for t in range(1, 21):
+        m = region.copy()
+        m[3, :3] += (0.02 * t, 0.01 * t, 0.0)
+        xforms.append(m.reshape(16))
+        r.updateFixedRegions(m.reshape(1, 16))
+        r.tick()
+        if t in (1, 10, 20):
+            out["pos%d" % t] = r.positions; out["vel%d" % t] = r.velocities
+    out["xforms"] = np.stack(xforms)
+    out["region"] = region.reshape(16); out["linked"] = lr.reshape(16)
+    save("clusters", **out)
+
+
+if __name__ == "__main__":
+    lib().pref_srand(1)
+    projections()
+    ccd_and_ranges()
+    factories()
+    collisions()
+    tetgen_cube()
+    stack()
+    clusters()
