@@ -358,7 +358,7 @@ int pies_b200_get_tri_occupancy(PiesB200Solver* s, int64_t* cells, uint32_t* cou
     std::vector<uint64_t> keys(P);
     std::vector<uint32_t> mem(P), start(w.nCells + 1);
     PIES_CHECK(s, cudaMemcpy(keys.data(), w.keys.p, P * 8, cudaMemcpyDeviceToHost));
-    PIES_CHECK(s, cudaMemcpy(mem.data(), w.memberTri.p, P * 4, cudaMemcpyDeviceToHost));
+    PIES_CHECK(s, cudaMemcpy(mem.data(), w.vals.p, P * 4, cudaMemcpyDeviceToHost));
     PIES_CHECK(s, cudaMemcpy(start.data(), w.cellStart.p, (w.nCells + 1ull) * 4, cudaMemcpyDeviceToHost));
     int by = w.keyPack[3], bz = w.keyPack[4];
     for (uint32_t c = 0; c < w.nCells; ++c) {

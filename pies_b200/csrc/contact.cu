@@ -5,15 +5,8 @@
 // Src/Solver.cpp:298-308,337-349 (local step / RHS), :367-383 (stabilisation), :431-484 (friction).
 //
 // Stabilisation and friction are sequential Gauss-Seidel sweeps over the collision list in the
-// reference, and the result depends on that order.  They are executed here in
-// exactly that order, in parallel where the order allows it:
-//   * the contact graph (nodes linked by collision entries) is split into connected components
-//     with a min-id union-find; components never interact, so each is swept by one CTA;
-//   * inside a component the CTA walks the entries in list order, a window at a time; in every
-//     round the entries whose four nodes are not claimed by an earlier pending entry run
-//     together (claims are taken with shared-memory atomicMin on the entry's position, so the
-//     earliest pending entry touching a node always wins).  This is the sequential dependency
-//     order, so results differ from the reference only by rounding.
+// reference, and the result depends on that order.  They run here as dataflow sweeps
+// that honour exactly that order per node (k_gs_dataflow below).
 #include "contact.h"
 
 #include "common.cuh"
@@ -96,93 +89,25 @@ int launchGatherContacts(cudaStream_t s, uint32_t n, const ContactLists& c, cons
   return 1;
 }
 
-// ---- contact-graph components (min-id union-find) --------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_uf_init(uint32_t n, uint32_t* __restrict__ parent) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) parent[i] = i;
-}
-
-__device__ __forceinline__ uint32_t ufFind(uint32_t* parent, uint32_t x) {
-  uint32_t p = *(volatile uint32_t*)(parent + x);
-  while (p != x) { x = p; p = *(volatile uint32_t*)(parent + x); }
-  return x;
-}
-
-__device__ __forceinline__ void ufUnite(uint32_t* parent, uint32_t u, uint32_t v) {
-  while (true) {
-    u = ufFind(parent, u);
-    v = ufFind(parent, v);
-    if (u == v) return;
-    if (u < v) { uint32_t t = u; u = v; v = t; }  // hook the larger root under the smaller one
-    uint32_t old = atomicMin(parent + u, v);
-    if (old == u) return;
-    u = old;  // someone else re-parented u meanwhile: merge what it points to with v
-  }
-}
-
-__global__ void __launch_bounds__(kThreads) k_uf_unite(uint32_t nTri, const uint4* __restrict__ entries,
-                                                       uint32_t* __restrict__ parent) {
-  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nTri) return;
-  uint4 id = entries[e];
-  ufUnite(parent, id.x, id.y);
-  ufUnite(parent, id.x, id.z);
-  ufUnite(parent, id.x, id.w);
-}
-
-__global__ void __launch_bounds__(kThreads) k_uf_keys(uint32_t nTri, const uint4* __restrict__ entries,
-                                                      uint32_t* __restrict__ parent, uint64_t* __restrict__ keys,
-                                                      uint32_t* __restrict__ vals) {
-  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nTri) return;
-  keys[e] = ufFind(parent, entries[e].x);  // min node id of the component: deterministic
-  vals[e] = e;
-}
-
-__global__ void __launch_bounds__(kThreads) k_comp_heads(uint32_t nTri, const uint64_t* __restrict__ keys,
-                                                         uint32_t* __restrict__ heads) {
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j > nTri) return;
-  heads[j] = (j < nTri && (j == 0 || keys[j] != keys[j - 1])) ? 1u : 0u;
-}
-
-__global__ void __launch_bounds__(kThreads) k_comp_starts(uint32_t nTri, const uint64_t* __restrict__ keys,
-                                                          const uint32_t* __restrict__ headScan,
-                                                          uint32_t* __restrict__ compStart, uint32_t* __restrict__ nComp) {
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nTri) return;
-  bool head = (j == 0 || keys[j] != keys[j - 1]);
-  uint32_t idx = headScan[j] + (head ? 1u : 0u) - 1u;
-  if (head) compStart[idx] = j;
-  if (j == nTri - 1) { compStart[idx + 1] = nTri; *nComp = idx + 1; }
-}
-
-int buildContactComponents(ContactWork& w, cudaStream_t s, uint32_t nNodes, const ContactLists& c) {
-  int L = 0;
-  w.nTri = c.nTri;
-  if (!c.nTri) return 0;
-  if (w.parent.reserve(nNodes + 1) != cudaSuccess || w.keys.reserve(c.nTri) != cudaSuccess ||
-      w.tmpKeys.reserve(c.nTri) != cudaSuccess || w.perm.reserve(c.nTri) != cudaSuccess ||
-      w.tmpVals.reserve(c.nTri) != cudaSuccess || w.heads.reserve(c.nTri + 2) != cudaSuccess ||
-      w.compStart.reserve(c.nTri + 2) != cudaSuccess || w.nComp.reserve(4) != cudaSuccess ||
-      w.sortHist.reserve(sortHistBytes(c.nTri) / 4 + 4) != cudaSuccess ||
-      w.scanScratch.reserve(scanScratchElems(c.nTri + 2)) != cudaSuccess)
-    return -1;
-  k_uf_init<<<gridFor(nNodes, kThreads), kThreads, 0, s>>>(nNodes, w.parent.p); ++L;
-  k_uf_unite<<<gridFor(c.nTri, kThreads), kThreads, 0, s>>>(c.nTri, c.tri, w.parent.p); ++L;
-  k_uf_keys<<<gridFor(c.nTri, kThreads), kThreads, 0, s>>>(c.nTri, c.tri, w.parent.p, w.keys.p, w.perm.p); ++L;
-  int bits = 1;
-  while ((1ull << bits) < (uint64_t)nNodes) ++bits;
-  L += launchSortPairs(s, c.nTri, w.keys.p, w.perm.p, w.tmpKeys.p, w.tmpVals.p, w.sortHist.p, bits);
-  k_comp_heads<<<gridFor(c.nTri + 1, kThreads), kThreads, 0, s>>>(c.nTri, w.keys.p, w.heads.p); ++L;
-  L += launchExclusiveScan(s, w.heads.p, c.nTri + 1, w.scanScratch.p);
-  k_comp_starts<<<gridFor(c.nTri, kThreads), kThreads, 0, s>>>(c.nTri, w.keys.p, w.heads.p, w.compStart.p, w.nComp.p); ++L;
-  return L;
-}
-
-// ---- ordered Gauss-Seidel executor --------------------------------------------------------------------
+// ---- ordered Gauss-Seidel executor (dataflow) ---------------------------------------------------------
+// The reference sweeps the collision list sequentially; entry e reads and writes its four nodes, so the
+// only constraint a parallel schedule has to respect is, per node, the list order of the entries that
+// touch it.  Detection gives every (entry, node) its ticket = number of earlier entries touching that
+// node.  Warps take chunks of 32 consecutive entries from a global counter (so every chunk below the
+// newest one is owned by a running warp); an entry executes as soon as nodeDone[v] == ticket for its
+// four nodes, then publishes nodeDone[v] = ticket + 1.  The earliest unfinished entry is always
+// runnable, so the sweep cannot stall, and the result equals the sequential sweep up to rounding of
+// the identical operations (same operand values, same order per node).
 constexpr int kGsThreads = 256;
-constexpr int kGsTable = 2048;
+
+__device__ __forceinline__ uint32_t ldAcquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stRelease(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 struct StabilizeOp {
   float4* q;
@@ -199,10 +124,11 @@ struct StabilizeOp {
     float wTri = b4.w + c4.w + d4.w;
     float wSum = a4.w + wTri;
     V3 da = disp * a4.w / wSum, dt = disp * wTri / wSum;
-    q[id.x] = f4(A + da, a4.w); q[id.y] = f4(B - dt, b4.w); q[id.z] = f4(C - dt, c4.w); q[id.w] = f4(D - dt, d4.w);
     float4 pa = __ldcg(prev + id.x), pb = __ldcg(prev + id.y), pc = __ldcg(prev + id.z), pd = __ldcg(prev + id.w);
-    prev[id.x] = f4(v3(pa) + da, pa.w); prev[id.y] = f4(v3(pb) - dt, pb.w);
-    prev[id.z] = f4(v3(pc) - dt, pc.w); prev[id.w] = f4(v3(pd) - dt, pd.w);
+    __stcg(q + id.x, f4(A + da, a4.w)); __stcg(q + id.y, f4(B - dt, b4.w));
+    __stcg(q + id.z, f4(C - dt, c4.w)); __stcg(q + id.w, f4(D - dt, d4.w));
+    __stcg(prev + id.x, f4(v3(pa) + da, pa.w)); __stcg(prev + id.y, f4(v3(pb) - dt, pb.w));
+    __stcg(prev + id.z, f4(v3(pc) - dt, pc.w)); __stcg(prev + id.w, f4(v3(pd) - dt, pd.w));
   }
 };
 
@@ -210,7 +136,7 @@ struct FrictionOp {
   const float4* q;
   float4* vel;
   float friction, staticThreshold;
-  // point-triangle friction / restitution (Solver.cpp:431-471)
+  // point-triangle friction / restitution (Solver.cpp:431-471); positions are not modified by this pass
   __device__ __forceinline__ void operator()(uint4 id) const {
     float4 a4 = q[id.x], b4 = q[id.y], c4 = q[id.z], d4 = q[id.w];
     V3 va = v3(__ldcg(vel + id.x)), vb = v3(__ldcg(vel + id.y)), vc = v3(__ldcg(vel + id.z)), vd = v3(__ldcg(vel + id.w));
@@ -225,38 +151,38 @@ struct FrictionOp {
     float wSum = a4.w + triW;
     V3 dv = (-fr) * perp - (1.1f * fminf(vDotN, 0.0f)) * nrm;
     V3 dtv = (-dv) * triW / wSum;
-    vel[id.x] = f4(va + dv * a4.w / wSum, 0.0f);
-    vel[id.y] = f4(vb + dtv, 0.0f); vel[id.z] = f4(vc + dtv, 0.0f); vel[id.w] = f4(vd + dtv, 0.0f);
+    __stcg(vel + id.x, f4(va + dv * a4.w / wSum, 0.0f));
+    __stcg(vel + id.y, f4(vb + dtv, 0.0f)); __stcg(vel + id.z, f4(vc + dtv, 0.0f)); __stcg(vel + id.w, f4(vd + dtv, 0.0f));
   }
 };
 
 template <typename Op>
-__global__ void __launch_bounds__(kGsThreads) k_gs_ordered(const uint4* __restrict__ entries,
-                                                           const uint32_t* __restrict__ perm,
-                                                           const uint32_t* __restrict__ compStart,
-                                                           const uint32_t* __restrict__ nCompPtr, Op op) {
-  __shared__ int owner[kGsTable];
-  for (int i = threadIdx.x; i < kGsTable; i += kGsThreads) owner[i] = 0x7fffffff;
-  __syncthreads();
-  const uint32_t nComp = *nCompPtr;
-  for (uint32_t comp = blockIdx.x; comp < nComp; comp += gridDim.x) {
-    uint32_t s = compStart[comp], e = compStart[comp + 1];
-    for (uint32_t base = s; base < e; base += kGsThreads) {
-      uint32_t idx = base + threadIdx.x;
-      bool pending = idx < e;
-      uint4 id = make_uint4(0, 0, 0, 0);
-      if (pending) id = entries[perm[idx]];
-      uint32_t h0 = (id.x * 2654435761u) >> 21, h1 = (id.y * 2654435761u) >> 21, h2 = (id.z * 2654435761u) >> 21,
-               h3 = (id.w * 2654435761u) >> 21;  // 11 bits -> kGsTable
-      while (__syncthreads_or(pending)) {
-        int me = (int)threadIdx.x;
-        if (pending) { atomicMin(&owner[h0], me); atomicMin(&owner[h1], me); atomicMin(&owner[h2], me); atomicMin(&owner[h3], me); }
-        __syncthreads();
-        bool ready = pending && owner[h0] == me && owner[h1] == me && owner[h2] == me && owner[h3] == me;
-        __syncthreads();
-        if (pending) { owner[h0] = 0x7fffffff; owner[h1] = 0x7fffffff; owner[h2] = 0x7fffffff; owner[h3] = 0x7fffffff; }
-        if (ready) { op(id); pending = false; }
-        __threadfence_block();
+__global__ void __launch_bounds__(kGsThreads) k_gs_dataflow(const uint4* __restrict__ entries,
+                                                            const uint4* __restrict__ ticket, uint32_t nTri,
+                                                            uint32_t* __restrict__ nodeDone,
+                                                            uint32_t* __restrict__ chunkCounter, Op op) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nChunks = (nTri + 31u) >> 5;
+  while (true) {
+    uint32_t chunk = 0;
+    if (lane == 0) chunk = atomicAdd(chunkCounter, 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (chunk >= nChunks) break;
+    uint32_t e = (chunk << 5) + (uint32_t)lane;
+    bool pending = e < nTri;
+    uint4 id = make_uint4(0, 0, 0, 0), tk = make_uint4(0, 0, 0, 0);
+    if (pending) { id = entries[e]; tk = ticket[e]; }
+    while (__any_sync(0xffffffffu, pending)) {
+      if (pending) {
+        bool ready = ldAcquire(nodeDone + id.x) == tk.x && ldAcquire(nodeDone + id.y) == tk.y &&
+                     ldAcquire(nodeDone + id.z) == tk.z && ldAcquire(nodeDone + id.w) == tk.w;
+        if (ready) {
+          op(id);
+          __threadfence();
+          stRelease(nodeDone + id.x, tk.x + 1u); stRelease(nodeDone + id.y, tk.y + 1u);
+          stRelease(nodeDone + id.z, tk.z + 1u); stRelease(nodeDone + id.w, tk.w + 1u);
+          pending = false;
+        }
       }
     }
   }
@@ -289,30 +215,45 @@ __global__ void __launch_bounds__(kThreads) k_floor_friction(uint32_t n, const u
   vel[i] = v;
 }
 
-static int gsGrid(uint32_t nTri) { return (int)std::min<uint32_t>(kNumSMs * 8, (nTri + kGsThreads - 1) / kGsThreads * 4 + 1); }
+constexpr int kSweepCounters = 64;
 
-int launchStabilize(cudaStream_t s, const ContactWork& w, const ContactLists& c, float4* q, float4* prev, const float4* snap,
-                    float thickness, uint32_t iterations) {
+int prepareContactSweeps(ContactWork& w, cudaStream_t s, const ContactLists& c) {
+  w.nTri = c.nTri;
+  w.sweepsUsed = 0;
+  if (!c.nTri) return 0;
+  if (w.sweepCounters.reserve(kSweepCounters) != cudaSuccess) return -1;
+  if (cudaMemsetAsync(w.sweepCounters.p, 0, kSweepCounters * sizeof(uint32_t), s) != cudaSuccess) return -1;
+  return 0;
+}
+
+template <typename Op>
+static int launchSweep(cudaStream_t s, ContactWork& w, const ContactLists& c, uint32_t n, Op op) {
+  if (w.sweepsUsed == kSweepCounters) {  // more sweeps than counters in one substep: recycle
+    cudaMemsetAsync(w.sweepCounters.p, 0, kSweepCounters * sizeof(uint32_t), s);
+    w.sweepsUsed = 0;
+  }
+  cudaMemsetAsync(c.nodeDone, 0, (size_t)n * sizeof(uint32_t), s);
+  uint32_t chunks = (c.nTri + 31u) / 32u;
+  int grid = (int)std::min<uint32_t>(kNumSMs * 8, (chunks + kGsThreads / 32 - 1) / (kGsThreads / 32));
+  k_gs_dataflow<Op><<<grid, kGsThreads, 0, s>>>(c.tri, c.ticket, c.nTri, c.nodeDone, w.sweepCounters.p + w.sweepsUsed, op);
+  ++w.sweepsUsed;
+  return 1;
+}
+
+int launchStabilize(cudaStream_t s, ContactWork& w, const ContactLists& c, uint32_t n, float4* q, float4* prev,
+                    const float4* snap, float thickness, uint32_t iterations) {
   int L = 0;
   for (uint32_t it = 0; it < iterations; ++it) {
-    if (c.nTri) {
-      k_gs_ordered<StabilizeOp><<<gsGrid(c.nTri), kGsThreads, 0, s>>>(c.tri, w.perm.p, w.compStart.p, w.nComp.p,
-                                                                     StabilizeOp{q, prev, thickness});
-      ++L;
-    }
+    if (c.nTri) L += launchSweep(s, w, c, n, StabilizeOp{q, prev, thickness});
     if (c.nFloor) { k_floor_snap<<<gridFor(c.nFloor, kThreads), kThreads, 0, s>>>(c.nFloor, c.floorNode, snap, q); ++L; }
   }
   return L;
 }
 
-int launchFriction(cudaStream_t s, const ContactWork& w, const ContactLists& c, uint32_t n, const float4* q, float4* vel,
+int launchFriction(cudaStream_t s, ContactWork& w, const ContactLists& c, uint32_t n, const float4* q, float4* vel,
                    float friction, float staticThreshold) {
   int L = 0;
-  if (c.nTri) {
-    k_gs_ordered<FrictionOp><<<gsGrid(c.nTri), kGsThreads, 0, s>>>(c.tri, w.perm.p, w.compStart.p, w.nComp.p,
-                                                                  FrictionOp{q, vel, friction, staticThreshold});
-    ++L;
-  }
+  if (c.nTri) L += launchSweep(s, w, c, n, FrictionOp{q, vel, friction, staticThreshold});
   if (c.nFloor) { k_floor_friction<<<gridFor(n, kThreads), kThreads, 0, s>>>(n, c.floorMult, vel, friction, staticThreshold); ++L; }
   return L;
 }

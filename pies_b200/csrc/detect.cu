@@ -22,50 +22,93 @@ namespace pies {
 static inline int gridFor(uint64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
 // ---- 1. ranges -----------------------------------------------------------------------------
-// bbox[0..2] = min cell, bbox[3..5] = max cell (inclusive), bbox[6] = bad-input flag
-__global__ void __launch_bounds__(kThreads) k_tri_ranges(uint32_t nTri, const uint32_t* __restrict__ tri,
+// bbox[0..2] = min cell, bbox[3..5] = max cell (inclusive), bbox[6] = bad-input flag, bbox[7] = hang-guard flag
+__device__ __forceinline__ uint32_t canonicalRank(uint32_t t, uint32_t nTri, uint32_t T) {
+  // thread (t % T) handles t, t+T, ...; per-thread lists are concatenated in thread order (Solver.cpp:714,852-873)
+  uint32_t th = t % T, k = t / T;
+  uint32_t full = nTri / T, rem = nTri % T;  // threads < rem own full+1 triangles
+  return th * full + (th < rem ? th : rem) + k;
+}
+
+__global__ void __launch_bounds__(kThreads) k_tri_ranges(uint32_t nTri, uint32_t threadCount, float floorLimit,
+                                                         const uint32_t* __restrict__ tri,
                                                          const float4* __restrict__ q, const float4* __restrict__ prev,
-                                                         int4* __restrict__ triMin, uint32_t* __restrict__ triLen,
-                                                         uint32_t* __restrict__ cnt, float4* __restrict__ aabbLo,
+                                                         int4* __restrict__ triMin, uint4* __restrict__ triRec,
+                                                         uint32_t* __restrict__ cnt, uint32_t* __restrict__ cntRank,
+                                                         uint32_t* __restrict__ floorRank, float4* __restrict__ aabbLo,
                                                          float4* __restrict__ aabbHi, int* __restrict__ bbox) {
+  __shared__ int sb[8];
+  if (threadIdx.x < 3) sb[threadIdx.x] = 0x7fffffff;
+  else if (threadIdx.x < 6) sb[threadIdx.x] = (int)0x80000000;
+  else if (threadIdx.x < 8) sb[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nTri) {
+    uint32_t a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
+    V3 p0 = v3(q[a]), p1 = v3(q[b]), p2 = v3(q[c]);
+    V3 o0 = v3(prev[a]), o1 = v3(prev[b]), o2 = v3(prev[c]);
+    int mx, my, mz;
+    unsigned lx, ly, lz;
+    bool bad;
+    ex::triCellRange(p0, p1, p2, o0, o1, o2, mx, my, mz, lx, ly, lz, bad);
+    if (bad) sb[6] = 1;
+    if (lx > 50u || ly > 50u || lz > 50u) lx = ly = lz = 0;  // TriCompRange cap: not inserted at all
+    uint32_t cells = lx * ly * lz;
+    // sweptTriRange cap (20 per axis): inserted but queries nothing; a queried range of > 1000 cells
+    // trips the reference's hang guard (every cell of the range holds at least this triangle), Solver.cpp:741-745
+    if (lx <= 20u && ly <= 20u && lz <= 20u && cells > 1000u) sb[7] = 1;
+    triMin[t] = make_int4(mx, my, mz, 0);
+    triRec[t] = make_uint4(a, b, c, lx | (ly << 8) | (lz << 16));
+    cnt[t] = cells;
+    uint32_t rank = canonicalRank(t, nTri, threadCount);
+    cntRank[rank] = cells;
+    // floor test per corner (Solver.cpp:829-834)
+    floorRank[rank] = (p0.y < floorLimit ? 1u : 0u) + (p1.y < floorLimit ? 1u : 0u) + (p2.y < floorLimit ? 1u : 0u);
+    if (cells) {
+      atomicMin(&sb[0], mx); atomicMin(&sb[1], my); atomicMin(&sb[2], mz);
+      atomicMax(&sb[3], mx + (int)lx - 1); atomicMax(&sb[4], my + (int)ly - 1); atomicMax(&sb[5], mz + (int)lz - 1);
+    }
+    aabbLo[t] = make_float4(fminf(fminf(fminf(p0.x, o0.x), fminf(p1.x, o1.x)), fminf(p2.x, o2.x)),
+                            fminf(fminf(fminf(p0.y, o0.y), fminf(p1.y, o1.y)), fminf(p2.y, o2.y)),
+                            fminf(fminf(fminf(p0.z, o0.z), fminf(p1.z, o1.z)), fminf(p2.z, o2.z)), 0.0f);
+    aabbHi[t] = make_float4(fmaxf(fmaxf(fmaxf(p0.x, o0.x), fmaxf(p1.x, o1.x)), fmaxf(p2.x, o2.x)),
+                            fmaxf(fmaxf(fmaxf(p0.y, o0.y), fmaxf(p1.y, o1.y)), fmaxf(p2.y, o2.y)),
+                            fmaxf(fmaxf(fmaxf(p0.z, o0.z), fmaxf(p1.z, o1.z)), fmaxf(p2.z, o2.z)), 0.0f);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) { if (sb[threadIdx.x] != 0x7fffffff) atomicMin(bbox + threadIdx.x, sb[threadIdx.x]); }
+  else if (threadIdx.x < 6) { if (sb[threadIdx.x] != (int)0x80000000) atomicMax(bbox + threadIdx.x, sb[threadIdx.x]); }
+  else if (threadIdx.x < 8) { if (sb[threadIdx.x]) atomicExch(bbox + threadIdx.x, 1); }
+}
+
+// floor list in canonical order: scanned floorRank gives each triangle's slot
+__global__ void __launch_bounds__(kThreads) k_floor_write(uint32_t nTri, uint32_t threadCount, float floorLimit,
+                                                          const uint4* __restrict__ triRec, const float4* __restrict__ q,
+                                                          const uint32_t* __restrict__ floorRank,
+                                                          uint32_t* __restrict__ outFloor) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nTri) return;
-  uint32_t a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
-  V3 p0 = v3(q[a]), p1 = v3(q[b]), p2 = v3(q[c]);
-  V3 o0 = v3(prev[a]), o1 = v3(prev[b]), o2 = v3(prev[c]);
-  int mx, my, mz;
-  unsigned lx, ly, lz;
-  bool bad;
-  ex::triCellRange(p0, p1, p2, o0, o1, o2, mx, my, mz, lx, ly, lz, bad);
-  if (bad) atomicExch(bbox + 6, 1);
-  if (lx > 50u || ly > 50u || lz > 50u) lx = ly = lz = 0;  // TriCompRange cap: not inserted at all
-  triMin[t] = make_int4(mx, my, mz, 0);
-  triLen[t] = lx | (ly << 8) | (lz << 16);
-  uint32_t cells = lx * ly * lz;
-  cnt[t] = cells;
-  if (cells) {
-    atomicMin(bbox + 0, mx); atomicMin(bbox + 1, my); atomicMin(bbox + 2, mz);
-    atomicMax(bbox + 3, mx + (int)lx - 1); atomicMax(bbox + 4, my + (int)ly - 1); atomicMax(bbox + 5, mz + (int)lz - 1);
-  }
-  aabbLo[t] = make_float4(fminf(fminf(fminf(p0.x, o0.x), fminf(p1.x, o1.x)), fminf(p2.x, o2.x)),
-                          fminf(fminf(fminf(p0.y, o0.y), fminf(p1.y, o1.y)), fminf(p2.y, o2.y)),
-                          fminf(fminf(fminf(p0.z, o0.z), fminf(p1.z, o1.z)), fminf(p2.z, o2.z)), 0.0f);
-  aabbHi[t] = make_float4(fmaxf(fmaxf(fmaxf(p0.x, o0.x), fmaxf(p1.x, o1.x)), fmaxf(p2.x, o2.x)),
-                          fmaxf(fmaxf(fmaxf(p0.y, o0.y), fmaxf(p1.y, o1.y)), fmaxf(p2.y, o2.y)),
-                          fmaxf(fmaxf(fmaxf(p0.z, o0.z), fmaxf(p1.z, o1.z)), fmaxf(p2.z, o2.z)), 0.0f);
+  uint32_t rank = canonicalRank(t, nTri, threadCount);
+  uint32_t beg = floorRank[rank], end = floorRank[rank + 1];
+  if (beg == end) return;
+  uint4 r = triRec[t];
+  uint32_t ids[3] = {r.x, r.y, r.z};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (q[ids[i]].y < floorLimit) outFloor[beg++] = ids[i];
 }
 
 // ---- 2. pairs ------------------------------------------------------------------------------
 struct KeyPack { int minX, minY, minZ; int bitsY, bitsZ; };
 
+// (cell key, triangle) pairs in ascending triangle order, cells of a triangle in (dx,dy,dz) order
 __global__ void __launch_bounds__(kThreads) k_emit_pairs(uint32_t nTri, const int4* __restrict__ triMin,
-                                                         const uint32_t* __restrict__ triLen,
+                                                         const uint4* __restrict__ triRec,
                                                          const uint32_t* __restrict__ off, KeyPack kp,
-                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                         uint32_t* __restrict__ pairTri) {
+                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nTri) return;
-  uint32_t len = triLen[t];
+  uint32_t len = triRec[t].w;
   uint32_t lx = len & 255u, ly = (len >> 8) & 255u, lz = (len >> 16) & 255u;
   if (!(lx * ly * lz)) return;
   int4 m = triMin[t];
@@ -77,24 +120,16 @@ __global__ void __launch_bounds__(kThreads) k_emit_pairs(uint32_t nTri, const in
         uint64_t ky = (uint64_t)(uint32_t)(m.y + (int)dy - kp.minY);
         uint64_t kz = (uint64_t)(uint32_t)(m.z + (int)dz - kp.minZ);
         keys[i] = (kx << (kp.bitsY + kp.bitsZ)) | (ky << kp.bitsZ) | kz;
-        vals[i] = i;
-        pairTri[i] = t;
+        vals[i] = t;
       }
 }
 
 // ---- 3. cell-start table -------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_mark_heads(uint64_t nPairs, const uint64_t* __restrict__ keys,
-                                                         const uint32_t* __restrict__ vals,
-                                                         const uint32_t* __restrict__ pairTri,
-                                                         uint32_t* __restrict__ heads, uint32_t* __restrict__ memberTri,
-                                                         uint32_t* __restrict__ posOf) {
+                                                         uint32_t* __restrict__ heads) {
   uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j > nPairs) return;
-  if (j == nPairs) { heads[j] = 0; return; }
-  heads[j] = (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
-  uint32_t i = vals[j];
-  memberTri[j] = pairTri[i];
-  posOf[i] = (uint32_t)j;
+  heads[j] = (j < nPairs && (j == 0 || keys[j] != keys[j - 1])) ? 1u : 0u;
 }
 
 // cellIdx (in place of the scanned heads) and cellStart
@@ -111,116 +146,101 @@ __global__ void __launch_bounds__(kThreads) k_cell_starts(uint64_t nPairs, const
 }
 
 // ---- 4. narrow phase ------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t canonicalRank(uint32_t t, uint32_t nTri, uint32_t T) {
-  // thread (t % T) handles t, t+T, ...; per-thread lists are concatenated in thread order (Solver.cpp:714,852-873)
-  uint32_t th = t % T, k = t / T;
-  uint32_t full = nTri / T, rem = nTri % T;  // threads < rem own full+1 triangles
-  return th * full + (th < rem ? th : rem) + k;
-}
-
+// One thread per (cell, member) pair of the sorted table: the member triangle is tested against
+// every triangle of that cell, which is what the reference's worker does when it visits this
+// bucket for this triangle.  Neighbouring threads sit in the same cell, so the loop over the
+// cell's members reads the same records in every lane (broadcast loads) while each lane keeps
+// its own triangle in registers.  Hits of pair (t, k-th cell of t) are counted into slot
+// rankOff[rank(t)] + k, i.e. directly in the reference's output order (thread-striped triangle
+// order, cells in (dx,dy,dz) order); after a scan the same kernel writes them.
 struct NarrowParams {
   uint32_t nTri, threadCount;
-  float threshold, floorLimit;  // floorHeight + thickness
+  float threshold;
   float cullMargin;
 };
 
 template <bool WRITE>
-__global__ void __launch_bounds__(128) k_narrow(NarrowParams np, const uint32_t* __restrict__ tri,
-                                                const float4* __restrict__ q, const float4* __restrict__ prev,
-                                                const uint32_t* __restrict__ triLen, const uint32_t* __restrict__ off,
-                                                const uint32_t* __restrict__ posOf, const uint32_t* __restrict__ cellIdx,
-                                                const uint32_t* __restrict__ cellStart,
-                                                const uint32_t* __restrict__ memberTri,
-                                                const float4* __restrict__ aabbLo, const float4* __restrict__ aabbHi,
-                                                uint32_t* __restrict__ hitCount /* canonical order, scanned when WRITE */,
-                                                uint32_t* __restrict__ floorCount, uint4* __restrict__ outTri,
-                                                uint32_t* __restrict__ outFloor, int* __restrict__ failFlag) {
-  uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (t >= np.nTri) return;
-  uint32_t rank = canonicalRank(t, np.nTri, np.threadCount);
-  uint32_t ia[3] = {tri[3 * t], tri[3 * t + 1], tri[3 * t + 2]};
+__global__ void __launch_bounds__(kThreads) k_pair_narrow(NarrowParams np, KeyPack kp, uint64_t nPairs,
+                                                          const uint64_t* __restrict__ keys,
+                                                          const uint32_t* __restrict__ memberTri,
+                                                          const uint32_t* __restrict__ cellIdx,
+                                                          const uint32_t* __restrict__ cellStart,
+                                                          const uint4* __restrict__ triRec, const int4* __restrict__ triMin,
+                                                          const float4* __restrict__ aabbLo, const float4* __restrict__ aabbHi,
+                                                          const float4* __restrict__ q, const float4* __restrict__ prev,
+                                                          const uint32_t* __restrict__ rankOff,
+                                                          uint32_t* __restrict__ hitCount /* canonical slots; scanned when WRITE */,
+                                                          uint4* __restrict__ outTri, int* __restrict__ failFlag) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nPairs) return;
+  uint32_t t = memberTri[j];
+  uint4 rec = triRec[t];
+  uint32_t lx = rec.w & 255u, ly = (rec.w >> 8) & 255u, lz = (rec.w >> 16) & 255u;
+  // slot of (t, this cell) in the canonical order
+  uint64_t key = keys[j];
+  int4 mn = triMin[t];
+  uint32_t dz = (uint32_t)((int)(key & ((1ull << kp.bitsZ) - 1ull)) + kp.minZ - mn.z);
+  uint32_t dy = (uint32_t)((int)((key >> kp.bitsZ) & ((1ull << kp.bitsY) - 1ull)) + kp.minY - mn.y);
+  uint32_t dx = (uint32_t)((int)(key >> (kp.bitsY + kp.bitsZ)) + kp.minX - mn.x);
+  uint32_t slot = rankOff[canonicalRank(t, np.nTri, np.threadCount)] + (dx * ly + dy) * lz + dz;
+  if (!WRITE && j == 0) hitCount[nPairs] = 0;
+  if (lx > 20u || ly > 20u || lz > 20u) {  // sweptTriRange cap: inserted but queries nothing
+    if (!WRITE) hitCount[slot] = 0;
+    return;
+  }
+  uint32_t cidx = cellIdx[j];
+  uint32_t s = cellStart[cidx], e = cellStart[cidx + 1];
+  if (e - s > 1000u) atomicExch(failFlag, 1);  // hang guard, Solver.cpp:751-755
+  uint32_t ia[3] = {rec.x, rec.y, rec.z};
   V3 pa[3], oa[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { pa[i] = v3(q[ia[i]]); oa[i] = v3(prev[ia[i]]); }
-  uint32_t len = triLen[t];
-  uint32_t lx = len & 255u, ly = (len >> 8) & 255u, lz = (len >> 16) & 255u;
-  uint32_t nCells = lx * ly * lz;
-  if (lx > 20u || ly > 20u || lz > 20u) nCells = 0;  // sweptTriRange cap: inserted but queries nothing
-  if (nCells > 1000u) { if (lane == 0) atomicExch(failFlag, 1); nCells = 0; }  // hang guard, Solver.cpp:741-745
-  uint32_t base = off[t];
-  uint32_t outPos = WRITE ? hitCount[rank] : 0u;
-  uint32_t total = 0;
-  // swept boxes of the three corners, padded by the cull margin
   float cLo[3][3], cHi[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
+    pa[i] = v3(q[ia[i]]); oa[i] = v3(prev[ia[i]]);
     cLo[i][0] = fminf(pa[i].x, oa[i].x) - np.cullMargin; cHi[i][0] = fmaxf(pa[i].x, oa[i].x) + np.cullMargin;
     cLo[i][1] = fminf(pa[i].y, oa[i].y) - np.cullMargin; cHi[i][1] = fmaxf(pa[i].y, oa[i].y) + np.cullMargin;
     cLo[i][2] = fminf(pa[i].z, oa[i].z) - np.cullMargin; cHi[i][2] = fmaxf(pa[i].z, oa[i].z) + np.cullMargin;
   }
-  for (uint32_t k = 0; k < nCells; ++k) {
-    uint32_t j = posOf[base + k];
-    uint32_t cidx = cellIdx[j];
-    uint32_t s = cellStart[cidx], e = cellStart[cidx + 1];
-    if (e - s > 1000u) { if (lane == 0) atomicExch(failFlag, 1); }  // hang guard, Solver.cpp:751-755
-    for (uint32_t m0 = s; m0 < e; m0 += 32) {
-      uint32_t m = m0 + lane;
-      uint32_t mask = 0;
-      uint32_t ib = 0, ic = 0, id = 0;
-      if (m < e) {
-        uint32_t o = memberTri[m];
-        ib = tri[3 * o]; ic = tri[3 * o + 1]; id = tri[3 * o + 2];
-        bool common = false;
+  // union of the three corner boxes: one test rejects most members
+  float uLo[3], uHi[3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) common |= (ia[i] == ib) | (ia[i] == ic) | (ia[i] == id);
-        if (!common) {
-          float4 lo = aabbLo[o], hi = aabbHi[o];
-          uint32_t maybe = 0;
+  for (int c = 0; c < 3; ++c) {
+    uLo[c] = fminf(cLo[0][c], fminf(cLo[1][c], cLo[2][c]));
+    uHi[c] = fmaxf(cHi[0][c], fmaxf(cHi[1][c], cHi[2][c]));
+  }
+  uint32_t outPos = WRITE ? hitCount[slot] : 0u;
+  uint32_t total = 0;
+  for (uint32_t m = s; m < e; ++m) {
+    uint32_t o = memberTri[m];
+    uint4 ro = triRec[o];
+    bool common = false;
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            bool ov = cLo[i][0] <= hi.x && cHi[i][0] >= lo.x && cLo[i][1] <= hi.y && cHi[i][1] >= lo.y &&
-                      cLo[i][2] <= hi.z && cHi[i][2] >= lo.z;
-            maybe |= ov ? (1u << i) : 0u;
-          }
-          if (maybe) {
-            V3 pb = v3(q[ib]), pc = v3(q[ic]), pd = v3(q[id]);
-            V3 ob = v3(prev[ib]), oc = v3(prev[ic]), od = v3(prev[id]);
-            V3 ab0 = ex::sub(oc, ob), ac0 = ex::sub(od, ob), ab1 = ex::sub(pc, pb), ac1 = ex::sub(pd, pb);
+    for (int i = 0; i < 3; ++i) common |= (ia[i] == ro.x) | (ia[i] == ro.y) | (ia[i] == ro.z);
+    if (common) continue;
+    float4 lo = aabbLo[o], hi = aabbHi[o];
+    if (!(uLo[0] <= hi.x && uHi[0] >= lo.x && uLo[1] <= hi.y && uHi[1] >= lo.y && uLo[2] <= hi.z && uHi[2] >= lo.z)) continue;
+    uint32_t maybe = 0;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              if (!(maybe & (1u << i))) continue;
-              float tt;
-              if (ex::pointTriangleCCD(ex::sub(oa[i], ob), ab0, ac0, ex::sub(pa[i], pb), ab1, ac1, np.threshold, tt))
-                mask |= 1u << i;
-            }
-          }
-        }
+    for (int i = 0; i < 3; ++i) {
+      bool ov = cLo[i][0] <= hi.x && cHi[i][0] >= lo.x && cLo[i][1] <= hi.y && cHi[i][1] >= lo.y &&
+                cLo[i][2] <= hi.z && cHi[i][2] >= lo.z;
+      maybe |= ov ? (1u << i) : 0u;
+    }
+    if (!maybe) continue;
+    V3 pb = v3(q[ro.x]), pc = v3(q[ro.y]), pd = v3(q[ro.z]);
+    V3 ob = v3(prev[ro.x]), oc = v3(prev[ro.y]), od = v3(prev[ro.z]);
+    V3 ab0 = ex::sub(oc, ob), ac0 = ex::sub(od, ob), ab1 = ex::sub(pc, pb), ac1 = ex::sub(pd, pb);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (!(maybe & (1u << i))) continue;
+      float tt;
+      if (ex::pointTriangleCCD(ex::sub(oa[i], ob), ab0, ac0, ex::sub(pa[i], pb), ab1, ac1, np.threshold, tt)) {
+        if (WRITE) outTri[outPos + total] = make_uint4(ia[i], ro.x, ro.y, ro.z);
+        ++total;
       }
-      uint32_t hits = __popc(mask);
-      // ordered by member (lane) then corner
-      uint32_t incl = hits;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      uint32_t chunkTotal = __shfl_sync(0xffffffffu, incl, 31);
-      if (WRITE && hits) {
-        uint32_t w = outPos + total + incl - hits;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-          if (mask & (1u << i)) outTri[w++] = make_uint4(ia[i], ib, ic, id);
-      }
-      total += chunkTotal;
     }
   }
-  if (lane == 0) {
-    // floor test per corner (Solver.cpp:829-834)
-    uint32_t f = 0;
-    uint32_t fbase = WRITE ? floorCount[rank] : 0u;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-      if (pa[i].y < np.floorLimit) { if (WRITE) outFloor[fbase + f] = ia[i]; ++f; }
-    if (!WRITE) { hitCount[rank] = total; floorCount[rank] = f; }
-  }
+  if (!WRITE) hitCount[slot] = total;
 }
 
 // ---- 5. node -> incident entries --------------------------------------------------------------
@@ -254,6 +274,17 @@ __global__ void __launch_bounds__(kThreads) k_floor_weight(uint32_t n, const uin
   w[i] = acc;
 }
 
+// ticket of every (entry, slot): its position in the node's ordered incidence list.  The ordered
+// Gauss-Seidel sweeps (contact.cu) run an entry once each of its four nodes has seen `ticket` earlier entries.
+__global__ void __launch_bounds__(kThreads) k_inc_tickets(uint64_t nInc, const uint64_t* __restrict__ sortedNode,
+                                                          const uint32_t* __restrict__ inc,
+                                                          const uint32_t* __restrict__ incPtr,
+                                                          uint32_t* __restrict__ ticket) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nInc) return;
+  ticket[inc[k]] = (uint32_t)k - incPtr[(uint32_t)sortedNode[k]];
+}
+
 __global__ void k_init_bbox(int* bbox) {
   bbox[0] = bbox[1] = bbox[2] = 0x7fffffff;
   bbox[3] = bbox[4] = bbox[5] = (int)0x80000000;
@@ -275,30 +306,42 @@ static int bitsFor(int64_t span) {  // bits to hold values 0..span
 int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, ContactLists& out, int* launches) {
   int L = 0;
   const uint32_t nTri = in.nTri, n = in.nNodes;
+  const uint32_t T = in.threadCount ? in.threadCount : 1u;
+  const float floorLimit = in.floorLimit;
   out.nTri = out.nFloor = 0;
   w.nPairs = 0; w.nCells = 0; w.failed = false; w.badInput = false;
   DCHECK(w.incPtr.reserve(n + 2));
   DCHECK(w.floorMult.reserve(n + 1));
   DCHECK(w.floorW.reserve(n + 1));
-  out.incPtr = (int*)w.incPtr.p; out.floorW = w.floorW.p; out.floorMult = w.floorMult.p;
+  DCHECK(w.nodeDone.reserve(n + 1));
+  out.incPtr = (int*)w.incPtr.p; out.floorW = w.floorW.p; out.floorMult = w.floorMult.p; out.nodeDone = w.nodeDone.p;
   if (!nTri) return 0;
-  DCHECK(w.triMin.reserve(nTri)); DCHECK(w.triLen.reserve(nTri)); DCHECK(w.cnt.reserve(nTri + 2));
+  DCHECK(w.triMin.reserve(nTri)); DCHECK(w.triRec.reserve(nTri)); DCHECK(w.cnt.reserve(nTri + 2));
+  DCHECK(w.cntRank.reserve(nTri + 2)); DCHECK(w.floorRank.reserve(nTri + 2));
   DCHECK(w.aabbLo.reserve(nTri)); DCHECK(w.aabbHi.reserve(nTri));
-  DCHECK(w.hitCount.reserve(nTri + 2)); DCHECK(w.floorCount.reserve(nTri + 2));
   DCHECK(w.bbox.reserve(8));
   DCHECK(w.scanScratch.reserve(scanScratchElems(std::max<uint64_t>(nTri + 2, w.scanCap))));
   k_init_bbox<<<1, 1, 0, s>>>(w.bbox.p); ++L;
-  DCHECK(cudaMemsetAsync(w.cnt.p, 0, (nTri + 2) * sizeof(uint32_t), s));
-  k_tri_ranges<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, in.tri, in.q, in.prev, w.triMin.p, w.triLen.p, w.cnt.p,
-                                                           w.aabbLo.p, w.aabbHi.p, w.bbox.p); ++L;
+  DCHECK(cudaMemsetAsync(w.cnt.p + nTri, 0, 2 * sizeof(uint32_t), s));
+  DCHECK(cudaMemsetAsync(w.cntRank.p + nTri, 0, 2 * sizeof(uint32_t), s));
+  DCHECK(cudaMemsetAsync(w.floorRank.p + nTri, 0, 2 * sizeof(uint32_t), s));
+  k_tri_ranges<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, T, floorLimit, in.tri, in.q, in.prev, w.triMin.p, w.triRec.p,
+                                                           w.cnt.p, w.cntRank.p, w.floorRank.p, w.aabbLo.p, w.aabbHi.p,
+                                                           w.bbox.p); ++L;
   L += launchExclusiveScan(s, w.cnt.p, nTri + 1, w.scanScratch.p);
+  L += launchExclusiveScan(s, w.cntRank.p, nTri + 1, w.scanScratch.p);
+  L += launchExclusiveScan(s, w.floorRank.p, nTri + 1, w.scanScratch.p);
   DCHECK(cudaMemcpyAsync(w.host, w.bbox.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
   DCHECK(cudaMemcpyAsync(w.host + 8, w.cnt.p + nTri, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  DCHECK(cudaMemcpyAsync(w.host + 11, w.floorRank.p + nTri, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   DCHECK(cudaStreamSynchronize(s));
   if (w.host[6]) { w.badInput = true; return 0; }
+  if (w.host[7]) { w.failed = true; if (launches) *launches += L; return 0; }  // reference latches _simFailed, lists stay empty
   uint64_t nPairs = (uint32_t)w.host[8];
+  uint32_t nFloor = (uint32_t)w.host[11];
   w.nPairs = nPairs;
-  NarrowParams np{nTri, in.threadCount ? in.threadCount : 1u, in.threshold, in.floorLimit, in.threshold + 1e-3f};
+  NarrowParams np{nTri, T, in.threshold, in.threshold + 1e-3f};
+  uint32_t nHit = 0;
   if (nPairs) {
     KeyPack kp{w.host[0], w.host[1], w.host[2], 0, 0};
     int bx = bitsFor((int64_t)w.host[3] - w.host[0]), by = bitsFor((int64_t)w.host[4] - w.host[1]),
@@ -308,59 +351,64 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
     w.keyPack[0] = kp.minX; w.keyPack[1] = kp.minY; w.keyPack[2] = kp.minZ; w.keyPack[3] = by; w.keyPack[4] = bz;
     DCHECK(w.keys.reserve(nPairs)); DCHECK(w.tmpKeys.reserve(nPairs));
     DCHECK(w.vals.reserve(nPairs)); DCHECK(w.tmpVals.reserve(nPairs));
-    DCHECK(w.pairTri.reserve(nPairs)); DCHECK(w.posOf.reserve(nPairs)); DCHECK(w.memberTri.reserve(nPairs));
-    DCHECK(w.heads.reserve(nPairs + 2)); DCHECK(w.cellStart.reserve(nPairs + 2));
+    DCHECK(w.heads.reserve(nPairs + 2)); DCHECK(w.cellStart.reserve(nPairs + 2)); DCHECK(w.hitCount.reserve(nPairs + 2));
     DCHECK(w.sortHist.reserve(sortHistBytes(nPairs) / 4 + 4));
     w.scanCap = std::max<uint64_t>(w.scanCap, nPairs + 2);
     DCHECK(w.scanScratch.reserve(scanScratchElems(w.scanCap)));
-    k_emit_pairs<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, w.triMin.p, w.triLen.p, w.cnt.p, kp, w.keys.p, w.vals.p,
-                                                             w.pairTri.p); ++L;
+    k_emit_pairs<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, w.triMin.p, w.triRec.p, w.cnt.p, kp, w.keys.p, w.vals.p); ++L;
     L += launchSortPairs(s, nPairs, w.keys.p, w.vals.p, w.tmpKeys.p, w.tmpVals.p, w.sortHist.p, bx + by + bz);
-    k_mark_heads<<<gridFor(nPairs + 1, kThreads), kThreads, 0, s>>>(nPairs, w.keys.p, w.vals.p, w.pairTri.p, w.heads.p,
-                                                                   w.memberTri.p, w.posOf.p); ++L;
+    k_mark_heads<<<gridFor(nPairs + 1, kThreads), kThreads, 0, s>>>(nPairs, w.keys.p, w.heads.p); ++L;
     L += launchExclusiveScan(s, w.heads.p, nPairs + 1, w.scanScratch.p);
     DCHECK(cudaMemcpyAsync(w.host + 9, w.heads.p + nPairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     k_cell_starts<<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(nPairs, w.keys.p, w.heads.p, w.cellStart.p); ++L;
+    // count pass
+    k_pair_narrow<false><<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p,
+                                                                       w.cellStart.p, w.triRec.p, w.triMin.p, w.aabbLo.p,
+                                                                       w.aabbHi.p, in.q, in.prev, w.cntRank.p, w.hitCount.p,
+                                                                       nullptr, w.bbox.p + 7); ++L;
+    L += launchExclusiveScan(s, w.hitCount.p, nPairs + 1, w.scanScratch.p);
+    DCHECK(cudaMemcpyAsync(w.host + 10, w.hitCount.p + nPairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    DCHECK(cudaMemcpyAsync(w.host + 12, w.bbox.p + 7, sizeof(int), cudaMemcpyDeviceToHost, s));
+    DCHECK(cudaStreamSynchronize(s));
+    w.nCells = (uint32_t)w.host[9];
+    if (w.host[12]) { w.failed = true; if (launches) *launches += L; return 0; }
+    nHit = (uint32_t)w.host[10];
+    DCHECK(w.triList.reserve(nHit + 1));
+    if (nHit) {
+      k_pair_narrow<true><<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p,
+                                                                        w.cellStart.p, w.triRec.p, w.triMin.p, w.aabbLo.p,
+                                                                        w.aabbHi.p, in.q, in.prev, w.cntRank.p, w.hitCount.p,
+                                                                        w.triList.p, w.bbox.p + 7); ++L;
+    }
   }
-  // count pass
-  DCHECK(cudaMemsetAsync(w.hitCount.p, 0, (nTri + 2) * sizeof(uint32_t), s));
-  DCHECK(cudaMemsetAsync(w.floorCount.p, 0, (nTri + 2) * sizeof(uint32_t), s));
-  k_narrow<false><<<gridFor((uint64_t)nTri * 32, 128), 128, 0, s>>>(np, in.tri, in.q, in.prev, w.triLen.p, w.cnt.p, w.posOf.p,
-                                                                    w.heads.p, w.cellStart.p, w.memberTri.p, w.aabbLo.p,
-                                                                    w.aabbHi.p, w.hitCount.p, w.floorCount.p, nullptr, nullptr,
-                                                                    w.bbox.p + 7); ++L;
-  L += launchExclusiveScan(s, w.hitCount.p, nTri + 1, w.scanScratch.p);
-  L += launchExclusiveScan(s, w.floorCount.p, nTri + 1, w.scanScratch.p);
-  DCHECK(cudaMemcpyAsync(w.host + 10, w.hitCount.p + nTri, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  DCHECK(cudaMemcpyAsync(w.host + 11, w.floorCount.p + nTri, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  DCHECK(cudaMemcpyAsync(w.host + 12, w.bbox.p + 7, sizeof(int), cudaMemcpyDeviceToHost, s));
-  DCHECK(cudaStreamSynchronize(s));
-  w.nCells = nPairs ? (uint32_t)w.host[9] : 0;
-  if (w.host[12]) { w.failed = true; if (launches) *launches += L; return 0; }  // reference latches _simFailed, lists stay empty
-  uint32_t nHit = (uint32_t)w.host[10], nFloor = (uint32_t)w.host[11];
-  DCHECK(w.triList.reserve(nHit + 1)); DCHECK(w.floorList.reserve(nFloor + 1));
-  k_narrow<true><<<gridFor((uint64_t)nTri * 32, 128), 128, 0, s>>>(np, in.tri, in.q, in.prev, w.triLen.p, w.cnt.p, w.posOf.p,
-                                                                   w.heads.p, w.cellStart.p, w.memberTri.p, w.aabbLo.p,
-                                                                   w.aabbHi.p, w.hitCount.p, w.floorCount.p, w.triList.p,
-                                                                   w.floorList.p, w.bbox.p + 7); ++L;
+  DCHECK(w.floorList.reserve(nFloor + 1));
+  if (nFloor) {
+    k_floor_write<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, T, floorLimit, w.triRec.p, in.q, w.floorRank.p,
+                                                              w.floorList.p); ++L;
+  }
   out.tri = w.triList.p; out.floorNode = w.floorList.p; out.nTri = nHit; out.nFloor = nFloor;
-  // incidence CSR + floor multiplicities
-  DCHECK(cudaMemsetAsync(w.incPtr.p, 0, (n + 2) * sizeof(uint32_t), s));
-  DCHECK(cudaMemsetAsync(w.floorMult.p, 0, (n + 1) * sizeof(uint32_t), s));
+  // incidence CSR + tickets + floor multiplicities
   if (nHit) {
     uint64_t nInc = 4ull * nHit;
+    DCHECK(cudaMemsetAsync(w.incPtr.p, 0, (n + 2) * sizeof(uint32_t), s));
     DCHECK(w.incKeys.reserve(nInc)); DCHECK(w.incTmpKeys.reserve(nInc));
-    DCHECK(w.incVals.reserve(nInc)); DCHECK(w.incTmpVals.reserve(nInc));
+    DCHECK(w.incVals.reserve(nInc)); DCHECK(w.incTmpVals.reserve(nInc)); DCHECK(w.ticket.reserve(nInc));
     DCHECK(w.sortHist.reserve(sortHistBytes(nInc) / 4 + 4));
     w.scanCap = std::max<uint64_t>(w.scanCap, std::max<uint64_t>(nInc, n) + 2);
     DCHECK(w.scanScratch.reserve(scanScratchElems(w.scanCap)));
     k_inc_emit<<<gridFor(nHit, kThreads), kThreads, 0, s>>>(nHit, w.triList.p, w.incKeys.p, w.incVals.p, w.incPtr.p); ++L;
     L += launchExclusiveScan(s, w.incPtr.p, n + 1, w.scanScratch.p);
     L += launchSortPairs(s, nInc, w.incKeys.p, w.incVals.p, w.incTmpKeys.p, w.incTmpVals.p, w.sortHist.p, bitsFor(n));
+    k_inc_tickets<<<gridFor(nInc, kThreads), kThreads, 0, s>>>(nInc, w.incKeys.p, w.incVals.p, w.incPtr.p, w.ticket.p); ++L;
     out.inc = w.incVals.p;
+    out.ticket = reinterpret_cast<uint4*>(w.ticket.p);
   }
-  if (nFloor) { k_floor_mult<<<gridFor(nFloor, kThreads), kThreads, 0, s>>>(nFloor, w.floorList.p, w.floorMult.p); ++L; }
-  k_floor_weight<<<gridFor(n, kThreads), kThreads, 0, s>>>(n, w.floorMult.p, w.floorW.p); ++L;
+  if (nFloor || w.floorDirty) {
+    DCHECK(cudaMemsetAsync(w.floorMult.p, 0, (n + 1) * sizeof(uint32_t), s));
+    if (nFloor) { k_floor_mult<<<gridFor(nFloor, kThreads), kThreads, 0, s>>>(nFloor, w.floorList.p, w.floorMult.p); ++L; }
+    k_floor_weight<<<gridFor(n, kThreads), kThreads, 0, s>>>(n, w.floorMult.p, w.floorW.p); ++L;
+    w.floorDirty = nFloor != 0;
+  }
   if (launches) *launches += L;
   return 0;
 }

@@ -18,11 +18,13 @@ struct DetectInput {
 
 struct DetectWork {
   DevBuf<int4> triMin;
-  DevBuf<uint32_t> triLen, cnt, hitCount, floorCount, scanScratch;
+  DevBuf<uint4> triRec;                         // (a, b, c, lx | ly << 8 | lz << 16)
+  DevBuf<uint32_t> cnt, cntRank, floorRank, hitCount, scanScratch;
   DevBuf<float4> aabbLo, aabbHi;
   DevBuf<int> bbox;
   DevBuf<uint64_t> keys, tmpKeys, incKeys, incTmpKeys;
-  DevBuf<uint32_t> vals, tmpVals, pairTri, posOf, memberTri, heads, cellStart, sortHist, incVals, incTmpVals;
+  DevBuf<uint32_t> vals /* sorted: member triangle of every (cell, member) pair */, tmpVals, heads, cellStart, sortHist,
+      incVals, incTmpVals, ticket, nodeDone;
   DevBuf<uint4> triList;
   DevBuf<uint32_t> floorList, incPtr, floorMult;
   DevBuf<float> floorW;
@@ -30,7 +32,7 @@ struct DetectWork {
   uint64_t nPairs = 0, scanCap = 0;
   uint32_t nCells = 0;
   int keyPack[5] = {0, 0, 0, 0, 0};  // minX, minY, minZ, bitsY, bitsZ of the last detection
-  bool failed = false, badInput = false;
+  bool failed = false, badInput = false, floorDirty = true;
   cudaError_t lastError = cudaSuccess;
 };
 

@@ -262,9 +262,8 @@ int runDetection(PiesB200Solver* s, ContactLists& lists) {
   PIES_CHECK(s, cudaGetLastError());
   if (s->detect->badInput) { s->simFailed = true; return fail(s, PIES_B200_ERANGE, "non-finite or out-of-range (|x| >= 2^30) positions reached collision detection"); }
   if (s->detect->failed) { s->simFailed = true; lists.nTri = lists.nFloor = 0; }  // Solver.cpp:852-856
-  int L2 = buildContactComponents(*s->contact, s->stream, s->n, lists);
-  if (L2 < 0) return failCuda(s, cudaErrorMemoryAllocation, "buildContactComponents", __LINE__);
-  s->launches += L2;
+  if (prepareContactSweeps(*s->contact, s->stream, lists) < 0)
+    return failCuda(s, cudaErrorMemoryAllocation, "prepareContactSweeps", __LINE__);
   if (lists.nTri) PIES_CHECK(s, s->contact->contribC.reserve(4ull * lists.nTri));
   s->stats.triCollisions = lists.nTri;
   s->stats.staticCollisions = lists.nFloor;
@@ -347,7 +346,7 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
 
     timer.begin(kPhContact);
     if (s->contact)
-      s->launches += launchStabilize(st, *s->contact, lists, s->q.p, s->prev.p, s->snap.p, o.collisionThickness,
+      s->launches += launchStabilize(st, *s->contact, lists, n, s->q.p, s->prev.p, s->snap.p, o.collisionThickness,
                                      o.collisionStabilizationIterations);
     timer.end();
     timer.begin(kPhOther);

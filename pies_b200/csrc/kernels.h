@@ -46,6 +46,10 @@ struct ContactLists {
   int* incPtr = nullptr; uint32_t* inc = nullptr;
   float* floorW = nullptr;     // per node: sum of floor-contact weights (multiplicity * 1e4)
   uint32_t* floorMult = nullptr;
+  // ordered Gauss-Seidel sweeps: ticket[e] = position of entry e in each of its four nodes' incidence
+  // lists; nodeDone[v] = entries touching v already executed in the current sweep
+  uint4* ticket = nullptr;
+  uint32_t* nodeDone = nullptr;
 };
 
 // ------------------------------------------------------------- PD kernels ----
