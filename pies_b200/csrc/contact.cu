@@ -15,18 +15,20 @@ namespace pies {
 
 static inline int gridFor(uint64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
-constexpr float kPtW = 10000.0f;     // PointTriangleCollisionConstraint::w (CollisionConstraint.h:32)
 constexpr float kFloorW = 10000.0f;  // StaticCollisionConstraint::w (CollisionConstraint.h:78)
 
 // ---- per-iteration projections (parallel, no ordering issue) ---------------------------------------
-// contribC[4e + slot] = w * (A^T A p)_slot with p = current positions, p_A pushed to `thickness`
-// above the triangle plane when below it (CollisionConstraint.cpp:86-124, :176-194).
+// contribC[4u + slot] = copies * w * (A^T A p)_slot for distinct contact u, with p = current positions and
+// p_A pushed to `thickness` above the triangle plane when below it (CollisionConstraint.cpp:86-124, :176-194).
+// The reference adds the identical term once per copy; the copies are folded into the weight here.
 __global__ void __launch_bounds__(kThreads) k_pt_project(uint32_t nTri, const uint4* __restrict__ entries,
+                                                         const float* __restrict__ weight,
                                                          const float4* __restrict__ q, float thickness,
                                                          float4* __restrict__ contribC) {
   uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nTri) return;
   uint4 id = entries[e];
+  const float kPtW = weight[e];  // copies * PointTriangleCollisionConstraint::w
   V3 A = v3(q[id.x]), B = v3(q[id.y]), C = v3(q[id.z]), D = v3(q[id.w]);
   V3 nrm = normalize(cross(C - B, D - B));
   float nDotP = dot(nrm, A - B);
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(kThreads) k_floor_project(uint32_t nFloor, con
 int launchContactProject(cudaStream_t s, const ContactLists& c, const float4* q, float thickness, float4* contribC,
                          float4* snap) {
   int L = 0;
-  if (c.nTri) { k_pt_project<<<gridFor(c.nTri, kThreads), kThreads, 0, s>>>(c.nTri, c.tri, q, thickness, contribC); ++L; }
+  if (c.nUnique) { k_pt_project<<<gridFor(c.nUnique, kThreads), kThreads, 0, s>>>(c.nUnique, c.uTri, c.uW, q, thickness, contribC); ++L; }
   if (c.nFloor) { k_floor_project<<<gridFor(c.nFloor, kThreads), kThreads, 0, s>>>(c.nFloor, c.floorNode, q, snap); ++L; }
   return L;
 }

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) k_pair_narrow(NarrowParams np, KeyPa
                                                           const float4* __restrict__ q, const float4* __restrict__ prev,
                                                           const uint32_t* __restrict__ rankOff,
                                                           uint32_t* __restrict__ hitCount /* canonical slots; scanned when WRITE */,
-                                                          uint4* __restrict__ outTri, int* __restrict__ failFlag) {
+                                                          uint4* __restrict__ outTri, uint32_t* __restrict__ outOther, int* __restrict__ failFlag) {
   uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nPairs) return;
   uint32_t t = memberTri[j];
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) k_pair_narrow(NarrowParams np, KeyPa
       if (!(maybe & (1u << i))) continue;
       float tt;
       if (ex::pointTriangleCCD(ex::sub(oa[i], ob), ab0, ac0, ex::sub(pa[i], pb), ab1, ac1, np.threshold, tt)) {
-        if (WRITE) outTri[outPos + total] = make_uint4(ia[i], ro.x, ro.y, ro.z);
+        if (WRITE) { outTri[outPos + total] = make_uint4(ia[i], ro.x, ro.y, ro.z); outOther[outPos + total] = o; }
         ++total;
       }
     }
@@ -272,6 +272,31 @@ __global__ void __launch_bounds__(kThreads) k_floor_weight(uint32_t n, const uin
   float acc = 0.0f;
   for (uint32_t k = 0; k < mult[i]; ++k) acc += 10000.0f;  // StaticCollisionConstraint::w, coeffRef += per duplicate
   w[i] = acc;
+}
+
+// ---- 6. unique contacts ---------------------------------------------------------------------
+// The reference's list holds the same (point, triangle) once per shared cell and per triangle the
+// point is a corner of; the ordered sweeps need every copy, but the collision MATRIX and
+// the right-hand side only need each distinct contact with its multiplicity (weight = copies * w).
+__global__ void __launch_bounds__(kThreads) k_uniq_keys(uint32_t nHit, const uint4* __restrict__ entries,
+                                                        const uint32_t* __restrict__ other, int bitsTri,
+                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nHit) return;
+  keys[e] = ((uint64_t)entries[e].x << bitsTri) | (uint64_t)other[e];
+  vals[e] = e;
+}
+
+__global__ void __launch_bounds__(kThreads) k_uniq_gather(const uint32_t* __restrict__ nUniquePtr,
+                                                          const uint32_t* __restrict__ start,
+                                                          const uint32_t* __restrict__ sortedEntry,
+                                                          const uint4* __restrict__ entries, uint4* __restrict__ uTri,
+                                                          float* __restrict__ uW) {
+  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= *nUniquePtr) return;
+  uint32_t j = start[u];
+  uTri[u] = entries[sortedEntry[j]];
+  uW[u] = 10000.0f * (float)(start[u + 1] - j);  // copies * PointTriangleCollisionConstraint::w (exact in fp32)
 }
 
 // ticket of every (entry, slot): its position in the node's ordered incidence list.  The ordered
@@ -314,7 +339,7 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
   DCHECK(w.floorMult.reserve(n + 1));
   DCHECK(w.floorW.reserve(n + 1));
   DCHECK(w.nodeDone.reserve(n + 1));
-  out.incPtr = (int*)w.incPtr.p; out.floorW = w.floorW.p; out.floorMult = w.floorMult.p; out.nodeDone = w.nodeDone.p;
+  out.floorW = w.floorW.p; out.floorMult = w.floorMult.p; out.nodeDone = w.nodeDone.p;
   if (!nTri) return 0;
   DCHECK(w.triMin.reserve(nTri)); DCHECK(w.triRec.reserve(nTri)); DCHECK(w.cnt.reserve(nTri + 2));
   DCHECK(w.cntRank.reserve(nTri + 2)); DCHECK(w.floorRank.reserve(nTri + 2));
@@ -365,7 +390,7 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
     k_pair_narrow<false><<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p,
                                                                        w.cellStart.p, w.triRec.p, w.triMin.p, w.aabbLo.p,
                                                                        w.aabbHi.p, in.q, in.prev, w.cntRank.p, w.hitCount.p,
-                                                                       nullptr, w.bbox.p + 7); ++L;
+                                                                       nullptr, nullptr, w.bbox.p + 7); ++L;
     L += launchExclusiveScan(s, w.hitCount.p, nPairs + 1, w.scanScratch.p);
     DCHECK(cudaMemcpyAsync(w.host + 10, w.hitCount.p + nPairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     DCHECK(cudaMemcpyAsync(w.host + 12, w.bbox.p + 7, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -373,12 +398,12 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
     w.nCells = (uint32_t)w.host[9];
     if (w.host[12]) { w.failed = true; if (launches) *launches += L; return 0; }
     nHit = (uint32_t)w.host[10];
-    DCHECK(w.triList.reserve(nHit + 1));
+    DCHECK(w.triList.reserve(nHit + 1)); DCHECK(w.otherTri.reserve(nHit + 1));
     if (nHit) {
       k_pair_narrow<true><<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p,
                                                                         w.cellStart.p, w.triRec.p, w.triMin.p, w.aabbLo.p,
                                                                         w.aabbHi.p, in.q, in.prev, w.cntRank.p, w.hitCount.p,
-                                                                        w.triList.p, w.bbox.p + 7); ++L;
+                                                                        w.triList.p, w.otherTri.p, w.bbox.p + 7); ++L;
     }
   }
   DCHECK(w.floorList.reserve(nFloor + 1));
@@ -400,8 +425,29 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
     L += launchExclusiveScan(s, w.incPtr.p, n + 1, w.scanScratch.p);
     L += launchSortPairs(s, nInc, w.incKeys.p, w.incVals.p, w.incTmpKeys.p, w.incTmpVals.p, w.sortHist.p, bitsFor(n));
     k_inc_tickets<<<gridFor(nInc, kThreads), kThreads, 0, s>>>(nInc, w.incKeys.p, w.incVals.p, w.incPtr.p, w.ticket.p); ++L;
-    out.inc = w.incVals.p;
     out.ticket = reinterpret_cast<uint4*>(w.ticket.p);
+    // distinct contacts with multiplicity (sorted by (point, triangle)), then their node incidence table
+    int bitsTri = bitsFor(nTri);
+    DCHECK(w.uTri.reserve(nHit)); DCHECK(w.uW.reserve(nHit)); DCHECK(w.uStart.reserve(nHit + 2)); DCHECK(w.uHeads.reserve(nHit + 2));
+    k_uniq_keys<<<gridFor(nHit, kThreads), kThreads, 0, s>>>(nHit, w.triList.p, w.otherTri.p, bitsTri, w.incKeys.p, w.incVals.p); ++L;
+    L += launchSortPairs(s, nHit, w.incKeys.p, w.incVals.p, w.incTmpKeys.p, w.incTmpVals.p, w.sortHist.p, bitsFor(n) + bitsTri);
+    k_mark_heads<<<gridFor(nHit + 1, kThreads), kThreads, 0, s>>>(nHit, w.incKeys.p, w.uHeads.p); ++L;
+    L += launchExclusiveScan(s, w.uHeads.p, nHit + 1, w.scanScratch.p);
+    k_cell_starts<<<gridFor(nHit, kThreads), kThreads, 0, s>>>(nHit, w.incKeys.p, w.uHeads.p, w.uStart.p); ++L;
+    // uHeads[nHit] = number of distinct contacts (device); the host needs it for the incidence sort
+    k_uniq_gather<<<gridFor(nHit, kThreads), kThreads, 0, s>>>(w.uHeads.p + nHit, w.uStart.p, w.incVals.p, w.triList.p,
+                                                              w.uTri.p, w.uW.p); ++L;
+    DCHECK(cudaMemcpyAsync(w.host + 13, w.uHeads.p + nHit, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    DCHECK(cudaStreamSynchronize(s));
+    uint32_t nU = (uint32_t)w.host[13];
+    uint64_t nUInc = 4ull * nU;
+    DCHECK(w.uIncPtr.reserve(n + 2)); DCHECK(w.uInc.reserve(nUInc)); DCHECK(w.uIncNode.reserve(nUInc));
+    DCHECK(cudaMemsetAsync(w.uIncPtr.p, 0, (n + 2) * sizeof(uint32_t), s));
+    k_inc_emit<<<gridFor(nU, kThreads), kThreads, 0, s>>>(nU, w.uTri.p, w.uIncNode.p, w.uInc.p, w.uIncPtr.p); ++L;
+    L += launchExclusiveScan(s, w.uIncPtr.p, n + 1, w.scanScratch.p);
+    L += launchSortPairs(s, nUInc, w.uIncNode.p, w.uInc.p, w.incTmpKeys.p, w.incTmpVals.p, w.sortHist.p, bitsFor(n));
+    out.uTri = w.uTri.p; out.uW = w.uW.p; out.nUnique = nU; out.incPtr = (int*)w.uIncPtr.p; out.inc = w.uInc.p;
+    w.nUnique = nU; w.nTouched = 0;
   }
   if (nFloor || w.floorDirty) {
     DCHECK(cudaMemsetAsync(w.floorMult.p, 0, (n + 1) * sizeof(uint32_t), s));

@@ -25,7 +25,11 @@ struct DetectWork {
   DevBuf<uint64_t> keys, tmpKeys, incKeys, incTmpKeys;
   DevBuf<uint32_t> vals /* sorted: member triangle of every (cell, member) pair */, tmpVals, heads, cellStart, sortHist,
       incVals, incTmpVals, ticket, nodeDone;
-  DevBuf<uint4> triList;
+  DevBuf<uint4> triList, uTri;     // full list (canonical order) and distinct contacts
+  DevBuf<uint32_t> otherTri, uStart, uHeads, uIncPtr, uInc;
+  DevBuf<uint64_t> uIncNode;
+  DevBuf<float> uW;
+  uint32_t nUnique = 0, nTouched = 0;
   DevBuf<uint32_t> floorList, incPtr, floorMult;
   DevBuf<float> floorW;
   int* host = nullptr;   // pinned, 16 ints

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -264,7 +265,7 @@ int runDetection(PiesB200Solver* s, ContactLists& lists) {
   if (s->detect->failed) { s->simFailed = true; lists.nTri = lists.nFloor = 0; }  // Solver.cpp:852-856
   if (prepareContactSweeps(*s->contact, s->stream, lists) < 0)
     return failCuda(s, cudaErrorMemoryAllocation, "prepareContactSweeps", __LINE__);
-  if (lists.nTri) PIES_CHECK(s, s->contact->contribC.reserve(4ull * lists.nTri));
+  if (lists.nUnique) PIES_CHECK(s, s->contact->contribC.reserve(4ull * lists.nUnique));
   s->stats.triCollisions = lists.nTri;
   s->stats.staticCollisions = lists.nFloor;
   return PIES_B200_OK;
@@ -338,6 +339,7 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
       }
       s->launches += launchPcgFinish(st, pw, n, s->q.p);
       uint32_t used = (uint32_t)s->hostFlag[1];
+      if (getenv("PIES_DEBUG_PCG")) std::fprintf(stderr, "[pcg] sub %u it %u: %u iterations\n", sub, it, used);
       s->lastPcgIters = std::max(1u, used);
       s->stats.pcgIterationsLastTick += used;
       timer.end();

@@ -25,7 +25,7 @@ struct DevBuf {
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
     release();
-    size_t want = n + n / 8 + 64;
+    size_t want = n + n / 2 + 64;  // geometric growth: contact-sized buffers grow a little every substep
     cudaError_t e = cudaMalloc(&p, want * sizeof(T));
     if (e == cudaSuccess) cap = want; else p = nullptr;
     return e;

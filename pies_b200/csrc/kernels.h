@@ -42,7 +42,10 @@ struct ContactLists {
   uint4* tri = nullptr;        // (a, b, c, d): point a against triangle (b, c, d)
   uint32_t* floorNode = nullptr;
   uint32_t nTri = 0, nFloor = 0;
-  // node -> incident point-triangle entries, CSR (value = 4 * entry + slot), entries ascending
+  // distinct (point, triangle) contacts with their weight = copies * 1e4 (the list above holds one copy
+  // per shared cell): what the collision matrix and the right-hand side are built from
+  uint4* uTri = nullptr; float* uW = nullptr; uint32_t nUnique = 0;
+  // node -> incident distinct contacts, CSR (value = 4 * contact + slot), contacts ascending
   int* incPtr = nullptr; uint32_t* inc = nullptr;
   float* floorW = nullptr;     // per node: sum of floor-contact weights (multiplicity * 1e4)
   uint32_t* floorMult = nullptr;

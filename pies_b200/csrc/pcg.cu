@@ -23,7 +23,6 @@ constexpr int kRZ0 = 6;   // r.z, even parity (3)
 constexpr int kRZ1 = 9;   // r.z, odd parity  (3)
 constexpr int kRR = 12;   // r.r             (3)
 
-constexpr float kPtWeight = 10000.0f;  // PointTriangleCollisionConstraint::w (CollisionConstraint.h:32)
 
 // Sum `partials[b*stride + slot + c]` over the fixed producer grid, same order in every CTA.
 __device__ __forceinline__ void reducePartials3(const float* __restrict__ partials, int slot, float (&out)[3],
@@ -67,7 +66,8 @@ __device__ __forceinline__ V3 applyRow(uint32_t i, const CsrMatrix& A, const Con
     int cb = c.incPtr[i], ce = c.incPtr[i + 1];
     for (int k = cb; k < ce; ++k) {
       uint32_t v = c.inc[k];
-      uint4 e = __ldg(c.tri + (v >> 2));
+      uint4 e = __ldg(c.uTri + (v >> 2));
+      float wgt = __ldg(c.uW + (v >> 2));
       uint32_t slot = v & 3u;
       V3 t;
       if (slot == 0) {
@@ -76,7 +76,7 @@ __device__ __forceinline__ V3 applyRow(uint32_t i, const CsrMatrix& A, const Con
       } else {
         t = xi - v3(__ldg(x + e.x));
       }
-      y += kPtWeight * t;
+      y += wgt * t;
     }
   }
   return y;
@@ -102,7 +102,8 @@ __device__ __forceinline__ void applyRowD(uint32_t i, const CsrMatrix& A, const 
     int cb = c.incPtr[i], ce = c.incPtr[i + 1];
     for (int k = cb; k < ce; ++k) {
       uint32_t v = c.inc[k];
-      uint4 e = __ldg(c.tri + (v >> 2));
+      uint4 e = __ldg(c.uTri + (v >> 2));
+      double wgt = (double)__ldg(c.uW + (v >> 2));
       uint32_t slot = v & 3u;
       double t[3];
       if (slot == 0) {
@@ -114,7 +115,7 @@ __device__ __forceinline__ void applyRowD(uint32_t i, const CsrMatrix& A, const 
         float4 xa = __ldg(x + e.x);
         t[0] = (double)xi.x - (double)xa.x; t[1] = (double)xi.y - (double)xa.y; t[2] = (double)xi.z - (double)xa.z;
       }
-      y[0] += (double)kPtWeight * t[0]; y[1] += (double)kPtWeight * t[1]; y[2] += (double)kPtWeight * t[2];
+      y[0] += wgt * t[0]; y[1] += wgt * t[1]; y[2] += wgt * t[2];
     }
   }
 }
