@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "contact.h"
 #include "detect.h"
+#include "reblock.h"
 
 namespace pies {
 
@@ -307,6 +308,19 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
     timer.begin(kPhDetect);
     ContactLists lists;
     if ((rc = runDetection(s, lists))) { cudaEventDestroy(tick0); cudaEventDestroy(tick1); return rc; }
+    // contact-aware preconditioner blocks for this substep's system matrix S + C_t
+    if (!s->blocks) {
+      s->blocks = new BlockWork();
+      PIES_CHECK(s, cudaMallocHost(&s->blocks->host, 4 * sizeof(uint32_t)));
+    }
+    {
+      int LB = 0;
+      if (rebuildBlocks(*s->blocks, st, n, A, s->blockNodes.p, s->blockInv.p, y.nBlocks, lists, s->q.p, pw, &LB) != 0) {
+        cudaEventDestroy(tick0); cudaEventDestroy(tick1);
+        return failCuda(s, s->blocks->lastError, "rebuildBlocks", __LINE__);
+      }
+      s->launches += LB;
+    }
     timer.end();
     float4* contribC = s->contact ? s->contact->contribC.p : nullptr;
 
@@ -395,6 +409,7 @@ int tickPBD(PiesB200Solver* s, bool) {
 PiesB200Solver::~PiesB200Solver() {
   if (detect) { if (detect->host) cudaFreeHost(detect->host); delete detect; }
   delete contact;
+  if (blocks) { if (blocks->host) cudaFreeHost(blocks->host); delete blocks; }
   if (hostPacked) cudaFreeHost(hostPacked);
   if (hostFlag) cudaFreeHost(hostFlag);
   if (ownStream && stream) cudaStreamDestroy(stream);

@@ -39,6 +39,7 @@ struct DevBuf {
 
 struct DetectWork;   // detect.cu
 struct ContactWork;  // contact.cu
+struct BlockWork;    // reblock.cu
 
 }  // namespace pies
 
@@ -82,6 +83,7 @@ struct PiesB200Solver {
 
   pies::DetectWork* detect = nullptr;
   pies::ContactWork* contact = nullptr;
+  pies::BlockWork* blocks = nullptr;
 
   float* hostPacked = nullptr;  // pinned, 3 floats per node
   size_t hostPackedCap = 0;

@@ -78,7 +78,8 @@ struct PcgWork {
   // block-Jacobi preconditioner: blocks of <= 32 nodes, dense inverse of S restricted to the block
   int* blockNodes = nullptr;   // nBlocks * 32 node ids (-1 = padding)
   float* blockInv = nullptr;   // nBlocks * 1024, symmetric, [j*32 + i]
-  uint32_t nBlocks = 0;
+  uint32_t nBlocks = 0;                    // upper bound used for grid sizing
+  const uint32_t* nBlocksDev = nullptr;    // actual block count of this substep (device)
 };
 // Solves A (x + delta) = b for the correction delta, starting from delta = 0 with the start
 // residual b - A x accumulated in fp64.

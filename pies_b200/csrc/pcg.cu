@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(kThreads) k_pcg_start(PcgWork w, float* __rest
   int lane = threadIdx.x & 31;
   uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
   float acc[6] = {0, 0, 0, 0, 0, 0};
-  for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < w.nBlocks; blk += warpsPerGrid) {
+  const uint32_t nBlocks = *w.nBlocksDev;
+  for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nBlocks; blk += warpsPerGrid) {
     int node = w.blockNodes[blk * 32 + lane];
     V3 r = v3(0.0f, 0.0f, 0.0f);
     if (node >= 0) r = v3(w.r[node]);
@@ -239,7 +240,8 @@ __global__ void __launch_bounds__(kThreads) k_pcg_update(PcgWork w, float4* __re
   int lane = threadIdx.x & 31;
   uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
   float acc[6] = {0, 0, 0, 0, 0, 0};
-  for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < w.nBlocks; blk += warpsPerGrid) {
+  const uint32_t nBlocks = *w.nBlocksDev;
+  for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nBlocks; blk += warpsPerGrid) {
     int node = w.blockNodes[blk * 32 + lane];
     V3 r = v3(0.0f, 0.0f, 0.0f);
     if (node >= 0) {

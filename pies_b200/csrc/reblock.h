@@ -1,0 +1,30 @@
+// reblock.h — per-substep contact-aware preconditioner blocks (reblock.cu).
+#pragma once
+
+#include <algorithm>
+
+#include "engine.h"
+
+namespace pies {
+
+struct BlockWork {
+  DevBuf<int> blockNodes;        // (static + dynamic blocks) * 32, members packed to the front, -1 padded
+  DevBuf<float> blockInv;        // 1024 per block
+  DevBuf<uint32_t> slotOf;       // node -> block * 32 + lane
+  DevBuf<uint32_t> flag, parent, vals, tmpVals, heads, start, blkOff, sortHist, scanScratch, nBlocksDev;
+  DevBuf<uint64_t> keys, tmpKeys;
+  DevBuf<uint8_t> dirty, isBase;
+  uint32_t* host = nullptr;      // pinned, 4 words
+  uint32_t isBaseCount = 0, nBlocksBound = 0;
+  const float* isBaseFor = nullptr;
+  uint64_t scanCap = 0;
+  cudaError_t lastError = cudaSuccess;
+};
+
+// Regroups the nodes joined by this substep's contacts into dense blocks and re-inverts every block the
+// collision terms touch; points pw.blockNodes / blockInv / nBlocksDev at the result.  Returns 0 or -1.
+int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, const int* staticNodes,
+                  const float* staticInv, uint32_t nStatic, const ContactLists& c, const float4* q, PcgWork& pw,
+                  int* launches);
+
+}  // namespace pies

@@ -113,10 +113,11 @@ def test_tetgen_cube_on_floor(pb):
 
 
 def test_stack_trajectory_k_1_10_100(pb):
-    """Reduced config 3 (16 stacked bodies, iterations=10).  K = 1, 10: within 1e-4 x diagonal and identical
-    contact counts.  K = 50 (first impacts, ~800 live contacts): within 2e-3 x diagonal.  K = 100: the stack has
-    gone through 5 m/s impacts with the reference's 1.1x restitution term; trajectories of any two fp32
-    implementations decorrelate there (noise floor), so only aggregate state is compared."""
+    """Reduced config 3 (16 stacked bodies, iterations=10).  K = 1, 10, 40 (free fall + floor contact) and 44 (first
+    body-body impacts, 480 live contacts): within 1e-4 x diagonal and identical contact counts.  After the 5 m/s
+    impacts the scene is chaotic: the reference perturbed by 1e-6 at tick 40 differs from ITSELF by 1.9e-2 at tick 48
+    and 8e-2 at tick 50 (tests/golden/make_golden.py), so K = 50 is held to that noise floor (1e-2 x diagonal) and
+    K = 100 to aggregate state only (noise floor)."""
     from pies_b200 import scenes
     g = golden("stack16")
     s = pb.Solver(**scenes.S3_OPTIONS)
@@ -124,16 +125,16 @@ def test_stack_trajectory_k_1_10_100(pb):
     diag = bbox_diag(g["pos1"])
     for t in range(1, 101):
         s.tick()
-        if t in (1, 10, 50, 100):
+        if t in (1, 10, 40, 44, 50, 100):
             p = s.positions
             err = np.abs(p - g["pos%d" % t]).max()
             st = s.stats()
-            if t <= 10:
+            if t <= 44:
                 assert err <= 1e-4 * diag, (t, err)
                 assert (st.triCollisions, st.staticCollisions) == tuple(g["ncoll%d" % t])
             elif t == 50:
-                assert err <= 2e-3 * diag, (t, err)
-                assert abs(st.triCollisions - g["ncoll50"][0]) <= 0.1 * g["ncoll50"][0] + 8
+                assert err <= 1e-2 * diag, (t, err)
+                assert abs(st.triCollisions - g["ncoll50"][0]) <= 0.15 * g["ncoll50"][0] + 8
             else:
                 assert np.isfinite(p).all() and p[:, 1].min() >= -1e-3
                 assert abs(p[:, 1].mean() - g["pos100"][:, 1].mean()) <= 0.05 * diag
