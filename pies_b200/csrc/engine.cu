@@ -153,9 +153,10 @@ int ensureBuilt(PiesB200Solver* s) {
   cudaStream_t st = s->stream;
   if ((rc = uploadState(s))) return rc;
   PIES_CHECK(s, s->msn.reserve(n)); PIES_CHECK(s, s->rhs.reserve(n)); PIES_CHECK(s, s->snap.reserve(n));
-  PIES_CHECK(s, s->pr.reserve(n)); PIES_CHECK(s, s->pp.reserve(n)); PIES_CHECK(s, s->pz.reserve(n)); PIES_CHECK(s, s->pap.reserve(n)); PIES_CHECK(s, s->pdelta.reserve(n));
-  PIES_CHECK(s, s->partials.reserve((size_t)kReduceBlocks * 16)); PIES_CHECK(s, s->scalars.reserve(16)); PIES_CHECK(s, s->flag.reserve(4));
-  PIES_CHECK(s, cudaMemsetAsync(s->partials.p, 0, (size_t)kReduceBlocks * 16 * sizeof(float), st));
+  PIES_CHECK(s, s->pr.reserve(n)); PIES_CHECK(s, s->pp.reserve(n)); PIES_CHECK(s, s->pp2.reserve(n)); PIES_CHECK(s, s->pz.reserve(n)); PIES_CHECK(s, s->pap.reserve(n)); PIES_CHECK(s, s->pdelta.reserve(n));
+  PIES_CHECK(s, s->partials.reserve((size_t)kReduceBlocks * 32)); PIES_CHECK(s, s->scalars.reserve(64)); PIES_CHECK(s, s->flag.reserve(4));
+  PIES_CHECK(s, cudaMemsetAsync(s->partials.p, 0, (size_t)kReduceBlocks * 32 * sizeof(float), st));
+  PIES_CHECK(s, cudaMemsetAsync(s->scalars.p, 0, 64 * sizeof(float), st));
   PIES_CHECK(s, cudaMemsetAsync(s->flag.p, 0, 4 * sizeof(int), st));
   PIES_CHECK(s, cudaMemsetAsync(s->snap.p, 0, (size_t)n * sizeof(float4), st));
   PIES_CHECK(s, s->contrib.reserve(y.nContrib + 1));
@@ -190,6 +191,7 @@ int ensureBuilt(PiesB200Solver* s) {
   sc.goalXformDirty = false;
   PIES_CHECK(s, uploadVec(s->incPtr, y.incPtr, st)); PIES_CHECK(s, uploadVec(s->inc, y.inc, st));
   PIES_CHECK(s, uploadVec(s->rowPtr, y.rowPtr, st)); PIES_CHECK(s, uploadVec(s->col, y.col, st)); PIES_CHECK(s, uploadVec(s->val, y.val, st));
+  PIES_CHECK(s, uploadVec(s->rowBatch, y.rowBatch, st));
   PIES_CHECK(s, uploadVec(s->blockNodes, y.blockNodes, st)); PIES_CHECK(s, uploadVec(s->blockInv, y.blockInv, st));
   PIES_CHECK(s, uploadVec(s->triIds, sc.triangles, st));
   PIES_CHECK(s, cudaStreamSynchronize(st));
@@ -297,8 +299,11 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
   BendElems be{s->bendIds.p, s->bendAngleW.p, (uint32_t)s->scene.bendW.size()};
   ClusterElems sh{s->shapeOff.p, s->shapeIds.p, (uint32_t)s->scene.shapeW.size(), (uint32_t)s->scene.shapeId.size()};
   ClusterElems go{s->goalOff.p, s->goalIds.p, (uint32_t)s->scene.goalW.size(), (uint32_t)s->scene.goalId.size()};
-  CsrMatrix A{s->rowPtr.p, s->col.p, s->val.p, n, (uint64_t)y.col.size()};
-  PcgWork pw{s->pr.p, s->pp.p, s->pz.p, s->pap.p, s->pdelta.p, s->partials.p, s->scalars.p, s->flag.p, s->blockNodes.p, s->blockInv.p, y.nBlocks};
+  CsrMatrix A{s->rowPtr.p, s->col.p, s->val.p, n, (uint64_t)y.col.size(), s->rowBatch.p,
+              (uint32_t)(y.rowBatch.empty() ? 0 : y.rowBatch.size() - 1)};
+  PcgWork pw;
+  pw.r = s->pr.p; pw.p = s->pp.p; pw.p2 = s->pp2.p; pw.z = s->pz.p; pw.ap = s->pap.p; pw.delta = s->pdelta.p;
+  pw.partials = s->partials.p; pw.scalars = s->scalars.p; pw.flag = s->flag.p;
 
   for (uint32_t sub = 0; sub < o.timeSubsteps; ++sub) {
     timer.begin(kPhOther);
@@ -340,16 +345,20 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
 
       timer.begin(kPhGlobal);
       s->launches += launchPcgInit(st, A, lists, pw, s->rhs.p, s->q.p, s->tune.pcgTolerance);
-      uint32_t done = 0, burst = std::max(1u, s->lastPcgIters);
+      // Iterations are enqueued in bursts without host round trips: converged solves turn the remaining
+      // launches into early exits (~2 us each), a host poll costs ~40 us of idle GPU, so the first burst
+      // slightly overshoots the previous solve's count.
+      uint32_t done = 0, burst = s->lastPcgIters + 2;
       bool converged = false;
       while (!converged && done < s->tune.pcgMaxIterations) {
         uint32_t todo = std::min(burst, s->tune.pcgMaxIterations - done);
-        for (uint32_t k = 0; k < todo; ++k) s->launches += launchPcgIteration(st, A, lists, pw, s->tune.pcgTolerance, (int)((done + k) & 1u));
+        for (uint32_t k = 0; k < todo; ++k) s->launches += launchPcgIteration(st, A, lists, pw, s->tune.pcgTolerance, (int)(done + k));
         done += todo;
+        s->launches += launchPcgCheck(st, pw, s->tune.pcgTolerance, (int)done - 1);
         PIES_CHECK(s, cudaMemcpyAsync(s->hostFlag, s->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         PIES_CHECK(s, cudaStreamSynchronize(st));
         converged = s->hostFlag[0] != 0;
-        burst = std::max(1u, s->tune.pcgCheckEvery);
+        burst = std::max(4u, s->tune.pcgCheckEvery);
       }
       s->launches += launchPcgFinish(st, pw, n, s->q.p);
       uint32_t used = (uint32_t)s->hostFlag[1];

@@ -63,7 +63,7 @@ struct PiesB200Solver {
   uint32_t n = 0;
   pies::HostSystem sys;
   pies::DevBuf<float4> q, prev, vel, msn, rhs, contrib, snap;
-  pies::DevBuf<float4> pr, pp, pz, pap, pdelta;
+  pies::DevBuf<float4> pr, pp, pp2, pz, pap, pdelta;
   pies::DevBuf<float> partials, scalars;
   pies::DevBuf<int> flag;
   pies::DevBuf<uint4> elemIds;
@@ -75,6 +75,7 @@ struct PiesB200Solver {
   pies::DevBuf<float> shapeW, goalMat, goalXform, goalW;
   pies::DevBuf<int> incPtr; pies::DevBuf<uint32_t> inc;
   pies::DevBuf<int> rowPtr, col; pies::DevBuf<float> val;
+  pies::DevBuf<uint32_t> rowBatch;
   pies::DevBuf<int> blockNodes; pies::DevBuf<float> blockInv;
   pies::DevBuf<uint32_t> triIds;  // 3 per triangle
   pies::DevBuf<float> packed;     // 3 floats per node, readback staging

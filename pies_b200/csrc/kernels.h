@@ -35,7 +35,11 @@ struct ClusterElems {  // shape- and goal-matching clusters (CSR over members)
 };
 
 // CSR of S = M/h^2 + sum w A^T A (Solver.cpp:174-210), both triangles.
-struct CsrMatrix { int* rowPtr = nullptr; int* col = nullptr; float* val = nullptr; uint32_t n = 0; uint64_t nnz = 0; };
+struct CsrMatrix {
+  int* rowPtr = nullptr; int* col = nullptr; float* val = nullptr; uint32_t n = 0; uint64_t nnz = 0;
+  // row batches of the CSR-stream mat-vec (system.h)
+  uint32_t* rowBatch = nullptr; uint32_t nBatches = 0;
+};
 
 // Per-substep collision lists in the reference's canonical order.
 struct ContactLists {
@@ -71,13 +75,15 @@ int launchVelocityUpdate(cudaStream_t s, uint32_t n, const float4* q, float4* pr
 
 // ------------------------------------------------------------------ PCG -----
 struct PcgWork {
-  float4 *r = nullptr, *p = nullptr, *z = nullptr, *ap = nullptr, *delta = nullptr;
-  float* partials = nullptr;   // kReduceBlocks * 16 floats
+  float4 *r = nullptr, *p = nullptr, *p2 = nullptr, *z = nullptr, *ap = nullptr, *delta = nullptr;
+  float* partials = nullptr;   // kReduceBlocks * 32 floats
   float* scalars = nullptr;    // see pcg.cu
-  int* flag = nullptr;         // [0] converged, [1] iterations done
-  // block-Jacobi preconditioner: blocks of <= 32 nodes, dense inverse of S restricted to the block
-  int* blockNodes = nullptr;   // nBlocks * 32 node ids (-1 = padding)
-  float* blockInv = nullptr;   // nBlocks * 1024, symmetric, [j*32 + i]
+  int* flag = nullptr;         // [0] converged, [1] iterations done, [2] ticket counter of the grid reductions
+  // block-Jacobi preconditioner (rebuilt per substep, reblock.cu): blocks of m <= 32 nodes, dense inverse of
+  // S + C_t restricted to the block
+  int* blockNodes = nullptr;   // nBlocks * 32 node ids, members first (-1 = padding)
+  float* blockInv = nullptr;   // per block m x m, symmetric, [j*m + i], at blockOff[b]
+  const uint2* blockMeta = nullptr;        // per block: (offset into blockInv in floats, m)
   uint32_t nBlocks = 0;                    // upper bound used for grid sizing
   const uint32_t* nBlocksDev = nullptr;    // actual block count of this substep (device)
 };
@@ -85,9 +91,9 @@ struct PcgWork {
 // residual b - A x accumulated in fp64.
 int launchPcgInit(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w,
                   const float4* b, const float4* x, float tol);
-// parity = iteration index & 1 (selects the double-buffered r.z partial slot)
-int launchPcgIteration(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, float tol,
-                       int parity);
+// it = iteration index within the solve (parity selects the double-buffered r.z slot and direction buffer)
+int launchPcgIteration(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, float tol, int it);
+int launchPcgCheck(cudaStream_t s, const PcgWork& w, float tol, int lastIt);
 // x += delta: the correction is accumulated separately and added with a single rounding
 int launchPcgFinish(cudaStream_t s, const PcgWork& w, uint32_t n, float4* x);
 

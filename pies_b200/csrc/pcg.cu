@@ -15,28 +15,47 @@
 
 namespace pies {
 
-constexpr int kPartialStride = 16;
-// partial slots
-constexpr int kPA = 0;    // p.Ap            (3)   written by spmv
-constexpr int kBB = 3;    // b.b             (3)   written by residual
-constexpr int kRZ0 = 6;   // r.z, even parity (3)
-constexpr int kRZ1 = 9;   // r.z, odd parity  (3)
-constexpr int kRR = 12;   // r.r             (3)
+constexpr int kPartialStride = 20;
+// partial / sum slots: per-CTA partials live at partials[cta * kPartialStride + slot]; the last CTA of every
+// producing kernel reduces them in a fixed order into scalars[kSums + slot], which the consumers read.
+constexpr int kPA = 0;    // p.Ap                      (3)   written by spmv
+constexpr int kBB = 3;    // b.b                       (3)   written by residual
+constexpr int kSet0 = 6;  // r.z (3) + r.r (3), written by even iterations
+constexpr int kSet1 = 12; // r.z (3) + r.r (3), written by odd iterations and by start ("iteration -1")
+constexpr int kSums = 16; // offset of the reduced sums inside `scalars`
 
-
-// Sum `partials[b*stride + slot + c]` over the fixed producer grid, same order in every CTA.
-__device__ __forceinline__ void reducePartials3(const float* __restrict__ partials, int slot, float (&out)[3],
-                                                float* smem /* >= 96 + 3 floats */) {
-  float v[3] = {0.0f, 0.0f, 0.0f};
-  for (int b = threadIdx.x; b < kReduceBlocks; b += blockDim.x) {
-    const float* p = partials + b * kPartialStride + slot;
-    v[0] += p[0]; v[1] += p[1]; v[2] += p[2];
+// Deterministic grid reduction without a second launch: every CTA publishes its partials, takes a ticket, and
+// the CTA holding the last ticket sums all partials in a fixed order (independent of which CTA that is).
+template <int K>
+__device__ __forceinline__ void lastBlockReduce(float* __restrict__ partials, int slot, float* __restrict__ scalars,
+                                                int* __restrict__ flag, float* smem /* K * 32 floats */) {
+  __shared__ int sLast;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned t = atomicAdd(reinterpret_cast<unsigned*>(flag + 2), 1u);
+    sLast = t == gridDim.x - 1 ? 1 : 0;
   }
-  blockSum<3>(v, smem);
-  if (threadIdx.x == 0) { smem[96] = v[0]; smem[97] = v[1]; smem[98] = v[2]; }
   __syncthreads();
-  out[0] = smem[96]; out[1] = smem[97]; out[2] = smem[98];
-  __syncthreads();
+  if (!sLast) return;
+  __threadfence();
+  float v[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = 0.0f;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+    const float* p = partials + b * kPartialStride + slot;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] += __ldcg(p + k);
+  }
+  blockSum<K>(v, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) scalars[kSums + slot + k] = v[k];
+    flag[2] = 0;
+  }
+}
+
+__device__ __forceinline__ void readSums3(const float* __restrict__ scalars, int slot, float (&out)[3]) {
+  out[0] = scalars[kSums + slot]; out[1] = scalars[kSums + slot + 1]; out[2] = scalars[kSums + slot + 2];
 }
 
 // CTA-uniform early exit once the solve has converged (lets the host enqueue a fixed
@@ -124,7 +143,7 @@ __device__ __forceinline__ void applyRowD(uint32_t i, const CsrMatrix& A, const 
 __global__ void __launch_bounds__(kThreads) k_pcg_residual(CsrMatrix A, ContactLists c, const float4* __restrict__ b,
                                                            const float4* __restrict__ x, float4* __restrict__ r,
                                                            float4* __restrict__ delta, float* __restrict__ partials,
-                                                           int* __restrict__ flag) {
+                                                           float* __restrict__ scalars, int* __restrict__ flag) {
   __shared__ float smem[128];
   float bb[3] = {0.0f, 0.0f, 0.0f};
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
@@ -142,6 +161,7 @@ __global__ void __launch_bounds__(kThreads) k_pcg_residual(CsrMatrix A, ContactL
     p[0] = bb[0]; p[1] = bb[1]; p[2] = bb[2];
     if (blockIdx.x == 0) { flag[0] = 0; flag[1] = 0; }
   }
+  lastBlockReduce<3>(partials, kBB, scalars, flag, smem);
 }
 
 // x += delta, once per solve (single rounding of the accumulated correction)
@@ -152,71 +172,170 @@ __global__ void __launch_bounds__(kThreads) k_pcg_finish(uint32_t n, float4* __r
   x[i] = make_float4(xv.x + d.x, xv.y + d.y, xv.z + d.z, xv.w);
 }
 
-// Warp-per-block preconditioner application on registers: z_lane = sum_j Minv[j][lane] r_j.
-__device__ __forceinline__ V3 applyBlockInv(const float* __restrict__ inv, V3 r, int lane) {
+// Warp-per-block preconditioner application.  The block's m x m inverse is contiguous (<= 4 KB): every lane
+// issues its up-to-8 independent 16 B loads at once (4 KB in flight per warp keeps HBM busy; a row-by-row
+// loop does not), parks them in shared memory, and the mat-vec z_lane = sum_j Minv[j][lane] r_j runs from there.
+constexpr int kPcgWarps = kThreads / 32;
+
+// Asynchronous global -> shared copy of the block's inverse (cp.async, 16 B per lane per step, no registers held).
+__device__ __forceinline__ void issueBlockInv(float* __restrict__ sInv, const float* __restrict__ inv, int m, int lane) {
+  const int size4 = (m * m + 3) >> 2;
+  __syncwarp();  // the previous block's reads of this buffer are finished
+  uint32_t dst = (uint32_t)__cvta_generic_to_shared(sInv) + 16u * lane;
+  const float4* src = reinterpret_cast<const float4*>(inv) + lane;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    if (lane + 32 * t < size4)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u * t), "l"(src + 32 * t) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ V3 applyBlockInv(const float* __restrict__ sInv, V3 r, int lane, int m) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
   V3 z = v3(0.0f, 0.0f, 0.0f);
-#pragma unroll 8
-  for (int j = 0; j < 32; ++j) {
-    float m = __ldg(inv + j * 32 + lane);
-    z.x += m * __shfl_sync(0xffffffffu, r.x, j);
-    z.y += m * __shfl_sync(0xffffffffu, r.y, j);
-    z.z += m * __shfl_sync(0xffffffffu, r.z, j);
+  const int col = lane < m ? lane : 0;
+#pragma unroll 4
+  for (int j = 0; j < m; ++j) {
+    float mv = sInv[j * m + col];
+    z.x += mv * __shfl_sync(0xffffffffu, r.x, j);
+    z.y += mv * __shfl_sync(0xffffffffu, r.y, j);
+    z.z += mv * __shfl_sync(0xffffffffu, r.z, j);
   }
   return z;
 }
 
-// z = Minv r ; p = z ; partial r.z (odd parity slot = "iteration -1") and r.r
-__global__ void __launch_bounds__(kThreads) k_pcg_start(PcgWork w, float* __restrict__ partials) {
+// z = Minv r ; partial r.z (odd parity slot = "iteration -1") and r.r
+__global__ void __launch_bounds__(kThreads, 4) k_pcg_start(PcgWork w, float* __restrict__ partials) {
   __shared__ float smem[6 * 32];
+  __shared__ __align__(16) float sInv[kPcgWarps][1024];
   int lane = threadIdx.x & 31;
   uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
   float acc[6] = {0, 0, 0, 0, 0, 0};
   const uint32_t nBlocks = *w.nBlocksDev;
   for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nBlocks; blk += warpsPerGrid) {
     int node = w.blockNodes[blk * 32 + lane];
+    const uint2 meta = w.blockMeta[blk];
+    const int m = (int)meta.y;
+    issueBlockInv(sInv[threadIdx.x >> 5], w.blockInv + meta.x, m, lane);
     V3 r = v3(0.0f, 0.0f, 0.0f);
     if (node >= 0) r = v3(w.r[node]);
-    V3 z = applyBlockInv(w.blockInv + (size_t)blk * 1024, r, lane);
+    V3 z = applyBlockInv(sInv[threadIdx.x >> 5], r, lane, m);
     if (node >= 0) {
       w.z[node] = f4(z, 0.0f);
-      w.p[node] = f4(z, 0.0f);
       acc[0] += r.x * z.x; acc[1] += r.y * z.y; acc[2] += r.z * z.z;
       acc[3] += r.x * r.x; acc[4] += r.y * r.y; acc[5] += r.z * r.z;
     }
   }
   blockSum<6>(acc, smem);
   if (threadIdx.x == 0) {
-    float* p = partials + blockIdx.x * kPartialStride;
-    p[kRZ1] = acc[0]; p[kRZ1 + 1] = acc[1]; p[kRZ1 + 2] = acc[2];
-    p[kRR] = acc[3]; p[kRR + 1] = acc[4]; p[kRR + 2] = acc[5];
+    float* p = partials + blockIdx.x * kPartialStride + kSet1;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) p[k] = acc[k];
   }
+  lastBlockReduce<6>(partials, kSet1, w.scalars, w.flag, smem);
 }
 
-// Convergence test on the start residual (so an already-solved system costs no iteration).
-__global__ void __launch_bounds__(kThreads) k_pcg_check(const float* __restrict__ partials, float* __restrict__ scalars,
-                                                        int* __restrict__ flag, float tol2) {
-  __shared__ float smem[128];
+// Convergence test on the latest residual norm (after start, or after the last enqueued iteration).
+__global__ void k_pcg_check(float* __restrict__ scalars, int* __restrict__ flag, int set, float tol2) {
   float bb[3], rr[3];
-  reducePartials3(partials, kBB, bb, smem);
-  reducePartials3(partials, kRR, rr, smem);
-  if (threadIdx.x == 0) {
-    bool conv = rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2];
-    float rel = 0.0f;
-    for (int k = 0; k < 3; ++k) if (bb[k] > 0.0f) rel = fmaxf(rel, rr[k] / bb[k]);
-    scalars[0] = sqrtf(rel);
-    if (conv) flag[0] = 1;
-  }
+  readSums3(scalars, kBB, bb);
+  readSums3(scalars, set + 3, rr);
+  bool conv = rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2];
+  float rel = 0.0f;
+  for (int k = 0; k < 3; ++k) if (bb[k] > 0.0f) rel = fmaxf(rel, rr[k] / bb[k]);
+  scalars[0] = sqrtf(rel);
+  if (conv) flag[0] = 1;
 }
 
-// (A) ap = A p ; partial p.ap
-__global__ void __launch_bounds__(kThreads) k_pcg_spmv(CsrMatrix A, ContactLists c, PcgWork w,
-                                                       float* __restrict__ partials) {
+// (A) w = A z as a CSR-stream product over host-built row batches (system.h), then locally beta = rz_new / rz_old ; p = z + beta p ;
+// ap = w + beta ap (A p by recurrence: A (z + beta p) = A z + beta A p) ; partial p.ap.  Every CTA first
+// re-evaluates the convergence test of the previous iteration from the same partials, so they all agree.
+// The solve is for the correction delta with an fp64 start residual, so only a few digits are asked of
+// this recurrence.
+constexpr int kSpmvTile = 2048;  // == HostSystem::kBatchNnz: products of one row batch, 24 KB of shared memory
+
+__global__ void __launch_bounds__(kThreads) k_pcg_spmv(CsrMatrix A, ContactLists c, PcgWork w, float* __restrict__ partials,
+                                                       int parity, int first, float tol2) {
   __shared__ float smem[128];
+  __shared__ float sProdX[kSpmvTile], sProdY[kSpmvTile], sProdZ[kSpmvTile];
   if (ctaConverged(w.flag)) return;
+  float rzNew[3], rzOld[3], rr[3], bb[3], beta[3] = {0.0f, 0.0f, 0.0f};
+  const int prevSet = parity ? kSet0 : kSet1, olderSet = parity ? kSet1 : kSet0;
+  readSums3(w.scalars, prevSet, rzNew);  // r.z and r.r written by the previous update (or start)
+  readSums3(w.scalars, prevSet + 3, rr);
+  readSums3(w.scalars, kBB, bb);
+  if (rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2]) return;  // the update latches the flag
+  if (!first) {
+    readSums3(w.scalars, olderSet, rzOld);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) beta[k] = rzOld[k] > 0.0f ? rzNew[k] / rzOld[k] : 0.0f;
+  }
+  const float4* __restrict__ z = w.z;
   float pap[3] = {0.0f, 0.0f, 0.0f};
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
-    V3 pi = v3(w.p[i]);
-    V3 y = applyRow(i, A, c, w.p, pi);
+  for (uint32_t b = blockIdx.x; b < A.nBatches; b += gridDim.x) {
+    const uint32_t r0 = A.rowBatch[b], r1 = A.rowBatch[b + 1];
+    const int e0 = A.rowPtr[r0], e1 = A.rowPtr[r1];
+    const uint32_t row = r0 + threadIdx.x;
+    const bool haveRow = row < r1;
+    int rb = 0, re = 0;
+    float4 zi = make_float4(0.0f, 0.0f, 0.0f, 0.0f), po = zi, apo = zi;
+    if (haveRow) {
+      rb = A.rowPtr[row]; re = A.rowPtr[row + 1];
+      zi = z[row];
+      if (!first) { po = w.p[row]; apo = w.ap[row]; }
+    }
+    V3 y = v3(0.0f, 0.0f, 0.0f);
+    for (int cs = e0; cs < e1; cs += kSpmvTile) {  // one pass unless a single row overflows the tile
+      const int ce = min(e1, cs + kSpmvTile);
+      // stream: coalesced (col, val), gather z, park the products
+      for (int e = cs + (int)threadIdx.x; e < ce; e += 4 * kThreads) {
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        const bool h1 = e + kThreads < ce, h2 = e + 2 * kThreads < ce, h3 = e + 3 * kThreads < ce;
+        c0 = __ldcs(A.col + e); a0 = __ldcs(A.val + e);
+        if (h1) { c1 = __ldcs(A.col + e + kThreads); a1 = __ldcs(A.val + e + kThreads); }
+        if (h2) { c2 = __ldcs(A.col + e + 2 * kThreads); a2 = __ldcs(A.val + e + 2 * kThreads); }
+        if (h3) { c3 = __ldcs(A.col + e + 3 * kThreads); a3 = __ldcs(A.val + e + 3 * kThreads); }
+        float4 x0 = __ldg(z + c0), x1 = __ldg(z + c1), x2 = __ldg(z + c2), x3 = __ldg(z + c3);
+        int o = e - cs;
+        sProdX[o] = a0 * x0.x; sProdY[o] = a0 * x0.y; sProdZ[o] = a0 * x0.z;
+        if (h1) { o += kThreads; sProdX[o] = a1 * x1.x; sProdY[o] = a1 * x1.y; sProdZ[o] = a1 * x1.z; }
+        if (h2) { o += kThreads; sProdX[o] = a2 * x2.x; sProdY[o] = a2 * x2.y; sProdZ[o] = a2 * x2.z; }
+        if (h3) { o += kThreads; sProdX[o] = a3 * x3.x; sProdY[o] = a3 * x3.y; sProdZ[o] = a3 * x3.z; }
+      }
+      __syncthreads();
+      if (haveRow) {  // per-row sum in CSR order
+        int kb = max(rb, cs), ke = min(re, ce);
+        for (int k = kb; k < ke; ++k) { y.x += sProdX[k - cs]; y.y += sProdY[k - cs]; y.z += sProdZ[k - cs]; }
+      }
+      __syncthreads();
+    }
+    if (!haveRow) continue;
+    const uint32_t i = row;
+    if (c.nFloor) {
+      float fw = c.floorW[i];
+      y.x += fw * zi.x; y.y += fw * zi.y; y.z += fw * zi.z;
+    }
+    if (c.nTri) {
+      int cb = c.incPtr[i], ce2 = c.incPtr[i + 1];
+      for (int kk = cb; kk < ce2; ++kk) {
+        uint32_t v = c.inc[kk];
+        uint4 e = __ldg(c.uTri + (v >> 2));
+        float wgt = __ldg(c.uW + (v >> 2));
+        V3 t;
+        if ((v & 3u) == 0u) t = 3.0f * v3(zi) - v3(__ldg(z + e.y)) - v3(__ldg(z + e.z)) - v3(__ldg(z + e.w));
+        else t = v3(zi) - v3(__ldg(z + e.x));
+        y += wgt * t;
+      }
+    }
+    V3 pi = v3(zi);
+    if (!first) {
+      pi = v3(fmaf(beta[0], po.x, zi.x), fmaf(beta[1], po.y, zi.y), fmaf(beta[2], po.z, zi.z));
+      y = v3(fmaf(beta[0], apo.x, y.x), fmaf(beta[1], apo.y, y.y), fmaf(beta[2], apo.z, y.z));
+    }
+    w.p[i] = f4(pi, 0.0f);
     w.ap[i] = f4(y, 0.0f);
     pap[0] += pi.x * y.x; pap[1] += pi.y * y.y; pap[2] += pi.z * y.z;
   }
@@ -225,35 +344,60 @@ __global__ void __launch_bounds__(kThreads) k_pcg_spmv(CsrMatrix A, ContactLists
     float* p = partials + blockIdx.x * kPartialStride + kPA;
     p[0] = pap[0]; p[1] = pap[1]; p[2] = pap[2];
   }
+  lastBlockReduce<3>(partials, kPA, w.scalars, w.flag, smem);
 }
 
-// (B) alpha = rz / pAp ; delta += alpha p ; r -= alpha ap ; z = Minv r ; partial r.z (parity slot), r.r
-__global__ void __launch_bounds__(kThreads) k_pcg_update(PcgWork w, float4* __restrict__ x,
-                                                         float* __restrict__ partials, int parity) {
+// (B) alpha = rz / pAp ; delta += alpha p ; r -= alpha ap ; z = Minv r ; partial r.z (parity slot), r.r.
+// Re-evaluates the same convergence test as (A) first: if (A) stopped, this stops too and CTA 0 latches the flag.
+__global__ void __launch_bounds__(kThreads, 4) k_pcg_update(PcgWork w, float4* __restrict__ x, float* __restrict__ partials,
+                                                         int parity, float tol2) {
   __shared__ float smem[6 * 32];
+  __shared__ __align__(16) float sInv[kPcgWarps][1024];
   if (ctaConverged(w.flag)) return;
-  float rz[3], pap[3], alpha[3];
-  reducePartials3(partials, parity ? kRZ0 : kRZ1, rz, smem);  // r.z of the previous step
-  reducePartials3(partials, kPA, pap, smem);
+  float rz[3], pap[3], alpha[3], rr[3], bb[3];
+  const int prevSet = parity ? kSet0 : kSet1, mySet = parity ? kSet1 : kSet0;
+  readSums3(w.scalars, prevSet + 3, rr);
+  readSums3(w.scalars, kBB, bb);
+  if (rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2]) {
+    // Late CTAs may already see the flag and leave through ctaConverged: same outcome.
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      float rel = 0.0f;
+      for (int k = 0; k < 3; ++k) if (bb[k] > 0.0f) rel = fmaxf(rel, rr[k] / bb[k]);
+      w.scalars[0] = sqrtf(rel);
+      w.flag[0] = 1;
+    }
+    return;
+  }
+  readSums3(w.scalars, prevSet, rz);  // r.z of the previous step
+  readSums3(w.scalars, kPA, pap);
 #pragma unroll
   for (int k = 0; k < 3; ++k) alpha[k] = pap[k] > 0.0f ? rz[k] / pap[k] : 0.0f;
   int lane = threadIdx.x & 31;
   uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
   float acc[6] = {0, 0, 0, 0, 0, 0};
   const uint32_t nBlocks = *w.nBlocksDev;
-  for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nBlocks; blk += warpsPerGrid) {
-    int node = w.blockNodes[blk * 32 + lane];
+  uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // software pipeline: the next block's membership and location are fetched while this block is processed
+  int nodeNext = -1;
+  uint2 metaNext = make_uint2(0u, 0u);
+  if (blk < nBlocks) { nodeNext = w.blockNodes[blk * 32 + lane]; metaNext = w.blockMeta[blk]; }
+  for (; blk < nBlocks; blk += warpsPerGrid) {
+    const int node = nodeNext;
+    const int m = (int)metaNext.y;
+    issueBlockInv(sInv[threadIdx.x >> 5], w.blockInv + metaNext.x, m, lane);
     V3 r = v3(0.0f, 0.0f, 0.0f);
+    float4 xv, pv4, ap4, r4;
+    if (node >= 0) { xv = x[node]; pv4 = w.p[node]; ap4 = w.ap[node]; r4 = w.r[node]; }
+    if (blk + warpsPerGrid < nBlocks) { nodeNext = w.blockNodes[(blk + warpsPerGrid) * 32 + lane]; metaNext = w.blockMeta[blk + warpsPerGrid]; }
     if (node >= 0) {
-      float4 xv = x[node];
-      V3 p = v3(w.p[node]), ap = v3(w.ap[node]);
-      r = v3(w.r[node]);
-      xv.x += alpha[0] * p.x; xv.y += alpha[1] * p.y; xv.z += alpha[2] * p.z;
+      V3 pv = v3(pv4), ap = v3(ap4);
+      r = v3(r4);
+      xv.x += alpha[0] * pv.x; xv.y += alpha[1] * pv.y; xv.z += alpha[2] * pv.z;
       r.x -= alpha[0] * ap.x; r.y -= alpha[1] * ap.y; r.z -= alpha[2] * ap.z;
       x[node] = xv;
       w.r[node] = f4(r, 0.0f);
     }
-    V3 z = applyBlockInv(w.blockInv + (size_t)blk * 1024, r, lane);
+    V3 z = applyBlockInv(sInv[threadIdx.x >> 5], r, lane, m);
     if (node >= 0) {
       w.z[node] = f4(z, 0.0f);
       acc[0] += r.x * z.x; acc[1] += r.y * z.y; acc[2] += r.z * z.z;
@@ -262,55 +406,34 @@ __global__ void __launch_bounds__(kThreads) k_pcg_update(PcgWork w, float4* __re
   }
   blockSum<6>(acc, smem);
   if (threadIdx.x == 0) {
-    float* p = partials + blockIdx.x * kPartialStride;
-    int s = parity ? kRZ1 : kRZ0;
-    p[s] = acc[0]; p[s + 1] = acc[1]; p[s + 2] = acc[2];
-    p[kRR] = acc[3]; p[kRR + 1] = acc[4]; p[kRR + 2] = acc[5];
-  }
-}
-
-// (C) beta = rz_new / rz_old ; p = z + beta p ; CTA 0 records convergence
-__global__ void __launch_bounds__(kThreads) k_pcg_direction(PcgWork w, uint32_t n, float* __restrict__ partials,
-                                                            int parity, float tol2) {
-  __shared__ float smem[128];
-  if (ctaConverged(w.flag)) return;
-  float rzNew[3], rzOld[3], rr[3], bb[3], beta[3];
-  reducePartials3(partials, parity ? kRZ1 : kRZ0, rzNew, smem);
-  reducePartials3(partials, parity ? kRZ0 : kRZ1, rzOld, smem);
-  reducePartials3(partials, kRR, rr, smem);
-  reducePartials3(partials, kBB, bb, smem);
-  bool conv = rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2];
+    float* pp = partials + blockIdx.x * kPartialStride + mySet;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) beta[k] = rzOld[k] > 0.0f ? rzNew[k] / rzOld[k] : 0.0f;
-  if (!conv) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-      float4 z = w.z[i], p = w.p[i];
-      w.p[i] = make_float4(z.x + beta[0] * p.x, z.y + beta[1] * p.y, z.z + beta[2] * p.z, 0.0f);
-    }
+    for (int k = 0; k < 6; ++k) pp[k] = acc[k];
+    if (blockIdx.x == 0) w.flag[1] += 1;
   }
-  // Late CTAs may already see the flipped flag and return early: harmless, p is dead once converged.
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    float rel = 0.0f;
-    for (int k = 0; k < 3; ++k) if (bb[k] > 0.0f) rel = fmaxf(rel, rr[k] / bb[k]);
-    w.scalars[0] = sqrtf(rel);
-    w.flag[1] += 1;
-    if (conv) w.flag[0] = 1;
-  }
+  lastBlockReduce<6>(partials, mySet, w.scalars, w.flag, smem);
 }
 
 int launchPcgInit(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, const float4* b,
                   const float4* x, float tol) {
-  k_pcg_residual<<<kReduceBlocks, kThreads, 0, s>>>(A, c, b, x, w.r, w.delta, w.partials, w.flag);
+  k_pcg_residual<<<kReduceBlocks, kThreads, 0, s>>>(A, c, b, x, w.r, w.delta, w.partials, w.scalars, w.flag);
   k_pcg_start<<<kReduceBlocks, kThreads, 0, s>>>(w, w.partials);
-  k_pcg_check<<<1, kThreads, 0, s>>>(w.partials, w.scalars, w.flag, tol * tol);
+  k_pcg_check<<<1, 1, 0, s>>>(w.scalars, w.flag, kSet1, tol * tol);
   return 3;
 }
 
-int launchPcgIteration(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, float tol, int parity) {
-  k_pcg_spmv<<<kReduceBlocks, kThreads, 0, s>>>(A, c, w, w.partials);
-  k_pcg_update<<<kReduceBlocks, kThreads, 0, s>>>(w, w.delta, w.partials, parity);
-  k_pcg_direction<<<kReduceBlocks, kThreads, 0, s>>>(w, A.n, w.partials, parity, tol * tol);
-  return 3;
+// One CG iteration = two kernels.  `it` = iteration index within the solve.
+int launchPcgIteration(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, float tol, int it) {
+  int parity = it & 1;
+  k_pcg_spmv<<<kReduceBlocks, kThreads, 0, s>>>(A, c, w, w.partials, parity, it == 0 ? 1 : 0, tol * tol);
+  k_pcg_update<<<kReduceBlocks, kThreads, 0, s>>>(w, w.delta, w.partials, parity, tol * tol);
+  return 2;
+}
+
+// Latches the convergence flag after the last enqueued iteration (the host reads it next).
+int launchPcgCheck(cudaStream_t s, const PcgWork& w, float tol, int lastIt) {
+  k_pcg_check<<<1, 1, 0, s>>>(w.scalars, w.flag, (lastIt & 1) ? kSet1 : kSet0, tol * tol);
+  return 1;
 }
 
 int launchPcgFinish(cudaStream_t s, const PcgWork& w, uint32_t n, float4* x) {

@@ -119,15 +119,27 @@ __global__ void __launch_bounds__(kThreads) k_assign_dynamic(uint32_t nT, uint32
                                                              const uint32_t* __restrict__ start,
                                                              const uint32_t* __restrict__ blkOff,
                                                              const uint32_t* __restrict__ nodes, int* __restrict__ blockNodes,
-                                                             uint32_t* __restrict__ slotOf, uint32_t* __restrict__ nBlocksOut) {
+                                                             uint32_t* __restrict__ slotOf, uint32_t* __restrict__ blockCount,
+                                                             uint32_t* __restrict__ nBlocksOut) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) *nBlocksOut = nStatic + (nT ? blkOff[*nClustersPtr] : 0u);
   if (j >= nT) return;
   uint32_t c = clusterIdx[j];
   uint32_t rank = j - start[c];
-  uint32_t slot = (nStatic + blkOff[c] + (rank >> 5)) * 32u + (rank & 31u);
+  uint32_t blk = nStatic + blkOff[c] + (rank >> 5);
+  uint32_t slot = blk * 32u + (rank & 31u);
   blockNodes[slot] = (int)nodes[j];
   slotOf[nodes[j]] = slot;
+  if ((rank & 31u) == 0u) blockCount[blk] = min(32u, start[c + 1] - start[c] - rank);
+}
+
+// storage of every block's inverse: m x m floats (rounded up to 16 B), offsets by exclusive scan
+__global__ void __launch_bounds__(kThreads) k_block_sizes(uint32_t bound, const uint32_t* __restrict__ nBlocksPtr,
+                                                          const uint32_t* __restrict__ blockCount, uint32_t* __restrict__ sq) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > bound) return;
+  uint32_t m = b < *nBlocksPtr ? blockCount[b] : 0u;
+  sq[b] = (m * m + 3u) & ~3u;
 }
 
 // static blocks: drop the touched nodes and pack the rest to the front (one warp per block)
@@ -135,7 +147,7 @@ __global__ void __launch_bounds__(kThreads) k_static_membership(uint32_t nStatic
                                                                 const uint32_t* __restrict__ flagScan,
                                                                 const float* __restrict__ floorW, int haveFloor,
                                                                 int* __restrict__ blockNodes, uint32_t* __restrict__ slotOf,
-                                                                uint8_t* __restrict__ dirty) {
+                                                                uint32_t* __restrict__ blockCount, uint8_t* __restrict__ dirty) {
   uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (b >= nStatic) return;
@@ -153,7 +165,10 @@ __global__ void __launch_bounds__(kThreads) k_static_membership(uint32_t nStatic
     blockNodes[dst] = node;
     slotOf[node] = dst;
   }
-  if (lane == 0) dirty[b] = (keepMask != presentMask || floorMask != 0u) ? 1 : 0;
+  if (lane == 0) {
+    dirty[b] = (keepMask != presentMask || floorMask != 0u) ? 1 : 0;
+    blockCount[b] = __popc(keepMask);
+  }
 }
 
 // ---- dense assembly + Cholesky inverse, one warp per block ----------------------------------------------
@@ -165,31 +180,26 @@ __global__ void __launch_bounds__(kFactorWarps * 32) k_block_factor(uint32_t nSt
                                                                     const int* __restrict__ blockNodes,
                                                                     const uint32_t* __restrict__ slotOf,
                                                                     const uint8_t* __restrict__ dirty,
-                                                                    uint8_t* __restrict__ isBase,
+                                                                    const uint32_t* __restrict__ blockOff,
                                                                     const float* __restrict__ baseInv,
-                                                                    float* __restrict__ blockInv) {
+                                                                    float* __restrict__ blockInv, uint2* __restrict__ blockMeta) {
   __shared__ float sM[kFactorWarps][32 * kLd];
   __shared__ float sX[kFactorWarps][32 * kLd];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b = blockIdx.x * kFactorWarps + warp;
   if (b >= *nBlocksPtr) return;
-  float* out = blockInv + (size_t)b * 1024;
-  if (b < nStatic && !dirty[b]) {  // untouched static block: its inverse is the once-per-topology one
-    if (!isBase[b]) {
-      const float4* src = reinterpret_cast<const float4*>(baseInv + (size_t)b * 1024);
-      float4* dst = reinterpret_cast<float4*>(out);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) dst[k * 32 + lane] = src[k * 32 + lane];
-      if (lane == 0) isBase[b] = 1;
-    }
-    return;
-  }
-  if (lane == 0 && b < nStatic) isBase[b] = 0;
-  float* M = sM[warp];
-  float* X = sX[warp];
+  float* out = blockInv + blockOff[b];
   const int node = blockNodes[b * 32 + lane];
   const uint32_t valid = __ballot_sync(0xffffffffu, node >= 0);
-  const int m = __popc(valid);  // members are packed at the front
+  const int m = __popc(valid);  // members are packed at the front; the inverse is stored m x m: out[j * m + i]
+  if (lane == 0) blockMeta[b] = make_uint2(blockOff[b], (uint32_t)m);
+  if (b < nStatic && !dirty[b]) {  // untouched static block: the once-per-topology inverse (stored 32 x 32)
+    const float* src = baseInv + (size_t)b * 1024;
+    for (int j = 0; j < m; ++j) if (lane < m) out[j * m + lane] = src[j * 32 + lane];
+    return;
+  }
+  float* M = sM[warp];
+  float* X = sX[warp];
   for (int k = 0; k < 32; ++k) { M[k * kLd + lane] = 0.0f; X[k * kLd + lane] = 0.0f; }
   __syncwarp();
   if (node >= 0) {
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(kFactorWarps * 32) k_block_factor(uint32_t nSt
     if (node >= 0) {
       for (int k = S.rowPtr[node]; k < S.rowPtr[node + 1]; ++k) if (S.col[k] == node) diag = S.val[k];
     }
-    for (int j = 0; j < 32; ++j) out[j * 32 + lane] = (j == lane && node >= 0) ? 1.0f / diag : 0.0f;
+    for (int j = 0; j < m; ++j) if (lane < m) out[j * m + lane] = j == lane ? 1.0f / diag : 0.0f;
     return;
   }
   // X = L^-1 (lower): lane c owns column c
@@ -254,14 +264,14 @@ __global__ void __launch_bounds__(kFactorWarps * 32) k_block_factor(uint32_t nSt
     }
   }
   __syncwarp();
-  // Minv = X^T X: lane i owns row i (== column i); stored [j * 32 + i]
-  for (int j = 0; j < 32; ++j) {
-    float s = 0.0f;
-    if (lane < m && j < m) {
+  // Minv = X^T X: lane i owns row i (== column i)
+  for (int j = 0; j < m; ++j) {
+    if (lane < m) {
+      float s = 0.0f;
       int k0 = lane > j ? lane : j;
       for (int k = k0; k < m; ++k) s += X[k * kLd + lane] * X[k * kLd + j];
+      out[j * m + lane] = s;
     }
-    out[j * 32 + lane] = s;
   }
 }
 
@@ -278,22 +288,8 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
                   int* launches) {
   int L = 0;
   RCHECK(w.nBlocksDev.reserve(4));
-  pw.nBlocksDev = w.nBlocksDev.p;
-  if (!c.nUnique && !c.nFloor) {  // nothing touches the system matrix this substep: once-per-topology blocks
-    pw.blockNodes = const_cast<int*>(staticNodes); pw.blockInv = const_cast<float*>(staticInv);
-    w.host[1] = nStatic;
-    RCHECK(cudaMemcpyAsync(w.nBlocksDev.p, w.host + 1, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    w.nBlocksBound = nStatic;
-    pw.nBlocks = nStatic;
-    return 0;
-  }
   RCHECK(w.flag.reserve(n + 2)); RCHECK(w.parent.reserve(n + 1)); RCHECK(w.slotOf.reserve(n + 1));
   RCHECK(w.dirty.reserve(nStatic + 1));
-  if (w.isBaseCount != nStatic || w.isBaseFor != staticInv) {
-    RCHECK(w.isBase.reserve(nStatic + 1));
-    RCHECK(cudaMemsetAsync(w.isBase.p, 0, nStatic + 1, s));
-    w.isBaseCount = nStatic; w.isBaseFor = staticInv;
-  }
   RCHECK(w.scanScratch.reserve(scanScratchElems(std::max<uint64_t>(n + 2, w.scanCap))));
   uint32_t nT = 0;
   if (c.nUnique) {
@@ -306,15 +302,14 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   } else {
     RCHECK(cudaMemsetAsync(w.flag.p, 0, (n + 2) * sizeof(uint32_t), s));
   }
-  // every cluster has >= 4 nodes (a contact joins 4 distinct nodes), so it needs <= size/4 ... blocks in total:
-  uint32_t dynBound = nT / 4 + nT / 32 + 2;
-  uint32_t bound = nStatic + (nT ? dynBound : 0);
+  // every cluster has >= 4 nodes (a contact joins 4 distinct nodes): #clusters <= nT / 4, #pieces <= that + nT / 32
+  uint32_t dynBound = nT ? nT / 4 + nT / 32 + 2 : 0;
+  uint32_t bound = nStatic + dynBound;
   w.nBlocksBound = bound;
-  {
-    const float* before = w.blockInv.p;
-    RCHECK(w.blockNodes.reserve((size_t)bound * 32)); RCHECK(w.blockInv.reserve((size_t)bound * 1024));
-    if (w.blockInv.p != before) RCHECK(cudaMemsetAsync(w.isBase.p, 0, nStatic + 1, s));  // fresh storage holds no inverse yet
-  }
+  RCHECK(w.blockNodes.reserve((size_t)bound * 32));
+  RCHECK(w.blockCount.reserve(bound + 2)); RCHECK(w.blockOff.reserve(bound + 2)); RCHECK(w.blockMeta.reserve(bound + 2));
+  RCHECK(w.blockInv.reserve((size_t)32 * n + 4ull * bound + 64));  // sum m^2 <= 32 * sum m = 32 n, plus rounding
+  w.scanCap = std::max<uint64_t>(w.scanCap, (uint64_t)bound + 2);
   if (nT) {
     RCHECK(w.keys.reserve(nT)); RCHECK(w.tmpKeys.reserve(nT)); RCHECK(w.vals.reserve(nT)); RCHECK(w.tmpVals.reserve(nT));
     RCHECK(w.heads.reserve(nT + 2)); RCHECK(w.start.reserve(nT + 2)); RCHECK(w.blkOff.reserve(nT + 2));
@@ -322,24 +317,30 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
     w.scanCap = std::max<uint64_t>(w.scanCap, (uint64_t)nT + 2);
     RCHECK(w.scanScratch.reserve(scanScratchElems(std::max<uint64_t>(n + 2, w.scanCap))));
     RCHECK(cudaMemsetAsync(w.blockNodes.p + (size_t)nStatic * 32, 0xff, (size_t)dynBound * 32 * sizeof(int), s));
+    RCHECK(cudaMemsetAsync(w.blockCount.p + nStatic, 0, (size_t)(dynBound + 1) * sizeof(uint32_t), s));
     k_touched_keys<<<gridFor(n, kThreads), kThreads, 0, s>>>(n, w.flag.p, w.parent.p, q, w.keys.p, w.vals.p); ++L;
     L += launchSortPairs(s, nT, w.keys.p, w.vals.p, w.tmpKeys.p, w.tmpVals.p, w.sortHist.p, bitsForU(n) + 15);
     k_cluster_heads<<<gridFor(nT + 1, kThreads), kThreads, 0, s>>>(nT, w.keys.p, w.heads.p); ++L;
     L += launchExclusiveScan(s, w.heads.p, nT + 1, w.scanScratch.p);
     k_cluster_starts<<<gridFor(nT, kThreads), kThreads, 0, s>>>(nT, w.keys.p, w.heads.p, w.start.p); ++L;
     k_cluster_blocks<<<gridFor(nT + 1, kThreads), kThreads, 0, s>>>(nT, w.heads.p + nT, w.start.p, w.blkOff.p); ++L;
-    L += launchExclusiveScan(s, w.blkOff.p, nT + 1, w.scanScratch.p);  // clusters <= nT; tail entries are zero/unused
+    L += launchExclusiveScan(s, w.blkOff.p, nT + 1, w.scanScratch.p);  // entries past #clusters are unused
+  } else {
+    RCHECK(w.scanScratch.reserve(scanScratchElems(std::max<uint64_t>(n + 2, w.scanCap))));
   }
   k_static_membership<<<gridFor((uint64_t)nStatic * 32, kThreads), kThreads, 0, s>>>(nStatic, staticNodes, w.flag.p, c.floorW,
                                                                                     c.nFloor ? 1 : 0, w.blockNodes.p,
-                                                                                    w.slotOf.p, w.dirty.p); ++L;
+                                                                                    w.slotOf.p, w.blockCount.p, w.dirty.p); ++L;
   k_assign_dynamic<<<gridFor(std::max(nT, 1u), kThreads), kThreads, 0, s>>>(nT, nStatic, w.heads.p + nT, w.heads.p, w.start.p,
                                                                            w.blkOff.p, w.vals.p, w.blockNodes.p, w.slotOf.p,
-                                                                           w.nBlocksDev.p); ++L;
+                                                                           w.blockCount.p, w.nBlocksDev.p); ++L;
+  k_block_sizes<<<gridFor(bound + 1, kThreads), kThreads, 0, s>>>(bound, w.nBlocksDev.p, w.blockCount.p, w.blockOff.p); ++L;
+  L += launchExclusiveScan(s, w.blockOff.p, bound + 1, w.scanScratch.p);
   k_block_factor<<<gridFor(bound, kFactorWarps), kFactorWarps * 32, 0, s>>>(nStatic, w.nBlocksDev.p, S, c, w.blockNodes.p,
-                                                                           w.slotOf.p, w.dirty.p, w.isBase.p, staticInv,
-                                                                           w.blockInv.p); ++L;
-  pw.blockNodes = w.blockNodes.p; pw.blockInv = w.blockInv.p; pw.nBlocks = bound;
+                                                                           w.slotOf.p, w.dirty.p, w.blockOff.p, staticInv,
+                                                                           w.blockInv.p, w.blockMeta.p); ++L;
+  pw.blockNodes = w.blockNodes.p; pw.blockInv = w.blockInv.p; pw.blockMeta = w.blockMeta.p; pw.nBlocks = bound;
+  pw.nBlocksDev = w.nBlocksDev.p;
   if (launches) *launches += L;
   return 0;
 }

@@ -9,14 +9,15 @@ namespace pies {
 
 struct BlockWork {
   DevBuf<int> blockNodes;        // (static + dynamic blocks) * 32, members packed to the front, -1 padded
-  DevBuf<float> blockInv;        // 1024 per block
+  DevBuf<float> blockInv;        // m x m per block (m = members), at blockOff[b]
+  DevBuf<uint32_t> blockCount, blockOff;
+  DevBuf<uint2> blockMeta;       // (blockOff, m) per block, what the CG kernels read
   DevBuf<uint32_t> slotOf;       // node -> block * 32 + lane
   DevBuf<uint32_t> flag, parent, vals, tmpVals, heads, start, blkOff, sortHist, scanScratch, nBlocksDev;
   DevBuf<uint64_t> keys, tmpKeys;
-  DevBuf<uint8_t> dirty, isBase;
+  DevBuf<uint8_t> dirty;
   uint32_t* host = nullptr;      // pinned, 4 words
-  uint32_t isBaseCount = 0, nBlocksBound = 0;
-  const float* isBaseFor = nullptr;
+  uint32_t nBlocksBound = 0;
   uint64_t scanCap = 0;
   cudaError_t lastError = cudaSuccess;
 };

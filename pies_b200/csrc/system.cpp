@@ -213,6 +213,21 @@ void buildSystem(const HostScene& sc, float h, HostSystem& out, unsigned threads
   rawCol.clear(); rawCol.shrink_to_fit();
   rawVal.clear(); rawVal.shrink_to_fit();
 
+  // ---- 3b. row batches for the CSR-stream mat-vec ---------------------------------------------------
+  out.rowBatch.clear();
+  out.rowBatch.push_back(0);
+  {
+    uint32_t first = 0;
+    for (uint32_t r = 0; r < n; ++r) {
+      uint32_t nnzIfAdded = (uint32_t)(out.rowPtr[r + 1] - out.rowPtr[first]);
+      if (r > first && (nnzIfAdded > HostSystem::kBatchNnz || r - first >= HostSystem::kBatchRows)) {
+        out.rowBatch.push_back(r);
+        first = r;
+      }
+    }
+    if (n) out.rowBatch.push_back(n);
+  }
+
   // ---- 4. block-Jacobi preconditioner: blocks of <= 32 nodes following connectivity ------------------
   Dsu dsu(n);
   for (uint32_t r = 0; r < n; ++r)

@@ -26,6 +26,12 @@ struct HostSystem {
   std::vector<int> rowPtr, col;
   std::vector<float> val;
 
+  // Row batches for the CG mat-vec (CSR-stream): consecutive rows whose non-zeros fit one shared-memory
+  // tile (<= kBatchNnz entries, <= kBatchRows rows).  A CTA streams a batch's (col, val) pairs fully coalesced,
+  // parks the products in shared memory and then sums them per row in CSR order.
+  std::vector<uint32_t> rowBatch;             // nBatches + 1 first rows
+  static constexpr uint32_t kBatchNnz = 2048, kBatchRows = 256;
+
   // block-Jacobi preconditioner
   uint32_t nBlocks = 0;
   std::vector<int> blockNodes;                // 32 per block, -1 padded
