@@ -100,6 +100,8 @@ int launchGatherContacts(cudaStream_t s, uint32_t n, const ContactLists& c, cons
 // four nodes, then publishes nodeDone[v] = ticket + 1.  The earliest unfinished entry is always
 // runnable, so the sweep cannot stall, and the result equals the sequential sweep up to rounding of
 // the identical operations (same operand values, same order per node).
+// (A chunk-level variant that runs the 32 entries of a chunk from shared memory was measured and dropped: at
+// chunk granularity the false dependencies serialise a percolated pile, 29 ms per sweep instead of 1.1 ms.)
 constexpr int kGsThreads = 256;
 
 __device__ __forceinline__ uint32_t ldAcquire(const uint32_t* p) {
@@ -161,6 +163,7 @@ struct FrictionOp {
 template <typename Op>
 __global__ void __launch_bounds__(kGsThreads) k_gs_dataflow(const uint4* __restrict__ entries,
                                                             const uint4* __restrict__ ticket, uint32_t nTri,
+                                                            const uint8_t* __restrict__ gsClass,
                                                             uint32_t* __restrict__ nodeDone,
                                                             uint32_t* __restrict__ chunkCounter, Op op) {
   const int lane = threadIdx.x & 31;
@@ -173,7 +176,11 @@ __global__ void __launch_bounds__(kGsThreads) k_gs_dataflow(const uint4* __restr
     uint32_t e = (chunk << 5) + (uint32_t)lane;
     bool pending = e < nTri;
     uint4 id = make_uint4(0, 0, 0, 0), tk = make_uint4(0, 0, 0, 0);
-    if (pending) { id = entries[e]; tk = ticket[e]; }
+    if (pending) {
+      id = entries[e];
+      // entries of small clusters are swept inside one warp (k_gs_cluster_*); they share no node with the rest
+      if (gsClass[id.x] != 2) pending = false; else tk = ticket[e];
+    }
     while (__any_sync(0xffffffffu, pending)) {
       if (pending) {
         bool ready = ldAcquire(nodeDone + id.x) == tk.x && ldAcquire(nodeDone + id.y) == tk.y &&
@@ -190,12 +197,135 @@ __global__ void __launch_bounds__(kGsThreads) k_gs_dataflow(const uint4* __restr
   }
 }
 
+// ---- ordered sweeps of small contact clusters inside one warp -------------------------------------------
+// A contact cluster (connected component of the contact graph, reblock.cu) of <= 32 nodes never interacts
+// with anything outside it during the sweeps, so one warp keeps its nodes in registers (lane = node),
+// walks the cluster's entries in list order and exchanges operands with shuffles: the sequential order of
+// the reference at register latency, all four stabilisation sweeps in one launch.
+__global__ void __launch_bounds__(kThreads) k_entry_keys(uint32_t nTri, const uint4* __restrict__ entries,
+                                                         const uint32_t* __restrict__ clusterOf,
+                                                         const uint32_t* __restrict__ slotOf, uint64_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ lanes, uint32_t* __restrict__ entCount) {
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nTri) return;
+  uint4 id = entries[e];
+  uint32_t c = clusterOf[id.x];
+  keys[e] = c;
+  lanes[e] = (slotOf[id.x] & 31u) | ((slotOf[id.y] & 31u) << 8) | ((slotOf[id.z] & 31u) << 16) | ((slotOf[id.w] & 31u) << 24);
+  atomicAdd(entCount + c, 1u);
+}
+
+__device__ __forceinline__ V3 shflV3(float4 v, int src) {
+  return v3(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src), __shfl_sync(0xffffffffu, v.z, src));
+}
+
+__global__ void __launch_bounds__(kThreads) k_gs_cluster_stabilize(ClusterView cv, float4* __restrict__ q,
+                                                                   float4* __restrict__ prev, const float4* __restrict__ snap,
+                                                                   const uint32_t* __restrict__ floorMult, int haveFloor,
+                                                                   float thickness, uint32_t sweeps) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t nC = *cv.nClusters;
+  for (uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nC; c += warpsPerGrid) {
+    const uint32_t nb = cv.start[c], size = cv.start[c + 1] - nb;
+    if (size > 32u) continue;  // large cluster: dataflow sweeps
+    const bool have = (uint32_t)lane < size;
+    const uint32_t node = have ? cv.nodes[nb + lane] : 0u;
+    float4 q4 = make_float4(0.0f, 0.0f, 0.0f, 1.0f), p4 = q4, s4 = q4;
+    bool onFloor = false;
+    if (have) {
+      q4 = q[node]; p4 = prev[node];
+      onFloor = haveFloor && floorMult[node] != 0u;
+      if (onFloor) s4 = snap[node];
+    }
+    const uint32_t eb = cv.entStart[c], ee = cv.entStart[c + 1];
+    for (uint32_t sweep = 0; sweep < sweeps; ++sweep) {
+      for (uint32_t base = eb; base < ee; base += 32) {
+        const uint32_t myW = base + lane < ee ? cv.lanes[base + lane] : 0u;
+        const int cnt = (int)min(32u, ee - base);
+        for (int i = 0; i < cnt; ++i) {
+          const uint32_t lw = __shfl_sync(0xffffffffu, myW, i);
+          const int la = lw & 31u, lb = (lw >> 8) & 31u, lc = (lw >> 16) & 31u, ld = (lw >> 24) & 31u;
+          // PointTriangleCollisionConstraint::stabilizeCollisions (CollisionConstraint.cpp:126-162), as StabilizeOp
+          V3 A = shflV3(q4, la), B = shflV3(q4, lb), C = shflV3(q4, lc), D = shflV3(q4, ld);
+          float wa = __shfl_sync(0xffffffffu, q4.w, la), wb = __shfl_sync(0xffffffffu, q4.w, lb),
+                wc = __shfl_sync(0xffffffffu, q4.w, lc), wd = __shfl_sync(0xffffffffu, q4.w, ld);
+          V3 nrm = normalize(cross(C - B, D - B));
+          float nDotP = dot(nrm, A - B);
+          if (!(nDotP < thickness)) continue;
+          V3 disp = (thickness - nDotP) * nrm;
+          float wTri = wb + wc + wd;
+          float wSum = wa + wTri;
+          V3 da = disp * wa / wSum, dt = disp * wTri / wSum;
+          if (lane == la) {
+            q4.x += da.x; q4.y += da.y; q4.z += da.z; p4.x += da.x; p4.y += da.y; p4.z += da.z;
+          } else if (lane == lb || lane == lc || lane == ld) {
+            q4.x -= dt.x; q4.y -= dt.y; q4.z -= dt.z; p4.x -= dt.x; p4.y -= dt.y; p4.z -= dt.z;
+          }
+        }
+      }
+      if (onFloor) { q4.x = s4.x; q4.y = s4.y; q4.z = s4.z; }  // Solver.cpp:379-382, after the sweep's tri entries
+    }
+    if (have) { q[node] = q4; prev[node] = p4; }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_gs_cluster_friction(ClusterView cv, const float4* __restrict__ q,
+                                                                  float4* __restrict__ vel, float friction,
+                                                                  float staticThreshold) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t nC = *cv.nClusters;
+  for (uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nC; c += warpsPerGrid) {
+    const uint32_t nb = cv.start[c], size = cv.start[c + 1] - nb;
+    if (size > 32u) continue;
+    const bool have = (uint32_t)lane < size;
+    const uint32_t node = have ? cv.nodes[nb + lane] : 0u;
+    float4 q4 = make_float4(0.0f, 0.0f, 0.0f, 1.0f), v4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (have) { q4 = q[node]; v4 = vel[node]; }
+    const uint32_t eb = cv.entStart[c], ee = cv.entStart[c + 1];
+    for (uint32_t base = eb; base < ee; base += 32) {
+      const uint32_t myW = base + lane < ee ? cv.lanes[base + lane] : 0u;
+      const int cnt = (int)min(32u, ee - base);
+      for (int i = 0; i < cnt; ++i) {
+        const uint32_t lw = __shfl_sync(0xffffffffu, myW, i);
+        const int la = lw & 31u, lb = (lw >> 8) & 31u, lc = (lw >> 16) & 31u, ld = (lw >> 24) & 31u;
+        // point-triangle friction / restitution (Solver.cpp:431-471), as FrictionOp
+        V3 B = shflV3(q4, lb), C = shflV3(q4, lc), D = shflV3(q4, ld);
+        float wa = __shfl_sync(0xffffffffu, q4.w, la), wb = __shfl_sync(0xffffffffu, q4.w, lb),
+              wc = __shfl_sync(0xffffffffu, q4.w, lc), wd = __shfl_sync(0xffffffffu, q4.w, ld);
+        V3 va = shflV3(v4, la), vb = shflV3(v4, lb), vc = shflV3(v4, lc), vd = shflV3(v4, ld);
+        V3 avgTri = (vb + vc + vd) / 3.0f;
+        V3 nrm = normalize(cross(C - B, D - B));
+        V3 rel = va - avgTri;
+        float vDotN = dot(rel, nrm);
+        V3 perp = rel - vDotN * nrm;
+        float fr = friction;
+        if (length(perp) < staticThreshold) fr = 1.0f;
+        float triW = wb + wc + wd;
+        float wSum = wa + triW;
+        V3 dv = (-fr) * perp - (1.1f * fminf(vDotN, 0.0f)) * nrm;
+        V3 dtv = (-dv) * triW / wSum;
+        if (lane == la) {
+          V3 nv = va + dv * wa / wSum;
+          v4.x = nv.x; v4.y = nv.y; v4.z = nv.z;
+        } else if (lane == lb || lane == lc || lane == ld) {
+          v4.x += dtv.x; v4.y += dtv.y; v4.z += dtv.z;
+        }
+      }
+    }
+    if (have) vel[node] = make_float4(v4.x, v4.y, v4.z, 0.0f);
+  }
+}
+
 // nodes on the floor go back to their projected position (Solver.cpp:379-382)
 __global__ void __launch_bounds__(kThreads) k_floor_snap(uint32_t nFloor, const uint32_t* __restrict__ nodes,
-                                                         const float4* __restrict__ snap, float4* __restrict__ q) {
+                                                         const float4* __restrict__ snap, float4* __restrict__ q,
+                                                         const uint8_t* __restrict__ gsClass, int cls) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nFloor) return;
   uint32_t node = nodes[i];
+  if (gsClass && gsClass[node] != cls) return;  // nodes of contact clusters are snapped inside their sweeps
   float4 p = snap[node];
   float4 cur = q[node];
   q[node] = make_float4(p.x, p.y, p.z, cur.w);
@@ -222,10 +352,35 @@ constexpr int kSweepCounters = 64;
 int prepareContactSweeps(ContactWork& w, cudaStream_t s, const ContactLists& c) {
   w.nTri = c.nTri;
   w.sweepsUsed = 0;
+  w.haveClusters = false;
   if (!c.nTri) return 0;
   if (w.sweepCounters.reserve(kSweepCounters) != cudaSuccess) return -1;
   if (cudaMemsetAsync(w.sweepCounters.p, 0, kSweepCounters * sizeof(uint32_t), s) != cudaSuccess) return -1;
   return 0;
+}
+
+// After reblock.cu has formed this substep's contact clusters: entries grouped by cluster (stable, so list
+// order survives inside a cluster) with the lanes of their four nodes.
+int prepareClusterSweeps(ContactWork& w, cudaStream_t s, const ContactLists& c, const ClusterTables& t) {
+  if (!c.nTri || !t.nTouched) return 0;
+  const uint32_t nTri = c.nTri, clusterBound = t.nTouched / 4 + 2;
+  if (w.keys.reserve(nTri) != cudaSuccess || w.tmpKeys.reserve(nTri) != cudaSuccess || w.lanes.reserve(nTri) != cudaSuccess ||
+      w.tmpVals.reserve(nTri) != cudaSuccess || w.entStart.reserve(clusterBound + 2) != cudaSuccess ||
+      w.sortHist.reserve(sortHistBytes(nTri) / 4 + 4) != cudaSuccess ||
+      w.scanScratch.reserve(scanScratchElems(std::max<uint64_t>(clusterBound + 2, 1024))) != cudaSuccess)
+    return -1;
+  int L = 0;
+  cudaMemsetAsync(w.entStart.p, 0, (size_t)(clusterBound + 2) * sizeof(uint32_t), s);
+  k_entry_keys<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, c.tri, t.clusterOf, t.slotOf, w.keys.p, w.lanes.p, w.entStart.p); ++L;
+  L += launchExclusiveScan(s, w.entStart.p, clusterBound + 1, w.scanScratch.p);
+  int bits = 1;
+  while ((1ull << bits) <= (uint64_t)clusterBound) ++bits;
+  L += launchSortPairs(s, nTri, w.keys.p, w.lanes.p, w.tmpKeys.p, w.tmpVals.p, w.sortHist.p, bits);
+  w.view = ClusterView{t.nClusters, t.start, t.nodes, w.entStart.p, w.lanes.p};
+  w.gsClass = t.gsClass;
+  w.clusterBound = clusterBound;
+  w.haveClusters = true;
+  return L;
 }
 
 template <typename Op>
@@ -237,25 +392,43 @@ static int launchSweep(cudaStream_t s, ContactWork& w, const ContactLists& c, ui
   cudaMemsetAsync(c.nodeDone, 0, (size_t)n * sizeof(uint32_t), s);
   uint32_t chunks = (c.nTri + 31u) / 32u;
   int grid = (int)std::min<uint32_t>(kNumSMs * 8, (chunks + kGsThreads / 32 - 1) / (kGsThreads / 32));
-  k_gs_dataflow<Op><<<grid, kGsThreads, 0, s>>>(c.tri, c.ticket, c.nTri, c.nodeDone, w.sweepCounters.p + w.sweepsUsed, op);
+  k_gs_dataflow<Op><<<grid, kGsThreads, 0, s>>>(c.tri, c.ticket, c.nTri, w.gsClass, c.nodeDone,
+                                                 w.sweepCounters.p + w.sweepsUsed, op);
   ++w.sweepsUsed;
   return 1;
+}
+
+static int clusterGrid(uint32_t clusterBound) {
+  return (int)std::min<uint32_t>(kNumSMs * 8, (clusterBound + kThreads / 32 - 1) / (kThreads / 32));
 }
 
 int launchStabilize(cudaStream_t s, ContactWork& w, const ContactLists& c, uint32_t n, float4* q, float4* prev,
                     const float4* snap, float thickness, uint32_t iterations) {
   int L = 0;
-  for (uint32_t it = 0; it < iterations; ++it) {
-    if (c.nTri) L += launchSweep(s, w, c, n, StabilizeOp{q, prev, thickness});
-    if (c.nFloor) { k_floor_snap<<<gridFor(c.nFloor, kThreads), kThreads, 0, s>>>(c.nFloor, c.floorNode, snap, q); ++L; }
+  if (!iterations) return 0;
+  const uint8_t* cls = (c.nTri && w.haveClusters) ? w.gsClass : nullptr;
+  if (cls) {
+    // small clusters: all sweeps (and their floor snaps) in one launch
+    k_gs_cluster_stabilize<<<clusterGrid(w.clusterBound), kThreads, 0, s>>>(w.view, q, prev, snap, c.floorMult, c.nFloor ? 1 : 0,
+                                                                           thickness, iterations); ++L;
+    // large clusters: dataflow sweeps, floor snap of their nodes after each one
+    for (uint32_t it = 0; it < iterations; ++it) {
+      L += launchSweep(s, w, c, n, StabilizeOp{q, prev, thickness});
+      if (c.nFloor) { k_floor_snap<<<gridFor(c.nFloor, kThreads), kThreads, 0, s>>>(c.nFloor, c.floorNode, snap, q, cls, 2); ++L; }
+    }
   }
+  // floor nodes outside every cluster: the snap is idempotent, once is the same as once per sweep
+  if (c.nFloor) { k_floor_snap<<<gridFor(c.nFloor, kThreads), kThreads, 0, s>>>(c.nFloor, c.floorNode, snap, q, cls, 0); ++L; }
   return L;
 }
 
 int launchFriction(cudaStream_t s, ContactWork& w, const ContactLists& c, uint32_t n, const float4* q, float4* vel,
                    float friction, float staticThreshold) {
   int L = 0;
-  if (c.nTri) L += launchSweep(s, w, c, n, FrictionOp{q, vel, friction, staticThreshold});
+  if (c.nTri && w.haveClusters) {
+    k_gs_cluster_friction<<<clusterGrid(w.clusterBound), kThreads, 0, s>>>(w.view, q, vel, friction, staticThreshold); ++L;
+    L += launchSweep(s, w, c, n, FrictionOp{q, vel, friction, staticThreshold});
+  }
   if (c.nFloor) { k_floor_friction<<<gridFor(n, kThreads), kThreads, 0, s>>>(n, c.floorMult, vel, friction, staticThreshold); ++L; }
   return L;
 }

@@ -7,14 +7,39 @@
 
 namespace pies {
 
+struct ClusterView {   // device view of this substep's contact clusters and their entries (contact.cu)
+  const uint32_t* nClusters = nullptr;
+  const uint32_t* start = nullptr;
+  const uint32_t* nodes = nullptr;
+  const uint32_t* entStart = nullptr;
+  const uint32_t* lanes = nullptr;
+};
+
+struct ClusterTables {  // what reblock.cu produced for this substep
+  const uint32_t* nClusters = nullptr;  // device count
+  const uint32_t* start = nullptr;      // cluster -> first position in nodes
+  const uint32_t* nodes = nullptr;      // touched nodes sorted by cluster
+  const uint32_t* clusterOf = nullptr;  // node -> cluster
+  const uint32_t* slotOf = nullptr;     // node -> block * 32 + lane (lane == rank inside a small cluster)
+  const uint8_t* gsClass = nullptr;     // node -> 0 / 1 (small cluster) / 2 (large cluster)
+  uint32_t nTouched = 0;
+};
+
 struct ContactWork {
-  DevBuf<uint32_t> sweepCounters;  // one chunk counter per ordered sweep of the substep
-  DevBuf<float4> contribC;         // 4 per point-triangle entry
-  uint32_t nTri = 0, sweepsUsed = 0;
+  DevBuf<uint32_t> sweepCounters;  // one chunk counter per ordered dataflow sweep of the substep
+  DevBuf<float4> contribC;         // 4 per distinct point-triangle contact
+  DevBuf<uint64_t> keys, tmpKeys;
+  DevBuf<uint32_t> lanes, tmpVals, entStart, sortHist, scanScratch;
+  ClusterView view;
+  const uint8_t* gsClass = nullptr;
+  uint32_t nTri = 0, sweepsUsed = 0, clusterBound = 0;
+  bool haveClusters = false;
 };
 
 // Once per substep, after detection: resets the chunk counters of the ordered sweeps.
 int prepareContactSweeps(ContactWork& w, cudaStream_t s, const ContactLists& c);
+// After reblock.cu: groups the entries by contact cluster for the in-warp sweeps.  Returns launches or -1.
+int prepareClusterSweeps(ContactWork& w, cudaStream_t s, const ContactLists& c, const ClusterTables& t);
 // Per PD iteration: collision projections (local step) and their RHS contributions.
 int launchContactProject(cudaStream_t s, const ContactLists& c, const float4* q, float thickness, float4* contribC,
                          float4* snap);

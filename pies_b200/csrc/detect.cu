@@ -146,13 +146,16 @@ __global__ void __launch_bounds__(kThreads) k_cell_starts(uint64_t nPairs, const
 }
 
 // ---- 4. narrow phase ------------------------------------------------------------------------
-// One thread per (cell, member) pair of the sorted table: the member triangle is tested against
-// every triangle of that cell, which is what the reference's worker does when it visits this
-// bucket for this triangle.  Neighbouring threads sit in the same cell, so the loop over the
-// cell's members reads the same records in every lane (broadcast loads) while each lane keeps
-// its own triangle in registers.  Hits of pair (t, k-th cell of t) are counted into slot
-// rankOff[rank(t)] + k, i.e. directly in the reference's output order (thread-striped triangle
-// order, cells in (dx,dy,dz) order); after a scan the same kernel writes them.
+// 4a. candidate filter: one thread per (cell, member) pair of the sorted table.  The member triangle is
+// compared with every triangle of that cell — what the reference's worker does when it visits this bucket
+// for this triangle — but only with the cheap tests: shared node, then swept corner box against the other
+// triangle's swept box (conservative: a pair that fails it cannot pass pointTriangleCCD).  Neighbouring
+// threads sit in the same cell, so the member loop reads the same records in every lane (broadcast) while
+// each lane keeps its own triangle in registers.  Candidates of pair (t, k-th cell of t) are counted into
+// slot rankOff[rank(t)] + k, i.e. directly in the reference's output order (thread-striped triangle order,
+// cells in (dx,dy,dz) order, members ascending, corners 0..2); after a scan the same kernel writes them.
+// 4b. CCD: one thread per candidate (point, triangle): the expensive swept test runs exactly once per
+// candidate, fully convergent, and a scan of the hit flags compacts the survivors in the same order.
 struct NarrowParams {
   uint32_t nTri, threadCount;
   float threshold;
@@ -160,7 +163,7 @@ struct NarrowParams {
 };
 
 template <bool WRITE>
-__global__ void __launch_bounds__(kThreads) k_pair_narrow(NarrowParams np, KeyPack kp, uint64_t nPairs,
+__global__ void __launch_bounds__(kThreads) k_pair_filter(NarrowParams np, KeyPack kp, uint64_t nPairs,
                                                           const uint64_t* __restrict__ keys,
                                                           const uint32_t* __restrict__ memberTri,
                                                           const uint32_t* __restrict__ cellIdx,
@@ -169,8 +172,8 @@ __global__ void __launch_bounds__(kThreads) k_pair_narrow(NarrowParams np, KeyPa
                                                           const float4* __restrict__ aabbLo, const float4* __restrict__ aabbHi,
                                                           const float4* __restrict__ q, const float4* __restrict__ prev,
                                                           const uint32_t* __restrict__ rankOff,
-                                                          uint32_t* __restrict__ hitCount /* canonical slots; scanned when WRITE */,
-                                                          uint4* __restrict__ outTri, uint32_t* __restrict__ outOther, int* __restrict__ failFlag) {
+                                                          uint32_t* __restrict__ candCount /* canonical slots; scanned when WRITE */,
+                                                          uint2* __restrict__ cand, uint32_t candCap, int* __restrict__ failFlag) {
   uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nPairs) return;
   uint32_t t = memberTri[j];
@@ -183,23 +186,22 @@ __global__ void __launch_bounds__(kThreads) k_pair_narrow(NarrowParams np, KeyPa
   uint32_t dy = (uint32_t)((int)((key >> kp.bitsZ) & ((1ull << kp.bitsY) - 1ull)) + kp.minY - mn.y);
   uint32_t dx = (uint32_t)((int)(key >> (kp.bitsY + kp.bitsZ)) + kp.minX - mn.x);
   uint32_t slot = rankOff[canonicalRank(t, np.nTri, np.threadCount)] + (dx * ly + dy) * lz + dz;
-  if (!WRITE && j == 0) hitCount[nPairs] = 0;
+  if (!WRITE && j == 0) candCount[nPairs] = 0;
   if (lx > 20u || ly > 20u || lz > 20u) {  // sweptTriRange cap: inserted but queries nothing
-    if (!WRITE) hitCount[slot] = 0;
+    if (!WRITE) candCount[slot] = 0;
     return;
   }
   uint32_t cidx = cellIdx[j];
   uint32_t s = cellStart[cidx], e = cellStart[cidx + 1];
   if (e - s > 1000u) atomicExch(failFlag, 1);  // hang guard, Solver.cpp:751-755
   uint32_t ia[3] = {rec.x, rec.y, rec.z};
-  V3 pa[3], oa[3];
   float cLo[3][3], cHi[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    pa[i] = v3(q[ia[i]]); oa[i] = v3(prev[ia[i]]);
-    cLo[i][0] = fminf(pa[i].x, oa[i].x) - np.cullMargin; cHi[i][0] = fmaxf(pa[i].x, oa[i].x) + np.cullMargin;
-    cLo[i][1] = fminf(pa[i].y, oa[i].y) - np.cullMargin; cHi[i][1] = fmaxf(pa[i].y, oa[i].y) + np.cullMargin;
-    cLo[i][2] = fminf(pa[i].z, oa[i].z) - np.cullMargin; cHi[i][2] = fmaxf(pa[i].z, oa[i].z) + np.cullMargin;
+    float4 p = q[ia[i]], o = prev[ia[i]];
+    cLo[i][0] = fminf(p.x, o.x) - np.cullMargin; cHi[i][0] = fmaxf(p.x, o.x) + np.cullMargin;
+    cLo[i][1] = fminf(p.y, o.y) - np.cullMargin; cHi[i][1] = fmaxf(p.y, o.y) + np.cullMargin;
+    cLo[i][2] = fminf(p.z, o.z) - np.cullMargin; cHi[i][2] = fmaxf(p.z, o.z) + np.cullMargin;
   }
   // union of the three corner boxes: one test rejects most members
   float uLo[3], uHi[3];
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(kThreads) k_pair_narrow(NarrowParams np, KeyPa
     uLo[c] = fminf(cLo[0][c], fminf(cLo[1][c], cLo[2][c]));
     uHi[c] = fmaxf(cHi[0][c], fmaxf(cHi[1][c], cHi[2][c]));
   }
-  uint32_t outPos = WRITE ? hitCount[slot] : 0u;
+  uint32_t outPos = WRITE ? candCount[slot] : 0u;
   uint32_t total = 0;
   for (uint32_t m = s; m < e; ++m) {
     uint32_t o = memberTri[m];
@@ -219,28 +221,51 @@ __global__ void __launch_bounds__(kThreads) k_pair_narrow(NarrowParams np, KeyPa
     if (common) continue;
     float4 lo = aabbLo[o], hi = aabbHi[o];
     if (!(uLo[0] <= hi.x && uHi[0] >= lo.x && uLo[1] <= hi.y && uHi[1] >= lo.y && uLo[2] <= hi.z && uHi[2] >= lo.z)) continue;
-    uint32_t maybe = 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       bool ov = cLo[i][0] <= hi.x && cHi[i][0] >= lo.x && cLo[i][1] <= hi.y && cHi[i][1] >= lo.y &&
                 cLo[i][2] <= hi.z && cHi[i][2] >= lo.z;
-      maybe |= ov ? (1u << i) : 0u;
-    }
-    if (!maybe) continue;
-    V3 pb = v3(q[ro.x]), pc = v3(q[ro.y]), pd = v3(q[ro.z]);
-    V3 ob = v3(prev[ro.x]), oc = v3(prev[ro.y]), od = v3(prev[ro.z]);
-    V3 ab0 = ex::sub(oc, ob), ac0 = ex::sub(od, ob), ab1 = ex::sub(pc, pb), ac1 = ex::sub(pd, pb);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      if (!(maybe & (1u << i))) continue;
-      float tt;
-      if (ex::pointTriangleCCD(ex::sub(oa[i], ob), ab0, ac0, ex::sub(pa[i], pb), ab1, ac1, np.threshold, tt)) {
-        if (WRITE) { outTri[outPos + total] = make_uint4(ia[i], ro.x, ro.y, ro.z); outOther[outPos + total] = o; }
+      if (ov) {
+        if (WRITE && outPos + total < candCap) cand[outPos + total] = make_uint2(ia[i], o);
         ++total;
       }
     }
   }
-  if (!WRITE) hitCount[slot] = total;
+  if (!WRITE) candCount[slot] = total;
+}
+
+__global__ void __launch_bounds__(128) k_ccd(const uint32_t* __restrict__ nCandPtr, uint32_t candCap,
+                                             const uint2* __restrict__ cand, const uint4* __restrict__ triRec,
+                                             const float4* __restrict__ q, const float4* __restrict__ prev,
+                                             float threshold, uint32_t* __restrict__ hit) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nCand = min(*nCandPtr, candCap);
+  if (k > nCand) return;
+  if (k == nCand) { hit[k] = 0; return; }
+  uint2 cd = cand[k];
+  uint4 ro = triRec[cd.y];
+  V3 pa = v3(q[cd.x]), oa = v3(prev[cd.x]);
+  V3 pb = v3(q[ro.x]), pc = v3(q[ro.y]), pd = v3(q[ro.z]);
+  V3 ob = v3(prev[ro.x]), oc = v3(prev[ro.y]), od = v3(prev[ro.z]);
+  float tt;
+  bool h = ex::pointTriangleCCD(ex::sub(oa, ob), ex::sub(oc, ob), ex::sub(od, ob), ex::sub(pa, pb), ex::sub(pc, pb),
+                                ex::sub(pd, pb), threshold, tt);
+  hit[k] = h ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(kThreads) k_compact_hits(const uint32_t* __restrict__ nCandPtr, uint32_t candCap,
+                                                           const uint2* __restrict__ cand, const uint4* __restrict__ triRec,
+                                                           const uint32_t* __restrict__ hitScan, uint4* __restrict__ outTri,
+                                                           uint32_t* __restrict__ outOther) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nCand = min(*nCandPtr, candCap);
+  if (k >= nCand) return;
+  uint32_t pos = hitScan[k];
+  if (hitScan[k + 1] == pos) return;
+  uint2 cd = cand[k];
+  uint4 ro = triRec[cd.y];
+  outTri[pos] = make_uint4(cd.x, ro.x, ro.y, ro.z);
+  outOther[pos] = cd.y;
 }
 
 // ---- 5. node -> incident entries --------------------------------------------------------------
@@ -386,24 +411,45 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
     L += launchExclusiveScan(s, w.heads.p, nPairs + 1, w.scanScratch.p);
     DCHECK(cudaMemcpyAsync(w.host + 9, w.heads.p + nPairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     k_cell_starts<<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(nPairs, w.keys.p, w.heads.p, w.cellStart.p); ++L;
-    // count pass
-    k_pair_narrow<false><<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p,
+    // candidate filter: count, scan, write (capacity from the previous substep; redone if it overflows)
+    k_pair_filter<false><<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p,
                                                                        w.cellStart.p, w.triRec.p, w.triMin.p, w.aabbLo.p,
                                                                        w.aabbHi.p, in.q, in.prev, w.cntRank.p, w.hitCount.p,
-                                                                       nullptr, nullptr, w.bbox.p + 7); ++L;
+                                                                       nullptr, 0, w.bbox.p + 7); ++L;
     L += launchExclusiveScan(s, w.hitCount.p, nPairs + 1, w.scanScratch.p);
-    DCHECK(cudaMemcpyAsync(w.host + 10, w.hitCount.p + nPairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    DCHECK(cudaMemcpyAsync(w.host + 12, w.bbox.p + 7, sizeof(int), cudaMemcpyDeviceToHost, s));
-    DCHECK(cudaStreamSynchronize(s));
-    w.nCells = (uint32_t)w.host[9];
-    if (w.host[12]) { w.failed = true; if (launches) *launches += L; return 0; }
-    nHit = (uint32_t)w.host[10];
-    DCHECK(w.triList.reserve(nHit + 1)); DCHECK(w.otherTri.reserve(nHit + 1));
-    if (nHit) {
-      k_pair_narrow<true><<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p,
+    uint32_t nCand = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      uint32_t cap = std::max<uint32_t>(w.candCap, 1u << 16);
+      DCHECK(w.cand.reserve(cap)); DCHECK(w.candHit.reserve((size_t)cap + 2));
+      w.scanCap = std::max<uint64_t>(w.scanCap, (uint64_t)cap + 2);
+      DCHECK(w.scanScratch.reserve(scanScratchElems(w.scanCap)));
+      k_pair_filter<true><<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p,
                                                                         w.cellStart.p, w.triRec.p, w.triMin.p, w.aabbLo.p,
                                                                         w.aabbHi.p, in.q, in.prev, w.cntRank.p, w.hitCount.p,
-                                                                        w.triList.p, w.otherTri.p, w.bbox.p + 7); ++L;
+                                                                        w.cand.p, cap, w.bbox.p + 7); ++L;
+      k_ccd<<<gridFor((uint64_t)cap + 1, 128), 128, 0, s>>>(w.hitCount.p + nPairs, cap, w.cand.p, w.triRec.p, in.q, in.prev,
+                                                          in.threshold, w.candHit.p); ++L;
+      // the scan runs over the capacity; flags past the candidate count are never read
+      DCHECK(cudaMemcpyAsync(w.host + 14, w.hitCount.p + nPairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      DCHECK(cudaMemcpyAsync(w.host + 12, w.bbox.p + 7, sizeof(int), cudaMemcpyDeviceToHost, s));
+      DCHECK(cudaStreamSynchronize(s));
+      nCand = (uint32_t)w.host[14];
+      if (nCand <= cap) break;
+      w.candCap = nCand + nCand / 2;  // overflow: the list was truncated, redo with room
+    }
+    w.candCap = std::max<uint32_t>(w.candCap, nCand + nCand / 4 + 1024);
+    w.nCells = (uint32_t)w.host[9];
+    if (w.host[12]) { w.failed = true; if (launches) *launches += L; return 0; }
+    if (nCand) {
+      L += launchExclusiveScan(s, w.candHit.p, (uint64_t)nCand + 1, w.scanScratch.p);
+      DCHECK(cudaMemcpyAsync(w.host + 10, w.candHit.p + nCand, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      DCHECK(cudaStreamSynchronize(s));
+      nHit = (uint32_t)w.host[10];
+    }
+    DCHECK(w.triList.reserve(nHit + 1)); DCHECK(w.otherTri.reserve(nHit + 1));
+    if (nHit) {
+      k_compact_hits<<<gridFor(nCand, kThreads), kThreads, 0, s>>>(w.hitCount.p + nPairs, w.candCap, w.cand.p, w.triRec.p,
+                                                                  w.candHit.p, w.triList.p, w.otherTri.p); ++L;
     }
   }
   DCHECK(w.floorList.reserve(nFloor + 1));

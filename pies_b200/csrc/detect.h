@@ -26,7 +26,9 @@ struct DetectWork {
   DevBuf<uint32_t> vals /* sorted: member triangle of every (cell, member) pair */, tmpVals, heads, cellStart, sortHist,
       incVals, incTmpVals, ticket, nodeDone;
   DevBuf<uint4> triList, uTri;     // full list (canonical order) and distinct contacts
-  DevBuf<uint32_t> otherTri, uStart, uHeads, uIncPtr, uInc;
+  DevBuf<uint32_t> otherTri, uStart, uHeads, uIncPtr, uInc, candHit;
+  DevBuf<uint2> cand;               // candidate (point node, triangle) pairs of the narrow phase, canonical order
+  uint32_t candCap = 0;
   DevBuf<uint64_t> uIncNode;
   DevBuf<float> uW;
   uint32_t nUnique = 0, nTouched = 0;

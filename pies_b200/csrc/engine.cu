@@ -325,6 +325,14 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
         return failCuda(s, s->blocks->lastError, "rebuildBlocks", __LINE__);
       }
       s->launches += LB;
+      const BlockWork& bw = *s->blocks;
+      ClusterTables ct{bw.heads.p + bw.nTouched, bw.start.p, bw.vals.p, bw.clusterOf.p, bw.slotOf.p, bw.gsClass.p, bw.nTouched};
+      int LC = s->contact ? prepareClusterSweeps(*s->contact, st, lists, ct) : 0;
+      if (LC < 0) {
+        cudaEventDestroy(tick0); cudaEventDestroy(tick1);
+        return failCuda(s, cudaErrorMemoryAllocation, "prepareClusterSweeps", __LINE__);
+      }
+      s->launches += LC;
     }
     timer.end();
     float4* contribC = s->contact ? s->contact->contribC.p : nullptr;

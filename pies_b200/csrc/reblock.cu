@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kThreads) k_assign_dynamic(uint32_t nT, uint32
                                                              const uint32_t* __restrict__ blkOff,
                                                              const uint32_t* __restrict__ nodes, int* __restrict__ blockNodes,
                                                              uint32_t* __restrict__ slotOf, uint32_t* __restrict__ blockCount,
+                                                             uint32_t* __restrict__ clusterOf, uint8_t* __restrict__ gsClass,
                                                              uint32_t* __restrict__ nBlocksOut) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) *nBlocksOut = nStatic + (nT ? blkOff[*nClustersPtr] : 0u);
@@ -130,7 +131,10 @@ __global__ void __launch_bounds__(kThreads) k_assign_dynamic(uint32_t nT, uint32
   uint32_t slot = blk * 32u + (rank & 31u);
   blockNodes[slot] = (int)nodes[j];
   slotOf[nodes[j]] = slot;
-  if ((rank & 31u) == 0u) blockCount[blk] = min(32u, start[c + 1] - start[c] - rank);
+  const uint32_t size = start[c + 1] - start[c];
+  clusterOf[nodes[j]] = c;
+  gsClass[nodes[j]] = size <= 32u ? 1 : 2;  // 1: the whole cluster is one block (in-warp ordered sweeps), 2: dataflow sweeps
+  if ((rank & 31u) == 0u) blockCount[blk] = min(32u, size - rank);
 }
 
 // storage of every block's inverse: m x m floats (rounded up to 16 B), offsets by exclusive scan
@@ -290,7 +294,9 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   RCHECK(w.nBlocksDev.reserve(4));
   RCHECK(w.flag.reserve(n + 2)); RCHECK(w.parent.reserve(n + 1)); RCHECK(w.slotOf.reserve(n + 1));
   RCHECK(w.dirty.reserve(nStatic + 1));
+  RCHECK(w.clusterOf.reserve(n + 1)); RCHECK(w.gsClass.reserve(n + 1));
   RCHECK(w.scanScratch.reserve(scanScratchElems(std::max<uint64_t>(n + 2, w.scanCap))));
+  RCHECK(cudaMemsetAsync(w.gsClass.p, 0, n + 1, s));
   uint32_t nT = 0;
   if (c.nUnique) {
     k_touched_flags<<<gridFor(n + 1, kThreads), kThreads, 0, s>>>(n, c.incPtr, w.flag.p, w.parent.p); ++L;
@@ -333,7 +339,8 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
                                                                                     w.slotOf.p, w.blockCount.p, w.dirty.p); ++L;
   k_assign_dynamic<<<gridFor(std::max(nT, 1u), kThreads), kThreads, 0, s>>>(nT, nStatic, w.heads.p + nT, w.heads.p, w.start.p,
                                                                            w.blkOff.p, w.vals.p, w.blockNodes.p, w.slotOf.p,
-                                                                           w.blockCount.p, w.nBlocksDev.p); ++L;
+                                                                           w.blockCount.p, w.clusterOf.p, w.gsClass.p,
+                                                                           w.nBlocksDev.p); ++L;
   k_block_sizes<<<gridFor(bound + 1, kThreads), kThreads, 0, s>>>(bound, w.nBlocksDev.p, w.blockCount.p, w.blockOff.p); ++L;
   L += launchExclusiveScan(s, w.blockOff.p, bound + 1, w.scanScratch.p);
   k_block_factor<<<gridFor(bound, kFactorWarps), kFactorWarps * 32, 0, s>>>(nStatic, w.nBlocksDev.p, S, c, w.blockNodes.p,
@@ -341,6 +348,7 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
                                                                            w.blockInv.p, w.blockMeta.p); ++L;
   pw.blockNodes = w.blockNodes.p; pw.blockInv = w.blockInv.p; pw.blockMeta = w.blockMeta.p; pw.nBlocks = bound;
   pw.nBlocksDev = w.nBlocksDev.p;
+  w.nTouched = nT;
   if (launches) *launches += L;
   return 0;
 }

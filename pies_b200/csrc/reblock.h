@@ -15,9 +15,11 @@ struct BlockWork {
   DevBuf<uint32_t> slotOf;       // node -> block * 32 + lane
   DevBuf<uint32_t> flag, parent, vals, tmpVals, heads, start, blkOff, sortHist, scanScratch, nBlocksDev;
   DevBuf<uint64_t> keys, tmpKeys;
-  DevBuf<uint8_t> dirty;
+  DevBuf<uint8_t> dirty, gsClass;  // gsClass[node]: 0 not in a contact, 1 small cluster (<= 32 nodes), 2 large cluster
+  DevBuf<uint32_t> clusterOf;      // node -> contact cluster (touched nodes only)
   uint32_t* host = nullptr;      // pinned, 4 words
-  uint32_t nBlocksBound = 0;
+  uint32_t nBlocksBound = 0, nTouched = 0;
+  // contact clusters of this substep: nodes sorted by cluster in vals[start[c] .. start[c+1]), count at heads[nTouched]
   uint64_t scanCap = 0;
   cudaError_t lastError = cudaSuccess;
 };
