@@ -184,6 +184,10 @@ int pies_b200_get_static_collisions(PiesB200Solver* s, uint32_t* ids); /* canoni
 /* Triangle-hash occupancy of the last detect(): cells sorted by (x,y,z), members ascending. */
 int pies_b200_tri_occupancy_counts(PiesB200Solver* s, uint64_t* nCells, uint64_t* nMembers);
 int pies_b200_get_tri_occupancy(PiesB200Solver* s, int64_t* cellsXYZ, uint32_t* counts, uint32_t* members);
+/* Node-hash occupancy (SpatialHash<Node>, reference Solver.cpp:81-82) of the last PBD iteration, same layout. */
+int pies_b200_detect_nodes(PiesB200Solver* s); /* rebuilds only the node hash on the current state */
+int pies_b200_node_occupancy_counts(PiesB200Solver* s, uint64_t* nCells, uint64_t* nMembers);
+int pies_b200_get_node_occupancy(PiesB200Solver* s, int64_t* cellsXYZ, uint32_t* counts, uint32_t* members);
 int pies_b200_get_stats(const PiesB200Solver* s, PiesB200Stats* out);
 
 /* ---- [additive] per-kernel probes: run the device functions of the hot kernels on caller data ---- */

@@ -372,6 +372,15 @@ int pies_b200_get_tri_occupancy(PiesB200Solver* s, int64_t* cells, uint32_t* cou
     return PIES_B200_OK;
   });
 }
+int pies_b200_detect_nodes(PiesB200Solver* s) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::pbdHashOnly(s); }); }
+int pies_b200_node_occupancy_counts(PiesB200Solver* s, uint64_t* nCells, uint64_t* nMembers) {
+  if (!s || !nCells || !nMembers) return PIES_B200_EINVAL;
+  return pies::pbdOccupancyCounts(s, nCells, nMembers);
+}
+int pies_b200_get_node_occupancy(PiesB200Solver* s, int64_t* cells, uint32_t* counts, uint32_t* members) {
+  if (!s || !cells || !counts || !members) return PIES_B200_EINVAL;
+  return guarded(s, [&]() { return pies::pbdOccupancy(s, cells, counts, members); });
+}
 int pies_b200_get_stats(const PiesB200Solver* s, PiesB200Stats* out) {
   if (!s || !out) return PIES_B200_EINVAL;
   *out = s->stats;

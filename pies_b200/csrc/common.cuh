@@ -35,6 +35,16 @@ __device__ __forceinline__ float4 ldStream(const float4* p) { return __ldcs(p); 
 __device__ __forceinline__ uint4 ldStream(const uint4* p) { return __ldcs(p); }
 __device__ __forceinline__ void stStream(float4* p, float4 v) { __stcs(p, v); }
 
+// Acquire / release accesses of the per-node progress counters of the ordered (dataflow) sweeps.
+__device__ __forceinline__ uint32_t ldAcquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stRelease(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ float warpSum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -104,15 +104,6 @@ int launchGatherContacts(cudaStream_t s, uint32_t n, const ContactLists& c, cons
 // chunk granularity the false dependencies serialise a percolated pile, 29 ms per sweep instead of 1.1 ms.)
 constexpr int kGsThreads = 256;
 
-__device__ __forceinline__ uint32_t ldAcquire(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void stRelease(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 struct StabilizeOp {
   float4* q;
   float4* prev;

@@ -417,15 +417,12 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
   return PIES_B200_OK;
 }
 
-int tickPBD(PiesB200Solver* s, bool) {
-  return fail(s, PIES_B200_EINVAL, "PBD path (reference Solver::tickPBD, Solver.cpp:40-160) is not built yet in this round");
-}
-
 }  // namespace pies
 
 PiesB200Solver::~PiesB200Solver() {
   if (detect) { if (detect->host) cudaFreeHost(detect->host); delete detect; }
   delete contact;
+  pies::destroyPbdWork(pbd);
   if (blocks) { if (blocks->host) cudaFreeHost(blocks->host); delete blocks; }
   if (hostPacked) cudaFreeHost(hostPacked);
   if (hostFlag) cudaFreeHost(hostFlag);

@@ -40,6 +40,8 @@ struct DevBuf {
 struct DetectWork;   // detect.cu
 struct ContactWork;  // contact.cu
 struct BlockWork;    // reblock.cu
+struct PbdWork;      // pbd.cu
+void destroyPbdWork(PbdWork* w);
 
 }  // namespace pies
 
@@ -85,6 +87,7 @@ struct PiesB200Solver {
   pies::DetectWork* detect = nullptr;
   pies::ContactWork* contact = nullptr;
   pies::BlockWork* blocks = nullptr;
+  pies::PbdWork* pbd = nullptr;
 
   float* hostPacked = nullptr;  // pinned, 3 floats per node
   size_t hostPackedCap = 0;
@@ -105,6 +108,9 @@ int tickPBD(PiesB200Solver* s, bool refreshMirror);
 int refreshVertexMirror(PiesB200Solver* s);
 int uploadStateArrays(PiesB200Solver* s, const float* pos, const float* prev, const float* vel);
 int runDetection(PiesB200Solver* s, ContactLists& lists);
+int pbdHashOnly(PiesB200Solver* s);
+int pbdOccupancyCounts(PiesB200Solver* s, uint64_t* nCells, uint64_t* nMembers);
+int pbdOccupancy(PiesB200Solver* s, int64_t* cellsXYZ, uint32_t* counts, uint32_t* members);
 }  // namespace pies
 
 #define PIES_CHECK(s, expr)                                                        \

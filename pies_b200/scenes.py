@@ -86,3 +86,62 @@ def add_tetgen_cube(ref, ours=None, side=8.0, n=8, origin=(0.0, 3.07, 0.0), dens
         ours.addTetMeshVolume(points, tets, faces, (0, 0, 0), density, strain_w, min_strain, max_strain, volume_w,
                               compression, stretching)
     return points, tets.astype(np.uint32), faces.astype(np.uint32)
+
+
+# ---- PBD scenes (config 2 and its small relatives) ------------------------------------------------------
+S2_OPTIONS = dict(iterations=4, timeSubsteps=1, solver="PBD", gridSpacing=2.0)
+
+
+def rope_points(n, radius=0.25, helix_radius=4.0, rise_per_turn=1.0, y0=1.0):
+    """n points spaced 2*radius apart (arc length) on a helix: consecutive nodes touch exactly, turns are
+    `rise_per_turn` apart so nothing overlaps at rest."""
+    spacing = 2.0 * radius
+    turn_len = np.sqrt((2 * np.pi * helix_radius) ** 2 + rise_per_turn ** 2)
+    s = spacing * np.arange(n, dtype=np.float64)
+    ang = 2 * np.pi * s / turn_len
+    return np.stack([helix_radius * np.cos(ang), y0 + rise_per_turn * s / turn_len, helix_radius * np.sin(ang)],
+                    axis=1).astype(np.float32)
+
+
+def spiral_points(n, radius=0.25, arm_gap=0.45, y0=1.0):
+    """n points spaced 2*radius apart on a flat Archimedean spiral whose arms are `arm_gap` apart: with
+    arm_gap < 2*radius neighbouring arms overlap, so node-node collisions are active from the first tick.
+    (The reference's PBD blows up when a hanging chain lands on the floor - its distance projection moves only
+    node 0 of a link, Constraints.cpp:11-37 - while a flat coil that lands all at once stays bounded.)"""
+    b = arm_gap / (2 * np.pi)
+    th = np.empty(n)
+    t = 2 * np.pi * 2.0          # start two turns out so the first turn is not degenerate
+    for i in range(n):
+        th[i] = t
+        t += 2.0 * radius / (b * np.sqrt(1.0 + t * t))
+    r = b * th
+    return np.stack([r * np.cos(th), np.full(n, y0), r * np.sin(th)], axis=1).astype(np.float32)
+
+
+def build_rope(s, n=100000, radius=0.25, w=1.0, pinned=True, shape="helix", **kw):
+    """S2: n-node distance-constraint chain, invMass 1, links created even-then-odd (so the reference's
+    sequential sweep is a 2-colour sweep), first node position-constrained."""
+    pts = rope_points(n, radius, **kw) if shape == "helix" else spiral_points(n, radius, **kw)
+    links = np.concatenate([np.arange(0, n - 1, 2), np.arange(1, n - 1, 2)]).astype(np.uint32)
+    if hasattr(s, "appendNodes"):       # pies_b200.Solver (bulk)
+        s.appendNodes(pts, None, radius, 1.0)
+        s.appendDistanceConstraints(np.stack([links, links + 1], axis=1), w)
+        if pinned:
+            s.appendPositionConstraints(np.array([0], np.uint32), 1.0)
+    else:                               # oracle RefSolver (white-box, one call per element)
+        if hasattr(s, "reserve"):
+            s.reserve(nodes=n, dist=n)
+        for p in pts:
+            s.appendNode(p, (0, 0, 0), radius, 1.0)
+        for a in links:
+            s.appendDistance(int(a), int(a) + 1, w)
+        if pinned:
+            s.appendPosition(0, 1.0)
+    return n
+
+
+def build_pbd_boxes(s):
+    """Distance-constraint boxes (createBox): one resting on the floor, one dropped onto it, one falling beside them."""
+    s.createBox((0.0, 0.6, 0.0), 1.0, 0.5)
+    s.createBox((0.3, 5.9, 0.2), 1.0, 0.5)
+    s.createBox((9.0, 3.0, 1.0), 1.0, 0.5)

@@ -111,6 +111,9 @@ _SIGNATURES = {
     "pies_b200_get_static_collisions": (C.c_int, [_vp, _u32p]),
     "pies_b200_tri_occupancy_counts": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pies_b200_get_tri_occupancy": (C.c_int, [_vp, _i64p, _u32p, _u32p]),
+    "pies_b200_detect_nodes": (C.c_int, [_vp]),
+    "pies_b200_node_occupancy_counts": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "pies_b200_get_node_occupancy": (C.c_int, [_vp, _i64p, _u32p, _u32p]),
     "pies_b200_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "pies_b200_probe_tet_projection": (C.c_int, [C.c_uint32, _f32p, _f32p, C.c_float, C.c_float, _f32p]),
     "pies_b200_probe_volume_projection": (C.c_int, [C.c_uint32, _f32p, _f32p, C.c_float, C.c_float, _f32p]),
@@ -370,6 +373,19 @@ class Solver:
         members = np.empty(nm.value, np.uint32)
         if nc.value:
             self._ck(lib().pies_b200_get_tri_occupancy(self.h, cells, counts, members))
+        return cells, counts, members
+
+    def detectNodes(self):
+        self._ck(lib().pies_b200_detect_nodes(self.h))
+
+    def nodeOccupancy(self):
+        """Node-hash cells of the last PBD iteration: (cells[nc,3] sorted by (x,y,z), counts[nc], members ascending per cell)."""
+        nc, nm = C.c_uint64(), C.c_uint64()
+        self._ck(lib().pies_b200_node_occupancy_counts(self.h, C.byref(nc), C.byref(nm)))
+        cells = np.empty((nc.value, 3), np.int64); counts = np.empty(nc.value, np.uint32)
+        members = np.empty(nm.value, np.uint32)
+        if nc.value:
+            self._ck(lib().pies_b200_get_node_occupancy(self.h, cells, counts, members))
         return cells, counts, members
 
     def stats(self):

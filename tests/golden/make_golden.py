@@ -217,6 +217,44 @@ def clusters():
     save("clusters", **out)
 
 
+def pbd():
+    """PBD path (config 2 ingredients): distance boxes colliding (node-node hash), a pinned 2 000-node rope coiling
+    on the floor, cloth sheets with bend constraints; plus the node-hash occupancy on a reference state."""
+    out = {}
+    r = RefSolver(**scenes.S2_OPTIONS)
+    scenes.build_pbd_boxes(r)
+    for t in range(1, 61):
+        r.tick()
+        if t in (1, 10, 25, 40, 60):
+            out["boxes_pos%d" % t] = r.positions; out["boxes_vel%d" % t] = r.velocities
+        if t == 40:
+            cells, cnts, members = r.nodeOccupancy()
+            out["boxes_occ_cells"] = cells; out["boxes_occ_counts"] = cnts; out["boxes_occ_members"] = members
+    r = RefSolver(**scenes.S2_OPTIONS)
+    scenes.build_rope(r, n=2000, helix_radius=2.0)
+    for t in range(1, 21):      # the reference blows up once the hanging chain starts to land (tick ~25): stop before
+        r.tick()
+        if t in (1, 10, 20):
+            out["rope_pos%d" % t] = r.positions; out["rope_vel%d" % t] = r.velocities
+    r = RefSolver(**scenes.S2_OPTIONS)
+    scenes.build_rope(r, n=1500, shape="spiral", pinned=False)
+    for t in range(1, 9):       # overlapping arms: collisions from tick 1; the reference's own iteration diverges by tick ~15
+        r.tick()
+        if t in (1, 2, 3, 5, 8):
+            out["spiral_pos%d" % t] = r.positions; out["spiral_vel%d" % t] = r.velocities
+    r = RefSolver(**scenes.S2_OPTIONS)
+    r.createSheet((0.0, 2.0, 0.0), 0.5, 1.0, 0.8)
+    r.createBendSheet((12.0, 2.0, 0.0), 0.5, 0.6)
+    for t in range(1, 11):      # NaN in the reference before tick 20
+        r.tick()
+        if t in (1, 5, 10):
+            out["sheets_pos%d" % t] = r.positions; out["sheets_vel%d" % t] = r.velocities
+    r = RefSolver(**scenes.S2_OPTIONS)
+    r.createTetBox((0.0, 1.0, 0.0), 0.5, (0, 0, 0), 0.5, 1.0, True)   # hinged: position constraints; tets ignored? no: F5
+    out["hinged_counts"] = np.array([r.count(k) for k in ("position", "distance", "tet", "bend")])
+    save("pbd", **out)
+
+
 if __name__ == "__main__":
     import sys
     lib().pref_srand(1)
@@ -231,3 +269,4 @@ if __name__ == "__main__":
     tetgen_cube()
     stack()
     clusters()
+    pbd()
