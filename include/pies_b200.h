@@ -190,6 +190,25 @@ int pies_b200_node_occupancy_counts(PiesB200Solver* s, uint64_t* nCells, uint64_
 int pies_b200_get_node_occupancy(PiesB200Solver* s, int64_t* cellsXYZ, uint32_t* counts, uint32_t* members);
 int pies_b200_get_stats(const PiesB200Solver* s, PiesB200Stats* out);
 
+/* ---- [additive] slab-partitioned (multi-GPU) hosts: one solver per GPU holds the bodies of its slab plus ghost
+ *      copies of the neighbouring slabs' boundary bodies; between the phases below the host overwrites the ghost
+ *      nodes in the device state arrays with their owners' values (NCCL).  pies_b200_tick_pd() is exactly
+ *      begin; per substep { substep_begin; iterations x iteration; substep_end }; end.
+ *      (reference Solver::tickPD, Solver.cpp:162-486: :229-262 / :264-365 / :367-484) ---- */
+int pies_b200_pd_tick_begin(PiesB200Solver* s);
+int pies_b200_pd_substep_begin(PiesB200Solver* s); /* inertia, detection, preconditioner blocks */
+int pies_b200_pd_iteration(PiesB200Solver* s);     /* one local/global iteration */
+int pies_b200_pd_substep_end(PiesB200Solver* s);   /* stabilisation, velocity update, friction */
+int pies_b200_pd_tick_end(PiesB200Solver* s);
+/* Device pointers of the node state: float4 per node, q = (x,y,z,invMass), prev = (x,y,z,radius), vel = (vx,vy,vz,0). */
+int pies_b200_device_state(PiesB200Solver* s, void** q, void** prev, void** vel, uint32_t* n);
+/* order[t] = position of local triangle t in the canonical collision-list order of the GLOBAL scene
+ * restricted to the local triangles; NULL restores the local thread striping. */
+int pies_b200_set_triangle_order(PiesB200Solver* s, uint32_t n, const uint32_t* order);
+/* mask[i] != 0: node i is owned by this solver (others are ghosts); only used for counting. */
+int pies_b200_set_owned_nodes(PiesB200Solver* s, uint32_t n, const uint8_t* mask);
+int pies_b200_count_owned_contacts(PiesB200Solver* s, uint32_t* nTri, uint32_t* nFloor);
+
 /* ---- [additive] per-kernel probes: run the device functions of the hot kernels on caller data ---- */
 /* Tet strain / volume projections (reference Constraints.cpp:76-128, :205-255): pos 12 floats,
  * qinv 9 floats column-major per tet; out 12 floats (projected[0..3]). */

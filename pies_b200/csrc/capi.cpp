@@ -372,6 +372,57 @@ int pies_b200_get_tri_occupancy(PiesB200Solver* s, int64_t* cells, uint32_t* cou
     return PIES_B200_OK;
   });
 }
+// ---- tick phases + halo support for slab-partitioned hosts ----
+int pies_b200_pd_tick_begin(PiesB200Solver* s) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::pdTickBegin(s); }); }
+int pies_b200_pd_substep_begin(PiesB200Solver* s) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::pdSubstepBegin(s); }); }
+int pies_b200_pd_iteration(PiesB200Solver* s) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::pdIteration(s); }); }
+int pies_b200_pd_substep_end(PiesB200Solver* s) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::pdSubstepEnd(s); }); }
+int pies_b200_pd_tick_end(PiesB200Solver* s) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::pdTickEnd(s, false); }); }
+int pies_b200_device_state(PiesB200Solver* s, void** q, void** prev, void** vel, uint32_t* n) {
+  return guarded(s, [&]() {
+    cudaSetDevice(s->device);
+    int rc = pies::ensureBuilt(s);
+    if (rc) return rc;
+    if (q) *q = s->q.p;
+    if (prev) *prev = s->prev.p;
+    if (vel) *vel = s->vel.p;
+    if (n) *n = s->n;
+    // the caller may write ghost-node values straight into these arrays: the host copies are stale from now on
+    s->deviceNewer = true; s->mirrorStale = true;
+    return PIES_B200_OK;
+  });
+}
+int pies_b200_set_triangle_order(PiesB200Solver* s, uint32_t n, const uint32_t* order) {
+  return guarded(s, [&]() {
+    cudaSetDevice(s->device);
+    if (!order || !n) { s->haveTriOrder = false; return PIES_B200_OK; }
+    if (n != s->scene.triCount()) return pies::fail(s, PIES_B200_EINVAL, "triangle order: one entry per triangle expected");
+    std::vector<uint8_t> seen(n, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+      if (order[i] >= n || seen[order[i]]) return pies::fail(s, PIES_B200_EINVAL, "triangle order is not a permutation");
+      seen[order[i]] = 1;
+    }
+    PIES_CHECK(s, s->triOrder.upload(order, n, s->stream));
+    PIES_CHECK(s, cudaStreamSynchronize(s->stream));
+    s->haveTriOrder = true;
+    return PIES_B200_OK;
+  });
+}
+int pies_b200_set_owned_nodes(PiesB200Solver* s, uint32_t n, const uint8_t* mask) {
+  return guarded(s, [&]() {
+    cudaSetDevice(s->device);
+    if (!mask || !n) { s->haveOwnedMask = false; return PIES_B200_OK; }
+    if (n != s->scene.nodeCount()) return pies::fail(s, PIES_B200_EINVAL, "owned mask: one entry per node expected");
+    PIES_CHECK(s, s->ownedMask.upload(mask, n, s->stream));
+    PIES_CHECK(s, cudaStreamSynchronize(s->stream));
+    s->haveOwnedMask = true;
+    return PIES_B200_OK;
+  });
+}
+int pies_b200_count_owned_contacts(PiesB200Solver* s, uint32_t* nTri, uint32_t* nFloor) {
+  if (!s || !nTri || !nFloor) return PIES_B200_EINVAL;
+  return guarded(s, [&]() { cudaSetDevice(s->device); return pies::countOwnedContacts(s, nTri, nFloor); });
+}
 int pies_b200_detect_nodes(PiesB200Solver* s) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::pbdHashOnly(s); }); }
 int pies_b200_node_occupancy_counts(PiesB200Solver* s, uint64_t* nCells, uint64_t* nMembers) {
   if (!s || !nCells || !nMembers) return PIES_B200_EINVAL;

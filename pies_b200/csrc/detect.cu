@@ -23,7 +23,10 @@ static inline int gridFor(uint64_t n, int threads) { return (int)((n + threads -
 
 // ---- 1. ranges -----------------------------------------------------------------------------
 // bbox[0..2] = min cell, bbox[3..5] = max cell (inclusive), bbox[6] = bad-input flag, bbox[7] = hang-guard flag
-__device__ __forceinline__ uint32_t canonicalRank(uint32_t t, uint32_t nTri, uint32_t T) {
+// `order` (optional) overrides the striping: order[t] = position of local triangle t in the canonical order of the
+// GLOBAL scene restricted to the local triangles (slab-partitioned solvers).
+__device__ __forceinline__ uint32_t canonicalRank(uint32_t t, uint32_t nTri, uint32_t T, const uint32_t* __restrict__ order) {
+  if (order) return order[t];
   // thread (t % T) handles t, t+T, ...; per-thread lists are concatenated in thread order (Solver.cpp:714,852-873)
   uint32_t th = t % T, k = t / T;
   uint32_t full = nTri / T, rem = nTri % T;  // threads < rem own full+1 triangles
@@ -31,6 +34,7 @@ __device__ __forceinline__ uint32_t canonicalRank(uint32_t t, uint32_t nTri, uin
 }
 
 __global__ void __launch_bounds__(kThreads) k_tri_ranges(uint32_t nTri, uint32_t threadCount, float floorLimit,
+                                                         const uint32_t* __restrict__ order,
                                                          const uint32_t* __restrict__ tri,
                                                          const float4* __restrict__ q, const float4* __restrict__ prev,
                                                          int4* __restrict__ triMin, uint4* __restrict__ triRec,
@@ -60,7 +64,7 @@ __global__ void __launch_bounds__(kThreads) k_tri_ranges(uint32_t nTri, uint32_t
     triMin[t] = make_int4(mx, my, mz, 0);
     triRec[t] = make_uint4(a, b, c, lx | (ly << 8) | (lz << 16));
     cnt[t] = cells;
-    uint32_t rank = canonicalRank(t, nTri, threadCount);
+    uint32_t rank = canonicalRank(t, nTri, threadCount, order);
     cntRank[rank] = cells;
     // floor test per corner (Solver.cpp:829-834)
     floorRank[rank] = (p0.y < floorLimit ? 1u : 0u) + (p1.y < floorLimit ? 1u : 0u) + (p2.y < floorLimit ? 1u : 0u);
@@ -83,12 +87,13 @@ __global__ void __launch_bounds__(kThreads) k_tri_ranges(uint32_t nTri, uint32_t
 
 // floor list in canonical order: scanned floorRank gives each triangle's slot
 __global__ void __launch_bounds__(kThreads) k_floor_write(uint32_t nTri, uint32_t threadCount, float floorLimit,
+                                                          const uint32_t* __restrict__ order,
                                                           const uint4* __restrict__ triRec, const float4* __restrict__ q,
                                                           const uint32_t* __restrict__ floorRank,
                                                           uint32_t* __restrict__ outFloor) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nTri) return;
-  uint32_t rank = canonicalRank(t, nTri, threadCount);
+  uint32_t rank = canonicalRank(t, nTri, threadCount, order);
   uint32_t beg = floorRank[rank], end = floorRank[rank + 1];
   if (beg == end) return;
   uint4 r = triRec[t];
@@ -160,6 +165,7 @@ struct NarrowParams {
   uint32_t nTri, threadCount;
   float threshold;
   float cullMargin;
+  const uint32_t* order;
 };
 
 template <bool WRITE>
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) k_pair_filter(NarrowParams np, KeyPa
   uint32_t dz = (uint32_t)((int)(key & ((1ull << kp.bitsZ) - 1ull)) + kp.minZ - mn.z);
   uint32_t dy = (uint32_t)((int)((key >> kp.bitsZ) & ((1ull << kp.bitsY) - 1ull)) + kp.minY - mn.y);
   uint32_t dx = (uint32_t)((int)(key >> (kp.bitsY + kp.bitsZ)) + kp.minX - mn.x);
-  uint32_t slot = rankOff[canonicalRank(t, np.nTri, np.threadCount)] + (dx * ly + dy) * lz + dz;
+  uint32_t slot = rankOff[canonicalRank(t, np.nTri, np.threadCount, np.order)] + (dx * ly + dy) * lz + dz;
   if (!WRITE && j == 0) candCount[nPairs] = 0;
   if (lx > 20u || ly > 20u || lz > 20u) {  // sweptTriRange cap: inserted but queries nothing
     if (!WRITE) candCount[slot] = 0;
@@ -375,7 +381,7 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
   DCHECK(cudaMemsetAsync(w.cnt.p + nTri, 0, 2 * sizeof(uint32_t), s));
   DCHECK(cudaMemsetAsync(w.cntRank.p + nTri, 0, 2 * sizeof(uint32_t), s));
   DCHECK(cudaMemsetAsync(w.floorRank.p + nTri, 0, 2 * sizeof(uint32_t), s));
-  k_tri_ranges<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, T, floorLimit, in.tri, in.q, in.prev, w.triMin.p, w.triRec.p,
+  k_tri_ranges<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, T, floorLimit, in.order, in.tri, in.q, in.prev, w.triMin.p, w.triRec.p,
                                                            w.cnt.p, w.cntRank.p, w.floorRank.p, w.aabbLo.p, w.aabbHi.p,
                                                            w.bbox.p); ++L;
   L += launchExclusiveScan(s, w.cnt.p, nTri + 1, w.scanScratch.p);
@@ -390,7 +396,7 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
   uint64_t nPairs = (uint32_t)w.host[8];
   uint32_t nFloor = (uint32_t)w.host[11];
   w.nPairs = nPairs;
-  NarrowParams np{nTri, T, in.threshold, in.threshold + 1e-3f};
+  NarrowParams np{nTri, T, in.threshold, in.threshold + 1e-3f, in.order};
   uint32_t nHit = 0;
   if (nPairs) {
     KeyPack kp{w.host[0], w.host[1], w.host[2], 0, 0};
@@ -454,7 +460,7 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
   }
   DCHECK(w.floorList.reserve(nFloor + 1));
   if (nFloor) {
-    k_floor_write<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, T, floorLimit, w.triRec.p, in.q, w.floorRank.p,
+    k_floor_write<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, T, floorLimit, in.order, w.triRec.p, in.q, w.floorRank.p,
                                                               w.floorList.p); ++L;
   }
   out.tri = w.triList.p; out.floorNode = w.floorList.p; out.nTri = nHit; out.nFloor = nFloor;

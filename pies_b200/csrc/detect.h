@@ -14,6 +14,7 @@ struct DetectInput {
   uint32_t nTri, nNodes, threadCount;
   float threshold;       // collisionThresholdDistance
   float floorLimit;      // floorHeight + collisionThickness
+  const uint32_t* order = nullptr;  // optional canonical-order override (device), see canonicalRank
 };
 
 struct DetectWork {

@@ -257,7 +257,8 @@ int runDetection(PiesB200Solver* s, ContactLists& lists) {
   }
   if (!s->contact) s->contact = new ContactWork();
   DetectInput in{s->triIds.p, s->q.p, s->prev.p, s->scene.triCount(), s->n, s->opt.threadCount,
-                 s->opt.collisionThresholdDistance, s->opt.floorHeight + s->opt.collisionThickness};
+                 s->opt.collisionThresholdDistance, s->opt.floorHeight + s->opt.collisionThickness,
+                 (s->haveTriOrder && s->triOrder.cap >= s->scene.triCount()) ? s->triOrder.p : nullptr};
   int L = 0;
   lists = ContactLists{};
   if (detectTriangles(*s->detect, s->stream, in, lists, &L) != 0)
@@ -274,136 +275,209 @@ int runDetection(PiesB200Solver* s, ContactLists& lists) {
   return PIES_B200_OK;
 }
 
-int tickPD(PiesB200Solver* s, bool refreshMirror) {
+// ---- PD tick, split into phases so a slab-partitioned host can exchange halos between them.
+// tickPD() below is the plain composition; the C ABI also exposes the phases (pies_b200_pd_*).
+struct PdTickCtx {
+  PhaseTimer timer;
+  cudaEvent_t tick0 = nullptr, tick1 = nullptr;
+  uint64_t launches0 = 0;
+  ContactLists lists;
+  bool inSubstep = false;
+  PdTickCtx(PiesB200Solver* s) : timer(s, g_eventPool) {}
+};
+
+void pdAbort(PiesB200Solver* s) {
+  PdTickCtx* c = static_cast<PdTickCtx*>(s->pdCtx);
+  if (!c) return;
+  if (c->tick0) cudaEventDestroy(c->tick0);
+  if (c->tick1) cudaEventDestroy(c->tick1);
+  delete c;
+  s->pdCtx = nullptr;
+}
+
+namespace {
+struct PdViews {
+  TetElems te; DistanceElems de; BendElems be; ClusterElems sh, go; CsrMatrix A; PcgWork pw;
+};
+PdViews pdViews(PiesB200Solver* s) {
+  const HostSystem& y = s->sys;
+  PdViews v;
+  v.te = TetElems{s->elemIds.p, s->elemQa.p, s->elemQb.p, s->elemPc.p, s->elemPd.p, y.nElems};
+  v.de = DistanceElems{s->distIds.p, s->distRestW.p, (uint32_t)s->scene.distW.size()};
+  v.be = BendElems{s->bendIds.p, s->bendAngleW.p, (uint32_t)s->scene.bendW.size()};
+  v.sh = ClusterElems{s->shapeOff.p, s->shapeIds.p, (uint32_t)s->scene.shapeW.size(), (uint32_t)s->scene.shapeId.size()};
+  v.go = ClusterElems{s->goalOff.p, s->goalIds.p, (uint32_t)s->scene.goalW.size(), (uint32_t)s->scene.goalId.size()};
+  v.A = CsrMatrix{s->rowPtr.p, s->col.p, s->val.p, s->n, (uint64_t)y.col.size(), s->rowBatch.p,
+                  (uint32_t)(y.rowBatch.empty() ? 0 : y.rowBatch.size() - 1)};
+  v.pw.r = s->pr.p; v.pw.p = s->pp.p; v.pw.p2 = s->pp2.p; v.pw.z = s->pz.p; v.pw.ap = s->pap.p; v.pw.delta = s->pdelta.p;
+  v.pw.partials = s->partials.p; v.pw.scalars = s->scalars.p; v.pw.flag = s->flag.p;
+  if (s->blocks) {  // the contact-aware blocks of the current substep (reblock.cu)
+    v.pw.blockNodes = s->blocks->cur.blockNodes; v.pw.blockInv = s->blocks->cur.blockInv;
+    v.pw.blockMeta = s->blocks->cur.blockMeta; v.pw.nBlocks = s->blocks->cur.nBlocks; v.pw.nBlocksDev = s->blocks->cur.nBlocksDev;
+  }
+  return v;
+}
+}  // namespace
+
+int pdTickBegin(PiesB200Solver* s) {
+  pdAbort(s);
   int rc = ensureBuilt(s);
   if (rc) return rc;
-  const uint32_t n = s->n;
   s->stats.substepsLastTick = 0;
   s->stats.projectionsLastTick = 0;
   s->stats.pcgIterationsLastTick = 0;
   s->stats.msLocal = s->stats.msGlobal = s->stats.msDetect = s->stats.msContact = s->stats.msOther = 0.0f;
   s->stats.msTetKernel = 0.0f; s->stats.tetKernelLaunches = 0;
-  uint64_t launches0 = s->launches;
+  PdTickCtx* c = new PdTickCtx(s);
+  c->launches0 = s->launches;
+  s->pdCtx = c;
+  if (!s->n) return PIES_B200_OK;
+  cudaEventCreate(&c->tick0); cudaEventCreate(&c->tick1);
+  cudaEventRecord(c->tick0, s->stream);
+  return PIES_B200_OK;
+}
+
+int pdSubstepBegin(PiesB200Solver* s) {
+  PdTickCtx* c = static_cast<PdTickCtx*>(s->pdCtx);
+  if (!c) return fail(s, PIES_B200_EINVAL, "pd_substep_begin outside pd_tick_begin/pd_tick_end");
+  const uint32_t n = s->n;
   if (!n) return PIES_B200_OK;
   cudaStream_t st = s->stream;
   const PiesB200Options& o = s->opt;
-  const HostSystem& y = s->sys;
   const float h = o.fixedTimestepSize / (float)o.timeSubsteps;
-  PhaseTimer timer(s, g_eventPool);
-  cudaEvent_t tick0, tick1;
-  cudaEventCreate(&tick0); cudaEventCreate(&tick1);
-  cudaEventRecord(tick0, st);
+  PhaseTimer& timer = c->timer;
+  int rc;
+  timer.begin(kPhOther);
+  s->launches += launchPredict(st, n, s->q.p, s->vel.p, s->msn.p, h);
+  timer.end();
 
-  TetElems te{s->elemIds.p, s->elemQa.p, s->elemQb.p, s->elemPc.p, s->elemPd.p, y.nElems};
-  DistanceElems de{s->distIds.p, s->distRestW.p, (uint32_t)s->scene.distW.size()};
-  BendElems be{s->bendIds.p, s->bendAngleW.p, (uint32_t)s->scene.bendW.size()};
-  ClusterElems sh{s->shapeOff.p, s->shapeIds.p, (uint32_t)s->scene.shapeW.size(), (uint32_t)s->scene.shapeId.size()};
-  ClusterElems go{s->goalOff.p, s->goalIds.p, (uint32_t)s->scene.goalW.size(), (uint32_t)s->scene.goalId.size()};
-  CsrMatrix A{s->rowPtr.p, s->col.p, s->val.p, n, (uint64_t)y.col.size(), s->rowBatch.p,
-              (uint32_t)(y.rowBatch.empty() ? 0 : y.rowBatch.size() - 1)};
-  PcgWork pw;
-  pw.r = s->pr.p; pw.p = s->pp.p; pw.p2 = s->pp2.p; pw.z = s->pz.p; pw.ap = s->pap.p; pw.delta = s->pdelta.p;
-  pw.partials = s->partials.p; pw.scalars = s->scalars.p; pw.flag = s->flag.p;
-
-  for (uint32_t sub = 0; sub < o.timeSubsteps; ++sub) {
-    timer.begin(kPhOther);
-    s->launches += launchPredict(st, n, s->q.p, s->vel.p, s->msn.p, h);
-    timer.end();
-
-    timer.begin(kPhDetect);
-    ContactLists lists;
-    if ((rc = runDetection(s, lists))) { cudaEventDestroy(tick0); cudaEventDestroy(tick1); return rc; }
-    // contact-aware preconditioner blocks for this substep's system matrix S + C_t
-    if (!s->blocks) {
-      s->blocks = new BlockWork();
-      PIES_CHECK(s, cudaMallocHost(&s->blocks->host, 4 * sizeof(uint32_t)));
-    }
-    {
-      int LB = 0;
-      if (rebuildBlocks(*s->blocks, st, n, A, s->blockNodes.p, s->blockInv.p, y.nBlocks, lists, s->q.p, pw, &LB) != 0) {
-        cudaEventDestroy(tick0); cudaEventDestroy(tick1);
-        return failCuda(s, s->blocks->lastError, "rebuildBlocks", __LINE__);
-      }
-      s->launches += LB;
-      const BlockWork& bw = *s->blocks;
-      ClusterTables ct{bw.heads.p + bw.nTouched, bw.start.p, bw.vals.p, bw.clusterOf.p, bw.slotOf.p, bw.gsClass.p, bw.nTouched};
-      int LC = s->contact ? prepareClusterSweeps(*s->contact, st, lists, ct) : 0;
-      if (LC < 0) {
-        cudaEventDestroy(tick0); cudaEventDestroy(tick1);
-        return failCuda(s, cudaErrorMemoryAllocation, "prepareClusterSweeps", __LINE__);
-      }
-      s->launches += LC;
-    }
-    timer.end();
-    float4* contribC = s->contact ? s->contact->contribC.p : nullptr;
-
-    for (uint32_t it = 0; it < o.iterations; ++it) {
-      timer.begin(kPhTetKernel);
-      s->launches += launchTetElems(st, te, s->q.p, s->contrib.p + y.baseTet);
-      timer.end();
-      timer.begin(kPhLocal);
-      s->launches += launchDistance(st, de, s->q.p, s->contrib.p + y.baseDist);
-      s->launches += launchBend(st, be, s->q.p, s->contrib.p + y.baseBend);
-      s->launches += launchShape(st, sh, s->shapeMat.p, s->shapeQinv.p, s->shapeQuat.p, s->shapeW.p, s->q.p, s->contrib.p + y.baseShape);
-      s->launches += launchGoal(st, go, s->goalMat.p, s->goalXform.p, s->goalW.p, s->contrib.p + y.baseGoal);
-      s->launches += launchContactProject(st, lists, s->q.p, o.collisionThickness, contribC, s->snap.p);
-      s->launches += launchGatherRhs(st, n, s->msn.p, s->incPtr.p, s->inc.p, s->contrib.p, s->rhs.p);
-      s->launches += launchGatherContacts(st, n, lists, contribC, s->snap.p, s->rhs.p);
-      timer.end();
-
-      timer.begin(kPhGlobal);
-      s->launches += launchPcgInit(st, A, lists, pw, s->rhs.p, s->q.p, s->tune.pcgTolerance);
-      // Iterations are enqueued in bursts without host round trips: converged solves turn the remaining
-      // launches into early exits (~2 us each), a host poll costs ~40 us of idle GPU, so the first burst
-      // slightly overshoots the previous solve's count.
-      uint32_t done = 0, burst = s->lastPcgIters + 2;
-      bool converged = false;
-      while (!converged && done < s->tune.pcgMaxIterations) {
-        uint32_t todo = std::min(burst, s->tune.pcgMaxIterations - done);
-        for (uint32_t k = 0; k < todo; ++k) s->launches += launchPcgIteration(st, A, lists, pw, s->tune.pcgTolerance, (int)(done + k));
-        done += todo;
-        s->launches += launchPcgCheck(st, pw, s->tune.pcgTolerance, (int)done - 1);
-        PIES_CHECK(s, cudaMemcpyAsync(s->hostFlag, s->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        PIES_CHECK(s, cudaStreamSynchronize(st));
-        converged = s->hostFlag[0] != 0;
-        burst = std::max(4u, s->tune.pcgCheckEvery);
-      }
-      s->launches += launchPcgFinish(st, pw, n, s->q.p);
-      uint32_t used = (uint32_t)s->hostFlag[1];
-      if (getenv("PIES_DEBUG_PCG")) std::fprintf(stderr, "[pcg] sub %u it %u: %u iterations\n", sub, it, used);
-      s->lastPcgIters = std::max(1u, used);
-      s->stats.pcgIterationsLastTick += used;
-      timer.end();
-      s->stats.projectionsLastTick += y.staticProjections + lists.nTri + lists.nFloor;
-    }
-
-    timer.begin(kPhContact);
-    if (s->contact)
-      s->launches += launchStabilize(st, *s->contact, lists, n, s->q.p, s->prev.p, s->snap.p, o.collisionThickness,
-                                     o.collisionStabilizationIterations);
-    timer.end();
-    timer.begin(kPhOther);
-    s->launches += launchVelocityUpdate(st, n, s->q.p, s->prev.p, s->vel.p, h, o.damping, o.gravity);
-    timer.end();
-    timer.begin(kPhContact);
-    if (s->contact) s->launches += launchFriction(st, *s->contact, lists, n, s->q.p, s->vel.p, o.friction, o.staticFrictionThreshold);
-    timer.end();
-    s->stats.collisionProjections = lists.nTri + lists.nFloor;
-    ++s->stats.substepsLastTick;
+  timer.begin(kPhDetect);
+  if ((rc = runDetection(s, c->lists))) { pdAbort(s); return rc; }
+  // contact-aware preconditioner blocks for this substep's system matrix S + C_t
+  if (!s->blocks) {
+    s->blocks = new BlockWork();
+    PIES_CHECK(s, cudaMallocHost(&s->blocks->host, 4 * sizeof(uint32_t)));
   }
+  {
+    PdViews v = pdViews(s);
+    int LB = 0;
+    if (rebuildBlocks(*s->blocks, st, n, v.A, s->blockNodes.p, s->blockInv.p, s->sys.nBlocks, c->lists, s->q.p, v.pw, &LB) != 0) {
+      cudaError_t e = s->blocks->lastError;
+      pdAbort(s);
+      return failCuda(s, e, "rebuildBlocks", __LINE__);
+    }
+    s->blocks->cur.blockNodes = v.pw.blockNodes; s->blocks->cur.blockInv = v.pw.blockInv; s->blocks->cur.blockMeta = v.pw.blockMeta;
+    s->blocks->cur.nBlocks = v.pw.nBlocks; s->blocks->cur.nBlocksDev = v.pw.nBlocksDev;
+    s->launches += LB;
+    const BlockWork& bw = *s->blocks;
+    ClusterTables ct{bw.heads.p + bw.nTouched, bw.start.p, bw.vals.p, bw.clusterOf.p, bw.slotOf.p, bw.gsClass.p, bw.nTouched};
+    int LC = s->contact ? prepareClusterSweeps(*s->contact, st, c->lists, ct) : 0;
+    if (LC < 0) { pdAbort(s); return failCuda(s, cudaErrorMemoryAllocation, "prepareClusterSweeps", __LINE__); }
+    s->launches += LC;
+  }
+  timer.end();
+  c->inSubstep = true;
+  return PIES_B200_OK;
+}
+
+int pdIteration(PiesB200Solver* s) {
+  PdTickCtx* c = static_cast<PdTickCtx*>(s->pdCtx);
+  if (!c || !c->inSubstep) return fail(s, PIES_B200_EINVAL, "pd_iteration outside a substep");
+  const uint32_t n = s->n;
+  if (!n) return PIES_B200_OK;
+  cudaStream_t st = s->stream;
+  const HostSystem& y = s->sys;
+  PhaseTimer& timer = c->timer;
+  const ContactLists& lists = c->lists;
+  PdViews v = pdViews(s);
+  float4* contribC = s->contact ? s->contact->contribC.p : nullptr;
+  timer.begin(kPhTetKernel);
+  s->launches += launchTetElems(st, v.te, s->q.p, s->contrib.p + y.baseTet);
+  timer.end();
+  timer.begin(kPhLocal);
+  s->launches += launchDistance(st, v.de, s->q.p, s->contrib.p + y.baseDist);
+  s->launches += launchBend(st, v.be, s->q.p, s->contrib.p + y.baseBend);
+  s->launches += launchShape(st, v.sh, s->shapeMat.p, s->shapeQinv.p, s->shapeQuat.p, s->shapeW.p, s->q.p, s->contrib.p + y.baseShape);
+  s->launches += launchGoal(st, v.go, s->goalMat.p, s->goalXform.p, s->goalW.p, s->contrib.p + y.baseGoal);
+  s->launches += launchContactProject(st, lists, s->q.p, s->opt.collisionThickness, contribC, s->snap.p);
+  s->launches += launchGatherRhs(st, n, s->msn.p, s->incPtr.p, s->inc.p, s->contrib.p, s->rhs.p);
+  s->launches += launchGatherContacts(st, n, lists, contribC, s->snap.p, s->rhs.p);
+  timer.end();
+
+  timer.begin(kPhGlobal);
+  s->launches += launchPcgInit(st, v.A, lists, v.pw, s->rhs.p, s->q.p, s->tune.pcgTolerance);
+  // Iterations are enqueued in bursts without host round trips: converged solves turn the remaining
+  // launches into early exits (~2 us each), a host poll costs ~40 us of idle GPU, so the first burst
+  // slightly overshoots the previous solve's count.
+  uint32_t done = 0, burst = s->lastPcgIters + 2;
+  bool converged = false;
+  while (!converged && done < s->tune.pcgMaxIterations) {
+    uint32_t todo = std::min(burst, s->tune.pcgMaxIterations - done);
+    for (uint32_t k = 0; k < todo; ++k) s->launches += launchPcgIteration(st, v.A, lists, v.pw, s->tune.pcgTolerance, (int)(done + k));
+    done += todo;
+    s->launches += launchPcgCheck(st, v.pw, s->tune.pcgTolerance, (int)done - 1);
+    PIES_CHECK(s, cudaMemcpyAsync(s->hostFlag, s->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PIES_CHECK(s, cudaStreamSynchronize(st));
+    converged = s->hostFlag[0] != 0;
+    burst = std::max(4u, s->tune.pcgCheckEvery);
+  }
+  s->launches += launchPcgFinish(st, v.pw, n, s->q.p);
+  uint32_t used = (uint32_t)s->hostFlag[1];
+  if (getenv("PIES_DEBUG_PCG")) std::fprintf(stderr, "[pcg] it: %u iterations\n", used);
+  s->lastPcgIters = std::max(1u, used);
+  s->stats.pcgIterationsLastTick += used;
+  timer.end();
+  s->stats.projectionsLastTick += y.staticProjections + lists.nTri + lists.nFloor;
+  return PIES_B200_OK;
+}
+
+int pdSubstepEnd(PiesB200Solver* s) {
+  PdTickCtx* c = static_cast<PdTickCtx*>(s->pdCtx);
+  if (!c || !c->inSubstep) return fail(s, PIES_B200_EINVAL, "pd_substep_end outside a substep");
+  c->inSubstep = false;
+  const uint32_t n = s->n;
+  if (!n) return PIES_B200_OK;
+  cudaStream_t st = s->stream;
+  const PiesB200Options& o = s->opt;
+  const float h = o.fixedTimestepSize / (float)o.timeSubsteps;
+  PhaseTimer& timer = c->timer;
+  const ContactLists& lists = c->lists;
+  timer.begin(kPhContact);
+  if (s->contact)
+    s->launches += launchStabilize(st, *s->contact, lists, n, s->q.p, s->prev.p, s->snap.p, o.collisionThickness,
+                                   o.collisionStabilizationIterations);
+  timer.end();
+  timer.begin(kPhOther);
+  s->launches += launchVelocityUpdate(st, n, s->q.p, s->prev.p, s->vel.p, h, o.damping, o.gravity);
+  timer.end();
+  timer.begin(kPhContact);
+  if (s->contact) s->launches += launchFriction(st, *s->contact, lists, n, s->q.p, s->vel.p, o.friction, o.staticFrictionThreshold);
+  timer.end();
+  s->stats.collisionProjections = lists.nTri + lists.nFloor;
+  ++s->stats.substepsLastTick;
+  return PIES_B200_OK;
+}
+
+int pdTickEnd(PiesB200Solver* s, bool refreshMirror) {
+  PdTickCtx* c = static_cast<PdTickCtx*>(s->pdCtx);
+  if (!c) return fail(s, PIES_B200_EINVAL, "pd_tick_end without pd_tick_begin");
+  if (!s->n) { pdAbort(s); return PIES_B200_OK; }
+  cudaStream_t st = s->stream;
   s->deviceNewer = true;
-  cudaEventRecord(tick1, st);
-  PIES_CHECK(s, cudaEventSynchronize(tick1));
-  cudaEventElapsedTime(&s->stats.msTick, tick0, tick1);
-  cudaEventDestroy(tick0); cudaEventDestroy(tick1);
+  cudaEventRecord(c->tick1, st);
+  cudaError_t es = cudaEventSynchronize(c->tick1);
+  if (es != cudaSuccess) { pdAbort(s); return failCuda(s, es, "cudaEventSynchronize", __LINE__); }
+  cudaEventElapsedTime(&s->stats.msTick, c->tick0, c->tick1);
   {
     float acc[kPhCount] = {0, 0, 0, 0, 0, 0};
     uint32_t cnt[kPhCount] = {0, 0, 0, 0, 0, 0};
-    timer.resolve(acc, cnt);
+    c->timer.resolve(acc, cnt);
     s->stats.msOther = acc[kPhOther]; s->stats.msDetect = acc[kPhDetect]; s->stats.msLocal = acc[kPhLocal] + acc[kPhTetKernel];
     s->stats.msGlobal = acc[kPhGlobal]; s->stats.msContact = acc[kPhContact];
     s->stats.msTetKernel = acc[kPhTetKernel]; s->stats.tetKernelLaunches = cnt[kPhTetKernel];
   }
+  uint64_t launches0 = c->launches0;
+  pdAbort(s);
   PIES_CHECK(s, cudaGetLastError());
   {
     float rel = 0.0f;
@@ -411,10 +485,52 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
     s->stats.pcgLastRelResidual = rel;
   }
   s->mirrorStale = true;
+  int rc;
   if (refreshMirror && (rc = refreshVertexMirror(s))) return rc;
   s->stats.kernelLaunchesLastTick = s->launches - launches0;
   s->stats.simFailed = s->simFailed ? 1u : 0u;
   return PIES_B200_OK;
+}
+
+// contacts of the last detection whose point node (point-triangle) / node (floor) this solver owns
+__global__ void __launch_bounds__(kThreads) k_count_owned(uint32_t nTri, const uint4* __restrict__ tri, uint32_t nFloor,
+                                                          const uint32_t* __restrict__ floorNode,
+                                                          const uint8_t* __restrict__ owned, uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t a = 0, b = 0;
+  if (i < nTri) a = owned[tri[i].x] ? 1u : 0u;
+  if (i < nFloor) b = owned[floorNode[i]] ? 1u : 0u;
+  a = __reduce_add_sync(0xffffffffu, a); b = __reduce_add_sync(0xffffffffu, b);
+  if ((threadIdx.x & 31) == 0) { if (a) atomicAdd(out, a); if (b) atomicAdd(out + 1, b); }
+}
+
+int countOwnedContacts(PiesB200Solver* s, uint32_t* nTri, uint32_t* nFloor) {
+  *nTri = s->stats.triCollisions; *nFloor = s->stats.staticCollisions;
+  if (!s->haveOwnedMask || !s->detect || (!*nTri && !*nFloor)) return PIES_B200_OK;
+  uint32_t m = std::max(*nTri, *nFloor);
+  PIES_CHECK(s, s->flag.reserve(4));
+  uint32_t* out = reinterpret_cast<uint32_t*>(s->flag.p) + 2;
+  PIES_CHECK(s, cudaMemsetAsync(out, 0, 2 * sizeof(uint32_t), s->stream));
+  k_count_owned<<<gridFor(m, kThreads), kThreads, 0, s->stream>>>(*nTri, s->detect->triList.p, *nFloor, s->detect->floorList.p,
+                                                                 s->ownedMask.p, out);
+  ++s->launches;
+  uint32_t host[2] = {0, 0};
+  PIES_CHECK(s, cudaMemcpyAsync(host, out, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  PIES_CHECK(s, cudaStreamSynchronize(s->stream));
+  *nTri = host[0]; *nFloor = host[1];
+  return PIES_B200_OK;
+}
+
+int tickPD(PiesB200Solver* s, bool refreshMirror) {
+  int rc = pdTickBegin(s);
+  if (rc) return rc;
+  for (uint32_t sub = 0; sub < s->opt.timeSubsteps; ++sub) {
+    if ((rc = pdSubstepBegin(s))) { pdAbort(s); return rc; }
+    for (uint32_t it = 0; it < s->opt.iterations; ++it)
+      if ((rc = pdIteration(s))) { pdAbort(s); return rc; }
+    if ((rc = pdSubstepEnd(s))) { pdAbort(s); return rc; }
+  }
+  return pdTickEnd(s, refreshMirror);
 }
 
 }  // namespace pies
@@ -423,6 +539,7 @@ PiesB200Solver::~PiesB200Solver() {
   if (detect) { if (detect->host) cudaFreeHost(detect->host); delete detect; }
   delete contact;
   pies::destroyPbdWork(pbd);
+  pies::pdAbort(this);
   if (blocks) { if (blocks->host) cudaFreeHost(blocks->host); delete blocks; }
   if (hostPacked) cudaFreeHost(hostPacked);
   if (hostFlag) cudaFreeHost(hostFlag);

@@ -88,6 +88,9 @@ struct PiesB200Solver {
   pies::ContactWork* contact = nullptr;
   pies::BlockWork* blocks = nullptr;
   pies::PbdWork* pbd = nullptr;
+  void* pdCtx = nullptr;          // PdTickCtx of a tick in progress (engine.cu)
+  pies::DevBuf<uint32_t> triOrder; bool haveTriOrder = false;  // canonical-order override (slab-partitioned hosts)
+  pies::DevBuf<uint8_t> ownedMask; bool haveOwnedMask = false; // nodes this rank owns (others are ghosts)
 
   float* hostPacked = nullptr;  // pinned, 3 floats per node
   size_t hostPackedCap = 0;
@@ -104,6 +107,13 @@ int fail(PiesB200Solver* s, int code, const char* msg);
 int ensureBuilt(PiesB200Solver* s);
 int downloadState(PiesB200Solver* s);  // device -> scene.pos/prev/vel
 int tickPD(PiesB200Solver* s, bool refreshMirror);
+int pdTickBegin(PiesB200Solver* s);
+int pdSubstepBegin(PiesB200Solver* s);
+int pdIteration(PiesB200Solver* s);
+int pdSubstepEnd(PiesB200Solver* s);
+int pdTickEnd(PiesB200Solver* s, bool refreshMirror);
+void pdAbort(PiesB200Solver* s);
+int countOwnedContacts(PiesB200Solver* s, uint32_t* nTri, uint32_t* nFloor);
 int tickPBD(PiesB200Solver* s, bool refreshMirror);
 int refreshVertexMirror(PiesB200Solver* s);
 int uploadStateArrays(PiesB200Solver* s, const float* pos, const float* prev, const float* vel);

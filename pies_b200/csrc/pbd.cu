@@ -26,6 +26,7 @@
 // association order (the reference is built for baseline x86-64, no FMA).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -460,20 +461,20 @@ __global__ void __launch_bounds__(kSweepThreads) k_pbd_collide(uint32_t nVis, co
               pi.x = ex::add(pi.x, da.x); pi.y = ex::add(pi.y, da.y); pi.z = ex::add(pi.z, da.z);
               // the visit list was pruned assuming no node strays further than delta from its position at hash
               // build, at ANY time during the sweep: check every write (the host redoes the pass if violated)
-              float4 bi = q0[i];
-              float moved = fmaxf(fmaxf(fabsf(pi.x - bi.x), fabsf(pi.y - bi.y)), fabsf(pi.z - bi.z));
-              if (!self) {
-                float4 bj = q0[j];
-                moved = fmaxf(moved, fmaxf(fmaxf(fabsf(pj.x + db.x - bj.x), fabsf(pj.y + db.y - bj.y)), fabsf(pj.z + db.z - bj.z)));
-              }
-              if (!(moved <= delta)) flags[0] = 1u;
-              if (self) {  // both updates land on the same node, one after the other
+              if (self) {  // both updates land on the same node, one after the other (net zero up to rounding)
                 pi.x = ex::add(pi.x, db.x); pi.y = ex::add(pi.y, db.y); pi.z = ex::add(pi.z, db.z);
                 __stcg(q + i, pi);
               } else {
                 pj.x = ex::add(pj.x, db.x); pj.y = ex::add(pj.y, db.y); pj.z = ex::add(pj.z, db.z);
                 __stcg(q + i, pi); __stcg(q + j, pj);
               }
+              float4 bi = q0[i];
+              float moved = fmaxf(fmaxf(fabsf(pi.x - bi.x), fabsf(pi.y - bi.y)), fabsf(pi.z - bi.z));
+              if (!self) {
+                float4 bj = q0[j];
+                moved = fmaxf(moved, fmaxf(fmaxf(fabsf(pj.x - bj.x), fabsf(pj.y - bj.y)), fabsf(pj.z - bj.z)));
+              }
+              if (!(moved <= delta)) flags[0] = 1u;
             }
           }
           __threadfence();
@@ -647,6 +648,9 @@ static int collideNodes(PiesB200Solver* s, PbdWork& w) {
     PCHECK(cudaMemcpyAsync(w.host + 11, w.flags.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PCHECK(cudaStreamSynchronize(st));
     w.visitsLastTick += nVis;
+    if (getenv("PIES_DEBUG_PBD"))
+      std::fprintf(stderr, "[pbd] pairs %llu cells %u visits %u delta %g attempt %d -> %s\n", (unsigned long long)nPairs, nCells,
+                   nVis, delta, attempt, w.host[11] ? "redo" : "ok");
     if (!w.host[11]) return PIES_B200_OK;
     // a node moved further than the pruning assumed: restore and redo with twice the bound
     PCHECK(cudaMemcpyAsync(s->q.p, w.q0.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, st));

@@ -22,6 +22,9 @@ struct BlockWork {
   // contact clusters of this substep: nodes sorted by cluster in vals[start[c] .. start[c+1]), count at heads[nTouched]
   uint64_t scanCap = 0;
   cudaError_t lastError = cudaSuccess;
+  // what rebuildBlocks() last pointed the CG at (kept so the per-iteration phases of a tick can rebuild their views)
+  struct Current { int* blockNodes = nullptr; float* blockInv = nullptr; const uint2* blockMeta = nullptr;
+                   uint32_t nBlocks = 0; const uint32_t* nBlocksDev = nullptr; } cur;
 };
 
 // Regroups the nodes joined by this substep's contacts into dense blocks and re-inverts every block the

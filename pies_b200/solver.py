@@ -112,6 +112,15 @@ _SIGNATURES = {
     "pies_b200_tri_occupancy_counts": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pies_b200_get_tri_occupancy": (C.c_int, [_vp, _i64p, _u32p, _u32p]),
     "pies_b200_detect_nodes": (C.c_int, [_vp]),
+    "pies_b200_pd_tick_begin": (C.c_int, [_vp]),
+    "pies_b200_pd_substep_begin": (C.c_int, [_vp]),
+    "pies_b200_pd_iteration": (C.c_int, [_vp]),
+    "pies_b200_pd_substep_end": (C.c_int, [_vp]),
+    "pies_b200_pd_tick_end": (C.c_int, [_vp]),
+    "pies_b200_device_state": (C.c_int, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
+    "pies_b200_set_triangle_order": (C.c_int, [_vp, C.c_uint32, _u32p]),
+    "pies_b200_set_owned_nodes": (C.c_int, [_vp, C.c_uint32, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")]),
+    "pies_b200_count_owned_contacts": (C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "pies_b200_node_occupancy_counts": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pies_b200_get_node_occupancy": (C.c_int, [_vp, _i64p, _u32p, _u32p]),
     "pies_b200_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
@@ -374,6 +383,44 @@ class Solver:
         if nc.value:
             self._ck(lib().pies_b200_get_tri_occupancy(self.h, cells, counts, members))
         return cells, counts, members
+
+    # ---- tick phases / halo support (slab-partitioned hosts, pies_b200/multigpu.py) ----
+    def pdTickBegin(self):
+        self._ck(lib().pies_b200_pd_tick_begin(self.h))
+
+    def pdSubstepBegin(self):
+        self._ck(lib().pies_b200_pd_substep_begin(self.h))
+
+    def pdIteration(self):
+        self._ck(lib().pies_b200_pd_iteration(self.h))
+
+    def pdSubstepEnd(self):
+        self._ck(lib().pies_b200_pd_substep_end(self.h))
+
+    def pdTickEnd(self):
+        self._ck(lib().pies_b200_pd_tick_end(self.h))
+
+    def deviceState(self):
+        """(q_ptr, prev_ptr, vel_ptr, n): raw device addresses of the float4 node-state planes."""
+        q, p, v, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32()
+        self._ck(lib().pies_b200_device_state(self.h, C.byref(q), C.byref(p), C.byref(v), C.byref(n)))
+        return q.value, p.value, v.value, n.value
+
+    def setTriangleOrder(self, order):
+        if order is None:
+            self._ck(lib().pies_b200_set_triangle_order(self.h, 0, np.zeros(1, np.uint32)))
+        else:
+            order = np.ascontiguousarray(order, np.uint32)
+            self._ck(lib().pies_b200_set_triangle_order(self.h, len(order), order))
+
+    def setOwnedNodes(self, mask):
+        mask = np.ascontiguousarray(mask, np.uint8)
+        self._ck(lib().pies_b200_set_owned_nodes(self.h, len(mask), mask))
+
+    def countOwnedContacts(self):
+        a, b = C.c_uint32(), C.c_uint32()
+        self._ck(lib().pies_b200_count_owned_contacts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def detectNodes(self):
         self._ck(lib().pies_b200_detect_nodes(self.h))

@@ -33,12 +33,15 @@ int main(int argc, char** argv) {
       solver.createBox(glm::vec3(6.0f * (i % 2), 3.0f + 6.0f * (i / 4), 6.0f * ((i / 2) % 2)), 1.0f, 0.5f);
   } else if (!std::strcmp(scene, "shapes")) {
     solver.createShapeMatchingBox(glm::vec3(0.0f, 3.0f, 0.0f), 3, 3, 3, 1.0f, glm::vec3(0.0f), 1000.0f);
-    solver.createShapeMatchingSheet(glm::vec3(10.0f, 3.0f, 0.0f), 1.0f, glm::vec3(0.0f), 1000.0f);
+    solver.createShapeMatchingBox(glm::vec3(4.0f, 2.0f, 1.0f), 4, 3, 5, 1.0f, glm::vec3(0.0f), 800.0f);
   } else {
     std::fprintf(stderr, "unknown scene %s\n", scene);
     return 2;
   }
   for (int t = 0; t < ticks; ++t) solver.tick(0.012f);
+#ifdef PIES_B200_H  // only the B200 build has an error channel (additive API)
+  if (solver.failed() || !solver.lastError().empty()) std::fprintf(stderr, "pies_b200: %s\n", solver.lastError().c_str());
+#endif
   const std::vector<Pies::Solver::Vertex>& v = solver.getVertices();
   std::FILE* f = std::fopen(argv[3], "wb");
   if (!f) return 3;

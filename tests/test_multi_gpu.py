@@ -1,0 +1,138 @@
+"""Slab-partitioned solver vs the single-GPU solver on the same scene (there is no reference for
+partitioning, so the test is N-rank result == 1-rank result).
+
+ * `lockstep` tests emulate 2 and 3 ranks inside one process on ONE GPU (same plan, same send/recv lists, ghost
+   rows copied tensor-to-tensor instead of through NCCL), so the halo logic is exercised on single-GPU boxes;
+ * `nccl` tests spawn one process per GPU and need >= 2 GPUs (skipped otherwise).
+
+Tolerance: 1e-4 x scene bbox diagonal, the north_star's position tolerance.  The partitioned solve is not
+bit-identical by construction: each rank's CG stops on its own residual norm, and a ghost body misses the contacts
+with its far-side neighbours within one iteration (corrected by the per-iteration halo overwrite)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, bbox_diag
+
+sys.path.insert(0, ROOT)
+from pies_b200 import multigpu  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+OPTS = dict(iterations=10, timeSubsteps=1, solver="PD")
+
+
+def row_specs(columns=4, layers=2, pitch=2.05, seed=3):
+    """Columns of boxes `pitch` apart along x (boxes are 2 wide: pitch 2.05 leaves a 0.05 gap, inside the 0.1 collision
+    threshold, so neighbouring columns are in contact from the first tick), `layers` boxes per column falling onto
+    each other and the floor."""
+    rng = np.random.default_rng(seed)
+    specs = []
+    for layer in range(layers):
+        for c in range(columns):
+            t = np.array([pitch * c, 0.3 + 2.4 * layer, 0.0]) + rng.uniform(0, 0.01, 3)
+            specs.append(multigpu.tetbox(t, v0=(0.0, -1.0 * layer, 0.0)))
+    return specs
+
+
+def _single(pb, specs, ticks):
+    s = pb.Solver(**OPTS)
+    for sp in specs:
+        multigpu.apply_spec(s, sp)
+    out = {}
+    for t in range(1, max(ticks) + 1):
+        s.tick()
+        if t in ticks:
+            out[t] = (s.positions.copy(), s.velocities.copy(), s.stats().triCollisions)
+    return out
+
+
+@pytest.mark.parametrize("world,halo,pitch", [(2, 1.0, 2.05), (3, 1.0, 2.05), (2, 0.5, 3.0)])
+def test_lockstep_ranks_match_single_solver(pb, world, halo, pitch):
+    ticks = (1, 5, 20, 40)
+    specs = row_specs(columns=6, pitch=pitch)
+    ref = _single(pb, specs, ticks)
+    ranks = [multigpu.SlabSolver(specs, rank=r, world=world, halo=halo, device=0, snap=0.5, **OPTS) for r in range(world)]
+    ghosts = sum(int((~r.owned).sum()) for r in ranks)
+    assert (ghosts > 0) == (pitch < 2.5)
+    diag = bbox_diag(ref[1][0])
+    for t in range(1, max(ticks) + 1):
+        multigpu.tick_lockstep(ranks)
+        if t in ticks:
+            pos, prev, vel = multigpu.gather_lockstep(ranks)
+            err = float(np.abs(pos - ref[t][0]).max())
+            assert err <= 1e-4 * diag, (world, t, err, 1e-4 * diag, ref[t][2])
+    if pitch < 2.5:
+        assert ref[max(ticks)][2] > 0        # the comparison did cover cross-cut contacts
+        owned_contacts = sum(sum(r.solver.countOwnedContacts()) for r in ranks)
+        st = _single(pb, specs, (max(ticks),))
+        assert owned_contacts > 0
+
+
+def test_world1_slab_solver_is_the_plain_solver(pb):
+    specs = row_specs(columns=3)
+    ref = _single(pb, specs, (10,))
+    s = multigpu.SlabSolver(specs, rank=0, world=1, device=0, **OPTS)
+    for _ in range(10):
+        s.tick()
+    assert (s.solver.positions == ref[10][0]).all()
+    assert s.projections_last_tick() == 10 * (96 * len(specs) + s.solver.stats().triCollisions + s.solver.stats().staticCollisions)
+
+
+def test_repartition_keeps_the_trajectory(pb):
+    """Forcing a repartition (rebuild from the gathered state) mid-run does not disturb the trajectory."""
+    specs = row_specs(columns=4)
+    ref = _single(pb, specs, (12,))
+    s = multigpu.SlabSolver(specs, rank=0, world=1, device=0, **OPTS)
+    for _ in range(6):
+        s.tick()
+    lo, hi = s.body_extents_x()
+    s._build(lo, hi, s.gather_state())
+    for _ in range(6):
+        s.tick()
+    diag = bbox_diag(ref[12][0])
+    assert float(np.abs(s.solver.positions - ref[12][0]).max()) <= 1e-4 * diag
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _nccl_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from pies_b200 import multigpu as mg
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    specs = row_specs(columns=6)
+    s = mg.SlabSolver(specs, rank=rank, world=world, halo=1.0, device=rank, dist=dist, snap=0.5, **OPTS)
+    for _ in range(20):
+        s.tick()
+    ok = s.check_halo(repartition=False)
+    pos, prev, vel = s.gather_state()
+    if rank == 0:
+        out["pos"] = pos; out["halo_bytes"] = s.halo_bytes; out["halo_ok"] = ok
+    dist.destroy_process_group()
+
+
+def test_nccl_two_ranks_match_single_solver(pb):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    specs = row_specs(columns=6)
+    ref = _single(pb, specs, (20,))
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_nccl_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    diag = bbox_diag(ref[20][0])
+    assert float(np.abs(out["pos"] - ref[20][0]).max()) <= 1e-4 * diag
+    assert out["halo_bytes"] > 0

@@ -1,0 +1,140 @@
+"""CPU (gloo, world_size 2 and 3) tests of the slab-partitioned driver's host logic (pies_b200/multigpu.py):
+the plan is identical on every rank, every body has exactly one owner, ghost sets are symmetric with the
+exchange lists, the canonical triangle order restricted to a rank is order-preserving, and the halo exchange
+overwrites exactly the ghost rows with the owners' values."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+sys.path.insert(0, ROOT)
+from pies_b200 import multigpu, scenes  # noqa: E402
+
+
+def _specs(n=96, nx=8, nz=4, pitch=3.0):
+    return [multigpu.tetbox(t) for t in scenes.s3_translations(n, nx=nx, nz=nz, pitch=pitch)]
+
+
+def _plan(world, halo, **kw):
+    sp = _specs(**kw)
+    return multigpu.SlabPlan([s["kind"] for s in sp], [s["lo"][0] for s in sp], [s["hi"][0] for s in sp], world, halo, snap=1.0)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_plan_covers_every_body_once_and_ghosts_are_foreign(world):
+    p = _plan(world, halo=1.5)
+    owned = np.concatenate([p.local[r][p.owner[p.local[r]] == r] for r in range(world)])
+    assert sorted(owned.tolist()) == list(range(p.n_bodies))
+    for r in range(world):
+        loc = p.local[r]
+        assert (np.diff(loc) > 0).all()                       # global order preserved
+        mask = p.owned_node_mask(r)
+        assert mask.sum() == p.nodes[loc][p.owner[loc] == r].sum()
+        l2g = p.local_to_global_nodes(r)
+        assert len(l2g) == len(mask) and (np.diff(l2g) > 0).all()
+
+
+def test_halo_width_selects_neighbour_columns():
+    # columns 3 apart, boxes 2 wide: the gap between columns is ~1
+    assert all(len(_plan(2, halo=0.5).local[r]) == (_plan(2, halo=0.5).owner == r).sum() for r in range(2))
+    p = _plan(2, halo=1.5)
+    for r in range(2):
+        ghosts = p.local[r][p.owner[p.local[r]] != r]
+        assert len(ghosts) == 4 * (96 // 32)                  # one column of the other slab: nz x layers bodies
+
+
+def test_exchange_lists_are_symmetric():
+    p = _plan(3, halo=1.5)
+    lists = [p.exchange_lists(r) for r in range(3)]
+    for r in range(3):
+        send, recv = lists[r]
+        for peer, ix in send.items():
+            assert len(ix) == len(lists[peer][1][r])          # what r sends to peer is what peer expects from r
+            # and refers to the same global nodes in the same order
+            assert (p.local_to_global_nodes(r)[ix] == p.local_to_global_nodes(peer)[lists[peer][1][r]]).all()
+        mask = p.owned_node_mask(r).astype(bool)
+        for peer, ix in send.items():
+            assert mask[ix].all()
+        for peer, ix in recv.items():
+            assert not mask[ix].any()
+
+
+def test_triangle_order_is_the_global_canonical_order_restricted():
+    p = _plan(2, halo=1.5)
+    n, T = int(p.tri_off[-1]), 8
+    t = np.arange(n)
+    grank = (t % T) * (n // T) + np.minimum(t % T, n % T) + t // T
+    for r in range(2):
+        loc = p.local[r]
+        gt = np.concatenate([p.tri_off[b] + np.arange(p.tris[b]) for b in loc])
+        order = p.triangle_order(r)
+        assert sorted(order.tolist()) == list(range(len(gt)))
+        # sorting local triangles by `order` sorts them by global canonical rank
+        by_order = gt[np.argsort(order)]
+        assert (np.diff(grank[by_order]) > 0).all()
+    # a single rank holding everything reproduces the plain striping
+    p1 = _plan(1, halo=1.5)
+    assert (p1.triangle_order(0) == grank).all()
+
+
+def test_missing_ghosts_alarm():
+    sp = _specs()
+    lo = np.array([s["lo"][0] for s in sp]); hi = np.array([s["hi"][0] for s in sp])
+    p = multigpu.SlabPlan([s["kind"] for s in sp], lo, hi, 2, halo=0.5, snap=1.0)
+    assert p.missing_ghosts(lo, hi) == []
+    # a body of slab 1 drifts against slab 0's extent
+    b = int(np.flatnonzero(p.owner == 1)[0])
+    lo2, hi2 = lo.copy(), hi.copy()
+    lo2[b] = p.ext[0][1] - 0.05; hi2[b] = lo2[b] + 2.0
+    miss = p.missing_ghosts(lo2, hi2)
+    assert any(r == 0 and b in ids for r, ids in miss)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = _plan(world, halo=1.5)
+    l2g = p.local_to_global_nodes(rank)
+    owned = p.owned_node_mask(rank).astype(bool)
+    # state plane: owned rows carry their global id, ghost rows carry garbage
+    planes = []
+    for k in range(3):
+        t = torch.full((len(l2g), 4), -1.0)
+        t[owned] = torch.as_tensor(l2g[owned] * 10.0 + k, dtype=torch.float32)[:, None].repeat(1, 4)
+        planes.append(t)
+    x = multigpu.HaloExchange(p, rank, "cpu", dist)
+    moved = x(planes)
+    ok = all(bool((pl[:, 0] == torch.as_tensor(l2g * 10.0 + k, dtype=torch.float32)).all()) for k, pl in enumerate(planes))
+    # second round with one plane, as after a PD iteration
+    planes[0][~torch.as_tensor(owned)] = -7.0
+    x([planes[0]])
+    ok2 = bool((planes[0][:, 0] == torch.as_tensor(l2g * 10.0, dtype=torch.float32)).all())
+    out[rank] = dict(ok=ok, ok2=ok2, moved=moved, ghosts=int((~owned).sum()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_gloo(world):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        assert out[r]["ok"] and out[r]["ok2"], out[r]
+        assert out[r]["ghosts"] > 0 and out[r]["moved"] > 0
