@@ -10,11 +10,14 @@ One "step" = one Solver::tick (one substep of 10 PD iterations + collision detec
            CUDA-event timed, max over ranks.
 `e2e`    : the same ticks through the host-facing API with HOST buffers: every step uploads the node
            state (pos/prev/vel) from pinned host memory, ticks, and reads the state back.
-`roofline`: the fused tet strain+volume projection kernel, algorithmic bytes / measured time.
 `cpu_baseline` / --impl reference: the unmodified reference (oracle/_ref) on the host cores, on a
            bounded sample of the same scene (6x6 columns x 21 layers = 756 bodies).
-Multi-GPU (round 1): ranks run independent replicas of S3 (weak scaling, no data-path collective);
-slab partitioning with NCCL halo exchange is not built yet.
+`roofline`: the kernel with the largest share of the step (the CSR-stream SpMV of the global solve), algorithmic
+           bytes / CUDA-event duration of sampled launches; the other hot kernels and the
+           local step + RHS pair of the north_star target are reported next to it.
+Multi-GPU: weak scaling over x slabs (pies_b200/multigpu.py): `world` S3 stacks side by side, each rank owns one
+           S3-sized slab plus a two-body ghost layer; ghost rows travel over NCCL point-to-point every substep and
+           every PD iteration.  No other collective on the data path.
 """
 import argparse
 import json
@@ -116,6 +119,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bodies", type=int, default=FULL_BODIES, help="debug: smaller S3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", type=float, default=4.0, help="ghost layer width along x (4.0 = two S3 columns)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -161,41 +165,72 @@ def main():
         except Exception as e:  # the oracle is optional here; say so instead of inventing a number
             cpu = {"error": str(e)}
 
-    s = pb.Solver(device=local_rank, **scenes.S3_OPTIONS)
-    scenes.build_s3(s, args.bodies)
+    # One dedicated CUDA stream per rank: the solver launches on it, NCCL orders its transfers against it, and
+    # the timed region is bracketed by events recorded on it.
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    drv = None
+    if world == 1:
+        s = pb.Solver(device=local_rank, **scenes.S3_OPTIONS)
+        scenes.build_s3(s, args.bodies)
+        s.setStream(stream.cuda_stream)
+        tick = s.tick
+        owned_static = 96 * args.bodies
+    else:
+        # Weak scaling: the scene is `world` S3 stacks side by side along x (32*world x 32 columns, same column
+        # height), cut into x slabs of equal constraint count; each rank simulates its slab plus a two-body-deep
+        # ghost layer and exchanges ghost rows with its neighbours every substep and every PD iteration.
+        from pies_b200 import multigpu
+        trans = scenes.s3_translations(args.bodies * world, nx=32 * world)
+        specs = [multigpu.tetbox(t) for t in trans]
+        drv = multigpu.SlabSolver(specs, rank=rank, world=world, halo=args.halo, device=local_rank, dist=dist, snap=0.5,
+                                  **scenes.S3_OPTIONS)
+        s = drv.solver
+        tick = drv.tick
+        owned_static = drv.owned_static
+        config["parallelism"] = "x-slabs x%d, %d-body S3 per rank, halo %.1f (two bodies deep), NCCL halo exchange per substep and per PD iteration" % (
+            world, args.bodies, args.halo)
+        config["nodes"] *= world; config["tets"] *= world; config["static_projections_per_iteration"] *= world
     n = len(s.getVertices())
     s.setTuning(profilePhases=True)
+
+    def projections():
+        if drv is not None:
+            return drv.projections_last_tick()
+        return s.stats().projectionsLastTick
+
     for _ in range(warmup):
-        s.tick()
+        tick()
     # snapshot so the device-resident and the end-to-end measurements replay the same ticks
     snap = [torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy() for _ in range(3)]
     snap[0][:] = s.positions; snap[1][:] = s.prevPositions; snap[2][:] = s.velocities
 
     # ---- device-resident run: K ticks, state stays in HBM ----
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern = {k: [0.0, 0] for k in ("tet", "gather", "spmv", "update")}
+    phases = {"local": 0.0, "global": 0.0, "detect": 0.0, "contact": 0.0, "other": 0.0}
+    proj = launches = pcg_iters = 0
     barrier()
     sampler = ClockSampler(local_rank)
-    dev_ms = 0.0
-    proj = launches = 0
-    tet_ms = 0.0
-    tet_launches = 0
-    tet_bytes = 0.0
-    phases = {"local": 0.0, "global": 0.0, "detect": 0.0, "contact": 0.0, "other": 0.0}
     t0 = time.time()
+    ev0.record(stream)
     for _ in range(args.steps):
-        s.tick()  # no getVertices() here: the state never leaves HBM
+        tick()  # no getVertices() here: the state never leaves HBM
         st = s.stats()
-        dev_ms += st.msTick
-        proj += st.projectionsLastTick
+        proj += projections()
         launches += st.kernelLaunchesLastTick
-        tet_ms += st.msTetKernel
-        tet_launches += st.tetKernelLaunches
+        pcg_iters += st.pcgIterationsLastTick
+        kern["tet"][0] += st.msTetKernel; kern["tet"][1] += st.tetKernelLaunches
+        kern["gather"][0] += st.msGatherKernel; kern["gather"][1] += st.gatherKernelLaunches
+        kern["spmv"][0] += st.msSpmvKernel; kern["spmv"][1] += st.spmvKernelLaunches
+        kern["update"][0] += st.msUpdateKernel; kern["update"][1] += st.updateKernelLaunches
         phases["local"] += st.msLocal; phases["global"] += st.msGlobal; phases["detect"] += st.msDetect
         phases["contact"] += st.msContact; phases["other"] += st.msOther
+    ev1.record(stream)
     barrier()
     wall_ms = 1e3 * (time.time() - t0)
     clocks = sampler.stop()
-    # msTick = CUDA events on the solver stream around each tick's kernels (the device time);
-    # wall_ms = the host's view of the same loop.
+    dev_ms = ev0.elapsed_time(ev1)   # CUDA events on the launching stream around the K ticks
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(proj), float(launches)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -203,6 +238,8 @@ def main():
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     dev_ms_max, wall_ms_max = t.tolist()
     proj_all, launches_all = tot.tolist()
+    halo_bytes = drv.halo_bytes if drv is not None else 0
+    halo_ok = drv.check_halo(repartition=False) if drv is not None else True   # every contact partner still inside the ghost layer
 
     # ---- end-to-end run: same ticks, host buffers in and out every step ----
     s.setState(snap[0], snap[1], snap[2])
@@ -212,51 +249,79 @@ def main():
     t0 = time.time()
     for _ in range(args.steps):
         s.setState(hp, hv, hq)          # H2D: 3 x 12 B per node from pinned memory
-        s.tick()
+        tick()
         s.getVertices()                 # the reference-facing readback: D2H 12 B per node into the Vertex mirror
         hp[:] = s.positions; hv[:] = s.prevPositions; hq[:] = s.velocities  # D2H of the full state
-        e2e_proj += s.stats().projectionsLastTick
+        e2e_proj += projections()
     barrier()
     e2e_s = time.time() - t0
     e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    ep = torch.tensor([float(e2e_proj)], dtype=torch.float64, device="cuda")
+    ep = torch.tensor([float(e2e_proj), float(n)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
         dist.all_reduce(ep, op=dist.ReduceOp.SUM)
+    e2e_proj_all, n_all = ep.tolist()
 
     if rank == 0:
         peak, peak_kind = load_peaks()
         st = s.stats()
-        per_launch_bytes = scenes.s3_algorithmic_bytes(0, 2 * 48 * args.bodies, 0, 0)  # tet-type projections only: 176 B each
-        avg_tet_ms = tet_ms / max(1, tet_launches)
-        achieved = per_launch_bytes / (avg_tet_ms * 1e-3) / 1e9 if avg_tet_ms > 0 else 0.0
+        nnz = s.systemNonZeros() if hasattr(s, "systemNonZeros") else 223 * (n // 27)
         total_phase = sum(phases.values()) or 1.0
+        # Algorithmic bytes per launch (the split of the 176 B per tet-type projection between the
+        # kernel that writes the contributions and the gather that re-reads them is stated in DESIGN.md section 4).
+        local_proj = 2 * (n // 27) * 48
+        alg = {"tet": 112 * local_proj, "gather": 64 * local_proj + 40 * n, "spmv": 8 * nnz + 64 * n, "update": 72 * n}
+        names = {"tet": "k_tet_elems (fused tet strain+volume projection: ids, Qinv, parameters in; 4 contributions out)",
+                 "gather": "k_gather_rhs (CSR gather of the contributions into the right-hand side)",
+                 "spmv": "k_pcg_spmv (CSR-stream A z with p / Ap recurrences)",
+                 "update": "k_pcg_update (x, r update + packed block-Jacobi apply; the preconditioner stream is not in the SURVEY model)"}
+        traffic = {}
+        traffic_file = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                with open(traffic_file) as f:
+                    traffic = json.load(f)
+            except Exception:
+                traffic = {}
+
+        def roof(k):
+            ms, cnt = kern[k]
+            avg = ms / max(1, cnt)
+            ach = alg[k] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
+            launches_per_step = (pcg_iters / args.steps) if k in ("spmv", "update") else 10.0
+            return {"bound": "hbm", "kernel": names[k], "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                    "frac": ach / peak, "algorithmic_bytes_per_launch": alg[k], "avg_launch_ms": avg, "launches_timed": cnt,
+                    "share_of_step": avg * launches_per_step / (dev_ms / args.steps),
+                    "traffic": traffic.get(k, {}).get("dram_bytes_per_launch")}
+        roofs = {k: roof(k) for k in kern}
+        dominant = max(roofs, key=lambda k: roofs[k]["share_of_step"])
+        # the local step + RHS assembly as the north_star words its target: 176 B per projection + 40 B per node
+        lr_ms = roofs["tet"]["avg_launch_ms"] + roofs["gather"]["avg_launch_ms"]
+        lr_bytes = alg["tet"] + alg["gather"]
         line = {
             "metric": "constraint projections/s", "value": proj_all / (dev_ms_max * 1e-3), "unit": "projections/s",
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
-            "substeps_per_s": world * args.steps / (dev_ms_max * 1e-3),
+            "substeps_per_s": args.steps / (dev_ms_max * 1e-3),
             "wall_ms_per_step": wall_ms_max / args.steps,
-            "e2e": {"value": ep.item() / e.item(), "unit": "projections/s", "h2d_bytes_per_step": 36 * n,
-                    "d2h_bytes_per_step": 48 * n, "ms_per_step": 1e3 * e.item() / args.steps},
+            "e2e": {"value": e2e_proj_all / e.item(), "unit": "projections/s", "h2d_bytes_per_step": int(36 * n_all),
+                    "d2h_bytes_per_step": int(48 * n_all), "ms_per_step": 1e3 * e.item() / args.steps},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_tet_elems (fused tet strain+volume projection)", "achieved": achieved,
-                         "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                         "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_tet_ms,
-                         "launches_timed": tet_launches, "share_of_step": tet_ms / total_phase, "traffic": None},
+            "roofline": roofs[dominant],
+            "roofline_other_kernels": {k: v for k, v in roofs.items() if k != dominant},
+            "roofline_local_step_plus_rhs": {"achieved": lr_bytes / (lr_ms * 1e-3) / 1e9 if lr_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                                             "frac": (lr_bytes / (lr_ms * 1e-3) / 1e9 / peak) if lr_ms > 0 else 0.0,
+                                             "algorithmic_bytes_per_iteration": lr_bytes, "ms_per_iteration": lr_ms,
+                                             "projections_per_s": local_proj / (lr_ms * 1e-3) if lr_ms > 0 else 0.0},
             "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
-            "pcg_iterations_last_tick": int(st.pcgIterationsLastTick),
+            "pcg_iterations_per_step": pcg_iters / args.steps,
             "contacts_last_tick": {"point_triangle": int(st.triCollisions), "floor": int(st.staticCollisions)},
         }
-        traffic_file = os.path.join(ROOT, "profiles", "tet_kernel_traffic.json")
-        if os.path.exists(traffic_file):
-            try:
-                with open(traffic_file) as f:
-                    line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
-            except Exception:
-                pass
+        if drv is not None:
+            line["halo"] = {"bytes_per_step_rank0": halo_bytes / args.steps, "ghost_layer_still_sufficient": bool(halo_ok), "ghost_nodes_rank0": int((~drv.owned).sum()),
+                            "owned_nodes_rank0": int(drv.owned.sum())}
         if cpu is not None:
             if "error" in cpu:
                 line["cpu_baseline"] = {"value": None, "unit": "projections/s", "cores": os.cpu_count(), "kind": "reference",

@@ -89,6 +89,13 @@ typedef struct PiesB200Stats {
   float msTetKernel;           /* time inside the fused tet strain+volume projection kernel alone */
   uint32_t tetKernelLaunches;  /* its launches in the last tick */
   uint32_t reserved;
+  /* sampled launches of the other hot kernels (one timed launch per PD iteration; phase timing on only) */
+  float msSpmvKernel;          /* k_pcg_spmv: CSR-stream A z + p / Ap recurrences */
+  float msUpdateKernel;        /* k_pcg_update: x, r update + block-Jacobi apply */
+  float msGatherKernel;        /* k_gather_rhs: CSR gather of the right-hand side */
+  uint32_t spmvKernelLaunches;
+  uint32_t updateKernelLaunches;
+  uint32_t gatherKernelLaunches;
 } PiesB200Stats;
 
 typedef struct PiesB200Solver PiesB200Solver;

@@ -7,6 +7,8 @@
 
 #include "contact.h"
 #include "detect.h"
+#include <cstdlib>
+
 #include "engine.h"
 
 using pies::fail;
@@ -18,6 +20,8 @@ template <typename F>
 int guarded(PiesB200Solver* s, F&& f) {
   if (!s) return PIES_B200_EINVAL;
   try {
+    cudaSetDevice(s->device);
+    pies::g_allocStream = s->stream;  // device buffers grow on the caller's stream (engine.h: DevBuf)
     return f();
   } catch (const std::bad_alloc&) {
     return fail(s, PIES_B200_ERANGE, "host allocation failed");
@@ -59,6 +63,8 @@ void pies_b200_default_options(PiesB200Options* o) {
 void pies_b200_default_tuning(PiesB200Tuning* t) {
   if (!t) return;
   t->pcgTolerance = 1e-7f; t->pcgMaxIterations = 200; t->pcgCheckEvery = 1; t->reserved = 0;
+  // experiment hook: PIES_B200_PCG_TOL overrides the default stopping tolerance (hosts use pies_b200_set_tuning)
+  if (const char* e = std::getenv("PIES_B200_PCG_TOL")) { float v = (float)std::atof(e); if (v > 0.0f && v < 1.0f) t->pcgTolerance = v; }
 }
 
 int pies_b200_create(const PiesB200Options* options, int device, PiesB200Solver** out) {
@@ -93,6 +99,14 @@ int pies_b200_create(const PiesB200Options* options, int device, PiesB200Solver*
   }
   s->ownStream = true;
   s->hostFlag[0] = s->hostFlag[1] = 0;
+  {  // keep freed device blocks cached in the default pool instead of returning them to the driver at every sync
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   *out = s;
   return PIES_B200_OK;
 }
@@ -167,7 +181,11 @@ const PiesB200Vertex* pies_b200_get_vertices(const PiesB200Solver* cs) {
   // The reference refreshes its mirror at the end of every substep (Solver.cpp:157,393); here the D2H copy
   // is deferred to the first getVertices() after a tick, which is observably the same and free for hosts
   // that do not read every tick.
-  if (s->mirrorStale && !s->simFailed) { cudaSetDevice(s->device); if (pies::refreshVertexMirror(s) != 0) return nullptr; }
+  if (s->mirrorStale && !s->simFailed) {
+    cudaSetDevice(s->device);
+    pies::g_allocStream = s->stream;
+    if (pies::refreshVertexMirror(s) != 0) return nullptr;
+  }
   return s->scene.vertices.data();
 }
 const uint32_t* pies_b200_get_lines(const PiesB200Solver* s) { return s ? s->scene.lines.data() : nullptr; }

@@ -226,7 +226,7 @@ int refreshVertexMirror(PiesB200Solver* s) {
 namespace {
 // Phase timing with CUDA event pairs recorded on the solver stream and resolved after the
 // tick's final synchronisation (no extra syncs inside the tick).  Enabled by tuning.reserved.
-enum Phase { kPhOther = 0, kPhDetect, kPhLocal, kPhGlobal, kPhContact, kPhTetKernel, kPhCount };
+enum Phase { kPhOther = 0, kPhDetect, kPhLocal, kPhGlobal, kPhContact, kPhTetKernel, kPhSpmvKernel, kPhUpdateKernel, kPhGatherKernel, kPhCount };
 struct PhaseTimer {
   PiesB200Solver* s;
   bool on;
@@ -238,10 +238,21 @@ struct PhaseTimer {
     if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
     return pool[used++];
   }
-  void begin(int phase) { if (on) { spans.emplace_back(phase, used); cudaEventRecord(next(), s->stream); next(); } }
-  void end() { if (on) cudaEventRecord(pool[spans.back().second + 1], s->stream); }
+  // spans may nest (a sampled kernel inside a phase): begin() returns the span to hand to end()
+  int begin(int phase) {
+    if (!on) return -1;
+    spans.emplace_back(phase, used); cudaEventRecord(next(), s->stream); next();
+    return (int)spans.size() - 1;
+  }
+  void end(int span = -1) {
+    if (!on) return;
+    const auto& sp = span >= 0 ? spans[span] : spans.back();
+    cudaEventRecord(pool[sp.second + 1], s->stream);
+  }
+  void discard(int span) { if (on && span >= 0) spans[span].first = -1; }  // e.g. a sampled launch that turned out to be an early exit
   void resolve(float (&acc)[kPhCount], uint32_t (&cnt)[kPhCount]) {
     for (auto& sp : spans) {
+      if (sp.first < 0) continue;
       float ms = 0.0f;
       if (cudaEventElapsedTime(&ms, pool[sp.second], pool[sp.second + 1]) == cudaSuccess) { acc[sp.first] += ms; ++cnt[sp.first]; }
     }
@@ -328,6 +339,8 @@ int pdTickBegin(PiesB200Solver* s) {
   s->stats.pcgIterationsLastTick = 0;
   s->stats.msLocal = s->stats.msGlobal = s->stats.msDetect = s->stats.msContact = s->stats.msOther = 0.0f;
   s->stats.msTetKernel = 0.0f; s->stats.tetKernelLaunches = 0;
+  s->stats.msSpmvKernel = s->stats.msUpdateKernel = s->stats.msGatherKernel = 0.0f;
+  s->stats.spmvKernelLaunches = s->stats.updateKernelLaunches = s->stats.gatherKernelLaunches = 0;
   PdTickCtx* c = new PdTickCtx(s);
   c->launches0 = s->launches;
   s->pdCtx = c;
@@ -341,7 +354,7 @@ int pdSubstepBegin(PiesB200Solver* s) {
   PdTickCtx* c = static_cast<PdTickCtx*>(s->pdCtx);
   if (!c) return fail(s, PIES_B200_EINVAL, "pd_substep_begin outside pd_tick_begin/pd_tick_end");
   const uint32_t n = s->n;
-  if (!n) return PIES_B200_OK;
+  if (!n) { c->inSubstep = true; return PIES_B200_OK; }  // empty scene: the phases are no-ops but stay well-formed
   cudaStream_t st = s->stream;
   const PiesB200Options& o = s->opt;
   const float h = o.fixedTimestepSize / (float)o.timeSubsteps;
@@ -394,17 +407,20 @@ int pdIteration(PiesB200Solver* s) {
   timer.begin(kPhTetKernel);
   s->launches += launchTetElems(st, v.te, s->q.p, s->contrib.p + y.baseTet);
   timer.end();
-  timer.begin(kPhLocal);
+  const int spLocal = timer.begin(kPhLocal);
   s->launches += launchDistance(st, v.de, s->q.p, s->contrib.p + y.baseDist);
   s->launches += launchBend(st, v.be, s->q.p, s->contrib.p + y.baseBend);
   s->launches += launchShape(st, v.sh, s->shapeMat.p, s->shapeQinv.p, s->shapeQuat.p, s->shapeW.p, s->q.p, s->contrib.p + y.baseShape);
   s->launches += launchGoal(st, v.go, s->goalMat.p, s->goalXform.p, s->goalW.p, s->contrib.p + y.baseGoal);
   s->launches += launchContactProject(st, lists, s->q.p, s->opt.collisionThickness, contribC, s->snap.p);
+  const int spGather = timer.begin(kPhGatherKernel);
   s->launches += launchGatherRhs(st, n, s->msn.p, s->incPtr.p, s->inc.p, s->contrib.p, s->rhs.p);
+  timer.end(spGather);
   s->launches += launchGatherContacts(st, n, lists, contribC, s->snap.p, s->rhs.p);
-  timer.end();
+  timer.end(spLocal);
 
-  timer.begin(kPhGlobal);
+  const int spGlobal = timer.begin(kPhGlobal);
+  int spSpmv = -1, spUpdate = -1;  // one sampled CG iteration (the second of the solve) per PD iteration
   s->launches += launchPcgInit(st, v.A, lists, v.pw, s->rhs.p, s->q.p, s->tune.pcgTolerance);
   // Iterations are enqueued in bursts without host round trips: converged solves turn the remaining
   // launches into early exits (~2 us each), a host poll costs ~40 us of idle GPU, so the first burst
@@ -413,7 +429,19 @@ int pdIteration(PiesB200Solver* s) {
   bool converged = false;
   while (!converged && done < s->tune.pcgMaxIterations) {
     uint32_t todo = std::min(burst, s->tune.pcgMaxIterations - done);
-    for (uint32_t k = 0; k < todo; ++k) s->launches += launchPcgIteration(st, v.A, lists, v.pw, s->tune.pcgTolerance, (int)(done + k));
+    for (uint32_t k = 0; k < todo; ++k) {
+      const int it = (int)(done + k);
+      if (it == 1 && timer.on) {
+        spSpmv = timer.begin(kPhSpmvKernel);
+        s->launches += launchPcgSpmv(st, v.A, lists, v.pw, s->tune.pcgTolerance, it);
+        timer.end(spSpmv);
+        spUpdate = timer.begin(kPhUpdateKernel);
+        s->launches += launchPcgUpdate(st, v.pw, s->tune.pcgTolerance, it);
+        timer.end(spUpdate);
+      } else {
+        s->launches += launchPcgIteration(st, v.A, lists, v.pw, s->tune.pcgTolerance, it);
+      }
+    }
     done += todo;
     s->launches += launchPcgCheck(st, v.pw, s->tune.pcgTolerance, (int)done - 1);
     PIES_CHECK(s, cudaMemcpyAsync(s->hostFlag, s->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -426,7 +454,8 @@ int pdIteration(PiesB200Solver* s) {
   if (getenv("PIES_DEBUG_PCG")) std::fprintf(stderr, "[pcg] it: %u iterations\n", used);
   s->lastPcgIters = std::max(1u, used);
   s->stats.pcgIterationsLastTick += used;
-  timer.end();
+  if (used < 2) { timer.discard(spSpmv); timer.discard(spUpdate); }  // the sampled launches were early exits
+  timer.end(spGlobal);
   s->stats.projectionsLastTick += y.staticProjections + lists.nTri + lists.nFloor;
   return PIES_B200_OK;
 }
@@ -469,12 +498,15 @@ int pdTickEnd(PiesB200Solver* s, bool refreshMirror) {
   if (es != cudaSuccess) { pdAbort(s); return failCuda(s, es, "cudaEventSynchronize", __LINE__); }
   cudaEventElapsedTime(&s->stats.msTick, c->tick0, c->tick1);
   {
-    float acc[kPhCount] = {0, 0, 0, 0, 0, 0};
-    uint32_t cnt[kPhCount] = {0, 0, 0, 0, 0, 0};
+    float acc[kPhCount] = {};
+    uint32_t cnt[kPhCount] = {};
     c->timer.resolve(acc, cnt);
     s->stats.msOther = acc[kPhOther]; s->stats.msDetect = acc[kPhDetect]; s->stats.msLocal = acc[kPhLocal] + acc[kPhTetKernel];
     s->stats.msGlobal = acc[kPhGlobal]; s->stats.msContact = acc[kPhContact];
     s->stats.msTetKernel = acc[kPhTetKernel]; s->stats.tetKernelLaunches = cnt[kPhTetKernel];
+    s->stats.msSpmvKernel = acc[kPhSpmvKernel]; s->stats.spmvKernelLaunches = cnt[kPhSpmvKernel];
+    s->stats.msUpdateKernel = acc[kPhUpdateKernel]; s->stats.updateKernelLaunches = cnt[kPhUpdateKernel];
+    s->stats.msGatherKernel = acc[kPhGatherKernel]; s->stats.gatherKernelLaunches = cnt[kPhGatherKernel];
   }
   uint64_t launches0 = c->launches0;
   pdAbort(s);

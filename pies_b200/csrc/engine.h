@@ -12,6 +12,12 @@
 
 namespace pies {
 
+// Stream every grow-only buffer (re)allocates on: the calling solver's stream, set at each C-ABI entry
+// (capi.cpp: guarded()).  Allocation is stream-ordered (cudaMallocAsync from the device's default pool, whose
+// release threshold pies_b200_create raises so freed blocks stay cached): growing a contact-sized buffer in
+// the middle of a substep neither synchronises the device nor goes back to the driver for memory.
+inline thread_local cudaStream_t g_allocStream = nullptr;
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -20,13 +26,13 @@ struct DevBuf {
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-  // grow-only; contents are NOT preserved
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }  // synchronising; destructor / clear only
+  // grow-only; contents are NOT preserved.  Work already enqueued on the stream keeps the old block (the free is stream-ordered).
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
-    release();
-    size_t want = n + n / 2 + 64;  // geometric growth: contact-sized buffers grow a little every substep
-    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (p) { cudaFreeAsync(p, g_allocStream); p = nullptr; cap = 0; }
+    size_t want = 2 * n + 64;  // geometric growth: contact-sized buffers grow a little every substep
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p), want * sizeof(T), g_allocStream);
     if (e == cudaSuccess) cap = want; else p = nullptr;
     return e;
   }

@@ -82,7 +82,7 @@ struct PcgWork {
   // block-Jacobi preconditioner (rebuilt per substep, reblock.cu): blocks of m <= 32 nodes, dense inverse of
   // S + C_t restricted to the block
   int* blockNodes = nullptr;   // nBlocks * 32 node ids, members first (-1 = padding)
-  float* blockInv = nullptr;   // per block m x m, symmetric, [j*m + i], at blockOff[b]
+  float* blockInv = nullptr;   // per block: packed lower triangle of the symmetric m x m inverse, (j, i <= j) at j (j + 1) / 2 + i
   const uint2* blockMeta = nullptr;        // per block: (offset into blockInv in floats, m)
   uint32_t nBlocks = 0;                    // upper bound used for grid sizing
   const uint32_t* nBlocksDev = nullptr;    // actual block count of this substep (device)
@@ -93,6 +93,8 @@ int launchPcgInit(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, con
                   const float4* b, const float4* x, float tol);
 // it = iteration index within the solve (parity selects the double-buffered r.z slot and direction buffer)
 int launchPcgIteration(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, float tol, int it);
+int launchPcgSpmv(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, float tol, int it);  // first half of an iteration
+int launchPcgUpdate(cudaStream_t s, const PcgWork& w, float tol, int it);                                          // second half
 int launchPcgCheck(cudaStream_t s, const PcgWork& w, float tol, int lastIt);
 // x += delta: the correction is accumulated separately and added with a single rounding
 int launchPcgFinish(cudaStream_t s, const PcgWork& w, uint32_t n, float4* x);

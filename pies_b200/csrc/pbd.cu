@@ -174,7 +174,8 @@ struct BendOp {  // BendConstraintProjection (Constraints.cpp:312-366) + project
     V3 n2 = v3(ex::div(c24.x, l24), ex::div(c24.y, l24), ex::div(c24.z, l24));
     float d = ex::dot3(n1, n2);
     float d2 = ex::mul(d, d);
-    float C = ex::sub(acosf(d), aw.x);
+    // the reference's unqualified acos()/sqrt() are the double overloads: C and the numerator are rounded to float once
+    float C = (float)(acos((double)d) - (double)aw.x);
     auto divv = [](V3 a, float s) { return v3(ex::div(a.x, s), ex::div(a.y, s), ex::div(a.z, s)); };
     V3 q3 = divv(ex::add(ex::cross3(p2, n2), ex::scale(ex::cross3(n1, p2), d)), l23);
     V3 q4 = divv(ex::add(ex::cross3(p2, n1), ex::scale(ex::cross3(n2, p2), d)), l24);
@@ -184,7 +185,8 @@ struct BendOp {  // BendConstraintProjection (Constraints.cpp:312-366) + project
     V3 q1 = ex::sub(ex::sub(v3(-q2.x, -q2.y, -q2.z), q3), q4);
     float wSum = ex::add(ex::add(ex::add(n1_.w, n2_.w), n3_.w), n4_.w);
     float qq = ex::add(ex::add(ex::add(ex::dot3(q1, q1), ex::dot3(q2, q2)), ex::dot3(q3, q3)), ex::dot3(q4, q4));
-    float num = ex::mul(__fsqrt_rn(fmaxf(ex::sub(1.0f, d2), 0.0f)), C);
+    float om = ex::sub(1.0f, d2);
+    float num = (float)(sqrt((double)(om < 0.0f ? 0.0f : om)) * (double)C);  // glm::max(x, 0) keeps a NaN x
     if (qq < 0.00001f) return;  // projected == positions: position += w * 0
     const V3 qs[4] = {q1, q2, q3, q4};
     float4 nodes[4] = {n1_, n2_, n3_, n4_};

@@ -172,19 +172,23 @@ __global__ void __launch_bounds__(kThreads) k_pcg_finish(uint32_t n, float4* __r
   x[i] = make_float4(xv.x + d.x, xv.y + d.y, xv.z + d.z, xv.w);
 }
 
-// Warp-per-block preconditioner application.  The block's m x m inverse is contiguous (<= 4 KB): every lane
-// issues its up-to-8 independent 16 B loads at once (4 KB in flight per warp keeps HBM busy; a row-by-row
-// loop does not), parks them in shared memory, and the mat-vec z_lane = sum_j Minv[j][lane] r_j runs from there.
+// Warp-per-block preconditioner application.  The block's symmetric inverse is stored as a packed lower
+// triangle (m (m + 1) / 2 floats, <= 2112 B, contiguous: half the HBM stream of a full m x m block): every lane
+// issues its up-to-5 independent 16 B loads at once, parks them in shared memory, and the mat-vec
+// z_lane = sum_j Minv(j, lane) r_j runs from there.  Triangular numbers are distinct modulo 32, so the packed
+// reads of one j are at most two-way bank conflicted.
 constexpr int kPcgWarps = kThreads / 32;
+constexpr int kInvFloats = 544;                 // >= 32 * 33 / 2 = 528, multiple of 32
+constexpr int kInvLoads = (528 / 4 + 31) / 32;  // 16 B loads per lane for the largest block
 
 // Asynchronous global -> shared copy of the block's inverse (cp.async, 16 B per lane per step, no registers held).
 __device__ __forceinline__ void issueBlockInv(float* __restrict__ sInv, const float* __restrict__ inv, int m, int lane) {
-  const int size4 = (m * m + 3) >> 2;
+  const int size4 = (m * (m + 1) / 2 + 3) >> 2;
   __syncwarp();  // the previous block's reads of this buffer are finished
   uint32_t dst = (uint32_t)__cvta_generic_to_shared(sInv) + 16u * lane;
   const float4* src = reinterpret_cast<const float4*>(inv) + lane;
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
+  for (int t = 0; t < kInvLoads; ++t) {
     if (lane + 32 * t < size4)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u * t), "l"(src + 32 * t) : "memory");
   }
@@ -196,9 +200,10 @@ __device__ __forceinline__ V3 applyBlockInv(const float* __restrict__ sInv, V3 r
   __syncwarp();
   V3 z = v3(0.0f, 0.0f, 0.0f);
   const int col = lane < m ? lane : 0;
+  const int colBase = col * (col + 1) / 2;
 #pragma unroll 4
   for (int j = 0; j < m; ++j) {
-    float mv = sInv[j * m + col];
+    float mv = sInv[j >= col ? j * (j + 1) / 2 + col : colBase + j];
     z.x += mv * __shfl_sync(0xffffffffu, r.x, j);
     z.y += mv * __shfl_sync(0xffffffffu, r.y, j);
     z.z += mv * __shfl_sync(0xffffffffu, r.z, j);
@@ -209,7 +214,7 @@ __device__ __forceinline__ V3 applyBlockInv(const float* __restrict__ sInv, V3 r
 // z = Minv r ; partial r.z (odd parity slot = "iteration -1") and r.r
 __global__ void __launch_bounds__(kThreads, 4) k_pcg_start(PcgWork w, float* __restrict__ partials) {
   __shared__ float smem[6 * 32];
-  __shared__ __align__(16) float sInv[kPcgWarps][1024];
+  __shared__ __align__(16) float sInv[kPcgWarps][kInvFloats];
   int lane = threadIdx.x & 31;
   uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
   float acc[6] = {0, 0, 0, 0, 0, 0};
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(kThreads) k_pcg_spmv(CsrMatrix A, ContactLists
 __global__ void __launch_bounds__(kThreads, 4) k_pcg_update(PcgWork w, float4* __restrict__ x, float* __restrict__ partials,
                                                          int parity, float tol2) {
   __shared__ float smem[6 * 32];
-  __shared__ __align__(16) float sInv[kPcgWarps][1024];
+  __shared__ __align__(16) float sInv[kPcgWarps][kInvFloats];
   if (ctaConverged(w.flag)) return;
   float rz[3], pap[3], alpha[3], rr[3], bb[3];
   const int prevSet = parity ? kSet0 : kSet1, mySet = parity ? kSet1 : kSet0;
@@ -423,11 +428,18 @@ int launchPcgInit(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, con
 }
 
 // One CG iteration = two kernels.  `it` = iteration index within the solve.
+int launchPcgSpmv(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, float tol, int it) {
+  k_pcg_spmv<<<kReduceBlocks, kThreads, 0, s>>>(A, c, w, w.partials, it & 1, it == 0 ? 1 : 0, tol * tol);
+  return 1;
+}
+
+int launchPcgUpdate(cudaStream_t s, const PcgWork& w, float tol, int it) {
+  k_pcg_update<<<kReduceBlocks, kThreads, 0, s>>>(w, w.delta, w.partials, it & 1, tol * tol);
+  return 1;
+}
+
 int launchPcgIteration(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, float tol, int it) {
-  int parity = it & 1;
-  k_pcg_spmv<<<kReduceBlocks, kThreads, 0, s>>>(A, c, w, w.partials, parity, it == 0 ? 1 : 0, tol * tol);
-  k_pcg_update<<<kReduceBlocks, kThreads, 0, s>>>(w, w.delta, w.partials, parity, tol * tol);
-  return 2;
+  return launchPcgSpmv(s, A, c, w, tol, it) + launchPcgUpdate(s, w, tol, it);
 }
 
 // Latches the convergence flag after the last enqueued iteration (the host reads it next).

@@ -130,14 +130,15 @@ __global__ void __launch_bounds__(kThreads) k_bend(BendElems e, const float4* __
   float l23 = length(p2Xp3), l24 = length(p2Xp4);
   V3 n1 = p2Xp3 / l23, n2 = p2Xp4 / l24;
   float d = dot(n1, n2);
-  float C = acosf(d) - aw.x;
+  float C = (float)(acos((double)d) - (double)aw.x);  // the reference's unqualified acos() is the double overload
   V3 q3 = (cross(p2, n2) + cross(n1, p2) * d) / l23;
   V3 q4 = (cross(p2, n1) + cross(n2, p2) * d) / l24;
   V3 q2 = -((cross(p3, n2) + cross(n1, p3) * d) / l23) - ((cross(p4, n1) + cross(n2, p4) * d) / l24);
   V3 q1 = -q2 - q3 - q4;
   float wSum = n1_.w + n2_.w + n3_.w + n4_.w;
   float qq = dot(q1, q1) + dot(q2, q2) + dot(q3, q3) + dot(q4, q4);
-  float num = sqrtf(fmaxf(1.0f - d * d, 0.0f)) * C;
+  float om = 1.0f - d * d;
+  float num = (float)(sqrt((double)(om < 0.0f ? 0.0f : om)) * (double)C);
   V3 o1 = x1, o2 = x2, o3 = x3, o4 = x4;
   if (!(qq < 0.00001f)) {
     o1 += -q1 * (4.0f * n1_.w / wSum) * num / qq;

@@ -137,13 +137,14 @@ __global__ void __launch_bounds__(kThreads) k_assign_dynamic(uint32_t nT, uint32
   if ((rank & 31u) == 0u) blockCount[blk] = min(32u, size - rank);
 }
 
-// storage of every block's inverse: m x m floats (rounded up to 16 B), offsets by exclusive scan
+// storage of every block's inverse: the lower triangle of the symmetric m x m matrix, packed by rows
+// (m (m + 1) / 2 floats, rounded up to 16 B; entry (j, i), i <= j, at j (j + 1) / 2 + i), offsets by exclusive scan
 __global__ void __launch_bounds__(kThreads) k_block_sizes(uint32_t bound, const uint32_t* __restrict__ nBlocksPtr,
                                                           const uint32_t* __restrict__ blockCount, uint32_t* __restrict__ sq) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > bound) return;
   uint32_t m = b < *nBlocksPtr ? blockCount[b] : 0u;
-  sq[b] = (m * m + 3u) & ~3u;
+  sq[b] = (m * (m + 1u) / 2u + 3u) & ~3u;
 }
 
 // static blocks: drop the touched nodes and pack the rest to the front (one warp per block)
@@ -195,11 +196,11 @@ __global__ void __launch_bounds__(kFactorWarps * 32) k_block_factor(uint32_t nSt
   float* out = blockInv + blockOff[b];
   const int node = blockNodes[b * 32 + lane];
   const uint32_t valid = __ballot_sync(0xffffffffu, node >= 0);
-  const int m = __popc(valid);  // members are packed at the front; the inverse is stored m x m: out[j * m + i]
+  const int m = __popc(valid);  // members are packed at the front; the inverse is stored as a packed lower triangle
   if (lane == 0) blockMeta[b] = make_uint2(blockOff[b], (uint32_t)m);
   if (b < nStatic && !dirty[b]) {  // untouched static block: the once-per-topology inverse (stored 32 x 32)
     const float* src = baseInv + (size_t)b * 1024;
-    for (int j = 0; j < m; ++j) if (lane < m) out[j * m + lane] = src[j * 32 + lane];
+    for (int j = 0; j < m; ++j) if (lane <= j) out[j * (j + 1) / 2 + lane] = src[j * 32 + lane];
     return;
   }
   float* M = sM[warp];
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kFactorWarps * 32) k_block_factor(uint32_t nSt
     if (node >= 0) {
       for (int k = S.rowPtr[node]; k < S.rowPtr[node + 1]; ++k) if (S.col[k] == node) diag = S.val[k];
     }
-    for (int j = 0; j < m; ++j) if (lane < m) out[j * m + lane] = j == lane ? 1.0f / diag : 0.0f;
+    for (int j = 0; j < m; ++j) if (lane <= j) out[j * (j + 1) / 2 + lane] = j == lane ? 1.0f / diag : 0.0f;
     return;
   }
   // X = L^-1 (lower): lane c owns column c
@@ -268,13 +269,12 @@ __global__ void __launch_bounds__(kFactorWarps * 32) k_block_factor(uint32_t nSt
     }
   }
   __syncwarp();
-  // Minv = X^T X: lane i owns row i (== column i)
+  // Minv = X^T X, lower triangle only: lane i <= j owns entry (j, i)
   for (int j = 0; j < m; ++j) {
-    if (lane < m) {
+    if (lane <= j) {
       float s = 0.0f;
-      int k0 = lane > j ? lane : j;
-      for (int k = k0; k < m; ++k) s += X[k * kLd + lane] * X[k * kLd + j];
-      out[j * m + lane] = s;
+      for (int k = j; k < m; ++k) s += X[k * kLd + lane] * X[k * kLd + j];
+      out[j * (j + 1) / 2 + lane] = s;
     }
   }
 }
@@ -314,7 +314,7 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   w.nBlocksBound = bound;
   RCHECK(w.blockNodes.reserve((size_t)bound * 32));
   RCHECK(w.blockCount.reserve(bound + 2)); RCHECK(w.blockOff.reserve(bound + 2)); RCHECK(w.blockMeta.reserve(bound + 2));
-  RCHECK(w.blockInv.reserve((size_t)32 * n + 4ull * bound + 64));  // sum m^2 <= 32 * sum m = 32 n, plus rounding
+  RCHECK(w.blockInv.reserve((size_t)17 * n + 4ull * bound + 64));  // sum m (m + 1) / 2 <= 16.5 * sum m, plus rounding
   w.scanCap = std::max<uint64_t>(w.scanCap, (uint64_t)bound + 2);
   if (nT) {
     RCHECK(w.keys.reserve(nT)); RCHECK(w.tmpKeys.reserve(nT)); RCHECK(w.vals.reserve(nT)); RCHECK(w.tmpVals.reserve(nT));

@@ -9,7 +9,7 @@ namespace pies {
 
 struct BlockWork {
   DevBuf<int> blockNodes;        // (static + dynamic blocks) * 32, members packed to the front, -1 padded
-  DevBuf<float> blockInv;        // m x m per block (m = members), at blockOff[b]
+  DevBuf<float> blockInv;        // packed lower triangle per block (m = members), at blockOff[b]
   DevBuf<uint32_t> blockCount, blockOff;
   DevBuf<uint2> blockMeta;       // (blockOff, m) per block, what the CG kernels read
   DevBuf<uint32_t> slotOf;       // node -> block * 32 + lane

@@ -48,6 +48,8 @@ class Stats(C.Structure):
         ("msDetect", C.c_float), ("msContact", C.c_float), ("msOther", C.c_float),
         ("pcgLastRelResidual", C.c_float), ("msTetKernel", C.c_float),
         ("tetKernelLaunches", C.c_uint32), ("reserved", C.c_uint32),
+        ("msSpmvKernel", C.c_float), ("msUpdateKernel", C.c_float), ("msGatherKernel", C.c_float),
+        ("spmvKernelLaunches", C.c_uint32), ("updateKernelLaunches", C.c_uint32), ("gatherKernelLaunches", C.c_uint32),
     ]
 
 

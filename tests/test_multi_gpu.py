@@ -5,9 +5,17 @@ partitioning, so the test is N-rank result == 1-rank result).
    rows copied tensor-to-tensor instead of through NCCL), so the halo logic is exercised on single-GPU boxes;
  * `nccl` tests spawn one process per GPU and need >= 2 GPUs (skipped otherwise).
 
-Tolerance: 1e-4 x scene bbox diagonal, the north_star's position tolerance.  The partitioned solve is not
-bit-identical by construction: each rank's CG stops on its own residual norm, and a ghost body misses the contacts
-with its far-side neighbours within one iteration (corrected by the per-iteration halo overwrite)."""
+Tolerance: 1e-4 x scene bbox diagonal, the north_star's position tolerance, inside the window in which the scene
+is not yet chaotic.  The partitioned solve is not bit-identical by construction: each rank's CG stops on its own
+residual norm, and a ghost body misses the contacts with its far-side neighbours within one iteration (corrected
+by the per-iteration halo overwrite).  Measured on a B200 (scripts/diag_r01c.py, profiles/r01d_diag_multigpu.log):
+
+ * the row-of-columns scene below amplifies ANY perturbation once the stacks land (ticks > ~16): the single-GPU
+   solver run with pcgTolerance 0.7e-7 instead of 1e-7 drifts from itself by 1.5e-3 at tick 20 and 0.15 at tick 40,
+   exactly like the partitioned run, so later ticks are checked for sanity only;
+ * a ghost layer ONE body deep (halo 1.0 at pitch 2.05) leaves a coupling error of ~2e-4 per tick on glued
+   columns; TWO bodies deep (halo 3.2) stays at the perturbation noise level (3e-5 at tick 5).  The tests and
+   bench.py therefore use a two-body halo."""
 import os
 import socket
 import sys
@@ -49,9 +57,10 @@ def _single(pb, specs, ticks):
     return out
 
 
-@pytest.mark.parametrize("world,halo,pitch", [(2, 1.0, 2.05), (3, 1.0, 2.05), (2, 0.5, 3.0)])
+@pytest.mark.parametrize("world,halo,pitch", [(2, 3.2, 2.05), (3, 3.2, 2.05), (2, 0.5, 3.0)])
 def test_lockstep_ranks_match_single_solver(pb, world, halo, pitch):
-    ticks = (1, 5, 20, 40)
+    strict = (1, 5, 10, 15)          # before the scene turns chaotic (see module docstring)
+    ticks = strict + (30,)
     specs = row_specs(columns=6, pitch=pitch)
     ref = _single(pb, specs, ticks)
     ranks = [multigpu.SlabSolver(specs, rank=r, world=world, halo=halo, device=0, snap=0.5, **OPTS) for r in range(world)]
@@ -63,12 +72,27 @@ def test_lockstep_ranks_match_single_solver(pb, world, halo, pitch):
         if t in ticks:
             pos, prev, vel = multigpu.gather_lockstep(ranks)
             err = float(np.abs(pos - ref[t][0]).max())
-            assert err <= 1e-4 * diag, (world, t, err, 1e-4 * diag, ref[t][2])
+            if t in strict:
+                assert err <= 1e-4 * diag, (world, t, err, 1e-4 * diag, ref[t][2])
+            else:   # chaotic regime: same bodies in the same places, nothing blown up or tunnelled
+                assert np.isfinite(pos).all() and pos[:, 1].min() >= -1e-3 and err <= 0.05 * diag, (world, t, err)
     if pitch < 2.5:
-        assert ref[max(ticks)][2] > 0        # the comparison did cover cross-cut contacts
+        assert ref[max(strict)][2] > 0        # the strict comparison did cover cross-cut contacts
         owned_contacts = sum(sum(r.solver.countOwnedContacts()) for r in ranks)
-        st = _single(pb, specs, (max(ticks),))
         assert owned_contacts > 0
+
+
+def test_one_body_halo_is_not_enough(pb):
+    """Documents the coupling error of a one-body-deep ghost layer (why the default is two): it stays bounded
+    (< 1e-3 x diagonal after 5 ticks) but above the strict tolerance of the two-body halo."""
+    specs = row_specs(columns=6, pitch=2.05)
+    ref = _single(pb, specs, (5,))
+    ranks = [multigpu.SlabSolver(specs, rank=r, world=2, halo=1.0, device=0, snap=0.5, **OPTS) for r in range(2)]
+    for _ in range(5):
+        multigpu.tick_lockstep(ranks)
+    pos, _, _ = multigpu.gather_lockstep(ranks)
+    err = float(np.abs(pos - ref[5][0]).max())
+    assert err <= 1e-3 * bbox_diag(ref[5][0]), err
 
 
 def test_world1_slab_solver_is_the_plain_solver(pb):
@@ -113,8 +137,8 @@ def _nccl_worker(rank, world, port, out):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     specs = row_specs(columns=6)
-    s = mg.SlabSolver(specs, rank=rank, world=world, halo=1.0, device=rank, dist=dist, snap=0.5, **OPTS)
-    for _ in range(20):
+    s = mg.SlabSolver(specs, rank=rank, world=world, halo=3.2, device=rank, dist=dist, snap=0.5, **OPTS)
+    for _ in range(10):
         s.tick()
     ok = s.check_halo(repartition=False)
     pos, prev, vel = s.gather_state()
@@ -129,10 +153,10 @@ def test_nccl_two_ranks_match_single_solver(pb):
         pytest.skip("needs >= 2 GPUs")
     import torch.multiprocessing as mp
     specs = row_specs(columns=6)
-    ref = _single(pb, specs, (20,))
+    ref = _single(pb, specs, (10,))
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_nccl_worker, args=(2, _free_port(), out), nprocs=2, join=True)
-    diag = bbox_diag(ref[20][0])
-    assert float(np.abs(out["pos"] - ref[20][0]).max()) <= 1e-4 * diag
+    diag = bbox_diag(ref[10][0])
+    assert float(np.abs(out["pos"] - ref[10][0]).max()) <= 1e-4 * diag
     assert out["halo_bytes"] > 0
