@@ -250,8 +250,8 @@ def main():
     for _ in range(args.steps):
         s.setState(hp, hv, hq)          # H2D: 3 x 12 B per node from pinned memory
         tick()
-        s.getVertices()                 # the reference-facing readback: D2H 12 B per node into the Vertex mirror
-        hp[:] = s.positions; hv[:] = s.prevPositions; hq[:] = s.velocities  # D2H of the full state
+        s.getVertices(copy=False)       # the reference-facing readback: D2H 12 B per node into the Vertex mirror
+        s.getState(hp, hv, hq)          # D2H of the full state into the same host buffers
         e2e_proj += projections()
     barrier()
     e2e_s = time.time() - t0

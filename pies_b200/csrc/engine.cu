@@ -69,9 +69,14 @@ int downloadVec3(PiesB200Solver* s, const float4* src, float* dstXYZ) {
   }
   k_pack3<<<gridFor(n, kThreads), kThreads, 0, s->stream>>>(n, src, s->packed.p);
   ++s->launches;
-  PIES_CHECK(s, cudaMemcpyAsync(s->hostPacked, s->packed.p, 3ull * n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  // A page-locked destination takes the DMA directly; pageable memory goes through the solver's pinned staging buffer.
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, dstXYZ) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  if (!pinned) cudaGetLastError();
+  float* dmaDst = pinned ? dstXYZ : s->hostPacked;
+  PIES_CHECK(s, cudaMemcpyAsync(dmaDst, s->packed.p, 3ull * n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
   PIES_CHECK(s, cudaStreamSynchronize(s->stream));
-  std::memcpy(dstXYZ, s->hostPacked, 3ull * n * sizeof(float));
+  if (!pinned) std::memcpy(dstXYZ, s->hostPacked, 3ull * n * sizeof(float));
   return PIES_B200_OK;
 }
 

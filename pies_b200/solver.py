@@ -242,13 +242,16 @@ class Solver:
     simFailed = property(lambda self: bool(lib().pies_b200_sim_failed(self.h)))
 
     # -- readback (Solver.h:65-69) --
-    def getVertices(self):
+    def getVertices(self, copy=True):
+        """Solver::getVertices (Solver.h:65).  copy=False hands out a view of the solver-owned mirror, valid until
+        the next mutating call - the reference's `const std::vector<Vertex>&` contract."""
         n = lib().pies_b200_vertex_count(self.h)
         if n == 0:
             return np.zeros(0, VERTEX_DTYPE)
         p = lib().pies_b200_get_vertices(self.h)
         buf = (C.c_char * (n * VERTEX_DTYPE.itemsize)).from_address(p)
-        return np.frombuffer(buf, dtype=VERTEX_DTYPE, count=n).copy()
+        a = np.frombuffer(buf, dtype=VERTEX_DTYPE, count=n)
+        return a.copy() if copy else a
 
     def getLines(self):
         n = lib().pies_b200_line_index_count(self.h)
@@ -358,6 +361,17 @@ class Solver:
     positions = property(lambda self: self._vec(lib().pies_b200_get_positions))
     prevPositions = property(lambda self: self._vec(lib().pies_b200_get_prev_positions))
     velocities = property(lambda self: self._vec(lib().pies_b200_get_velocities))
+
+    def getState(self, pos=None, prev=None, vel=None):
+        """Reads the node state into caller-owned C-contiguous float32 (n, 3) arrays (pinned or pageable)."""
+        n = lib().pies_b200_vertex_count(self.h)
+        for a, fn in ((pos, lib().pies_b200_get_positions), (prev, lib().pies_b200_get_prev_positions),
+                      (vel, lib().pies_b200_get_velocities)):
+            if a is None:
+                continue
+            if a.dtype != np.float32 or not a.flags.c_contiguous or a.size != 3 * n:
+                raise ValueError("getState needs C-contiguous float32 arrays of %d x 3" % n)
+            self._ck(fn(self.h, a))
 
     def setState(self, pos=None, prev=None, vel=None):
         arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in (pos, prev, vel)]
