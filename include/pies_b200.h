@@ -65,7 +65,9 @@ typedef struct PiesB200Tuning {
   float pcgTolerance;        /* stop when ||r||_2 <= tol * ||b||_2 per coordinate column; default 1e-7 */
   uint32_t pcgMaxIterations; /* default 200 */
   uint32_t pcgCheckEvery;    /* host polls the device convergence flag every k iterations; default 1 */
-  uint32_t reserved;         /* 1 = record per-phase CUDA-event timings into PiesB200Stats (no extra syncs) */
+  uint32_t reserved;         /* flag bits: 1 = record per-phase CUDA-event timings into PiesB200Stats (no extra syncs);
+                              * 2 = ordered contact sweeps of every cluster above 32 nodes by the dataflow executor
+                              *     (no shared-memory sweeps of mid-size clusters; same result, for testing) */
 } PiesB200Tuning;
 
 /* Counters and device-side phase timings of the most recent tick ([additive]). */
@@ -88,7 +90,8 @@ typedef struct PiesB200Stats {
   float pcgLastRelResidual;
   float msTetKernel;           /* time inside the fused tet strain+volume projection kernel alone */
   uint32_t tetKernelLaunches;  /* its launches in the last tick */
-  uint32_t reserved;
+  uint32_t reserved;           /* contact clusters of the last substep swept from shared memory (low 16 bits, saturating)
+                                * and by the dataflow executor (high 16 bits) */
   /* sampled launches of the other hot kernels (one timed launch per PD iteration; phase timing on only) */
   float msSpmvKernel;          /* k_pcg_spmv: CSR-stream A z + p / Ap recurrences */
   float msUpdateKernel;        /* k_pcg_update: x, r update + block-Jacobi apply */

@@ -8,6 +8,7 @@
 // reference, and the result depends on that order.  They run here as dataflow sweeps
 // that honour exactly that order per node (k_gs_dataflow below).
 #include "contact.h"
+#include "reblock.h"
 
 #include "common.cuh"
 
@@ -195,14 +196,16 @@ __global__ void __launch_bounds__(kGsThreads) k_gs_dataflow(const uint4* __restr
 // the reference at register latency, all four stabilisation sweeps in one launch.
 __global__ void __launch_bounds__(kThreads) k_entry_keys(uint32_t nTri, const uint4* __restrict__ entries,
                                                          const uint32_t* __restrict__ clusterOf,
-                                                         const uint32_t* __restrict__ slotOf, uint64_t* __restrict__ keys,
+                                                         const uint32_t* __restrict__ rankOf, uint64_t* __restrict__ keys,
                                                          uint32_t* __restrict__ lanes, uint32_t* __restrict__ entCount) {
   uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nTri) return;
   uint4 id = entries[e];
   uint32_t c = clusterOf[id.x];
-  keys[e] = c;
-  lanes[e] = (slotOf[id.x] & 31u) | ((slotOf[id.y] & 31u) << 8) | ((slotOf[id.z] & 31u) << 16) | ((slotOf[id.w] & 31u) << 24);
+  // The sort only looks at the cluster bits, so the high word of the key travels as a second payload:
+  // ranks of the four nodes inside their cluster, 16 bits each (unused above 65535 nodes: dataflow sweeps).
+  keys[e] = ((uint64_t)((rankOf[id.z] & 0xffffu) | (rankOf[id.w] << 16)) << 32) | c;
+  lanes[e] = (rankOf[id.x] & 0xffffu) | (rankOf[id.y] << 16);
   atomicAdd(entCount + c, 1u);
 }
 
@@ -233,10 +236,11 @@ __global__ void __launch_bounds__(kThreads) k_gs_cluster_stabilize(ClusterView c
     for (uint32_t sweep = 0; sweep < sweeps; ++sweep) {
       for (uint32_t base = eb; base < ee; base += 32) {
         const uint32_t myW = base + lane < ee ? cv.lanes[base + lane] : 0u;
+        const uint32_t myW2 = base + lane < ee ? (uint32_t)(cv.keys[base + lane] >> 32) : 0u;
         const int cnt = (int)min(32u, ee - base);
         for (int i = 0; i < cnt; ++i) {
-          const uint32_t lw = __shfl_sync(0xffffffffu, myW, i);
-          const int la = lw & 31u, lb = (lw >> 8) & 31u, lc = (lw >> 16) & 31u, ld = (lw >> 24) & 31u;
+          const uint32_t lw = __shfl_sync(0xffffffffu, myW, i), lw2 = __shfl_sync(0xffffffffu, myW2, i);
+          const int la = lw & 31u, lb = (lw >> 16) & 31u, lc = lw2 & 31u, ld = (lw2 >> 16) & 31u;
           // PointTriangleCollisionConstraint::stabilizeCollisions (CollisionConstraint.cpp:126-162), as StabilizeOp
           V3 A = shflV3(q4, la), B = shflV3(q4, lb), C = shflV3(q4, lc), D = shflV3(q4, ld);
           float wa = __shfl_sync(0xffffffffu, q4.w, la), wb = __shfl_sync(0xffffffffu, q4.w, lb),
@@ -277,10 +281,11 @@ __global__ void __launch_bounds__(kThreads) k_gs_cluster_friction(ClusterView cv
     const uint32_t eb = cv.entStart[c], ee = cv.entStart[c + 1];
     for (uint32_t base = eb; base < ee; base += 32) {
       const uint32_t myW = base + lane < ee ? cv.lanes[base + lane] : 0u;
+      const uint32_t myW2 = base + lane < ee ? (uint32_t)(cv.keys[base + lane] >> 32) : 0u;
       const int cnt = (int)min(32u, ee - base);
       for (int i = 0; i < cnt; ++i) {
-        const uint32_t lw = __shfl_sync(0xffffffffu, myW, i);
-        const int la = lw & 31u, lb = (lw >> 8) & 31u, lc = (lw >> 16) & 31u, ld = (lw >> 24) & 31u;
+        const uint32_t lw = __shfl_sync(0xffffffffu, myW, i), lw2 = __shfl_sync(0xffffffffu, myW2, i);
+        const int la = lw & 31u, lb = (lw >> 16) & 31u, lc = lw2 & 31u, ld = (lw2 >> 16) & 31u;
         // point-triangle friction / restitution (Solver.cpp:431-471), as FrictionOp
         V3 B = shflV3(q4, lb), C = shflV3(q4, lc), D = shflV3(q4, ld);
         float wa = __shfl_sync(0xffffffffu, q4.w, la), wb = __shfl_sync(0xffffffffu, q4.w, lb),
@@ -306,6 +311,127 @@ __global__ void __launch_bounds__(kThreads) k_gs_cluster_friction(ClusterView cv
       }
     }
     if (have) vel[node] = make_float4(v4.x, v4.y, v4.z, 0.0f);
+  }
+}
+
+// ---- ordered sweeps of mid-size contact clusters: one warp, nodes staged in shared memory ----------------------
+// A cluster of 33 .. kMidClusterMax nodes (a column of stacked bodies, say) has little parallelism inside: its
+// entries chain through shared nodes, and the dataflow executor pays an L2 round trip per link of that chain.
+// Here one warp copies the cluster's nodes into shared memory and walks the entries in list order, every lane
+// evaluating the same entry from broadcast reads (lanes 0..3 write the four nodes back): the reference's
+// sequential order at shared-memory latency, all sweeps and their floor snaps in one launch.  Clusters are
+// independent, so which CTA takes which cluster does not matter.
+constexpr int kMidWarpsPerSm = 6;
+
+__global__ void __launch_bounds__(32) k_gs_mid_stabilize(ClusterView cv, const uint32_t* __restrict__ nMidPtr,
+                                                         float4* __restrict__ q, float4* __restrict__ prev,
+                                                         const float4* __restrict__ snap,
+                                                         const uint32_t* __restrict__ floorMult, int haveFloor,
+                                                         float thickness, uint32_t sweeps) {
+  __shared__ float4 sq[kMidClusterMax], sp[kMidClusterMax];
+  const int lane = threadIdx.x;
+  const uint32_t nMid = *nMidPtr;
+  for (uint32_t mi = blockIdx.x; mi < nMid; mi += gridDim.x) {
+    const uint32_t c = cv.midList[mi];
+    const uint32_t nb = cv.start[c], size = cv.start[c + 1] - nb;
+    for (uint32_t k = lane; k < size; k += 32) {
+      const uint32_t node = cv.nodes[nb + k];
+      sq[k] = q[node]; sp[k] = prev[node];
+    }
+    __syncwarp();
+    const uint32_t eb = cv.entStart[c], ee = cv.entStart[c + 1];
+    for (uint32_t sweep = 0; sweep < sweeps; ++sweep) {
+      for (uint32_t base = eb; base < ee; base += 32) {
+        const uint32_t myW = base + lane < ee ? cv.lanes[base + lane] : 0u;
+        const uint32_t myW2 = base + lane < ee ? (uint32_t)(cv.keys[base + lane] >> 32) : 0u;
+        const int cnt = (int)min(32u, ee - base);
+        for (int i = 0; i < cnt; ++i) {
+          const uint32_t lw = __shfl_sync(0xffffffffu, myW, i), lw2 = __shfl_sync(0xffffffffu, myW2, i);
+          const uint32_t ra = lw & 0xffffu, rb = lw >> 16, rc = lw2 & 0xffffu, rd = lw2 >> 16;
+          // PointTriangleCollisionConstraint::stabilizeCollisions (CollisionConstraint.cpp:126-162), as StabilizeOp
+          const float4 a4 = sq[ra], b4 = sq[rb], c4 = sq[rc], d4 = sq[rd];
+          V3 A = v3(a4), B = v3(b4), C = v3(c4), D = v3(d4);
+          V3 nrm = normalize(cross(C - B, D - B));
+          float nDotP = dot(nrm, A - B);
+          if (!(nDotP < thickness)) continue;
+          V3 disp = (thickness - nDotP) * nrm;
+          float wTri = b4.w + c4.w + d4.w;
+          float wSum = a4.w + wTri;
+          V3 da = disp * a4.w / wSum, dt = disp * wTri / wSum;
+          if (lane < 4) {
+            const uint32_t r = lane == 0 ? ra : lane == 1 ? rb : lane == 2 ? rc : rd;
+            const float4 cur = lane == 0 ? a4 : lane == 1 ? b4 : lane == 2 ? c4 : d4;
+            const V3 d = lane == 0 ? da : -dt;
+            const float4 pv = sp[r];
+            sq[r] = make_float4(cur.x + d.x, cur.y + d.y, cur.z + d.z, cur.w);
+            sp[r] = make_float4(pv.x + d.x, pv.y + d.y, pv.z + d.z, pv.w);
+          }
+          __syncwarp();
+        }
+      }
+      if (haveFloor) {  // Solver.cpp:379-382, after the sweep's point-triangle entries
+        for (uint32_t k = lane; k < size; k += 32) {
+          const uint32_t node = cv.nodes[nb + k];
+          if (floorMult[node] != 0u) { const float4 s4 = snap[node]; sq[k] = make_float4(s4.x, s4.y, s4.z, sq[k].w); }
+        }
+        __syncwarp();
+      }
+    }
+    for (uint32_t k = lane; k < size; k += 32) {
+      const uint32_t node = cv.nodes[nb + k];
+      q[node] = sq[k]; prev[node] = sp[k];
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(32) k_gs_mid_friction(ClusterView cv, const uint32_t* __restrict__ nMidPtr,
+                                                        const float4* __restrict__ q, float4* __restrict__ vel,
+                                                        float friction, float staticThreshold) {
+  __shared__ float4 sq[kMidClusterMax], sv[kMidClusterMax];
+  const int lane = threadIdx.x;
+  const uint32_t nMid = *nMidPtr;
+  for (uint32_t mi = blockIdx.x; mi < nMid; mi += gridDim.x) {
+    const uint32_t c = cv.midList[mi];
+    const uint32_t nb = cv.start[c], size = cv.start[c + 1] - nb;
+    for (uint32_t k = lane; k < size; k += 32) {
+      const uint32_t node = cv.nodes[nb + k];
+      sq[k] = q[node]; sv[k] = vel[node];
+    }
+    __syncwarp();
+    const uint32_t eb = cv.entStart[c], ee = cv.entStart[c + 1];
+    for (uint32_t base = eb; base < ee; base += 32) {
+      const uint32_t myW = base + lane < ee ? cv.lanes[base + lane] : 0u;
+      const uint32_t myW2 = base + lane < ee ? (uint32_t)(cv.keys[base + lane] >> 32) : 0u;
+      const int cnt = (int)min(32u, ee - base);
+      for (int i = 0; i < cnt; ++i) {
+        const uint32_t lw = __shfl_sync(0xffffffffu, myW, i), lw2 = __shfl_sync(0xffffffffu, myW2, i);
+        const uint32_t ra = lw & 0xffffu, rb = lw >> 16, rc = lw2 & 0xffffu, rd = lw2 >> 16;
+        // point-triangle friction / restitution (Solver.cpp:431-471), as FrictionOp
+        const float4 a4 = sq[ra], b4 = sq[rb], c4 = sq[rc], d4 = sq[rd];
+        const V3 va = v3(sv[ra]), vb = v3(sv[rb]), vc = v3(sv[rc]), vd = v3(sv[rd]);
+        V3 avgTri = (vb + vc + vd) / 3.0f;
+        V3 nrm = normalize(cross(v3(c4) - v3(b4), v3(d4) - v3(b4)));
+        V3 rel = va - avgTri;
+        float vDotN = dot(rel, nrm);
+        V3 perp = rel - vDotN * nrm;
+        float fr = friction;
+        if (length(perp) < staticThreshold) fr = 1.0f;
+        float triW = b4.w + c4.w + d4.w;
+        float wSum = a4.w + triW;
+        V3 dv = (-fr) * perp - (1.1f * fminf(vDotN, 0.0f)) * nrm;
+        V3 dtv = (-dv) * triW / wSum;
+        if (lane < 4) {
+          const uint32_t r = lane == 0 ? ra : lane == 1 ? rb : lane == 2 ? rc : rd;
+          const V3 v0 = lane == 0 ? va : lane == 1 ? vb : lane == 2 ? vc : vd;
+          const V3 nv = lane == 0 ? va + dv * a4.w / wSum : v0 + dtv;
+          sv[r] = f4(nv, 0.0f);
+        }
+        __syncwarp();
+      }
+    }
+    for (uint32_t k = lane; k < size; k += 32) vel[cv.nodes[nb + k]] = make_float4(sv[k].x, sv[k].y, sv[k].z, 0.0f);
+    __syncwarp();
   }
 }
 
@@ -362,13 +488,14 @@ int prepareClusterSweeps(ContactWork& w, cudaStream_t s, const ContactLists& c, 
     return -1;
   int L = 0;
   cudaMemsetAsync(w.entStart.p, 0, (size_t)(clusterBound + 2) * sizeof(uint32_t), s);
-  k_entry_keys<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, c.tri, t.clusterOf, t.slotOf, w.keys.p, w.lanes.p, w.entStart.p); ++L;
+  k_entry_keys<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, c.tri, t.clusterOf, t.rankOf, w.keys.p, w.lanes.p, w.entStart.p); ++L;
   L += launchExclusiveScan(s, w.entStart.p, clusterBound + 1, w.scanScratch.p);
   int bits = 1;
   while ((1ull << bits) <= (uint64_t)clusterBound) ++bits;
   L += launchSortPairs(s, nTri, w.keys.p, w.lanes.p, w.tmpKeys.p, w.tmpVals.p, w.sortHist.p, bits);
-  w.view = ClusterView{t.nClusters, t.start, t.nodes, w.entStart.p, w.lanes.p};
+  w.view = ClusterView{t.nClusters, t.start, t.nodes, w.entStart.p, w.lanes.p, w.keys.p, t.midList};
   w.gsClass = t.gsClass;
+  w.hostCounts = t.hostCounts; w.countsReady = t.countsReady; w.nMidDev = t.nMidDev;
   w.clusterBound = clusterBound;
   w.haveClusters = true;
   return L;
@@ -402,8 +529,15 @@ int launchStabilize(cudaStream_t s, ContactWork& w, const ContactLists& c, uint3
     // small clusters: all sweeps (and their floor snaps) in one launch
     k_gs_cluster_stabilize<<<clusterGrid(w.clusterBound), kThreads, 0, s>>>(w.view, q, prev, snap, c.floorMult, c.nFloor ? 1 : 0,
                                                                            thickness, iterations); ++L;
+    // how many mid / large clusters this substep has was copied to the host right after they were formed
+    if (w.countsReady) cudaEventSynchronize(w.countsReady);
+    const uint32_t nMid = w.hostCounts ? w.hostCounts[0] : 0u, nLarge = w.hostCounts ? w.hostCounts[1] : 1u;
+    if (nMid) {
+      k_gs_mid_stabilize<<<(int)std::min<uint32_t>(nMid, kNumSMs * kMidWarpsPerSm), 32, 0, s>>>(w.view, w.nMidDev, q, prev, snap, c.floorMult,
+                                                                                         c.nFloor ? 1 : 0, thickness, iterations); ++L;
+    }
     // large clusters: dataflow sweeps, floor snap of their nodes after each one
-    for (uint32_t it = 0; it < iterations; ++it) {
+    for (uint32_t it = 0; nLarge && it < iterations; ++it) {
       L += launchSweep(s, w, c, n, StabilizeOp{q, prev, thickness});
       if (c.nFloor) { k_floor_snap<<<gridFor(c.nFloor, kThreads), kThreads, 0, s>>>(c.nFloor, c.floorNode, snap, q, cls, 2); ++L; }
     }
@@ -418,7 +552,13 @@ int launchFriction(cudaStream_t s, ContactWork& w, const ContactLists& c, uint32
   int L = 0;
   if (c.nTri && w.haveClusters) {
     k_gs_cluster_friction<<<clusterGrid(w.clusterBound), kThreads, 0, s>>>(w.view, q, vel, friction, staticThreshold); ++L;
-    L += launchSweep(s, w, c, n, FrictionOp{q, vel, friction, staticThreshold});
+    if (w.countsReady) cudaEventSynchronize(w.countsReady);
+    const uint32_t nMid = w.hostCounts ? w.hostCounts[0] : 0u, nLarge = w.hostCounts ? w.hostCounts[1] : 1u;
+    if (nMid) {
+      k_gs_mid_friction<<<(int)std::min<uint32_t>(nMid, kNumSMs * kMidWarpsPerSm), 32, 0, s>>>(w.view, w.nMidDev, q, vel, friction,
+                                                                                        staticThreshold); ++L;
+    }
+    if (nLarge) L += launchSweep(s, w, c, n, FrictionOp{q, vel, friction, staticThreshold});
   }
   if (c.nFloor) { k_floor_friction<<<gridFor(n, kThreads), kThreads, 0, s>>>(n, c.floorMult, vel, friction, staticThreshold); ++L; }
   return L;

@@ -12,7 +12,9 @@ struct ClusterView {   // device view of this substep's contact clusters and the
   const uint32_t* start = nullptr;
   const uint32_t* nodes = nullptr;
   const uint32_t* entStart = nullptr;
-  const uint32_t* lanes = nullptr;
+  const uint32_t* lanes = nullptr;   // per entry (grouped by cluster, list order inside): rank of a | rank of b << 16
+  const uint64_t* keys = nullptr;    // per entry: (rank of c | rank of d << 16) << 32 | cluster
+  const uint32_t* midList = nullptr; // clusters of 33 .. kMidClusterMax nodes
 };
 
 struct ClusterTables {  // what reblock.cu produced for this substep
@@ -20,9 +22,13 @@ struct ClusterTables {  // what reblock.cu produced for this substep
   const uint32_t* start = nullptr;      // cluster -> first position in nodes
   const uint32_t* nodes = nullptr;      // touched nodes sorted by cluster
   const uint32_t* clusterOf = nullptr;  // node -> cluster
-  const uint32_t* slotOf = nullptr;     // node -> block * 32 + lane (lane == rank inside a small cluster)
-  const uint8_t* gsClass = nullptr;     // node -> 0 / 1 (small cluster) / 2 (large cluster)
+  const uint32_t* rankOf = nullptr;     // node -> position inside its cluster (== lane inside a small cluster)
+  const uint8_t* gsClass = nullptr;     // node -> 0 / 1 (small cluster) / 3 (mid cluster) / 2 (large cluster)
   uint32_t nTouched = 0;
+  const uint32_t* midList = nullptr;    // mid clusters (device list)
+  const uint32_t* nMidDev = nullptr;    // device count of mid clusters
+  const uint32_t* hostCounts = nullptr; // pinned: [0] mid clusters, [1] large clusters, valid once countsReady fired
+  cudaEvent_t countsReady = nullptr;
 };
 
 struct ContactWork {
@@ -32,6 +38,9 @@ struct ContactWork {
   DevBuf<uint32_t> lanes, tmpVals, entStart, sortHist, scanScratch;
   ClusterView view;
   const uint8_t* gsClass = nullptr;
+  const uint32_t* hostCounts = nullptr;
+  const uint32_t* nMidDev = nullptr;
+  cudaEvent_t countsReady = nullptr;
   uint32_t nTri = 0, sweepsUsed = 0, clusterBound = 0;
   bool haveClusters = false;
 };

@@ -330,6 +330,50 @@ __global__ void __launch_bounds__(kThreads) k_uniq_gather(const uint32_t* __rest
   uW[u] = 10000.0f * (float)(start[u + 1] - j);  // copies * PointTriangleCollisionConstraint::w (exact in fp32)
 }
 
+// ---- 7. the collision matrix in streamable form ----------------------------------------------------
+// Off-diagonal entries per node (to be scanned): a contact contributes three to its point row and one to each
+// corner row (A^T A = [[3,-1,-1,-1],[-1,1,0,0],[-1,0,1,0],[-1,0,0,1]], CollisionConstraint.cpp:74-83).
+__global__ void __launch_bounds__(kThreads) k_ccsr_count(uint32_t n, const uint32_t* __restrict__ uIncPtr,
+                                                         const uint32_t* __restrict__ uInc, uint32_t* __restrict__ cPtr) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  uint32_t cnt = 0;
+  if (i < n)
+    for (uint32_t k = uIncPtr[i]; k < uIncPtr[i + 1]; ++k) cnt += (uInc[k] & 3u) == 0u ? 3u : 1u;
+  cPtr[i] = cnt;
+}
+
+// Entries in the node's incidence order (contacts ascending), diagonal = contact terms then the floor weight.
+__global__ void __launch_bounds__(kThreads) k_ccsr_fill(uint32_t n, const uint32_t* __restrict__ uIncPtr,
+                                                        const uint32_t* __restrict__ uInc, const uint4* __restrict__ uTri,
+                                                        const float* __restrict__ uW, const uint32_t* __restrict__ cPtr,
+                                                        const float* __restrict__ floorW, int* __restrict__ cCol,
+                                                        float* __restrict__ cVal, float* __restrict__ cDiag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float diag = 0.0f;
+  if (uIncPtr) {
+    uint32_t o = cPtr[i];
+    for (uint32_t k = uIncPtr[i]; k < uIncPtr[i + 1]; ++k) {
+      const uint32_t v = uInc[k];
+      const uint4 e = uTri[v >> 2];
+      const float wgt = uW[v >> 2];
+      if ((v & 3u) == 0u) {
+        diag += 3.0f * wgt;
+        cCol[o] = (int)e.y; cCol[o + 1] = (int)e.z; cCol[o + 2] = (int)e.w;
+        cVal[o] = -wgt; cVal[o + 1] = -wgt; cVal[o + 2] = -wgt;
+        o += 3;
+      } else {
+        diag += wgt;
+        cCol[o] = (int)e.x; cVal[o] = -wgt;
+        ++o;
+      }
+    }
+  }
+  if (floorW) diag += floorW[i];
+  cDiag[i] = diag;
+}
+
 // ticket of every (entry, slot): its position in the node's ordered incidence list.  The ordered
 // Gauss-Seidel sweeps (contact.cu) run an entry once each of its four nodes has seen `ticket` earlier entries.
 __global__ void __launch_bounds__(kThreads) k_inc_tickets(uint64_t nInc, const uint64_t* __restrict__ sortedNode,
@@ -506,6 +550,19 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
     if (nFloor) { k_floor_mult<<<gridFor(nFloor, kThreads), kThreads, 0, s>>>(nFloor, w.floorList.p, w.floorMult.p); ++L; }
     k_floor_weight<<<gridFor(n, kThreads), kThreads, 0, s>>>(n, w.floorMult.p, w.floorW.p); ++L;
     w.floorDirty = nFloor != 0;
+  }
+  if (nHit || nFloor) {
+    DCHECK(w.cDiag.reserve(n + 1));
+    const uint32_t nU = nHit ? w.nUnique : 0u;
+    if (nU) {
+      DCHECK(w.cPtr.reserve(n + 2)); DCHECK(w.cCol.reserve(6ull * nU + 4)); DCHECK(w.cVal.reserve(6ull * nU + 4));
+      k_ccsr_count<<<gridFor(n + 1, kThreads), kThreads, 0, s>>>(n, w.uIncPtr.p, w.uInc.p, w.cPtr.p); ++L;
+      L += launchExclusiveScan(s, w.cPtr.p, n + 1, w.scanScratch.p);
+    }
+    k_ccsr_fill<<<gridFor(n, kThreads), kThreads, 0, s>>>(n, nU ? w.uIncPtr.p : nullptr, w.uInc.p, w.uTri.p, w.uW.p, w.cPtr.p,
+                                                         nFloor ? w.floorW.p : nullptr, w.cCol.p, w.cVal.p, w.cDiag.p); ++L;
+    out.cDiag = w.cDiag.p;
+    if (nU) { out.cPtr = (int*)w.cPtr.p; out.cCol = w.cCol.p; out.cVal = w.cVal.p; }
   }
   if (launches) *launches += L;
   return 0;

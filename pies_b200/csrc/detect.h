@@ -35,6 +35,8 @@ struct DetectWork {
   uint32_t nUnique = 0, nTouched = 0;
   DevBuf<uint32_t> floorList, incPtr, floorMult;
   DevBuf<float> floorW;
+  // contact matrix C_t of the substep as CSR (off-diagonals) + per-node diagonal (contacts + floor), see k_ccsr_fill
+  DevBuf<uint32_t> cPtr; DevBuf<int> cCol; DevBuf<float> cVal, cDiag;
   int* host = nullptr;   // pinned, 16 ints
   uint64_t nPairs = 0, scanCap = 0;
   uint32_t nCells = 0;

@@ -238,7 +238,7 @@ struct PhaseTimer {
   std::vector<cudaEvent_t>& pool;
   std::vector<std::pair<int, size_t>> spans;  // (phase, index of the start event)
   size_t used = 0;
-  explicit PhaseTimer(PiesB200Solver* s_, std::vector<cudaEvent_t>& pool_) : s(s_), on(s_->tune.reserved != 0), pool(pool_) {}
+  explicit PhaseTimer(PiesB200Solver* s_, std::vector<cudaEvent_t>& pool_) : s(s_), on((s_->tune.reserved & 1u) != 0), pool(pool_) {}
   cudaEvent_t next() {
     if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
     return pool[used++];
@@ -376,6 +376,7 @@ int pdSubstepBegin(PiesB200Solver* s) {
     s->blocks = new BlockWork();
     PIES_CHECK(s, cudaMallocHost(&s->blocks->host, 4 * sizeof(uint32_t)));
   }
+  s->blocks->midClusterMax = (s->tune.reserved & 2u) ? 0u : kMidClusterMax;
   {
     PdViews v = pdViews(s);
     int LB = 0;
@@ -388,7 +389,8 @@ int pdSubstepBegin(PiesB200Solver* s) {
     s->blocks->cur.nBlocks = v.pw.nBlocks; s->blocks->cur.nBlocksDev = v.pw.nBlocksDev;
     s->launches += LB;
     const BlockWork& bw = *s->blocks;
-    ClusterTables ct{bw.heads.p + bw.nTouched, bw.start.p, bw.vals.p, bw.clusterOf.p, bw.slotOf.p, bw.gsClass.p, bw.nTouched};
+    ClusterTables ct{bw.heads.p + bw.nTouched, bw.start.p, bw.vals.p, bw.clusterOf.p, bw.rankOf.p, bw.gsClass.p, bw.nTouched,
+                     bw.midList.p, bw.midCount.p, bw.host + 1, bw.countsReady};
     int LC = s->contact ? prepareClusterSweeps(*s->contact, st, c->lists, ct) : 0;
     if (LC < 0) { pdAbort(s); return failCuda(s, cudaErrorMemoryAllocation, "prepareClusterSweeps", __LINE__); }
     s->launches += LC;
@@ -481,6 +483,11 @@ int pdSubstepEnd(PiesB200Solver* s) {
     s->launches += launchStabilize(st, *s->contact, lists, n, s->q.p, s->prev.p, s->snap.p, o.collisionThickness,
                                    o.collisionStabilizationIterations);
   timer.end();
+  s->stats.reserved = 0;
+  if (s->blocks && s->blocks->countsReady && lists.nTri) {
+    cudaEventSynchronize(s->blocks->countsReady);
+    s->stats.reserved = std::min(s->blocks->host[1], 65535u) | (std::min(s->blocks->host[2], 65535u) << 16);
+  }
   timer.begin(kPhOther);
   s->launches += launchVelocityUpdate(st, n, s->q.p, s->prev.p, s->vel.p, h, o.damping, o.gravity);
   timer.end();

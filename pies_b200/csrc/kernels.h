@@ -52,6 +52,11 @@ struct ContactLists {
   // node -> incident distinct contacts, CSR (value = 4 * contact + slot), contacts ascending
   int* incPtr = nullptr; uint32_t* inc = nullptr;
   float* floorW = nullptr;     // per node: sum of floor-contact weights (multiplicity * 1e4)
+  // The same collision matrix C_t in streamable form (what the CG mat-vec reads): off-diagonal entries as CSR
+  // (a point row holds -w for its three triangle corners, a corner row -w for the point; entries in incidence
+  // order) and the per-node diagonal sum (3 w / w per contact + the floor weight).  cDiag is valid when
+  // nTri || nFloor, the CSR when nUnique.
+  int* cPtr = nullptr; int* cCol = nullptr; float* cVal = nullptr; float* cDiag = nullptr;
   uint32_t* floorMult = nullptr;
   // ordered Gauss-Seidel sweeps: ticket[e] = position of entry e in each of its four nodes' incidence
   // lists; nodeDone[v] = entries touching v already executed in the current sweep

@@ -259,19 +259,64 @@ __global__ void k_pcg_check(float* __restrict__ scalars, int* __restrict__ flag,
 // re-evaluates the convergence test of the previous iteration from the same partials, so they all agree.
 // The solve is for the correction delta with an fp64 start residual, so only a few digits are asked of
 // this recurrence.
-constexpr int kSpmvTile = 2048;  // == HostSystem::kBatchNnz: products of one row batch, 24 KB of shared memory
+//
+// A = S + C_t is streamed as two CSR segments per row batch: the batch's slice of S (built once per topology) and
+// its slice of the substep's collision matrix (detect.cu, k_ccsr_fill), concatenated into one virtual entry range.
+// The (col, val) pairs of a CTA's NEXT batch are staged into shared memory with cp.async while the current batch
+// is processed (double buffer), so the only exposed latency per batch is the gather of z.
+constexpr int kSpmvTile = 2048;  // == HostSystem::kBatchNnz: entries of one row batch per pass
 
-__global__ void __launch_bounds__(kThreads) k_pcg_spmv(CsrMatrix A, ContactLists c, PcgWork w, float* __restrict__ partials,
-                                                       int parity, int first, float tol2) {
+struct SpmvBatch { uint32_t r0, r1; int e0, nA, f0, total; };
+
+__device__ __forceinline__ SpmvBatch loadBatch(const CsrMatrix& A, const int* __restrict__ cPtr, uint32_t b) {
+  SpmvBatch m;
+  m.r0 = A.rowBatch[b]; m.r1 = A.rowBatch[b + 1];
+  m.e0 = A.rowPtr[m.r0]; m.nA = A.rowPtr[m.r1] - m.e0;
+  m.f0 = 0; m.total = m.nA;
+  if (cPtr) { m.f0 = cPtr[m.r0]; m.total += cPtr[m.r1] - m.f0; }
+  return m;
+}
+
+__device__ __forceinline__ void cpAsync4(void* smemDst, const void* gmemSrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc) : "memory");
+}
+
+// virtual entries [cs, min(total, cs + tile)) of batch m -> (sCol, sVal), one commit group
+__device__ __forceinline__ void stageEntries(int* sCol, float* sVal, const CsrMatrix& A, const ContactLists& c,
+                                             const SpmvBatch& m, int cs) {
+  const int ce = min(m.total, cs + kSpmvTile);
+  for (int v = cs + (int)threadIdx.x; v < ce; v += kThreads) {
+    const int* pc; const float* pv;
+    if (v < m.nA) { pc = A.col + m.e0 + v; pv = A.val + m.e0 + v; }
+    else { pc = c.cCol + m.f0 + (v - m.nA); pv = c.cVal + m.f0 + (v - m.nA); }
+    cpAsync4(sCol + (v - cs), pc);
+    cpAsync4(sVal + (v - cs), pv);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 4) k_pcg_spmv(CsrMatrix A, ContactLists c, PcgWork w, float* __restrict__ partials,
+                                                          int parity, int first, float tol2) {
   __shared__ float smem[128];
-  __shared__ float sProdX[kSpmvTile], sProdY[kSpmvTile], sProdZ[kSpmvTile];
+  __shared__ __align__(16) int sCol[2][kSpmvTile];    // staged columns; overwritten in place by the y-products
+  __shared__ __align__(16) float sVal[2][kSpmvTile];  // staged values; overwritten in place by the x-products
+  __shared__ float sZ[kSpmvTile];                     // z-products
   if (ctaConverged(w.flag)) return;
+  // the first batch's entries do not depend on the scalars: start their copy before reading those
+  const uint32_t nB = A.nBatches;
+  uint32_t b = blockIdx.x;
+  SpmvBatch cur{}, nxt{};
+  if (b < nB) { cur = loadBatch(A, c.cPtr, b); stageEntries(sCol[0], sVal[0], A, c, cur, 0); }
+  if (b + gridDim.x < nB) nxt = loadBatch(A, c.cPtr, b + gridDim.x);
   float rzNew[3], rzOld[3], rr[3], bb[3], beta[3] = {0.0f, 0.0f, 0.0f};
   const int prevSet = parity ? kSet0 : kSet1, olderSet = parity ? kSet1 : kSet0;
   readSums3(w.scalars, prevSet, rzNew);  // r.z and r.r written by the previous update (or start)
   readSums3(w.scalars, prevSet + 3, rr);
   readSums3(w.scalars, kBB, bb);
-  if (rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2]) return;  // the update latches the flag
+  if (rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2]) {  // the update latches the flag
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    return;
+  }
   if (!first) {
     readSums3(w.scalars, olderSet, rzOld);
 #pragma unroll
@@ -279,70 +324,73 @@ __global__ void __launch_bounds__(kThreads) k_pcg_spmv(CsrMatrix A, ContactLists
   }
   const float4* __restrict__ z = w.z;
   float pap[3] = {0.0f, 0.0f, 0.0f};
-  for (uint32_t b = blockIdx.x; b < A.nBatches; b += gridDim.x) {
-    const uint32_t r0 = A.rowBatch[b], r1 = A.rowBatch[b + 1];
-    const int e0 = A.rowPtr[r0], e1 = A.rowPtr[r1];
-    const uint32_t row = r0 + threadIdx.x;
-    const bool haveRow = row < r1;
-    int rb = 0, re = 0;
+  int buf = 0;
+  for (; b < nB; b += gridDim.x) {
+    // next batch: its entries go to the other buffer now, the batch after it is described for the next round
+    const bool pre = b + gridDim.x < nB;
+    if (pre) stageEntries(sCol[buf ^ 1], sVal[buf ^ 1], A, c, nxt, 0);
+    SpmvBatch nn{};
+    if (b + 2u * gridDim.x < nB) nn = loadBatch(A, c.cPtr, b + 2u * gridDim.x);
+    const uint32_t row = cur.r0 + threadIdx.x;
+    const bool haveRow = row < cur.r1;
+    int rb = 0, re = 0, cb = 0, cf = 0;
+    float dg = 0.0f;
     float4 zi = make_float4(0.0f, 0.0f, 0.0f, 0.0f), po = zi, apo = zi;
     if (haveRow) {
-      rb = A.rowPtr[row]; re = A.rowPtr[row + 1];
+      rb = A.rowPtr[row] - cur.e0; re = A.rowPtr[row + 1] - cur.e0;
+      if (c.cPtr) { cb = cur.nA + c.cPtr[row] - cur.f0; cf = cur.nA + c.cPtr[row + 1] - cur.f0; }
+      if (c.cDiag) dg = c.cDiag[row];
       zi = z[row];
       if (!first) { po = w.p[row]; apo = w.ap[row]; }
     }
+    if (pre) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
     V3 y = v3(0.0f, 0.0f, 0.0f);
-    for (int cs = e0; cs < e1; cs += kSpmvTile) {  // one pass unless a single row overflows the tile
-      const int ce = min(e1, cs + kSpmvTile);
-      // stream: coalesced (col, val), gather z, park the products
-      for (int e = cs + (int)threadIdx.x; e < ce; e += 4 * kThreads) {
-        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-        const bool h1 = e + kThreads < ce, h2 = e + 2 * kThreads < ce, h3 = e + 3 * kThreads < ce;
-        c0 = __ldcs(A.col + e); a0 = __ldcs(A.val + e);
-        if (h1) { c1 = __ldcs(A.col + e + kThreads); a1 = __ldcs(A.val + e + kThreads); }
-        if (h2) { c2 = __ldcs(A.col + e + 2 * kThreads); a2 = __ldcs(A.val + e + 2 * kThreads); }
-        if (h3) { c3 = __ldcs(A.col + e + 3 * kThreads); a3 = __ldcs(A.val + e + 3 * kThreads); }
-        float4 x0 = __ldg(z + c0), x1 = __ldg(z + c1), x2 = __ldg(z + c2), x3 = __ldg(z + c3);
-        int o = e - cs;
-        sProdX[o] = a0 * x0.x; sProdY[o] = a0 * x0.y; sProdZ[o] = a0 * x0.z;
-        if (h1) { o += kThreads; sProdX[o] = a1 * x1.x; sProdY[o] = a1 * x1.y; sProdZ[o] = a1 * x1.z; }
-        if (h2) { o += kThreads; sProdX[o] = a2 * x2.x; sProdY[o] = a2 * x2.y; sProdZ[o] = a2 * x2.z; }
-        if (h3) { o += kThreads; sProdX[o] = a3 * x3.x; sProdY[o] = a3 * x3.y; sProdZ[o] = a3 * x3.z; }
+    for (int cs = 0; cs < cur.total; cs += kSpmvTile) {  // one pass unless the batch overflows the tile
+      if (cs > 0) {
+        stageEntries(sCol[buf], sVal[buf], A, c, cur, cs);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+      }
+      const int cnt = min(cur.total - cs, kSpmvTile);
+      int* pcol = sCol[buf];
+      float* px = sVal[buf];
+      float* py = reinterpret_cast<float*>(sCol[buf]);
+      // gather z and park the products (four independent gathers in flight per thread)
+      for (int o = (int)threadIdx.x; o < cnt; o += 4 * kThreads) {
+        const bool h1 = o + kThreads < cnt, h2 = o + 2 * kThreads < cnt, h3 = o + 3 * kThreads < cnt;
+        int c0 = pcol[o], c1 = 0, c2 = 0, c3 = 0;
+        float a0 = px[o], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        if (h1) { c1 = pcol[o + kThreads]; a1 = px[o + kThreads]; }
+        if (h2) { c2 = pcol[o + 2 * kThreads]; a2 = px[o + 2 * kThreads]; }
+        if (h3) { c3 = pcol[o + 3 * kThreads]; a3 = px[o + 3 * kThreads]; }
+        const float4 x0 = __ldg(z + c0), x1 = __ldg(z + c1), x2 = __ldg(z + c2), x3 = __ldg(z + c3);
+        px[o] = a0 * x0.x; py[o] = a0 * x0.y; sZ[o] = a0 * x0.z;
+        if (h1) { px[o + kThreads] = a1 * x1.x; py[o + kThreads] = a1 * x1.y; sZ[o + kThreads] = a1 * x1.z; }
+        if (h2) { px[o + 2 * kThreads] = a2 * x2.x; py[o + 2 * kThreads] = a2 * x2.y; sZ[o + 2 * kThreads] = a2 * x2.z; }
+        if (h3) { px[o + 3 * kThreads] = a3 * x3.x; py[o + 3 * kThreads] = a3 * x3.y; sZ[o + 3 * kThreads] = a3 * x3.z; }
       }
       __syncthreads();
-      if (haveRow) {  // per-row sum in CSR order
-        int kb = max(rb, cs), ke = min(re, ce);
-        for (int k = kb; k < ke; ++k) { y.x += sProdX[k - cs]; y.y += sProdY[k - cs]; y.z += sProdZ[k - cs]; }
+      if (haveRow) {  // per-row sums in CSR order: the S segment, then the collision segment
+        const int ce = cs + cnt;
+        for (int k = max(rb, cs); k < min(re, ce); ++k) { y.x += px[k - cs]; y.y += py[k - cs]; y.z += sZ[k - cs]; }
+        for (int k = max(cb, cs); k < min(cf, ce); ++k) { y.x += px[k - cs]; y.y += py[k - cs]; y.z += sZ[k - cs]; }
       }
       __syncthreads();
     }
-    if (!haveRow) continue;
-    const uint32_t i = row;
-    if (c.nFloor) {
-      float fw = c.floorW[i];
-      y.x += fw * zi.x; y.y += fw * zi.y; y.z += fw * zi.z;
-    }
-    if (c.nTri) {
-      int cb = c.incPtr[i], ce2 = c.incPtr[i + 1];
-      for (int kk = cb; kk < ce2; ++kk) {
-        uint32_t v = c.inc[kk];
-        uint4 e = __ldg(c.uTri + (v >> 2));
-        float wgt = __ldg(c.uW + (v >> 2));
-        V3 t;
-        if ((v & 3u) == 0u) t = 3.0f * v3(zi) - v3(__ldg(z + e.y)) - v3(__ldg(z + e.z)) - v3(__ldg(z + e.w));
-        else t = v3(zi) - v3(__ldg(z + e.x));
-        y += wgt * t;
+    if (haveRow) {
+      y.x = fmaf(dg, zi.x, y.x); y.y = fmaf(dg, zi.y, y.y); y.z = fmaf(dg, zi.z, y.z);
+      V3 pi = v3(zi);
+      if (!first) {
+        pi = v3(fmaf(beta[0], po.x, zi.x), fmaf(beta[1], po.y, zi.y), fmaf(beta[2], po.z, zi.z));
+        y = v3(fmaf(beta[0], apo.x, y.x), fmaf(beta[1], apo.y, y.y), fmaf(beta[2], apo.z, y.z));
       }
+      w.p[row] = f4(pi, 0.0f);
+      w.ap[row] = f4(y, 0.0f);
+      pap[0] += pi.x * y.x; pap[1] += pi.y * y.y; pap[2] += pi.z * y.z;
     }
-    V3 pi = v3(zi);
-    if (!first) {
-      pi = v3(fmaf(beta[0], po.x, zi.x), fmaf(beta[1], po.y, zi.y), fmaf(beta[2], po.z, zi.z));
-      y = v3(fmaf(beta[0], apo.x, y.x), fmaf(beta[1], apo.y, y.y), fmaf(beta[2], apo.z, y.z));
-    }
-    w.p[i] = f4(pi, 0.0f);
-    w.ap[i] = f4(y, 0.0f);
-    pap[0] += pi.x * y.x; pap[1] += pi.y * y.y; pap[2] += pi.z * y.z;
+    cur = nxt; nxt = nn; buf ^= 1;
   }
   blockSum<3>(pap, smem);
   if (threadIdx.x == 0) {

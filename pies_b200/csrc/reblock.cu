@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(kThreads) k_assign_dynamic(uint32_t nT, uint32
                                                              const uint32_t* __restrict__ nodes, int* __restrict__ blockNodes,
                                                              uint32_t* __restrict__ slotOf, uint32_t* __restrict__ blockCount,
                                                              uint32_t* __restrict__ clusterOf, uint8_t* __restrict__ gsClass,
+                                                             uint32_t* __restrict__ rankOf, uint32_t* __restrict__ midList,
+                                                             uint32_t* __restrict__ midCount, uint32_t midMax,
                                                              uint32_t* __restrict__ nBlocksOut) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) *nBlocksOut = nStatic + (nT ? blkOff[*nClustersPtr] : 0u);
@@ -133,7 +135,14 @@ __global__ void __launch_bounds__(kThreads) k_assign_dynamic(uint32_t nT, uint32
   slotOf[nodes[j]] = slot;
   const uint32_t size = start[c + 1] - start[c];
   clusterOf[nodes[j]] = c;
-  gsClass[nodes[j]] = size <= 32u ? 1 : 2;  // 1: the whole cluster is one block (in-warp ordered sweeps), 2: dataflow sweeps
+  rankOf[nodes[j]] = rank;
+  // 1: the whole cluster is one block (in-warp ordered sweeps from registers), 3: one warp sweeps it from shared
+  // memory, 2: dataflow sweeps
+  gsClass[nodes[j]] = size <= 32u ? 1 : (size <= midMax ? 3 : 2);
+  if (rank == 0u && size > 32u) {
+    if (size <= midMax) midList[atomicAdd(midCount, 1u)] = c;  // order irrelevant: clusters are independent
+    else atomicAdd(midCount + 1, 1u);
+  }
   if ((rank & 31u) == 0u) blockCount[blk] = min(32u, size - rank);
 }
 
@@ -294,7 +303,10 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   RCHECK(w.nBlocksDev.reserve(4));
   RCHECK(w.flag.reserve(n + 2)); RCHECK(w.parent.reserve(n + 1)); RCHECK(w.slotOf.reserve(n + 1));
   RCHECK(w.dirty.reserve(nStatic + 1));
-  RCHECK(w.clusterOf.reserve(n + 1)); RCHECK(w.gsClass.reserve(n + 1));
+  RCHECK(w.clusterOf.reserve(n + 1)); RCHECK(w.gsClass.reserve(n + 1)); RCHECK(w.rankOf.reserve(n + 1));
+  RCHECK(w.midCount.reserve(4));
+  RCHECK(cudaMemsetAsync(w.midCount.p, 0, 4 * sizeof(uint32_t), s));
+  if (!w.countsReady) RCHECK(cudaEventCreateWithFlags(&w.countsReady, cudaEventDisableTiming));
   RCHECK(w.scanScratch.reserve(scanScratchElems(std::max<uint64_t>(n + 2, w.scanCap))));
   RCHECK(cudaMemsetAsync(w.gsClass.p, 0, n + 1, s));
   uint32_t nT = 0;
@@ -319,6 +331,7 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   if (nT) {
     RCHECK(w.keys.reserve(nT)); RCHECK(w.tmpKeys.reserve(nT)); RCHECK(w.vals.reserve(nT)); RCHECK(w.tmpVals.reserve(nT));
     RCHECK(w.heads.reserve(nT + 2)); RCHECK(w.start.reserve(nT + 2)); RCHECK(w.blkOff.reserve(nT + 2));
+    RCHECK(w.midList.reserve(nT / 33 + 2));
     RCHECK(w.sortHist.reserve(sortHistBytes(nT) / 4 + 4));
     w.scanCap = std::max<uint64_t>(w.scanCap, (uint64_t)nT + 2);
     RCHECK(w.scanScratch.reserve(scanScratchElems(std::max<uint64_t>(n + 2, w.scanCap))));
@@ -340,7 +353,10 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   k_assign_dynamic<<<gridFor(std::max(nT, 1u), kThreads), kThreads, 0, s>>>(nT, nStatic, w.heads.p + nT, w.heads.p, w.start.p,
                                                                            w.blkOff.p, w.vals.p, w.blockNodes.p, w.slotOf.p,
                                                                            w.blockCount.p, w.clusterOf.p, w.gsClass.p,
+                                                                           w.rankOf.p, w.midList.p, w.midCount.p, w.midClusterMax,
                                                                            w.nBlocksDev.p); ++L;
+  RCHECK(cudaMemcpyAsync(w.host + 1, w.midCount.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  RCHECK(cudaEventRecord(w.countsReady, s));
   k_block_sizes<<<gridFor(bound + 1, kThreads), kThreads, 0, s>>>(bound, w.nBlocksDev.p, w.blockCount.p, w.blockOff.p); ++L;
   L += launchExclusiveScan(s, w.blockOff.p, bound + 1, w.scanScratch.p);
   k_block_factor<<<gridFor(bound, kFactorWarps), kFactorWarps * 32, 0, s>>>(nStatic, w.nBlocksDev.p, S, c, w.blockNodes.p,

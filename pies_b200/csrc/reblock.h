@@ -7,6 +7,8 @@
 
 namespace pies {
 
+constexpr uint32_t kMidClusterMax = 1024;  // nodes of a contact cluster one warp can stage in shared memory (2 x 16 B each)
+
 struct BlockWork {
   DevBuf<int> blockNodes;        // (static + dynamic blocks) * 32, members packed to the front, -1 padded
   DevBuf<float> blockInv;        // packed lower triangle per block (m = members), at blockOff[b]
@@ -15,8 +17,15 @@ struct BlockWork {
   DevBuf<uint32_t> slotOf;       // node -> block * 32 + lane
   DevBuf<uint32_t> flag, parent, vals, tmpVals, heads, start, blkOff, sortHist, scanScratch, nBlocksDev;
   DevBuf<uint64_t> keys, tmpKeys;
-  DevBuf<uint8_t> dirty, gsClass;  // gsClass[node]: 0 not in a contact, 1 small cluster (<= 32 nodes), 2 large cluster
+  DevBuf<uint8_t> dirty, gsClass;  // gsClass[node]: 0 not in a contact, 1 small cluster (<= 32 nodes), 3 mid cluster (<= kMidClusterMax), 2 large cluster
   DevBuf<uint32_t> clusterOf;      // node -> contact cluster (touched nodes only)
+  DevBuf<uint32_t> rankOf;         // node -> position inside its cluster (touched nodes only)
+  // clusters of 33 .. kMidClusterMax nodes (swept by one warp from shared memory, contact.cu): list + counters
+  // [0] = mid clusters, [1] = clusters larger than that (dataflow sweeps); host copy in host[1..2] once countsReady fired
+  DevBuf<uint32_t> midList, midCount;
+  cudaEvent_t countsReady = nullptr;
+  ~BlockWork() { if (countsReady) cudaEventDestroy(countsReady); }
+  uint32_t midClusterMax = kMidClusterMax;  // tuning: 0 sends every cluster above 32 nodes to the dataflow sweeps
   uint32_t* host = nullptr;      // pinned, 4 words
   uint32_t nBlocksBound = 0, nTouched = 0;
   // contact clusters of this substep: nodes sorted by cluster in vals[start[c] .. start[c+1]), count at heads[nTouched]

@@ -199,7 +199,7 @@ class Solver:
         except Exception:
             pass
 
-    def setTuning(self, pcgTolerance=None, pcgMaxIterations=None, pcgCheckEvery=None, profilePhases=None):
+    def setTuning(self, pcgTolerance=None, pcgMaxIterations=None, pcgCheckEvery=None, profilePhases=None, dataflowSweepsOnly=None):
         t = Tuning()
         lib().pies_b200_default_tuning(C.byref(t))
         cur = getattr(self, "_tuning", None)
@@ -208,7 +208,8 @@ class Solver:
         if pcgTolerance is not None: t.pcgTolerance = pcgTolerance
         if pcgMaxIterations is not None: t.pcgMaxIterations = pcgMaxIterations
         if pcgCheckEvery is not None: t.pcgCheckEvery = pcgCheckEvery
-        if profilePhases is not None: t.reserved = int(bool(profilePhases))
+        if profilePhases is not None: t.reserved = (t.reserved & ~1) | int(bool(profilePhases))
+        if dataflowSweepsOnly is not None: t.reserved = (t.reserved & ~2) | (2 if dataflowSweepsOnly else 0)
         self._tuning = t
         self._ck(lib().pies_b200_set_tuning(self.h, C.byref(t)))
 

@@ -171,6 +171,30 @@ def test_run_to_run_bit_stable(pb):
     assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all() and (out[0][2] == out[1][2]).all()
 
 
+def test_ordered_sweep_executors_agree(pb):
+    """The ordered stabilisation / friction sweeps have three executors (registers for clusters <= 32 nodes, one warp
+    from shared memory up to 1024 nodes, ticketed dataflow above): all replay the reference's sequential order per
+    node, so forcing every cluster above 32 nodes through the dataflow executor must give the same trajectory (same
+    operations in the same order; only fp contraction may differ between the kernels)."""
+    from pies_b200 import scenes
+    out = []
+    for dataflow_only in (False, True):
+        s = pb.Solver(**scenes.S3_OPTIONS)
+        scenes.build_s3(s, bodies=16, nx=2, nz=2)
+        s.setTuning(dataflowSweepsOnly=dataflow_only)
+        for _ in range(46):
+            s.tick()
+        st = s.stats()
+        assert st.triCollisions > 100
+        mid, large = st.reserved & 0xffff, st.reserved >> 16
+        assert (mid == 0 and large > 0) if dataflow_only else (mid > 0 and large == 0), (mid, large)
+        out.append((s.positions.copy(), s.velocities.copy(), s.triCollisions().copy()))
+    assert (out[0][2] == out[1][2]).all()
+    diag = bbox_diag(out[0][0])
+    assert np.abs(out[0][0] - out[1][0]).max() <= 1e-6 * diag
+    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-3
+
+
 def test_free_fall_matches_closed_form(pb):
     """Size-independent property: before any contact a stack in free fall follows
     v_{n+1} = (1-d) v_n - h g exactly (gravity enters through the velocity update only)."""
