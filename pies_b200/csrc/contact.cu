@@ -194,18 +194,24 @@ __global__ void __launch_bounds__(kGsThreads) k_gs_dataflow(const uint4* __restr
 // with anything outside it during the sweeps, so one warp keeps its nodes in registers (lane = node),
 // walks the cluster's entries in list order and exchanges operands with shuffles: the sequential order of
 // the reference at register latency, all four stabilisation sweeps in one launch.
+// Sorted-entry records: the sort only looks at the low kClusterBits of the key, so the rest travels as payload:
+//   key = (rank a | rank b << 10 | rank c << 20 | rank d << 30) << kClusterBits | cluster,   value = list index
+// (rank = position of the node inside its cluster; 10 bits cover the clusters the in-warp / in-CTA executors take,
+// larger clusters never read them).
+constexpr int kClusterBits = 24;
+
 __global__ void __launch_bounds__(kThreads) k_entry_keys(uint32_t nTri, const uint4* __restrict__ entries,
                                                          const uint32_t* __restrict__ clusterOf,
                                                          const uint32_t* __restrict__ rankOf, uint64_t* __restrict__ keys,
-                                                         uint32_t* __restrict__ lanes, uint32_t* __restrict__ entCount) {
+                                                         uint32_t* __restrict__ entryOf, uint32_t* __restrict__ entCount) {
   uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nTri) return;
   uint4 id = entries[e];
   uint32_t c = clusterOf[id.x];
-  // The sort only looks at the cluster bits, so the high word of the key travels as a second payload:
-  // ranks of the four nodes inside their cluster, 16 bits each (unused above 65535 nodes: dataflow sweeps).
-  keys[e] = ((uint64_t)((rankOf[id.z] & 0xffffu) | (rankOf[id.w] << 16)) << 32) | c;
-  lanes[e] = (rankOf[id.x] & 0xffffu) | (rankOf[id.y] << 16);
+  uint64_t ranks = (uint64_t)(rankOf[id.x] & 1023u) | ((uint64_t)(rankOf[id.y] & 1023u) << 10) |
+                   ((uint64_t)(rankOf[id.z] & 1023u) << 20) | ((uint64_t)(rankOf[id.w] & 1023u) << 30);
+  keys[e] = (ranks << kClusterBits) | c;
+  entryOf[e] = e;
   atomicAdd(entCount + c, 1u);
 }
 
@@ -235,12 +241,13 @@ __global__ void __launch_bounds__(kThreads) k_gs_cluster_stabilize(ClusterView c
     const uint32_t eb = cv.entStart[c], ee = cv.entStart[c + 1];
     for (uint32_t sweep = 0; sweep < sweeps; ++sweep) {
       for (uint32_t base = eb; base < ee; base += 32) {
-        const uint32_t myW = base + lane < ee ? cv.lanes[base + lane] : 0u;
-        const uint32_t myW2 = base + lane < ee ? (uint32_t)(cv.keys[base + lane] >> 32) : 0u;
+        const uint64_t myK = base + lane < ee ? cv.keys[base + lane] >> kClusterBits : 0ull;
+        const uint32_t myW = (uint32_t)(myK & 31u) | ((uint32_t)(myK >> 10) & 31u) << 8 | ((uint32_t)(myK >> 20) & 31u) << 16 |
+                             ((uint32_t)(myK >> 30) & 31u) << 24;
         const int cnt = (int)min(32u, ee - base);
         for (int i = 0; i < cnt; ++i) {
-          const uint32_t lw = __shfl_sync(0xffffffffu, myW, i), lw2 = __shfl_sync(0xffffffffu, myW2, i);
-          const int la = lw & 31u, lb = (lw >> 16) & 31u, lc = lw2 & 31u, ld = (lw2 >> 16) & 31u;
+          const uint32_t lw = __shfl_sync(0xffffffffu, myW, i);
+          const int la = lw & 31u, lb = (lw >> 8) & 31u, lc = (lw >> 16) & 31u, ld = (lw >> 24) & 31u;
           // PointTriangleCollisionConstraint::stabilizeCollisions (CollisionConstraint.cpp:126-162), as StabilizeOp
           V3 A = shflV3(q4, la), B = shflV3(q4, lb), C = shflV3(q4, lc), D = shflV3(q4, ld);
           float wa = __shfl_sync(0xffffffffu, q4.w, la), wb = __shfl_sync(0xffffffffu, q4.w, lb),
@@ -280,12 +287,13 @@ __global__ void __launch_bounds__(kThreads) k_gs_cluster_friction(ClusterView cv
     if (have) { q4 = q[node]; v4 = vel[node]; }
     const uint32_t eb = cv.entStart[c], ee = cv.entStart[c + 1];
     for (uint32_t base = eb; base < ee; base += 32) {
-      const uint32_t myW = base + lane < ee ? cv.lanes[base + lane] : 0u;
-      const uint32_t myW2 = base + lane < ee ? (uint32_t)(cv.keys[base + lane] >> 32) : 0u;
+      const uint64_t myK = base + lane < ee ? cv.keys[base + lane] >> kClusterBits : 0ull;
+      const uint32_t myW = (uint32_t)(myK & 31u) | ((uint32_t)(myK >> 10) & 31u) << 8 | ((uint32_t)(myK >> 20) & 31u) << 16 |
+                           ((uint32_t)(myK >> 30) & 31u) << 24;
       const int cnt = (int)min(32u, ee - base);
       for (int i = 0; i < cnt; ++i) {
-        const uint32_t lw = __shfl_sync(0xffffffffu, myW, i), lw2 = __shfl_sync(0xffffffffu, myW2, i);
-        const int la = lw & 31u, lb = (lw >> 16) & 31u, lc = lw2 & 31u, ld = (lw2 >> 16) & 31u;
+        const uint32_t lw = __shfl_sync(0xffffffffu, myW, i);
+        const int la = lw & 31u, lb = (lw >> 8) & 31u, lc = (lw >> 16) & 31u, ld = (lw >> 24) & 31u;
         // point-triangle friction / restitution (Solver.cpp:431-471), as FrictionOp
         V3 B = shflV3(q4, lb), C = shflV3(q4, lc), D = shflV3(q4, ld);
         float wa = __shfl_sync(0xffffffffu, q4.w, la), wb = __shfl_sync(0xffffffffu, q4.w, lb),
@@ -314,124 +322,140 @@ __global__ void __launch_bounds__(kThreads) k_gs_cluster_friction(ClusterView cv
   }
 }
 
-// ---- ordered sweeps of mid-size contact clusters: one warp, nodes staged in shared memory ----------------------
-// A cluster of 33 .. kMidClusterMax nodes (a column of stacked bodies, say) has little parallelism inside: its
-// entries chain through shared nodes, and the dataflow executor pays an L2 round trip per link of that chain.
-// Here one warp copies the cluster's nodes into shared memory and walks the entries in list order, every lane
-// evaluating the same entry from broadcast reads (lanes 0..3 write the four nodes back): the reference's
-// sequential order at shared-memory latency, all sweeps and their floor snaps in one launch.  Clusters are
-// independent, so which CTA takes which cluster does not matter.
-constexpr int kMidWarpsPerSm = 6;
+// ---- ordered sweeps of mid-size contact clusters: one CTA, nodes staged in shared memory ----------------------
+// A cluster of 33 .. kMidClusterMax nodes (a column of stacked bodies, a small pile) chains its entries through
+// shared nodes, and the global dataflow executor pays an L2 round trip per link of that chain.  Here one CTA
+// copies the cluster's nodes into shared memory and runs the same ticketed dataflow there: warps take chunks of 32
+// consecutive entries (list order) from a shared counter, an entry runs once sDone[v] == ticket for its four nodes
+// and publishes ticket + 1.  All sweeps and their floor snaps happen in one launch.  Clusters are independent, so
+// which CTA takes which cluster does not matter; per node the order is the reference's sequential order.
+constexpr int kMidThreads = 256;
+constexpr int kMidCtasPerSm = 4;
 
-__global__ void __launch_bounds__(32) k_gs_mid_stabilize(ClusterView cv, const uint32_t* __restrict__ nMidPtr,
-                                                         float4* __restrict__ q, float4* __restrict__ prev,
-                                                         const float4* __restrict__ snap,
-                                                         const uint32_t* __restrict__ floorMult, int haveFloor,
-                                                         float thickness, uint32_t sweeps) {
-  __shared__ float4 sq[kMidClusterMax], sp[kMidClusterMax];
-  const int lane = threadIdx.x;
-  const uint32_t nMid = *nMidPtr;
-  for (uint32_t mi = blockIdx.x; mi < nMid; mi += gridDim.x) {
-    const uint32_t c = cv.midList[mi];
-    const uint32_t nb = cv.start[c], size = cv.start[c + 1] - nb;
-    for (uint32_t k = lane; k < size; k += 32) {
-      const uint32_t node = cv.nodes[nb + k];
-      sq[k] = q[node]; sp[k] = prev[node];
-    }
-    __syncwarp();
-    const uint32_t eb = cv.entStart[c], ee = cv.entStart[c + 1];
-    for (uint32_t sweep = 0; sweep < sweeps; ++sweep) {
-      for (uint32_t base = eb; base < ee; base += 32) {
-        const uint32_t myW = base + lane < ee ? cv.lanes[base + lane] : 0u;
-        const uint32_t myW2 = base + lane < ee ? (uint32_t)(cv.keys[base + lane] >> 32) : 0u;
-        const int cnt = (int)min(32u, ee - base);
-        for (int i = 0; i < cnt; ++i) {
-          const uint32_t lw = __shfl_sync(0xffffffffu, myW, i), lw2 = __shfl_sync(0xffffffffu, myW2, i);
-          const uint32_t ra = lw & 0xffffu, rb = lw >> 16, rc = lw2 & 0xffffu, rd = lw2 >> 16;
-          // PointTriangleCollisionConstraint::stabilizeCollisions (CollisionConstraint.cpp:126-162), as StabilizeOp
-          const float4 a4 = sq[ra], b4 = sq[rb], c4 = sq[rc], d4 = sq[rd];
-          V3 A = v3(a4), B = v3(b4), C = v3(c4), D = v3(d4);
-          V3 nrm = normalize(cross(C - B, D - B));
-          float nDotP = dot(nrm, A - B);
-          if (!(nDotP < thickness)) continue;
-          V3 disp = (thickness - nDotP) * nrm;
-          float wTri = b4.w + c4.w + d4.w;
-          float wSum = a4.w + wTri;
-          V3 da = disp * a4.w / wSum, dt = disp * wTri / wSum;
-          if (lane < 4) {
-            const uint32_t r = lane == 0 ? ra : lane == 1 ? rb : lane == 2 ? rc : rd;
-            const float4 cur = lane == 0 ? a4 : lane == 1 ? b4 : lane == 2 ? c4 : d4;
-            const V3 d = lane == 0 ? da : -dt;
-            const float4 pv = sp[r];
-            sq[r] = make_float4(cur.x + d.x, cur.y + d.y, cur.z + d.z, cur.w);
-            sp[r] = make_float4(pv.x + d.x, pv.y + d.y, pv.z + d.z, pv.w);
-          }
-          __syncwarp();
-        }
-      }
-      if (haveFloor) {  // Solver.cpp:379-382, after the sweep's point-triangle entries
-        for (uint32_t k = lane; k < size; k += 32) {
-          const uint32_t node = cv.nodes[nb + k];
-          if (floorMult[node] != 0u) { const float4 s4 = snap[node]; sq[k] = make_float4(s4.x, s4.y, s4.z, sq[k].w); }
-        }
-        __syncwarp();
-      }
-    }
-    for (uint32_t k = lane; k < size; k += 32) {
-      const uint32_t node = cv.nodes[nb + k];
-      q[node] = sq[k]; prev[node] = sp[k];
-    }
-    __syncwarp();
-  }
+__device__ __forceinline__ float4 ldsVolatile(const float4* p) {
+  float4 v;
+  asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stsVolatile(float4* p, float4 v) {
+  asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t ldsVolatile(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stsVolatile(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(32) k_gs_mid_friction(ClusterView cv, const uint32_t* __restrict__ nMidPtr,
-                                                        const float4* __restrict__ q, float4* __restrict__ vel,
-                                                        float friction, float staticThreshold) {
-  __shared__ float4 sq[kMidClusterMax], sv[kMidClusterMax];
-  const int lane = threadIdx.x;
+// kStabilize: s0 = position, s1 = prevPosition, `sweeps` sweeps with the floor snap after each (StabilizeOp);
+// otherwise s0 = position (read only), s1 = velocity, one sweep (FrictionOp).
+template <bool kStabilize>
+__global__ void __launch_bounds__(kMidThreads, kMidCtasPerSm) k_gs_mid(ClusterView cv, const uint32_t* __restrict__ nMidPtr,
+                                                                      const uint4* __restrict__ ticket,
+                                                                      float4* __restrict__ g0, float4* __restrict__ g1,
+                                                                      const float4* __restrict__ snap,
+                                                                      const uint32_t* __restrict__ floorMult, int haveFloor,
+                                                                      float pa /* thickness | friction */,
+                                                                      float pb /* - | staticThreshold */, uint32_t sweeps) {
+  __shared__ float4 s0[kMidClusterMax], s1[kMidClusterMax];
+  __shared__ uint32_t sDone[kMidClusterMax];
+  __shared__ uint32_t sChunk;
+  const int lane = threadIdx.x & 31;
   const uint32_t nMid = *nMidPtr;
   for (uint32_t mi = blockIdx.x; mi < nMid; mi += gridDim.x) {
     const uint32_t c = cv.midList[mi];
     const uint32_t nb = cv.start[c], size = cv.start[c + 1] - nb;
-    for (uint32_t k = lane; k < size; k += 32) {
+    for (uint32_t k = threadIdx.x; k < size; k += kMidThreads) {
       const uint32_t node = cv.nodes[nb + k];
-      sq[k] = q[node]; sv[k] = vel[node];
+      s0[k] = g0[node]; s1[k] = g1[node];
     }
-    __syncwarp();
     const uint32_t eb = cv.entStart[c], ee = cv.entStart[c + 1];
-    for (uint32_t base = eb; base < ee; base += 32) {
-      const uint32_t myW = base + lane < ee ? cv.lanes[base + lane] : 0u;
-      const uint32_t myW2 = base + lane < ee ? (uint32_t)(cv.keys[base + lane] >> 32) : 0u;
-      const int cnt = (int)min(32u, ee - base);
-      for (int i = 0; i < cnt; ++i) {
-        const uint32_t lw = __shfl_sync(0xffffffffu, myW, i), lw2 = __shfl_sync(0xffffffffu, myW2, i);
-        const uint32_t ra = lw & 0xffffu, rb = lw >> 16, rc = lw2 & 0xffffu, rd = lw2 >> 16;
-        // point-triangle friction / restitution (Solver.cpp:431-471), as FrictionOp
-        const float4 a4 = sq[ra], b4 = sq[rb], c4 = sq[rc], d4 = sq[rd];
-        const V3 va = v3(sv[ra]), vb = v3(sv[rb]), vc = v3(sv[rc]), vd = v3(sv[rd]);
-        V3 avgTri = (vb + vc + vd) / 3.0f;
-        V3 nrm = normalize(cross(v3(c4) - v3(b4), v3(d4) - v3(b4)));
-        V3 rel = va - avgTri;
-        float vDotN = dot(rel, nrm);
-        V3 perp = rel - vDotN * nrm;
-        float fr = friction;
-        if (length(perp) < staticThreshold) fr = 1.0f;
-        float triW = b4.w + c4.w + d4.w;
-        float wSum = a4.w + triW;
-        V3 dv = (-fr) * perp - (1.1f * fminf(vDotN, 0.0f)) * nrm;
-        V3 dtv = (-dv) * triW / wSum;
-        if (lane < 4) {
-          const uint32_t r = lane == 0 ? ra : lane == 1 ? rb : lane == 2 ? rc : rd;
-          const V3 v0 = lane == 0 ? va : lane == 1 ? vb : lane == 2 ? vc : vd;
-          const V3 nv = lane == 0 ? va + dv * a4.w / wSum : v0 + dtv;
-          sv[r] = f4(nv, 0.0f);
+    const uint32_t nChunks = (ee - eb + 31u) >> 5;
+    for (uint32_t sweep = 0; sweep < sweeps; ++sweep) {
+      for (uint32_t k = threadIdx.x; k < size; k += kMidThreads) sDone[k] = 0u;
+      if (threadIdx.x == 0) sChunk = 0u;
+      __syncthreads();
+      while (true) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&sChunk, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= nChunks) break;
+        const uint32_t pos = eb + (chunk << 5) + (uint32_t)lane;
+        bool pending = pos < ee;
+        uint32_t ra = 0, rb = 0, rc = 0, rd = 0;
+        uint4 tk = make_uint4(0, 0, 0, 0);
+        if (pending) {
+          const uint64_t r = cv.keys[pos] >> kClusterBits;
+          ra = (uint32_t)r & 1023u; rb = (uint32_t)(r >> 10) & 1023u; rc = (uint32_t)(r >> 20) & 1023u; rd = (uint32_t)(r >> 30) & 1023u;
+          tk = ticket[cv.entryOf[pos]];
         }
-        __syncwarp();
+        while (__any_sync(0xffffffffu, pending)) {
+          if (pending) {
+            const bool ready = ldsVolatile(sDone + ra) == tk.x && ldsVolatile(sDone + rb) == tk.y &&
+                               ldsVolatile(sDone + rc) == tk.z && ldsVolatile(sDone + rd) == tk.w;
+            if (ready) {
+              __threadfence_block();
+              const float4 a4 = ldsVolatile(s0 + ra), b4 = ldsVolatile(s0 + rb), c4 = ldsVolatile(s0 + rc), d4 = ldsVolatile(s0 + rd);
+              if (kStabilize) {
+                // PointTriangleCollisionConstraint::stabilizeCollisions (CollisionConstraint.cpp:126-162), as StabilizeOp
+                V3 A = v3(a4), B = v3(b4), C = v3(c4), D = v3(d4);
+                V3 nrm = normalize(cross(C - B, D - B));
+                float nDotP = dot(nrm, A - B);
+                if (nDotP < pa) {
+                  V3 disp = (pa - nDotP) * nrm;
+                  float wTri = b4.w + c4.w + d4.w;
+                  float wSum = a4.w + wTri;
+                  V3 da = disp * a4.w / wSum, dt = disp * wTri / wSum;
+                  const float4 p0 = ldsVolatile(s1 + ra), p1 = ldsVolatile(s1 + rb), p2 = ldsVolatile(s1 + rc), p3 = ldsVolatile(s1 + rd);
+                  stsVolatile(s0 + ra, f4(A + da, a4.w)); stsVolatile(s0 + rb, f4(B - dt, b4.w));
+                  stsVolatile(s0 + rc, f4(C - dt, c4.w)); stsVolatile(s0 + rd, f4(D - dt, d4.w));
+                  stsVolatile(s1 + ra, f4(v3(p0) + da, p0.w)); stsVolatile(s1 + rb, f4(v3(p1) - dt, p1.w));
+                  stsVolatile(s1 + rc, f4(v3(p2) - dt, p2.w)); stsVolatile(s1 + rd, f4(v3(p3) - dt, p3.w));
+                }
+              } else {
+                // point-triangle friction / restitution (Solver.cpp:431-471), as FrictionOp
+                const V3 va = v3(ldsVolatile(s1 + ra)), vb = v3(ldsVolatile(s1 + rb)), vc = v3(ldsVolatile(s1 + rc)), vd = v3(ldsVolatile(s1 + rd));
+                V3 avgTri = (vb + vc + vd) / 3.0f;
+                V3 nrm = normalize(cross(v3(c4) - v3(b4), v3(d4) - v3(b4)));
+                V3 rel = va - avgTri;
+                float vDotN = dot(rel, nrm);
+                V3 perp = rel - vDotN * nrm;
+                float fr = pa;
+                if (length(perp) < pb) fr = 1.0f;
+                float triW = b4.w + c4.w + d4.w;
+                float wSum = a4.w + triW;
+                V3 dv = (-fr) * perp - (1.1f * fminf(vDotN, 0.0f)) * nrm;
+                V3 dtv = (-dv) * triW / wSum;
+                stsVolatile(s1 + ra, f4(va + dv * a4.w / wSum, 0.0f));
+                stsVolatile(s1 + rb, f4(vb + dtv, 0.0f)); stsVolatile(s1 + rc, f4(vc + dtv, 0.0f)); stsVolatile(s1 + rd, f4(vd + dtv, 0.0f));
+              }
+              __threadfence_block();
+              stsVolatile(sDone + ra, tk.x + 1u); stsVolatile(sDone + rb, tk.y + 1u);
+              stsVolatile(sDone + rc, tk.z + 1u); stsVolatile(sDone + rd, tk.w + 1u);
+              pending = false;
+            }
+          }
+        }
       }
+      __syncthreads();
+      if (kStabilize && haveFloor) {  // Solver.cpp:379-382, after the sweep's point-triangle entries
+        for (uint32_t k = threadIdx.x; k < size; k += kMidThreads) {
+          const uint32_t node = cv.nodes[nb + k];
+          if (floorMult[node] != 0u) { const float4 s4 = snap[node]; s0[k] = make_float4(s4.x, s4.y, s4.z, s0[k].w); }
+        }
+      }
+      __syncthreads();
     }
-    for (uint32_t k = lane; k < size; k += 32) vel[cv.nodes[nb + k]] = make_float4(sv[k].x, sv[k].y, sv[k].z, 0.0f);
-    __syncwarp();
+    for (uint32_t k = threadIdx.x; k < size; k += kMidThreads) {
+      const uint32_t node = cv.nodes[nb + k];
+      if (kStabilize) { g0[node] = s0[k]; g1[node] = s1[k]; }
+      else g1[node] = make_float4(s1[k].x, s1[k].y, s1[k].z, 0.0f);
+    }
+    __syncthreads();
   }
 }
 
@@ -492,6 +516,7 @@ int prepareClusterSweeps(ContactWork& w, cudaStream_t s, const ContactLists& c, 
   L += launchExclusiveScan(s, w.entStart.p, clusterBound + 1, w.scanScratch.p);
   int bits = 1;
   while ((1ull << bits) <= (uint64_t)clusterBound) ++bits;
+  if (bits > kClusterBits) return -1;  // > 16 M contact clusters in one substep: beyond the sorted-entry record layout
   L += launchSortPairs(s, nTri, w.keys.p, w.lanes.p, w.tmpKeys.p, w.tmpVals.p, w.sortHist.p, bits);
   w.view = ClusterView{t.nClusters, t.start, t.nodes, w.entStart.p, w.lanes.p, w.keys.p, t.midList};
   w.gsClass = t.gsClass;
@@ -533,8 +558,8 @@ int launchStabilize(cudaStream_t s, ContactWork& w, const ContactLists& c, uint3
     if (w.countsReady) cudaEventSynchronize(w.countsReady);
     const uint32_t nMid = w.hostCounts ? w.hostCounts[0] : 0u, nLarge = w.hostCounts ? w.hostCounts[1] : 1u;
     if (nMid) {
-      k_gs_mid_stabilize<<<(int)std::min<uint32_t>(nMid, kNumSMs * kMidWarpsPerSm), 32, 0, s>>>(w.view, w.nMidDev, q, prev, snap, c.floorMult,
-                                                                                         c.nFloor ? 1 : 0, thickness, iterations); ++L;
+      k_gs_mid<true><<<(int)std::min<uint32_t>(nMid, kNumSMs * kMidCtasPerSm), kMidThreads, 0, s>>>(
+          w.view, w.nMidDev, c.ticket, q, prev, snap, c.floorMult, c.nFloor ? 1 : 0, thickness, 0.0f, iterations); ++L;
     }
     // large clusters: dataflow sweeps, floor snap of their nodes after each one
     for (uint32_t it = 0; nLarge && it < iterations; ++it) {
@@ -555,8 +580,8 @@ int launchFriction(cudaStream_t s, ContactWork& w, const ContactLists& c, uint32
     if (w.countsReady) cudaEventSynchronize(w.countsReady);
     const uint32_t nMid = w.hostCounts ? w.hostCounts[0] : 0u, nLarge = w.hostCounts ? w.hostCounts[1] : 1u;
     if (nMid) {
-      k_gs_mid_friction<<<(int)std::min<uint32_t>(nMid, kNumSMs * kMidWarpsPerSm), 32, 0, s>>>(w.view, w.nMidDev, q, vel, friction,
-                                                                                        staticThreshold); ++L;
+      k_gs_mid<false><<<(int)std::min<uint32_t>(nMid, kNumSMs * kMidCtasPerSm), kMidThreads, 0, s>>>(
+          w.view, w.nMidDev, c.ticket, const_cast<float4*>(q), vel, nullptr, nullptr, 0, friction, staticThreshold, 1u); ++L;
     }
     if (nLarge) L += launchSweep(s, w, c, n, FrictionOp{q, vel, friction, staticThreshold});
   }

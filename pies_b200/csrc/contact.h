@@ -12,8 +12,8 @@ struct ClusterView {   // device view of this substep's contact clusters and the
   const uint32_t* start = nullptr;
   const uint32_t* nodes = nullptr;
   const uint32_t* entStart = nullptr;
-  const uint32_t* lanes = nullptr;   // per entry (grouped by cluster, list order inside): rank of a | rank of b << 16
-  const uint64_t* keys = nullptr;    // per entry: (rank of c | rank of d << 16) << 32 | cluster
+  const uint32_t* entryOf = nullptr; // per sorted entry (grouped by cluster, list order inside): its index in the list
+  const uint64_t* keys = nullptr;    // per sorted entry: ranks of its four nodes inside the cluster (10 bits each) << 24 | cluster
   const uint32_t* midList = nullptr; // clusters of 33 .. kMidClusterMax nodes
 };
 

@@ -265,6 +265,10 @@ __global__ void k_pcg_check(float* __restrict__ scalars, int* __restrict__ flag,
 // The (col, val) pairs of a CTA's NEXT batch are staged into shared memory with cp.async while the current batch
 // is processed (double buffer), so the only exposed latency per batch is the gather of z.
 constexpr int kSpmvTile = 2048;  // == HostSystem::kBatchNnz: entries of one row batch per pass
+// Shared-memory slot of tile entry o: one pad word per 32 entries.  The per-row sums read runs of ~8 consecutive
+// entries per thread (stride ~8 between lanes), which would hit 4 banks 8 ways; padded, stride 8 is conflict-free.
+constexpr int kSpmvSlots = kSpmvTile + kSpmvTile / 32;
+__device__ __forceinline__ int spmvSlot(int o) { return o + (o >> 5); }
 
 struct SpmvBatch { uint32_t r0, r1; int e0, nA, f0, total; };
 
@@ -289,8 +293,8 @@ __device__ __forceinline__ void stageEntries(int* sCol, float* sVal, const CsrMa
     const int* pc; const float* pv;
     if (v < m.nA) { pc = A.col + m.e0 + v; pv = A.val + m.e0 + v; }
     else { pc = c.cCol + m.f0 + (v - m.nA); pv = c.cVal + m.f0 + (v - m.nA); }
-    cpAsync4(sCol + (v - cs), pc);
-    cpAsync4(sVal + (v - cs), pv);
+    cpAsync4(sCol + spmvSlot(v - cs), pc);
+    cpAsync4(sVal + spmvSlot(v - cs), pv);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -298,9 +302,9 @@ __device__ __forceinline__ void stageEntries(int* sCol, float* sVal, const CsrMa
 __global__ void __launch_bounds__(kThreads, 4) k_pcg_spmv(CsrMatrix A, ContactLists c, PcgWork w, float* __restrict__ partials,
                                                           int parity, int first, float tol2) {
   __shared__ float smem[128];
-  __shared__ __align__(16) int sCol[2][kSpmvTile];    // staged columns; overwritten in place by the y-products
-  __shared__ __align__(16) float sVal[2][kSpmvTile];  // staged values; overwritten in place by the x-products
-  __shared__ float sZ[kSpmvTile];                     // z-products
+  __shared__ __align__(16) int sCol[2][kSpmvSlots];    // staged columns; overwritten in place by the y-products
+  __shared__ __align__(16) float sVal[2][kSpmvSlots];  // staged values; overwritten in place by the x-products
+  __shared__ float sZ[kSpmvSlots];                     // z-products
   if (ctaConverged(w.flag)) return;
   // the first batch's entries do not depend on the scalars: start their copy before reading those
   const uint32_t nB = A.nBatches;
@@ -360,22 +364,23 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_spmv(CsrMatrix A, ContactLi
       // gather z and park the products (four independent gathers in flight per thread)
       for (int o = (int)threadIdx.x; o < cnt; o += 4 * kThreads) {
         const bool h1 = o + kThreads < cnt, h2 = o + 2 * kThreads < cnt, h3 = o + 3 * kThreads < cnt;
-        int c0 = pcol[o], c1 = 0, c2 = 0, c3 = 0;
-        float a0 = px[o], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-        if (h1) { c1 = pcol[o + kThreads]; a1 = px[o + kThreads]; }
-        if (h2) { c2 = pcol[o + 2 * kThreads]; a2 = px[o + 2 * kThreads]; }
-        if (h3) { c3 = pcol[o + 3 * kThreads]; a3 = px[o + 3 * kThreads]; }
+        const int s0 = spmvSlot(o), s1 = spmvSlot(o + kThreads), s2 = spmvSlot(o + 2 * kThreads), s3 = spmvSlot(o + 3 * kThreads);
+        int c0 = pcol[s0], c1 = 0, c2 = 0, c3 = 0;
+        float a0 = px[s0], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        if (h1) { c1 = pcol[s1]; a1 = px[s1]; }
+        if (h2) { c2 = pcol[s2]; a2 = px[s2]; }
+        if (h3) { c3 = pcol[s3]; a3 = px[s3]; }
         const float4 x0 = __ldg(z + c0), x1 = __ldg(z + c1), x2 = __ldg(z + c2), x3 = __ldg(z + c3);
-        px[o] = a0 * x0.x; py[o] = a0 * x0.y; sZ[o] = a0 * x0.z;
-        if (h1) { px[o + kThreads] = a1 * x1.x; py[o + kThreads] = a1 * x1.y; sZ[o + kThreads] = a1 * x1.z; }
-        if (h2) { px[o + 2 * kThreads] = a2 * x2.x; py[o + 2 * kThreads] = a2 * x2.y; sZ[o + 2 * kThreads] = a2 * x2.z; }
-        if (h3) { px[o + 3 * kThreads] = a3 * x3.x; py[o + 3 * kThreads] = a3 * x3.y; sZ[o + 3 * kThreads] = a3 * x3.z; }
+        px[s0] = a0 * x0.x; py[s0] = a0 * x0.y; sZ[s0] = a0 * x0.z;
+        if (h1) { px[s1] = a1 * x1.x; py[s1] = a1 * x1.y; sZ[s1] = a1 * x1.z; }
+        if (h2) { px[s2] = a2 * x2.x; py[s2] = a2 * x2.y; sZ[s2] = a2 * x2.z; }
+        if (h3) { px[s3] = a3 * x3.x; py[s3] = a3 * x3.y; sZ[s3] = a3 * x3.z; }
       }
       __syncthreads();
       if (haveRow) {  // per-row sums in CSR order: the S segment, then the collision segment
         const int ce = cs + cnt;
-        for (int k = max(rb, cs); k < min(re, ce); ++k) { y.x += px[k - cs]; y.y += py[k - cs]; y.z += sZ[k - cs]; }
-        for (int k = max(cb, cs); k < min(cf, ce); ++k) { y.x += px[k - cs]; y.y += py[k - cs]; y.z += sZ[k - cs]; }
+        for (int k = max(rb, cs); k < min(re, ce); ++k) { const int sl = spmvSlot(k - cs); y.x += px[sl]; y.y += py[sl]; y.z += sZ[sl]; }
+        for (int k = max(cb, cs); k < min(cf, ce); ++k) { const int sl = spmvSlot(k - cs); y.x += px[sl]; y.y += py[sl]; y.z += sZ[sl]; }
       }
       __syncthreads();
     }

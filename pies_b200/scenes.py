@@ -145,3 +145,86 @@ def build_pbd_boxes(s):
     s.createBox((0.0, 0.6, 0.0), 1.0, 0.5)
     s.createBox((0.3, 5.9, 0.2), 1.0, 0.5)
     s.createBox((9.0, 3.0, 1.0), 1.0, 0.5)
+
+
+# ---- config 4 / config 5, any size ------------------------------------------
+def lattice_hull(cx, cy, cz, offset=0):
+    """Outward-wound surface triangles of a createShapeMatchingBox body (node id = offset + (i*cy + j)*cz + k,
+    PrimitiveUtilities.cpp:1003-1013).  The factory itself emits no triangles, so without
+    these config 4 has no point-triangle CCD and no friction."""
+    def nid(i, j, k):
+        return offset + (i * cy + j) * cz + k
+    tris = []
+    def quad(a, b, c, d, flip):
+        if flip:
+            b, d = d, b
+        tris.append((a, b, c)); tris.append((a, c, d))
+    for j in range(cy - 1):
+        for k in range(cz - 1):
+            for i, flip in ((0, False), (cx - 1, True)):
+                quad(nid(i, j, k), nid(i, j, k + 1), nid(i, j + 1, k + 1), nid(i, j + 1, k), flip)
+    for i in range(cx - 1):
+        for k in range(cz - 1):
+            for j, flip in ((0, False), (cy - 1, True)):
+                quad(nid(i, j, k), nid(i + 1, j, k), nid(i + 1, j, k + 1), nid(i, j, k + 1), flip)
+    for i in range(cx - 1):
+        for j in range(cy - 1):
+            for k, flip in ((0, False), (cz - 1, True)):
+                quad(nid(i, j, k), nid(i, j + 1, k), nid(i + 1, j + 1, k), nid(i + 1, j, k), flip)
+    return np.asarray(tris, np.uint32)
+
+
+def s4_translations(bodies, per_side, pitch=5.0, y0=1.0):
+    i = np.arange(bodies)
+    t = np.stack([pitch * (i % per_side), y0 + pitch * (i // (per_side * per_side)), pitch * ((i // per_side) % per_side)],
+                 axis=1).astype(np.float32)
+    return (t + lcg_jitter(bodies, seed=4242)).astype(np.float32)
+
+
+def build_s4(s, bodies=15625, per_side=25, cx=4, cy=8, cz=8, w=1000.0, pitch=5.0, y0=1.0, goal_bodies=244, goal_w=1000.0):
+    """S4: `bodies` x createShapeMatchingBox(cx, cy, cz) (one cluster per body, factory scale 0.5, invMass 0.1) on a
+    lattice of the given pitch, hull triangles appended on both sides, and one unit-cube-derived goal region around
+    each of the first `goal_bodies` bodies (addFixedRegions, w = goal_w).  Returns (translations, region matrices);
+    the caller scripts updateFixedRegions."""
+    trans = s4_translations(bodies, per_side, pitch, y0)
+    n_per = cx * cy * cz
+    hull = lattice_hull(cx, cy, cz)
+    for b, t in enumerate(trans):
+        s.createShapeMatchingBox(t, cx, cy, cz, 0.5, (0.0, 0.0, 0.0), w)
+        tri = hull + np.uint32(b * n_per)
+        if hasattr(s, "appendTriangles"):
+            s.appendTriangles(tri)
+        else:
+            for a, bb, c in tri:
+                s.appendTriangle(int(a), int(bb), int(c))
+    ext = 0.5 * np.array([cx - 1, cy - 1, cz - 1], np.float32)
+    regions = []
+    for t in trans[:goal_bodies]:
+        m = np.zeros((4, 4), np.float32)          # column-major storage: m[c, r]
+        m[0, 0], m[1, 1], m[2, 2], m[3, 3] = ext[0] + 0.5, ext[1] + 0.5, ext[2] + 0.5, 1.0
+        m[3, :3] = t + 0.5 * ext                  # unit cube centred on the body, 0.25 larger on every side
+        regions.append(m.reshape(16))
+    regions = np.stack(regions) if regions else np.zeros((0, 16), np.float32)
+    if len(regions):
+        s.addFixedRegions(regions, goal_w)
+    return trans, regions
+
+
+def s4_region_script(regions, tick, speed=0.02):
+    """The scripted rigid motion of the goal regions: a slow translation along +x with a vertical sway."""
+    out = regions.reshape(-1, 4, 4).copy()
+    out[:, 3, 0] += speed * tick
+    out[:, 3, 1] += 0.5 * speed * np.sin(0.2 * tick)
+    return out.reshape(-1, 16)
+
+
+def build_s5(ref, ours=None, bodies=512, per_side=8, n=24, side=8.0, pitch=10.0, y0=3.07):
+    """S5: `bodies` x addTriMeshVolume of the side-8 cube with an n x n-quad surface per face (n = 24: 16 437 tets each),
+    strain w 1000 [0.8, 1] + volume w 1000 [1, 1], on a lattice of the given pitch above the floor.  The reference
+    tetrahedralises (its vendored TetGen); our side receives the same meshes."""
+    i = np.arange(bodies)
+    origins = np.stack([pitch * (i % per_side), y0 + pitch * (i // (per_side * per_side)), pitch * ((i // per_side) % per_side)],
+                       axis=1).astype(np.float32) + lcg_jitter(bodies, seed=5151)
+    for o in origins:
+        add_tetgen_cube(ref, ours, side=side, n=n, origin=tuple(float(x) for x in o))
+    return origins

@@ -171,18 +171,29 @@ def test_run_to_run_bit_stable(pb):
     assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all() and (out[0][2] == out[1][2]).all()
 
 
+def pile(s, n=10):
+    """Ten tet boxes dropped at 2 m/s with alternating lateral offsets: they topple, so contacts reach side faces and
+    the contact clusters grow past 32 nodes (reference run: one 67-node cluster at tick 34, 168 nodes at tick 60)."""
+    for i in range(n):
+        s.createTetBox((0.35 * (i % 2), 0.55 + 1.25 * i, 0.3 * ((i // 2) % 2)), 1.0, (0.0, -2.0, 0.0), 1000.0, 1.0, False)
+
+
 def test_ordered_sweep_executors_agree(pb):
-    """The ordered stabilisation / friction sweeps have three executors (registers for clusters <= 32 nodes, one warp
-    from shared memory up to 1024 nodes, ticketed dataflow above): all replay the reference's sequential order per
-    node, so forcing every cluster above 32 nodes through the dataflow executor must give the same trajectory (same
-    operations in the same order; only fp contraction may differ between the kernels)."""
-    from pies_b200 import scenes
+    """The ordered stabilisation / friction sweeps have three executors (registers for clusters <= 32 nodes, one CTA
+    from shared memory up to 1024 nodes, ticketed dataflow through L2 above): all replay the reference's sequential
+    order per node, so forcing every cluster above 32 nodes through the global dataflow executor must give the same
+    result (same operations in the same order; only fp contraction may differ between the kernels).  Both executors
+    start from the same snapshot of a toppling pile and advance two ticks."""
+    s = pb.Solver(iterations=10)
+    pile(s)
+    for _ in range(44):
+        s.tick()
+    snap = [s.positions.copy(), s.prevPositions.copy(), s.velocities.copy()]
     out = []
     for dataflow_only in (False, True):
-        s = pb.Solver(**scenes.S3_OPTIONS)
-        scenes.build_s3(s, bodies=16, nx=2, nz=2)
+        s.setState(*snap)
         s.setTuning(dataflowSweepsOnly=dataflow_only)
-        for _ in range(46):
+        for _ in range(2):
             s.tick()
         st = s.stats()
         assert st.triCollisions > 100
