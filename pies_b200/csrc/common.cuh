@@ -9,6 +9,7 @@ namespace pies {
 constexpr int kNumSMs = 148;          // B200
 constexpr int kThreads = 256;         // default CTA size for streaming kernels
 constexpr int kReduceBlocks = 592;    // 148 SMs x 4 resident CTAs: fixed grid => fixed-order reductions
+constexpr int kMaxReduceBlocks = 2368; // 148 x 16: largest grid a kernel with a last-CTA reduction may use (partials capacity)
 
 struct V3 { float x, y, z; };
 

@@ -159,8 +159,8 @@ int ensureBuilt(PiesB200Solver* s) {
   if ((rc = uploadState(s))) return rc;
   PIES_CHECK(s, s->msn.reserve(n)); PIES_CHECK(s, s->rhs.reserve(n)); PIES_CHECK(s, s->snap.reserve(n));
   PIES_CHECK(s, s->pr.reserve(n)); PIES_CHECK(s, s->pp.reserve(n)); PIES_CHECK(s, s->pp2.reserve(n)); PIES_CHECK(s, s->pz.reserve(n)); PIES_CHECK(s, s->pap.reserve(n)); PIES_CHECK(s, s->pdelta.reserve(n));
-  PIES_CHECK(s, s->partials.reserve((size_t)kReduceBlocks * 32)); PIES_CHECK(s, s->scalars.reserve(64)); PIES_CHECK(s, s->flag.reserve(4));
-  PIES_CHECK(s, cudaMemsetAsync(s->partials.p, 0, (size_t)kReduceBlocks * 32 * sizeof(float), st));
+  PIES_CHECK(s, s->partials.reserve((size_t)kMaxReduceBlocks * 32)); PIES_CHECK(s, s->scalars.reserve(64)); PIES_CHECK(s, s->flag.reserve(4));
+  PIES_CHECK(s, cudaMemsetAsync(s->partials.p, 0, (size_t)kMaxReduceBlocks * 32 * sizeof(float), st));
   PIES_CHECK(s, cudaMemsetAsync(s->scalars.p, 0, 64 * sizeof(float), st));
   PIES_CHECK(s, cudaMemsetAsync(s->flag.p, 0, 4 * sizeof(int), st));
   PIES_CHECK(s, cudaMemsetAsync(s->snap.p, 0, (size_t)n * sizeof(float4), st));
@@ -196,7 +196,8 @@ int ensureBuilt(PiesB200Solver* s) {
   sc.goalXformDirty = false;
   PIES_CHECK(s, uploadVec(s->incPtr, y.incPtr, st)); PIES_CHECK(s, uploadVec(s->inc, y.inc, st));
   PIES_CHECK(s, uploadVec(s->rowPtr, y.rowPtr, st)); PIES_CHECK(s, uploadVec(s->col, y.col, st)); PIES_CHECK(s, uploadVec(s->val, y.val, st));
-  PIES_CHECK(s, uploadVec(s->rowBatch, y.rowBatch, st));
+  PIES_CHECK(s, uploadVec(s->sellPtr, y.sellPtr, st)); PIES_CHECK(s, uploadVec(s->sellRow, y.sellRow, st));
+  PIES_CHECK(s, uploadVec(s->sellCol, y.sellCol, st)); PIES_CHECK(s, uploadVec(s->sellVal, y.sellVal, st));
   PIES_CHECK(s, uploadVec(s->blockNodes, y.blockNodes, st)); PIES_CHECK(s, uploadVec(s->blockInv, y.blockInv, st));
   PIES_CHECK(s, uploadVec(s->triIds, sc.triangles, st));
   PIES_CHECK(s, cudaStreamSynchronize(st));
@@ -323,8 +324,8 @@ PdViews pdViews(PiesB200Solver* s) {
   v.be = BendElems{s->bendIds.p, s->bendAngleW.p, (uint32_t)s->scene.bendW.size()};
   v.sh = ClusterElems{s->shapeOff.p, s->shapeIds.p, (uint32_t)s->scene.shapeW.size(), (uint32_t)s->scene.shapeId.size()};
   v.go = ClusterElems{s->goalOff.p, s->goalIds.p, (uint32_t)s->scene.goalW.size(), (uint32_t)s->scene.goalId.size()};
-  v.A = CsrMatrix{s->rowPtr.p, s->col.p, s->val.p, s->n, (uint64_t)y.col.size(), s->rowBatch.p,
-                  (uint32_t)(y.rowBatch.empty() ? 0 : y.rowBatch.size() - 1)};
+  v.A = CsrMatrix{s->rowPtr.p, s->col.p, s->val.p, s->n, (uint64_t)y.col.size(), s->sellPtr.p, s->sellRow.p, s->sellCol.p,
+                  s->sellVal.p, (uint32_t)(y.sellPtr.empty() ? 0 : y.sellPtr.size() - 1)};
   v.pw.r = s->pr.p; v.pw.p = s->pp.p; v.pw.p2 = s->pp2.p; v.pw.z = s->pz.p; v.pw.ap = s->pap.p; v.pw.delta = s->pdelta.p;
   v.pw.partials = s->partials.p; v.pw.scalars = s->scalars.p; v.pw.flag = s->flag.p;
   if (s->blocks) {  // the contact-aware blocks of the current substep (reblock.cu)

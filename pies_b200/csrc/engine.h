@@ -83,7 +83,7 @@ struct PiesB200Solver {
   pies::DevBuf<float> shapeW, goalMat, goalXform, goalW;
   pies::DevBuf<int> incPtr; pies::DevBuf<uint32_t> inc;
   pies::DevBuf<int> rowPtr, col; pies::DevBuf<float> val;
-  pies::DevBuf<uint32_t> rowBatch;
+  pies::DevBuf<uint32_t> sellPtr, sellRow; pies::DevBuf<int> sellCol; pies::DevBuf<float> sellVal;
   pies::DevBuf<int> blockNodes; pies::DevBuf<float> blockInv;
   pies::DevBuf<uint32_t> triIds;  // 3 per triangle
   pies::DevBuf<float> packed;     // 3 floats per node, readback staging

@@ -37,8 +37,10 @@ struct ClusterElems {  // shape- and goal-matching clusters (CSR over members)
 // CSR of S = M/h^2 + sum w A^T A (Solver.cpp:174-210), both triangles.
 struct CsrMatrix {
   int* rowPtr = nullptr; int* col = nullptr; float* val = nullptr; uint32_t n = 0; uint64_t nnz = 0;
-  // row batches of the CSR-stream mat-vec (system.h)
-  uint32_t* rowBatch = nullptr; uint32_t nBatches = 0;
+  // sliced-ELLPACK copy read by the CG mat-vec (system.h): slice s holds rows sellRow[32 s + lane], entry k of a
+  // lane at sellPtr[s] + 32 k + lane
+  uint32_t* sellPtr = nullptr; uint32_t* sellRow = nullptr; int* sellCol = nullptr; float* sellVal = nullptr;
+  uint32_t nSlices = 0;
 };
 
 // Per-substep collision lists in the reference's canonical order.

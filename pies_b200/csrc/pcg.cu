@@ -10,6 +10,8 @@
 //
 // Determinism: every dot product is reduced in a fixed order (per-CTA partials on a
 // fixed grid, summed redundantly by each consumer CTA in the same order) — no atomics.
+#include <algorithm>
+
 #include "kernels.h"
 #include "common.cuh"
 
@@ -195,19 +197,24 @@ __device__ __forceinline__ void issueBlockInv(float* __restrict__ sInv, const fl
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__device__ __forceinline__ V3 applyBlockInv(const float* __restrict__ sInv, V3 r, int lane, int m) {
+// z_lane = sum_j Minv(j, lane) r_j.  r is parked in shared memory (one float4 per member) so every step reads it
+// with a single broadcast load instead of three shuffles; tri walks the triangular numbers j (j + 1) / 2.
+__device__ __forceinline__ V3 applyBlockInv(const float* __restrict__ sInv, float4* __restrict__ sR, V3 r, int lane, int m) {
+  sR[lane] = make_float4(r.x, r.y, r.z, 0.0f);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
   V3 z = v3(0.0f, 0.0f, 0.0f);
   const int col = lane < m ? lane : 0;
   const int colBase = col * (col + 1) / 2;
+  int tri = 0;
 #pragma unroll 4
   for (int j = 0; j < m; ++j) {
-    float mv = sInv[j >= col ? j * (j + 1) / 2 + col : colBase + j];
-    z.x += mv * __shfl_sync(0xffffffffu, r.x, j);
-    z.y += mv * __shfl_sync(0xffffffffu, r.y, j);
-    z.z += mv * __shfl_sync(0xffffffffu, r.z, j);
+    const float mv = sInv[j >= col ? tri + col : colBase + j];
+    const float4 rj = sR[j];
+    z.x = fmaf(mv, rj.x, z.x); z.y = fmaf(mv, rj.y, z.y); z.z = fmaf(mv, rj.z, z.z);
+    tri += j + 1;
   }
+  __syncwarp();  // sR is rewritten for the warp's next block
   return z;
 }
 
@@ -215,6 +222,7 @@ __device__ __forceinline__ V3 applyBlockInv(const float* __restrict__ sInv, V3 r
 __global__ void __launch_bounds__(kThreads, 4) k_pcg_start(PcgWork w, float* __restrict__ partials) {
   __shared__ float smem[6 * 32];
   __shared__ __align__(16) float sInv[kPcgWarps][kInvFloats];
+  __shared__ float4 sR[kPcgWarps][32];
   int lane = threadIdx.x & 31;
   uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
   float acc[6] = {0, 0, 0, 0, 0, 0};
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_start(PcgWork w, float* __r
     issueBlockInv(sInv[threadIdx.x >> 5], w.blockInv + meta.x, m, lane);
     V3 r = v3(0.0f, 0.0f, 0.0f);
     if (node >= 0) r = v3(w.r[node]);
-    V3 z = applyBlockInv(sInv[threadIdx.x >> 5], r, lane, m);
+    V3 z = applyBlockInv(sInv[threadIdx.x >> 5], sR[threadIdx.x >> 5], r, lane, m);
     if (node >= 0) {
       w.z[node] = f4(z, 0.0f);
       acc[0] += r.x * z.x; acc[1] += r.y * z.y; acc[2] += r.z * z.z;
@@ -254,148 +262,82 @@ __global__ void k_pcg_check(float* __restrict__ scalars, int* __restrict__ flag,
   if (conv) flag[0] = 1;
 }
 
-// (A) w = A z as a CSR-stream product over host-built row batches (system.h), then locally beta = rz_new / rz_old ; p = z + beta p ;
-// ap = w + beta ap (A p by recurrence: A (z + beta p) = A z + beta A p) ; partial p.ap.  Every CTA first
-// re-evaluates the convergence test of the previous iteration from the same partials, so they all agree.
-// The solve is for the correction delta with an fp64 start residual, so only a few digits are asked of
-// this recurrence.
+// (A) w = A z, then locally beta = rz_new / rz_old ; p = z + beta p ; ap = w + beta ap (A p by recurrence:
+// A (z + beta p) = A z + beta A p) ; partial p.ap.  Every CTA first re-evaluates the convergence test of the
+// previous iteration from the same partials, so they all agree.  The solve is for the correction delta with an
+// fp64 start residual, so only a few digits are asked of this recurrence.
 //
-// A = S + C_t is streamed as two CSR segments per row batch: the batch's slice of S (built once per topology) and
-// its slice of the substep's collision matrix (detect.cu, k_ccsr_fill), concatenated into one virtual entry range.
-// The (col, val) pairs of a CTA's NEXT batch are staged into shared memory with cp.async while the current batch
-// is processed (double buffer), so the only exposed latency per batch is the gather of z.
-constexpr int kSpmvTile = 2048;  // == HostSystem::kBatchNnz: entries of one row batch per pass
-// Shared-memory slot of tile entry o: one pad word per 32 entries.  The per-row sums read runs of ~8 consecutive
-// entries per thread (stride ~8 between lanes), which would hit 4 banks 8 ways; padded, stride 8 is conflict-free.
-constexpr int kSpmvSlots = kSpmvTile + kSpmvTile / 32;
-__device__ __forceinline__ int spmvSlot(int o) { return o + (o >> 5); }
-
-struct SpmvBatch { uint32_t r0, r1; int e0, nA, f0, total; };
-
-__device__ __forceinline__ SpmvBatch loadBatch(const CsrMatrix& A, const int* __restrict__ cPtr, uint32_t b) {
-  SpmvBatch m;
-  m.r0 = A.rowBatch[b]; m.r1 = A.rowBatch[b + 1];
-  m.e0 = A.rowPtr[m.r0]; m.nA = A.rowPtr[m.r1] - m.e0;
-  m.f0 = 0; m.total = m.nA;
-  if (cPtr) { m.f0 = cPtr[m.r0]; m.total += cPtr[m.r1] - m.f0; }
-  return m;
-}
-
-__device__ __forceinline__ void cpAsync4(void* smemDst, const void* gmemSrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc) : "memory");
-}
-
-// virtual entries [cs, min(total, cs + tile)) of batch m -> (sCol, sVal), one commit group
-__device__ __forceinline__ void stageEntries(int* sCol, float* sVal, const CsrMatrix& A, const ContactLists& c,
-                                             const SpmvBatch& m, int cs) {
-  const int ce = min(m.total, cs + kSpmvTile);
-  for (int v = cs + (int)threadIdx.x; v < ce; v += kThreads) {
-    const int* pc; const float* pv;
-    if (v < m.nA) { pc = A.col + m.e0 + v; pv = A.val + m.e0 + v; }
-    else { pc = c.cCol + m.f0 + (v - m.nA); pv = c.cVal + m.f0 + (v - m.nA); }
-    cpAsync4(sCol + spmvSlot(v - cs), pc);
-    cpAsync4(sVal + spmvSlot(v - cs), pv);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-__global__ void __launch_bounds__(kThreads, 4) k_pcg_spmv(CsrMatrix A, ContactLists c, PcgWork w, float* __restrict__ partials,
-                                                          int parity, int first, float tol2) {
+// A = S + C_t.  S is read from its sliced-ELLPACK copy (system.h): one warp per slice of 32 rows, lane = row, entry k
+// of every lane in one coalesced 128 B load, all loads of a slice independent (no staging, no barriers).  The
+// substep's collision matrix follows as a short per-row CSR segment (detect.cu, k_ccsr_fill) plus its diagonal.
+// Per row the sum runs in CSR order: S entries, collision entries, collision diagonal.
+__global__ void __launch_bounds__(kThreads) k_pcg_spmv(CsrMatrix A, ContactLists c, PcgWork w, float* __restrict__ partials,
+                                                       int parity, int first, float tol2) {
   __shared__ float smem[128];
-  __shared__ __align__(16) int sCol[2][kSpmvSlots];    // staged columns; overwritten in place by the y-products
-  __shared__ __align__(16) float sVal[2][kSpmvSlots];  // staged values; overwritten in place by the x-products
-  __shared__ float sZ[kSpmvSlots];                     // z-products
   if (ctaConverged(w.flag)) return;
-  // the first batch's entries do not depend on the scalars: start their copy before reading those
-  const uint32_t nB = A.nBatches;
-  uint32_t b = blockIdx.x;
-  SpmvBatch cur{}, nxt{};
-  if (b < nB) { cur = loadBatch(A, c.cPtr, b); stageEntries(sCol[0], sVal[0], A, c, cur, 0); }
-  if (b + gridDim.x < nB) nxt = loadBatch(A, c.cPtr, b + gridDim.x);
   float rzNew[3], rzOld[3], rr[3], bb[3], beta[3] = {0.0f, 0.0f, 0.0f};
   const int prevSet = parity ? kSet0 : kSet1, olderSet = parity ? kSet1 : kSet0;
   readSums3(w.scalars, prevSet, rzNew);  // r.z and r.r written by the previous update (or start)
   readSums3(w.scalars, prevSet + 3, rr);
   readSums3(w.scalars, kBB, bb);
-  if (rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2]) {  // the update latches the flag
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    return;
-  }
+  if (rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2]) return;  // the update latches the flag
   if (!first) {
     readSums3(w.scalars, olderSet, rzOld);
 #pragma unroll
     for (int k = 0; k < 3; ++k) beta[k] = rzOld[k] > 0.0f ? rzNew[k] / rzOld[k] : 0.0f;
   }
   const float4* __restrict__ z = w.z;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
   float pap[3] = {0.0f, 0.0f, 0.0f};
-  int buf = 0;
-  for (; b < nB; b += gridDim.x) {
-    // next batch: its entries go to the other buffer now, the batch after it is described for the next round
-    const bool pre = b + gridDim.x < nB;
-    if (pre) stageEntries(sCol[buf ^ 1], sVal[buf ^ 1], A, c, nxt, 0);
-    SpmvBatch nn{};
-    if (b + 2u * gridDim.x < nB) nn = loadBatch(A, c.cPtr, b + 2u * gridDim.x);
-    const uint32_t row = cur.r0 + threadIdx.x;
-    const bool haveRow = row < cur.r1;
-    int rb = 0, re = 0, cb = 0, cf = 0;
+  for (uint32_t sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sl < A.nSlices; sl += warpsPerGrid) {
+    const uint32_t base = A.sellPtr[sl];
+    const int len = (int)((A.sellPtr[sl + 1] - base) >> 5);
+    const uint32_t row = A.sellRow[sl * 32u + lane];
+    const bool haveRow = row != 0xffffffffu;
+    int cb = 0, cf = 0;
     float dg = 0.0f;
     float4 zi = make_float4(0.0f, 0.0f, 0.0f, 0.0f), po = zi, apo = zi;
     if (haveRow) {
-      rb = A.rowPtr[row] - cur.e0; re = A.rowPtr[row + 1] - cur.e0;
-      if (c.cPtr) { cb = cur.nA + c.cPtr[row] - cur.f0; cf = cur.nA + c.cPtr[row + 1] - cur.f0; }
+      if (c.cPtr) { cb = c.cPtr[row]; cf = c.cPtr[row + 1]; }
       if (c.cDiag) dg = c.cDiag[row];
       zi = z[row];
       if (!first) { po = w.p[row]; apo = w.ap[row]; }
     }
-    if (pre) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+    const int* __restrict__ pc = A.sellCol + base + lane;
+    const float* __restrict__ pv = A.sellVal + base + lane;
     V3 y = v3(0.0f, 0.0f, 0.0f);
-    for (int cs = 0; cs < cur.total; cs += kSpmvTile) {  // one pass unless the batch overflows the tile
-      if (cs > 0) {
-        stageEntries(sCol[buf], sVal[buf], A, c, cur, cs);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-      }
-      const int cnt = min(cur.total - cs, kSpmvTile);
-      int* pcol = sCol[buf];
-      float* px = sVal[buf];
-      float* py = reinterpret_cast<float*>(sCol[buf]);
-      // gather z and park the products (four independent gathers in flight per thread)
-      for (int o = (int)threadIdx.x; o < cnt; o += 4 * kThreads) {
-        const bool h1 = o + kThreads < cnt, h2 = o + 2 * kThreads < cnt, h3 = o + 3 * kThreads < cnt;
-        const int s0 = spmvSlot(o), s1 = spmvSlot(o + kThreads), s2 = spmvSlot(o + 2 * kThreads), s3 = spmvSlot(o + 3 * kThreads);
-        int c0 = pcol[s0], c1 = 0, c2 = 0, c3 = 0;
-        float a0 = px[s0], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-        if (h1) { c1 = pcol[s1]; a1 = px[s1]; }
-        if (h2) { c2 = pcol[s2]; a2 = px[s2]; }
-        if (h3) { c3 = pcol[s3]; a3 = px[s3]; }
-        const float4 x0 = __ldg(z + c0), x1 = __ldg(z + c1), x2 = __ldg(z + c2), x3 = __ldg(z + c3);
-        px[s0] = a0 * x0.x; py[s0] = a0 * x0.y; sZ[s0] = a0 * x0.z;
-        if (h1) { px[s1] = a1 * x1.x; py[s1] = a1 * x1.y; sZ[s1] = a1 * x1.z; }
-        if (h2) { px[s2] = a2 * x2.x; py[s2] = a2 * x2.y; sZ[s2] = a2 * x2.z; }
-        if (h3) { px[s3] = a3 * x3.x; py[s3] = a3 * x3.y; sZ[s3] = a3 * x3.z; }
-      }
-      __syncthreads();
-      if (haveRow) {  // per-row sums in CSR order: the S segment, then the collision segment
-        const int ce = cs + cnt;
-        for (int k = max(rb, cs); k < min(re, ce); ++k) { const int sl = spmvSlot(k - cs); y.x += px[sl]; y.y += py[sl]; y.z += sZ[sl]; }
-        for (int k = max(cb, cs); k < min(cf, ce); ++k) { const int sl = spmvSlot(k - cs); y.x += px[sl]; y.y += py[sl]; y.z += sZ[sl]; }
-      }
-      __syncthreads();
+    int k = 0;
+    for (; k + 4 <= len; k += 4) {
+      const int c0 = __ldcs(pc + 32 * k), c1 = __ldcs(pc + 32 * (k + 1)), c2 = __ldcs(pc + 32 * (k + 2)), c3 = __ldcs(pc + 32 * (k + 3));
+      const float a0 = __ldcs(pv + 32 * k), a1 = __ldcs(pv + 32 * (k + 1)), a2 = __ldcs(pv + 32 * (k + 2)), a3 = __ldcs(pv + 32 * (k + 3));
+      const float4 x0 = __ldg(z + c0), x1 = __ldg(z + c1), x2 = __ldg(z + c2), x3 = __ldg(z + c3);
+      y.x = fmaf(a0, x0.x, y.x); y.y = fmaf(a0, x0.y, y.y); y.z = fmaf(a0, x0.z, y.z);
+      y.x = fmaf(a1, x1.x, y.x); y.y = fmaf(a1, x1.y, y.y); y.z = fmaf(a1, x1.z, y.z);
+      y.x = fmaf(a2, x2.x, y.x); y.y = fmaf(a2, x2.y, y.y); y.z = fmaf(a2, x2.z, y.z);
+      y.x = fmaf(a3, x3.x, y.x); y.y = fmaf(a3, x3.y, y.y); y.z = fmaf(a3, x3.z, y.z);
     }
-    if (haveRow) {
-      y.x = fmaf(dg, zi.x, y.x); y.y = fmaf(dg, zi.y, y.y); y.z = fmaf(dg, zi.z, y.z);
-      V3 pi = v3(zi);
-      if (!first) {
-        pi = v3(fmaf(beta[0], po.x, zi.x), fmaf(beta[1], po.y, zi.y), fmaf(beta[2], po.z, zi.z));
-        y = v3(fmaf(beta[0], apo.x, y.x), fmaf(beta[1], apo.y, y.y), fmaf(beta[2], apo.z, y.z));
-      }
-      w.p[row] = f4(pi, 0.0f);
-      w.ap[row] = f4(y, 0.0f);
-      pap[0] += pi.x * y.x; pap[1] += pi.y * y.y; pap[2] += pi.z * y.z;
+    for (; k < len; ++k) {
+      const int c0 = __ldcs(pc + 32 * k);
+      const float a0 = __ldcs(pv + 32 * k);
+      const float4 x0 = __ldg(z + c0);
+      y.x = fmaf(a0, x0.x, y.x); y.y = fmaf(a0, x0.y, y.y); y.z = fmaf(a0, x0.z, y.z);
     }
-    cur = nxt; nxt = nn; buf ^= 1;
+    if (!haveRow) continue;
+    for (int e = cb; e < cf; ++e) {
+      const float a0 = c.cVal[e];
+      const float4 x0 = __ldg(z + c.cCol[e]);
+      y.x = fmaf(a0, x0.x, y.x); y.y = fmaf(a0, x0.y, y.y); y.z = fmaf(a0, x0.z, y.z);
+    }
+    y.x = fmaf(dg, zi.x, y.x); y.y = fmaf(dg, zi.y, y.y); y.z = fmaf(dg, zi.z, y.z);
+    V3 pi = v3(zi);
+    if (!first) {
+      pi = v3(fmaf(beta[0], po.x, zi.x), fmaf(beta[1], po.y, zi.y), fmaf(beta[2], po.z, zi.z));
+      y = v3(fmaf(beta[0], apo.x, y.x), fmaf(beta[1], apo.y, y.y), fmaf(beta[2], apo.z, y.z));
+    }
+    w.p[row] = f4(pi, 0.0f);
+    w.ap[row] = f4(y, 0.0f);
+    pap[0] += pi.x * y.x; pap[1] += pi.y * y.y; pap[2] += pi.z * y.z;
   }
   blockSum<3>(pap, smem);
   if (threadIdx.x == 0) {
@@ -411,6 +353,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_update(PcgWork w, float4* _
                                                          int parity, float tol2) {
   __shared__ float smem[6 * 32];
   __shared__ __align__(16) float sInv[kPcgWarps][kInvFloats];
+  __shared__ float4 sR[kPcgWarps][32];
   if (ctaConverged(w.flag)) return;
   float rz[3], pap[3], alpha[3], rr[3], bb[3];
   const int prevSet = parity ? kSet0 : kSet1, mySet = parity ? kSet1 : kSet0;
@@ -455,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_update(PcgWork w, float4* _
       x[node] = xv;
       w.r[node] = f4(r, 0.0f);
     }
-    V3 z = applyBlockInv(sInv[threadIdx.x >> 5], r, lane, m);
+    V3 z = applyBlockInv(sInv[threadIdx.x >> 5], sR[threadIdx.x >> 5], r, lane, m);
     if (node >= 0) {
       w.z[node] = f4(z, 0.0f);
       acc[0] += r.x * z.x; acc[1] += r.y * z.y; acc[2] += r.z * z.z;
@@ -482,7 +425,10 @@ int launchPcgInit(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, con
 
 // One CG iteration = two kernels.  `it` = iteration index within the solve.
 int launchPcgSpmv(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, float tol, int it) {
-  k_pcg_spmv<<<kReduceBlocks, kThreads, 0, s>>>(A, c, w, w.partials, it & 1, it == 0 ? 1 : 0, tol * tol);
+  // one warp per slice while the partials buffer allows it (the grid is fixed per topology => fixed-order reduction)
+  const int grid = (int)std::min<uint32_t>((A.nSlices + kPcgWarps - 1) / kPcgWarps, (uint32_t)kMaxReduceBlocks);
+  if (grid <= 0) return 0;
+  k_pcg_spmv<<<grid, kThreads, 0, s>>>(A, c, w, w.partials, it & 1, it == 0 ? 1 : 0, tol * tol);
   return 1;
 }
 

@@ -213,19 +213,40 @@ void buildSystem(const HostScene& sc, float h, HostSystem& out, unsigned threads
   rawCol.clear(); rawCol.shrink_to_fit();
   rawVal.clear(); rawVal.shrink_to_fit();
 
-  // ---- 3b. row batches for the CSR-stream mat-vec ---------------------------------------------------
-  out.rowBatch.clear();
-  out.rowBatch.push_back(0);
+  // ---- 3b. sliced ELLPACK copy for the CG mat-vec -----------------------------------------------------
   {
-    uint32_t first = 0;
-    for (uint32_t r = 0; r < n; ++r) {
-      uint32_t nnzIfAdded = (uint32_t)(out.rowPtr[r + 1] - out.rowPtr[first]);
-      if (r > first && (nnzIfAdded > HostSystem::kBatchNnz || r - first >= HostSystem::kBatchRows)) {
-        out.rowBatch.push_back(r);
-        first = r;
+    const uint32_t nSlices = (n + 31u) / 32u;
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    auto len = [&](uint32_t r) { return (uint32_t)(out.rowPtr[r + 1] - out.rowPtr[r]); };
+    for (uint32_t w0 = 0; w0 < n; w0 += HostSystem::kSellWindow) {
+      uint32_t w1 = std::min(n, w0 + HostSystem::kSellWindow);
+      std::stable_sort(order.begin() + w0, order.begin() + w1, [&](uint32_t a, uint32_t b) { return len(a) > len(b); });
+    }
+    out.sellPtr.assign(nSlices + 1, 0);
+    out.sellRow.assign((size_t)nSlices * 32, 0xffffffffu);
+    for (uint32_t sl = 0; sl < nSlices; ++sl) {
+      uint32_t longest = 0;
+      for (uint32_t l = 0; l < 32 && sl * 32 + l < n; ++l) {
+        out.sellRow[(size_t)sl * 32 + l] = order[sl * 32 + l];
+        longest = std::max(longest, len(order[sl * 32 + l]));
+      }
+      out.sellPtr[sl + 1] = out.sellPtr[sl] + 32u * longest;
+    }
+    out.sellCol.assign(out.sellPtr[nSlices], 0);
+    out.sellVal.assign(out.sellPtr[nSlices], 0.0f);
+    for (uint32_t sl = 0; sl < nSlices; ++sl) {
+      const uint32_t longest = (out.sellPtr[sl + 1] - out.sellPtr[sl]) / 32u;
+      for (uint32_t l = 0; l < 32; ++l) {
+        const uint32_t r = out.sellRow[(size_t)sl * 32 + l];
+        const uint32_t m = r == 0xffffffffu ? 0u : len(r);
+        for (uint32_t k = 0; k < longest; ++k) {
+          const size_t idx = (size_t)out.sellPtr[sl] + 32u * k + l;
+          if (k < m) { out.sellCol[idx] = out.col[out.rowPtr[r] + k]; out.sellVal[idx] = out.val[out.rowPtr[r] + k]; }
+          else out.sellCol[idx] = r == 0xffffffffu ? 0 : (int)r;
+        }
       }
     }
-    if (n) out.rowBatch.push_back(n);
   }
 
   // ---- 4. block-Jacobi preconditioner: blocks of <= 32 nodes following connectivity ------------------

@@ -26,11 +26,15 @@ struct HostSystem {
   std::vector<int> rowPtr, col;
   std::vector<float> val;
 
-  // Row batches for the CG mat-vec (CSR-stream): consecutive rows whose non-zeros fit one shared-memory
-  // tile (<= kBatchNnz entries, <= kBatchRows rows).  A CTA streams a batch's (col, val) pairs fully coalesced,
-  // parks the products in shared memory and then sums them per row in CSR order.
-  std::vector<uint32_t> rowBatch;             // nBatches + 1 first rows
-  static constexpr uint32_t kBatchNnz = 2048, kBatchRows = 256;
+  // The same matrix for the CG mat-vec, sliced ELLPACK (SELL-32-sigma): rows are sorted by length inside windows of
+  // kSellWindow consecutive rows, cut into slices of 32 (one warp), every slice padded to its longest row and stored
+  // column-major, so lane l reads entry k of its row at sellPtr[s] + 32 k + l: coalesced, no staging, no divergence.
+  // Entries of a row keep their CSR order.
+  std::vector<uint32_t> sellPtr;              // nSlices + 1 element offsets (multiples of 32)
+  std::vector<uint32_t> sellRow;              // 32 per slice, 0xffffffff = padding lane
+  std::vector<int> sellCol;                   // padded entries: column = the row itself, value = 0
+  std::vector<float> sellVal;
+  static constexpr uint32_t kSellWindow = 1024;
 
   // block-Jacobi preconditioner
   uint32_t nBlocks = 0;
