@@ -245,13 +245,21 @@ def main():
     s.setState(snap[0], snap[1], snap[2])
     hp, hv, hq = snap
     e2e_proj = 0
+    e2e_parts = {"h2d_state": 0.0, "tick": 0.0, "d2h_vertices": 0.0, "d2h_state": 0.0}
     barrier()
     t0 = time.time()
     for _ in range(args.steps):
+        ta = time.time()
         s.setState(hp, hv, hq)          # H2D: 3 x 12 B per node from pinned memory
+        tb = time.time()
         tick()
+        tc = time.time()
         s.getVertices(copy=False)       # the reference-facing readback: D2H 12 B per node into the Vertex mirror
+        td = time.time()
         s.getState(hp, hv, hq)          # D2H of the full state into the same host buffers
+        te = time.time()
+        e2e_parts["h2d_state"] += tb - ta; e2e_parts["tick"] += tc - tb
+        e2e_parts["d2h_vertices"] += td - tc; e2e_parts["d2h_state"] += te - td
         e2e_proj += projections()
     barrier()
     e2e_s = time.time() - t0
@@ -306,7 +314,8 @@ def main():
             "substeps_per_s": args.steps / (dev_ms_max * 1e-3),
             "wall_ms_per_step": wall_ms_max / args.steps,
             "e2e": {"value": e2e_proj_all / e.item(), "unit": "projections/s", "h2d_bytes_per_step": int(36 * n_all),
-                    "d2h_bytes_per_step": int(48 * n_all), "ms_per_step": 1e3 * e.item() / args.steps},
+                    "d2h_bytes_per_step": int(48 * n_all), "ms_per_step": 1e3 * e.item() / args.steps,
+                    "breakdown_ms_rank0": {k: 1e3 * v / args.steps for k, v in e2e_parts.items()}},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": roofs[dominant],

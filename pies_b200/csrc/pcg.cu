@@ -205,14 +205,15 @@ __device__ __forceinline__ V3 applyBlockInv(const float* __restrict__ sInv, floa
   __syncwarp();
   V3 z = v3(0.0f, 0.0f, 0.0f);
   const int col = lane < m ? lane : 0;
-  const int colBase = col * (col + 1) / 2;
-  int tri = 0;
+  // entry (j, col) of the packed lower triangle: row `col` up to the diagonal (consecutive), then column `col`
+  // downwards (stride j + 1)
+  int off = col * (col + 1) / 2;
 #pragma unroll 4
   for (int j = 0; j < m; ++j) {
-    const float mv = sInv[j >= col ? tri + col : colBase + j];
+    const float mv = sInv[off];
     const float4 rj = sR[j];
     z.x = fmaf(mv, rj.x, z.x); z.y = fmaf(mv, rj.y, z.y); z.z = fmaf(mv, rj.z, z.z);
-    tri += j + 1;
+    off += j < col ? 1 : j + 1;
   }
   __syncwarp();  // sR is rewritten for the warp's next block
   return z;
@@ -267,77 +268,168 @@ __global__ void k_pcg_check(float* __restrict__ scalars, int* __restrict__ flag,
 // previous iteration from the same partials, so they all agree.  The solve is for the correction delta with an
 // fp64 start residual, so only a few digits are asked of this recurrence.
 //
-// A = S + C_t.  S is read from its sliced-ELLPACK copy (system.h): one warp per slice of 32 rows, lane = row, entry k
-// of every lane in one coalesced 128 B load, all loads of a slice independent (no staging, no barriers).  The
-// substep's collision matrix follows as a short per-row CSR segment (detect.cu, k_ccsr_fill) plus its diagonal.
-// Per row the sum runs in CSR order: S entries, collision entries, collision diagonal.
-__global__ void __launch_bounds__(kThreads) k_pcg_spmv(CsrMatrix A, ContactLists c, PcgWork w, float* __restrict__ partials,
-                                                       int parity, int first, float tol2) {
+// A = S + C_t, processed in windows of 256 consecutive rows (one CTA step, one warp per 32-row slice):
+//   * S comes from its sliced-ELLPACK copy (system.h; rows sorted by length inside the window, slices padded and
+//     column-major, so lane l finds entry k of its row at 32 k + l: conflict-free, no divergence);
+//   * C_t, the substep's collision matrix, is the window's slice of the contact CSR (detect.cu, k_ccsr_fill) plus the
+//     per-node diagonal;
+//   * z of the window's own rows is staged too: for a body-ordered mesh almost every column of a row lies inside the
+//     window, so the gather runs from shared memory; other columns fall back to a global load.
+// Everything a window needs ((col, val) of both matrices, z) is copied by cp.async into one of two buffers while the
+// previous window is computed, so the only exposed global latency is the first window's.  Per row the sum runs in
+// CSR order: S entries, collision entries, collision diagonal.
+constexpr int kWinRows = 256;    // == HostSystem::kSellWindow
+constexpr int kWinTile = 3072;   // staged S entries per window (27-node bodies: ~2 250); the rest is read from global
+constexpr int kWinCTile = 768;   // staged collision entries per window
+constexpr int kSpmvCtasPerSm = 3;
+constexpr size_t kSpmvSmem = 2 * ((size_t)(kWinTile + kWinCTile) * 8 + (size_t)kWinRows * 16);
+
+struct SpmvWindow { uint32_t base, cnt; int cbase, ccnt; };  // S entries [base, base + cnt), collision entries [cbase, cbase + ccnt)
+
+__device__ __forceinline__ SpmvWindow loadWindow(const CsrMatrix& A, const int* __restrict__ cPtr, uint32_t wdw) {
+  SpmvWindow m;
+  const uint32_t s0 = wdw * (kWinRows / 32), s1 = min(A.nSlices, s0 + kWinRows / 32);
+  m.base = A.sellPtr[s0]; m.cnt = A.sellPtr[s1] - m.base;
+  m.cbase = 0; m.ccnt = 0;
+  if (cPtr) {
+    const uint32_t r0 = wdw * kWinRows, r1 = min(A.n, r0 + kWinRows);
+    m.cbase = cPtr[r0]; m.ccnt = cPtr[r1] - m.cbase;
+  }
+  return m;
+}
+
+__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cpAsync4(void* smemDst, const void* gmemSrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc) : "memory");
+}
+
+struct SpmvBuffers { int* col; float* val; int* ccol; float* cval; float4* z; };
+__device__ __forceinline__ SpmvBuffers spmvBuffers(unsigned char* smemBase, int which) {
+  unsigned char* p = smemBase + (size_t)which * (kSpmvSmem / 2);
+  SpmvBuffers b;
+  b.z = reinterpret_cast<float4*>(p); p += (size_t)kWinRows * 16;
+  b.col = reinterpret_cast<int*>(p); p += (size_t)kWinTile * 4;
+  b.val = reinterpret_cast<float*>(p); p += (size_t)kWinTile * 4;
+  b.ccol = reinterpret_cast<int*>(p); p += (size_t)kWinCTile * 4;
+  b.cval = reinterpret_cast<float*>(p);
+  return b;
+}
+
+// one commit group: the window's S entries (16 B granules: slices are 128 B aligned), its collision entries (4 B: a
+// CSR slice starts anywhere) and z of its rows
+__device__ __forceinline__ void stageWindow(const SpmvBuffers& b, const CsrMatrix& A, const ContactLists& c,
+                                            const float4* __restrict__ z, const SpmvWindow& m, uint32_t wdw) {
+  const uint32_t cnt = min(m.cnt, (uint32_t)kWinTile);
+  for (uint32_t i = 4u * threadIdx.x; i < cnt; i += 4u * kThreads) {
+    cpAsync16(b.col + i, A.sellCol + m.base + i);
+    cpAsync16(b.val + i, A.sellVal + m.base + i);
+  }
+  const int ccnt = min(m.ccnt, kWinCTile);
+  for (int i = (int)threadIdx.x; i < ccnt; i += kThreads) {
+    cpAsync4(b.ccol + i, c.cCol + m.cbase + i);
+    cpAsync4(b.cval + i, c.cVal + m.cbase + i);
+  }
+  const uint32_t row = wdw * kWinRows + threadIdx.x;
+  if (row < A.n) cpAsync16(b.z + threadIdx.x, z + row);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix A, ContactLists c, PcgWork w,
+                                                                       float* __restrict__ partials, int parity, int first,
+                                                                       float tol2) {
+  extern __shared__ __align__(16) unsigned char spmvSmem[];
   __shared__ float smem[128];
-  if (ctaConverged(w.flag)) return;
+  const float4* __restrict__ z = w.z;
+  const uint32_t nWin = (A.n + kWinRows - 1) / kWinRows;
+  uint32_t wdw = blockIdx.x;
+  // the first window does not depend on the scalars: start its copy before looking at them
+  SpmvWindow cur{}, nxt{};
+  if (wdw < nWin) { cur = loadWindow(A, c.cPtr, wdw); stageWindow(spmvBuffers(spmvSmem, 0), A, c, z, cur, wdw); }
+  if (wdw + gridDim.x < nWin) nxt = loadWindow(A, c.cPtr, wdw + gridDim.x);
+  // convergence state: every thread reads the same words (no barrier, one round trip)
   float rzNew[3], rzOld[3], rr[3], bb[3], beta[3] = {0.0f, 0.0f, 0.0f};
   const int prevSet = parity ? kSet0 : kSet1, olderSet = parity ? kSet1 : kSet0;
+  const int done = *(volatile const int*)w.flag;
   readSums3(w.scalars, prevSet, rzNew);  // r.z and r.r written by the previous update (or start)
   readSums3(w.scalars, prevSet + 3, rr);
   readSums3(w.scalars, kBB, bb);
-  if (rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2]) return;  // the update latches the flag
+  if (!first) readSums3(w.scalars, olderSet, rzOld);
+  if (done || (rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2])) {  // the update latches the flag
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    return;
+  }
   if (!first) {
-    readSums3(w.scalars, olderSet, rzOld);
 #pragma unroll
     for (int k = 0; k < 3; ++k) beta[k] = rzOld[k] > 0.0f ? rzNew[k] / rzOld[k] : 0.0f;
   }
-  const float4* __restrict__ z = w.z;
-  const int lane = threadIdx.x & 31;
-  const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float pap[3] = {0.0f, 0.0f, 0.0f};
-  for (uint32_t sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sl < A.nSlices; sl += warpsPerGrid) {
-    const uint32_t base = A.sellPtr[sl];
-    const int len = (int)((A.sellPtr[sl + 1] - base) >> 5);
-    const uint32_t row = A.sellRow[sl * 32u + lane];
-    const bool haveRow = row != 0xffffffffu;
-    int cb = 0, cf = 0;
+  int buf = 0;
+  for (; wdw < nWin; wdw += gridDim.x) {
+    const bool pre = wdw + gridDim.x < nWin;
+    if (pre) stageWindow(spmvBuffers(spmvSmem, buf ^ 1), A, c, z, nxt, wdw + gridDim.x);
+    SpmvWindow nn{};
+    if (wdw + 2u * gridDim.x < nWin) nn = loadWindow(A, c.cPtr, wdw + 2u * gridDim.x);
+    const SpmvBuffers sb = spmvBuffers(spmvSmem, buf);
+    const uint32_t sl = wdw * (kWinRows / 32) + warp;
+    const bool haveSlice = sl < A.nSlices;
+    const int row0 = (int)(wdw * kWinRows);
+    uint32_t row = 0xffffffffu, sbase = 0;
+    int len = 0, cb = 0, cf = 0;
     float dg = 0.0f;
-    float4 zi = make_float4(0.0f, 0.0f, 0.0f, 0.0f), po = zi, apo = zi;
+    float4 po = make_float4(0.0f, 0.0f, 0.0f, 0.0f), apo = po;
+    if (haveSlice) {
+      sbase = A.sellPtr[sl];
+      len = (int)((A.sellPtr[sl + 1] - sbase) >> 5);
+      sbase -= cur.base;
+      row = A.sellRow[sl * 32u + lane];
+    }
+    const bool haveRow = row != 0xffffffffu;
     if (haveRow) {
-      if (c.cPtr) { cb = c.cPtr[row]; cf = c.cPtr[row + 1]; }
+      if (c.cPtr) { cb = c.cPtr[row] - cur.cbase; cf = c.cPtr[row + 1] - cur.cbase; }
       if (c.cDiag) dg = c.cDiag[row];
-      zi = z[row];
       if (!first) { po = w.p[row]; apo = w.ap[row]; }
     }
-    const int* __restrict__ pc = A.sellCol + base + lane;
-    const float* __restrict__ pv = A.sellVal + base + lane;
+    if (pre) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
     V3 y = v3(0.0f, 0.0f, 0.0f);
-    int k = 0;
-    for (; k + 4 <= len; k += 4) {
-      const int c0 = __ldcs(pc + 32 * k), c1 = __ldcs(pc + 32 * (k + 1)), c2 = __ldcs(pc + 32 * (k + 2)), c3 = __ldcs(pc + 32 * (k + 3));
-      const float a0 = __ldcs(pv + 32 * k), a1 = __ldcs(pv + 32 * (k + 1)), a2 = __ldcs(pv + 32 * (k + 2)), a3 = __ldcs(pv + 32 * (k + 3));
-      const float4 x0 = __ldg(z + c0), x1 = __ldg(z + c1), x2 = __ldg(z + c2), x3 = __ldg(z + c3);
-      y.x = fmaf(a0, x0.x, y.x); y.y = fmaf(a0, x0.y, y.y); y.z = fmaf(a0, x0.z, y.z);
-      y.x = fmaf(a1, x1.x, y.x); y.y = fmaf(a1, x1.y, y.y); y.z = fmaf(a1, x1.z, y.z);
-      y.x = fmaf(a2, x2.x, y.x); y.y = fmaf(a2, x2.y, y.y); y.z = fmaf(a2, x2.z, y.z);
-      y.x = fmaf(a3, x3.x, y.x); y.y = fmaf(a3, x3.y, y.y); y.z = fmaf(a3, x3.z, y.z);
+    // S: entry k of this lane's row sits at sbase + 32 k + lane of the window's block
+#pragma unroll 4
+    for (int k = 0; k < len; ++k) {
+      const uint32_t o = sbase + 32u * k + lane;
+      int cc; float a;
+      if (o < (uint32_t)kWinTile) { cc = sb.col[o]; a = sb.val[o]; }
+      else { cc = __ldcs(A.sellCol + cur.base + o); a = __ldcs(A.sellVal + cur.base + o); }
+      const uint32_t loc = (uint32_t)(cc - row0);
+      const float4 x = loc < (uint32_t)kWinRows ? sb.z[loc] : __ldg(z + cc);
+      y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z);
     }
-    for (; k < len; ++k) {
-      const int c0 = __ldcs(pc + 32 * k);
-      const float a0 = __ldcs(pv + 32 * k);
-      const float4 x0 = __ldg(z + c0);
-      y.x = fmaf(a0, x0.x, y.x); y.y = fmaf(a0, x0.y, y.y); y.z = fmaf(a0, x0.z, y.z);
+    if (haveRow) {
+      // C_t: the row's entries inside the window's collision slice
+      for (int e = cb; e < cf; ++e) {
+        int cc; float a;
+        if (e < kWinCTile) { cc = sb.ccol[e]; a = sb.cval[e]; }
+        else { cc = c.cCol[cur.cbase + e]; a = c.cVal[cur.cbase + e]; }
+        const uint32_t loc = (uint32_t)(cc - row0);
+        const float4 x = loc < (uint32_t)kWinRows ? sb.z[loc] : __ldg(z + cc);
+        y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z);
+      }
+      const float4 zi = sb.z[row - (uint32_t)row0];
+      y.x = fmaf(dg, zi.x, y.x); y.y = fmaf(dg, zi.y, y.y); y.z = fmaf(dg, zi.z, y.z);
+      V3 pi = v3(zi);
+      if (!first) {
+        pi = v3(fmaf(beta[0], po.x, zi.x), fmaf(beta[1], po.y, zi.y), fmaf(beta[2], po.z, zi.z));
+        y = v3(fmaf(beta[0], apo.x, y.x), fmaf(beta[1], apo.y, y.y), fmaf(beta[2], apo.z, y.z));
+      }
+      w.p[row] = f4(pi, 0.0f);
+      w.ap[row] = f4(y, 0.0f);
+      pap[0] += pi.x * y.x; pap[1] += pi.y * y.y; pap[2] += pi.z * y.z;
     }
-    if (!haveRow) continue;
-    for (int e = cb; e < cf; ++e) {
-      const float a0 = c.cVal[e];
-      const float4 x0 = __ldg(z + c.cCol[e]);
-      y.x = fmaf(a0, x0.x, y.x); y.y = fmaf(a0, x0.y, y.y); y.z = fmaf(a0, x0.z, y.z);
-    }
-    y.x = fmaf(dg, zi.x, y.x); y.y = fmaf(dg, zi.y, y.y); y.z = fmaf(dg, zi.z, y.z);
-    V3 pi = v3(zi);
-    if (!first) {
-      pi = v3(fmaf(beta[0], po.x, zi.x), fmaf(beta[1], po.y, zi.y), fmaf(beta[2], po.z, zi.z));
-      y = v3(fmaf(beta[0], apo.x, y.x), fmaf(beta[1], apo.y, y.y), fmaf(beta[2], apo.z, y.z));
-    }
-    w.p[row] = f4(pi, 0.0f);
-    w.ap[row] = f4(y, 0.0f);
-    pap[0] += pi.x * y.x; pap[1] += pi.y * y.y; pap[2] += pi.z * y.z;
+    __syncthreads();  // this buffer is refilled by the next round's prefetch
+    cur = nxt; nxt = nn; buf ^= 1;
   }
   blockSum<3>(pap, smem);
   if (threadIdx.x == 0) {
@@ -425,10 +517,12 @@ int launchPcgInit(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, con
 
 // One CG iteration = two kernels.  `it` = iteration index within the solve.
 int launchPcgSpmv(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, float tol, int it) {
-  // one warp per slice while the partials buffer allows it (the grid is fixed per topology => fixed-order reduction)
-  const int grid = (int)std::min<uint32_t>((A.nSlices + kPcgWarps - 1) / kPcgWarps, (uint32_t)kMaxReduceBlocks);
+  // > 48 KB of dynamic shared memory needs the opt-in (a per-device function attribute: renewed once per solve)
+  if (it == 0) cudaFuncSetAttribute(k_pcg_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmem);
+  const uint32_t nWin = (A.n + kWinRows - 1) / kWinRows;
+  const int grid = (int)std::min<uint32_t>(nWin, (uint32_t)(kNumSMs * kSpmvCtasPerSm));  // fixed per topology => fixed-order reduction
   if (grid <= 0) return 0;
-  k_pcg_spmv<<<grid, kThreads, 0, s>>>(A, c, w, w.partials, it & 1, it == 0 ? 1 : 0, tol * tol);
+  k_pcg_spmv<<<grid, kThreads, kSpmvSmem, s>>>(A, c, w, w.partials, it & 1, it == 0 ? 1 : 0, tol * tol);
   return 1;
 }
 

@@ -34,7 +34,7 @@ struct HostSystem {
   std::vector<uint32_t> sellRow;              // 32 per slice, 0xffffffff = padding lane
   std::vector<int> sellCol;                   // padded entries: column = the row itself, value = 0
   std::vector<float> sellVal;
-  static constexpr uint32_t kSellWindow = 1024;
+  static constexpr uint32_t kSellWindow = 256;   // == rows one CTA of k_pcg_spmv stages per step (pcg.cu kWinRows)
 
   // block-Jacobi preconditioner
   uint32_t nBlocks = 0;
