@@ -200,6 +200,20 @@ int ensureBuilt(PiesB200Solver* s) {
   PIES_CHECK(s, uploadVec(s->sellCol, y.sellCol, st)); PIES_CHECK(s, uploadVec(s->sellVal, y.sellVal, st));
   PIES_CHECK(s, uploadVec(s->blockNodes, y.blockNodes, st)); PIES_CHECK(s, uploadVec(s->blockInv, y.blockInv, st));
   PIES_CHECK(s, uploadVec(s->triIds, sc.triangles, st));
+  {
+    // The per-substep collision buffers (detect.cu, reblock.cu, contact.cu) first appear, and later grow, in the middle
+    // of a run; growing the stream-ordered pool there costs tens of milliseconds in one tick.  Reserve the pool once
+    // per topology instead: allocate and free a block sized for a contact-rich substep (the pool keeps freed memory,
+    // capi.cpp sets its release threshold to "never").
+    size_t freeB = 0, totalB = 0;
+    if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+      size_t want = std::max<size_t>(256ull << 20, 3072ull * sc.triCount() + 1024ull * n);
+      want = std::min(want, freeB / 4);
+      void* warm = nullptr;
+      if (want && cudaMallocAsync(&warm, want, st) == cudaSuccess) cudaFreeAsync(warm, st);
+    }
+    cudaGetLastError();
+  }
   PIES_CHECK(s, cudaStreamSynchronize(st));
   s->builtVersion = sc.topologyVersion;
   s->hostStateDirty = false;

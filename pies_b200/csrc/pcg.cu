@@ -336,18 +336,33 @@ __device__ __forceinline__ void stageWindow(const SpmvBuffers& b, const CsrMatri
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+struct SpmvSlice { uint32_t sbase; int len; uint32_t row; };  // a warp's slice: first entry (absolute), padded length, lane's row
+__device__ __forceinline__ SpmvSlice loadSlice(const CsrMatrix& A, uint32_t wdw, int warp, int lane) {
+  SpmvSlice m{0u, 0, 0xffffffffu};
+  const uint32_t sl = wdw * (kWinRows / 32) + warp;
+  if (sl < A.nSlices) {
+    m.sbase = A.sellPtr[sl];
+    m.len = (int)((A.sellPtr[sl + 1] - m.sbase) >> 5);
+    m.row = A.sellRow[sl * 32u + lane];
+  }
+  return m;
+}
+
 __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix A, ContactLists c, PcgWork w,
                                                                        float* __restrict__ partials, int parity, int first,
                                                                        float tol2) {
   extern __shared__ __align__(16) unsigned char spmvSmem[];
   __shared__ float smem[128];
+  __shared__ float sPz[kWinCTile];  // z-products of the window's collision entries (x- and y-products reuse the staged slots)
   const float4* __restrict__ z = w.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t nWin = (A.n + kWinRows - 1) / kWinRows;
   uint32_t wdw = blockIdx.x;
   // the first window does not depend on the scalars: start its copy before looking at them
   SpmvWindow cur{}, nxt{};
-  if (wdw < nWin) { cur = loadWindow(A, c.cPtr, wdw); stageWindow(spmvBuffers(spmvSmem, 0), A, c, z, cur, wdw); }
-  if (wdw + gridDim.x < nWin) nxt = loadWindow(A, c.cPtr, wdw + gridDim.x);
+  SpmvSlice sc{0u, 0, 0xffffffffu}, sn = sc;
+  if (wdw < nWin) { cur = loadWindow(A, c.cPtr, wdw); stageWindow(spmvBuffers(spmvSmem, 0), A, c, z, cur, wdw); sc = loadSlice(A, wdw, warp, lane); }
+  if (wdw + gridDim.x < nWin) { nxt = loadWindow(A, c.cPtr, wdw + gridDim.x); sn = loadSlice(A, wdw + gridDim.x, warp, lane); }
   // convergence state: every thread reads the same words (no barrier, one round trip)
   float rzNew[3], rzOld[3], rr[3], bb[3], beta[3] = {0.0f, 0.0f, 0.0f};
   const int prevSet = parity ? kSet0 : kSet1, olderSet = parity ? kSet1 : kSet0;
@@ -364,30 +379,25 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
 #pragma unroll
     for (int k = 0; k < 3; ++k) beta[k] = rzOld[k] > 0.0f ? rzNew[k] / rzOld[k] : 0.0f;
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float pap[3] = {0.0f, 0.0f, 0.0f};
   int buf = 0;
   for (; wdw < nWin; wdw += gridDim.x) {
     const bool pre = wdw + gridDim.x < nWin;
     if (pre) stageWindow(spmvBuffers(spmvSmem, buf ^ 1), A, c, z, nxt, wdw + gridDim.x);
+    // descriptions two windows ahead (consumed by the next round's prefetch), this round's per-row words
     SpmvWindow nn{};
-    if (wdw + 2u * gridDim.x < nWin) nn = loadWindow(A, c.cPtr, wdw + 2u * gridDim.x);
+    SpmvSlice snn{0u, 0, 0xffffffffu};
+    if (wdw + 2u * gridDim.x < nWin) { nn = loadWindow(A, c.cPtr, wdw + 2u * gridDim.x); snn = loadSlice(A, wdw + 2u * gridDim.x, warp, lane); }
     const SpmvBuffers sb = spmvBuffers(spmvSmem, buf);
-    const uint32_t sl = wdw * (kWinRows / 32) + warp;
-    const bool haveSlice = sl < A.nSlices;
     const int row0 = (int)(wdw * kWinRows);
-    uint32_t row = 0xffffffffu, sbase = 0;
-    int len = 0, cb = 0, cf = 0;
+    const uint32_t row = sc.row;
+    const bool haveRow = row != 0xffffffffu;
+    const uint32_t sbase = sc.sbase - cur.base;
+    const int len = sc.len;
+    int cb = 0, cf = 0;
     float dg = 0.0f;
     float4 po = make_float4(0.0f, 0.0f, 0.0f, 0.0f), apo = po;
-    if (haveSlice) {
-      sbase = A.sellPtr[sl];
-      len = (int)((A.sellPtr[sl + 1] - sbase) >> 5);
-      sbase -= cur.base;
-      row = A.sellRow[sl * 32u + lane];
-    }
-    const bool haveRow = row != 0xffffffffu;
-    if (haveRow) {
+    if (haveRow) {  // consumed after the S loop
       if (c.cPtr) { cb = c.cPtr[row] - cur.cbase; cf = c.cPtr[row + 1] - cur.cbase; }
       if (c.cDiag) dg = c.cDiag[row];
       if (!first) { po = w.p[row]; apo = w.ap[row]; }
@@ -395,8 +405,24 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
     if (pre) asm volatile("cp.async.wait_group 1;" ::: "memory");
     else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    V3 y = v3(0.0f, 0.0f, 0.0f);
+    // C_t, cooperative part: every thread gathers z for up to three staged collision entries of the window (contacts
+    // couple different bodies, so these columns are mostly outside the window: all gathers of the CTA fly together
+    // and land while the S loop runs)
+    const int ccnt = min(cur.ccnt, kWinCTile);
+    float ca[3]; float4 cx[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int e = (int)threadIdx.x + j * kThreads;
+      ca[j] = 0.0f; cx[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (e < ccnt) {
+        const int cc = sb.ccol[e];
+        ca[j] = sb.cval[e];
+        const uint32_t loc = (uint32_t)(cc - row0);
+        cx[j] = loc < (uint32_t)kWinRows ? sb.z[loc] : __ldg(z + cc);
+      }
+    }
     // S: entry k of this lane's row sits at sbase + 32 k + lane of the window's block
+    V3 y = v3(0.0f, 0.0f, 0.0f);
 #pragma unroll 4
     for (int k = 0; k < len; ++k) {
       const uint32_t o = sbase + 32u * k + lane;
@@ -407,15 +433,27 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
       const float4 x = loc < (uint32_t)kWinRows ? sb.z[loc] : __ldg(z + cc);
       y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z);
     }
+    if (ccnt) {  // CTA-uniform
+      float* px = sb.cval;
+      float* py = reinterpret_cast<float*>(sb.ccol);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int e = (int)threadIdx.x + j * kThreads;
+        if (e < ccnt) { px[e] = ca[j] * cx[j].x; py[e] = ca[j] * cx[j].y; sPz[e] = ca[j] * cx[j].z; }
+      }
+      __syncthreads();
+    }
     if (haveRow) {
-      // C_t: the row's entries inside the window's collision slice
+      // C_t, per row: its products in CSR order (entries past the staged tile straight from global memory)
+      const float* px = sb.cval;
+      const float* py = reinterpret_cast<const float*>(sb.ccol);
       for (int e = cb; e < cf; ++e) {
-        int cc; float a;
-        if (e < kWinCTile) { cc = sb.ccol[e]; a = sb.cval[e]; }
-        else { cc = c.cCol[cur.cbase + e]; a = c.cVal[cur.cbase + e]; }
-        const uint32_t loc = (uint32_t)(cc - row0);
-        const float4 x = loc < (uint32_t)kWinRows ? sb.z[loc] : __ldg(z + cc);
-        y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z);
+        if (e < kWinCTile) { y.x += px[e]; y.y += py[e]; y.z += sPz[e]; }
+        else {
+          const float a = c.cVal[cur.cbase + e];
+          const float4 x = __ldg(z + c.cCol[cur.cbase + e]);
+          y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z);
+        }
       }
       const float4 zi = sb.z[row - (uint32_t)row0];
       y.x = fmaf(dg, zi.x, y.x); y.y = fmaf(dg, zi.y, y.y); y.z = fmaf(dg, zi.z, y.z);
@@ -428,8 +466,8 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
       w.ap[row] = f4(y, 0.0f);
       pap[0] += pi.x * y.x; pap[1] += pi.y * y.y; pap[2] += pi.z * y.z;
     }
-    __syncthreads();  // this buffer is refilled by the next round's prefetch
-    cur = nxt; nxt = nn; buf ^= 1;
+    __syncthreads();  // this buffer (and sPz) is refilled by the next round
+    cur = nxt; nxt = nn; sc = sn; sn = snn; buf ^= 1;
   }
   blockSum<3>(pap, smem);
   if (threadIdx.x == 0) {

@@ -3,7 +3,7 @@
 # usage: scripts/gpu_quick.sh <tag>     (outputs under gpurun_out/<tag>/)
 TAG=${1:-run}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > $OUT/memcheck.log 2>&1; echo "memcheck exit $?" | tee -a $OUT/memcheck.log
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest exit $?" | tee -a $OUT/pytest.log
+timeout 900 python -m pytest tests -m gpu -x -q $PYTEST_ARGS > $OUT/pytest.log 2>&1; echo "pytest exit $?" | tee -a $OUT/pytest.log
 timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
 TICKS=${TIMELINE_TICKS:-125} timeout 600 python scripts/dev_s3.py > $OUT/timeline.log 2>&1
 SKIP=${PROF_SKIP:-60} TICKS=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
