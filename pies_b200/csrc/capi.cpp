@@ -302,6 +302,13 @@ static int getVec(PiesB200Solver* s, int which, float* out) {
   if (!s || !out) return PIES_B200_EINVAL;
   return guarded(s, [&]() {
     cudaSetDevice(s->device);
+    if (s->deviceNewer && s->n && s->builtVersion == s->scene.topologyVersion && s->n == s->scene.nodeCount()) {
+      // the live copy is on the device: one pack kernel + one DMA straight into the caller's buffer (no detour through
+      // the host scene, whose copy stays marked stale)
+      pies::g_allocStream = s->stream;
+      const float4* src = which == 0 ? s->q.p : which == 1 ? s->prev.p : s->vel.p;
+      return pies::downloadVec3(s, src, out);
+    }
     int rc = pies::downloadState(s);
     if (rc) return rc;
     const std::vector<float>& v = which == 0 ? s->scene.pos : which == 1 ? s->scene.prev : s->scene.vel;

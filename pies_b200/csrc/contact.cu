@@ -589,4 +589,22 @@ int launchFriction(cudaStream_t s, ContactWork& w, const ContactLists& c, uint32
   return L;
 }
 
+// Loads this file's kernels now (CUDA loads a kernel lazily at its first launch; for the collision kernels that
+// would be the first contact tick of a run, ~1 ms each in the middle of the simulation).
+void preloadContactKernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_pt_project);
+  cudaFuncGetAttributes(&a, k_floor_project);
+  cudaFuncGetAttributes(&a, k_gather_contacts);
+  cudaFuncGetAttributes(&a, k_gs_dataflow<StabilizeOp>);
+  cudaFuncGetAttributes(&a, k_gs_dataflow<FrictionOp>);
+  cudaFuncGetAttributes(&a, k_entry_keys);
+  cudaFuncGetAttributes(&a, k_gs_cluster_stabilize);
+  cudaFuncGetAttributes(&a, k_gs_cluster_friction);
+  cudaFuncGetAttributes(&a, k_gs_mid<true>);
+  cudaFuncGetAttributes(&a, k_gs_mid<false>);
+  cudaFuncGetAttributes(&a, k_floor_snap);
+  cudaFuncGetAttributes(&a, k_floor_friction);
+}
+
 }  // namespace pies

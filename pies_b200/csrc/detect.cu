@@ -568,4 +568,28 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
   return 0;
 }
 
+// Loads this file's kernels now (CUDA loads a kernel lazily at its first launch; for the collision kernels that
+// would be the first contact tick of a run, ~1 ms each in the middle of the simulation).
+void preloadDetectKernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_tri_ranges);
+  cudaFuncGetAttributes(&a, k_floor_write);
+  cudaFuncGetAttributes(&a, k_emit_pairs);
+  cudaFuncGetAttributes(&a, k_mark_heads);
+  cudaFuncGetAttributes(&a, k_cell_starts);
+  cudaFuncGetAttributes(&a, k_pair_filter<false>);
+  cudaFuncGetAttributes(&a, k_pair_filter<true>);
+  cudaFuncGetAttributes(&a, k_ccd);
+  cudaFuncGetAttributes(&a, k_compact_hits);
+  cudaFuncGetAttributes(&a, k_inc_emit);
+  cudaFuncGetAttributes(&a, k_floor_mult);
+  cudaFuncGetAttributes(&a, k_floor_weight);
+  cudaFuncGetAttributes(&a, k_uniq_keys);
+  cudaFuncGetAttributes(&a, k_uniq_gather);
+  cudaFuncGetAttributes(&a, k_ccsr_count);
+  cudaFuncGetAttributes(&a, k_ccsr_fill);
+  cudaFuncGetAttributes(&a, k_inc_tickets);
+  cudaFuncGetAttributes(&a, k_init_bbox);
+}
+
 }  // namespace pies

@@ -200,6 +200,7 @@ int ensureBuilt(PiesB200Solver* s) {
   PIES_CHECK(s, uploadVec(s->sellCol, y.sellCol, st)); PIES_CHECK(s, uploadVec(s->sellVal, y.sellVal, st));
   PIES_CHECK(s, uploadVec(s->blockNodes, y.blockNodes, st)); PIES_CHECK(s, uploadVec(s->blockInv, y.blockInv, st));
   PIES_CHECK(s, uploadVec(s->triIds, sc.triangles, st));
+  preloadDetectKernels(); preloadContactKernels(); preloadReblockKernels(); preloadSortKernels(); preloadPcgKernels();
   {
     // The per-substep collision buffers (detect.cu, reblock.cu, contact.cu) first appear, and later grow, in the middle
     // of a run; growing the stream-ordered pool there costs tens of milliseconds in one tick.  Reserve the pool once
@@ -238,7 +239,20 @@ int refreshVertexMirror(PiesB200Solver* s) {
   PIES_CHECK(s, cudaStreamSynchronize(s->stream));
   PiesB200Vertex* v = s->scene.vertices.data();
   const float* p = s->hostPacked;
-  for (uint32_t i = 0; i < n; ++i) { v[i].position[0] = p[3 * i]; v[i].position[1] = p[3 * i + 1]; v[i].position[2] = p[3 * i + 2]; }
+  auto scatter = [v, p](uint32_t i0, uint32_t i1) {
+    for (uint32_t i = i0; i < i1; ++i) { v[i].position[0] = p[3 * i]; v[i].position[1] = p[3 * i + 1]; v[i].position[2] = p[3 * i + 2]; }
+  };
+  // 36 B-stride writes: memory bound on one core for large scenes, so split the range over a few threads
+  const unsigned T = n >= (1u << 17) ? std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1u;
+  if (T > 1) {
+    std::vector<std::thread> pool;
+    const uint32_t chunk = (n + T - 1) / T;
+    for (unsigned t = 1; t < T; ++t) pool.emplace_back(scatter, std::min(n, t * chunk), std::min(n, (t + 1) * chunk));
+    scatter(0, std::min(n, chunk));
+    for (auto& th : pool) th.join();
+  } else {
+    scatter(0, n);
+  }
   s->mirrorStale = false;
   return PIES_B200_OK;
 }

@@ -112,6 +112,7 @@ int failCuda(PiesB200Solver* s, cudaError_t e, const char* what, int line);
 int fail(PiesB200Solver* s, int code, const char* msg);
 int ensureBuilt(PiesB200Solver* s);
 int downloadState(PiesB200Solver* s);  // device -> scene.pos/prev/vel
+int downloadVec3(PiesB200Solver* s, const float4* src, float* dstXYZ);  // one device plane -> packed xyz in the caller's (pinned or pageable) buffer
 int tickPD(PiesB200Solver* s, bool refreshMirror);
 int pdTickBegin(PiesB200Solver* s);
 int pdSubstepBegin(PiesB200Solver* s);

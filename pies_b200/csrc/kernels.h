@@ -119,4 +119,12 @@ size_t sortHistBytes(uint64_t n);
 int launchSortPairs(cudaStream_t s, uint64_t n, uint64_t* keys, uint32_t* vals, uint64_t* tmpKeys,
                     uint32_t* tmpVals, void* hist, int keyBits);
 
+// ------------------------------------------------------------- preload -----
+// Force-load every kernel of a file (no lazy loading in the middle of a run).
+void preloadDetectKernels();
+void preloadContactKernels();
+void preloadReblockKernels();
+void preloadSortKernels();
+void preloadPcgKernels();
+
 }  // namespace pies

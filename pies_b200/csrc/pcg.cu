@@ -279,24 +279,26 @@ __global__ void k_pcg_check(float* __restrict__ scalars, int* __restrict__ flag,
 // previous window is computed, so the only exposed global latency is the first window's.  Per row the sum runs in
 // CSR order: S entries, collision entries, collision diagonal.
 constexpr int kWinRows = 256;    // == HostSystem::kSellWindow
-constexpr int kWinTile = 3072;   // staged S entries per window (27-node bodies: ~2 250); the rest is read from global
-constexpr int kWinCTile = 768;   // staged collision entries per window
+constexpr int kWinSlices = kWinRows / 32;
+constexpr int kWinTile = 2816;   // staged S entries per window (27-node bodies: ~2 260); the rest is read from global
+constexpr int kWinCTile = 768;   // staged collision entries per window (three per thread)
 constexpr int kSpmvCtasPerSm = 3;
-constexpr size_t kSpmvSmem = 2 * ((size_t)(kWinTile + kWinCTile) * 8 + (size_t)kWinRows * 16);
+constexpr int kWinDescs = 64;    // windows of one CTA described per round (more: the pipeline drains and restarts)
+
+// one staging buffer; everything the window's rows need except p / ap
+struct SpmvBuf {
+  float4 z[kWinRows];
+  int col[kWinTile]; float val[kWinTile];
+  int ccol[kWinCTile]; float cval[kWinCTile];
+  uint32_t sellRow[kWinRows];
+  int cPtr[kWinRows + 4];
+  float cDiag[kWinRows];
+  uint32_t sellPtr[kWinSlices + 4];
+};
+constexpr size_t kSpmvSmem = 2 * sizeof(SpmvBuf);
+static_assert(sizeof(SpmvBuf) % 16 == 0, "buffer halves stay 16 B aligned");
 
 struct SpmvWindow { uint32_t base, cnt; int cbase, ccnt; };  // S entries [base, base + cnt), collision entries [cbase, cbase + ccnt)
-
-__device__ __forceinline__ SpmvWindow loadWindow(const CsrMatrix& A, const int* __restrict__ cPtr, uint32_t wdw) {
-  SpmvWindow m;
-  const uint32_t s0 = wdw * (kWinRows / 32), s1 = min(A.nSlices, s0 + kWinRows / 32);
-  m.base = A.sellPtr[s0]; m.cnt = A.sellPtr[s1] - m.base;
-  m.cbase = 0; m.ccnt = 0;
-  if (cPtr) {
-    const uint32_t r0 = wdw * kWinRows, r1 = min(A.n, r0 + kWinRows);
-    m.cbase = cPtr[r0]; m.ccnt = cPtr[r1] - m.cbase;
-  }
-  return m;
-}
 
 __device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc) : "memory");
@@ -305,47 +307,33 @@ __device__ __forceinline__ void cpAsync4(void* smemDst, const void* gmemSrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc) : "memory");
 }
 
-struct SpmvBuffers { int* col; float* val; int* ccol; float* cval; float4* z; };
-__device__ __forceinline__ SpmvBuffers spmvBuffers(unsigned char* smemBase, int which) {
-  unsigned char* p = smemBase + (size_t)which * (kSpmvSmem / 2);
-  SpmvBuffers b;
-  b.z = reinterpret_cast<float4*>(p); p += (size_t)kWinRows * 16;
-  b.col = reinterpret_cast<int*>(p); p += (size_t)kWinTile * 4;
-  b.val = reinterpret_cast<float*>(p); p += (size_t)kWinTile * 4;
-  b.ccol = reinterpret_cast<int*>(p); p += (size_t)kWinCTile * 4;
-  b.cval = reinterpret_cast<float*>(p);
-  return b;
-}
-
-// one commit group: the window's S entries (16 B granules: slices are 128 B aligned), its collision entries (4 B: a
-// CSR slice starts anywhere) and z of its rows
-__device__ __forceinline__ void stageWindow(const SpmvBuffers& b, const CsrMatrix& A, const ContactLists& c,
+// One commit group with everything of window `wdw`: S entries (16 B granules: slices are 128 B aligned), collision
+// entries (4 B: a CSR slice starts anywhere), z / sellRow / cDiag / cPtr of its rows, its slice offsets.  No register
+// ever depends on the copied words, so nothing waits before the matching cp.async.wait_group.
+__device__ __forceinline__ void stageWindow(SpmvBuf& b, const CsrMatrix& A, const ContactLists& c,
                                             const float4* __restrict__ z, const SpmvWindow& m, uint32_t wdw) {
+  const uint32_t t = threadIdx.x;
   const uint32_t cnt = min(m.cnt, (uint32_t)kWinTile);
-  for (uint32_t i = 4u * threadIdx.x; i < cnt; i += 4u * kThreads) {
+  for (uint32_t i = 4u * t; i < cnt; i += 4u * kThreads) {
     cpAsync16(b.col + i, A.sellCol + m.base + i);
     cpAsync16(b.val + i, A.sellVal + m.base + i);
   }
   const int ccnt = min(m.ccnt, kWinCTile);
-  for (int i = (int)threadIdx.x; i < ccnt; i += kThreads) {
+  for (int i = (int)t; i < ccnt; i += kThreads) {
     cpAsync4(b.ccol + i, c.cCol + m.cbase + i);
     cpAsync4(b.cval + i, c.cVal + m.cbase + i);
   }
-  const uint32_t row = wdw * kWinRows + threadIdx.x;
-  if (row < A.n) cpAsync16(b.z + threadIdx.x, z + row);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-struct SpmvSlice { uint32_t sbase; int len; uint32_t row; };  // a warp's slice: first entry (absolute), padded length, lane's row
-__device__ __forceinline__ SpmvSlice loadSlice(const CsrMatrix& A, uint32_t wdw, int warp, int lane) {
-  SpmvSlice m{0u, 0, 0xffffffffu};
-  const uint32_t sl = wdw * (kWinRows / 32) + warp;
-  if (sl < A.nSlices) {
-    m.sbase = A.sellPtr[sl];
-    m.len = (int)((A.sellPtr[sl + 1] - m.sbase) >> 5);
-    m.row = A.sellRow[sl * 32u + lane];
+  const uint32_t r0 = wdw * kWinRows, row = r0 + t;
+  const uint32_t s0 = wdw * kWinSlices;
+  if (row < A.n) cpAsync16(b.z + t, z + row);
+  if (r0 + t < A.nSlices * 32u) cpAsync4(b.sellRow + t, A.sellRow + r0 + t);  // sellRow is padded to whole slices; the last window may end early
+  if (row < A.n) {
+    if (c.cDiag) cpAsync4(b.cDiag + t, c.cDiag + row);
+    if (c.cPtr) cpAsync4(b.cPtr + t, c.cPtr + row);
   }
-  return m;
+  if (t == 0 && c.cPtr) cpAsync4(b.cPtr + min((uint32_t)kWinRows, A.n - r0), c.cPtr + min(A.n, r0 + kWinRows));
+  if (t <= (uint32_t)kWinSlices && s0 + t <= A.nSlices) cpAsync4(b.sellPtr + t, A.sellPtr + s0 + t);
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix A, ContactLists c, PcgWork w,
@@ -354,15 +342,11 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
   extern __shared__ __align__(16) unsigned char spmvSmem[];
   __shared__ float smem[128];
   __shared__ float sPz[kWinCTile];  // z-products of the window's collision entries (x- and y-products reuse the staged slots)
+  __shared__ SpmvWindow sDesc[kWinDescs];
+  SpmvBuf* bufs = reinterpret_cast<SpmvBuf*>(spmvSmem);
   const float4* __restrict__ z = w.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t nWin = (A.n + kWinRows - 1) / kWinRows;
-  uint32_t wdw = blockIdx.x;
-  // the first window does not depend on the scalars: start its copy before looking at them
-  SpmvWindow cur{}, nxt{};
-  SpmvSlice sc{0u, 0, 0xffffffffu}, sn = sc;
-  if (wdw < nWin) { cur = loadWindow(A, c.cPtr, wdw); stageWindow(spmvBuffers(spmvSmem, 0), A, c, z, cur, wdw); sc = loadSlice(A, wdw, warp, lane); }
-  if (wdw + gridDim.x < nWin) { nxt = loadWindow(A, c.cPtr, wdw + gridDim.x); sn = loadSlice(A, wdw + gridDim.x, warp, lane); }
   // convergence state: every thread reads the same words (no barrier, one round trip)
   float rzNew[3], rzOld[3], rr[3], bb[3], beta[3] = {0.0f, 0.0f, 0.0f};
   const int prevSet = parity ? kSet0 : kSet1, olderSet = parity ? kSet1 : kSet0;
@@ -371,103 +355,118 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
   readSums3(w.scalars, prevSet + 3, rr);
   readSums3(w.scalars, kBB, bb);
   if (!first) readSums3(w.scalars, olderSet, rzOld);
-  if (done || (rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2])) {  // the update latches the flag
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    return;
-  }
+  if (done || (rr[0] <= tol2 * bb[0] && rr[1] <= tol2 * bb[1] && rr[2] <= tol2 * bb[2])) return;  // the update latches the flag
   if (!first) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) beta[k] = rzOld[k] > 0.0f ? rzNew[k] / rzOld[k] : 0.0f;
   }
   float pap[3] = {0.0f, 0.0f, 0.0f};
-  int buf = 0;
-  for (; wdw < nWin; wdw += gridDim.x) {
-    const bool pre = wdw + gridDim.x < nWin;
-    if (pre) stageWindow(spmvBuffers(spmvSmem, buf ^ 1), A, c, z, nxt, wdw + gridDim.x);
-    // descriptions two windows ahead (consumed by the next round's prefetch), this round's per-row words
-    SpmvWindow nn{};
-    SpmvSlice snn{0u, 0, 0xffffffffu};
-    if (wdw + 2u * gridDim.x < nWin) { nn = loadWindow(A, c.cPtr, wdw + 2u * gridDim.x); snn = loadSlice(A, wdw + 2u * gridDim.x, warp, lane); }
-    const SpmvBuffers sb = spmvBuffers(spmvSmem, buf);
-    const int row0 = (int)(wdw * kWinRows);
-    const uint32_t row = sc.row;
-    const bool haveRow = row != 0xffffffffu;
-    const uint32_t sbase = sc.sbase - cur.base;
-    const int len = sc.len;
-    int cb = 0, cf = 0;
-    float dg = 0.0f;
-    float4 po = make_float4(0.0f, 0.0f, 0.0f, 0.0f), apo = po;
-    if (haveRow) {  // consumed after the S loop
-      if (c.cPtr) { cb = c.cPtr[row] - cur.cbase; cf = c.cPtr[row + 1] - cur.cbase; }
-      if (c.cDiag) dg = c.cDiag[row];
-      if (!first) { po = w.p[row]; apo = w.ap[row]; }
-    }
-    if (pre) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    // C_t, cooperative part: every thread gathers z for up to three staged collision entries of the window (contacts
-    // couple different bodies, so these columns are mostly outside the window: all gathers of the CTA fly together
-    // and land while the S loop runs)
-    const int ccnt = min(cur.ccnt, kWinCTile);
-    float ca[3]; float4 cx[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int e = (int)threadIdx.x + j * kThreads;
-      ca[j] = 0.0f; cx[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if (e < ccnt) {
-        const int cc = sb.ccol[e];
-        ca[j] = sb.cval[e];
-        const uint32_t loc = (uint32_t)(cc - row0);
-        cx[j] = loc < (uint32_t)kWinRows ? sb.z[loc] : __ldg(z + cc);
+  // windows of this CTA: blockIdx.x, + gridDim.x, ...; described kWinDescs at a time
+  for (uint32_t first_w = blockIdx.x; first_w < nWin; first_w += (uint32_t)kWinDescs * gridDim.x) {
+    const uint32_t mine = min((uint32_t)kWinDescs, (nWin - first_w + gridDim.x - 1) / gridDim.x);
+    if (threadIdx.x < mine) {
+      const uint32_t wd = first_w + threadIdx.x * gridDim.x;
+      const uint32_t s0 = wd * kWinSlices, s1 = min(A.nSlices, s0 + kWinSlices);
+      SpmvWindow m;
+      m.base = A.sellPtr[s0]; m.cnt = A.sellPtr[s1] - m.base;
+      m.cbase = 0; m.ccnt = 0;
+      if (c.cPtr) {
+        const uint32_t r0 = wd * kWinRows, r1 = min(A.n, r0 + kWinRows);
+        m.cbase = c.cPtr[r0]; m.ccnt = c.cPtr[r1] - m.cbase;
       }
+      sDesc[threadIdx.x] = m;
     }
-    // S: entry k of this lane's row sits at sbase + 32 k + lane of the window's block
-    V3 y = v3(0.0f, 0.0f, 0.0f);
-#pragma unroll 4
-    for (int k = 0; k < len; ++k) {
-      const uint32_t o = sbase + 32u * k + lane;
-      int cc; float a;
-      if (o < (uint32_t)kWinTile) { cc = sb.col[o]; a = sb.val[o]; }
-      else { cc = __ldcs(A.sellCol + cur.base + o); a = __ldcs(A.sellVal + cur.base + o); }
-      const uint32_t loc = (uint32_t)(cc - row0);
-      const float4 x = loc < (uint32_t)kWinRows ? sb.z[loc] : __ldg(z + cc);
-      y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z);
-    }
-    if (ccnt) {  // CTA-uniform
-      float* px = sb.cval;
-      float* py = reinterpret_cast<float*>(sb.ccol);
+    __syncthreads();
+    stageWindow(bufs[0], A, c, z, sDesc[0], first_w);
+    for (uint32_t i = 0; i < mine; ++i) {
+      const uint32_t wdw = first_w + i * gridDim.x;
+      const bool pre = i + 1 < mine;
+      if (pre) stageWindow(bufs[(i + 1) & 1], A, c, z, sDesc[i + 1], wdw + gridDim.x);
+      SpmvBuf& sb = bufs[i & 1];
+      const SpmvWindow cur = sDesc[i];
+      if (pre) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      const int row0 = (int)(wdw * kWinRows);
+      const uint32_t sl = wdw * kWinSlices + warp;
+      const bool haveSlice = sl < A.nSlices;
+      const uint32_t row = haveSlice ? sb.sellRow[warp * 32 + lane] : 0xffffffffu;
+      const bool haveRow = row != 0xffffffffu;
+      // p / ap of the row: issued now, consumed after the loops
+      float4 po = make_float4(0.0f, 0.0f, 0.0f, 0.0f), apo = po;
+      if (haveRow && !first) { po = w.p[row]; apo = w.ap[row]; }
+      // C_t, cooperative part: every thread gathers z for up to three staged collision entries of the window (contacts
+      // couple different bodies, so these columns are mostly outside the window: all gathers of the CTA fly together
+      // and land while the S loop runs)
+      const int ccnt = min(cur.ccnt, kWinCTile);
+      float ca[3]; float4 cx[3];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const int e = (int)threadIdx.x + j * kThreads;
-        if (e < ccnt) { px[e] = ca[j] * cx[j].x; py[e] = ca[j] * cx[j].y; sPz[e] = ca[j] * cx[j].z; }
+        ca[j] = 0.0f; cx[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (e < ccnt) {
+          const int cc = sb.ccol[e];
+          ca[j] = sb.cval[e];
+          const uint32_t loc = (uint32_t)(cc - row0);
+          cx[j] = loc < (uint32_t)kWinRows ? sb.z[loc] : __ldg(z + cc);
+        }
       }
-      __syncthreads();
-    }
-    if (haveRow) {
-      // C_t, per row: its products in CSR order (entries past the staged tile straight from global memory)
-      const float* px = sb.cval;
-      const float* py = reinterpret_cast<const float*>(sb.ccol);
-      for (int e = cb; e < cf; ++e) {
-        if (e < kWinCTile) { y.x += px[e]; y.y += py[e]; y.z += sPz[e]; }
-        else {
-          const float a = c.cVal[cur.cbase + e];
-          const float4 x = __ldg(z + c.cCol[cur.cbase + e]);
+      // S: entry k of this lane's row sits at sbase + 32 k + lane of the window's block
+      V3 y = v3(0.0f, 0.0f, 0.0f);
+      if (haveSlice) {
+        const uint32_t sbase = sb.sellPtr[warp] - cur.base;
+        const int len = (int)((sb.sellPtr[warp + 1] - sb.sellPtr[warp]) >> 5);
+#pragma unroll 4
+        for (int k = 0; k < len; ++k) {
+          const uint32_t o = sbase + 32u * k + lane;
+          int cc; float a;
+          if (o < (uint32_t)kWinTile) { cc = sb.col[o]; a = sb.val[o]; }
+          else { cc = __ldcs(A.sellCol + cur.base + o); a = __ldcs(A.sellVal + cur.base + o); }
+          const uint32_t loc = (uint32_t)(cc - row0);
+          const float4 x = loc < (uint32_t)kWinRows ? sb.z[loc] : __ldg(z + cc);
           y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z);
         }
       }
-      const float4 zi = sb.z[row - (uint32_t)row0];
-      y.x = fmaf(dg, zi.x, y.x); y.y = fmaf(dg, zi.y, y.y); y.z = fmaf(dg, zi.z, y.z);
-      V3 pi = v3(zi);
-      if (!first) {
-        pi = v3(fmaf(beta[0], po.x, zi.x), fmaf(beta[1], po.y, zi.y), fmaf(beta[2], po.z, zi.z));
-        y = v3(fmaf(beta[0], apo.x, y.x), fmaf(beta[1], apo.y, y.y), fmaf(beta[2], apo.z, y.z));
+      if (ccnt) {  // CTA-uniform
+        float* px = sb.cval;
+        float* py = reinterpret_cast<float*>(sb.ccol);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int e = (int)threadIdx.x + j * kThreads;
+          if (e < ccnt) { px[e] = ca[j] * cx[j].x; py[e] = ca[j] * cx[j].y; sPz[e] = ca[j] * cx[j].z; }
+        }
+        __syncthreads();
       }
-      w.p[row] = f4(pi, 0.0f);
-      w.ap[row] = f4(y, 0.0f);
-      pap[0] += pi.x * y.x; pap[1] += pi.y * y.y; pap[2] += pi.z * y.z;
+      if (haveRow) {
+        const uint32_t lr = row - (uint32_t)row0;
+        // C_t, per row: its products in CSR order (entries past the staged tile straight from global memory)
+        if (c.cPtr) {
+          const float* px = sb.cval;
+          const float* py = reinterpret_cast<const float*>(sb.ccol);
+          const int cb = sb.cPtr[lr] - cur.cbase, cf = sb.cPtr[lr + 1] - cur.cbase;
+          for (int e = cb; e < cf; ++e) {
+            if (e < kWinCTile) { y.x += px[e]; y.y += py[e]; y.z += sPz[e]; }
+            else {
+              const float a = c.cVal[cur.cbase + e];
+              const float4 x = __ldg(z + c.cCol[cur.cbase + e]);
+              y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z);
+            }
+          }
+        }
+        const float dg = c.cDiag ? sb.cDiag[lr] : 0.0f;
+        const float4 zi = sb.z[lr];
+        y.x = fmaf(dg, zi.x, y.x); y.y = fmaf(dg, zi.y, y.y); y.z = fmaf(dg, zi.z, y.z);
+        V3 pi = v3(zi);
+        if (!first) {
+          pi = v3(fmaf(beta[0], po.x, zi.x), fmaf(beta[1], po.y, zi.y), fmaf(beta[2], po.z, zi.z));
+          y = v3(fmaf(beta[0], apo.x, y.x), fmaf(beta[1], apo.y, y.y), fmaf(beta[2], apo.z, y.z));
+        }
+        w.p[row] = f4(pi, 0.0f);
+        w.ap[row] = f4(y, 0.0f);
+        pap[0] += pi.x * y.x; pap[1] += pi.y * y.y; pap[2] += pi.z * y.z;
+      }
+      __syncthreads();  // this buffer (and sPz) is refilled by the next round
     }
-    __syncthreads();  // this buffer (and sPz) is refilled by the next round
-    cur = nxt; nxt = nn; sc = sn; sn = snn; buf ^= 1;
   }
   blockSum<3>(pap, smem);
   if (threadIdx.x == 0) {
@@ -582,6 +581,18 @@ int launchPcgCheck(cudaStream_t s, const PcgWork& w, float tol, int lastIt) {
 int launchPcgFinish(cudaStream_t s, const PcgWork& w, uint32_t n, float4* x) {
   k_pcg_finish<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(n, x, w.delta);
   return 1;
+}
+
+// Loads this file's kernels now (CUDA loads a kernel lazily at its first launch; for the collision kernels that
+// would be the first contact tick of a run, ~1 ms each in the middle of the simulation).
+void preloadPcgKernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_pcg_residual);
+  cudaFuncGetAttributes(&a, k_pcg_finish);
+  cudaFuncGetAttributes(&a, k_pcg_start);
+  cudaFuncGetAttributes(&a, k_pcg_check);
+  cudaFuncGetAttributes(&a, k_pcg_spmv);
+  cudaFuncGetAttributes(&a, k_pcg_update);
 }
 
 }  // namespace pies

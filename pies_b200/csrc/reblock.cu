@@ -369,4 +369,20 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   return 0;
 }
 
+// Loads this file's kernels now (CUDA loads a kernel lazily at its first launch; for the collision kernels that
+// would be the first contact tick of a run, ~1 ms each in the middle of the simulation).
+void preloadReblockKernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_touched_flags);
+  cudaFuncGetAttributes(&a, k_uf_unite);
+  cudaFuncGetAttributes(&a, k_touched_keys);
+  cudaFuncGetAttributes(&a, k_cluster_heads);
+  cudaFuncGetAttributes(&a, k_cluster_starts);
+  cudaFuncGetAttributes(&a, k_cluster_blocks);
+  cudaFuncGetAttributes(&a, k_assign_dynamic);
+  cudaFuncGetAttributes(&a, k_block_sizes);
+  cudaFuncGetAttributes(&a, k_static_membership);
+  cudaFuncGetAttributes(&a, k_block_factor);
+}
+
 }  // namespace pies

@@ -171,4 +171,14 @@ int launchSortPairs(cudaStream_t s, uint64_t n, uint64_t* keys, uint32_t* vals, 
   return launches;
 }
 
+// Loads this file's kernels now (CUDA loads a kernel lazily at its first launch; for the collision kernels that
+// would be the first contact tick of a run, ~1 ms each in the middle of the simulation).
+void preloadSortKernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_scan_tile);
+  cudaFuncGetAttributes(&a, k_scan_add);
+  cudaFuncGetAttributes(&a, k_sort_hist);
+  cudaFuncGetAttributes(&a, k_sort_scatter);
+}
+
 }  // namespace pies
