@@ -280,8 +280,8 @@ __global__ void k_pcg_check(float* __restrict__ scalars, int* __restrict__ flag,
 // CSR order: S entries, collision entries, collision diagonal.
 constexpr int kWinRows = 256;    // == HostSystem::kSellWindow
 constexpr int kWinSlices = kWinRows / 32;
-constexpr int kWinTile = 2816;   // staged S entries per window (27-node bodies: ~2 260); the rest is read from global
-constexpr int kWinCTile = 768;   // staged collision entries per window (three per thread)
+constexpr int kWinTile = 2432;   // staged S entries per window (27-node bodies: 2 336 with padding); the rest is read from global
+constexpr int kWinCTile = 512;   // staged collision entries per window (two per thread)
 constexpr int kSpmvCtasPerSm = 3;
 constexpr int kWinDescs = 64;    // windows of one CTA described per round (more: the pipeline drains and restarts)
 
@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
   extern __shared__ __align__(16) unsigned char spmvSmem[];
   __shared__ float smem[128];
   __shared__ float sPz[kWinCTile];  // z-products of the window's collision entries (x- and y-products reuse the staged slots)
+  __shared__ float sPzS[kWinTile];  // z-products of the window's S entries
   __shared__ SpmvWindow sDesc[kWinDescs];
   SpmvBuf* bufs = reinterpret_cast<SpmvBuf*>(spmvSmem);
   const float4* __restrict__ z = w.z;
@@ -395,13 +396,13 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
       // p / ap of the row: issued now, consumed after the loops
       float4 po = make_float4(0.0f, 0.0f, 0.0f, 0.0f), apo = po;
       if (haveRow && !first) { po = w.p[row]; apo = w.ap[row]; }
-      // C_t, cooperative part: every thread gathers z for up to three staged collision entries of the window (contacts
-      // couple different bodies, so these columns are mostly outside the window: all gathers of the CTA fly together
-      // and land while the S loop runs)
+      // Phase 1, balanced over the CTA: every thread turns staged entries into products a * z[col], in place (x over
+      // val, y over col, z into sPz / sPzS).  Collision entries first: contacts couple different bodies, so their
+      // columns are mostly outside the window and those global gathers should be in flight while the S tile runs.
       const int ccnt = min(cur.ccnt, kWinCTile);
-      float ca[3]; float4 cx[3];
+      float ca[2]; float4 cx[2];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
+      for (int j = 0; j < 2; ++j) {
         const int e = (int)threadIdx.x + j * kThreads;
         ca[j] = 0.0f; cx[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (e < ccnt) {
@@ -411,31 +412,51 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
           cx[j] = loc < (uint32_t)kWinRows ? sb.z[loc] : __ldg(z + cc);
         }
       }
-      // S: entry k of this lane's row sits at sbase + 32 k + lane of the window's block
+      {
+        const int scnt = (int)min(cur.cnt, (uint32_t)kWinTile);
+        float* px = sb.val;
+        float* py = reinterpret_cast<float*>(sb.col);
+#pragma unroll 2
+        for (int e = (int)threadIdx.x; e < scnt; e += kThreads) {
+          const int cc = sb.col[e];
+          const float a = sb.val[e];
+          const uint32_t loc = (uint32_t)(cc - row0);
+          float4 x;
+          if (loc < (uint32_t)kWinRows) x = sb.z[loc]; else x = __ldg(z + cc);
+          px[e] = a * x.x; py[e] = a * x.y; sPzS[e] = a * x.z;
+        }
+      }
+      if (ccnt) {
+        float* px = sb.cval;
+        float* py = reinterpret_cast<float*>(sb.ccol);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int e = (int)threadIdx.x + j * kThreads;
+          if (e < ccnt) { px[e] = ca[j] * cx[j].x; py[e] = ca[j] * cx[j].y; sPz[e] = ca[j] * cx[j].z; }
+        }
+      }
+      __syncthreads();
+      // Phase 2, one warp per slice: the row's products in CSR order; entry k of this lane's row sits at
+      // sbase + 32 k + lane of the window's block (conflict-free)
       V3 y = v3(0.0f, 0.0f, 0.0f);
       if (haveSlice) {
         const uint32_t sbase = sb.sellPtr[warp] - cur.base;
         const int len = (int)((sb.sellPtr[warp + 1] - sb.sellPtr[warp]) >> 5);
+        const float* px = sb.val;
+        const float* py = reinterpret_cast<const float*>(sb.col);
+        const int kIn = min(len, (int)(((uint32_t)kWinTile > sbase ? (uint32_t)kWinTile - sbase : 0u) >> 5));  // steps wholly inside the staged tile
 #pragma unroll 4
-        for (int k = 0; k < len; ++k) {
+        for (int k = 0; k < kIn; ++k) {
           const uint32_t o = sbase + 32u * k + lane;
-          int cc; float a;
-          if (o < (uint32_t)kWinTile) { cc = sb.col[o]; a = sb.val[o]; }
-          else { cc = __ldcs(A.sellCol + cur.base + o); a = __ldcs(A.sellVal + cur.base + o); }
-          const uint32_t loc = (uint32_t)(cc - row0);
-          const float4 x = loc < (uint32_t)kWinRows ? sb.z[loc] : __ldg(z + cc);
+          y.x += px[o]; y.y += py[o]; y.z += sPzS[o];
+        }
+        for (int k = kIn; k < len; ++k) {  // past the staged tile: straight from global memory
+          const uint32_t o = sbase + 32u * k + lane;
+          const int cc = __ldcs(A.sellCol + cur.base + o);
+          const float a = __ldcs(A.sellVal + cur.base + o);
+          const float4 x = __ldg(z + cc);
           y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z);
         }
-      }
-      if (ccnt) {  // CTA-uniform
-        float* px = sb.cval;
-        float* py = reinterpret_cast<float*>(sb.ccol);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int e = (int)threadIdx.x + j * kThreads;
-          if (e < ccnt) { px[e] = ca[j] * cx[j].x; py[e] = ca[j] * cx[j].y; sPz[e] = ca[j] * cx[j].z; }
-        }
-        __syncthreads();
       }
       if (haveRow) {
         const uint32_t lr = row - (uint32_t)row0;
