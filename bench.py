@@ -12,7 +12,7 @@ One "step" = one Solver::tick (one substep of 10 PD iterations + collision detec
            state (pos/prev/vel) from pinned host memory, ticks, and reads the state back.
 `cpu_baseline` / --impl reference: the unmodified reference (oracle/_ref) on the host cores, on a
            bounded sample of the same scene (6x6 columns x 21 layers = 756 bodies).
-`roofline`: the kernel with the largest share of the step (the CSR-stream SpMV of the global solve), algorithmic
+`roofline`: the kernel with the largest share of the step (the mat-vec of the global solve), algorithmic
            bytes / CUDA-event duration of sampled launches; the other hot kernels and the
            local step + RHS pair of the north_star target are reported next to it.
 Multi-GPU: weak scaling over x slabs (pies_b200/multigpu.py): `world` S3 stacks side by side, each rank owns one
@@ -281,7 +281,7 @@ def main():
         alg = {"tet": 112 * local_proj, "gather": 64 * local_proj + 40 * n, "spmv": 8 * nnz + 64 * n, "update": 72 * n}
         names = {"tet": "k_tet_elems (fused tet strain+volume projection: ids, Qinv, parameters in; 4 contributions out)",
                  "gather": "k_gather_rhs (CSR gather of the contributions into the right-hand side)",
-                 "spmv": "k_pcg_spmv (CSR-stream A z with p / Ap recurrences)",
+                 "spmv": "k_pcg_spmv (A z over SELL-32 windows staged by cp.async, with p / Ap recurrences)",
                  "update": "k_pcg_update (x, r update + packed block-Jacobi apply; the preconditioner stream is not in the SURVEY model)"}
         traffic = {}
         traffic_file = os.path.join(ROOT, "profiles", "kernel_traffic.json")
