@@ -60,6 +60,13 @@ __device__ __forceinline__ void readSums3(const float* __restrict__ scalars, int
   out[0] = scalars[kSums + slot]; out[1] = scalars[kSums + slot + 1]; out[2] = scalars[kSums + slot + 2];
 }
 
+// Programmatic dependent launch (the two kernels of a CG iteration are launched with the stream-serialisation
+// attribute): everything before pdlWait() may overlap the tail of the previous kernel, so it must only touch data
+// no kernel of the solve writes (matrix, block tables); pdlWait() returns once the previous grid has completed and
+// its writes are visible.  pdlLaunchDependents() lets the next kernel start its own independent prologue.
+__device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdlLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // CTA-uniform early exit once the solve has converged (lets the host enqueue a fixed
 // number of iterations without a sync; finished iterations cost one flag read).
 __device__ __forceinline__ bool ctaConverged(const int* flag) {
@@ -348,6 +355,27 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
   const float4* __restrict__ z = w.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t nWin = (A.n + kWinRows - 1) / kWinRows;
+  // descriptions of this CTA's first windows: static data, read while the previous kernel drains
+  auto describe = [&](uint32_t first_w) {
+    const uint32_t mine = min((uint32_t)kWinDescs, (nWin - first_w + gridDim.x - 1) / gridDim.x);
+    if (threadIdx.x < mine) {
+      const uint32_t wd = first_w + threadIdx.x * gridDim.x;
+      const uint32_t s0 = wd * kWinSlices, s1 = min(A.nSlices, s0 + kWinSlices);
+      SpmvWindow m;
+      m.base = A.sellPtr[s0]; m.cnt = A.sellPtr[s1] - m.base;
+      m.cbase = 0; m.ccnt = 0;
+      if (c.cPtr) {
+        const uint32_t r0 = wd * kWinRows, r1 = min(A.n, r0 + kWinRows);
+        m.cbase = c.cPtr[r0]; m.ccnt = c.cPtr[r1] - m.cbase;
+      }
+      sDesc[threadIdx.x] = m;
+    }
+    return mine;
+  };
+  uint32_t mineFirst = 0;
+  if (blockIdx.x < nWin) mineFirst = describe(blockIdx.x);
+  pdlWait();
+  pdlLaunchDependents();
   // convergence state: every thread reads the same words (no barrier, one round trip)
   float rzNew[3], rzOld[3], rr[3], bb[3], beta[3] = {0.0f, 0.0f, 0.0f};
   const int prevSet = parity ? kSet0 : kSet1, olderSet = parity ? kSet1 : kSet0;
@@ -364,19 +392,7 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
   float pap[3] = {0.0f, 0.0f, 0.0f};
   // windows of this CTA: blockIdx.x, + gridDim.x, ...; described kWinDescs at a time
   for (uint32_t first_w = blockIdx.x; first_w < nWin; first_w += (uint32_t)kWinDescs * gridDim.x) {
-    const uint32_t mine = min((uint32_t)kWinDescs, (nWin - first_w + gridDim.x - 1) / gridDim.x);
-    if (threadIdx.x < mine) {
-      const uint32_t wd = first_w + threadIdx.x * gridDim.x;
-      const uint32_t s0 = wd * kWinSlices, s1 = min(A.nSlices, s0 + kWinSlices);
-      SpmvWindow m;
-      m.base = A.sellPtr[s0]; m.cnt = A.sellPtr[s1] - m.base;
-      m.cbase = 0; m.ccnt = 0;
-      if (c.cPtr) {
-        const uint32_t r0 = wd * kWinRows, r1 = min(A.n, r0 + kWinRows);
-        m.cbase = c.cPtr[r0]; m.ccnt = c.cPtr[r1] - m.cbase;
-      }
-      sDesc[threadIdx.x] = m;
-    }
+    const uint32_t mine = first_w == blockIdx.x ? mineFirst : describe(first_w);
     __syncthreads();
     stageWindow(bufs[0], A, c, z, sDesc[0], first_w);
     for (uint32_t i = 0; i < mine; ++i) {
@@ -504,7 +520,17 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_update(PcgWork w, float4* _
   __shared__ float smem[6 * 32];
   __shared__ __align__(16) float sInv[kPcgWarps][kInvFloats];
   __shared__ float4 sR[kPcgWarps][32];
-  if (ctaConverged(w.flag)) return;
+  // block tables are per-substep data no kernel of the solve writes: fetch the first block while the mat-vec drains
+  const int lane = threadIdx.x & 31;
+  const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t nBlocks = *w.nBlocksDev;
+  uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int nodeNext = -1;
+  uint2 metaNext = make_uint2(0u, 0u);
+  if (blk < nBlocks) { nodeNext = w.blockNodes[blk * 32 + lane]; metaNext = w.blockMeta[blk]; }
+  pdlWait();
+  pdlLaunchDependents();
+  if (*(volatile const int*)w.flag) return;
   float rz[3], pap[3], alpha[3], rr[3], bb[3];
   const int prevSet = parity ? kSet0 : kSet1, mySet = parity ? kSet1 : kSet0;
   readSums3(w.scalars, prevSet + 3, rr);
@@ -523,15 +549,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_update(PcgWork w, float4* _
   readSums3(w.scalars, kPA, pap);
 #pragma unroll
   for (int k = 0; k < 3; ++k) alpha[k] = pap[k] > 0.0f ? rz[k] / pap[k] : 0.0f;
-  int lane = threadIdx.x & 31;
-  uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
   float acc[6] = {0, 0, 0, 0, 0, 0};
-  const uint32_t nBlocks = *w.nBlocksDev;
-  uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   // software pipeline: the next block's membership and location are fetched while this block is processed
-  int nodeNext = -1;
-  uint2 metaNext = make_uint2(0u, 0u);
-  if (blk < nBlocks) { nodeNext = w.blockNodes[blk * 32 + lane]; metaNext = w.blockMeta[blk]; }
   for (; blk < nBlocks; blk += warpsPerGrid) {
     const int node = nodeNext;
     const int m = (int)metaNext.y;
@@ -580,12 +599,24 @@ int launchPcgSpmv(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, con
   const uint32_t nWin = (A.n + kWinRows - 1) / kWinRows;
   const int grid = (int)std::min<uint32_t>(nWin, (uint32_t)(kNumSMs * kSpmvCtasPerSm));  // fixed per topology => fixed-order reduction
   if (grid <= 0) return 0;
-  k_pcg_spmv<<<grid, kThreads, kSpmvSmem, s>>>(A, c, w, w.partials, it & 1, it == 0 ? 1 : 0, tol * tol);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSpmvSmem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k_pcg_spmv, A, c, w, w.partials, it & 1, it == 0 ? 1 : 0, tol * tol);
   return 1;
 }
 
 int launchPcgUpdate(cudaStream_t s, const PcgWork& w, float tol, int it) {
-  k_pcg_update<<<kReduceBlocks, kThreads, 0, s>>>(w, w.delta, w.partials, it & 1, tol * tol);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kReduceBlocks); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k_pcg_update, w, w.delta, w.partials, it & 1, tol * tol);
   return 1;
 }
 
