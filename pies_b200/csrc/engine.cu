@@ -328,6 +328,7 @@ struct PdTickCtx {
   uint64_t launches0 = 0;
   ContactLists lists;
   bool inSubstep = false;
+  uint32_t iterIndex = 0;  // PD iteration inside the current substep
   PdTickCtx(PiesB200Solver* s) : timer(s, g_eventPool) {}
 };
 
@@ -426,6 +427,7 @@ int pdSubstepBegin(PiesB200Solver* s) {
   }
   timer.end();
   c->inSubstep = true;
+  c->iterIndex = 0;
   return PIES_B200_OK;
 }
 
@@ -461,7 +463,11 @@ int pdIteration(PiesB200Solver* s) {
   // Iterations are enqueued in bursts without host round trips: converged solves turn the remaining
   // launches into early exits (~2 us each), a host poll costs ~40 us of idle GPU, so the first burst
   // slightly overshoots the previous solve's count.
-  uint32_t done = 0, burst = s->lastPcgIters + 2;
+  // The k-th PD iteration of a substep needs about what the k-th of the previous substep needed (the first solve after
+  // the inertia step more than the later ones), which predicts the burst better than the previous solve of this substep.
+  const uint32_t k = c->iterIndex++;
+  if (s->pcgItersByIteration.size() <= k) s->pcgItersByIteration.resize(k + 1, s->lastPcgIters);
+  uint32_t done = 0, burst = s->pcgItersByIteration[k] + 1;
   bool converged = false;
   while (!converged && done < s->tune.pcgMaxIterations) {
     uint32_t todo = std::min(burst, s->tune.pcgMaxIterations - done);
@@ -489,6 +495,7 @@ int pdIteration(PiesB200Solver* s) {
   uint32_t used = (uint32_t)s->hostFlag[1];
   if (getenv("PIES_DEBUG_PCG")) std::fprintf(stderr, "[pcg] it: %u iterations\n", used);
   s->lastPcgIters = std::max(1u, used);
+  s->pcgItersByIteration[k] = s->lastPcgIters;
   s->stats.pcgIterationsLastTick += used;
   if (used < 2) { timer.discard(spSpmv); timer.discard(spUpdate); }  // the sampled launches were early exits
   timer.end(spGlobal);

@@ -102,6 +102,7 @@ struct PiesB200Solver {
   size_t hostPackedCap = 0;
   int* hostFlag = nullptr;      // pinned, 4 ints
   uint32_t lastPcgIters = 1;
+  std::vector<uint32_t> pcgItersByIteration;  // CG iterations the k-th PD iteration of the previous substep needed (burst prediction)
   uint64_t launches = 0;
 
   ~PiesB200Solver();
