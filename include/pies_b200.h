@@ -234,6 +234,12 @@ int pies_b200_probe_node_range(uint32_t n, const float* pos3, const float* radiu
                                int64_t* mins, uint32_t* lens);
 /* Stable LSD radix sort used by the cell tables (64-bit keys, 32-bit payload). */
 int pies_b200_probe_sort_pairs(uint64_t n, uint64_t* keys, uint32_t* vals, int keyBits);
+/* Host-only (no device needed): the sliced-ELLPACK copy of a CSR matrix that the CG mat-vec reads (system.h).
+ * First call with sellCol == NULL to get the padded entry count in *paddedNnz; sellPtr holds (n + 31) / 32 + 1
+ * words, sellRow 32 per slice (0xffffffff = padding lane).  Replaces nothing in the reference (its LLT reads
+ * Eigen's CSC, Solver.cpp:213-215); exposed so the layout is testable without a GPU. */
+int pies_b200_probe_sell(uint32_t n, const int32_t* rowPtr, const int32_t* col, const float* val, uint32_t* sellPtr,
+                         uint32_t* sellRow, int32_t* sellCol, float* sellVal, uint64_t* paddedNnz);
 
 #ifdef __cplusplus
 }

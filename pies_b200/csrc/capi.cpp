@@ -465,3 +465,23 @@ int pies_b200_get_stats(const PiesB200Solver* s, PiesB200Stats* out) {
 }
 
 }  // extern "C"
+
+// ---- host-only probe of the sliced-ELLPACK builder (system.cpp) ----
+extern "C" int pies_b200_probe_sell(uint32_t n, const int32_t* rowPtr, const int32_t* col, const float* val, uint32_t* sellPtr,
+                         uint32_t* sellRow, int32_t* sellCol, float* sellVal, uint64_t* paddedNnz) {
+  if (!rowPtr || !paddedNnz || (n && rowPtr[n] && (!col || !val))) return PIES_B200_EINVAL;
+  try {
+    std::vector<uint32_t> ptr, row;
+    std::vector<int> c;
+    std::vector<float> v;
+    pies::buildSell(n, rowPtr, col, val, ptr, row, c, v);
+    *paddedNnz = c.size();
+    if (sellPtr) std::memcpy(sellPtr, ptr.data(), ptr.size() * sizeof(uint32_t));
+    if (sellRow) std::memcpy(sellRow, row.data(), row.size() * sizeof(uint32_t));
+    if (sellCol) std::memcpy(sellCol, c.data(), c.size() * sizeof(int));
+    if (sellVal) std::memcpy(sellVal, v.data(), v.size() * sizeof(float));
+    return PIES_B200_OK;
+  } catch (...) {
+    return PIES_B200_EINVAL;
+  }
+}

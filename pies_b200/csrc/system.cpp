@@ -60,6 +60,43 @@ struct Dsu {
 
 }  // namespace
 
+// Sliced ELLPACK (SELL-32-sigma) copy of a CSR matrix, see system.h.
+void buildSell(uint32_t n, const int* rowPtr, const int* col, const float* val, std::vector<uint32_t>& sellPtr,
+               std::vector<uint32_t>& sellRow, std::vector<int>& sellCol, std::vector<float>& sellVal) {
+  const uint32_t nSlices = (n + 31u) / 32u;
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; ++i) order[i] = i;
+  auto len = [&](uint32_t r) { return (uint32_t)(rowPtr[r + 1] - rowPtr[r]); };
+  for (uint32_t w0 = 0; w0 < n; w0 += HostSystem::kSellWindow) {
+    uint32_t w1 = std::min(n, w0 + HostSystem::kSellWindow);
+    std::stable_sort(order.begin() + w0, order.begin() + w1, [&](uint32_t a, uint32_t b) { return len(a) > len(b); });
+  }
+  sellPtr.assign(nSlices + 1, 0);
+  sellRow.assign((size_t)nSlices * 32, 0xffffffffu);
+  for (uint32_t sl = 0; sl < nSlices; ++sl) {
+    uint32_t longest = 0;
+    for (uint32_t l = 0; l < 32 && sl * 32 + l < n; ++l) {
+      sellRow[(size_t)sl * 32 + l] = order[sl * 32 + l];
+      longest = std::max(longest, len(order[sl * 32 + l]));
+    }
+    sellPtr[sl + 1] = sellPtr[sl] + 32u * longest;
+  }
+  sellCol.assign(sellPtr[nSlices], 0);
+  sellVal.assign(sellPtr[nSlices], 0.0f);
+  for (uint32_t sl = 0; sl < nSlices; ++sl) {
+    const uint32_t longest = (sellPtr[sl + 1] - sellPtr[sl]) / 32u;
+    for (uint32_t l = 0; l < 32; ++l) {
+      const uint32_t r = sellRow[(size_t)sl * 32 + l];
+      const uint32_t m = r == 0xffffffffu ? 0u : len(r);
+      for (uint32_t k = 0; k < longest; ++k) {
+        const size_t idx = (size_t)sellPtr[sl] + 32u * k + l;
+        if (k < m) { sellCol[idx] = col[rowPtr[r] + k]; sellVal[idx] = val[rowPtr[r] + k]; }
+        else sellCol[idx] = r == 0xffffffffu ? 0 : (int)r;
+      }
+    }
+  }
+}
+
 void buildSystem(const HostScene& sc, float h, HostSystem& out, unsigned threads) {
   out = HostSystem{};
   const uint32_t n = sc.nodeCount();
@@ -214,40 +251,7 @@ void buildSystem(const HostScene& sc, float h, HostSystem& out, unsigned threads
   rawVal.clear(); rawVal.shrink_to_fit();
 
   // ---- 3b. sliced ELLPACK copy for the CG mat-vec -----------------------------------------------------
-  {
-    const uint32_t nSlices = (n + 31u) / 32u;
-    std::vector<uint32_t> order(n);
-    for (uint32_t i = 0; i < n; ++i) order[i] = i;
-    auto len = [&](uint32_t r) { return (uint32_t)(out.rowPtr[r + 1] - out.rowPtr[r]); };
-    for (uint32_t w0 = 0; w0 < n; w0 += HostSystem::kSellWindow) {
-      uint32_t w1 = std::min(n, w0 + HostSystem::kSellWindow);
-      std::stable_sort(order.begin() + w0, order.begin() + w1, [&](uint32_t a, uint32_t b) { return len(a) > len(b); });
-    }
-    out.sellPtr.assign(nSlices + 1, 0);
-    out.sellRow.assign((size_t)nSlices * 32, 0xffffffffu);
-    for (uint32_t sl = 0; sl < nSlices; ++sl) {
-      uint32_t longest = 0;
-      for (uint32_t l = 0; l < 32 && sl * 32 + l < n; ++l) {
-        out.sellRow[(size_t)sl * 32 + l] = order[sl * 32 + l];
-        longest = std::max(longest, len(order[sl * 32 + l]));
-      }
-      out.sellPtr[sl + 1] = out.sellPtr[sl] + 32u * longest;
-    }
-    out.sellCol.assign(out.sellPtr[nSlices], 0);
-    out.sellVal.assign(out.sellPtr[nSlices], 0.0f);
-    for (uint32_t sl = 0; sl < nSlices; ++sl) {
-      const uint32_t longest = (out.sellPtr[sl + 1] - out.sellPtr[sl]) / 32u;
-      for (uint32_t l = 0; l < 32; ++l) {
-        const uint32_t r = out.sellRow[(size_t)sl * 32 + l];
-        const uint32_t m = r == 0xffffffffu ? 0u : len(r);
-        for (uint32_t k = 0; k < longest; ++k) {
-          const size_t idx = (size_t)out.sellPtr[sl] + 32u * k + l;
-          if (k < m) { out.sellCol[idx] = out.col[out.rowPtr[r] + k]; out.sellVal[idx] = out.val[out.rowPtr[r] + k]; }
-          else out.sellCol[idx] = r == 0xffffffffu ? 0 : (int)r;
-        }
-      }
-    }
-  }
+  buildSell(n, out.rowPtr.data(), out.col.data(), out.val.data(), out.sellPtr, out.sellRow, out.sellCol, out.sellVal);
 
   // ---- 4. block-Jacobi preconditioner: blocks of <= 32 nodes following connectivity ------------------
   Dsu dsu(n);

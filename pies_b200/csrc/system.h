@@ -44,6 +44,10 @@ struct HostSystem {
   uint64_t staticProjections = 0;             // per PD iteration, shape/goal count one per member
 };
 
+// Sliced-ELLPACK copy of a CSR matrix (layout described in HostSystem).  Host only.
+void buildSell(uint32_t n, const int* rowPtr, const int* col, const float* val, std::vector<uint32_t>& sellPtr,
+               std::vector<uint32_t>& sellRow, std::vector<int>& sellCol, std::vector<float>& sellVal);
+
 // h = fixedTimestepSize / timeSubsteps.  threads: worker threads for the row-wise assembly.
 void buildSystem(const HostScene& sc, float h, HostSystem& out, unsigned threads);
 

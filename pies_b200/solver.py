@@ -132,6 +132,7 @@ _SIGNATURES = {
     "pies_b200_probe_tri_range": (C.c_int, [C.c_uint32, _f32p, _f32p, _i64p, _u32p]),
     "pies_b200_probe_node_range": (C.c_int, [C.c_uint32, _f32p, _f32p, C.c_float, _i64p, _u32p]),
     "pies_b200_probe_sort_pairs": (C.c_int, [C.c_uint64, _u64p, _u32p, C.c_int]),
+    "pies_b200_probe_sell": (C.c_int, [C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_uint64)]),
 }
 
 _lib = None
@@ -503,3 +504,17 @@ def probe_sort_pairs(keys, vals, keyBits):
     k = np.ascontiguousarray(keys, np.uint64).copy(); v = np.ascontiguousarray(vals, np.uint32).copy()
     _ckp(lib().pies_b200_probe_sort_pairs(len(k), k, v, keyBits))
     return k, v
+
+
+def probe_sell(rowPtr, col, val):
+    """Host-only: the sliced-ELLPACK copy (sellPtr, sellRow, sellCol, sellVal) the CG mat-vec reads, from a CSR matrix."""
+    rp = np.ascontiguousarray(rowPtr, np.int32); c = np.ascontiguousarray(col, np.int32); v = np.ascontiguousarray(val, np.float32)
+    n = len(rp) - 1
+    padded = C.c_uint64(0)
+    p = lambda a: a.ctypes.data_as(_vp)
+    _ckp(lib().pies_b200_probe_sell(n, p(rp), p(c), p(v), None, None, None, None, C.byref(padded)))
+    ns = (n + 31) // 32
+    sp = np.zeros(ns + 1, np.uint32); sr = np.zeros(32 * ns, np.uint32)
+    sc = np.zeros(padded.value, np.int32); sv = np.zeros(padded.value, np.float32)
+    _ckp(lib().pies_b200_probe_sell(n, p(rp), p(c), p(v), p(sp), p(sr), p(sc), p(sv), C.byref(padded)))
+    return sp, sr, sc, sv

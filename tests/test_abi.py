@@ -4,6 +4,8 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
+
 import pytest
 
 from conftest import ROOT
@@ -91,3 +93,44 @@ def test_product_does_not_reference_the_oracle():
                     if re.search(r"oracle[/.]|libpies_ref|libpies_oracle|refapi", text):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_sell_copy_is_the_same_matrix(pb):
+    """Host logic of the CG mat-vec's matrix layout (pies_b200/csrc/system.cpp, buildSell): the sliced-ELLPACK copy must
+    hold exactly the CSR entries, row by row in CSR order, padded with zeros, rows permuted only inside 256-row windows
+    and sorted by length there, slices padded to their longest row."""
+    from pies_b200 import solver
+    rng = np.random.default_rng(7)
+    for n in (1, 31, 32, 33, 256, 257, 1000):
+        lens = rng.integers(0, 20, n)
+        lens[rng.integers(0, n)] = 45                      # one long row
+        row_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        col = rng.integers(0, n, row_ptr[-1]).astype(np.int32)
+        val = rng.standard_normal(row_ptr[-1]).astype(np.float32)
+        sp, sr, sc, sv = solver.probe_sell(row_ptr, col, val)
+        ns = (n + 31) // 32
+        assert sp[0] == 0 and len(sp) == ns + 1 and (np.diff(sp.astype(np.int64)) % 32 == 0).all()
+        rows = sr[sr != 0xFFFFFFFF]
+        assert sorted(rows.tolist()) == list(range(n))                      # a permutation of the rows
+        for w0 in range(0, n, 256):                                         # ... inside its own window, longest first
+            w = sr[w0:min(w0 + 256, 32 * ns)]
+            w = w[w != 0xFFFFFFFF]
+            assert w.min() >= w0 and w.max() < min(n, w0 + 256)
+            assert (np.diff(lens[w]) <= 0).all()
+        x = rng.standard_normal(n)
+        y_csr = np.array([np.dot(val[row_ptr[r]:row_ptr[r + 1]].astype(np.float64), x[col[row_ptr[r]:row_ptr[r + 1]]]) for r in range(n)])
+        y = np.zeros(n)
+        for s in range(ns):
+            width = (int(sp[s + 1]) - int(sp[s])) // 32
+            for lane in range(32):
+                r = sr[32 * s + lane]
+                idx = int(sp[s]) + 32 * np.arange(width) + lane
+                if r == 0xFFFFFFFF:
+                    assert (sv[idx] == 0).all()
+                    continue
+                m = lens[r]
+                assert width >= m
+                assert (sc[idx[:m]] == col[row_ptr[r]:row_ptr[r + 1]]).all() and (sv[idx[:m]] == val[row_ptr[r]:row_ptr[r + 1]]).all()
+                assert (sv[idx[m:]] == 0).all()
+                y[r] = np.dot(sv[idx].astype(np.float64), x[sc[idx]])
+        assert np.allclose(y, y_csr, rtol=0, atol=1e-12)
