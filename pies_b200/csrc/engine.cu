@@ -588,8 +588,9 @@ int countOwnedContacts(PiesB200Solver* s, uint32_t* nTri, uint32_t* nFloor) {
   *nTri = s->stats.triCollisions; *nFloor = s->stats.staticCollisions;
   if (!s->haveOwnedMask || !s->detect || (!*nTri && !*nFloor)) return PIES_B200_OK;
   uint32_t m = std::max(*nTri, *nFloor);
-  PIES_CHECK(s, s->flag.reserve(4));
-  uint32_t* out = reinterpret_cast<uint32_t*>(s->flag.p) + 2;
+  // NOT s->flag: flag[2] is the ticket counter of the CG kernels' grid reductions and must stay 0 between kernels
+  PIES_CHECK(s, s->ownedCount.reserve(2));
+  uint32_t* out = s->ownedCount.p;
   PIES_CHECK(s, cudaMemsetAsync(out, 0, 2 * sizeof(uint32_t), s->stream));
   k_count_owned<<<gridFor(m, kThreads), kThreads, 0, s->stream>>>(*nTri, s->detect->triList.p, *nFloor, s->detect->floorList.p,
                                                                  s->ownedMask.p, out);

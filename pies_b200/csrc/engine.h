@@ -96,6 +96,7 @@ struct PiesB200Solver {
   pies::PbdWork* pbd = nullptr;
   void* pdCtx = nullptr;          // PdTickCtx of a tick in progress (engine.cu)
   pies::DevBuf<uint32_t> triOrder; bool haveTriOrder = false;  // canonical-order override (slab-partitioned hosts)
+  pies::DevBuf<uint32_t> ownedCount;  // output of countOwnedContacts (its own buffer: `flag` belongs to the CG reductions)
   pies::DevBuf<uint8_t> ownedMask; bool haveOwnedMask = false; // nodes this rank owns (others are ghosts)
 
   float* hostPacked = nullptr;  // pinned, 3 floats per node

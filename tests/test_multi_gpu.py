@@ -160,3 +160,26 @@ def test_nccl_two_ranks_match_single_solver(pb):
     diag = bbox_diag(ref[10][0])
     assert float(np.abs(out["pos"] - ref[10][0]).max()) <= 1e-4 * diag
     assert out["halo_bytes"] > 0
+
+
+def test_counting_owned_contacts_does_not_disturb_the_solve(pb):
+    """bench.py asks every rank for its owned contacts after every tick (countOwnedContacts).  That query once wrote
+    its result over the ticket counter of the CG kernels' grid reductions, so from the first contact on the dot products
+    were never reduced and the solves stopped at once (seen as ~2 CG iterations per tick in a 2-GPU bench).  A solver
+    that is queried every tick must follow the trajectory of one that is not, bit for bit."""
+    specs = row_specs(columns=3, layers=2)
+    plain = _single(pb, specs, ticks=(30,))
+    s = pb.Solver(**OPTS)
+    for sp in specs:
+        multigpu.apply_spec(s, sp)
+    s.tick()
+    s.setOwnedNodes(np.ones(len(s.getVertices()), np.uint8))
+    seen = 0
+    for t in range(2, 31):
+        s.tick()
+        nt, nf = s.countOwnedContacts()
+        st = s.stats()
+        assert (nt, nf) == (st.triCollisions, st.staticCollisions)
+        seen = max(seen, nt)
+    assert seen > 0
+    assert (s.positions == plain[30][0]).all() and (s.velocities == plain[30][1]).all()
