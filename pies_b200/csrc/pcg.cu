@@ -2,14 +2,16 @@
 //
 // Replaces the reference's per-substep sparse Cholesky re-factorisation and solve
 // (reference Src/Solver.cpp:242-262 SimplicialLLT(S + C_t), :356 solve) with a
-// matrix that is never re-assembled: A = S (CSR, built once per topology) + C_t applied
-// matrix-free from the substep's collision lists (point-triangle blocks
-// w [3 -1 -1 -1; -1 1 0 0; -1 0 1 0; -1 0 0 1], CollisionConstraint.cpp:74-83, and the
-// floor diagonal, :442-445).  The three coordinate columns are solved together with
-// separate CG scalars per column, warm-started at the current positions.
+// matrix that is never re-assembled: A = S (built once per topology; CSR for the start
+// residual, sliced ELLPACK for the iterations) + C_t, the substep's collision terms
+// (point-triangle blocks w [3 -1 -1 -1; -1 1 0 0; -1 0 1 0; -1 0 0 1],
+// CollisionConstraint.cpp:74-83, and the floor diagonal, :442-445), read from the contact
+// lists by the start residual and from their CSR form (detect.cu, k_ccsr_fill) by the mat-vec.
+// The three coordinate columns are solved together with separate CG scalars per column,
+// warm-started at the current positions.
 //
-// Determinism: every dot product is reduced in a fixed order (per-CTA partials on a
-// fixed grid, summed redundantly by each consumer CTA in the same order) — no atomics.
+// Determinism: every dot product is reduced in a fixed order (per-CTA partials on a grid that
+// is fixed per topology, summed by the last CTA to finish in partial order) — no float atomics.
 #include <algorithm>
 
 #include "kernels.h"
@@ -67,50 +69,8 @@ __device__ __forceinline__ void readSums3(const float* __restrict__ scalars, int
 __device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdlLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// CTA-uniform early exit once the solve has converged (lets the host enqueue a fixed
-// number of iterations without a sync; finished iterations cost one flag read).
-__device__ __forceinline__ bool ctaConverged(const int* flag) {
-  __shared__ int sflag;
-  if (threadIdx.x == 0) sflag = *(volatile const int*)flag;
-  __syncthreads();
-  return sflag != 0;
-}
-
-// y_i = (A x)_i for one row: CSR part + matrix-free collision part.
-__device__ __forceinline__ V3 applyRow(uint32_t i, const CsrMatrix& A, const ContactLists& c,
-                                       const float4* __restrict__ x, V3 xi) {
-  V3 y = v3(0.0f, 0.0f, 0.0f);
-  int beg = A.rowPtr[i], end = A.rowPtr[i + 1];
-  for (int k = beg; k < end; ++k) {
-    float a = __ldg(A.val + k);
-    float4 xv = __ldg(x + __ldg(A.col + k));
-    y.x += a * xv.x; y.y += a * xv.y; y.z += a * xv.z;
-  }
-  if (c.nFloor) {
-    float fw = c.floorW[i];
-    y.x += fw * xi.x; y.y += fw * xi.y; y.z += fw * xi.z;
-  }
-  if (c.nTri) {
-    int cb = c.incPtr[i], ce = c.incPtr[i + 1];
-    for (int k = cb; k < ce; ++k) {
-      uint32_t v = c.inc[k];
-      uint4 e = __ldg(c.uTri + (v >> 2));
-      float wgt = __ldg(c.uW + (v >> 2));
-      uint32_t slot = v & 3u;
-      V3 t;
-      if (slot == 0) {
-        V3 xb = v3(__ldg(x + e.y)), xc = v3(__ldg(x + e.z)), xd = v3(__ldg(x + e.w));
-        t = 3.0f * xi - xb - xc - xd;
-      } else {
-        t = xi - v3(__ldg(x + e.x));
-      }
-      y += wgt * t;
-    }
-  }
-  return y;
-}
-
-// Same row product accumulated in fp64 (float products are exact in double): used once per
+// y_i = (A x)_i for one row (CSR part + collision part from the contact lists), accumulated in fp64 (float
+// products are exact in double): used once per
 // solve for the start residual, where b and A x agree to ~7 digits and the difference is what
 // matters (velocities are position differences divided by h, so sub-ulp position errors count).
 __device__ __forceinline__ void applyRowD(uint32_t i, const CsrMatrix& A, const ContactLists& c,
