@@ -147,22 +147,30 @@ class HaloExchange:
         self.recv = {p: torch.as_tensor(ix, dtype=torch.long, device=device) for p, ix in sorted(recv.items())}
         self.bytes_per_plane = 16 * (sum(len(v) for v in self.send.values()) + sum(len(v) for v in self.recv.values()))
         self.active = bool(self.send or self.recv)
+        self._cache = {}
+
+    def _plan_for(self, k, like):
+        """Send / receive buffers and the P2P op list for k planes, built once (the exchange runs 11 times per tick:
+        allocation and op construction would otherwise be most of its host time)."""
+        torch, dist = self.torch, self.dist
+        if k not in self._cache:
+            sbuf = {p: torch.empty((k, len(ix), 4), dtype=like.dtype, device=like.device) for p, ix in self.send.items()}
+            rbuf = {p: torch.empty((k, len(ix), 4), dtype=like.dtype, device=like.device) for p, ix in self.recv.items()}
+            ops = [dist.P2POp(dist.isend, sbuf[p], p, group=self.group) for p in self.send]
+            ops += [dist.P2POp(dist.irecv, rbuf[p], p, group=self.group) for p in self.recv]
+            self._cache[k] = (sbuf, rbuf, ops)
+        return self._cache[k]
 
     def __call__(self, planes):
         """planes: list of [n,4] tensors; ghost rows are overwritten with the owners' rows."""
         if not self.active or self.dist is None:
             return 0
         torch, dist = self.torch, self.dist
-        ops, bufs = [], []
         k = len(planes)
+        sbuf, rbuf, ops = self._plan_for(k, planes[0])
         for p, ix in self.send.items():
-            out = torch.stack([pl.index_select(0, ix) for pl in planes]).contiguous()
-            ops.append(dist.P2POp(dist.isend, out, p, group=self.group))
-            bufs.append(out)
-        rbuf = {}
-        for p, ix in self.recv.items():
-            rbuf[p] = torch.empty((k, len(ix), 4), dtype=planes[0].dtype, device=planes[0].device)
-            ops.append(dist.P2POp(dist.irecv, rbuf[p], p, group=self.group))
+            for j, pl in enumerate(planes):
+                torch.index_select(pl, 0, ix, out=sbuf[p][j])
         for req in dist.batch_isend_irecv(ops):
             req.wait()
         for p, ix in self.recv.items():
