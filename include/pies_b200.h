@@ -93,7 +93,7 @@ typedef struct PiesB200Stats {
   uint32_t reserved;           /* contact clusters of the last substep swept from shared memory (low 16 bits, saturating)
                                 * and by the dataflow executor (high 16 bits) */
   /* sampled launches of the other hot kernels (one timed launch per PD iteration; phase timing on only) */
-  float msSpmvKernel;          /* k_pcg_spmv: CSR-stream A z + p / Ap recurrences */
+  float msSpmvKernel;          /* k_pcg_spmv: A z (SELL windows) + p / Ap recurrences */
   float msUpdateKernel;        /* k_pcg_update: x, r update + block-Jacobi apply */
   float msGatherKernel;        /* k_gather_rhs: CSR gather of the right-hand side */
   uint32_t spmvKernelLaunches;

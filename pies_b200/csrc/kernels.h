@@ -83,7 +83,7 @@ int launchVelocityUpdate(cudaStream_t s, uint32_t n, const float4* q, float4* pr
 // ------------------------------------------------------------------ PCG -----
 struct PcgWork {
   float4 *r = nullptr, *p = nullptr, *p2 = nullptr, *z = nullptr, *ap = nullptr, *delta = nullptr;
-  float* partials = nullptr;   // kReduceBlocks * 32 floats
+  float* partials = nullptr;   // kMaxReduceBlocks * 32 floats (per-CTA partial sums, kPartialStride apart)
   float* scalars = nullptr;    // see pcg.cu
   int* flag = nullptr;         // [0] converged, [1] iterations done, [2] ticket counter of the grid reductions
   // block-Jacobi preconditioner (rebuilt per substep, reblock.cu): blocks of m <= 32 nodes, dense inverse of
