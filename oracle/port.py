@@ -166,3 +166,47 @@ def free_fall(pos, vel, ticks, h=0.012, gravity=10.0, damping=0.006, floor=0.0):
         vel[:, 1] = vel[:, 1] - h * F32(gravity)
         pos = q
     return pos, vel
+
+
+# --------------------------------------------------------------------------------------------------
+# Collision terms of the global system (Src/CollisionConstraint.cpp)
+# --------------------------------------------------------------------------------------------------
+PT_WEIGHT = F32(10000.0)      # PointTriangleCollisionConstraint::w, CollisionConstraint.h:32
+FLOOR_WEIGHT = F32(10000.0)   # StaticCollisionConstraint::w, CollisionConstraint.h:78
+
+
+def collision_matrix(n, tri_list, floor_list):
+    """C_t, what the collision constraints of one substep add to the system matrix (Solver.cpp:242-262).
+    tri_list: (m, 4) entries (a, b, c, d) of the point-triangle list WITH its duplicates (one copy per shared cell,
+    SURVEY F7): each adds w * A^T A with A = [0; -1 1 0 0; -1 0 1 0; -1 0 0 1] (CollisionConstraint.cpp:74-83,176-184),
+    i.e. w * [[3,-1,-1,-1],[-1,1,0,0],[-1,0,1,0],[-1,0,0,1]] on rows/columns (a, b, c, d).
+    floor_list: node ids of the floor list with duplicates: each adds w on the diagonal (CollisionConstraint.cpp:442-445).
+    Returns a dense (n, n) float64 matrix (sums of exactly representable multiples of 1e4)."""
+    C = np.zeros((n, n), np.float64)
+    ata = np.array([[3, -1, -1, -1], [-1, 1, 0, 0], [-1, 0, 1, 0], [-1, 0, 0, 1]], np.float64) * float(PT_WEIGHT)
+    for e in np.asarray(tri_list, np.int64).reshape(-1, 4):
+        C[np.ix_(e, e)] += ata
+    for v in np.asarray(floor_list, np.int64).reshape(-1):
+        C[v, v] += float(FLOOR_WEIGHT)
+    return C
+
+
+def collision_csr(n, tri_list, floor_list):
+    """The same matrix in the streamable form the CUDA mat-vec reads (pies_b200/csrc/detect.cu, k_ccsr_fill): distinct
+    contacts with weight = copies * w, off-diagonals per node in (contact, slot) order, diagonal summed separately.
+    Returns (cPtr, cCol, cVal, cDiag)."""
+    tri = np.asarray(tri_list, np.int64).reshape(-1, 4)
+    uniq, copies = (np.unique(tri, axis=0, return_counts=True) if len(tri) else (tri, np.zeros(0, np.int64)))
+    rows = [[] for _ in range(n)]
+    diag = np.zeros(n, np.float64)
+    for (a, b, c, d), k in zip(uniq, copies):
+        w = float(PT_WEIGHT) * k
+        rows[a] += [(b, -w), (c, -w), (d, -w)]; diag[a] += 3 * w
+        for v in (b, c, d):
+            rows[v].append((a, -w)); diag[v] += w
+    for v in np.asarray(floor_list, np.int64).reshape(-1):
+        diag[v] += float(FLOOR_WEIGHT)
+    ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    col = np.array([c for r in rows for c, _ in r], np.int64)
+    val = np.array([v for r in rows for _, v in r], np.float64)
+    return ptr, col, val, diag

@@ -94,6 +94,8 @@ def lib():
             "pref_get_tri_collisions": (None, [vp, _u32p]),
             "pref_get_static_collisions": (None, [vp, _u32p]),
             "pref_stiffness_nnz": (C.c_int64, [vp]),
+            "pref_system_nnz": (C.c_int64, [vp]),
+            "pref_get_system": (None, [vp, _i32p, _i32p, _f32p, _f32p, _f32p]),
             "pref_probe_tet": (None, [C.c_uint32, _f32p, _f32p, C.c_float, C.c_float, _f32p]),
             "pref_probe_volume": (None, [C.c_uint32, _f32p, _f32p, C.c_float, C.c_float, _f32p]),
             "pref_probe_qinv": (None, [C.c_uint32, _f32p, _f32p]),
@@ -318,6 +320,15 @@ class RefSolver:
         w = C.c_float()
         lib().pref_get_goal(self.h, i, ids, mat, C.byref(w))
         return ids, mat, w.value
+
+    def system(self):
+        """White-box: the system of the last global step, S + C_t as (rows, cols, vals) triplets (Solver.cpp:242-262),
+        its last right-hand side and the solver's answer (both n x 3)."""
+        nnz, n = lib().pref_system_nnz(self.h), self.count("node")
+        rows = np.empty(nnz, np.int32); cols = np.empty(nnz, np.int32); vals = np.empty(nnz, np.float32)
+        rhs = np.empty((n, 3), np.float32); state = np.empty((n, 3), np.float32)
+        lib().pref_get_system(self.h, rows, cols, vals, rhs, state)
+        return rows, cols, vals, rhs, state
 
     def triCollisions(self):
         out = np.empty((self.count("tri_collision"), 4), dtype=np.uint32)

@@ -105,3 +105,46 @@ def test_free_fall_restatement_against_golden():
     pos, vel = port.free_fall(pos0, vel0, 1)
     diag = float(np.linalg.norm(pos0.max(0) - pos0.min(0)))
     assert np.abs(pos - traj[0]).max() <= 1e-4 * diag
+
+
+def test_collision_matrix_against_the_reference_system(ref):
+    """The reference's own S + C_t of a contact tick minus its S of a contact-free tick is the restated collision matrix
+    (duplicates of the list counted with their multiplicity, 1e4 per point-triangle copy and per floor copy), and the
+    streamable CSR form the CUDA mat-vec reads is the same matrix."""
+    from oracle import port
+
+    def scene(s):
+        s.createTetBox((0.1, 0.3, 0.1), 1.0, (0, 0, 0), 1000.0, 1.0, False)
+        s.createTetBox((0.4, 2.6, 0.3), 1.0, (0, -5, 0), 1000.0, 1.0, False)
+
+    r = ref.RefSolver(iterations=10)
+    scene(r)
+    n = 54
+
+    def dense():
+        rows, cols, vals, _, _ = r.system()
+        m = np.zeros((n, n))
+        np.add.at(m, (rows, cols), vals.astype(np.float64))
+        return m
+
+    r.tick(2)
+    assert r.count("tri_collision") == 0 and r.count("static_collision") == 0
+    S = dense()
+    assert np.allclose(S, S.T)
+    seen = 0
+    for t in range(2, 16):
+        r.tick()
+        tri, floor = r.triCollisions(), r.staticCollisions()
+        if not len(tri) and not len(floor):
+            continue
+        seen += 1
+        C = dense() - S
+        want = port.collision_matrix(n, tri, floor)
+        assert np.abs(C - want).max() <= 1e-3 * max(1.0, np.abs(want).max()), t      # fp32 sums of S + multiples of 1e4
+        ptr, col, val, diag = port.collision_csr(n, tri, floor)
+        csr = np.diag(diag)
+        for i in range(n):
+            np.add.at(csr[i], col[ptr[i]:ptr[i + 1]], val[ptr[i]:ptr[i + 1]])
+        assert np.array_equal(csr, want), t
+        assert ptr[-1] == 6 * len(np.unique(tri, axis=0)) if len(tri) else ptr[-1] == 0
+    assert seen >= 8
