@@ -190,6 +190,10 @@ int pies_b200_detect(PiesB200Solver* s);
 uint32_t pies_b200_tri_collision_count(const PiesB200Solver* s);
 uint32_t pies_b200_static_collision_count(const PiesB200Solver* s);
 int pies_b200_get_tri_collisions(PiesB200Solver* s, uint32_t* ids4);   /* canonical reference order */
+/* [additive, parity] The collision terms C_t that the last detection added to the system (what the reference adds to
+ * S in Solver.cpp:242-262), in the form the CG mat-vec streams: off-diagonals as a per-node CSR, diagonal separately.
+ * Call with cCol == NULL to read *nnz (and fill cPtr, n + 1 entries, and cDiag, n entries, when given). */
+int pies_b200_get_collision_csr(PiesB200Solver* s, uint64_t* nnz, int32_t* cPtr, int32_t* cCol, float* cVal, float* cDiag);
 int pies_b200_get_static_collisions(PiesB200Solver* s, uint32_t* ids); /* canonical reference order */
 /* Triangle-hash occupancy of the last detect(): cells sorted by (x,y,z), members ascending. */
 int pies_b200_tri_occupancy_counts(PiesB200Solver* s, uint64_t* nCells, uint64_t* nMembers);

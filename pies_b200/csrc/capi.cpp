@@ -361,6 +361,34 @@ int pies_b200_get_tri_collisions(PiesB200Solver* s, uint32_t* ids) {
   PIES_CHECK(s, cudaMemcpy(ids, s->detect->triList.p, 16ull * s->stats.triCollisions, cudaMemcpyDeviceToHost));
   return PIES_B200_OK;
 }
+int pies_b200_get_collision_csr(PiesB200Solver* s, uint64_t* nnz, int32_t* cPtr, int32_t* cCol, float* cVal, float* cDiag) {
+  if (!s || !nnz) return PIES_B200_EINVAL;
+  return guarded(s, [&]() {
+    cudaSetDevice(s->device);
+    const uint32_t n = s->n;
+    const bool any = s->detect && (s->stats.triCollisions || s->stats.staticCollisions);
+    const bool csr = any && s->stats.triCollisions && s->detect->nUnique;
+    *nnz = 0;
+    if (csr) {
+      uint32_t last = 0;
+      PIES_CHECK(s, cudaMemcpy(&last, s->detect->cPtr.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      *nnz = last;
+    }
+    if (cPtr) {
+      if (csr) PIES_CHECK(s, cudaMemcpy(cPtr, s->detect->cPtr.p, (size_t)(n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      else std::memset(cPtr, 0, (size_t)(n + 1) * sizeof(int32_t));
+    }
+    if (cDiag) {
+      if (any) PIES_CHECK(s, cudaMemcpy(cDiag, s->detect->cDiag.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+      else std::memset(cDiag, 0, (size_t)n * sizeof(float));
+    }
+    if (cCol && cVal && *nnz) {
+      PIES_CHECK(s, cudaMemcpy(cCol, s->detect->cCol.p, *nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      PIES_CHECK(s, cudaMemcpy(cVal, s->detect->cVal.p, *nnz * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return PIES_B200_OK;
+  });
+}
 int pies_b200_get_static_collisions(PiesB200Solver* s, uint32_t* ids) {
   if (!s || !ids) return PIES_B200_EINVAL;
   if (!s->stats.staticCollisions) return PIES_B200_OK;

@@ -110,6 +110,7 @@ _SIGNATURES = {
     "pies_b200_tri_collision_count": (C.c_uint32, [_vp]),
     "pies_b200_static_collision_count": (C.c_uint32, [_vp]),
     "pies_b200_get_tri_collisions": (C.c_int, [_vp, _u32p]),
+    "pies_b200_get_collision_csr": (C.c_int, [_vp, C.POINTER(C.c_uint64), _vp, _vp, _vp, _vp]),
     "pies_b200_get_static_collisions": (C.c_int, [_vp, _u32p]),
     "pies_b200_tri_occupancy_counts": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pies_b200_get_tri_occupancy": (C.c_int, [_vp, _i64p, _u32p, _u32p]),
@@ -387,6 +388,18 @@ class Solver:
         out = np.empty((lib().pies_b200_tri_collision_count(self.h), 4), dtype=np.uint32)
         self._ck(lib().pies_b200_get_tri_collisions(self.h, out))
         return out
+
+    def collisionCsr(self):
+        """(cPtr, cCol, cVal, cDiag): the collision terms of the last detection as the CG mat-vec streams them."""
+        n = lib().pies_b200_vertex_count(self.h)
+        nnz = C.c_uint64(0)
+        ptr = np.zeros(n + 1, np.int32); diag = np.zeros(n, np.float32)
+        p = lambda a: a.ctypes.data_as(_vp)
+        self._ck(lib().pies_b200_get_collision_csr(self.h, C.byref(nnz), p(ptr), None, None, p(diag)))
+        col = np.zeros(nnz.value, np.int32); val = np.zeros(nnz.value, np.float32)
+        if nnz.value:
+            self._ck(lib().pies_b200_get_collision_csr(self.h, C.byref(nnz), None, p(col), p(val), None))
+        return ptr, col, val, diag
 
     def staticCollisions(self):
         out = np.empty(lib().pies_b200_static_collision_count(self.h), dtype=np.uint32)

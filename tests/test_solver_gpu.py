@@ -284,3 +284,29 @@ def test_bodies_added_between_ticks(pb, ref):
     for _ in range(5):
         r.tick(); s.tick()
     assert np.abs(s.positions - r.positions).max() <= 1e-4 * bbox_diag(r.positions)
+
+
+def test_collision_csr_is_the_reference_collision_matrix(pb):
+    """The collision terms the CG mat-vec streams (detect.cu, k_ccsr_fill) are exactly the matrix the reference adds to S
+    for the same lists: oracle/port.py restates that assembly (pinned against the compiled reference's own S + C_t in the
+    CPU suite); here the device CSR of the reference's contact states must reproduce it entry for entry."""
+    from oracle import port
+    g = golden("collisions")
+    s = pb.Solver(iterations=10)
+    two_box(s)
+    s.tick()
+    n = len(s.getVertices())
+    for t in (3, 10, 14, 30):
+        s.setState(g["t%d_pos" % t], g["t%d_prev" % t], None)
+        s.detect()
+        assert (s.triCollisions() == g["t%d_tri" % t]).all()
+        ptr, col, val, diag = s.collisionCsr()
+        wptr, wcol, wval, wdiag = port.collision_csr(n, g["t%d_tri" % t], g["t%d_floor" % t])
+        assert (ptr == wptr).all() and (diag.astype(np.float64) == wdiag).all(), t
+        for i in range(n):   # same entries per row (the device orders a row by (point, triangle index), the port by node ids)
+            a, b = slice(ptr[i], ptr[i + 1]), slice(wptr[i], wptr[i + 1])
+            assert sorted(zip(col[a].tolist(), val[a].astype(np.float64).tolist())) == sorted(zip(wcol[b].tolist(), wval[b].tolist())), (t, i)
+        dense = np.diag(diag.astype(np.float64))
+        for i in range(n):
+            np.add.at(dense[i], col[ptr[i]:ptr[i + 1]], val[ptr[i]:ptr[i + 1]].astype(np.float64))
+        assert np.array_equal(dense, port.collision_matrix(n, g["t%d_tri" % t], g["t%d_floor" % t])), t
