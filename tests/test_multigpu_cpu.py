@@ -126,6 +126,17 @@ def _worker(rank, world, port, out):
     planes[0][~torch.as_tensor(owned)] = -7.0
     x([planes[0]])
     ok2 = bool((planes[0][:, 0] == torch.as_tensor(l2g * 10.0, dtype=torch.float32)).all())
+    # the exchange keeps its buffers and op lists between calls (11 calls per tick): repeated rounds with changing
+    # owner values and both plane counts must keep delivering the current values
+    for rnd in range(3):
+        for k, pl in enumerate(planes):
+            pl[torch.as_tensor(owned)] += 1000.0
+            pl[~torch.as_tensor(owned)] = -3.0
+        x(planes if rnd != 1 else [planes[0]])
+        want = [torch.as_tensor(l2g * 10.0 + k, dtype=torch.float32) + 1000.0 * (rnd + 1) for k in range(3)]
+        ok2 = ok2 and bool((planes[0][:, 0] == want[0]).all())
+        if rnd != 1:
+            ok2 = ok2 and all(bool((planes[k][:, 0] == want[k]).all()) for k in (1, 2))
     out[rank] = dict(ok=ok, ok2=ok2, moved=moved, ghosts=int((~owned).sum()))
     dist.destroy_process_group()
 
