@@ -6,6 +6,10 @@ iterations per substep, one B200 per rank.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 One "step" = one Solver::tick (one substep of 10 PD iterations + collision detection/response).
+The scene is first rolled forward, untimed, to simulation tick --preroll (default 60: the columns have landed on the
+floor and on each other, ~290 k point-triangle contacts), so whatever --warmup / --steps the caller passes the timed
+window covers collisions and a real global solve; the free-fall regime (ticks 3..13, no contacts) is measured too and
+reported under `free_fall`.  The reference arm rolls its sample forward to the same tick.
 `value`  : whole-job projections/s with all state resident in HBM (tick loop without host readback),
            CUDA-event timed, max over ranks.
 `e2e`    : the same ticks through the host-facing API with HOST buffers: every step uploads the node
@@ -84,21 +88,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args, steps, warmup, quiet=False):
-    """Times the unmodified reference (oracle/_ref) on the host cores on the bounded sample."""
+def run_reference(args, steps, warmup, quiet=False, threads=8):
+    """Times the unmodified reference (oracle/_ref) on the host cores on the bounded sample, over the same tick window
+    as the GPU arm (preroll + warmup untimed, then `steps`).  threads = SolverOptions::threadCount: 8 is the reference
+    default (Solver.h:36) and what fixes the collision-list order on both arms; the reference is serial
+    outside detection (Solver.cpp:269), so more threads only speed up the hash and the CCD."""
     from oracle import refapi
     from pies_b200 import scenes
     if not refapi.available():
         raise RuntimeError("oracle/_ref/libpies_ref.so missing (build it where /root/reference exists)")
-    cores = os.cpu_count() or 1
-    threads = max(1, min(cores, 64))
     r = refapi.RefSolver(threadCount=threads, **scenes.S3_OPTIONS)
     scenes.build_s3(r, **SAMPLE)
     per_iter = 2 * 48 * SAMPLE["bodies"]
     t0 = time.time()
     r.tick()  # first tick: stiffness assembly + first factorisation (quadratic in the reference, SURVEY F15)
     first = time.time() - t0
-    for _ in range(max(0, warmup - 1)):
+    skip = max(0, args.preroll + warmup - 1)
+    for _ in range(skip):
         r.tick()
     proj = 0
     t0 = time.time()
@@ -107,8 +113,9 @@ def run_reference(args, steps, warmup, quiet=False):
         proj += 10 * (per_iter + r.count("tri_collision") + r.count("static_collision"))
     dt = time.time() - t0
     return {"value": proj / dt, "seconds": dt, "first_tick_s": first, "cores": threads, "steps": steps,
-            "sample": "%d of %d bodies (%dx%d columns x 21 layers), ticks %d..%d" % (
-                SAMPLE["bodies"], FULL_BODIES, SAMPLE["nx"], SAMPLE["nz"], warmup, warmup + steps)}
+            "contacts_last_tick": {"point_triangle": int(r.count("tri_collision")), "floor": int(r.count("static_collision"))},
+            "sample": "%d of %d bodies (%dx%d columns x 21 layers), ticks %d..%d, threadCount %d" % (
+                SAMPLE["bodies"], FULL_BODIES, SAMPLE["nx"], SAMPLE["nz"], skip + 1, skip + 1 + steps, threads)}
 
 
 def main():
@@ -120,6 +127,7 @@ def main():
     ap.add_argument("--bodies", type=int, default=FULL_BODIES, help="debug: smaller S3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", type=float, default=4.0, help="ghost layer width along x (4.0 = two S3 columns)")
+    ap.add_argument("--preroll", type=int, default=60, help="untimed ticks before warm-up: 60 = the contact regime")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -133,13 +141,23 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        res = run_reference(args, args.steps, args.warmup)
+        res = run_reference(args, args.steps, args.warmup, threads=8)
+        cores = os.cpu_count() or 1
+        extra = None
+        if cores > 8:  # the same window with every host core in the detection phase (SURVEY section 8d asks for both)
+            try:
+                e = run_reference(args, min(args.steps, 5), args.warmup, threads=min(cores, 64))
+                extra = {"value": e["value"], "cores": e["cores"], "steps": e["steps"]}
+            except Exception as ex:
+                extra = {"error": str(ex)}
         line = {"impl": "reference", "metric": "constraint projections/s", "value": res["value"], "unit": "projections/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(config, workload=config["workload"] + " [CPU sample: " + res["sample"] + "]"),
                 "cpu_baseline": {"value": res["value"], "unit": "projections/s", "cores": res["cores"], "kind": "reference",
-                                 "sample": res["sample"], "first_tick_s": res["first_tick_s"]},
+                                 "sample": res["sample"], "first_tick_s": res["first_tick_s"], "host_cores": cores,
+                                 "all_cores_run": extra},
+                "contacts_last_tick": res["contacts_last_tick"],
                 "e2e": {"value": res["value"], "unit": "projections/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -161,7 +179,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu = run_reference(args, steps=12, warmup=min(warmup, 20), quiet=True)
+            cpu = run_reference(args, steps=10, warmup=min(warmup, 5), quiet=True, threads=8)
         except Exception as e:  # the oracle is optional here; say so instead of inventing a number
             cpu = {"error": str(e)}
 
@@ -199,6 +217,31 @@ def main():
             return drv.projections_last_tick()
         return s.stats().projectionsLastTick
 
+    # free-fall regime first (extra key): ticks 3..13, no contacts, the global solve is one exact block solve per body
+    free_fall = None
+    done_ticks = 0
+    if args.preroll >= 13:
+        for _ in range(3):
+            tick()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        f0.record(stream)
+        fproj = 0
+        fph = {"local": 0.0, "global": 0.0, "detect": 0.0, "contact": 0.0, "other": 0.0}
+        for _ in range(10):
+            tick()
+            fst = s.stats()
+            fproj += projections()
+            fph["local"] += fst.msLocal; fph["global"] += fst.msGlobal; fph["detect"] += fst.msDetect
+            fph["contact"] += fst.msContact; fph["other"] += fst.msOther
+        f1.record(stream)
+        barrier()
+        fms = f0.elapsed_time(f1)
+        free_fall = {"ticks": "3..13", "ms_per_step": fms / 10, "projections_per_s_rank0": fproj / (fms * 1e-3),
+                     "phase_ms_per_step": {k: v / 10 for k, v in fph.items()}}
+        done_ticks = 13
+    for _ in range(max(0, args.preroll - done_ticks)):
+        tick()
     for _ in range(warmup):
         tick()
     # snapshot so the device-resident and the end-to-end measurements replay the same ticks
@@ -207,7 +250,9 @@ def main():
 
     # ---- device-resident run: K ticks, state stays in HBM ----
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern = {k: [0.0, 0] for k in ("tet", "gather", "spmv", "update")}
+    kern = {k: [0.0, 0] for k in ("tet", "gather", "spmv", "update", "island")}
+    island_row_iters = 0
+    cap_hits = 0
     phases = {"local": 0.0, "global": 0.0, "detect": 0.0, "contact": 0.0, "other": 0.0}
     proj = launches = pcg_iters = 0
     barrier()
@@ -224,6 +269,9 @@ def main():
         kern["gather"][0] += st.msGatherKernel; kern["gather"][1] += st.gatherKernelLaunches
         kern["spmv"][0] += st.msSpmvKernel; kern["spmv"][1] += st.spmvKernelLaunches
         kern["update"][0] += st.msUpdateKernel; kern["update"][1] += st.updateKernelLaunches
+        kern["island"][0] += st.msIslandKernels; kern["island"][1] += st.islandKernelLaunches
+        island_row_iters += st.pcgIslandRowIterations
+        cap_hits += st.pcgCapHits
         phases["local"] += st.msLocal; phases["global"] += st.msGlobal; phases["detect"] += st.msDetect
         phases["contact"] += st.msContact; phases["other"] += st.msOther
     ev1.record(stream)
@@ -278,11 +326,17 @@ def main():
         # Algorithmic bytes per launch (the split of the 176 B per tet-type projection between the
         # kernel that writes the contributions and the gather that re-reads them is stated in DESIGN.md section 4).
         local_proj = 2 * (n // 27) * 48
-        alg = {"tet": 112 * local_proj, "gather": 64 * local_proj + 40 * n, "spmv": 8 * nnz + 64 * n, "update": 72 * n}
+        # island solves: a CG iteration of the SURVEY model costs 8 B per non-zero + 136 B per node; the island kernels ran
+        # island_row_iters x 32 row-iterations in kern["island"][1] solves (iterations differ per island)
+        isl_solves = max(1, kern["island"][1])
+        alg = {"tet": 112 * local_proj, "gather": 64 * local_proj + 40 * n, "spmv": 8 * nnz + 64 * n, "update": 72 * n,
+               "island": int(32 * island_row_iters * (8.0 * nnz / n + 136.0) / isl_solves)}
         names = {"tet": "k_tet_elems (fused tet strain+volume projection: ids, Qinv, parameters in; 4 contributions out)",
                  "gather": "k_gather_rhs (CSR gather of the contributions into the right-hand side)",
                  "spmv": "k_pcg_spmv (A z over SELL-32 windows staged by cp.async, with p / Ap recurrences)",
-                 "update": "k_pcg_update (x, r update + packed block-Jacobi apply; the preconditioner stream is not in the SURVEY model)"}
+                 "update": "k_pcg_update (x, r update + packed block-Jacobi apply; the preconditioner stream is not in the SURVEY model)",
+                 "island": "k_island_pcg<*> (one global solve = every island's whole PCG in shared memory, all tiers; bytes = the SURVEY "
+                           "CG model x the iterations each island ran, so on-chip reuse can put this above the HBM peak)"}
         traffic = {}
         traffic_file = os.path.join(ROOT, "profiles", "kernel_traffic.json")
         if os.path.exists(traffic_file):
@@ -296,7 +350,9 @@ def main():
             ms, cnt = kern[k]
             avg = ms / max(1, cnt)
             ach = alg[k] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
-            launches_per_step = (pcg_iters / args.steps) if k in ("spmv", "update") else 10.0
+            launches_per_step = 10.0
+            if k in ("spmv", "update"):
+                launches_per_step = (pcg_iters / args.steps) if kern[k][1] else 0.0
             return {"bound": "hbm", "kernel": names[k], "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                     "frac": ach / peak, "algorithmic_bytes_per_launch": alg[k], "avg_launch_ms": avg, "launches_timed": cnt,
                     "share_of_step": avg * launches_per_step / (dev_ms / args.steps),
@@ -326,6 +382,12 @@ def main():
                                              "projections_per_s": local_proj / (lr_ms * 1e-3) if lr_ms > 0 else 0.0},
             "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
             "pcg_iterations_per_step": pcg_iters / args.steps,
+            "pcg_cap_hits": int(cap_hits),
+            "islands_last_tick": {"warp": int(st.islandsTier[0]), "cta320": int(st.islandsTier[1]), "cta512": int(st.islandsTier[2]),
+                                  "cta1024": int(st.islandsTier[3]), "grid_wide": int(st.islandsGlobal),
+                                  "grid_wide_nodes": int(st.islandNodesGlobal)},
+            "tick_window": [args.preroll + warmup, args.preroll + warmup + args.steps],
+            "free_fall": free_fall,
             "contacts_last_tick": {"point_triangle": int(st.triCollisions), "floor": int(st.staticCollisions)},
         }
         if drv is not None:

@@ -29,6 +29,7 @@ extern "C" {
 #define PIES_B200_ECUDA -2    /* CUDA runtime / launch failure (also latches simFailed) */
 #define PIES_B200_ENODEV -3   /* no usable sm_100 device: there is no CPU fallback */
 #define PIES_B200_ERANGE -4   /* a scene exceeds a documented limit */
+#define PIES_B200_ENOCONV -5  /* the global solve stopped at pcgMaxIterations far from its tolerance (the tick completed; see stats) */
 
 /* Mirrors Pies::SolverOptions field for field, same defaults
  * (reference Include/Pies/Solver.h:23-38); solver: 0 = PBD, 1 = PD
@@ -67,7 +68,9 @@ typedef struct PiesB200Tuning {
   uint32_t pcgCheckEvery;    /* host polls the device convergence flag every k iterations; default 1 */
   uint32_t reserved;         /* flag bits: 1 = record per-phase CUDA-event timings into PiesB200Stats (no extra syncs);
                               * 2 = ordered contact sweeps of every cluster above 32 nodes by the dataflow executor
-                              *     (no shared-memory sweeps of mid-size clusters; same result, for testing) */
+                              *     (no shared-memory sweeps of mid-size clusters; same result, for testing);
+                              * 4 = no island-local solves: every island goes to the grid-wide CG (for testing);
+                              * 16 << t = island tier t (0..3) disabled: its islands move to the next tier that fits */
 } PiesB200Tuning;
 
 /* Counters and device-side phase timings of the most recent tick ([additive]). */
@@ -99,6 +102,18 @@ typedef struct PiesB200Stats {
   uint32_t spmvKernelLaunches;
   uint32_t updateKernelLaunches;
   uint32_t gatherKernelLaunches;
+  /* global solve by islands (connected components of S + C_t), last substep: islands solved by one warp / one CTA
+   * (tiers 0..3) and islands, with their node count, left to the grid-wide CG */
+  uint32_t islandsTier[4];
+  uint32_t islandsGlobal;
+  uint32_t islandNodesGlobal;
+  /* solves of the last tick (island-local or grid-wide) that stopped at pcgMaxIterations instead of the tolerance,
+   * and the worst relative residual among them (0 when none) */
+  uint32_t pcgCapHits;
+  float pcgWorstCapResidual;
+  float msIslandKernels;       /* time inside the island-local solve kernels (phase timing on only) */
+  uint32_t islandKernelLaunches;
+  uint64_t pcgIslandRowIterations; /* sum over island solves of iterations x ceil(rows / 32): the work the island kernels did */
 } PiesB200Stats;
 
 typedef struct PiesB200Solver PiesB200Solver;

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "contact.h"
 #include "detect.h"
+#include "islands.h"
 #include "reblock.h"
 
 namespace pies {
@@ -200,7 +201,10 @@ int ensureBuilt(PiesB200Solver* s) {
   PIES_CHECK(s, uploadVec(s->sellCol, y.sellCol, st)); PIES_CHECK(s, uploadVec(s->sellVal, y.sellVal, st));
   PIES_CHECK(s, uploadVec(s->blockNodes, y.blockNodes, st)); PIES_CHECK(s, uploadVec(s->blockInv, y.blockInv, st));
   PIES_CHECK(s, uploadVec(s->triIds, sc.triangles, st));
+  if (!s->islands) s->islands = new IslandWork();
+  if (uploadIslandStatics(*s->islands, st, y) != 0) return failCuda(s, s->islands->lastError, "uploadIslandStatics", __LINE__);
   preloadDetectKernels(); preloadContactKernels(); preloadReblockKernels(); preloadSortKernels(); preloadPcgKernels();
+  preloadIslandKernels();
   {
     // The per-substep collision buffers (detect.cu, reblock.cu, contact.cu) first appear, and later grow, in the middle
     // of a run; growing the stream-ordered pool there costs tens of milliseconds in one tick.  Reserve the pool once
@@ -260,7 +264,7 @@ int refreshVertexMirror(PiesB200Solver* s) {
 namespace {
 // Phase timing with CUDA event pairs recorded on the solver stream and resolved after the
 // tick's final synchronisation (no extra syncs inside the tick).  Enabled by tuning.reserved.
-enum Phase { kPhOther = 0, kPhDetect, kPhLocal, kPhGlobal, kPhContact, kPhTetKernel, kPhSpmvKernel, kPhUpdateKernel, kPhGatherKernel, kPhCount };
+enum Phase { kPhOther = 0, kPhDetect, kPhLocal, kPhGlobal, kPhContact, kPhTetKernel, kPhSpmvKernel, kPhUpdateKernel, kPhGatherKernel, kPhIslandKernel, kPhCount };
 struct PhaseTimer {
   PiesB200Solver* s;
   bool on;
@@ -292,7 +296,6 @@ struct PhaseTimer {
     }
   }
 };
-std::vector<cudaEvent_t> g_eventPool;
 }  // namespace
 
 int runDetection(PiesB200Solver* s, ContactLists& lists) {
@@ -329,7 +332,10 @@ struct PdTickCtx {
   ContactLists lists;
   bool inSubstep = false;
   uint32_t iterIndex = 0;  // PD iteration inside the current substep
-  PdTickCtx(PiesB200Solver* s) : timer(s, g_eventPool) {}
+  uint32_t solveIndex = 0; // global solves so far in this tick (record of IslandWork::solveStats)
+  uint64_t globalIters = 0;  // per solve: CG iterations of the grid-wide solve, kept to combine with the island counts
+  std::vector<uint32_t> globalItersPerSolve;
+  PdTickCtx(PiesB200Solver* s) : timer(s, s->eventPool) {}
 };
 
 void pdAbort(PiesB200Solver* s) {
@@ -376,10 +382,17 @@ int pdTickBegin(PiesB200Solver* s) {
   s->stats.msTetKernel = 0.0f; s->stats.tetKernelLaunches = 0;
   s->stats.msSpmvKernel = s->stats.msUpdateKernel = s->stats.msGatherKernel = 0.0f;
   s->stats.spmvKernelLaunches = s->stats.updateKernelLaunches = s->stats.gatherKernelLaunches = 0;
+  s->stats.pcgCapHits = 0; s->stats.pcgWorstCapResidual = 0.0f; s->stats.msIslandKernels = 0.0f;
+  s->stats.islandKernelLaunches = 0; s->stats.pcgIslandRowIterations = 0;
   PdTickCtx* c = new PdTickCtx(s);
   c->launches0 = s->launches;
   s->pdCtx = c;
   if (!s->n) return PIES_B200_OK;
+  if (s->islands) {
+    const size_t words = 4ull * s->opt.timeSubsteps * s->opt.iterations + 4;
+    PIES_CHECK(s, s->islands->solveStats.reserve(words));
+    PIES_CHECK(s, cudaMemsetAsync(s->islands->solveStats.p, 0, words * sizeof(uint32_t), s->stream));
+  }
   cudaEventCreate(&c->tick0); cudaEventCreate(&c->tick1);
   cudaEventRecord(c->tick0, s->stream);
   return PIES_B200_OK;
@@ -424,6 +437,20 @@ int pdSubstepBegin(PiesB200Solver* s) {
     int LC = s->contact ? prepareClusterSweeps(*s->contact, st, c->lists, ct) : 0;
     if (LC < 0) { pdAbort(s); return failCuda(s, cudaErrorMemoryAllocation, "prepareClusterSweeps", __LINE__); }
     s->launches += LC;
+    // islands of S + C_t: which solves stay inside one warp / one CTA (islands.cu)
+    if (s->islands) {
+      const uint32_t tiers = (s->tune.reserved & 4u) ? 0u : (0xFu & ~((s->tune.reserved >> 4) & 0xFu));
+      int LI = 0;
+      if (buildIslands(*s->islands, st, n, v.A, c->lists, bw.slotOf.p, bw.blockCount.p, bw.nBlocksBound, tiers, &LI) != 0) {
+        cudaError_t e = s->islands->lastError;
+        pdAbort(s);
+        return failCuda(s, e, "buildIslands", __LINE__);
+      }
+      s->launches += LI;
+      for (int t = 0; t < kIslandTiers; ++t) s->stats.islandsTier[t] = s->islands->tierCount[t];
+      s->stats.islandsGlobal = s->islands->nLeftIslands;
+      s->stats.islandNodesGlobal = s->islands->nLeftNodes;
+    }
   }
   timer.end();
   c->inSubstep = true;
@@ -458,46 +485,70 @@ int pdIteration(PiesB200Solver* s) {
   timer.end(spLocal);
 
   const int spGlobal = timer.begin(kPhGlobal);
-  int spSpmv = -1, spUpdate = -1;  // one sampled CG iteration (the second of the solve) per PD iteration
-  s->launches += launchPcgInit(st, v.A, lists, v.pw, s->rhs.p, s->q.p, s->tune.pcgTolerance);
-  // Iterations are enqueued in bursts without host round trips: converged solves turn the remaining
-  // launches into early exits (~2 us each), a host poll costs ~40 us of idle GPU, so the first burst
-  // slightly overshoots the previous solve's count.
-  // The k-th PD iteration of a substep needs about what the k-th of the previous substep needed (the first solve after
-  // the inertia step more than the later ones), which predicts the burst better than the previous solve of this substep.
   const uint32_t k = c->iterIndex++;
-  if (s->pcgItersByIteration.size() <= k) s->pcgItersByIteration.resize(k + 1, s->lastPcgIters);
-  uint32_t done = 0, burst = s->pcgItersByIteration[k] + 1;
-  bool converged = false;
-  while (!converged && done < s->tune.pcgMaxIterations) {
-    uint32_t todo = std::min(burst, s->tune.pcgMaxIterations - done);
-    for (uint32_t k = 0; k < todo; ++k) {
-      const int it = (int)(done + k);
-      if (it == 1 && timer.on) {
-        spSpmv = timer.begin(kPhSpmvKernel);
-        s->launches += launchPcgSpmv(st, v.A, lists, v.pw, s->tune.pcgTolerance, it);
-        timer.end(spSpmv);
-        spUpdate = timer.begin(kPhUpdateKernel);
-        s->launches += launchPcgUpdate(st, v.pw, s->tune.pcgTolerance, it);
-        timer.end(spUpdate);
-      } else {
-        s->launches += launchPcgIteration(st, v.A, lists, v.pw, s->tune.pcgTolerance, it);
-      }
+  const uint32_t solveSlot = c->solveIndex++;
+  uint32_t used = 0;
+  bool gridWide = true;
+  if (s->islands && s->blocks) {
+    IslandWork& iw = *s->islands;
+    const bool any = iw.tierCount[0] || iw.tierCount[1] || iw.tierCount[2] || iw.tierCount[3];
+    if (any) {
+      const int spIsl = timer.begin(kPhIslandKernel);
+      s->launches += launchIslandSolve(iw, st, v.A, lists, v.pw, s->blocks->slotOf.p, s->rhs.p, s->q.p, s->tune.pcgTolerance,
+                                       s->tune.pcgMaxIterations, solveSlot);
+      timer.end(spIsl);
     }
-    done += todo;
-    s->launches += launchPcgCheck(st, v.pw, s->tune.pcgTolerance, (int)done - 1);
-    PIES_CHECK(s, cudaMemcpyAsync(s->hostFlag, s->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    PIES_CHECK(s, cudaStreamSynchronize(st));
-    converged = s->hostFlag[0] != 0;
-    burst = std::max(4u, s->tune.pcgCheckEvery);
+    gridWide = iw.nLeftIslands != 0;
   }
-  s->launches += launchPcgFinish(st, v.pw, n, s->q.p);
-  uint32_t used = (uint32_t)s->hostFlag[1];
-  if (getenv("PIES_DEBUG_PCG")) std::fprintf(stderr, "[pcg] it: %u iterations\n", used);
-  s->lastPcgIters = std::max(1u, used);
-  s->pcgItersByIteration[k] = s->lastPcgIters;
-  s->stats.pcgIterationsLastTick += used;
-  if (used < 2) { timer.discard(spSpmv); timer.discard(spUpdate); }  // the sampled launches were early exits
+  if (gridWide) {
+    int spSpmv = -1, spUpdate = -1;  // one sampled CG iteration (the second of the solve) per PD iteration
+    s->launches += launchPcgInit(st, v.A, lists, v.pw, s->rhs.p, s->q.p, s->tune.pcgTolerance);
+    // Iterations are enqueued in bursts without host round trips: converged solves turn the remaining
+    // launches into early exits (~2 us each), a host poll costs ~40 us of idle GPU, so the first burst
+    // slightly overshoots the previous solve's count.
+    // The k-th PD iteration of a substep needs about what the k-th of the previous substep needed (the first solve after
+    // the inertia step more than the later ones), which predicts the burst better than the previous solve of this substep.
+    if (s->pcgItersByIteration.size() <= k) s->pcgItersByIteration.resize(k + 1, s->lastPcgIters);
+    uint32_t done = 0, burst = s->pcgItersByIteration[k] + 1;
+    bool converged = false;
+    while (!converged && done < s->tune.pcgMaxIterations) {
+      uint32_t todo = std::min(burst, s->tune.pcgMaxIterations - done);
+      for (uint32_t j = 0; j < todo; ++j) {
+        const int it = (int)(done + j);
+        if (it == 1 && timer.on) {
+          spSpmv = timer.begin(kPhSpmvKernel);
+          s->launches += launchPcgSpmv(st, v.A, lists, v.pw, s->tune.pcgTolerance, it);
+          timer.end(spSpmv);
+          spUpdate = timer.begin(kPhUpdateKernel);
+          s->launches += launchPcgUpdate(st, v.pw, s->tune.pcgTolerance, it);
+          timer.end(spUpdate);
+        } else {
+          s->launches += launchPcgIteration(st, v.A, lists, v.pw, s->tune.pcgTolerance, it);
+        }
+      }
+      done += todo;
+      s->launches += launchPcgCheck(st, v.pw, s->tune.pcgTolerance, (int)done - 1);
+      PIES_CHECK(s, cudaMemcpyAsync(s->hostFlag, s->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+      PIES_CHECK(s, cudaMemcpyAsync(s->hostFlag + 2, s->scalars.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+      PIES_CHECK(s, cudaStreamSynchronize(st));
+      converged = s->hostFlag[0] != 0;
+      burst = std::max(4u, s->tune.pcgCheckEvery);
+    }
+    s->launches += launchPcgFinish(st, v.pw, n, s->q.p);
+    used = (uint32_t)s->hostFlag[1];
+    if (getenv("PIES_DEBUG_PCG")) std::fprintf(stderr, "[pcg] it: %u iterations\n", used);
+    s->lastPcgIters = std::max(1u, used);
+    s->pcgItersByIteration[k] = s->lastPcgIters;
+    if (used < 2) { timer.discard(spSpmv); timer.discard(spUpdate); }  // the sampled launches were early exits
+    float rel;
+    std::memcpy(&rel, s->hostFlag + 2, sizeof(float));
+    s->stats.pcgLastRelResidual = rel;
+    if (!converged) {  // stopped at the cap: say so (pdTickEnd turns a residual far above the tolerance into an error)
+      ++s->stats.pcgCapHits;
+      s->stats.pcgWorstCapResidual = std::max(s->stats.pcgWorstCapResidual, rel);
+    }
+  }
+  c->globalItersPerSolve.push_back(used);
   timer.end(spGlobal);
   s->stats.projectionsLastTick += y.staticProjections + lists.nTri + lists.nFloor;
   return PIES_B200_OK;
@@ -555,21 +606,46 @@ int pdTickEnd(PiesB200Solver* s, bool refreshMirror) {
     s->stats.msSpmvKernel = acc[kPhSpmvKernel]; s->stats.spmvKernelLaunches = cnt[kPhSpmvKernel];
     s->stats.msUpdateKernel = acc[kPhUpdateKernel]; s->stats.updateKernelLaunches = cnt[kPhUpdateKernel];
     s->stats.msGatherKernel = acc[kPhGatherKernel]; s->stats.gatherKernelLaunches = cnt[kPhGatherKernel];
+    s->stats.msIslandKernels = acc[kPhIslandKernel]; s->stats.islandKernelLaunches = cnt[kPhIslandKernel];
   }
   uint64_t launches0 = c->launches0;
+  const std::vector<uint32_t> solves = c->globalItersPerSolve;
   pdAbort(s);
   PIES_CHECK(s, cudaGetLastError());
+  int rcConv = PIES_B200_OK;
   {
-    float rel = 0.0f;
-    cudaMemcpy(&rel, s->scalars.p, sizeof(float), cudaMemcpyDeviceToHost);
-    s->stats.pcgLastRelResidual = rel;
+    // per-solve records of the island kernels (max iterations, work, islands stopped at the cap, their worst residual)
+    // combined with the grid-wide CG's counts: a solve took as many iterations as its slowest part
+    const size_t nSolves = solves.size();
+    std::vector<uint32_t> rec(4 * nSolves + 4, 0u);
+    if (s->islands && s->islands->solveStats.p && nSolves)
+      PIES_CHECK(s, cudaMemcpy(rec.data(), s->islands->solveStats.p, 4 * nSolves * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nSolves; ++i) {
+      s->stats.pcgIterationsLastTick += std::max(solves[i], rec[4 * i]);
+      s->stats.pcgIslandRowIterations += rec[4 * i + 1];
+      if (rec[4 * i + 2]) {
+        s->stats.pcgCapHits += rec[4 * i + 2];
+        float rel;
+        std::memcpy(&rel, &rec[4 * i + 3], sizeof(float));
+        s->stats.pcgWorstCapResidual = std::max(s->stats.pcgWorstCapResidual, rel);
+      }
+    }
+    // Stopping at the cap a little above the tolerance is fp32 stagnation and only counted; far above it the solve
+    // did not converge and the caller must know (the reference's Cholesky cannot fail this way).
+    if (s->stats.pcgCapHits && s->stats.pcgWorstCapResidual > 1000.0f * s->tune.pcgTolerance) {
+      char buf[256];
+      std::snprintf(buf, sizeof(buf), "global solve not converged: %u solves stopped at pcgMaxIterations = %u, worst relative residual %.3g (tolerance %.3g)",
+                    s->stats.pcgCapHits, s->tune.pcgMaxIterations, s->stats.pcgWorstCapResidual, s->tune.pcgTolerance);
+      s->err = buf;
+      rcConv = PIES_B200_ENOCONV;
+    }
   }
   s->mirrorStale = true;
   int rc;
   if (refreshMirror && (rc = refreshVertexMirror(s))) return rc;
   s->stats.kernelLaunchesLastTick = s->launches - launches0;
   s->stats.simFailed = s->simFailed ? 1u : 0u;
-  return PIES_B200_OK;
+  return rcConv;
 }
 
 // contacts of the last detection whose point node (point-triangle) / node (floor) this solver owns
@@ -622,6 +698,8 @@ PiesB200Solver::~PiesB200Solver() {
   pies::destroyPbdWork(pbd);
   pies::pdAbort(this);
   if (blocks) { if (blocks->host) cudaFreeHost(blocks->host); delete blocks; }
+  delete islands;
+  for (cudaEvent_t e : eventPool) cudaEventDestroy(e);
   if (hostPacked) cudaFreeHost(hostPacked);
   if (hostFlag) cudaFreeHost(hostFlag);
   if (ownStream && stream) cudaStreamDestroy(stream);

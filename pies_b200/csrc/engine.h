@@ -46,6 +46,7 @@ struct DevBuf {
 struct DetectWork;   // detect.cu
 struct ContactWork;  // contact.cu
 struct BlockWork;    // reblock.cu
+struct IslandWork;   // islands.cu
 struct PbdWork;      // pbd.cu
 void destroyPbdWork(PbdWork* w);
 
@@ -93,6 +94,7 @@ struct PiesB200Solver {
   pies::DetectWork* detect = nullptr;
   pies::ContactWork* contact = nullptr;
   pies::BlockWork* blocks = nullptr;
+  pies::IslandWork* islands = nullptr;
   pies::PbdWork* pbd = nullptr;
   void* pdCtx = nullptr;          // PdTickCtx of a tick in progress (engine.cu)
   pies::DevBuf<uint32_t> triOrder; bool haveTriOrder = false;  // canonical-order override (slab-partitioned hosts)
@@ -103,6 +105,7 @@ struct PiesB200Solver {
   size_t hostPackedCap = 0;
   int* hostFlag = nullptr;      // pinned, 4 ints
   uint32_t lastPcgIters = 1;
+  std::vector<cudaEvent_t> eventPool;  // phase-timing events of this solver (created on its device)
   std::vector<uint32_t> pcgItersByIteration;  // CG iterations the k-th PD iteration of the previous substep needed (burst prediction)
   uint64_t launches = 0;
 

@@ -1,0 +1,766 @@
+// islands.cu — the global step of Projective Dynamics solved island by island.
+//
+// The reference factorises S + C_t as one sparse matrix every substep and solves with it (reference
+// Src/Solver.cpp:242-262 SimplicialLLT(S + C_t), :356 solve).  That matrix is block diagonal: S couples only the nodes
+// of one body, and the collision terms C_t (CollisionConstraint.cpp:74-83) couple bodies only where a point-triangle
+// contact joins them.  A connected component of its graph — an "island": static bodies united through this substep's
+// contacts — is an independent linear system, and nearly all of them are small (a free body; a column of stacked
+// boxes).  So instead of a grid-wide CG whose every iteration streams the whole matrix from HBM and synchronises the
+// device twice, every island is solved by its own team (a warp or one CTA) that keeps the island's matrix, the
+// inverses of its preconditioner blocks and the CG vectors in shared memory for the whole solve, iterates with team
+// barriers only, and stops on its own residual:  ||r_island|| <= tol ||b_island||  per coordinate column (a stricter
+// test than the same bound on the global norms).  Only islands too large for one CTA go to the grid-wide CG (pcg.cu).
+//
+// Determinism: the island order (bodies ascending inside an island, nodes ascending inside a body) comes from a
+// stable sort, every dot product is reduced in a fixed order inside the team, no float atomics.
+#include "islands.h"
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace pies {
+
+static inline int gridFor(uint64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------------ builder ----
+__device__ __forceinline__ uint32_t islFind(uint32_t* parent, uint32_t x) {
+  uint32_t p = *(volatile uint32_t*)(parent + x);
+  while (p != x) { x = p; p = *(volatile uint32_t*)(parent + x); }
+  return x;
+}
+__device__ __forceinline__ void islUnite(uint32_t* parent, uint32_t u, uint32_t v) {
+  while (true) {
+    u = islFind(parent, u);
+    v = islFind(parent, v);
+    if (u == v) return;
+    if (u < v) { uint32_t t = u; u = v; v = t; }  // hook the larger root under the smaller one
+    uint32_t old = atomicMin(parent + u, v);
+    if (old == u) return;
+    u = old;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_isl_init(uint32_t nB, uint32_t* __restrict__ parent) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nB) parent[b] = b;
+}
+
+__global__ void __launch_bounds__(kThreads) k_isl_unite(uint32_t nU, const uint4* __restrict__ uTri,
+                                                        const uint32_t* __restrict__ bodyOf, uint32_t* __restrict__ parent) {
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nU) return;
+  const uint4 id = uTri[e];
+  const uint32_t a = bodyOf[id.x], b = bodyOf[id.y], c = bodyOf[id.z], d = bodyOf[id.w];
+  if (a != b) islUnite(parent, a, b);
+  if (c != b) islUnite(parent, b, c);
+  if (d != b && d != c) islUnite(parent, b, d);
+}
+
+// sort keys: the island's root body; payload: the body.  Without contacts every body is its own island.
+__global__ void __launch_bounds__(kThreads) k_isl_keys(uint32_t nB, uint32_t* __restrict__ parent, int united,
+                                                       uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nB) return;
+  keys[b] = united ? islFind(parent, b) : b;
+  vals[b] = b;
+}
+
+// per sorted body: head flag (to be scanned into the island index) and node count (to be scanned into node offsets)
+__global__ void __launch_bounds__(kThreads) k_isl_heads(uint32_t nB, const uint64_t* __restrict__ keys,
+                                                        const uint32_t* __restrict__ vals, const uint32_t* __restrict__ bodyPtr,
+                                                        uint32_t* __restrict__ heads, uint32_t* __restrict__ nodeOff,
+                                                        uint32_t* __restrict__ posOfBody) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > nB) return;
+  if (j == nB) { heads[j] = 0; nodeOff[j] = 0; return; }
+  heads[j] = (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
+  const uint32_t b = vals[j];
+  nodeOff[j] = bodyPtr[b + 1] - bodyPtr[b];
+  posOfBody[b] = j;
+}
+
+__global__ void __launch_bounds__(kThreads) k_isl_starts(uint32_t nB, uint32_t n, const uint64_t* __restrict__ keys,
+                                                         const uint32_t* __restrict__ headScan,
+                                                         const uint32_t* __restrict__ nodeOff, uint32_t* __restrict__ islStart,
+                                                         uint32_t* __restrict__ counts) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nB) return;
+  const bool head = j == 0 || keys[j] != keys[j - 1];
+  if (head) islStart[headScan[j]] = nodeOff[j];
+  if (j == nB - 1) {
+    const uint32_t nIsl = headScan[nB];
+    islStart[nIsl] = n;
+    counts[0] = nIsl;
+  }
+}
+
+// island order of the nodes, its inverse, and the row lengths of S + C_t in that order (to be scanned)
+__global__ void __launch_bounds__(kThreads) k_isl_nodes(uint32_t n, const uint32_t* __restrict__ bodyOf,
+                                                        const uint32_t* __restrict__ rankInBody,
+                                                        const uint32_t* __restrict__ posOfBody,
+                                                        const uint32_t* __restrict__ nodeOff, const int* __restrict__ rowPtr,
+                                                        const int* __restrict__ cPtr, uint32_t* __restrict__ order,
+                                                        uint32_t* __restrict__ pos, uint32_t* __restrict__ nnzOff) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { nnzOff[n] = 0; return; }
+  const uint32_t p = nodeOff[posOfBody[bodyOf[i]]] + rankInBody[i];
+  order[p] = i;
+  pos[i] = p;
+  uint32_t len = (uint32_t)(rowPtr[i + 1] - rowPtr[i]);
+  if (cPtr) len += (uint32_t)(cPtr[i + 1] - cPtr[i]);
+  nnzOff[p] = len;
+}
+
+struct IslandTierTable { IslandCaps caps[kIslandTiers]; uint32_t enabled; };
+
+__global__ void __launch_bounds__(kThreads) k_isl_classify(const uint32_t* counts0, IslandTierTable tt,
+                                                           const uint32_t* __restrict__ islStart,
+                                                           const uint32_t* __restrict__ nnzOff, const uint32_t* __restrict__ order,
+                                                           const uint32_t* __restrict__ slotOf,
+                                                           const uint32_t* __restrict__ blockCount, uint32_t listStride,
+                                                           uint32_t* __restrict__ tierList, uint32_t* counts) {
+  uint32_t isl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (isl >= counts0[0]) return;
+  const uint32_t s0 = islStart[isl], m = islStart[isl + 1] - s0;
+  const uint32_t nnz = nnzOff[s0 + m] - nnzOff[s0];
+  int tier = kIslandTiers;
+  for (int t = 0; t < kIslandTiers; ++t) {
+    if (!((tt.enabled >> t) & 1u)) continue;
+    if (m > tt.caps[t].maxNodes || (tt.caps[t].maxNnz && nnz > tt.caps[t].maxNnz)) continue;
+    if (t == 0 && blockCount[slotOf[order[s0]] >> 5] != m) continue;  // the warp tier wants the island in ONE preconditioner block
+    tier = t;
+    break;
+  }
+  const uint32_t at = atomicAdd(counts + 1 + tier, 1u);  // list order only decides scheduling: islands are independent
+  tierList[(size_t)tier * listStride + at] = isl;
+  if (tier == kIslandTiers) atomicAdd(counts + 2 + kIslandTiers, m);
+}
+
+// ------------------------------------------------------------------------------------------------ solver ----
+struct IslandLayout { uint32_t r, p, val, inv, blkOff, blkSrc, col, members, leader, blkM, red, ctr, total; };
+
+static IslandLayout islandLayout(const IslandCaps& c, int team, bool matSmem) {
+  IslandLayout L{};
+  uint32_t off = 0;
+  auto take = [&](uint32_t bytes) { uint32_t at = off; off += (bytes + 15u) & ~15u; return at; };
+  L.r = take(16u * c.maxNodes);
+  L.p = take(16u * c.maxNodes);
+  L.val = take(matSmem ? 4u * c.maxNnz : 0u);
+  L.inv = take(4u * c.maxInv);
+  L.blkOff = take(4u * c.maxBlocks);
+  L.blkSrc = take(4u * c.maxBlocks);
+  L.col = take(matSmem ? 2u * c.maxNnz : 0u);
+  L.members = take(64u * c.maxBlocks);
+  L.leader = take(c.maxBlocks ? 2u * c.maxNodes : 0u);
+  L.blkM = take(c.maxBlocks);
+  L.red = take(team > 32 ? 2u * 9u * 32u * 4u : 0u);
+  L.ctr = take(16u);
+  L.total = off;
+  return L;
+}
+
+struct IslandArgs {
+  const uint32_t* counts; const uint32_t* tierList; uint32_t listStride;
+  const uint32_t* islStart; const uint32_t* order; const uint32_t* pos; const uint32_t* nnzOff;
+  const int* rowPtr; const int* col; const float* val;
+  const int* cPtr; const int* cCol; const float* cVal; const float* cDiag;
+  const uint32_t* slotOf; const int* blockNodes; const float* blockInv; const uint2* blockMeta;
+  uint32_t* blkLocal;          // block * 32 + lane -> local row of that member (scratch, written per solve)
+  int* matCol; float* matVal;  // tier 3 scratch copy of the matrix in island-local indices
+  float4* deltaScratch;        // tier 3: accumulated correction, island order
+  float4* apScratch; float4* zScratch; uint32_t* slotIsl;  // tier 3: A p, z and the preconditioner slot per row, island order
+  const float4* b; float4* x;
+  float tol2; uint32_t maxIter; uint32_t* stats;
+};
+
+template <int TEAM>
+__device__ __forceinline__ void teamSync() {
+  if (TEAM == 32) __syncwarp(); else __syncthreads();
+}
+
+// Fixed-order sum of K values per thread over the team; every thread gets the result.  CTA teams alternate between
+// two scratch buffers, so one barrier per reduction is enough.
+template <int TEAM, int K>
+__device__ __forceinline__ void teamReduce(float (&v)[K], float* __restrict__ sRed, int& phase, int tid) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warpSum(v[k]);
+  if (TEAM == 32) return;
+  float* buf = sRed + phase * (9 * 32);
+  phase ^= 1;
+  const int lane = tid & 31, warp = tid >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) buf[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float t = lane < TEAM / 32 ? buf[k * 32 + lane] : 0.0f;
+    v[k] = warpSum(t);
+  }
+}
+
+template <int TEAM, int RPT, bool MAT_SMEM>
+__global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEAM <= 320 ? 2 : 1)) k_island_pcg(IslandArgs a, IslandLayout L, IslandCaps caps, int tier) {
+  extern __shared__ __align__(16) unsigned char islSmem[];
+  constexpr int kTeams = TEAM == 32 ? 8 : 1;
+  constexpr bool kDeltaGlobal = !MAT_SMEM;
+  using ColT = typename std::conditional<MAT_SMEM, uint16_t, int>::type;
+  const int team = TEAM == 32 ? (int)(threadIdx.x >> 5) : 0;
+  const int tid = TEAM == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  unsigned char* base = islSmem + (size_t)team * L.total;
+  float4* sR = reinterpret_cast<float4*>(base + L.r);
+  float4* sP = reinterpret_cast<float4*>(base + L.p);
+  float* sInv = reinterpret_cast<float*>(base + L.inv);
+  uint32_t* sBlkOff = reinterpret_cast<uint32_t*>(base + L.blkOff);
+  uint32_t* sBlkSrc = reinterpret_cast<uint32_t*>(base + L.blkSrc);
+  uint16_t* sMem = reinterpret_cast<uint16_t*>(base + L.members);
+  uint16_t* sLeader = reinterpret_cast<uint16_t*>(base + L.leader);
+  uint8_t* sBlkM = reinterpret_cast<uint8_t*>(base + L.blkM);
+  float* sRed = reinterpret_cast<float*>(base + L.red);
+  uint32_t* sCtr = reinterpret_cast<uint32_t*>(base + L.ctr);
+  const uint32_t count = a.counts[1 + tier];
+  const uint32_t* list = a.tierList + (size_t)tier * a.listStride;
+  int phase = 0;
+  for (uint32_t wi = blockIdx.x * kTeams + team; wi < count; wi += gridDim.x * kTeams) {
+    const uint32_t isl = list[wi];
+    const uint32_t s0 = a.islStart[isl], m = a.islStart[isl + 1] - s0;
+    const uint32_t z0 = a.nnzOff[s0];
+    float* mv = MAT_SMEM ? reinterpret_cast<float*>(base + L.val) : a.matVal + z0;
+    ColT* mc = MAT_SMEM ? reinterpret_cast<ColT*>(base + L.col) : reinterpret_cast<ColT*>(a.matCol + z0);
+    if (tid == 0) { sCtr[0] = 0; sCtr[1] = 0; }
+    teamSync<TEAM>();
+    // ---- stage the island: matrix rows in local indices (collision diagonal folded into the diagonal entry), the
+    //      fp64 start residual r = b - A x (b and A x agree to ~7 digits and the difference is what matters), blocks
+    uint32_t rs[RPT], rn[RPT], rb[RPT], slot[RPT], gid[RPT];
+    float dl[RPT][3];
+    float red9[9] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // r.z (3), r.r (3), b.b (3)
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+      rs[k] = 0; rn[k] = 0; rb[k] = 0xffffffffu; slot[k] = 0; gid[k] = 0;
+      dl[k][0] = dl[k][1] = dl[k][2] = 0.0f;
+      if (l >= m) continue;
+      const uint32_t g = a.order[s0 + l];
+      gid[k] = g;
+      const uint32_t rstart = a.nnzOff[s0 + l] - z0, rend = a.nnzOff[s0 + l + 1] - z0;
+      rs[k] = rstart; rn[k] = rend - rstart;
+      const float4 xi = a.x[g], bi = a.b[g];
+      const float cd = a.cDiag ? a.cDiag[g] : 0.0f;
+      double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+      uint32_t e = rstart;
+      for (int kk = a.rowPtr[g]; kk < a.rowPtr[g + 1]; ++kk, ++e) {
+        const int c = __ldg(a.col + kk);
+        float v = __ldg(a.val + kk);
+        const float4 xv = a.x[c];
+        y0 += (double)v * (double)xv.x; y1 += (double)v * (double)xv.y; y2 += (double)v * (double)xv.z;
+        uint32_t lc = a.pos[c] - s0;
+        if (lc >= m) { lc = l; v = 0.0f; }  // explicit zeros may point outside the body (bend stencils): drop them
+        if ((uint32_t)c == g) v += cd;
+        mc[e] = (ColT)lc; mv[e] = v;
+      }
+      if (a.cPtr) {
+        for (int kk = a.cPtr[g]; kk < a.cPtr[g + 1]; ++kk, ++e) {
+          const int c = a.cCol[kk];
+          const float v = a.cVal[kk];
+          const float4 xv = a.x[c];
+          y0 += (double)v * (double)xv.x; y1 += (double)v * (double)xv.y; y2 += (double)v * (double)xv.z;
+          mc[e] = (ColT)(a.pos[c] - s0); mv[e] = v;
+        }
+      }
+      y0 += (double)cd * (double)xi.x; y1 += (double)cd * (double)xi.y; y2 += (double)cd * (double)xi.z;
+      sR[l] = make_float4((float)((double)bi.x - y0), (float)((double)bi.y - y1), (float)((double)bi.z - y2), 0.0f);
+      red9[6] += bi.x * bi.x; red9[7] += bi.y * bi.y; red9[8] += bi.z * bi.z;
+      if (kDeltaGlobal) a.deltaScratch[s0 + l] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      const uint32_t sl = a.slotOf[g];
+      slot[k] = sl;
+      a.blkLocal[sl] = l;
+      if (caps.maxBlocks) {
+        sLeader[l] = 0xffffu;
+        if ((sl & 31u) == 0u) {  // first member of its block: claim a table entry and room for the inverse
+          const uint2 meta = a.blockMeta[sl >> 5];
+          const uint32_t size = (meta.y * (meta.y + 1u) / 2u + 3u) & ~3u;
+          const uint32_t idx = atomicAdd(sCtr, 1u);
+          if (idx < caps.maxBlocks) {
+            const uint32_t off = atomicAdd(sCtr + 1, size);
+            if (off + size <= caps.maxInv) { sBlkOff[idx] = off; sBlkSrc[idx] = meta.x; sBlkM[idx] = (uint8_t)meta.y; sLeader[l] = (uint16_t)idx; }
+            else sBlkM[idx] = 0;
+          }
+        }
+      }
+    }
+    teamSync<TEAM>();
+    if (caps.maxBlocks) {
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+        if (l >= m) continue;
+        const uint32_t lead = a.pos[a.blockNodes[(slot[k] >> 5) * 32]] - s0;
+        const uint32_t idx = sLeader[lead];
+        if (idx != 0xffffu) { rb[k] = (idx << 5) | (slot[k] & 31u); sMem[idx * 32 + (slot[k] & 31u)] = (uint16_t)l; }
+      }
+      teamSync<TEAM>();
+      // inverses: one warp per block, 16 B per lane and step
+      const uint32_t nBlk = min(sCtr[0], caps.maxBlocks);
+      for (uint32_t idx = (uint32_t)tid >> 5; idx < nBlk; idx += TEAM / 32) {
+        const uint32_t mB = sBlkM[idx];
+        if (!mB) continue;
+        const uint32_t size4 = (mB * (mB + 1u) / 2u + 3u) >> 2;
+        const float4* src = reinterpret_cast<const float4*>(a.blockInv + sBlkSrc[idx]);
+        float4* dst = reinterpret_cast<float4*>(sInv + sBlkOff[idx]);
+        for (uint32_t t = (uint32_t)tid & 31u; t < size4; t += 32u) dst[t] = __ldg(src + t);
+      }
+    }
+    teamSync<TEAM>();
+
+    // z = Minv r for one of this thread's rows
+    auto precond = [&](int k, float (&z)[3]) {
+      z[0] = z[1] = z[2] = 0.0f;
+      if (rb[k] != 0xffffffffu) {
+        const uint32_t idx = rb[k] >> 5;
+        const int lane = (int)(rb[k] & 31u), mB = (int)sBlkM[idx];
+        const float* inv = sInv + sBlkOff[idx];
+        const uint16_t* mem = sMem + idx * 32;
+        int off = lane * (lane + 1) / 2;
+#pragma unroll 3
+        for (int j = 0; j < mB; ++j) {
+          const float w = inv[off];
+          const float4 rj = sR[mem[j]];
+          z[0] = fmaf(w, rj.x, z[0]); z[1] = fmaf(w, rj.y, z[1]); z[2] = fmaf(w, rj.z, z[2]);
+          off += j < lane ? 1 : j + 1;
+        }
+      } else {  // block not resident (tier 3, or the island has more blocks than the tier's table): same sum from global memory
+        const uint32_t b = slot[k] >> 5;
+        const int lane = (int)(slot[k] & 31u);
+        const uint2 meta = a.blockMeta[b];
+        const float* inv = a.blockInv + meta.x;
+        const uint32_t* loc = a.blkLocal + (size_t)b * 32;
+        int off = lane * (lane + 1) / 2;
+        for (int j = 0; j < (int)meta.y; ++j) {
+          const float w = __ldg(inv + off);
+          const float4 rj = sR[loc[j]];
+          z[0] = fmaf(w, rj.x, z[0]); z[1] = fmaf(w, rj.y, z[1]); z[2] = fmaf(w, rj.z, z[2]);
+          off += j < lane ? 1 : j + 1;
+        }
+      }
+    };
+
+    // ---- CG on the correction delta (x is updated once at the end: a single rounding of the sum)
+    float zz[RPT][3];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+      if (l >= m) continue;
+      precond(k, zz[k]);
+      const float4 r = sR[l];
+      red9[0] += r.x * zz[k][0]; red9[1] += r.y * zz[k][1]; red9[2] += r.z * zz[k][2];
+      red9[3] += r.x * r.x; red9[4] += r.y * r.y; red9[5] += r.z * r.z;
+      sP[l] = make_float4(zz[k][0], zz[k][1], zz[k][2], 0.0f);
+    }
+    teamReduce<TEAM, 9>(red9, sRed, phase, tid);
+    float rz[3] = {red9[0], red9[1], red9[2]};
+    float rr[3] = {red9[3], red9[4], red9[5]};
+    const float bb[3] = {red9[6], red9[7], red9[8]};
+    auto converged = [&]() {
+      return rr[0] <= a.tol2 * bb[0] + 1e-36f && rr[1] <= a.tol2 * bb[1] + 1e-36f && rr[2] <= a.tol2 * bb[2] + 1e-36f;
+    };
+    teamSync<TEAM>();  // p visible
+    uint32_t iters = 0;
+    bool conv = converged();
+    while (!conv && iters < a.maxIter) {
+      float ap[RPT][3];
+      float pap[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+        ap[k][0] = ap[k][1] = ap[k][2] = 0.0f;
+        if (l >= m) continue;
+        const uint32_t e1 = rs[k] + rn[k];
+#pragma unroll 4
+        for (uint32_t e = rs[k]; e < e1; ++e) {
+          const float v = mv[e];
+          const float4 pv = sP[mc[e]];
+          ap[k][0] = fmaf(v, pv.x, ap[k][0]); ap[k][1] = fmaf(v, pv.y, ap[k][1]); ap[k][2] = fmaf(v, pv.z, ap[k][2]);
+        }
+        const float4 pl = sP[l];
+        pap[0] += pl.x * ap[k][0]; pap[1] += pl.y * ap[k][1]; pap[2] += pl.z * ap[k][2];
+      }
+      teamReduce<TEAM, 3>(pap, sRed, phase, tid);
+      float alpha[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) alpha[c] = pap[c] > 0.0f ? rz[c] / pap[c] : 0.0f;
+      float rl[RPT][3];
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+        if (l >= m) continue;
+        const float4 pl = sP[l];
+        if (kDeltaGlobal) {
+          float4 d = a.deltaScratch[s0 + l];
+          d.x = fmaf(alpha[0], pl.x, d.x); d.y = fmaf(alpha[1], pl.y, d.y); d.z = fmaf(alpha[2], pl.z, d.z);
+          a.deltaScratch[s0 + l] = d;
+        } else {
+          dl[k][0] = fmaf(alpha[0], pl.x, dl[k][0]); dl[k][1] = fmaf(alpha[1], pl.y, dl[k][1]); dl[k][2] = fmaf(alpha[2], pl.z, dl[k][2]);
+        }
+        const float4 r = sR[l];
+        rl[k][0] = fmaf(-alpha[0], ap[k][0], r.x); rl[k][1] = fmaf(-alpha[1], ap[k][1], r.y); rl[k][2] = fmaf(-alpha[2], ap[k][2], r.z);
+        sR[l] = make_float4(rl[k][0], rl[k][1], rl[k][2], 0.0f);
+      }
+      teamSync<TEAM>();  // r visible
+      float red6[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+        if (l >= m) continue;
+        precond(k, zz[k]);
+        red6[0] += rl[k][0] * zz[k][0]; red6[1] += rl[k][1] * zz[k][1]; red6[2] += rl[k][2] * zz[k][2];
+        red6[3] += rl[k][0] * rl[k][0]; red6[4] += rl[k][1] * rl[k][1]; red6[5] += rl[k][2] * rl[k][2];
+      }
+      teamReduce<TEAM, 6>(red6, sRed, phase, tid);
+      float beta[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { beta[c] = rz[c] > 0.0f ? red6[c] / rz[c] : 0.0f; rz[c] = red6[c]; rr[c] = red6[3 + c]; }
+      ++iters;
+      conv = converged();
+      if (conv) break;
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+        if (l >= m) continue;
+        const float4 pl = sP[l];
+        sP[l] = make_float4(fmaf(beta[0], pl.x, zz[k][0]), fmaf(beta[1], pl.y, zz[k][1]), fmaf(beta[2], pl.z, zz[k][2]), 0.0f);
+      }
+      teamSync<TEAM>();  // p visible
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+      if (l >= m) continue;
+      float4 xv = a.x[gid[k]];
+      if (kDeltaGlobal) {
+        const float4 d = a.deltaScratch[s0 + l];
+        xv.x += d.x; xv.y += d.y; xv.z += d.z;
+      } else {
+        xv.x += dl[k][0]; xv.y += dl[k][1]; xv.z += dl[k][2];
+      }
+      a.x[gid[k]] = xv;
+    }
+    if (tid == 0) {
+      atomicMax(a.stats, iters);
+      atomicAdd(a.stats + 1, iters * ((m + 31u) >> 5));
+      if (!conv) {
+        float rel = 0.0f;
+        for (int c = 0; c < 3; ++c) if (bb[c] > 0.0f) rel = fmaxf(rel, rr[c] / bb[c]);
+        atomicAdd(a.stats + 2, 1u);
+        atomicMax(a.stats + 3, __float_as_uint(sqrtf(rel)));
+      }
+    }
+    teamSync<TEAM>();  // the team's shared memory is restaged for its next island
+  }
+}
+
+// Tier 3: islands of up to a few thousand nodes (a tetrahedralised body of config 5; several toppled columns of the S3
+// stack).  One 1024-thread CTA per island; r and p (what other rows gather) live in shared memory, per-row state that only
+// its own thread touches (delta, A p, z) in global scratch in island order, the matrix in an island-local copy in global
+// memory that stays in L2 while the CTA re-reads it every iteration, block inverses straight from the preconditioner tables.
+constexpr int kBigTeam = 1024;
+__global__ void __launch_bounds__(kBigTeam) k_island_pcg_big(IslandArgs a, uint32_t maxNodes, int tier) {
+  extern __shared__ __align__(16) unsigned char islSmem[];
+  float4* sR = reinterpret_cast<float4*>(islSmem);
+  float4* sP = sR + maxNodes;
+  float* sRed = reinterpret_cast<float*>(sP + maxNodes);
+  const int tid = (int)threadIdx.x;
+  const uint32_t count = a.counts[1 + tier];
+  const uint32_t* list = a.tierList + (size_t)tier * a.listStride;
+  int phase = 0;
+  for (uint32_t wi = blockIdx.x; wi < count; wi += gridDim.x) {
+    const uint32_t isl = list[wi];
+    const uint32_t s0 = a.islStart[isl], m = a.islStart[isl + 1] - s0;
+    const uint32_t z0 = a.nnzOff[s0];
+    float* mv = a.matVal + z0;
+    int* mc = a.matCol + z0;
+    float red9[9] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    for (uint32_t l = (uint32_t)tid; l < m; l += kBigTeam) {
+      const uint32_t g = a.order[s0 + l];
+      const float4 xi = a.x[g], bi = a.b[g];
+      const float cd = a.cDiag ? a.cDiag[g] : 0.0f;
+      double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+      uint32_t e = a.nnzOff[s0 + l] - z0;
+      for (int kk = a.rowPtr[g]; kk < a.rowPtr[g + 1]; ++kk, ++e) {
+        const int c = __ldg(a.col + kk);
+        float v = __ldg(a.val + kk);
+        const float4 xv = a.x[c];
+        y0 += (double)v * (double)xv.x; y1 += (double)v * (double)xv.y; y2 += (double)v * (double)xv.z;
+        uint32_t lc = a.pos[c] - s0;
+        if (lc >= m) { lc = l; v = 0.0f; }
+        if ((uint32_t)c == g) v += cd;
+        mc[e] = (int)lc; mv[e] = v;
+      }
+      if (a.cPtr) {
+        for (int kk = a.cPtr[g]; kk < a.cPtr[g + 1]; ++kk, ++e) {
+          const int c = a.cCol[kk];
+          const float v = a.cVal[kk];
+          const float4 xv = a.x[c];
+          y0 += (double)v * (double)xv.x; y1 += (double)v * (double)xv.y; y2 += (double)v * (double)xv.z;
+          mc[e] = (int)(a.pos[c] - s0); mv[e] = v;
+        }
+      }
+      y0 += (double)cd * (double)xi.x; y1 += (double)cd * (double)xi.y; y2 += (double)cd * (double)xi.z;
+      sR[l] = make_float4((float)((double)bi.x - y0), (float)((double)bi.y - y1), (float)((double)bi.z - y2), 0.0f);
+      red9[6] += bi.x * bi.x; red9[7] += bi.y * bi.y; red9[8] += bi.z * bi.z;
+      a.deltaScratch[s0 + l] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      const uint32_t sl = a.slotOf[g];
+      a.slotIsl[s0 + l] = sl;
+      a.blkLocal[sl] = l;
+    }
+    __syncthreads();
+    auto precond = [&](uint32_t l, float (&z)[3]) {
+      const uint32_t sl = a.slotIsl[s0 + l];
+      const uint32_t b = sl >> 5;
+      const int lane = (int)(sl & 31u);
+      const uint2 meta = a.blockMeta[b];
+      const float* inv = a.blockInv + meta.x;
+      const uint32_t* loc = a.blkLocal + (size_t)b * 32;
+      int off = lane * (lane + 1) / 2;
+      z[0] = z[1] = z[2] = 0.0f;
+#pragma unroll 4
+      for (int j = 0; j < (int)meta.y; ++j) {
+        const float w = __ldg(inv + off);
+        const float4 rj = sR[loc[j]];
+        z[0] = fmaf(w, rj.x, z[0]); z[1] = fmaf(w, rj.y, z[1]); z[2] = fmaf(w, rj.z, z[2]);
+        off += j < lane ? 1 : j + 1;
+      }
+    };
+    for (uint32_t l = (uint32_t)tid; l < m; l += kBigTeam) {
+      float z[3];
+      precond(l, z);
+      const float4 r = sR[l];
+      red9[0] += r.x * z[0]; red9[1] += r.y * z[1]; red9[2] += r.z * z[2];
+      red9[3] += r.x * r.x; red9[4] += r.y * r.y; red9[5] += r.z * r.z;
+      sP[l] = make_float4(z[0], z[1], z[2], 0.0f);
+    }
+    teamReduce<kBigTeam, 9>(red9, sRed, phase, tid);
+    float rz[3] = {red9[0], red9[1], red9[2]};
+    float rr[3] = {red9[3], red9[4], red9[5]};
+    const float bb[3] = {red9[6], red9[7], red9[8]};
+    auto converged = [&]() {
+      return rr[0] <= a.tol2 * bb[0] + 1e-36f && rr[1] <= a.tol2 * bb[1] + 1e-36f && rr[2] <= a.tol2 * bb[2] + 1e-36f;
+    };
+    __syncthreads();
+    uint32_t iters = 0;
+    bool conv = converged();
+    while (!conv && iters < a.maxIter) {
+      float pap[3] = {0.0f, 0.0f, 0.0f};
+      for (uint32_t l = (uint32_t)tid; l < m; l += kBigTeam) {
+        const uint32_t e0 = a.nnzOff[s0 + l] - z0, e1 = a.nnzOff[s0 + l + 1] - z0;
+        float ap0 = 0.0f, ap1 = 0.0f, ap2 = 0.0f;
+#pragma unroll 4
+        for (uint32_t e = e0; e < e1; ++e) {
+          const float v = mv[e];
+          const float4 pv = sP[mc[e]];
+          ap0 = fmaf(v, pv.x, ap0); ap1 = fmaf(v, pv.y, ap1); ap2 = fmaf(v, pv.z, ap2);
+        }
+        const float4 pl = sP[l];
+        pap[0] += pl.x * ap0; pap[1] += pl.y * ap1; pap[2] += pl.z * ap2;
+        a.apScratch[s0 + l] = make_float4(ap0, ap1, ap2, 0.0f);
+      }
+      teamReduce<kBigTeam, 3>(pap, sRed, phase, tid);
+      float alpha[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) alpha[c] = pap[c] > 0.0f ? rz[c] / pap[c] : 0.0f;
+      for (uint32_t l = (uint32_t)tid; l < m; l += kBigTeam) {
+        const float4 pl = sP[l], ap = a.apScratch[s0 + l], r = sR[l];
+        float4 d = a.deltaScratch[s0 + l];
+        d.x = fmaf(alpha[0], pl.x, d.x); d.y = fmaf(alpha[1], pl.y, d.y); d.z = fmaf(alpha[2], pl.z, d.z);
+        a.deltaScratch[s0 + l] = d;
+        sR[l] = make_float4(fmaf(-alpha[0], ap.x, r.x), fmaf(-alpha[1], ap.y, r.y), fmaf(-alpha[2], ap.z, r.z), 0.0f);
+      }
+      __syncthreads();
+      float red6[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+      for (uint32_t l = (uint32_t)tid; l < m; l += kBigTeam) {
+        float z[3];
+        precond(l, z);
+        const float4 r = sR[l];
+        red6[0] += r.x * z[0]; red6[1] += r.y * z[1]; red6[2] += r.z * z[2];
+        red6[3] += r.x * r.x; red6[4] += r.y * r.y; red6[5] += r.z * r.z;
+        a.zScratch[s0 + l] = make_float4(z[0], z[1], z[2], 0.0f);
+      }
+      teamReduce<kBigTeam, 6>(red6, sRed, phase, tid);
+      float beta[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { beta[c] = rz[c] > 0.0f ? red6[c] / rz[c] : 0.0f; rz[c] = red6[c]; rr[c] = red6[3 + c]; }
+      ++iters;
+      conv = converged();
+      if (conv) break;
+      for (uint32_t l = (uint32_t)tid; l < m; l += kBigTeam) {
+        const float4 pl = sP[l], z = a.zScratch[s0 + l];
+        sP[l] = make_float4(fmaf(beta[0], pl.x, z.x), fmaf(beta[1], pl.y, z.y), fmaf(beta[2], pl.z, z.z), 0.0f);
+      }
+      __syncthreads();
+    }
+    for (uint32_t l = (uint32_t)tid; l < m; l += kBigTeam) {
+      const uint32_t g = a.order[s0 + l];
+      float4 xv = a.x[g];
+      const float4 d = a.deltaScratch[s0 + l];
+      xv.x += d.x; xv.y += d.y; xv.z += d.z;
+      a.x[g] = xv;
+    }
+    if (tid == 0) {
+      atomicMax(a.stats, iters);
+      atomicAdd(a.stats + 1, iters * ((m + 31u) >> 5));
+      if (!conv) {
+        float rel = 0.0f;
+        for (int c = 0; c < 3; ++c) if (bb[c] > 0.0f) rel = fmaxf(rel, rr[c] / bb[c]);
+        atomicAdd(a.stats + 2, 1u);
+        atomicMax(a.stats + 3, __float_as_uint(sqrtf(rel)));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- host -----
+namespace {
+struct TierConfig { int team, rpt; bool matSmem; IslandCaps caps; int ctasPerSm; };
+// caps: nodes, matrix entries, inverse floats, blocks resident in shared memory
+const TierConfig kTiers[kIslandTiers] = {
+    {32, 1, true, {32u, 640u, 576u, 4u}, 3},
+    {320, 2, true, {640u, 6656u, 9216u, 96u}, 2},
+    {512, 2, true, {1024u, 12288u, 17408u, 192u}, 1},
+    {1024, 0, false, {7168u, 0u, 0u, 0u}, 1},  // k_island_pcg_big
+};
+// Test hook: PIES_B200_ISLAND_MAXBLOCKS=k shrinks the shared-memory block tables of the CTA tiers to k entries, so islands
+// with more preconditioner blocks exercise the from-global-memory path of the block-Jacobi apply.
+IslandCaps tierCaps(int t) {
+  IslandCaps c = kTiers[t].caps;
+  static const int forced = [] { const char* e = std::getenv("PIES_B200_ISLAND_MAXBLOCKS"); return e ? std::atoi(e) : -1; }();
+  if (forced > 0 && t >= 1 && c.maxBlocks) c.maxBlocks = std::min<uint32_t>(c.maxBlocks, (uint32_t)forced);
+  return c;
+}
+IslandLayout tierLayout(int t) { return islandLayout(kTiers[t].caps, kTiers[t].team, kTiers[t].matSmem); }
+size_t tierSmem(int t) { return (size_t)tierLayout(t).total * (kTiers[t].team == 32 ? 8 : 1); }
+
+template <typename K>
+void launchTier(K kernel, int t, int grid, cudaStream_t s, const IslandArgs& a) {
+  const size_t smem = tierSmem(t);
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int threads = kTiers[t].team == 32 ? 256 : kTiers[t].team;
+  kernel<<<grid, threads, smem, s>>>(a, tierLayout(t), tierCaps(t), t);
+}
+}  // namespace
+
+#define ICHECK(expr)                                        \
+  do {                                                      \
+    cudaError_t _e = (expr);                                \
+    if (_e != cudaSuccess) { w.lastError = _e; return -1; } \
+  } while (0)
+
+static int bitsForU(uint64_t span) { int b = 1; while ((1ull << b) <= span) ++b; return b; }
+
+int uploadIslandStatics(IslandWork& w, cudaStream_t s, const HostSystem& y) {
+  w.nBodies = y.nBodies;
+  ICHECK(w.bodyOf.upload(y.bodyOf.data(), y.bodyOf.size(), s));
+  ICHECK(w.rankInBody.upload(y.rankInBody.data(), y.rankInBody.size(), s));
+  ICHECK(w.bodyPtr.upload(y.bodyPtr.data(), y.bodyPtr.size(), s));
+  if (!w.host) { ICHECK(cudaMallocHost(&w.host, 1024 * sizeof(uint32_t))); w.hostCap = 1024; }
+  if (!w.ready) ICHECK(cudaEventCreateWithFlags(&w.ready, cudaEventDisableTiming));
+  return 0;
+}
+
+int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, const ContactLists& c,
+                 const uint32_t* slotOf, const uint32_t* blockCount, uint32_t nBlocksBound, uint32_t tiersEnabled,
+                 int* launches) {
+  int L = 0;
+  const uint32_t nB = w.nBodies;
+  for (int t = 0; t < kIslandTiers; ++t) w.tierCount[t] = 0;
+  w.nLeftIslands = 0; w.nLeftNodes = 0;
+  if (!n || !nB) return 0;
+  ICHECK(w.parent.reserve(nB + 1)); ICHECK(w.keys.reserve(nB + 1)); ICHECK(w.tmpKeys.reserve(nB + 1));
+  ICHECK(w.vals.reserve(nB + 1)); ICHECK(w.tmpVals.reserve(nB + 1)); ICHECK(w.heads.reserve(nB + 2));
+  ICHECK(w.nodeOff.reserve(nB + 2)); ICHECK(w.posOfBody.reserve(nB + 1)); ICHECK(w.islStart.reserve(nB + 2));
+  ICHECK(w.order.reserve(n + 1)); ICHECK(w.pos.reserve(n + 1)); ICHECK(w.nnzOff.reserve(n + 2));
+  ICHECK(w.tierList.reserve((size_t)(kIslandTiers + 1) * nB)); ICHECK(w.counts.reserve(16));
+  ICHECK(w.blkLocal.reserve((size_t)nBlocksBound * 32 + 32)); ICHECK(w.slotIsl.reserve(n + 1));
+  ICHECK(w.sortHist.reserve(sortHistBytes(nB) / 4 + 4));
+  w.scanCap = std::max<uint64_t>(w.scanCap, std::max<uint64_t>(n, nB) + 2);
+  ICHECK(w.scanScratch.reserve(scanScratchElems(w.scanCap)));
+  ICHECK(cudaMemsetAsync(w.counts.p, 0, 16 * sizeof(uint32_t), s));
+  const int united = c.nUnique ? 1 : 0;
+  if (united) {
+    k_isl_init<<<gridFor(nB, kThreads), kThreads, 0, s>>>(nB, w.parent.p); ++L;
+    k_isl_unite<<<gridFor(c.nUnique, kThreads), kThreads, 0, s>>>(c.nUnique, c.uTri, w.bodyOf.p, w.parent.p); ++L;
+  }
+  k_isl_keys<<<gridFor(nB, kThreads), kThreads, 0, s>>>(nB, w.parent.p, united, w.keys.p, w.vals.p); ++L;
+  if (united) L += launchSortPairs(s, nB, w.keys.p, w.vals.p, w.tmpKeys.p, w.tmpVals.p, w.sortHist.p, bitsForU(nB));
+  k_isl_heads<<<gridFor(nB + 1, kThreads), kThreads, 0, s>>>(nB, w.keys.p, w.vals.p, w.bodyPtr.p, w.heads.p, w.nodeOff.p,
+                                                            w.posOfBody.p); ++L;
+  L += launchExclusiveScan(s, w.heads.p, nB + 1, w.scanScratch.p);
+  L += launchExclusiveScan(s, w.nodeOff.p, nB + 1, w.scanScratch.p);
+  k_isl_starts<<<gridFor(nB, kThreads), kThreads, 0, s>>>(nB, n, w.keys.p, w.heads.p, w.nodeOff.p, w.islStart.p, w.counts.p); ++L;
+  k_isl_nodes<<<gridFor(n + 1, kThreads), kThreads, 0, s>>>(n, w.bodyOf.p, w.rankInBody.p, w.posOfBody.p, w.nodeOff.p, S.rowPtr,
+                                                           c.nUnique ? c.cPtr : nullptr, w.order.p, w.pos.p, w.nnzOff.p); ++L;
+  L += launchExclusiveScan(s, w.nnzOff.p, n + 1, w.scanScratch.p);
+  IslandTierTable tt;
+  for (int t = 0; t < kIslandTiers; ++t) tt.caps[t] = kTiers[t].caps;
+  tt.enabled = tiersEnabled;
+  k_isl_classify<<<gridFor(nB, kThreads), kThreads, 0, s>>>(w.counts.p, tt, w.islStart.p, w.nnzOff.p, w.order.p, slotOf, blockCount,
+                                                           nB, w.tierList.p, w.counts.p); ++L;
+  ICHECK(cudaMemcpyAsync(w.host, w.counts.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  ICHECK(cudaEventRecord(w.ready, s));
+  ICHECK(cudaEventSynchronize(w.ready));
+  for (int t = 0; t < kIslandTiers; ++t) w.tierCount[t] = w.host[1 + t];
+  w.nLeftIslands = w.host[1 + kIslandTiers];
+  w.nLeftNodes = w.host[2 + kIslandTiers];
+  if (w.tierCount[3]) {  // tier 3 keeps an island-local copy of the matrix in global memory
+    const size_t nnz = S.nnz + 6ull * c.nUnique + 16;
+    ICHECK(w.matCol.reserve(nnz)); ICHECK(w.matVal.reserve(nnz));
+  }
+  if (launches) *launches += L;
+  return 0;
+}
+
+int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const ContactLists& c, const PcgWork& pw,
+                      const uint32_t* slotOf, const float4* b, float4* x, float tol, uint32_t maxIter, uint32_t statSlot) {
+  IslandArgs a{};
+  a.counts = w.counts.p; a.tierList = w.tierList.p; a.listStride = w.nBodies;
+  a.islStart = w.islStart.p; a.order = w.order.p; a.pos = w.pos.p; a.nnzOff = w.nnzOff.p;
+  a.rowPtr = S.rowPtr; a.col = S.col; a.val = S.val;
+  a.cPtr = c.nUnique ? c.cPtr : nullptr; a.cCol = c.cCol; a.cVal = c.cVal; a.cDiag = (c.nTri || c.nFloor) ? c.cDiag : nullptr;
+  a.slotOf = slotOf; a.blockNodes = pw.blockNodes; a.blockInv = pw.blockInv; a.blockMeta = pw.blockMeta;
+  a.blkLocal = w.blkLocal.p; a.matCol = w.matCol.p; a.matVal = w.matVal.p; a.deltaScratch = pw.delta;
+  a.apScratch = pw.ap; a.zScratch = pw.z; a.slotIsl = w.slotIsl.p;
+  a.b = b; a.x = x; a.tol2 = tol * tol; a.maxIter = maxIter; a.stats = w.solveStats.p + 4ull * statSlot;
+  int L = 0;
+  // largest islands first: their CTAs run longest
+  if (w.tierCount[3]) {
+    const uint32_t maxNodes = kTiers[3].caps.maxNodes;
+    const size_t smem = 32ull * maxNodes + 2 * 9 * 32 * sizeof(float);
+    cudaFuncSetAttribute(k_island_pcg_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_island_pcg_big<<<(int)std::min<uint32_t>(w.tierCount[3], kNumSMs), kBigTeam, smem, s>>>(a, maxNodes, 3);
+    ++L;
+  }
+  if (w.tierCount[2]) { launchTier(k_island_pcg<512, 2, true>, 2, (int)std::min<uint32_t>(w.tierCount[2], kNumSMs), s, a); ++L; }
+  if (w.tierCount[1]) { launchTier(k_island_pcg<320, 2, true>, 1, (int)std::min<uint32_t>(w.tierCount[1], 2 * kNumSMs), s, a); ++L; }
+  if (w.tierCount[0]) { launchTier(k_island_pcg<32, 1, true>, 0, (int)std::min<uint32_t>((w.tierCount[0] + 7) / 8, 3 * kNumSMs), s, a); ++L; }
+  return L;
+}
+
+void preloadIslandKernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_isl_init);
+  cudaFuncGetAttributes(&a, k_isl_unite);
+  cudaFuncGetAttributes(&a, k_isl_keys);
+  cudaFuncGetAttributes(&a, k_isl_heads);
+  cudaFuncGetAttributes(&a, k_isl_starts);
+  cudaFuncGetAttributes(&a, k_isl_nodes);
+  cudaFuncGetAttributes(&a, k_isl_classify);
+  cudaFuncGetAttributes(&a, k_island_pcg<32, 1, true>);
+  cudaFuncGetAttributes(&a, k_island_pcg<320, 2, true>);
+  cudaFuncGetAttributes(&a, k_island_pcg<512, 2, true>);
+  cudaFuncGetAttributes(&a, k_island_pcg_big);
+}
+
+}  // namespace pies

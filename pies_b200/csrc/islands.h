@@ -1,0 +1,62 @@
+// islands.h — per-substep islands of the global solve and the island-local PCG (islands.cu).
+#pragma once
+
+#include "engine.h"
+
+namespace pies {
+
+// Tiers of the island-local solve.  An island is a connected component of S + C_t (static bodies joined by this
+// substep's contacts); the system matrix is block diagonal over islands, so every island is an independent solve.
+//   tier 0: one warp per island (<= 32 nodes in a single preconditioner block: every free body of the S3 stack)
+//   tier 1: one 320-thread CTA, matrix + block inverses + r, p resident in shared memory, two CTAs per SM
+//   tier 2: one 512-thread CTA, the same with the whole shared memory of an SM
+//   tier 3: one 1024-thread CTA, r and p in shared memory, the island's matrix re-indexed in a global scratch copy
+//           (L2 resident: one CTA re-reads a few hundred KB per iteration)
+// Islands above tier 3 are left to the grid-wide CG of pcg.cu.
+constexpr int kIslandTiers = 4;
+struct IslandCaps { uint32_t maxNodes, maxNnz, maxInv, maxBlocks; };
+
+struct IslandWork {
+  // once per topology
+  DevBuf<uint32_t> bodyOf, rankInBody, bodyPtr;
+  uint32_t nBodies = 0;
+  // once per substep
+  DevBuf<uint32_t> parent, vals, tmpVals, heads, nodeOff, posOfBody, islStart, order, pos, nnzOff, sortHist, scanScratch;
+  DevBuf<uint64_t> keys, tmpKeys;
+  DevBuf<uint32_t> tierList;      // (kIslandTiers + 1) lists of nBodies entries; list kIslandTiers = islands left to the global CG
+  DevBuf<uint32_t> counts;        // device: [0] islands, [1 + t] islands of tier t, [1 + kIslandTiers] left over, then nodes left over
+  DevBuf<uint32_t> blkLocal;      // preconditioner block * 32 + lane -> island-local row of that member (written by every solve)
+  DevBuf<uint32_t> slotIsl;       // tier 3: preconditioner slot of every row, island order
+  DevBuf<int> matCol;             // tier 3: island-local copy of the matrix (column = local row index), at nnzOff
+  DevBuf<float> matVal;
+  DevBuf<uint32_t> solveStats;    // 4 words per solve of a tick: max iterations, sum of iterations x rows, islands at the cap, worst residual
+  uint32_t* host = nullptr;       // pinned copy of counts (8 words) + solveStats
+  uint32_t hostCap = 0;
+  cudaEvent_t ready = nullptr;
+  uint64_t scanCap = 0;
+  uint32_t nLeftIslands = 0, nLeftNodes = 0;  // host copies after buildIslands
+  uint32_t tierCount[kIslandTiers] = {0, 0, 0, 0};
+  cudaError_t lastError = cudaSuccess;
+  ~IslandWork() {
+    if (ready) cudaEventDestroy(ready);
+    if (host) cudaFreeHost(host);
+  }
+};
+
+// Upload of the static body tables (HostSystem::bodyOf ...).
+int uploadIslandStatics(IslandWork& w, cudaStream_t s, const HostSystem& y);
+
+// Builds this substep's islands from the contact lists and classifies them.  Synchronises the stream once (the host
+// needs to know whether any island is left to the global CG).  slotOf / blockCount: this substep's preconditioner
+// blocks (reblock.cu).  Returns 0 or -1.
+int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, const ContactLists& c,
+                 const uint32_t* slotOf, const uint32_t* blockCount, uint32_t nBlocksBound, uint32_t tiersEnabled,
+                 int* launches);
+
+// Solves A x = b on every island of tiers 0..3 (x holds the start value).  statSlot: which 4-word record of solveStats.
+int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const ContactLists& c, const PcgWork& pw,
+                      const uint32_t* slotOf, const float4* b, float4* x, float tol, uint32_t maxIter, uint32_t statSlot);
+
+void preloadIslandKernels();
+
+}  // namespace pies

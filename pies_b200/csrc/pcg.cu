@@ -220,6 +220,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_start(PcgWork w, float* __r
 
 // Convergence test on the latest residual norm (after start, or after the last enqueued iteration).
 __global__ void k_pcg_check(float* __restrict__ scalars, int* __restrict__ flag, int set, float tol2) {
+  // Already latched by an update kernel in the middle of the burst: the later launches exited early, so `set` holds an
+  // older (larger) residual than the one the latch was decided on; scalars[0] is already the right one.
+  if (flag[0]) return;
   float bb[3], rr[3];
   readSums3(scalars, kBB, bb);
   readSums3(scalars, set + 3, rr);

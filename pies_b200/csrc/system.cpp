@@ -293,6 +293,30 @@ void buildSystem(const HostScene& sc, float h, HostSystem& out, unsigned threads
     }
   }
   out.nBlocks = (uint32_t)(bn.size() / 32);
+  // ---- 4b. static bodies (the units the per-substep islands are made of) -----------------------------------
+  {
+    for (uint32_t b = 0; b < out.nBlocks; ++b)  // small components packed into one block stay together
+      for (int k = 1; k < 32 && bn[32 * b + k] >= 0; ++k) dsu.unite((uint32_t)bn[32 * b], (uint32_t)bn[32 * b + k]);
+    out.bodyOf.assign(n, 0);
+    out.rankInBody.assign(n, 0);
+    std::vector<uint32_t> bodyOfRoot(n, 0xffffffffu);
+    out.nBodies = 0;
+    for (uint32_t i = 0; i < n; ++i) {  // min-hooking: a root is its body's smallest node, so bodies come out in node order
+      const uint32_t r = dsu.find(i);
+      if (bodyOfRoot[r] == 0xffffffffu) bodyOfRoot[r] = out.nBodies++;
+      out.bodyOf[i] = bodyOfRoot[r];
+    }
+    out.bodyPtr.assign(out.nBodies + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) ++out.bodyPtr[out.bodyOf[i] + 1];
+    for (uint32_t b = 0; b < out.nBodies; ++b) out.bodyPtr[b + 1] += out.bodyPtr[b];
+    out.bodyNodes.assign(n, 0);
+    std::vector<uint32_t> cur(out.bodyPtr.begin(), out.bodyPtr.end() - 1);
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint32_t b = out.bodyOf[i];
+      out.rankInBody[i] = cur[b] - out.bodyPtr[b];
+      out.bodyNodes[cur[b]++] = i;
+    }
+  }
   out.blockInv.assign((size_t)out.nBlocks * 1024, 0.0f);
   auto invertBlocks = [&](unsigned t) {
     std::vector<double> a(32 * 32), inv(32 * 32);

@@ -41,6 +41,15 @@ struct HostSystem {
   std::vector<int> blockNodes;                // 32 per block, -1 padded
   std::vector<float> blockInv;                // 1024 per block, symmetric
 
+  // Static bodies: connected components of S (nodes that also share a preconditioner block are kept together).
+  // The per-substep islands of the global solve (islands.cu) are unions of bodies joined by contacts.  Bodies are
+  // numbered by their smallest node; bodyNodes lists every body's nodes in ascending order.
+  uint32_t nBodies = 0;
+  std::vector<uint32_t> bodyOf;               // n: node -> body
+  std::vector<uint32_t> rankInBody;           // n: node -> position inside bodyNodes[bodyPtr[b] ..)
+  std::vector<uint32_t> bodyPtr;              // nBodies + 1
+  std::vector<uint32_t> bodyNodes;            // n
+
   uint64_t staticProjections = 0;             // per PD iteration, shape/goal count one per member
 };
 

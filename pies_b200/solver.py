@@ -50,6 +50,10 @@ class Stats(C.Structure):
         ("tetKernelLaunches", C.c_uint32), ("reserved", C.c_uint32),
         ("msSpmvKernel", C.c_float), ("msUpdateKernel", C.c_float), ("msGatherKernel", C.c_float),
         ("spmvKernelLaunches", C.c_uint32), ("updateKernelLaunches", C.c_uint32), ("gatherKernelLaunches", C.c_uint32),
+        ("islandsTier", C.c_uint32 * 4), ("islandsGlobal", C.c_uint32), ("islandNodesGlobal", C.c_uint32),
+        ("pcgCapHits", C.c_uint32), ("pcgWorstCapResidual", C.c_float),
+        ("msIslandKernels", C.c_float), ("islandKernelLaunches", C.c_uint32),
+        ("pcgIslandRowIterations", C.c_uint64),
     ]
 
 
@@ -201,7 +205,8 @@ class Solver:
         except Exception:
             pass
 
-    def setTuning(self, pcgTolerance=None, pcgMaxIterations=None, pcgCheckEvery=None, profilePhases=None, dataflowSweepsOnly=None):
+    def setTuning(self, pcgTolerance=None, pcgMaxIterations=None, pcgCheckEvery=None, profilePhases=None, dataflowSweepsOnly=None,
+                  islandSolves=None, islandTiersOff=None):
         t = Tuning()
         lib().pies_b200_default_tuning(C.byref(t))
         cur = getattr(self, "_tuning", None)
@@ -212,6 +217,8 @@ class Solver:
         if pcgCheckEvery is not None: t.pcgCheckEvery = pcgCheckEvery
         if profilePhases is not None: t.reserved = (t.reserved & ~1) | int(bool(profilePhases))
         if dataflowSweepsOnly is not None: t.reserved = (t.reserved & ~2) | (2 if dataflowSweepsOnly else 0)
+        if islandSolves is not None: t.reserved = (t.reserved & ~4) | (0 if islandSolves else 4)
+        if islandTiersOff is not None: t.reserved = (t.reserved & ~0xF0) | ((int(islandTiersOff) & 0xF) << 4)
         self._tuning = t
         self._ck(lib().pies_b200_set_tuning(self.h, C.byref(t)))
 

@@ -310,3 +310,69 @@ def test_collision_csr_is_the_reference_collision_matrix(pb):
         for i in range(n):
             np.add.at(dense[i], col[ptr[i]:ptr[i + 1]], val[ptr[i]:ptr[i + 1]].astype(np.float64))
         assert np.array_equal(dense, port.collision_matrix(n, g["t%d_tri" % t], g["t%d_floor" % t])), t
+
+
+# ---- global solve by islands (islands.cu) ---------------------------------------------------------------
+def _stack(pb, **tuning):
+    from pies_b200 import scenes
+    s = pb.Solver(**scenes.S3_OPTIONS)
+    scenes.build_s3(s, bodies=48, nx=2, nz=2)   # four columns of twelve bodies: islands of up to 324 nodes once stacked
+    if tuning:
+        s.setTuning(**tuning)
+    return s
+
+
+@pytest.mark.parametrize("tiers_off,label", [(0, "all tiers"), (1, "no warp tier"), (3, "CTA-512 and CTA-1024 only"),
+                                              (7, "CTA-1024 only")])
+def test_island_solves_agree_with_grid_wide_cg(pb, tiers_off, label):
+    """The island-local PCG (one warp / one CTA per connected component of S + C_t) and the grid-wide CG solve the same
+    systems to the same tolerance: trajectories agree within the solver tolerance's footprint (1e-5 x diagonal) through
+    free fall, floor contact and the first body-body impacts, with identical contact counts; every tier is forced in
+    turn so each kernel variant runs."""
+    a = _stack(pb, islandSolves=False)
+    b = _stack(pb, islandTiersOff=tiers_off)
+    diag = bbox_diag(a.positions)
+    seen = np.zeros(4, np.int64)
+    for t in range(1, 47):
+        a.tick(); b.tick()
+        sa, sb = a.stats(), b.stats()
+        assert (sa.triCollisions, sa.staticCollisions) == (sb.triCollisions, sb.staticCollisions), (label, t)
+        assert sa.islandsGlobal == 0 or sum(sa.islandsTier) == 0
+        assert sb.islandsGlobal == 0, (label, t)             # nothing in this scene is too large for a CTA
+        assert sb.pcgCapHits == 0 and sa.pcgCapHits == 0
+        seen += np.array(list(sb.islandsTier))
+        err = np.abs(a.positions - b.positions).max()
+        assert err <= 1e-5 * diag, (label, t, err)
+    for tier in range(4):
+        if tiers_off & (1 << tier):
+            assert seen[tier] == 0, (label, tier)
+    assert seen.sum() > 0 and sb.triCollisions > 0
+
+
+def test_island_block_table_overflow_path(pb, monkeypatch):
+    """Islands with more preconditioner blocks than a CTA tier's shared-memory table apply those blocks from global
+    memory: same result."""
+    a = _stack(pb)
+    for _ in range(46):
+        a.tick()
+    monkeypatch.setenv("PIES_B200_ISLAND_MAXBLOCKS", "3")
+    import subprocess, sys, os
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np; import pies_b200 as pb; from pies_b200 import scenes\n"
+            "s = pb.Solver(**scenes.S3_OPTIONS); scenes.build_s3(s, bodies=48, nx=2, nz=2)\n"
+            "[s.tick() for _ in range(46)]\n"
+            "np.save(sys.argv[1], s.positions)" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = os.path.join(os.environ.get("TMPDIR", "/tmp"), "pies_island_overflow.npy")
+    subprocess.run([sys.executable, "-c", code, out], check=True, env=dict(os.environ))  # the env hook is read once per process
+    b = np.load(out)
+    assert np.abs(a.positions - b).max() <= 1e-5 * bbox_diag(b)
+
+
+def test_pcg_cap_is_loud(pb):
+    """A solve that stops at pcgMaxIterations far from its tolerance is reported: counter, residual and an error code
+    (the reference's Cholesky cannot fail this way, so silence would hide a wrong trajectory)."""
+    s = _stack(pb, pcgMaxIterations=1, pcgTolerance=1e-12)
+    with pytest.raises(pb.PiesError, match="not converged"):
+        for _ in range(3):
+            s.tick()
+    st = s.stats()
+    assert st.pcgCapHits > 0 and st.pcgWorstCapResidual > 1e-9
