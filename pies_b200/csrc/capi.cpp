@@ -38,6 +38,7 @@ int mutate(PiesB200Solver* s, F&& f) {
   return guarded(s, [&]() {
     int rc = pies::downloadState(s);
     if (rc) return rc;
+    pies::unregisterVertexMirror(s);  // the factories grow scene.vertices
     f();
     s->renderStateDirty = true;
     return PIES_B200_OK;
@@ -168,7 +169,18 @@ int pies_b200_get_render_state_dirty(const PiesB200Solver* s) { return s && s->r
 int pies_b200_set_render_state_dirty(PiesB200Solver* s, int d) { if (!s) return PIES_B200_EINVAL; s->renderStateDirty = d != 0; return 0; }
 int pies_b200_sim_failed(const PiesB200Solver* s) { return s && s->simFailed ? 1 : 0; }
 int pies_b200_clear(PiesB200Solver* s) {
-  return guarded(s, [&]() { s->scene.clear(); s->deviceNewer = false; s->renderStateDirty = true; return PIES_B200_OK; });
+  return guarded(s, [&]() {
+    pies::pdAbort(s);
+    pies::unregisterVertexMirror(s);
+    s->scene.clear();
+    // nothing of the old scene may be read back any more: no device state, no stale mirror, no collision lists
+    s->deviceNewer = false; s->mirrorStale = false; s->hostStateDirty = false; s->n = 0;
+    s->builtVersion = ~0ull;
+    s->stats.triCollisions = s->stats.staticCollisions = 0;
+    s->stats.collisionProjections = 0;
+    s->renderStateDirty = true;
+    return PIES_B200_OK;
+  });
 }
 
 // ---- readback ----
@@ -181,7 +193,7 @@ const PiesB200Vertex* pies_b200_get_vertices(const PiesB200Solver* cs) {
   // The reference refreshes its mirror at the end of every substep (Solver.cpp:157,393); here the D2H copy
   // is deferred to the first getVertices() after a tick, which is observably the same and free for hosts
   // that do not read every tick.
-  if (s->mirrorStale && !s->simFailed) {
+  if (s->mirrorStale && !s->simFailed && s->builtVersion == s->scene.topologyVersion && s->n == s->scene.nodeCount()) {
     cudaSetDevice(s->device);
     pies::g_allocStream = s->stream;
     if (pies::refreshVertexMirror(s) != 0) return nullptr;
@@ -366,6 +378,8 @@ int pies_b200_get_collision_csr(PiesB200Solver* s, uint64_t* nnz, int32_t* cPtr,
   return guarded(s, [&]() {
     cudaSetDevice(s->device);
     const uint32_t n = s->n;
+    if (s->builtVersion != s->scene.topologyVersion || n != s->scene.nodeCount())
+      return fail(s, PIES_B200_EINVAL, "the scene changed since the last detection: tick or detect first");
     const bool any = s->detect && (s->stats.triCollisions || s->stats.staticCollisions);
     const bool csr = any && s->stats.triCollisions && s->detect->nUnique;
     *nnz = 0;
@@ -426,11 +440,11 @@ int pies_b200_get_tri_occupancy(PiesB200Solver* s, int64_t* cells, uint32_t* cou
   });
 }
 // ---- tick phases + halo support for slab-partitioned hosts ----
-int pies_b200_pd_tick_begin(PiesB200Solver* s) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::pdTickBegin(s); }); }
-int pies_b200_pd_substep_begin(PiesB200Solver* s) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::pdSubstepBegin(s); }); }
-int pies_b200_pd_iteration(PiesB200Solver* s) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::pdIteration(s); }); }
-int pies_b200_pd_substep_end(PiesB200Solver* s) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::pdSubstepEnd(s); }); }
-int pies_b200_pd_tick_end(PiesB200Solver* s) { return guarded(s, [&]() { cudaSetDevice(s->device); return pies::pdTickEnd(s, false); }); }
+int pies_b200_pd_tick_begin(PiesB200Solver* s) { return guarded(s, [&]() { if (s->simFailed) return PIES_B200_OK; cudaSetDevice(s->device); return pies::pdTickBegin(s); }); }
+int pies_b200_pd_substep_begin(PiesB200Solver* s) { return guarded(s, [&]() { if (s->simFailed) return PIES_B200_OK; cudaSetDevice(s->device); return pies::pdSubstepBegin(s); }); }
+int pies_b200_pd_iteration(PiesB200Solver* s) { return guarded(s, [&]() { if (s->simFailed) return PIES_B200_OK; cudaSetDevice(s->device); return pies::pdIteration(s); }); }
+int pies_b200_pd_substep_end(PiesB200Solver* s) { return guarded(s, [&]() { if (s->simFailed) return PIES_B200_OK; cudaSetDevice(s->device); return pies::pdSubstepEnd(s); }); }
+int pies_b200_pd_tick_end(PiesB200Solver* s) { return guarded(s, [&]() { if (s->simFailed) return PIES_B200_OK; cudaSetDevice(s->device); return pies::pdTickEnd(s, false); }); }
 int pies_b200_device_state(PiesB200Solver* s, void** q, void** prev, void** vel, uint32_t* n) {
   return guarded(s, [&]() {
     cudaSetDevice(s->device);

@@ -58,6 +58,12 @@ static cudaError_t uploadVec(DevBuf<T>& d, const std::vector<U>& h, cudaStream_t
   return d.upload(reinterpret_cast<const T*>(h.data()), h.size() * sizeof(U) / sizeof(T), s);
 }
 
+int ensureTickEvents(PiesB200Solver* s) {
+  for (int k = 0; k < 2; ++k)
+    if (!s->tickEv[k]) PIES_CHECK(s, cudaEventCreate(&s->tickEv[k]));
+  return PIES_B200_OK;
+}
+
 int downloadVec3(PiesB200Solver* s, const float4* src, float* dstXYZ) {
   uint32_t n = s->n;
   if (!n) return PIES_B200_OK;
@@ -221,42 +227,49 @@ int ensureBuilt(PiesB200Solver* s) {
   }
   PIES_CHECK(s, cudaStreamSynchronize(st));
   s->builtVersion = sc.topologyVersion;
+  s->vtxDevValid = false;
   s->hostStateDirty = false;
   s->stats.staticProjections = y.staticProjections;
   s->lastPcgIters = 1;
   return PIES_B200_OK;
 }
 
+// positions into the device copy of the Vertex mirror: 3 floats at the head of every 9-float record
+__global__ void __launch_bounds__(kThreads) k_vertex_positions(uint32_t n, const float4* __restrict__ q, float* __restrict__ vtx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = q[i];
+  float* o = vtx + 9ull * i;
+  o[0] = v.x; o[1] = v.y; o[2] = v.z;
+}
+
+void unregisterVertexMirror(PiesB200Solver* s) {
+  if (s->vtxRegistered) { cudaHostUnregister(s->vtxRegistered); cudaGetLastError(); }
+  s->vtxRegistered = nullptr; s->vtxRegisteredBytes = 0;
+}
+
+// Solver::getVertices (Solver.h:65): the reference refreshes _vertices[i].position on the host at the end of every substep
+// (Solver.cpp:393); here the whole 36 B-stride mirror comes back in one DMA, no host-side scatter.
 int refreshVertexMirror(PiesB200Solver* s) {
   if (!s->n) return PIES_B200_OK;
-  uint32_t n = s->n;
-  PIES_CHECK(s, s->packed.reserve(3ull * n));
-  if (s->hostPackedCap < 3ull * n) {
-    if (s->hostPacked) cudaFreeHost(s->hostPacked);
-    s->hostPacked = nullptr; s->hostPackedCap = 0;
-    PIES_CHECK(s, cudaMallocHost(&s->hostPacked, (3ull * n + 64) * sizeof(float)));
-    s->hostPackedCap = 3ull * n + 64;
+  const uint32_t n = s->n;
+  static_assert(sizeof(PiesB200Vertex) == 36, "Vertex is 9 floats");
+  const size_t bytes = (size_t)n * sizeof(PiesB200Vertex);
+  PiesB200Vertex* host = s->scene.vertices.data();
+  PIES_CHECK(s, s->vtxDev.reserve(9ull * n));
+  if (!s->vtxDevValid) {  // colours, radii: static per topology
+    PIES_CHECK(s, cudaMemcpyAsync(s->vtxDev.p, host, bytes, cudaMemcpyHostToDevice, s->stream));
+    s->vtxDevValid = true;
   }
-  k_pack3<<<gridFor(n, kThreads), kThreads, 0, s->stream>>>(n, s->q.p, s->packed.p);
+  k_vertex_positions<<<gridFor(n, kThreads), kThreads, 0, s->stream>>>(n, s->q.p, s->vtxDev.p);
   ++s->launches;
-  PIES_CHECK(s, cudaMemcpyAsync(s->hostPacked, s->packed.p, 3ull * n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-  PIES_CHECK(s, cudaStreamSynchronize(s->stream));
-  PiesB200Vertex* v = s->scene.vertices.data();
-  const float* p = s->hostPacked;
-  auto scatter = [v, p](uint32_t i0, uint32_t i1) {
-    for (uint32_t i = i0; i < i1; ++i) { v[i].position[0] = p[3 * i]; v[i].position[1] = p[3 * i + 1]; v[i].position[2] = p[3 * i + 2]; }
-  };
-  // 36 B-stride writes: memory bound on one core for large scenes, so split the range over a few threads
-  const unsigned T = n >= (1u << 17) ? std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1u;
-  if (T > 1) {
-    std::vector<std::thread> pool;
-    const uint32_t chunk = (n + T - 1) / T;
-    for (unsigned t = 1; t < T; ++t) pool.emplace_back(scatter, std::min(n, t * chunk), std::min(n, (t + 1) * chunk));
-    scatter(0, std::min(n, chunk));
-    for (auto& th : pool) th.join();
-  } else {
-    scatter(0, n);
+  if (s->vtxRegistered != host || s->vtxRegisteredBytes != bytes) {
+    unregisterVertexMirror(s);
+    if (cudaHostRegister(host, bytes, cudaHostRegisterDefault) == cudaSuccess) { s->vtxRegistered = host; s->vtxRegisteredBytes = bytes; }
+    else cudaGetLastError();  // pageable destination: the runtime stages the copy, still no scatter
   }
+  PIES_CHECK(s, cudaMemcpyAsync(host, s->vtxDev.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+  PIES_CHECK(s, cudaStreamSynchronize(s->stream));
   s->mirrorStale = false;
   return PIES_B200_OK;
 }
@@ -341,9 +354,7 @@ struct PdTickCtx {
 void pdAbort(PiesB200Solver* s) {
   PdTickCtx* c = static_cast<PdTickCtx*>(s->pdCtx);
   if (!c) return;
-  if (c->tick0) cudaEventDestroy(c->tick0);
-  if (c->tick1) cudaEventDestroy(c->tick1);
-  delete c;
+  delete c;  // the tick events belong to the solver
   s->pdCtx = nullptr;
 }
 
@@ -393,10 +404,18 @@ int pdTickBegin(PiesB200Solver* s) {
     PIES_CHECK(s, s->islands->solveStats.reserve(words));
     PIES_CHECK(s, cudaMemsetAsync(s->islands->solveStats.p, 0, words * sizeof(uint32_t), s->stream));
   }
-  cudaEventCreate(&c->tick0); cudaEventCreate(&c->tick1);
+  if ((rc = ensureTickEvents(s))) { pdAbort(s); return rc; }
+  c->tick0 = s->tickEv[0]; c->tick1 = s->tickEv[1];
   cudaEventRecord(c->tick0, s->stream);
   return PIES_B200_OK;
 }
+
+// PIES_CHECK inside a tick phase: drops the tick context before returning the error
+#define PD_CHECK(s, expr)                                                          \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) { pdAbort(s); return failCuda((s), _e, #expr, __LINE__); } \
+  } while (0)
 
 int pdSubstepBegin(PiesB200Solver* s) {
   PdTickCtx* c = static_cast<PdTickCtx*>(s->pdCtx);
@@ -417,7 +436,7 @@ int pdSubstepBegin(PiesB200Solver* s) {
   // contact-aware preconditioner blocks for this substep's system matrix S + C_t
   if (!s->blocks) {
     s->blocks = new BlockWork();
-    PIES_CHECK(s, cudaMallocHost(&s->blocks->host, 4 * sizeof(uint32_t)));
+    PD_CHECK(s, cudaMallocHost(&s->blocks->host, 4 * sizeof(uint32_t)));
   }
   s->blocks->midClusterMax = (s->tune.reserved & 2u) ? 0u : kMidClusterMax;
   {
@@ -528,9 +547,9 @@ int pdIteration(PiesB200Solver* s) {
       }
       done += todo;
       s->launches += launchPcgCheck(st, v.pw, s->tune.pcgTolerance, (int)done - 1);
-      PIES_CHECK(s, cudaMemcpyAsync(s->hostFlag, s->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-      PIES_CHECK(s, cudaMemcpyAsync(s->hostFlag + 2, s->scalars.p, sizeof(float), cudaMemcpyDeviceToHost, st));
-      PIES_CHECK(s, cudaStreamSynchronize(st));
+      PD_CHECK(s, cudaMemcpyAsync(s->hostFlag, s->flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+      PD_CHECK(s, cudaMemcpyAsync(s->hostFlag + 2, s->scalars.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+      PD_CHECK(s, cudaStreamSynchronize(st));
       converged = s->hostFlag[0] != 0;
       burst = std::max(4u, s->tune.pcgCheckEvery);
     }
@@ -699,7 +718,9 @@ PiesB200Solver::~PiesB200Solver() {
   pies::pdAbort(this);
   if (blocks) { if (blocks->host) cudaFreeHost(blocks->host); delete blocks; }
   delete islands;
+  pies::unregisterVertexMirror(this);
   for (cudaEvent_t e : eventPool) cudaEventDestroy(e);
+  for (cudaEvent_t e : tickEv) if (e) cudaEventDestroy(e);
   if (hostPacked) cudaFreeHost(hostPacked);
   if (hostFlag) cudaFreeHost(hostFlag);
   if (ownStream && stream) cudaStreamDestroy(stream);

@@ -88,6 +88,10 @@ struct PiesB200Solver {
   pies::DevBuf<int> blockNodes; pies::DevBuf<float> blockInv;
   pies::DevBuf<uint32_t> triIds;  // 3 per triangle
   pies::DevBuf<float> packed;     // 3 floats per node, readback staging
+  // Device-side copy of the Vertex mirror (36 B per vertex, Solver.h:42-49): the static attributes are uploaded once per
+  // topology, a kernel refreshes the positions, and getVertices() is one contiguous DMA into the (page-locked) host vector.
+  pies::DevBuf<float> vtxDev; bool vtxDevValid = false;
+  void* vtxRegistered = nullptr; size_t vtxRegisteredBytes = 0;  // the host vector's storage while it is cudaHostRegister-ed
   // PBD
   pies::DevBuf<uint32_t> posIds; pies::DevBuf<float4> posTargetW;
 
@@ -106,6 +110,7 @@ struct PiesB200Solver {
   int* hostFlag = nullptr;      // pinned, 4 ints
   uint32_t lastPcgIters = 1;
   std::vector<cudaEvent_t> eventPool;  // phase-timing events of this solver (created on its device)
+  cudaEvent_t tickEv[2] = {nullptr, nullptr};  // brackets of the whole tick, created once
   std::vector<uint32_t> pcgItersByIteration;  // CG iterations the k-th PD iteration of the previous substep needed (burst prediction)
   uint64_t launches = 0;
 
@@ -114,6 +119,7 @@ struct PiesB200Solver {
 
 namespace pies {
 int failCuda(PiesB200Solver* s, cudaError_t e, const char* what, int line);
+int ensureTickEvents(PiesB200Solver* s);
 int fail(PiesB200Solver* s, int code, const char* msg);
 int ensureBuilt(PiesB200Solver* s);
 int downloadState(PiesB200Solver* s);  // device -> scene.pos/prev/vel
@@ -128,6 +134,7 @@ void pdAbort(PiesB200Solver* s);
 int countOwnedContacts(PiesB200Solver* s, uint32_t* nTri, uint32_t* nFloor);
 int tickPBD(PiesB200Solver* s, bool refreshMirror);
 int refreshVertexMirror(PiesB200Solver* s);
+void unregisterVertexMirror(PiesB200Solver* s);  // before anything that may reallocate scene.vertices
 int uploadStateArrays(PiesB200Solver* s, const float* pos, const float* prev, const float* vel);
 int runDetection(PiesB200Solver* s, ContactLists& lists);
 int pbdHashOnly(PiesB200Solver* s);

@@ -165,7 +165,7 @@ static IslandLayout islandLayout(const IslandCaps& c, int team, bool matSmem) {
 struct IslandArgs {
   const uint32_t* counts; const uint32_t* tierList; uint32_t listStride;
   const uint32_t* islStart; const uint32_t* order; const uint32_t* pos; const uint32_t* nnzOff;
-  const int* rowPtr; const int* col; const float* val;
+  const int* rowPtr; const int* col; const float* val; const uint32_t* colRank; const uint32_t* rankInBody;
   const int* cPtr; const int* cCol; const float* cVal; const float* cDiag;
   const uint32_t* slotOf; const int* blockNodes; const float* blockInv; const uint2* blockMeta;
   uint32_t* blkLocal;          // block * 32 + lane -> local row of that member (scratch, written per solve)
@@ -233,50 +233,47 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
     ColT* mc = MAT_SMEM ? reinterpret_cast<ColT*>(base + L.col) : reinterpret_cast<ColT*>(a.matCol + z0);
     if (tid == 0) { sCtr[0] = 0; sCtr[1] = 0; }
     teamSync<TEAM>();
-    // ---- stage the island: matrix rows in local indices (collision diagonal folded into the diagonal entry), the
-    //      fp64 start residual r = b - A x (b and A x agree to ~7 digits and the difference is what matters), blocks
+    // ---- stage the island.  Rows are re-indexed without a gather per entry: S never leaves a body and the island order
+    //      keeps a body's nodes together by rank, so local column = (row's body base) + rank of the column (host table).
+    //      x of the island goes to sP and b to sR for the start residual below.
     uint32_t rs[RPT], rn[RPT], rb[RPT], slot[RPT], gid[RPT];
-    float dl[RPT][3];
+    float dl[RPT][3], cdg[RPT];
     float red9[9] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // r.z (3), r.r (3), b.b (3)
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
       const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
-      rs[k] = 0; rn[k] = 0; rb[k] = 0xffffffffu; slot[k] = 0; gid[k] = 0;
+      rs[k] = 0; rn[k] = 0; rb[k] = 0xffffffffu; slot[k] = 0; gid[k] = 0; cdg[k] = 0.0f;
       dl[k][0] = dl[k][1] = dl[k][2] = 0.0f;
       if (l >= m) continue;
       const uint32_t g = a.order[s0 + l];
       gid[k] = g;
       const uint32_t rstart = a.nnzOff[s0 + l] - z0, rend = a.nnzOff[s0 + l + 1] - z0;
       rs[k] = rstart; rn[k] = rend - rstart;
-      const float4 xi = a.x[g], bi = a.b[g];
-      const float cd = a.cDiag ? a.cDiag[g] : 0.0f;
-      double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-      uint32_t e = rstart;
-      for (int kk = a.rowPtr[g]; kk < a.rowPtr[g + 1]; ++kk, ++e) {
-        const int c = __ldg(a.col + kk);
-        float v = __ldg(a.val + kk);
-        const float4 xv = a.x[c];
-        y0 += (double)v * (double)xv.x; y1 += (double)v * (double)xv.y; y2 += (double)v * (double)xv.z;
-        uint32_t lc = a.pos[c] - s0;
-        if (lc >= m) { lc = l; v = 0.0f; }  // explicit zeros may point outside the body (bend stencils): drop them
-        if ((uint32_t)c == g) v += cd;
-        mc[e] = (ColT)lc; mv[e] = v;
-      }
-      if (a.cPtr) {
-        for (int kk = a.cPtr[g]; kk < a.cPtr[g + 1]; ++kk, ++e) {
-          const int c = a.cCol[kk];
-          const float v = a.cVal[kk];
-          const float4 xv = a.x[c];
-          y0 += (double)v * (double)xv.x; y1 += (double)v * (double)xv.y; y2 += (double)v * (double)xv.z;
-          mc[e] = (ColT)(a.pos[c] - s0); mv[e] = v;
-        }
-      }
-      y0 += (double)cd * (double)xi.x; y1 += (double)cd * (double)xi.y; y2 += (double)cd * (double)xi.z;
-      sR[l] = make_float4((float)((double)bi.x - y0), (float)((double)bi.y - y1), (float)((double)bi.z - y2), 0.0f);
-      red9[6] += bi.x * bi.x; red9[7] += bi.y * bi.y; red9[8] += bi.z * bi.z;
-      if (kDeltaGlobal) a.deltaScratch[s0 + l] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      const int kk0 = a.rowPtr[g], kk1 = a.rowPtr[g + 1];
+      const uint32_t bodyBase = l - a.rankInBody[g];
+      const float4 bi = a.b[g];
+      sP[l] = a.x[g];
+      sR[l] = bi;
+      cdg[k] = a.cDiag ? a.cDiag[g] : 0.0f;
       const uint32_t sl = a.slotOf[g];
       slot[k] = sl;
+      uint32_t e = rstart;
+#pragma unroll 4
+      for (int kk = kk0; kk < kk1; ++kk, ++e) {
+        const uint32_t rk = __ldg(a.colRank + kk);
+        const float v = __ldg(a.val + kk);
+        const bool out = rk == 0xffffffffu;  // an explicit zero pointing outside the body (bend stencils): dropped
+        mc[e] = (ColT)(out ? l : bodyBase + rk);
+        mv[e] = out ? 0.0f : v;
+      }
+      if (a.cPtr) {
+        const int c0 = a.cPtr[g], c1 = a.cPtr[g + 1];
+        for (int kk = c0; kk < c1; ++kk, ++e) {
+          mc[e] = (ColT)(__ldg(a.pos + __ldg(a.cCol + kk)) - s0);
+          mv[e] = __ldg(a.cVal + kk);
+        }
+      }
+      red9[6] += bi.x * bi.x; red9[7] += bi.y * bi.y; red9[8] += bi.z * bi.z;
       a.blkLocal[sl] = l;
       if (caps.maxBlocks) {
         sLeader[l] = 0xffffu;
@@ -291,6 +288,25 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
           }
         }
       }
+    }
+    teamSync<TEAM>();
+    // start residual r = b - A x from shared memory, accumulated in fp64 (float products are exact in double): b and A x
+    // agree to ~7 digits and the difference is what matters
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+      if (l >= m) continue;
+      const float4 xi = sP[l];
+      double y0 = (double)cdg[k] * (double)xi.x, y1 = (double)cdg[k] * (double)xi.y, y2 = (double)cdg[k] * (double)xi.z;
+      const uint32_t e1 = rs[k] + rn[k];
+#pragma unroll 4
+      for (uint32_t e = rs[k]; e < e1; ++e) {
+        const double v = (double)mv[e];
+        const float4 xv = sP[mc[e]];
+        y0 += v * (double)xv.x; y1 += v * (double)xv.y; y2 += v * (double)xv.z;
+      }
+      const float4 bi = sR[l];
+      sR[l] = make_float4((float)((double)bi.x - y0), (float)((double)bi.y - y1), (float)((double)bi.z - y2), 0.0f);
     }
     teamSync<TEAM>();
     if (caps.maxBlocks) {
@@ -386,6 +402,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
           ap[k][0] = fmaf(v, pv.x, ap[k][0]); ap[k][1] = fmaf(v, pv.y, ap[k][1]); ap[k][2] = fmaf(v, pv.z, ap[k][2]);
         }
         const float4 pl = sP[l];
+        ap[k][0] = fmaf(cdg[k], pl.x, ap[k][0]); ap[k][1] = fmaf(cdg[k], pl.y, ap[k][1]); ap[k][2] = fmaf(cdg[k], pl.z, ap[k][2]);
         pap[0] += pl.x * ap[k][0]; pap[1] += pl.y * ap[k][1]; pap[2] += pl.z * ap[k][2];
       }
       teamReduce<TEAM, 3>(pap, sRed, phase, tid);
@@ -665,8 +682,14 @@ int uploadIslandStatics(IslandWork& w, cudaStream_t s, const HostSystem& y) {
   ICHECK(w.bodyOf.upload(y.bodyOf.data(), y.bodyOf.size(), s));
   ICHECK(w.rankInBody.upload(y.rankInBody.data(), y.rankInBody.size(), s));
   ICHECK(w.bodyPtr.upload(y.bodyPtr.data(), y.bodyPtr.size(), s));
+  ICHECK(w.colRank.upload(y.colRank.data(), y.colRank.size(), s));
   if (!w.host) { ICHECK(cudaMallocHost(&w.host, 1024 * sizeof(uint32_t))); w.hostCap = 1024; }
   if (!w.ready) ICHECK(cudaEventCreateWithFlags(&w.ready, cudaEventDisableTiming));
+  if (!w.fork) ICHECK(cudaEventCreateWithFlags(&w.fork, cudaEventDisableTiming));
+  for (int k = 0; k < 2; ++k) {
+    if (!w.aux[k]) ICHECK(cudaStreamCreateWithFlags(&w.aux[k], cudaStreamNonBlocking));
+    if (!w.join[k]) ICHECK(cudaEventCreateWithFlags(&w.join[k], cudaEventDisableTiming));
+  }
   return 0;
 }
 
@@ -727,24 +750,36 @@ int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const C
   IslandArgs a{};
   a.counts = w.counts.p; a.tierList = w.tierList.p; a.listStride = w.nBodies;
   a.islStart = w.islStart.p; a.order = w.order.p; a.pos = w.pos.p; a.nnzOff = w.nnzOff.p;
-  a.rowPtr = S.rowPtr; a.col = S.col; a.val = S.val;
+  a.rowPtr = S.rowPtr; a.col = S.col; a.val = S.val; a.colRank = w.colRank.p; a.rankInBody = w.rankInBody.p;
   a.cPtr = c.nUnique ? c.cPtr : nullptr; a.cCol = c.cCol; a.cVal = c.cVal; a.cDiag = (c.nTri || c.nFloor) ? c.cDiag : nullptr;
   a.slotOf = slotOf; a.blockNodes = pw.blockNodes; a.blockInv = pw.blockInv; a.blockMeta = pw.blockMeta;
   a.blkLocal = w.blkLocal.p; a.matCol = w.matCol.p; a.matVal = w.matVal.p; a.deltaScratch = pw.delta;
   a.apScratch = pw.ap; a.zScratch = pw.z; a.slotIsl = w.slotIsl.p;
   a.b = b; a.x = x; a.tol2 = tol * tol; a.maxIter = maxIter; a.stats = w.solveStats.p + 4ull * statSlot;
   int L = 0;
-  // largest islands first: their CTAs run longest
+  // Tiers 2 and 3 hold a handful of islands each of which keeps one CTA busy for a long chain of iterations: they run on
+  // their own streams, beside the thousands of small islands of tiers 0 and 1 that fill the other SMs.
+  const bool side = w.tierCount[3] || w.tierCount[2];
+  if (side) cudaEventRecord(w.fork, s);
   if (w.tierCount[3]) {
+    cudaStreamWaitEvent(w.aux[0], w.fork, 0);
     const uint32_t maxNodes = kTiers[3].caps.maxNodes;
     const size_t smem = 32ull * maxNodes + 2 * 9 * 32 * sizeof(float);
     cudaFuncSetAttribute(k_island_pcg_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_island_pcg_big<<<(int)std::min<uint32_t>(w.tierCount[3], kNumSMs), kBigTeam, smem, s>>>(a, maxNodes, 3);
+    k_island_pcg_big<<<(int)std::min<uint32_t>(w.tierCount[3], kNumSMs), kBigTeam, smem, w.aux[0]>>>(a, maxNodes, 3);
+    cudaEventRecord(w.join[0], w.aux[0]);
     ++L;
   }
-  if (w.tierCount[2]) { launchTier(k_island_pcg<512, 2, true>, 2, (int)std::min<uint32_t>(w.tierCount[2], kNumSMs), s, a); ++L; }
+  if (w.tierCount[2]) {
+    cudaStreamWaitEvent(w.aux[1], w.fork, 0);
+    launchTier(k_island_pcg<512, 2, true>, 2, (int)std::min<uint32_t>(w.tierCount[2], kNumSMs), w.aux[1], a);
+    cudaEventRecord(w.join[1], w.aux[1]);
+    ++L;
+  }
   if (w.tierCount[1]) { launchTier(k_island_pcg<320, 2, true>, 1, (int)std::min<uint32_t>(w.tierCount[1], 2 * kNumSMs), s, a); ++L; }
   if (w.tierCount[0]) { launchTier(k_island_pcg<32, 1, true>, 0, (int)std::min<uint32_t>((w.tierCount[0] + 7) / 8, 3 * kNumSMs), s, a); ++L; }
+  if (w.tierCount[3]) cudaStreamWaitEvent(s, w.join[0], 0);
+  if (w.tierCount[2]) cudaStreamWaitEvent(s, w.join[1], 0);
   return L;
 }
 

@@ -18,7 +18,7 @@ struct IslandCaps { uint32_t maxNodes, maxNnz, maxInv, maxBlocks; };
 
 struct IslandWork {
   // once per topology
-  DevBuf<uint32_t> bodyOf, rankInBody, bodyPtr;
+  DevBuf<uint32_t> bodyOf, rankInBody, bodyPtr, colRank;
   uint32_t nBodies = 0;
   // once per substep
   DevBuf<uint32_t> parent, vals, tmpVals, heads, nodeOff, posOfBody, islStart, order, pos, nnzOff, sortHist, scanScratch;
@@ -33,12 +33,17 @@ struct IslandWork {
   uint32_t* host = nullptr;       // pinned copy of counts (8 words) + solveStats
   uint32_t hostCap = 0;
   cudaEvent_t ready = nullptr;
+  // the CTA tiers with few, long-running islands (2, 3) run beside the small tiers on their own streams
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
   uint64_t scanCap = 0;
   uint32_t nLeftIslands = 0, nLeftNodes = 0;  // host copies after buildIslands
   uint32_t tierCount[kIslandTiers] = {0, 0, 0, 0};
   cudaError_t lastError = cudaSuccess;
   ~IslandWork() {
     if (ready) cudaEventDestroy(ready);
+    if (fork) cudaEventDestroy(fork);
+    for (int k = 0; k < 2; ++k) { if (join[k]) cudaEventDestroy(join[k]); if (aux[k]) cudaStreamDestroy(aux[k]); }
     if (host) cudaFreeHost(host);
   }
 };

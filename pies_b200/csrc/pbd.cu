@@ -684,8 +684,8 @@ int tickPBD(PiesB200Solver* s, bool refreshMirror) {
   cudaStream_t st = s->stream;
   const PiesB200Options& o = s->opt;
   const float dt = o.fixedTimestepSize / (float)o.timeSubsteps;
-  cudaEvent_t tick0, tick1;
-  cudaEventCreate(&tick0); cudaEventCreate(&tick1);
+  if ((rc = ensureTickEvents(s))) return rc;
+  cudaEvent_t tick0 = s->tickEv[0], tick1 = s->tickEv[1];  // solver-owned: an early return below leaks nothing
   cudaEventRecord(tick0, st);
   PCHECK(cudaMemsetAsync(w.counters.p, 0, 64 * sizeof(uint32_t), st));
   w.countersUsed = 0; w.visitsLastTick = 0;
@@ -713,7 +713,6 @@ done:
   cudaEventRecord(tick1, st);
   cudaError_t es = cudaEventSynchronize(tick1);
   cudaEventElapsedTime(&s->stats.msTick, tick0, tick1);
-  cudaEventDestroy(tick0); cudaEventDestroy(tick1);
   if (rc) return rc;
   if (es != cudaSuccess) return failCuda(s, es, "cudaEventSynchronize", __LINE__);
   PCHECK(cudaGetLastError());

@@ -316,6 +316,12 @@ void buildSystem(const HostScene& sc, float h, HostSystem& out, unsigned threads
       out.rankInBody[i] = cur[b] - out.bodyPtr[b];
       out.bodyNodes[cur[b]++] = i;
     }
+    out.colRank.resize(out.col.size());
+    for (uint32_t r = 0; r < n; ++r)
+      for (int k = out.rowPtr[r]; k < out.rowPtr[r + 1]; ++k) {
+        const uint32_t c = (uint32_t)out.col[k];
+        out.colRank[k] = out.bodyOf[c] == out.bodyOf[r] ? out.rankInBody[c] : 0xffffffffu;
+      }
   }
   out.blockInv.assign((size_t)out.nBlocks * 1024, 0.0f);
   auto invertBlocks = [&](unsigned t) {

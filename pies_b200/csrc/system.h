@@ -49,6 +49,9 @@ struct HostSystem {
   std::vector<uint32_t> rankInBody;           // n: node -> position inside bodyNodes[bodyPtr[b] ..)
   std::vector<uint32_t> bodyPtr;              // nBodies + 1
   std::vector<uint32_t> bodyNodes;            // n
+  // per CSR entry of S: rankInBody of its column (S never leaves a body), 0xffffffff for an explicit zero that points
+  // outside the row's body (bend stencils); lets the island solver re-index a row without a gather per entry
+  std::vector<uint32_t> colRank;
 
   uint64_t staticProjections = 0;             // per PD iteration, shape/goal count one per member
 };

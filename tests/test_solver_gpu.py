@@ -271,6 +271,28 @@ def test_empty_scene_and_clear(pb):
     assert np.isfinite(s.positions).all()
 
 
+def test_clear_then_smaller_scene_reads_only_the_new_scene(pb):
+    """tick -> clear -> create a SMALLER scene -> getVertices with no getVertices in between: the stale device state of
+    the old scene must not be scattered into (and past the end of) the new vertex mirror, and the collision readback
+    must refuse instead of copying the old scene's row pointers."""
+    s = pb.Solver(iterations=10)
+    for k in range(4):
+        s.createTetBox((3.0 * k, 0.3, 0.0), 1.0, (0, 0, 0), 1000.0, 1.0, False)   # resting on the floor: floor contacts
+    for _ in range(20):
+        s.tick()
+    assert s.stats().staticCollisions > 0
+    s.clear()
+    s.createBox((1.0, 2.0, 3.0), 0.5, 100.0)           # 8 nodes instead of 108
+    g = golden("factories")
+    v = s.getVertices()
+    assert len(v) == len(g["box_pos"]) and (v["position"] == g["box_pos"]).all()
+    assert s.stats().staticCollisions == 0 and s.stats().triCollisions == 0
+    with pytest.raises(pb.PiesError):
+        s.collisionCsr()
+    s.tick()
+    assert np.isfinite(s.positions).all() and len(s.positions) == len(g["box_pos"])
+
+
 def test_bodies_added_between_ticks(pb, ref):
     """Hosts add bodies while the simulation runs; both sides must agree afterwards."""
     r = ref.RefSolver()
