@@ -80,7 +80,7 @@ public:
   // The reference's default constructor leaves its per-thread scratch empty and crashes on the first PD
   // tick; here Solver() == Solver(SolverOptions{}).
   Solver() : Solver(SolverOptions{}) {}
-  explicit Solver(const SolverOptions& options, int device = -1) : _options(options) {
+  Solver(const SolverOptions& options, int device = -1) : _options(options) {  // not explicit, like the reference (Solver.h:55)
     PiesB200Options o;
     pies_b200_default_options(&o);
     o.fixedTimestepSize = options.fixedTimestepSize;

@@ -70,7 +70,9 @@ typedef struct PiesB200Tuning {
                               * 2 = ordered contact sweeps of every cluster above 32 nodes by the dataflow executor
                               *     (no shared-memory sweeps of mid-size clusters; same result, for testing);
                               * 4 = no island-local solves: every island goes to the grid-wide CG (for testing);
-                              * 16 << t = island tier t (0..3) disabled: its islands move to the next tier that fits */
+                              * 16 << t = island tier t (0..3) disabled: its islands move to the next tier that fits;
+                              * 256 = island tier 3 enabled (one 1024-thread CTA per island of up to 7 168 nodes; off by default:
+                              *       such islands go to the grid-wide CG) */
 } PiesB200Tuning;
 
 /* Counters and device-side phase timings of the most recent tick ([additive]). */

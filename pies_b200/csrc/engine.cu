@@ -458,7 +458,10 @@ int pdSubstepBegin(PiesB200Solver* s) {
     s->launches += LC;
     // islands of S + C_t: which solves stay inside one warp / one CTA (islands.cu)
     if (s->islands) {
-      const uint32_t tiers = (s->tune.reserved & 4u) ? 0u : (0xFu & ~((s->tune.reserved >> 4) & 0xFu));
+      // tier 3 (one 1024-thread CTA per island of up to 7 168 nodes) is opt-in: a handful of such islands keep single SMs
+      // busy for milliseconds, the grid-wide CG spreads them over the whole device
+      const uint32_t avail = (s->tune.reserved & 256u) ? 0xFu : 0x7u;
+      const uint32_t tiers = (s->tune.reserved & 4u) ? 0u : (avail & ~((s->tune.reserved >> 4) & 0xFu));
       int LI = 0;
       if (buildIslands(*s->islands, st, n, v.A, c->lists, bw.slotOf.p, bw.blockCount.p, bw.nBlocksBound, tiers, &LI) != 0) {
         cudaError_t e = s->islands->lastError;

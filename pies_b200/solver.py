@@ -206,7 +206,7 @@ class Solver:
             pass
 
     def setTuning(self, pcgTolerance=None, pcgMaxIterations=None, pcgCheckEvery=None, profilePhases=None, dataflowSweepsOnly=None,
-                  islandSolves=None, islandTiersOff=None):
+                  islandSolves=None, islandTiersOff=None, islandBigTier=None):
         t = Tuning()
         lib().pies_b200_default_tuning(C.byref(t))
         cur = getattr(self, "_tuning", None)
@@ -219,6 +219,7 @@ class Solver:
         if dataflowSweepsOnly is not None: t.reserved = (t.reserved & ~2) | (2 if dataflowSweepsOnly else 0)
         if islandSolves is not None: t.reserved = (t.reserved & ~4) | (0 if islandSolves else 4)
         if islandTiersOff is not None: t.reserved = (t.reserved & ~0xF0) | ((int(islandTiersOff) & 0xF) << 4)
+        if islandBigTier is not None: t.reserved = (t.reserved & ~256) | (256 if islandBigTier else 0)
         self._tuning = t
         self._ck(lib().pies_b200_set_tuning(self.h, C.byref(t)))
 

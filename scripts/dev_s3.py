@@ -10,7 +10,7 @@ s = pb.Solver(**scenes.S3_OPTIONS)
 scenes.build_s3(s, bodies)
 print("scene built in %.2fs, nodes %d" % (time.time() - t0, len(s.getVertices())), flush=True)
 s.setTuning(profilePhases=True, dataflowSweepsOnly=bool(int(os.environ.get("DATAFLOW_ONLY", "0"))),
-            islandSolves=not int(os.environ.get("NO_ISLANDS", "0")), islandTiersOff=int(os.environ.get("TIERS_OFF", "0")))
+            islandSolves=not int(os.environ.get("NO_ISLANDS", "0")), islandTiersOff=int(os.environ.get("TIERS_OFF", "0")), islandBigTier=bool(int(os.environ.get("BIG_TIER", "0"))))
 t0 = time.time(); s.tick(); print("first tick (incl. system build + upload) %.2fs" % (time.time() - t0), flush=True)
 for t in range(1, ticks):
     t1 = time.time(); s.tick(); wall = time.time() - t1

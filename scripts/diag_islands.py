@@ -9,7 +9,7 @@ def make(**tune):
     s = pb.Solver(**scenes.S3_OPTIONS); scenes.build_s3(s, bodies=16, nx=2, nz=2)
     if tune: s.setTuning(**tune)
     return s
-runs = {"grid": make(islandSolves=False), "isl": make(), "noWarp": make(islandTiersOff=1), "t2+": make(islandTiersOff=3), "t3": make(islandTiersOff=7),
+runs = {"grid": make(islandSolves=False), "isl": make(), "noWarp": make(islandTiersOff=1), "t2+": make(islandTiersOff=3), "t3": make(islandTiersOff=7, islandBigTier=True),
         "isl_tol1e-8": make(pcgTolerance=1e-8)}
 for t in range(1, 47):
     P = {}

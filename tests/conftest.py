@@ -37,3 +37,12 @@ def ref():
 def bbox_diag(p):
     p = np.asarray(p)
     return float(np.linalg.norm(p.max(0) - p.min(0)))
+
+
+def noise_floor(scene, tick):
+    """Largest position difference the UNMODIFIED reference shows against itself at `tick` of `scene` when its positions
+    are perturbed by at most 1e-6 (about one fp32 ulp) before every tick (tests/golden/sensitivity.py, committed numbers
+    in tests/golden/sensitivity.json): the floor an equally valid fp32 evaluation cannot be expected to beat."""
+    import json
+    with open(os.path.join(GOLDEN, "sensitivity.json")) as f:
+        return float(json.load(f)[scene]["every_tick"][str(tick)])

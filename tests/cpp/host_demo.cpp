@@ -5,13 +5,40 @@
 // that nothing in this file changes between the two builds; tests/test_cpp_dropin.py runs both
 // and compares the vertex positions they write.
 //
-// usage: host_demo <scene> <ticks> <out.bin>     scene in {twobox, sheet, boxes, shapes}
+// usage: host_demo <scene> <ticks> <out.bin>     scene in {twobox, sheet, boxes, shapes, tetcube}
 #include <Pies/Solver.h>
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <tuple>
 #include <vector>
+
+// closed triangulated surface of an axis-aligned cube, n x n quads per face, shared vertices: the input of
+// Solver::addTriMeshVolume (reference Solver.h:77-87), which tetrahedralises it with TetGen on both builds
+static void cubeSurface(float side, int n, glm::vec3 origin, std::vector<glm::vec3>& verts, std::vector<uint32_t>& tris) {
+  std::map<std::tuple<int, int, int>, uint32_t> index;
+  auto vid = [&](int i, int j, int k) {
+    auto key = std::make_tuple(i, j, k);
+    auto it = index.find(key);
+    if (it != index.end()) return it->second;
+    uint32_t id = (uint32_t)verts.size();
+    verts.push_back(origin + glm::vec3(side * i / n, side * j / n, side * k / n));
+    index.emplace(key, id);
+    return id;
+  };
+  auto quad = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    tris.insert(tris.end(), {a, b, c, a, c, d});
+  };
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < n; ++b)
+      for (int f = 0; f <= n; f += n) {
+        quad(vid(f, a, b), vid(f, a + 1, b), vid(f, a + 1, b + 1), vid(f, a, b + 1));
+        quad(vid(a, f, b), vid(a + 1, f, b), vid(a + 1, f, b + 1), vid(a, f, b + 1));
+        quad(vid(a, b, f), vid(a + 1, b, f), vid(a + 1, b + 1, f), vid(a, b + 1, f));
+      }
+}
 
 int main(int argc, char** argv) {
   if (argc < 4) { std::fprintf(stderr, "usage: %s <scene> <ticks> <out.bin>\n", argv[0]); return 2; }
@@ -34,6 +61,11 @@ int main(int argc, char** argv) {
   } else if (!std::strcmp(scene, "shapes")) {
     solver.createShapeMatchingBox(glm::vec3(0.0f, 3.0f, 0.0f), 3, 3, 3, 1.0f, glm::vec3(0.0f), 1000.0f);
     solver.createShapeMatchingBox(glm::vec3(4.0f, 2.0f, 1.0f), 4, 3, 5, 1.0f, glm::vec3(0.0f), 800.0f);
+  } else if (!std::strcmp(scene, "tetcube")) {
+    std::vector<glm::vec3> verts;
+    std::vector<uint32_t> tris;
+    cubeSurface(4.0f, 4, glm::vec3(0.0f, 1.07f, 0.0f), verts, tris);
+    solver.addTriMeshVolume(verts, tris, glm::vec3(0.0f), 1.0f, 1000.0f, 0.8f, 1.0f, 1000.0f, 1.0f, 1.0f);
   } else {
     std::fprintf(stderr, "unknown scene %s\n", scene);
     return 2;

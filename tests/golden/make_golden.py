@@ -183,11 +183,14 @@ def stack():
     r = RefSolver(**scenes.S3_OPTIONS)
     scenes.build_s3(r, bodies=16, nx=2, nz=2)
     out = {}
+    counts = []
     for t in range(1, 101):
         r.tick()
+        counts.append((r.count("tri_collision"), r.count("static_collision")))
         if t in (1, 10, 40, 44, 50, 100):
             out["pos%d" % t] = r.positions; out["vel%d" % t] = r.velocities
             out["ncoll%d" % t] = np.array([r.count("tri_collision"), r.count("static_collision")])
+    out["counts"] = np.asarray(counts)   # per tick: a threshold contact caught by only one side shows up here first
     save("stack16", **out)
 
 
@@ -255,6 +258,40 @@ def pbd():
     save("pbd", **out)
 
 
+def s1_full():
+    """S1 at full size (config 1): the side-8 cube with a 20 x 20-quad surface per face (~10 k tets after the reference's
+    TetGen run), strain + volume w 1000, default options, dropped from y0 = 3.07 onto the floor (first floor contacts
+    around tick 64).  The mesh itself is part of the fixture, so the GPU side needs no TetGen and no oracle."""
+    with quiet():
+        r = RefSolver()
+        pts, tets, faces = scenes.add_tetgen_cube(r, n=20, origin=(0.0, 3.07, 0.0))
+    out = dict(points=pts, tets=tets, faces=faces)
+    for t in range(1, 101):
+        r.tick()
+        if t in (1, 10, 60, 70, 80, 100):
+            out["pos%d" % t] = r.positions; out["vel%d" % t] = r.velocities
+            out["ncoll%d" % t] = np.array([r.count("tri_collision"), r.count("static_collision")])
+    save("s1_full", **out)
+
+
+def s5_pair():
+    """Two S5 bodies at full resolution (config 5: the side-8 cube with a 24 x 24-quad surface, 16 437 tets / 4 508
+    nodes each): one resting just above the floor, the second dropped onto it from half a unit above, offset in x and z,
+    so the run covers floor contact, body-body point-triangle contacts and a 9 k-node island."""
+    with quiet():
+        r = RefSolver()
+        pts, tets, faces = scenes.add_tetgen_cube(r, n=24, origin=(0.0, 0.07, 0.0))
+        pts2, tets2, faces2 = scenes.add_tetgen_cube(r, n=24, origin=(1.3, 8.57, 0.9))
+    # TetGen runs once per body: the two meshes need not be translates of each other, so both are kept
+    out = dict(points=pts, tets=tets, faces=faces, points2=pts2, tets2=tets2, faces2=faces2)
+    for t in range(1, 61):
+        r.tick()
+        if t in (1, 10, 30, 40, 50, 60):
+            out["pos%d" % t] = r.positions; out["vel%d" % t] = r.velocities
+            out["ncoll%d" % t] = np.array([r.count("tri_collision"), r.count("static_collision")])
+    save("s5_pair", **out)
+
+
 if __name__ == "__main__":
     import sys
     lib().pref_srand(1)
@@ -270,3 +307,5 @@ if __name__ == "__main__":
     stack()
     clusters()
     pbd()
+    s1_full()
+    s5_pair()

@@ -93,3 +93,61 @@ def test_config5_reduced_tetgen_bodies(pb, ref):
     scenes.build_s5(r2, d, **kw)
     assert len(g.getVertices()) == r.count("node") and (g.getTriangles() == r.getTriangles()).all()
     run_against_reference(r, g, d, 36)
+
+
+# ---- configs 1 and 5 at full per-body size, against committed reference fixtures (no oracle, no TetGen at run time) ----
+def test_config1_full_size_tetgen_cube(pb):
+    """BASELINE configs[0] at its stated size: the ~10 k-tet TetGen cube (mesh committed with the fixture,
+    tests/golden/make_golden.py::s1_full) falling onto the floor, default options.  Positions within 1e-4 x diagonal of
+    the reference and identical contact counts through free fall, first floor contact (tick 64) and settling; the CG
+    iterations of a 3 067-node connected mesh are reported (the body is one island: CTA-1024 tier)."""
+    from conftest import golden
+    g = golden("s1_full")
+    s = pb.Solver()
+    s.addTetMeshVolume(g["points"], g["tets"], g["faces"], (0, 0, 0), 1.0, 1000.0, 0.8, 1.0, 1000.0, 1.0, 1.0)
+    tol = 1e-4 * bbox_diag(g["points"])
+    iters = []
+    for t in range(1, 101):
+        s.tick()
+        st = s.stats()
+        iters.append(st.pcgIterationsLastTick / 4.0)
+        assert st.pcgCapHits == 0, t
+        if t in (1, 10, 60, 70, 80, 100):
+            assert (st.triCollisions, st.staticCollisions) == tuple(g["ncoll%d" % t]), t
+            err = np.abs(s.positions - g["pos%d" % t]).max()
+            assert err <= tol, (t, err, tol)
+    print("config 1 (10 960 tets): CG iterations per solve, mean %.1f max %.1f; tiers %s grid-wide %d" % (
+        np.mean(iters), np.max(iters), list(st.islandsTier), st.islandsGlobal))
+
+
+def test_config5_two_full_size_bodies(pb):
+    """Two config-5 bodies at full resolution (16 546 + 16 441 tets, both meshes committed with the fixture,
+    make_golden.py::s5_pair): floor contact from tick 10, body-body contact from tick ~45.  Until the bodies touch the
+    trajectory is held to 1e-4 x diagonal with identical contact counts; at tick 50 and 60 (thousands of live
+    point-triangle contacts between two flat faces) the counts may differ by the threshold cases and positions are held to
+    1e-3 x diagonal.  Reports the CG iterations per solve of 4.5 k-node connected meshes under the <= 32-node block
+    preconditioner."""
+    from conftest import golden
+    g = golden("s5_pair")
+    s = pb.Solver()
+    args = ((0, 0, 0), 1.0, 1000.0, 0.8, 1.0, 1000.0, 1.0, 1.0)
+    s.addTetMeshVolume(g["points"], g["tets"], g["faces"], *args)
+    s.addTetMeshVolume(g["points2"], g["tets2"], g["faces2"], *args)
+    diag = bbox_diag(np.concatenate([g["points"], g["points2"]]))
+    iters = []
+    for t in range(1, 61):
+        s.tick()
+        st = s.stats()
+        iters.append(st.pcgIterationsLastTick / 4.0)
+        assert st.pcgCapHits == 0, t
+        if t in (1, 10, 30, 40, 50, 60):
+            err = np.abs(s.positions - g["pos%d" % t]).max()
+            nt, nf = g["ncoll%d" % t]
+            if t <= 40:
+                assert (st.triCollisions, st.staticCollisions) == (nt, nf), t
+                assert err <= 1e-4 * diag, (t, err)
+            else:
+                assert st.staticCollisions == nf and abs(int(st.triCollisions) - int(nt)) <= 0.05 * nt + 8, (t, st.triCollisions, nt)
+                assert err <= 1e-3 * diag, (t, err)
+    print("config 5 pair: CG iterations per solve, mean %.1f max %.1f; tiers %s grid-wide %d (%d nodes)" % (
+        np.mean(iters), np.max(iters), list(st.islandsTier), st.islandsGlobal, st.islandNodesGlobal))

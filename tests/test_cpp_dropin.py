@@ -47,7 +47,7 @@ def test_reference_build_of_the_demo_runs(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scene,ticks", [("twobox", 12), ("sheet", 10), ("shapes", 6), ("boxes", 10)])
+@pytest.mark.parametrize("scene,ticks", [("twobox", 12), ("sheet", 10), ("shapes", 6), ("boxes", 10), ("tetcube", 12)])
 def test_same_host_source_same_result(tmp_path, scene, ticks):
     """Positions within 1e-4 x bbox diagonal (north_star tolerance); radii, triangles and lines exact."""
     _need(OURS, REF)
