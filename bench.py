@@ -127,8 +127,16 @@ def main():
     ap.add_argument("--bodies", type=int, default=FULL_BODIES, help="debug: smaller S3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", type=float, default=4.0, help="ghost layer width along x (4.0 = two S3 columns)")
-    ap.add_argument("--preroll", type=int, default=60, help="untimed ticks before warm-up: 60 = the contact regime")
+    ap.add_argument("--preroll", type=int, default=None, help="untimed ticks before warm-up (default: 60 for s3, 70 for s5 = the contact regime)")
+    ap.add_argument("--workload", default="s3", choices=["s3", "s5"],
+                    help="s3 (default, the metric's configuration; weak scaling for --gpus > 1) or s5: BASELINE configs[4], "
+                         "512 TetGen bodies of 16.5 k tets, STRONG scaling: the same scene cut into --gpus x-slabs")
+    ap.add_argument("--big-tier", action="store_true", help="island tier 3 on (one 1024-thread CTA per island of up to 7 168 nodes)")
     args = ap.parse_args()
+    if args.preroll is None:
+        args.preroll = 70 if args.workload == "s5" else 60
+    if args.workload == "s5" and args.bodies == FULL_BODIES:
+        args.bodies = 512
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -138,7 +146,16 @@ def main():
               "iterations": 10, "substeps": 1, "parallelism": "replicas x%d" % world if world > 1 else "1 GPU",
               "l2": "working set > L2 (elements 80 MB + contributions 64 MB + CSR/preconditioner 120 MB per PD iteration)"}
 
+    if args.workload == "s5":
+        config = {"workload": "S5: %d x TetGen cube body (16 546 tets, 4 518 nodes, 6 912 boundary triangles each; one committed mesh "
+                              "replicated), PD, tet strain+volume, 10 iterations/substep, dropped onto the floor and each other" % args.bodies,
+                  "nodes": 4518 * args.bodies, "tets": 16546 * args.bodies, "static_projections_per_iteration": 2 * 16546 * args.bodies,
+                  "iterations": 10, "substeps": 1, "parallelism": "1 GPU", "l2": "working set > L2"}
     if args.impl == "reference":
+        if args.workload != "s3":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference arm times the metric's configuration (S3) only"}))
+            return 0
         if rank != 0:
             return 0
         res = run_reference(args, args.steps, args.warmup, threads=8)
@@ -177,7 +194,7 @@ def main():
         torch.cuda.synchronize()
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "s3":
         try:
             cpu = run_reference(args, steps=10, warmup=min(warmup, 5), quiet=True, threads=8)
         except Exception as e:  # the oracle is optional here; say so instead of inventing a number
@@ -188,7 +205,28 @@ def main():
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
     drv = None
-    if world == 1:
+    scaling = "weak"
+    if args.workload == "s5":
+        scaling = "strong"
+        if world == 1:
+            s = pb.Solver(device=local_rank, **scenes.S3_OPTIONS)
+            scenes.build_s5_replicated(s, args.bodies)
+            s.setStream(stream.cuda_stream)
+            tick = s.tick
+        else:
+            # Strong scaling: the SAME scene on every world size, cut into x slabs of equal constraint count.  Bodies are 8
+            # wide on a pitch of 10, so a ghost layer of 1.0 is empty while the bodies fall straight down; every rank checks
+            # the layer before the timed window (and repartitions with ghosts if bodies have drifted into reach).
+            from pies_b200 import multigpu
+            pts, tets, faces = scenes.cube24_mesh()
+            specs = [multigpu.tetmesh(pts + o, tets, faces) for o in scenes.s5_origins(args.bodies)]
+            drv = multigpu.SlabSolver(specs, rank=rank, world=world, halo=1.0, device=local_rank, dist=dist, snap=1.0,
+                                      **scenes.S3_OPTIONS)
+            s = drv.solver
+            tick = drv.tick
+            config["parallelism"] = ("x-slabs x%d of the same %d-body scene (strong scaling), ghost layer 1.0, NCCL halo exchange from inside "
+                                     "pies_b200_tick when bodies of different slabs come within reach" % (world, args.bodies))
+    elif world == 1:
         s = pb.Solver(device=local_rank, **scenes.S3_OPTIONS)
         scenes.build_s3(s, args.bodies)
         s.setStream(stream.cuda_stream)
@@ -206,11 +244,11 @@ def main():
         s = drv.solver
         tick = drv.tick
         owned_static = drv.owned_static
-        config["parallelism"] = "x-slabs x%d, %d-body S3 per rank, halo %.1f (two bodies deep), NCCL halo exchange per substep and per PD iteration" % (
-            world, args.bodies, args.halo)
+        config["parallelism"] = ("x-slabs x%d, %d-body S3 per rank, halo %.1f (two bodies deep), NCCL halo exchange per substep and per PD "
+                                 "iteration from inside pies_b200_tick (ncclSend/ncclRecv, csrc/halo.cu)" % (world, args.bodies, args.halo))
         config["nodes"] *= world; config["tets"] *= world; config["static_projections_per_iteration"] *= world
     n = len(s.getVertices())
-    s.setTuning(profilePhases=True)
+    s.setTuning(profilePhases=True, islandBigTier=bool(args.big_tier))
 
     def projections():
         if drv is not None:
@@ -244,6 +282,17 @@ def main():
         tick()
     for _ in range(warmup):
         tick()
+    repartitioned = False
+    if drv is not None:
+        # untimed: every rank checks that its ghost layer still holds every body its own bodies can touch and the scene is
+        # repartitioned if not, so the timed window below never runs on a stale partition
+        repartitioned = not drv.check_halo(repartition=True)
+        s = drv.solver
+        s.setTuning(profilePhases=True, islandBigTier=bool(args.big_tier))
+        if repartitioned:
+            for _ in range(3):
+                tick()
+        n = len(s.getVertices())
     # snapshot so the device-resident and the end-to-end measurements replay the same ticks
     snap = [torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy() for _ in range(3)]
     snap[0][:] = s.positions; snap[1][:] = s.prevPositions; snap[2][:] = s.velocities
@@ -253,8 +302,10 @@ def main():
     kern = {k: [0.0, 0] for k in ("tet", "gather", "spmv", "update", "island")}
     island_row_iters = 0
     cap_hits = 0
-    phases = {"local": 0.0, "global": 0.0, "detect": 0.0, "contact": 0.0, "other": 0.0}
+    phases = {"local": 0.0, "global": 0.0, "detect": 0.0, "contact": 0.0, "other": 0.0, "halo": 0.0}
     proj = launches = pcg_iters = 0
+    if drv is not None:
+        drv.halo_bytes = 0
     barrier()
     sampler = ClockSampler(local_rank)
     t0 = time.time()
@@ -273,7 +324,7 @@ def main():
         island_row_iters += st.pcgIslandRowIterations
         cap_hits += st.pcgCapHits
         phases["local"] += st.msLocal; phases["global"] += st.msGlobal; phases["detect"] += st.msDetect
-        phases["contact"] += st.msContact; phases["other"] += st.msOther
+        phases["contact"] += st.msContact; phases["other"] += st.msOther; phases["halo"] += st.msHalo
     ev1.record(stream)
     barrier()
     wall_ms = 1e3 * (time.time() - t0)
@@ -321,11 +372,11 @@ def main():
     if rank == 0:
         peak, peak_kind = load_peaks()
         st = s.stats()
-        nnz = s.systemNonZeros() if hasattr(s, "systemNonZeros") else 223 * (n // 27)
+        nnz = int(st.systemNonZeros)
         total_phase = sum(phases.values()) or 1.0
         # Algorithmic bytes per launch (the split of the 176 B per tet-type projection between the
         # kernel that writes the contributions and the gather that re-reads them is stated in DESIGN.md section 4).
-        local_proj = 2 * (n // 27) * 48
+        local_proj = int(st.staticProjections)
         # island solves: a CG iteration of the SURVEY model costs 8 B per non-zero + 136 B per node; the island kernels ran
         # island_row_iters x 32 row-iterations in kern["island"][1] solves (iterations differ per island)
         isl_solves = max(1, kern["island"][1])
@@ -365,7 +416,7 @@ def main():
         line = {
             "metric": "constraint projections/s", "value": proj_all / (dev_ms_max * 1e-3), "unit": "projections/s",
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": dev_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
             "substeps_per_s": args.steps / (dev_ms_max * 1e-3),
             "wall_ms_per_step": wall_ms_max / args.steps,
@@ -392,7 +443,8 @@ def main():
         }
         if drv is not None:
             line["halo"] = {"bytes_per_step_rank0": halo_bytes / args.steps, "ghost_layer_still_sufficient": bool(halo_ok), "ghost_nodes_rank0": int((~drv.owned).sum()),
-                            "owned_nodes_rank0": int(drv.owned.sum())}
+                            "owned_nodes_rank0": int(drv.owned.sum()), "exchanges_per_step": int(st.haloExchangesLastTick),
+                            "inside_the_library": bool(drv.native_halo), "repartitioned_before_timing": bool(repartitioned)}
         if cpu is not None:
             if "error" in cpu:
                 line["cpu_baseline"] = {"value": None, "unit": "projections/s", "cores": os.cpu_count(), "kind": "reference",

@@ -116,6 +116,13 @@ typedef struct PiesB200Stats {
   float msIslandKernels;       /* time inside the island-local solve kernels (phase timing on only) */
   uint32_t islandKernelLaunches;
   uint64_t pcgIslandRowIterations; /* sum over island solves of iterations x ceil(rows / 32): the work the island kernels did */
+  /* slab-partitioned runs (pies_b200_halo_*): bytes sent + received, exchanges and device time of the halo exchanges */
+  uint64_t haloBytesLastTick;
+  uint32_t haloExchangesLastTick;
+  float msHalo;
+  uint64_t systemNonZeros;     /* non-zeros of S = M/h^2 + sum w A^T A (both triangles), for the CG byte model */
+  uint32_t staticBodies;       /* connected components of S */
+  uint32_t reserved2;
 } PiesB200Stats;
 
 typedef struct PiesB200Solver PiesB200Solver;
@@ -239,6 +246,21 @@ int pies_b200_set_triangle_order(PiesB200Solver* s, uint32_t n, const uint32_t* 
 /* mask[i] != 0: node i is owned by this solver (others are ghosts); only used for counting. */
 int pies_b200_set_owned_nodes(PiesB200Solver* s, uint32_t n, const uint8_t* mask);
 int pies_b200_count_owned_contacts(PiesB200Solver* s, uint32_t* nTri, uint32_t* nFloor);
+
+/* ---- [additive] multi-GPU inside the library: NCCL halo exchange of a slab-partitioned scene (the
+ *      reference is single-process, so this replaces nothing in it).  One process (or thread) per GPU; each solver holds
+ *      its slab's bodies plus ghost copies of the neighbours' boundary bodies, created in global body order.  After
+ *      halo_init + halo_set_lists, pies_b200_tick() itself overwrites the ghost rows with their owners' values at every
+ *      substep start (position, previous position, velocity) and after every local/global iteration (position), and all
+ *      ranks stop together if one fails.  NCCL is dlopen-ed (libnccl.so.2); without it halo_init fails. ---- */
+int pies_b200_halo_unique_id(void* out128);                       /* ncclGetUniqueId: call on one rank, hand the 128 bytes to all */
+int pies_b200_halo_init(PiesB200Solver* s, int rank, int world, const void* id128);  /* collective: ncclCommInitRank */
+/* peers[k]: rank of the k-th slab neighbour; sendIdx holds, peer after peer, the local rows that are ghosts on that peer
+ * (sendCounts[k] of them), recvIdx the local ghost rows owned by it; both sides list shared bodies in global order. */
+int pies_b200_halo_set_lists(PiesB200Solver* s, int nPeers, const int* peers, const uint32_t* sendCounts,
+                             const uint32_t* sendIdx, const uint32_t* recvCounts, const uint32_t* recvIdx);
+int pies_b200_halo_exchange(PiesB200Solver* s, int planes);      /* explicit exchange, planes = 1 or 3 (tick() does this itself) */
+int pies_b200_halo_destroy(PiesB200Solver* s);
 
 /* ---- [additive] per-kernel probes: run the device functions of the hot kernels on caller data ---- */
 /* Tet strain / volume projections (reference Constraints.cpp:76-128, :205-255): pos 12 floats,

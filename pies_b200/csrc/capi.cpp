@@ -10,6 +10,7 @@
 #include <cstdlib>
 
 #include "engine.h"
+#include "halo.h"
 
 using pies::fail;
 
@@ -146,7 +147,8 @@ int pies_b200_get_options(const PiesB200Solver* s, PiesB200Options* out) {
 
 // ---- stepping ----
 static int tickOnce(PiesB200Solver* s, int which, bool refresh) {
-  if (s->simFailed) return PIES_B200_OK;  // Solver.cpp:26-28: silent no-op once failed
+  // Solver.cpp:26-28: silent no-op once failed (a slab rank still joins its peers' failure reduction inside tickPD)
+  if (s->simFailed && !(which != 0 && s->halo && s->halo->world > 1)) return PIES_B200_OK;
   cudaSetDevice(s->device);
   (void)refresh;  // the vertex mirror is refreshed lazily by pies_b200_get_vertices
   if (which == 0) return pies::tickPBD(s, false);
@@ -181,6 +183,28 @@ int pies_b200_clear(PiesB200Solver* s) {
     s->renderStateDirty = true;
     return PIES_B200_OK;
   });
+}
+
+// ---- multi-GPU halo (halo.cu) ----
+int pies_b200_halo_unique_id(void* out128) {
+  if (!out128) return PIES_B200_EINVAL;
+  std::string err;
+  int rc = pies::haloUniqueId(out128, &err);
+  if (rc) g_createError = "halo_unique_id: " + err;
+  return rc;
+}
+int pies_b200_halo_init(PiesB200Solver* s, int rank, int world, const void* id128) {
+  return guarded(s, [&]() { cudaSetDevice(s->device); return pies::haloInit(s, rank, world, id128); });
+}
+int pies_b200_halo_set_lists(PiesB200Solver* s, int nPeers, const int* peers, const uint32_t* sendCounts, const uint32_t* sendIdx,
+                             const uint32_t* recvCounts, const uint32_t* recvIdx) {
+  return guarded(s, [&]() { cudaSetDevice(s->device); return pies::haloSetLists(s, nPeers, peers, sendCounts, sendIdx, recvCounts, recvIdx); });
+}
+int pies_b200_halo_exchange(PiesB200Solver* s, int planes) {
+  return guarded(s, [&]() { cudaSetDevice(s->device); int rc = pies::haloExchange(s, planes); if (!rc) s->deviceNewer = true; return rc; });
+}
+int pies_b200_halo_destroy(PiesB200Solver* s) {
+  return guarded(s, [&]() { cudaSetDevice(s->device); cudaStreamSynchronize(s->stream); pies::haloDestroy(s); return PIES_B200_OK; });
 }
 
 // ---- readback ----

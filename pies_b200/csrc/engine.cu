@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "contact.h"
 #include "detect.h"
+#include "halo.h"
 #include "islands.h"
 #include "reblock.h"
 
@@ -230,6 +231,8 @@ int ensureBuilt(PiesB200Solver* s) {
   s->vtxDevValid = false;
   s->hostStateDirty = false;
   s->stats.staticProjections = y.staticProjections;
+  s->stats.systemNonZeros = y.col.size();
+  s->stats.staticBodies = y.nBodies;
   s->lastPcgIters = 1;
   return PIES_B200_OK;
 }
@@ -277,7 +280,7 @@ int refreshVertexMirror(PiesB200Solver* s) {
 namespace {
 // Phase timing with CUDA event pairs recorded on the solver stream and resolved after the
 // tick's final synchronisation (no extra syncs inside the tick).  Enabled by tuning.reserved.
-enum Phase { kPhOther = 0, kPhDetect, kPhLocal, kPhGlobal, kPhContact, kPhTetKernel, kPhSpmvKernel, kPhUpdateKernel, kPhGatherKernel, kPhIslandKernel, kPhCount };
+enum Phase { kPhOther = 0, kPhDetect, kPhLocal, kPhGlobal, kPhContact, kPhTetKernel, kPhSpmvKernel, kPhUpdateKernel, kPhGatherKernel, kPhIslandKernel, kPhHalo, kPhCount };
 struct PhaseTimer {
   PiesB200Solver* s;
   bool on;
@@ -395,6 +398,7 @@ int pdTickBegin(PiesB200Solver* s) {
   s->stats.spmvKernelLaunches = s->stats.updateKernelLaunches = s->stats.gatherKernelLaunches = 0;
   s->stats.pcgCapHits = 0; s->stats.pcgWorstCapResidual = 0.0f; s->stats.msIslandKernels = 0.0f;
   s->stats.islandKernelLaunches = 0; s->stats.pcgIslandRowIterations = 0;
+  s->stats.msHalo = 0.0f; s->stats.haloBytesLastTick = 0; s->stats.haloExchangesLastTick = 0;
   PdTickCtx* c = new PdTickCtx(s);
   c->launches0 = s->launches;
   s->pdCtx = c;
@@ -629,6 +633,7 @@ int pdTickEnd(PiesB200Solver* s, bool refreshMirror) {
     s->stats.msUpdateKernel = acc[kPhUpdateKernel]; s->stats.updateKernelLaunches = cnt[kPhUpdateKernel];
     s->stats.msGatherKernel = acc[kPhGatherKernel]; s->stats.gatherKernelLaunches = cnt[kPhGatherKernel];
     s->stats.msIslandKernels = acc[kPhIslandKernel]; s->stats.islandKernelLaunches = cnt[kPhIslandKernel];
+    s->stats.msHalo = acc[kPhHalo];
   }
   uint64_t launches0 = c->launches0;
   const std::vector<uint32_t> solves = c->globalItersPerSolve;
@@ -700,16 +705,44 @@ int countOwnedContacts(PiesB200Solver* s, uint32_t* nTri, uint32_t* nFloor) {
   return PIES_B200_OK;
 }
 
+// One halo exchange inside a tick (slab-partitioned runs), timed as its own phase.
+static int tickHalo(PiesB200Solver* s, int planes) {
+  PdTickCtx* c = static_cast<PdTickCtx*>(s->pdCtx);
+  int span = c ? c->timer.begin(kPhHalo) : -1;
+  int rc = haloExchange(s, planes);
+  if (c) c->timer.end(span);
+  return rc;
+}
+
 int tickPD(PiesB200Solver* s, bool refreshMirror) {
+  const bool multi = s->halo && s->halo->world > 1;
+  if (multi) {
+    // every rank takes part in this reduction at every tick, failed or not, so that they all stop at the same tick:
+    // a rank that went on alone would wait for its neighbours' halos forever
+    bool any = false;
+    int rcf = haloAnyFailed(s, s->simFailed, &any);
+    if (rcf) return rcf;
+    if (any) { s->simFailed = true; s->stats.simFailed = 1u; return PIES_B200_OK; }  // Solver.cpp:26-28: silent no-op once failed
+    s->halo->bytesLastTick = 0; s->halo->exchangesLastTick = 0;
+  }
   int rc = pdTickBegin(s);
   if (rc) return rc;
+  // After a failure in the middle of a tick a slab rank keeps its place in the communication pattern (its neighbours are
+  // waiting in the matching exchanges) and only skips the compute; the next tick's reduction stops every rank.
+  int failed = PIES_B200_OK;
   for (uint32_t sub = 0; sub < s->opt.timeSubsteps; ++sub) {
-    if ((rc = pdSubstepBegin(s))) { pdAbort(s); return rc; }
-    for (uint32_t it = 0; it < s->opt.iterations; ++it)
-      if ((rc = pdIteration(s))) { pdAbort(s); return rc; }
-    if ((rc = pdSubstepEnd(s))) { pdAbort(s); return rc; }
+    if (multi && (rc = tickHalo(s, 3))) return rc;
+    if (!failed && (rc = pdSubstepBegin(s))) { pdAbort(s); failed = rc; if (!multi) return rc; }
+    for (uint32_t it = 0; it < s->opt.iterations; ++it) {
+      if (!failed && (rc = pdIteration(s))) { pdAbort(s); failed = rc; if (!multi) return rc; }
+      if (multi && (rc = tickHalo(s, 1))) return rc;
+    }
+    if (!failed && (rc = pdSubstepEnd(s))) { pdAbort(s); failed = rc; if (!multi) return rc; }
   }
-  return pdTickEnd(s, refreshMirror);
+  if (failed) { s->simFailed = true; return failed; }
+  rc = pdTickEnd(s, refreshMirror);
+  if (multi) { s->stats.haloBytesLastTick = s->halo->bytesLastTick; s->stats.haloExchangesLastTick = (uint32_t)s->halo->exchangesLastTick; }
+  return rc;
 }
 
 }  // namespace pies
@@ -721,6 +754,7 @@ PiesB200Solver::~PiesB200Solver() {
   pies::pdAbort(this);
   if (blocks) { if (blocks->host) cudaFreeHost(blocks->host); delete blocks; }
   delete islands;
+  delete halo;
   pies::unregisterVertexMirror(this);
   for (cudaEvent_t e : eventPool) cudaEventDestroy(e);
   for (cudaEvent_t e : tickEv) if (e) cudaEventDestroy(e);

@@ -47,6 +47,7 @@ struct DetectWork;   // detect.cu
 struct ContactWork;  // contact.cu
 struct BlockWork;    // reblock.cu
 struct IslandWork;   // islands.cu
+struct HaloWork;     // halo.cu
 struct PbdWork;      // pbd.cu
 void destroyPbdWork(PbdWork* w);
 
@@ -99,6 +100,7 @@ struct PiesB200Solver {
   pies::ContactWork* contact = nullptr;
   pies::BlockWork* blocks = nullptr;
   pies::IslandWork* islands = nullptr;
+  pies::HaloWork* halo = nullptr;   // set by pies_b200_halo_init: slab-partitioned multi-GPU run
   pies::PbdWork* pbd = nullptr;
   void* pdCtx = nullptr;          // PdTickCtx of a tick in progress (engine.cu)
   pies::DevBuf<uint32_t> triOrder; bool haveTriOrder = false;  // canonical-order override (slab-partitioned hosts)

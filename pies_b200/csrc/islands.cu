@@ -363,80 +363,89 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
       }
     };
 
-    // ---- PCG on the correction delta (x is updated once at the end: a single rounding of the sum), in the
-    //      Chronopoulos-Gear arrangement: z = Minv r and w = A z first, then ONE reduction per iteration for
-    //      gamma = r.z, delta = w.z and r.r, from which  beta = gamma / gamma_old,
-    //      alpha = gamma / (delta - beta gamma / alpha_old),  p = z + beta p,  s = w + beta s (= A p),  delta_x += alpha p,
-    //      r -= alpha s.  Three team barriers per iteration (z visible, the reduction, r visible) instead of six, and
-    //      p, s and the correction stay in registers: only r and z, which other rows gather, live in shared memory (z in sP).
-    float pr[RPT][3], sr[RPT][3];
+    // ---- CG on the correction delta (x is updated once at the end: a single rounding of the sum).  Plain two-reduction
+    //      CG: the single-reduction (Chronopoulos-Gear) arrangement was measured too (r02c): 4 % faster on the CTA tier,
+    //      slower on the warp tier (one extra preconditioner + mat-vec per solve), and its recurrences cost accuracy.
+    float zz[RPT][3];
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) { pr[k][0] = pr[k][1] = pr[k][2] = 0.0f; sr[k][0] = sr[k][1] = sr[k][2] = 0.0f; }
-    float bb[3] = {red9[6], red9[7], red9[8]};
-    teamReduce<TEAM, 3>(bb, sRed, phase, tid);
-    float gammaOld[3] = {0.0f, 0.0f, 0.0f}, alphaOld[3] = {0.0f, 0.0f, 0.0f};
-    float rr[3] = {0.0f, 0.0f, 0.0f};
+    for (int k = 0; k < RPT; ++k) {
+      const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+      if (l >= m) continue;
+      precond(k, zz[k]);
+      const float4 r = sR[l];
+      red9[0] += r.x * zz[k][0]; red9[1] += r.y * zz[k][1]; red9[2] += r.z * zz[k][2];
+      red9[3] += r.x * r.x; red9[4] += r.y * r.y; red9[5] += r.z * r.z;
+      sP[l] = make_float4(zz[k][0], zz[k][1], zz[k][2], 0.0f);
+    }
+    teamReduce<TEAM, 9>(red9, sRed, phase, tid);
+    float rz[3] = {red9[0], red9[1], red9[2]};
+    float rr[3] = {red9[3], red9[4], red9[5]};
+    const float bb[3] = {red9[6], red9[7], red9[8]};
+    auto converged = [&]() {
+      return rr[0] <= a.tol2 * bb[0] + 1e-36f && rr[1] <= a.tol2 * bb[1] + 1e-36f && rr[2] <= a.tol2 * bb[2] + 1e-36f;
+    };
+    teamSync<TEAM>();  // p visible
     uint32_t iters = 0;
-    bool conv = false;
-    while (true) {
-      float zz[RPT][3];
+    bool conv = converged();
+    while (!conv && iters < a.maxIter) {
+      float ap[RPT][3];
+      float pap[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
-        if (l >= m) continue;
-        precond(k, zz[k]);
-        sP[l] = make_float4(zz[k][0], zz[k][1], zz[k][2], 0.0f);
-      }
-      teamSync<TEAM>();  // z visible
-      float ww[RPT][3];
-      float red[9] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-      for (int k = 0; k < RPT; ++k) {
-        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
-        ww[k][0] = ww[k][1] = ww[k][2] = 0.0f;
+        ap[k][0] = ap[k][1] = ap[k][2] = 0.0f;
         if (l >= m) continue;
         const uint32_t e1 = rs[k] + rn[k];
 #pragma unroll 4
         for (uint32_t e = rs[k]; e < e1; ++e) {
           const float v = mv[e];
-          const float4 zv = sP[mc[e]];
-          ww[k][0] = fmaf(v, zv.x, ww[k][0]); ww[k][1] = fmaf(v, zv.y, ww[k][1]); ww[k][2] = fmaf(v, zv.z, ww[k][2]);
+          const float4 pv = sP[mc[e]];
+          ap[k][0] = fmaf(v, pv.x, ap[k][0]); ap[k][1] = fmaf(v, pv.y, ap[k][1]); ap[k][2] = fmaf(v, pv.z, ap[k][2]);
         }
-        ww[k][0] = fmaf(cdg[k], zz[k][0], ww[k][0]); ww[k][1] = fmaf(cdg[k], zz[k][1], ww[k][1]); ww[k][2] = fmaf(cdg[k], zz[k][2], ww[k][2]);
-        const float4 r = sR[l];
-        red[0] += r.x * zz[k][0]; red[1] += r.y * zz[k][1]; red[2] += r.z * zz[k][2];
-        red[3] += ww[k][0] * zz[k][0]; red[4] += ww[k][1] * zz[k][1]; red[5] += ww[k][2] * zz[k][2];
-        red[6] += r.x * r.x; red[7] += r.y * r.y; red[8] += r.z * r.z;
+        const float4 pl = sP[l];
+        ap[k][0] = fmaf(cdg[k], pl.x, ap[k][0]); ap[k][1] = fmaf(cdg[k], pl.y, ap[k][1]); ap[k][2] = fmaf(cdg[k], pl.z, ap[k][2]);
+        pap[0] += pl.x * ap[k][0]; pap[1] += pl.y * ap[k][1]; pap[2] += pl.z * ap[k][2];
       }
-      teamReduce<TEAM, 9>(red, sRed, phase, tid);
-      rr[0] = red[6]; rr[1] = red[7]; rr[2] = red[8];
-      conv = rr[0] <= a.tol2 * bb[0] + 1e-36f && rr[1] <= a.tol2 * bb[1] + 1e-36f && rr[2] <= a.tol2 * bb[2] + 1e-36f;
-      if (conv || iters >= a.maxIter) break;
-      float alpha[3], beta[3];
+      teamReduce<TEAM, 3>(pap, sRed, phase, tid);
+      float alpha[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float gamma = red[c], dlt = red[3 + c];
-        beta[c] = (iters && gammaOld[c] > 0.0f) ? gamma / gammaOld[c] : 0.0f;
-        const float den = (iters && alphaOld[c] > 0.0f) ? dlt - beta[c] * gamma / alphaOld[c] : dlt;
-        alpha[c] = den > 0.0f ? gamma / den : 0.0f;
-        gammaOld[c] = gamma; alphaOld[c] = alpha[c];
-      }
+      for (int c = 0; c < 3; ++c) alpha[c] = pap[c] > 0.0f ? rz[c] / pap[c] : 0.0f;
+      float rl[RPT][3];
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
         if (l >= m) continue;
-        float4 r = sR[l];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          pr[k][c] = fmaf(beta[c], pr[k][c], zz[k][c]);
-          sr[k][c] = fmaf(beta[c], sr[k][c], ww[k][c]);
-          dl[k][c] = fmaf(alpha[c], pr[k][c], dl[k][c]);
-        }
-        r.x = fmaf(-alpha[0], sr[k][0], r.x); r.y = fmaf(-alpha[1], sr[k][1], r.y); r.z = fmaf(-alpha[2], sr[k][2], r.z);
-        sR[l] = r;
+        const float4 pl = sP[l];
+        dl[k][0] = fmaf(alpha[0], pl.x, dl[k][0]); dl[k][1] = fmaf(alpha[1], pl.y, dl[k][1]); dl[k][2] = fmaf(alpha[2], pl.z, dl[k][2]);
+        const float4 r = sR[l];
+        rl[k][0] = fmaf(-alpha[0], ap[k][0], r.x); rl[k][1] = fmaf(-alpha[1], ap[k][1], r.y); rl[k][2] = fmaf(-alpha[2], ap[k][2], r.z);
+        sR[l] = make_float4(rl[k][0], rl[k][1], rl[k][2], 0.0f);
       }
-      ++iters;
       teamSync<TEAM>();  // r visible
+      float red6[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+        if (l >= m) continue;
+        precond(k, zz[k]);
+        red6[0] += rl[k][0] * zz[k][0]; red6[1] += rl[k][1] * zz[k][1]; red6[2] += rl[k][2] * zz[k][2];
+        red6[3] += rl[k][0] * rl[k][0]; red6[4] += rl[k][1] * rl[k][1]; red6[5] += rl[k][2] * rl[k][2];
+      }
+      teamReduce<TEAM, 6>(red6, sRed, phase, tid);
+      float beta[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { beta[c] = rz[c] > 0.0f ? red6[c] / rz[c] : 0.0f; rz[c] = red6[c]; rr[c] = red6[3 + c]; }
+      ++iters;
+      conv = converged();
+      if (conv) break;
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) {
+        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+        if (l >= m) continue;
+        const float4 pl = sP[l];
+        sP[l] = make_float4(fmaf(beta[0], pl.x, zz[k][0]), fmaf(beta[1], pl.y, zz[k][1]), fmaf(beta[2], pl.z, zz[k][2]), 0.0f);
+      }
+      teamSync<TEAM>();  // p visible
     }
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {

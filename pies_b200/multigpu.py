@@ -15,9 +15,14 @@ neighbours, and that error is removed by overwriting the ghost nodes with their 
   * at every substep start: position, previous position, velocity (24+12 B per node),
   * after every PD iteration: position (the north_star's "halo exchanged per iteration"),
 
-through `torch.distributed` point-to-point ops (NCCL over NVLink on GPUs; gloo in the CPU tests).
-No data-path collective exists besides this exchange.  If bodies drift so that a contact partner is
-missing from a rank's ghost set (`check_halo`), the scene is repartitioned from the gathered state.
+inside the library: `pies_b200_halo_*` (csrc/halo.cu) packs the rows, exchanges them with ncclSend / ncclRecv in one
+group and unpacks them, all on the solver's stream, from within `pies_b200_tick` — this module only computes the
+partition and the exchange lists and hands the NCCL unique id around (over the caller's `torch.distributed` group,
+which is rendezvous plumbing only).  Without NCCL (the gloo CPU tests, the single-GPU lockstep emulation) the same
+lists drive a `torch.distributed` point-to-point exchange between the phases of the tick.
+No data-path collective exists besides this exchange and a one-int failure reduction per tick.  Every `check_every`
+ticks the ranks compare the bodies' current extents with the ghost sets (`check_halo`); if a contact partner could be
+missing from a rank's ghost set the scene is repartitioned from the gathered state.
 
 Nothing here touches the oracle; the solver behind it is the CUDA library only.
 """
@@ -26,22 +31,32 @@ import numpy as np
 from .sharding import slab_partition
 
 # ------------------------------------------------------------------------------------------------
-# body specs: what a rank needs to know about a body without building it
-KINDS = {
-    # kind: (nodes, triangles, static projections per PD iteration)
-    "tetbox": (27, 48, 96),      # createTetBox non-hinged: 3x3x3 nodes, 48 tets -> 48 strain + 48 volume, 48 triangles
-}
-
-
+# body specs: what a rank needs to know about a body without building it — node / triangle / static projection counts
+# (per PD iteration) and the x extent — plus what it takes to build it through the reference's factories
 def tetbox(t, scale=1.0, v0=(0.0, 0.0, 0.0), w=1000.0, mass=1.0):
+    """createTetBox, non-hinged: 3x3x3 nodes, 48 tets -> 48 strain + 48 volume constraints, 48 triangles."""
     t = np.asarray(t, np.float32)
     return dict(kind="tetbox", t=t, scale=float(scale), v0=tuple(v0), w=float(w), mass=float(mass),
-                lo=t.astype(np.float64), hi=t.astype(np.float64) + 2.0 * scale)
+                nodes=27, tris=48, proj=96, lo=t.astype(np.float64), hi=t.astype(np.float64) + 2.0 * scale)
+
+
+def tetmesh(points, tets, faces, v0=(0.0, 0.0, 0.0), density=1.0, strain_w=1000.0, min_strain=0.8, max_strain=1.0,
+            volume_w=1000.0, compression=1.0, stretching=1.0):
+    """A tetrahedralised body as Solver::addTriMeshVolume leaves it after TetGen (config 1 / config 5 bodies):
+    points, tets (4 ids) and re-wound boundary faces (3 ids), local to the body."""
+    points = np.ascontiguousarray(points, np.float32)
+    per_tet = (1 if strain_w != 0 else 0) + (1 if volume_w != 0 else 0)
+    return dict(kind="tetmesh", points=points, tets=np.ascontiguousarray(tets, np.uint32), faces=np.ascontiguousarray(faces, np.uint32),
+                v0=tuple(v0), args=(density, strain_w, min_strain, max_strain, volume_w, compression, stretching),
+                nodes=len(points), tris=len(faces), proj=per_tet * len(tets),
+                lo=points.min(0).astype(np.float64), hi=points.max(0).astype(np.float64))
 
 
 def apply_spec(solver, spec):
     if spec["kind"] == "tetbox":
         solver.createTetBox(spec["t"], spec["scale"], spec["v0"], spec["w"], spec["mass"], False)
+    elif spec["kind"] == "tetmesh":
+        solver.addTetMeshVolume(spec["points"], spec["tets"], spec["faces"], spec["v0"], *spec["args"])
     else:
         raise ValueError("unknown body kind %r" % spec["kind"])
 
@@ -49,12 +64,12 @@ def apply_spec(solver, spec):
 class SlabPlan:
     """Deterministic partition + halo plan, identical on every rank (pure numpy)."""
 
-    def __init__(self, kinds, lo_x, hi_x, world, halo, thread_count=8, snap=0.0):
-        nb = len(kinds)
+    def __init__(self, counts, lo_x, hi_x, world, halo, thread_count=8, snap=0.0):
+        """counts: per body (nodes, triangles, static projections per PD iteration)."""
+        counts = np.asarray(counts, np.int64).reshape(-1, 3)
+        nb = len(counts)
         self.world, self.halo, self.thread_count = world, float(halo), int(thread_count)
-        self.nodes = np.array([KINDS[k][0] for k in kinds], np.int64)
-        self.tris = np.array([KINDS[k][1] for k in kinds], np.int64)
-        self.proj = np.array([KINDS[k][2] for k in kinds], np.int64)
+        self.nodes, self.tris, self.proj = counts[:, 0].copy(), counts[:, 1].copy(), counts[:, 2].copy()
         self.node_off = np.concatenate([[0], np.cumsum(self.nodes)])
         self.tri_off = np.concatenate([[0], np.cumsum(self.tris)])
         lo_x = np.asarray(lo_x, np.float64); hi_x = np.asarray(hi_x, np.float64)
@@ -189,12 +204,19 @@ class _DevPlane:
 class SlabSolver:
     """PD solver of a multi-body scene sharded across the ranks of a torch.distributed group."""
 
-    def __init__(self, specs, rank=0, world=1, halo=1.0, device=0, dist=None, group=None, snap=0.0, **options):
+    def __init__(self, specs, rank=0, world=1, halo=1.0, device=0, dist=None, group=None, snap=0.0, check_every=0,
+                 native_halo=None, **options):
+        """check_every = k > 0: every k ticks all ranks check the ghost layer and repartition if needed (collective).
+        native_halo: exchange ghost rows inside the library over NCCL (default: whenever the group's backend is nccl)."""
         import torch
         from .solver import Solver
         self.torch, self.dist, self.group = torch, dist, group
         self.rank, self.world, self.halo, self.device, self.options = rank, world, float(halo), device, dict(options)
         self.snap = float(snap)
+        self.check_every, self.ticks = int(check_every), 0
+        if native_halo is None:
+            native_halo = bool(dist is not None and world > 1 and dist.get_backend(group) == "nccl")
+        self.native_halo = bool(native_halo)
         self.specs = list(specs)
         self._Solver = Solver
         self.repartitions = 0
@@ -205,9 +227,14 @@ class SlabSolver:
     def _build(self, lo_x, hi_x, state):
         torch = self.torch
         opts = dict(self.options)
-        self.plan = SlabPlan([s["kind"] for s in self.specs], lo_x, hi_x, self.world, self.halo,
+        self.plan = SlabPlan([(s["nodes"], s["tris"], s["proj"]) for s in self.specs], lo_x, hi_x, self.world, self.halo,
                              thread_count=opts.get("threadCount", 8), snap=self.snap)
         r = self.rank
+        old = getattr(self, "solver", None)
+        if old is not None:      # repartition: the old communicator goes first (collective, like its creation)
+            if self.native_halo:
+                old.haloDestroy()
+            old.close()
         self.solver = s = self._Solver(device=self.device, **opts)
         for b in self.plan.local[r]:
             apply_spec(s, self.specs[int(b)])
@@ -229,6 +256,13 @@ class SlabSolver:
         else:
             self.q = self.prev = self.vel = torch.zeros((0, 4), device=dev)
         self.halo_x = HaloExchange(self.plan, r, dev, self.dist if self.world > 1 else None, self.group)
+        if self.native_halo and self.world > 1:
+            # rank 0 draws the NCCL unique id; the caller's process group only carries these 128 bytes
+            uid = [self._Solver.haloUniqueId() if r == 0 else None]
+            self.dist.broadcast_object_list(uid, src=0, group=self.group)
+            s.haloInit(r, self.world, uid[0])
+            send, recv = self.plan.exchange_lists(r)
+            s.haloSetLists(send, recv)
         loc = self.plan.local[r]
         own_b = self.plan.owner[loc] == r
         self.owned_static = int(self.plan.proj[loc][own_b].sum())
@@ -243,6 +277,14 @@ class SlabSolver:
 
     def tick(self):
         s, o = self.solver, self.solver.getOptions()
+        if self.check_every and self.ticks and self.ticks % self.check_every == 0:
+            self.check_halo(repartition=True)   # collective: the same tick on every rank
+            s = self.solver
+        self.ticks += 1
+        if self.native_halo and self.world > 1:
+            s.tick()                             # the library exchanges the halos itself (csrc/halo.cu)
+            self.halo_bytes += s.stats().haloBytesLastTick
+            return
         s.pdTickBegin()
         for _ in range(o.timeSubsteps):
             self.halo_bytes += self.halo_x([self.q, self.prev, self.vel])

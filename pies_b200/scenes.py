@@ -228,3 +228,28 @@ def build_s5(ref, ours=None, bodies=512, per_side=8, n=24, side=8.0, pitch=10.0,
     for o in origins:
         add_tetgen_cube(ref, ours, side=side, n=n, origin=tuple(float(x) for x in o))
     return origins
+
+
+def cube24_mesh():
+    """The config-5 body as the reference's TetGen run leaves it (side-8 cube, 24 x 24 quads per face: 4 518 nodes,
+    16 546 tets, 6 912 boundary triangles), committed under pies_b200/data/ so that large S5 scenes can be built without
+    TetGen (generated by tests/golden/make_golden.py::s5_pair: first body, origin moved to 0)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "cube24.npz"))
+    return g["points"], g["tets"], g["faces"]
+
+
+def s5_origins(bodies=512, per_side=8, pitch=10.0, y0=3.07):
+    i = np.arange(bodies)
+    o = np.stack([pitch * (i % per_side), y0 + pitch * (i // (per_side * per_side)), pitch * ((i // per_side) % per_side)],
+                 axis=1).astype(np.float32)
+    return (o + lcg_jitter(bodies, seed=5151)).astype(np.float32)
+
+
+def build_s5_replicated(s, bodies=512, per_side=8, pitch=10.0, y0=3.07):
+    """S5 from ONE committed TetGen mesh replicated on the lattice of SURVEY section 8(d) (the reference re-runs TetGen per
+    body; its meshes differ by a handful of tets from body to body, which no throughput figure depends on)."""
+    pts, tets, faces = cube24_mesh()
+    for o in s5_origins(bodies, per_side, pitch, y0):
+        s.addTetMeshVolume(pts + o, tets, faces, (0, 0, 0), 1.0, 1000.0, 0.8, 1.0, 1000.0, 1.0, 1.0)
+    return bodies

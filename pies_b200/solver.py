@@ -54,6 +54,8 @@ class Stats(C.Structure):
         ("pcgCapHits", C.c_uint32), ("pcgWorstCapResidual", C.c_float),
         ("msIslandKernels", C.c_float), ("islandKernelLaunches", C.c_uint32),
         ("pcgIslandRowIterations", C.c_uint64),
+        ("haloBytesLastTick", C.c_uint64), ("haloExchangesLastTick", C.c_uint32), ("msHalo", C.c_float),
+        ("systemNonZeros", C.c_uint64), ("staticBodies", C.c_uint32), ("reserved2", C.c_uint32),
     ]
 
 
@@ -128,6 +130,11 @@ _SIGNATURES = {
     "pies_b200_set_triangle_order": (C.c_int, [_vp, C.c_uint32, _u32p]),
     "pies_b200_set_owned_nodes": (C.c_int, [_vp, C.c_uint32, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")]),
     "pies_b200_count_owned_contacts": (C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "pies_b200_halo_unique_id": (C.c_int, [_vp]),
+    "pies_b200_halo_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "pies_b200_halo_set_lists": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "pies_b200_halo_exchange": (C.c_int, [_vp, C.c_int]),
+    "pies_b200_halo_destroy": (C.c_int, [_vp]),
     "pies_b200_node_occupancy_counts": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pies_b200_get_node_occupancy": (C.c_int, [_vp, _i64p, _u32p, _u32p]),
     "pies_b200_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
@@ -455,6 +462,38 @@ class Solver:
     def setOwnedNodes(self, mask):
         mask = np.ascontiguousarray(mask, np.uint8)
         self._ck(lib().pies_b200_set_owned_nodes(self.h, len(mask), mask))
+
+    # -- multi-GPU halo inside the library (include/pies_b200.h: pies_b200_halo_*) --
+    @staticmethod
+    def haloUniqueId():
+        """128 bytes from ncclGetUniqueId (call on one rank, broadcast to all)."""
+        buf = C.create_string_buffer(128)
+        rc = lib().pies_b200_halo_unique_id(C.cast(buf, _vp))
+        if rc != 0:
+            raise PiesError("pies_b200_halo_unique_id failed (%d): %s" % (rc, lib().pies_b200_last_error(None).decode()))
+        return buf.raw
+
+    def haloInit(self, rank, world, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(lib().pies_b200_halo_init(self.h, rank, world, C.cast(buf, _vp)))
+
+    def haloSetLists(self, send, recv):
+        """send / recv: dicts peer -> local row indices (pies_b200.multigpu.SlabPlan.exchange_lists)."""
+        peers = sorted(set(send) | set(recv))
+        e = np.zeros(0, np.uint32)
+        sc = np.array([len(send.get(p, e)) for p in peers], np.uint32)
+        rcnt = np.array([len(recv.get(p, e)) for p in peers], np.uint32)
+        si = np.ascontiguousarray(np.concatenate([np.asarray(send.get(p, e), np.uint32) for p in peers]) if peers else e)
+        ri = np.ascontiguousarray(np.concatenate([np.asarray(recv.get(p, e), np.uint32) for p in peers]) if peers else e)
+        pa = np.ascontiguousarray(peers, np.int32)
+        ptr = lambda a: a.ctypes.data_as(_vp) if len(a) else None
+        self._ck(lib().pies_b200_halo_set_lists(self.h, len(peers), ptr(pa), ptr(sc), ptr(si), ptr(rcnt), ptr(ri)))
+
+    def haloExchange(self, planes):
+        self._ck(lib().pies_b200_halo_exchange(self.h, planes))
+
+    def haloDestroy(self):
+        self._ck(lib().pies_b200_halo_destroy(self.h))
 
     def countOwnedContacts(self):
         a, b = C.c_uint32(), C.c_uint32()

@@ -46,3 +46,12 @@ def noise_floor(scene, tick):
     import json
     with open(os.path.join(GOLDEN, "sensitivity.json")) as f:
         return float(json.load(f)[scene]["every_tick"][str(tick)])
+
+
+def translation_floor(scene, tick):
+    """Largest position difference between the UNMODIFIED reference and ITSELF on the same bodies translated by about one
+    body size in x / z (tests/golden/sensitivity.py::translation_floor).  On TetGen meshes with sliver tets the reference's
+    fp32 Cholesky is far from translation invariant, which bounds how closely any implementation can agree with it."""
+    import json
+    with open(os.path.join(GOLDEN, "sensitivity.json")) as f:
+        return float(json.load(f)[scene + "_translation"]["max_abs_diff"][str(tick)])

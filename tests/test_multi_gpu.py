@@ -128,7 +128,32 @@ def _free_port():
     return p
 
 
-def _nccl_worker(rank, world, port, out):
+def test_lockstep_with_tetgen_bodies(pb):
+    """The slab plan handles any body kind: two TetGen cubes (the committed config-1 test mesh) side by side within
+    contact reach plus tet boxes, two emulated ranks against the single solver."""
+    from conftest import golden
+    g = golden("tetgen_cube")
+    specs = []
+    for k, dx in enumerate((0.0, 8.06, 16.12)):    # side-8 cubes 0.06 apart: neighbours are in contact from the start
+        pts = g["points"] + np.array([dx, 0.0, 0.0], np.float32)
+        specs.append(multigpu.tetmesh(pts, g["tets"], g["faces"]))
+    specs += row_specs(columns=2, layers=1, pitch=2.05, seed=5)
+    for sp in specs[3:]:
+        sp["t"] = sp["t"] + np.array([26.0, 0.0, 0.0], np.float32); sp["lo"] = sp["lo"] + [26.0, 0, 0]; sp["hi"] = sp["hi"] + [26.0, 0, 0]
+    ticks = (1, 5, 10)
+    ref = _single(pb, specs, ticks)
+    ranks = [multigpu.SlabSolver(specs, rank=r, world=2, halo=9.0, device=0, **OPTS) for r in range(2)]
+    assert sum(int((~r.owned).sum()) for r in ranks) > 0
+    diag = bbox_diag(ref[1][0])
+    for t in range(1, max(ticks) + 1):
+        multigpu.tick_lockstep(ranks)
+        if t in ticks:
+            pos, _, _ = multigpu.gather_lockstep(ranks)
+            assert float(np.abs(pos - ref[t][0]).max()) <= 1e-4 * diag, t
+    assert ref[10][2] > 0
+
+
+def _nccl_worker(rank, world, port, out, native=True):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -137,17 +162,25 @@ def _nccl_worker(rank, world, port, out):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     specs = row_specs(columns=6)
-    s = mg.SlabSolver(specs, rank=rank, world=world, halo=3.2, device=rank, dist=dist, snap=0.5, **OPTS)
+    s = mg.SlabSolver(specs, rank=rank, world=world, halo=3.2, device=rank, dist=dist, snap=0.5, check_every=4,
+                      native_halo=native, **OPTS)
+    assert s.native_halo == native
     for _ in range(10):
         s.tick()
     ok = s.check_halo(repartition=False)
     pos, prev, vel = s.gather_state()
     if rank == 0:
         out["pos"] = pos; out["halo_bytes"] = s.halo_bytes; out["halo_ok"] = ok
+        out["exchanges"] = s.solver.stats().haloExchangesLastTick
+    if native:
+        s.solver.haloDestroy()
     dist.destroy_process_group()
 
 
-def test_nccl_two_ranks_match_single_solver(pb):
+@pytest.mark.parametrize("native", [True, False])
+def test_nccl_two_ranks_match_single_solver(pb, native):
+    """native: the halo exchange inside libpies_b200.so (ncclSend / ncclRecv from pies_b200_tick, csrc/halo.cu);
+    otherwise the same lists through torch.distributed point-to-point ops between the phases of the tick."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -156,10 +189,12 @@ def test_nccl_two_ranks_match_single_solver(pb):
     ref = _single(pb, specs, (10,))
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_nccl_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_nccl_worker, args=(2, _free_port(), out, native), nprocs=2, join=True)
     diag = bbox_diag(ref[10][0])
     assert float(np.abs(out["pos"] - ref[10][0]).max()) <= 1e-4 * diag
     assert out["halo_bytes"] > 0
+    if native:
+        assert out["exchanges"] == 11      # one 3-plane exchange per substep + one per PD iteration
 
 
 def test_counting_owned_contacts_does_not_disturb_the_solve(pb):

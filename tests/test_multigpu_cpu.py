@@ -24,7 +24,7 @@ def _specs(n=96, nx=8, nz=4, pitch=3.0):
 
 def _plan(world, halo, **kw):
     sp = _specs(**kw)
-    return multigpu.SlabPlan([s["kind"] for s in sp], [s["lo"][0] for s in sp], [s["hi"][0] for s in sp], world, halo, snap=1.0)
+    return multigpu.SlabPlan([(s["nodes"], s["tris"], s["proj"]) for s in sp], [s["lo"][0] for s in sp], [s["hi"][0] for s in sp], world, halo, snap=1.0)
 
 
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
@@ -87,7 +87,7 @@ def test_triangle_order_is_the_global_canonical_order_restricted():
 def test_missing_ghosts_alarm():
     sp = _specs()
     lo = np.array([s["lo"][0] for s in sp]); hi = np.array([s["hi"][0] for s in sp])
-    p = multigpu.SlabPlan([s["kind"] for s in sp], lo, hi, 2, halo=0.5, snap=1.0)
+    p = multigpu.SlabPlan([(s["nodes"], s["tris"], s["proj"]) for s in sp], lo, hi, 2, halo=0.5, snap=1.0)
     assert p.missing_ghosts(lo, hi) == []
     # a body of slab 1 drifts against slab 0's extent
     b = int(np.flatnonzero(p.owner == 1)[0])
