@@ -47,18 +47,34 @@ __global__ void __launch_bounds__(kThreads) k_scan_tile(uint32_t* __restrict__ d
   for (int k = 0; k < kScanItems; ++k) { if (base + k < n) data[base + k] = run; run += v[k]; }
 }
 
+// Second (and last) kernel of a multi-tile scan: every CTA sums the totals of the tiles before its own (a few thousand
+// L2-resident words at most) and adds that offset to its tile.  No third launch for a scan of the tile totals.
 __global__ void __launch_bounds__(kThreads) k_scan_add(uint32_t* __restrict__ data, uint64_t n,
                                                        const uint32_t* __restrict__ tileSums) {
+  __shared__ uint32_t warpTotals[kThreads / 32];
+  __shared__ uint32_t sAdd;
+  uint32_t acc = 0;
+  for (uint32_t i = threadIdx.x; i < blockIdx.x; i += kThreads) acc += tileSums[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) warpTotals[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) t += warpTotals[w];
+    sAdd = t;
+  }
+  __syncthreads();
+  const uint32_t add = sAdd;
+  if (!add) return;
   uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-  uint32_t add = tileSums[blockIdx.x];
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) if (base + k < n) data[base + k] += add;
 }
 
 size_t scanScratchElems(uint64_t n) {
-  size_t total = 0;
-  while (n > (uint64_t)kScanTile) { n = (n + kScanTile - 1) / kScanTile; total += n + 1; }
-  return total + 2;
+  return (size_t)((n + kScanTile - 1) / kScanTile) + 2;
 }
 
 // In-place exclusive scan of data[0..n); scratch holds scanScratchElems(n) uint32.
@@ -70,9 +86,8 @@ int launchExclusiveScan(cudaStream_t s, uint32_t* data, uint64_t n, uint32_t* sc
     return 1;
   }
   k_scan_tile<<<(unsigned)tiles, kThreads, 0, s>>>(data, n, scratch);
-  int launches = 1 + launchExclusiveScan(s, scratch, tiles, scratch + tiles + 1);
   k_scan_add<<<(unsigned)tiles, kThreads, 0, s>>>(data, n, scratch);
-  return launches + 1;
+  return 2;
 }
 
 // ------------------------------------------------------------------ sort -----

@@ -4,8 +4,8 @@ Bodies are independent except through contacts, so a multi-body scene is cut int
 slabs along x with equal constraint counts; each rank owns the bodies of its slab.  Bodies whose
 swept extent reaches within `halo` of a cut are reported as boundary bodies: their surface nodes
 are what a rank has to publish to its slab neighbour before collision detection.
-Round 1 uses this only to assign whole-scene replicas / body subsets in bench.py and in the
-gloo tests; the NCCL halo exchange inside the tick is the next step.
+pies_b200/multigpu.py builds the per-rank solvers and exchange lists from this partition; the halo exchange itself runs
+inside libpies_b200.so (csrc/halo.cu).
 """
 import numpy as np
 
