@@ -118,6 +118,105 @@ def run_reference(args, steps, warmup, quiet=False, threads=8):
                 SAMPLE["bodies"], FULL_BODIES, SAMPLE["nx"], SAMPLE["nz"], skip + 1, skip + 1 + steps, threads)}
 
 
+def run_other(args, local_rank):
+    """configs[1] (S2: 100 000-node distance chain, PBD, node-node collisions through the node hash) and configs[3]
+    (S4: 15 625 shape-matching bodies of 4 x 8 x 8 particles = 4 M particles, hull triangles, 244 goal regions driven by a
+    scripted transform, CCD + friction) on one GPU: the same JSON line, the byte model of SURVEY section 8(d) applied to
+    the whole tick (72 B per distance projection, 44 B per shape / goal member, 136 B per point-triangle and 48 B per
+    floor contact, 52 + 76 B per node and substep for the advection / velocity passes)."""
+    import torch
+    import pies_b200 as pb
+    from pies_b200 import scenes
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    t0 = time.time()
+    if args.workload == "s2":
+        n_nodes = 100000 if args.bodies == FULL_BODIES else args.bodies
+        s = pb.Solver(device=local_rank, **scenes.S2_OPTIONS)
+        scenes.build_rope(s, n=n_nodes, shape="spiral")
+        per_tick = None
+        workload = "S2: %d-node distance-constraint chain (flat coil, arms overlapping: node-node collisions from the first tick), PBD, 4 iterations" % n_nodes
+        iterations, script = 4, None
+    else:
+        bodies = 15625 if args.bodies == FULL_BODIES else args.bodies
+        per_side = max(1, int(round(bodies ** (1.0 / 3.0))))
+        s = pb.Solver(device=local_rank, iterations=4)
+        _, regions = scenes.build_s4(s, bodies=bodies, per_side=per_side, goal_bodies=min(244, bodies))
+        workload = "S4: %d x createShapeMatchingBox(4, 8, 8) = %d particles, one 256-particle cluster per body, hull triangles, %d goal regions, PD, 4 iterations" % (
+            bodies, 256 * bodies, min(244, bodies))
+        iterations = 4
+        script = (lambda t: s.updateFixedRegions(scenes.s4_region_script(regions, t))) if len(regions) else None
+    s.setStream(stream.cuda_stream)
+    s.setTuning(profilePhases=True)
+    build_s = time.time() - t0
+    n = len(s.getVertices())
+    tick_no = [0]
+
+    def tick():
+        tick_no[0] += 1
+        if script is not None:
+            script(tick_no[0])
+        s.tick()
+    for _ in range(args.preroll + max(args.warmup, 3)):
+        tick()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    proj = launches = 0
+    contacts = 0
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        tick()
+        st = s.stats()
+        proj += st.projectionsLastTick; launches += st.kernelLaunchesLastTick
+        contacts += st.collisionProjections
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    # end to end: the reference-facing readback (getVertices) after every tick
+    t0 = time.time()
+    e2e_proj = 0
+    for _ in range(args.steps):
+        tick()
+        s.getVertices(copy=False)
+        e2e_proj += s.stats().projectionsLastTick
+    torch.cuda.synchronize()
+    e2e_s = time.time() - t0
+    st = s.stats()
+    peak, peak_kind = load_peaks()
+    if args.workload == "s2":
+        per_proj = 72.0
+        static_bytes = iterations * per_proj * (n - 1) + (52 + 76) * n
+        contact_bytes = 72.0 * (contacts / args.steps)     # a node-node visit moves two nodes like a distance projection
+    else:
+        members = int(st.staticProjections)
+        static_bytes = iterations * (44.0 * members + 40.0 * n) + (52 + 76) * n
+        contact_bytes = iterations * (136.0 * st.triCollisions + 48.0 * st.staticCollisions)
+    alg = static_bytes + contact_bytes
+    ms = dev_ms / args.steps
+    line = {"metric": "constraint projections/s", "value": proj / (dev_ms * 1e-3), "unit": "projections/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.workload == "s2" else "f32 (shape matching in f64 like the reference)",
+            "data": "synthetic", "config": {"workload": workload, "nodes": n, "iterations": iterations, "substeps": 1,
+                                            "parallelism": "1 GPU", "preroll_ticks": args.preroll, "scene_build_s": build_s},
+            "substeps_per_s": args.steps / (dev_ms * 1e-3),
+            "e2e": {"value": e2e_proj / e2e_s, "unit": "projections/s", "h2d_bytes_per_step": int(64 * len(regions)) if args.workload == "s4" else 0,
+                    "d2h_bytes_per_step": int(36 * n), "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole tick (all kernels of the " + ("PBD" if args.workload == "s2" else "PD") + " loop)",
+                         "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(alg), "avg_launch_ms": ms,
+                         "launches_timed": args.steps, "share_of_step": 1.0, "traffic": None},
+            "phase_ms_per_step": {"local": st.msLocal, "global": st.msGlobal, "detect": st.msDetect, "contact": st.msContact, "other": st.msOther},
+            "contacts_last_tick": {"point_triangle": int(st.triCollisions), "floor": int(st.staticCollisions),
+                                   "collision_projections": int(st.collisionProjections)},
+            "cpu_baseline": None}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -128,9 +227,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", type=float, default=4.0, help="ghost layer width along x (4.0 = two S3 columns)")
     ap.add_argument("--preroll", type=int, default=None, help="untimed ticks before warm-up (default: 60 for s3, 70 for s5 = the contact regime)")
-    ap.add_argument("--workload", default="s3", choices=["s3", "s5"],
-                    help="s3 (default, the metric's configuration; weak scaling for --gpus > 1) or s5: BASELINE configs[4], "
-                         "512 TetGen bodies of 16.5 k tets, STRONG scaling: the same scene cut into --gpus x-slabs")
+    ap.add_argument("--workload", default="s3", choices=["s3", "s5", "s2", "s4"],
+                    help="s3 (default, the metric's configuration; weak scaling for --gpus > 1); s5: BASELINE configs[4], "
+                         "512 TetGen bodies of 16.5 k tets, STRONG scaling: the same scene cut into --gpus x-slabs; "
+                         "s2: configs[1], the 100 k-node PBD rope; s4: configs[3], 4 M shape-matching particles (1 GPU each)")
     ap.add_argument("--big-tier", action="store_true", help="island tier 3 on (one 1024-thread CTA per island of up to 7 168 nodes)")
     args = ap.parse_args()
     if args.preroll is None:
@@ -146,6 +246,14 @@ def main():
               "iterations": 10, "substeps": 1, "parallelism": "replicas x%d" % world if world > 1 else "1 GPU",
               "l2": "working set > L2 (elements 80 MB + contributions 64 MB + CSR/preconditioner 120 MB per PD iteration)"}
 
+    if args.workload in ("s2", "s4"):
+        if args.impl == "reference" or world > 1:
+            if rank == 0:
+                print(json.dumps({"impl": args.impl, "unavailable": "workloads s2 / s4 run our arm on one GPU only"}))
+            return 0
+        if args.preroll is None or args.preroll in (60, 70):
+            args.preroll = 20
+        return run_other(args, local_rank)
     if args.workload == "s5":
         config = {"workload": "S5: %d x TetGen cube body (16 546 tets, 4 518 nodes, 6 912 boundary triangles each; one committed mesh "
                               "replicated), PD, tet strain+volume, 10 iterations/substep, dropped onto the floor and each other" % args.bodies,

@@ -525,6 +525,7 @@ int pdIteration(PiesB200Solver* s) {
       timer.end(spIsl);
     }
     gridWide = iw.nLeftIslands != 0;
+    if (gridWide) applyRestriction(iw, v.pw);  // only the rows of the left-over islands
   }
   if (gridWide) {
     int spSpmv = -1, spUpdate = -1;  // one sampled CG iteration (the second of the solve) per PD iteration

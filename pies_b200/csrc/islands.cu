@@ -139,6 +139,34 @@ __global__ void __launch_bounds__(kThreads) k_isl_classify(const uint32_t* count
   if (tier == kIslandTiers) atomicAdd(counts + 2 + kIslandTiers, m);
 }
 
+// Marks the nodes of the islands left to the grid-wide CG, the 256-row windows that hold one and their preconditioner
+// blocks (one CTA per left-over island; they are few and large).
+__global__ void __launch_bounds__(kThreads) k_isl_mark_big(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ list,
+                                                           const uint32_t* __restrict__ islStart, const uint32_t* __restrict__ order,
+                                                           const uint32_t* __restrict__ slotOf, uint8_t* __restrict__ big,
+                                                           uint32_t* __restrict__ winFlag, uint32_t* __restrict__ blkFlag) {
+  const uint32_t nLeft = counts[1 + kIslandTiers];
+  for (uint32_t k = blockIdx.x; k < nLeft; k += gridDim.x) {
+    const uint32_t isl = list[k];
+    const uint32_t s0 = islStart[isl], m = islStart[isl + 1] - s0;
+    for (uint32_t l = threadIdx.x; l < m; l += blockDim.x) {
+      const uint32_t g = order[s0 + l];
+      big[g] = 1;
+      winFlag[g >> 8] = 1u;            // benign race: every writer stores 1
+      blkFlag[slotOf[g] >> 5] = 1u;
+    }
+  }
+}
+
+// ascending list of the set flags from their exclusive scan; the count goes to out count
+__global__ void __launch_bounds__(kThreads) k_isl_compact(uint32_t n, const uint32_t* __restrict__ scan, uint32_t* __restrict__ list,
+                                                          uint32_t* __restrict__ count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { *count = scan[n]; return; }
+  if (scan[i + 1] != scan[i]) list[scan[i]] = i;
+}
+
 // ------------------------------------------------------------------------------------------------ solver ----
 struct IslandLayout { uint32_t r, p, val, inv, blkOff, blkSrc, col, members, leader, blkM, red, ctr, total; };
 
@@ -727,6 +755,26 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   for (int t = 0; t < kIslandTiers; ++t) w.tierCount[t] = w.host[1 + t];
   w.nLeftIslands = w.host[1 + kIslandTiers];
   w.nLeftNodes = w.host[2 + kIslandTiers];
+  // Both kinds present: the grid-wide CG only has to run over the rows of the left-over islands.
+  w.restricted = false;
+  const bool anyLocal = w.tierCount[0] || w.tierCount[1] || w.tierCount[2] || w.tierCount[3];
+  if (w.nLeftIslands && anyLocal) {
+    const uint32_t nWin = (n + 255u) / 256u;
+    ICHECK(w.big.reserve(n + 1)); ICHECK(w.winFlag.reserve(nWin + 2)); ICHECK(w.blkFlag.reserve(nBlocksBound + 2));
+    ICHECK(w.actWin.reserve(nWin + 1)); ICHECK(w.actBlk.reserve(nBlocksBound + 1)); ICHECK(w.actCounts.reserve(4));
+    w.scanCap = std::max<uint64_t>(w.scanCap, std::max<uint64_t>(nWin, nBlocksBound) + 2);
+    ICHECK(w.scanScratch.reserve(scanScratchElems(w.scanCap)));
+    ICHECK(cudaMemsetAsync(w.big.p, 0, n + 1, s));
+    ICHECK(cudaMemsetAsync(w.winFlag.p, 0, (nWin + 2) * sizeof(uint32_t), s));
+    ICHECK(cudaMemsetAsync(w.blkFlag.p, 0, ((size_t)nBlocksBound + 2) * sizeof(uint32_t), s));
+    k_isl_mark_big<<<(int)std::min<uint32_t>(w.nLeftIslands, 4 * kNumSMs), kThreads, 0, s>>>(
+        w.counts.p, w.tierList.p + (size_t)kIslandTiers * nB, w.islStart.p, w.order.p, slotOf, w.big.p, w.winFlag.p, w.blkFlag.p); ++L;
+    L += launchExclusiveScan(s, w.winFlag.p, nWin + 1, w.scanScratch.p);
+    k_isl_compact<<<gridFor(nWin + 1, kThreads), kThreads, 0, s>>>(nWin, w.winFlag.p, w.actWin.p, w.actCounts.p); ++L;
+    L += launchExclusiveScan(s, w.blkFlag.p, (uint64_t)nBlocksBound + 1, w.scanScratch.p);
+    k_isl_compact<<<gridFor((uint64_t)nBlocksBound + 1, kThreads), kThreads, 0, s>>>(nBlocksBound, w.blkFlag.p, w.actBlk.p, w.actCounts.p + 1); ++L;
+    w.restricted = true;
+  }
   if (w.tierCount[3]) {  // tier 3 keeps an island-local copy of the matrix in global memory
     const size_t nnz = S.nnz + 6ull * c.nUnique + 16;
     ICHECK(w.matCol.reserve(nnz)); ICHECK(w.matVal.reserve(nnz));
@@ -773,8 +821,15 @@ int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const C
   return L;
 }
 
+void applyRestriction(const IslandWork& w, PcgWork& pw) {
+  if (!w.restricted) return;
+  pw.big = w.big.p; pw.actWin = w.actWin.p; pw.actBlk = w.actBlk.p; pw.actCounts = w.actCounts.p;
+}
+
 void preloadIslandKernels() {
   cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, k_isl_mark_big);
+  cudaFuncGetAttributes(&a, k_isl_compact);
   cudaFuncGetAttributes(&a, k_isl_init);
   cudaFuncGetAttributes(&a, k_isl_unite);
   cudaFuncGetAttributes(&a, k_isl_keys);

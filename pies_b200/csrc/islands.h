@@ -29,6 +29,10 @@ struct IslandWork {
   DevBuf<uint32_t> slotIsl;       // tier 3: preconditioner slot of every row, island order
   DevBuf<int> matCol;             // tier 3: island-local copy of the matrix (column = local row index), at nnzOff
   DevBuf<float> matVal;
+  // restriction of the grid-wide CG to the islands left over (PcgWork::big / actWin / actBlk): built when both kinds exist
+  DevBuf<uint8_t> big;
+  DevBuf<uint32_t> winFlag, blkFlag, actWin, actBlk, actCounts;
+  bool restricted = false;
   DevBuf<uint32_t> solveStats;    // 4 words per solve of a tick: max iterations, sum of iterations x rows, islands at the cap, worst residual
   uint32_t* host = nullptr;       // pinned copy of counts (8 words) + solveStats
   uint32_t hostCap = 0;
@@ -61,6 +65,9 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
 // Solves A x = b on every island of tiers 0..3 (x holds the start value).  statSlot: which 4-word record of solveStats.
 int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const ContactLists& c, const PcgWork& pw,
                       const uint32_t* slotOf, const float4* b, float4* x, float tol, uint32_t maxIter, uint32_t statSlot);
+
+// Points pw at the active-row tables when this substep's grid-wide solve is restricted to the left-over islands.
+void applyRestriction(const IslandWork& w, PcgWork& pw);
 
 void preloadIslandKernels();
 

@@ -93,6 +93,13 @@ struct PcgWork {
   const uint2* blockMeta = nullptr;        // per block: (offset into blockInv in floats, m)
   uint32_t nBlocks = 0;                    // upper bound used for grid sizing
   const uint32_t* nBlocksDev = nullptr;    // actual block count of this substep (device)
+  // Restriction of the grid-wide solve to the islands the island-local kernels left over (islands.cu); all null = every
+  // row.  big[i] != 0: node i takes part; actWin: ascending list of the 256-row windows holding such a node, actBlk: of
+  // the preconditioner blocks made of such nodes; counts[0] = #windows, counts[1] = #blocks (device).
+  const uint8_t* big = nullptr;
+  const uint32_t* actWin = nullptr;
+  const uint32_t* actBlk = nullptr;
+  const uint32_t* actCounts = nullptr;
 };
 // Solves A (x + delta) = b for the correction delta, starting from delta = 0 with the start
 // residual b - A x accumulated in fp64.

@@ -109,13 +109,17 @@ __device__ __forceinline__ void applyRowD(uint32_t i, const CsrMatrix& A, const 
 }
 
 // r = b - A x (fp64 accumulation) ; delta = 0 ; partial b.b
-__global__ void __launch_bounds__(kThreads) k_pcg_residual(CsrMatrix A, ContactLists c, const float4* __restrict__ b,
+__global__ void __launch_bounds__(kThreads) k_pcg_residual(CsrMatrix A, ContactLists c, PcgWork w, const float4* __restrict__ b,
                                                            const float4* __restrict__ x, float4* __restrict__ r,
                                                            float4* __restrict__ delta, float* __restrict__ partials,
                                                            float* __restrict__ scalars, int* __restrict__ flag) {
   __shared__ float smem[128];
   float bb[3] = {0.0f, 0.0f, 0.0f};
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
+  // one 256-row window per CTA step: all of them, or the active ones when the solve is restricted to left-over islands
+  const uint32_t nWin = w.actWin ? w.actCounts[0] : (A.n + kThreads - 1) / kThreads;
+  for (uint32_t wi = blockIdx.x; wi < nWin; wi += gridDim.x) {
+    const uint32_t i = (w.actWin ? w.actWin[wi] : wi) * kThreads + threadIdx.x;
+    if (i >= A.n || (w.big && !w.big[i])) continue;
     float4 xi4 = x[i];
     double y[3];
     applyRowD(i, A, c, x, v3(xi4), y);
@@ -134,9 +138,10 @@ __global__ void __launch_bounds__(kThreads) k_pcg_residual(CsrMatrix A, ContactL
 }
 
 // x += delta, once per solve (single rounding of the accumulated correction)
-__global__ void __launch_bounds__(kThreads) k_pcg_finish(uint32_t n, float4* __restrict__ x, const float4* __restrict__ delta) {
+__global__ void __launch_bounds__(kThreads) k_pcg_finish(uint32_t n, float4* __restrict__ x, const float4* __restrict__ delta,
+                                                         const uint8_t* __restrict__ big) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || (big && !big[i])) return;
   float4 xv = x[i], d = delta[i];
   x[i] = make_float4(xv.x + d.x, xv.y + d.y, xv.z + d.z, xv.w);
 }
@@ -194,8 +199,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_start(PcgWork w, float* __r
   int lane = threadIdx.x & 31;
   uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
   float acc[6] = {0, 0, 0, 0, 0, 0};
-  const uint32_t nBlocks = *w.nBlocksDev;
-  for (uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; blk < nBlocks; blk += warpsPerGrid) {
+  const uint32_t nBlocks = w.actBlk ? w.actCounts[1] : *w.nBlocksDev;
+  for (uint32_t bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; bi < nBlocks; bi += warpsPerGrid) {
+    const uint32_t blk = w.actBlk ? w.actBlk[bi] : bi;
     int node = w.blockNodes[blk * 32 + lane];
     const uint2 meta = w.blockMeta[blk];
     const int m = (int)meta.y;
@@ -268,7 +274,7 @@ struct SpmvBuf {
 constexpr size_t kSpmvSmem = 2 * sizeof(SpmvBuf);
 static_assert(sizeof(SpmvBuf) % 16 == 0, "buffer halves stay 16 B aligned");
 
-struct SpmvWindow { uint32_t base, cnt; int cbase, ccnt; };  // S entries [base, base + cnt), collision entries [cbase, cbase + ccnt)
+struct SpmvWindow { uint32_t base, cnt; int cbase, ccnt; uint32_t win, pad; };  // S entries [base, base + cnt), collision entries [cbase, cbase + ccnt)
 
 __device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gmemSrc) : "memory");
@@ -317,12 +323,14 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
   SpmvBuf* bufs = reinterpret_cast<SpmvBuf*>(spmvSmem);
   const float4* __restrict__ z = w.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t nWin = (A.n + kWinRows - 1) / kWinRows;
+  // windows: all of them, or the active ones when the solve is restricted to the left-over islands (islands.cu)
+  const uint32_t nWin = w.actWin ? w.actCounts[0] : (A.n + kWinRows - 1) / kWinRows;
   // descriptions of this CTA's first windows: static data, read while the previous kernel drains
   auto describe = [&](uint32_t first_w) {
     const uint32_t mine = min((uint32_t)kWinDescs, (nWin - first_w + gridDim.x - 1) / gridDim.x);
     if (threadIdx.x < mine) {
-      const uint32_t wd = first_w + threadIdx.x * gridDim.x;
+      const uint32_t wslot = first_w + threadIdx.x * gridDim.x;
+      const uint32_t wd = w.actWin ? w.actWin[wslot] : wslot;
       const uint32_t s0 = wd * kWinSlices, s1 = min(A.nSlices, s0 + kWinSlices);
       SpmvWindow m;
       m.base = A.sellPtr[s0]; m.cnt = A.sellPtr[s1] - m.base;
@@ -331,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
         const uint32_t r0 = wd * kWinRows, r1 = min(A.n, r0 + kWinRows);
         m.cbase = c.cPtr[r0]; m.ccnt = c.cPtr[r1] - m.cbase;
       }
+      m.win = wd; m.pad = 0;
       sDesc[threadIdx.x] = m;
     }
     return mine;
@@ -357,11 +366,11 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
   for (uint32_t first_w = blockIdx.x; first_w < nWin; first_w += (uint32_t)kWinDescs * gridDim.x) {
     const uint32_t mine = first_w == blockIdx.x ? mineFirst : describe(first_w);
     __syncthreads();
-    stageWindow(bufs[0], A, c, z, sDesc[0], first_w);
+    stageWindow(bufs[0], A, c, z, sDesc[0], sDesc[0].win);
     for (uint32_t i = 0; i < mine; ++i) {
-      const uint32_t wdw = first_w + i * gridDim.x;
+      const uint32_t wdw = sDesc[i].win;
       const bool pre = i + 1 < mine;
-      if (pre) stageWindow(bufs[(i + 1) & 1], A, c, z, sDesc[i + 1], wdw + gridDim.x);
+      if (pre) stageWindow(bufs[(i + 1) & 1], A, c, z, sDesc[i + 1], sDesc[i + 1].win);
       SpmvBuf& sb = bufs[i & 1];
       const SpmvWindow cur = sDesc[i];
       if (pre) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -371,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix
       const uint32_t sl = wdw * kWinSlices + warp;
       const bool haveSlice = sl < A.nSlices;
       const uint32_t row = haveSlice ? sb.sellRow[warp * 32 + lane] : 0xffffffffu;
-      const bool haveRow = row != 0xffffffffu;
+      const bool haveRow = row != 0xffffffffu && (!w.big || w.big[row]);
       // p / ap of the row: issued now, consumed after the loops
       float4 po = make_float4(0.0f, 0.0f, 0.0f, 0.0f), apo = po;
       if (haveRow && !first) { po = w.p[row]; apo = w.ap[row]; }
@@ -486,11 +495,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_update(PcgWork w, float4* _
   // block tables are per-substep data no kernel of the solve writes: fetch the first block while the mat-vec drains
   const int lane = threadIdx.x & 31;
   const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t nBlocks = *w.nBlocksDev;
-  uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nBlocks = w.actBlk ? w.actCounts[1] : *w.nBlocksDev;
+  uint32_t bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int nodeNext = -1;
   uint2 metaNext = make_uint2(0u, 0u);
-  if (blk < nBlocks) { nodeNext = w.blockNodes[blk * 32 + lane]; metaNext = w.blockMeta[blk]; }
+  if (bi < nBlocks) { const uint32_t blk = w.actBlk ? w.actBlk[bi] : bi; nodeNext = w.blockNodes[blk * 32 + lane]; metaNext = w.blockMeta[blk]; }
   pdlWait();
   pdlLaunchDependents();
   if (*(volatile const int*)w.flag) return;
@@ -514,14 +523,17 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_update(PcgWork w, float4* _
   for (int k = 0; k < 3; ++k) alpha[k] = pap[k] > 0.0f ? rz[k] / pap[k] : 0.0f;
   float acc[6] = {0, 0, 0, 0, 0, 0};
   // software pipeline: the next block's membership and location are fetched while this block is processed
-  for (; blk < nBlocks; blk += warpsPerGrid) {
+  for (; bi < nBlocks; bi += warpsPerGrid) {
     const int node = nodeNext;
     const int m = (int)metaNext.y;
     issueBlockInv(sInv[threadIdx.x >> 5], w.blockInv + metaNext.x, m, lane);
     V3 r = v3(0.0f, 0.0f, 0.0f);
     float4 xv, pv4, ap4, r4;
     if (node >= 0) { xv = x[node]; pv4 = w.p[node]; ap4 = w.ap[node]; r4 = w.r[node]; }
-    if (blk + warpsPerGrid < nBlocks) { nodeNext = w.blockNodes[(blk + warpsPerGrid) * 32 + lane]; metaNext = w.blockMeta[blk + warpsPerGrid]; }
+    if (bi + warpsPerGrid < nBlocks) {
+      const uint32_t nb = w.actBlk ? w.actBlk[bi + warpsPerGrid] : bi + warpsPerGrid;
+      nodeNext = w.blockNodes[nb * 32 + lane]; metaNext = w.blockMeta[nb];
+    }
     if (node >= 0) {
       V3 pv = v3(pv4), ap = v3(ap4);
       r = v3(r4);
@@ -549,7 +561,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_pcg_update(PcgWork w, float4* _
 
 int launchPcgInit(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, const float4* b,
                   const float4* x, float tol) {
-  k_pcg_residual<<<kReduceBlocks, kThreads, 0, s>>>(A, c, b, x, w.r, w.delta, w.partials, w.scalars, w.flag);
+  k_pcg_residual<<<kReduceBlocks, kThreads, 0, s>>>(A, c, w, b, x, w.r, w.delta, w.partials, w.scalars, w.flag);
   k_pcg_start<<<kReduceBlocks, kThreads, 0, s>>>(w, w.partials);
   k_pcg_check<<<1, 1, 0, s>>>(w.scalars, w.flag, kSet1, tol * tol);
   return 3;
@@ -594,7 +606,7 @@ int launchPcgCheck(cudaStream_t s, const PcgWork& w, float tol, int lastIt) {
 }
 
 int launchPcgFinish(cudaStream_t s, const PcgWork& w, uint32_t n, float4* x) {
-  k_pcg_finish<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(n, x, w.delta);
+  k_pcg_finish<<<(n + kThreads - 1) / kThreads, kThreads, 0, s>>>(n, x, w.delta, w.big);
   return 1;
 }
 
