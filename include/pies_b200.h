@@ -72,7 +72,9 @@ typedef struct PiesB200Tuning {
                               * 4 = no island-local solves: every island goes to the grid-wide CG (for testing);
                               * 16 << t = island tier t (0..3) disabled: its islands move to the next tier that fits;
                               * 256 = island tier 3 enabled (one 1024-thread CTA per island of up to 7 168 nodes; off by default:
-                              *       such islands go to the grid-wide CG) */
+                              *       such islands go to the grid-wide CG);
+                              * 512 = cold-start the 3x3 SVD of every tet projection (no warm start from the previous iteration's
+                              *       factors: same result up to rounding, for testing) */
 } PiesB200Tuning;
 
 /* Counters and device-side phase timings of the most recent tick ([additive]). */
@@ -161,6 +163,16 @@ uint32_t pies_b200_triangle_count(const PiesB200Solver* s);
 const PiesB200Vertex* pies_b200_get_vertices(const PiesB200Solver* s);
 const uint32_t* pies_b200_get_lines(const PiesB200Solver* s);
 const uint32_t* pies_b200_get_triangles(const PiesB200Solver* s); /* 3 per triangle */
+
+/* [additive] Zero-copy render interop (the reference's hosts are renderers that upload getVertices()
+ * to a vertex buffer every frame, Solver.h:42-49,65).  The Vertex mirror also exists on the device, 36 B per vertex:
+ * device_vertices brings its positions up to date on the solver's stream (one kernel, no host copy) and returns the
+ * device pointer.  With set_vertex_buffer the host supplies that buffer itself — e.g. a Vulkan / OpenGL vertex buffer
+ * imported into CUDA (cudaImportExternalMemory, cudaGraphicsMapResources): the solver then writes the vertices straight
+ * into the renderer's memory.  The buffer must hold vertex_count() x 36 bytes and stay valid until replaced (NULL
+ * returns to the internal one); after a topology change the static attributes are rewritten on the next call. */
+int pies_b200_set_vertex_buffer(PiesB200Solver* s, void* deviceBuffer);
+int pies_b200_device_vertices(PiesB200Solver* s, void** deviceVertices, uint32_t* count);
 
 /* ---- scene construction: the reference's factories (Src/PrimitiveUtilities.cpp) ---- */
 int pies_b200_add_nodes(PiesB200Solver* s, uint32_t n, const float* xyz);                      /* :42-75 */

@@ -185,6 +185,38 @@ int pies_b200_clear(PiesB200Solver* s) {
   });
 }
 
+// ---- render interop ----
+int pies_b200_set_vertex_buffer(PiesB200Solver* s, void* deviceBuffer) {
+  return guarded(s, [&]() {
+    if (deviceBuffer) {
+      cudaPointerAttributes attr{};
+      if (cudaPointerGetAttributes(&attr, deviceBuffer) != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        return fail(s, PIES_B200_EINVAL, "set_vertex_buffer: not a device pointer");
+      }
+    }
+    s->vtxExternal = static_cast<float*>(deviceBuffer);
+    s->vtxDevValid = false;
+    return PIES_B200_OK;
+  });
+}
+int pies_b200_device_vertices(PiesB200Solver* s, void** deviceVertices, uint32_t* count) {
+  if (!s || !deviceVertices) return PIES_B200_EINVAL;
+  return guarded(s, [&]() {
+    cudaSetDevice(s->device);
+    int rc = pies::ensureBuilt(s);
+    if (rc) return rc;
+    *deviceVertices = nullptr;
+    if (count) *count = s->n;
+    if (!s->n) return PIES_B200_OK;
+    float* dev = nullptr;
+    if ((rc = pies::refreshDeviceVertices(s, &dev))) return rc;
+    PIES_CHECK(s, cudaStreamSynchronize(s->stream));  // the array is complete when this returns (any stream may read it)
+    *deviceVertices = dev;
+    return PIES_B200_OK;
+  });
+}
+
 // ---- multi-GPU halo (halo.cu) ----
 int pies_b200_halo_unique_id(void* out128) {
   if (!out128) return PIES_B200_EINVAL;

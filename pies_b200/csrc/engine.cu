@@ -180,6 +180,11 @@ int ensureBuilt(PiesB200Solver* s) {
   PIES_CHECK(s, uploadVec(s->elemIds, y.elemIds, st));
   PIES_CHECK(s, uploadVec(s->elemQa, y.elemQa, st)); PIES_CHECK(s, uploadVec(s->elemQb, y.elemQb, st));
   PIES_CHECK(s, uploadVec(s->elemPc, y.elemPc, st)); PIES_CHECK(s, uploadVec(s->elemPd, y.elemPd, st));
+  {  // SVD warm-start state: identity rotations
+    std::vector<float4> ident(2ull * y.nElems, make_float4(0.0f, 0.0f, 0.0f, 1.0f));
+    PIES_CHECK(s, s->elemRot.upload(ident.data(), ident.size(), st));
+    PIES_CHECK(s, cudaStreamSynchronize(st));
+  }
   PIES_CHECK(s, uploadVec(s->distIds, sc.distId, st));
   {
     std::vector<float2> rw(sc.distW.size());
@@ -253,25 +258,37 @@ void unregisterVertexMirror(PiesB200Solver* s) {
 
 // Solver::getVertices (Solver.h:65): the reference refreshes _vertices[i].position on the host at the end of every substep
 // (Solver.cpp:393); here the whole 36 B-stride mirror comes back in one DMA, no host-side scatter.
-int refreshVertexMirror(PiesB200Solver* s) {
-  if (!s->n) return PIES_B200_OK;
+// Device-side Vertex array (internal, or the caller's render buffer): static attributes once per topology, positions now.
+int refreshDeviceVertices(PiesB200Solver* s, float** out) {
   const uint32_t n = s->n;
   static_assert(sizeof(PiesB200Vertex) == 36, "Vertex is 9 floats");
   const size_t bytes = (size_t)n * sizeof(PiesB200Vertex);
-  PiesB200Vertex* host = s->scene.vertices.data();
-  PIES_CHECK(s, s->vtxDev.reserve(9ull * n));
+  float* dev = s->vtxExternal;
+  if (!dev) { PIES_CHECK(s, s->vtxDev.reserve(9ull * n)); dev = s->vtxDev.p; }
   if (!s->vtxDevValid) {  // colours, radii: static per topology
-    PIES_CHECK(s, cudaMemcpyAsync(s->vtxDev.p, host, bytes, cudaMemcpyHostToDevice, s->stream));
+    PIES_CHECK(s, cudaMemcpyAsync(dev, s->scene.vertices.data(), bytes, cudaMemcpyHostToDevice, s->stream));
     s->vtxDevValid = true;
   }
-  k_vertex_positions<<<gridFor(n, kThreads), kThreads, 0, s->stream>>>(n, s->q.p, s->vtxDev.p);
+  k_vertex_positions<<<gridFor(n, kThreads), kThreads, 0, s->stream>>>(n, s->q.p, dev);
   ++s->launches;
+  *out = dev;
+  return PIES_B200_OK;
+}
+
+int refreshVertexMirror(PiesB200Solver* s) {
+  if (!s->n) return PIES_B200_OK;
+  const uint32_t n = s->n;
+  const size_t bytes = (size_t)n * sizeof(PiesB200Vertex);
+  PiesB200Vertex* host = s->scene.vertices.data();
+  float* dev = nullptr;
+  int rc = refreshDeviceVertices(s, &dev);
+  if (rc) return rc;
   if (s->vtxRegistered != host || s->vtxRegisteredBytes != bytes) {
     unregisterVertexMirror(s);
     if (cudaHostRegister(host, bytes, cudaHostRegisterDefault) == cudaSuccess) { s->vtxRegistered = host; s->vtxRegisteredBytes = bytes; }
     else cudaGetLastError();  // pageable destination: the runtime stages the copy, still no scatter
   }
-  PIES_CHECK(s, cudaMemcpyAsync(host, s->vtxDev.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+  PIES_CHECK(s, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
   PIES_CHECK(s, cudaStreamSynchronize(s->stream));
   s->mirrorStale = false;
   return PIES_B200_OK;
@@ -368,7 +385,7 @@ struct PdViews {
 PdViews pdViews(PiesB200Solver* s) {
   const HostSystem& y = s->sys;
   PdViews v;
-  v.te = TetElems{s->elemIds.p, s->elemQa.p, s->elemQb.p, s->elemPc.p, s->elemPd.p, y.nElems};
+  v.te = TetElems{s->elemIds.p, s->elemQa.p, s->elemQb.p, s->elemPc.p, s->elemPd.p, (s->tune.reserved & 512u) ? nullptr : s->elemRot.p, y.nElems};
   v.de = DistanceElems{s->distIds.p, s->distRestW.p, (uint32_t)s->scene.distW.size()};
   v.be = BendElems{s->bendIds.p, s->bendAngleW.p, (uint32_t)s->scene.bendW.size()};
   v.sh = ClusterElems{s->shapeOff.p, s->shapeIds.p, (uint32_t)s->scene.shapeW.size(), (uint32_t)s->scene.shapeId.size()};

@@ -77,7 +77,7 @@ struct PiesB200Solver {
   pies::DevBuf<float> partials, scalars;
   pies::DevBuf<int> flag;
   pies::DevBuf<uint4> elemIds;
-  pies::DevBuf<float4> elemQa, elemQb, elemPc, elemPd;
+  pies::DevBuf<float4> elemQa, elemQb, elemPc, elemPd, elemRot;
   pies::DevBuf<uint2> distIds; pies::DevBuf<float2> distRestW;
   pies::DevBuf<uint4> bendIds; pies::DevBuf<float2> bendAngleW;
   pies::DevBuf<uint32_t> shapeOff, shapeIds, goalOff, goalIds;
@@ -92,6 +92,7 @@ struct PiesB200Solver {
   // Device-side copy of the Vertex mirror (36 B per vertex, Solver.h:42-49): the static attributes are uploaded once per
   // topology, a kernel refreshes the positions, and getVertices() is one contiguous DMA into the (page-locked) host vector.
   pies::DevBuf<float> vtxDev; bool vtxDevValid = false;
+  float* vtxExternal = nullptr;   // caller-owned device vertex buffer (render interop), used instead of vtxDev when set
   void* vtxRegistered = nullptr; size_t vtxRegisteredBytes = 0;  // the host vector's storage while it is cudaHostRegister-ed
   // PBD
   pies::DevBuf<uint32_t> posIds; pies::DevBuf<float4> posTargetW;
@@ -136,6 +137,7 @@ void pdAbort(PiesB200Solver* s);
 int countOwnedContacts(PiesB200Solver* s, uint32_t* nTri, uint32_t* nFloor);
 int tickPBD(PiesB200Solver* s, bool refreshMirror);
 int refreshVertexMirror(PiesB200Solver* s);
+int refreshDeviceVertices(PiesB200Solver* s, float** out);  // positions into the device-side Vertex array, no host copy
 void unregisterVertexMirror(PiesB200Solver* s);  // before anything that may reallocate scene.vertices
 int uploadStateArrays(PiesB200Solver* s, const float* pos, const float* prev, const float* vel);
 int runDetection(PiesB200Solver* s, ContactLists& lists);

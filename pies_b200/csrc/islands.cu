@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(kThreads) k_isl_classify(const uint32_t* count
                                                            const uint32_t* __restrict__ nnzOff, const uint32_t* __restrict__ order,
                                                            const uint32_t* __restrict__ slotOf,
                                                            const uint32_t* __restrict__ blockCount, uint32_t listStride,
-                                                           uint32_t* __restrict__ tierList, uint32_t* counts) {
+                                                           uint32_t* __restrict__ tierList, uint4* __restrict__ tierDesc,
+                                                           uint32_t* counts) {
   uint32_t isl = blockIdx.x * blockDim.x + threadIdx.x;
   if (isl >= counts0[0]) return;
   const uint32_t s0 = islStart[isl], m = islStart[isl + 1] - s0;
@@ -136,6 +137,8 @@ __global__ void __launch_bounds__(kThreads) k_isl_classify(const uint32_t* count
   }
   const uint32_t at = atomicAdd(counts + 1 + tier, 1u);  // list order only decides scheduling: islands are independent
   tierList[(size_t)tier * listStride + at] = isl;
+  // everything a team needs to start on the island in one 16 B record (it prefetches the next one while it solves)
+  tierDesc[(size_t)tier * listStride + at] = make_uint4(isl, s0, m, nnzOff[s0]);
   if (tier == kIslandTiers) atomicAdd(counts + 2 + kIslandTiers, m);
 }
 
@@ -191,7 +194,7 @@ static IslandLayout islandLayout(const IslandCaps& c, int team, bool matSmem) {
 }
 
 struct IslandArgs {
-  const uint32_t* counts; const uint32_t* tierList; uint32_t listStride;
+  const uint32_t* counts; const uint32_t* tierList; const uint4* tierDesc; uint32_t listStride;
   const uint32_t* islStart; const uint32_t* order; const uint32_t* pos; const uint32_t* nnzOff;
   const int* rowPtr; const int* col; const float* val; const uint32_t* colRank; const uint32_t* rankInBody;
   const int* cPtr; const int* cCol; const float* cVal; const float* cDiag;
@@ -250,12 +253,15 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
   float* sRed = reinterpret_cast<float*>(base + L.red);
   uint32_t* sCtr = reinterpret_cast<uint32_t*>(base + L.ctr);
   const uint32_t count = a.counts[1 + tier];
-  const uint32_t* list = a.tierList + (size_t)tier * a.listStride;
+  const uint4* descs = a.tierDesc + (size_t)tier * a.listStride;
   int phase = 0;
-  for (uint32_t wi = blockIdx.x * kTeams + team; wi < count; wi += gridDim.x * kTeams) {
-    const uint32_t isl = list[wi];
-    const uint32_t s0 = a.islStart[isl], m = a.islStart[isl + 1] - s0;
-    const uint32_t z0 = a.nnzOff[s0];
+  const uint32_t stride = gridDim.x * kTeams;
+  uint32_t wi = blockIdx.x * kTeams + team;
+  uint4 descNext = wi < count ? __ldg(descs + wi) : make_uint4(0u, 0u, 0u, 0u);
+  for (; wi < count; wi += stride) {
+    const uint4 desc = descNext;
+    if (wi + stride < count) descNext = __ldg(descs + wi + stride);  // in flight while this island is solved
+    const uint32_t s0 = desc.y, m = desc.z, z0 = desc.w;
     float* mv = MAT_SMEM ? reinterpret_cast<float*>(base + L.val) : a.matVal + z0;
     ColT* mc = MAT_SMEM ? reinterpret_cast<ColT*>(base + L.col) : reinterpret_cast<ColT*>(a.matCol + z0);
     if (tid == 0) { sCtr[0] = 0; sCtr[1] = 0; }
@@ -285,13 +291,20 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
       const uint32_t sl = a.slotOf[g];
       slot[k] = sl;
       uint32_t e = rstart;
-#pragma unroll 4
-      for (int kk = kk0; kk < kk1; ++kk, ++e) {
-        const uint32_t rk = __ldg(a.colRank + kk);
-        const float v = __ldg(a.val + kk);
-        const bool out = rk == 0xffffffffu;  // an explicit zero pointing outside the body (bend stencils): dropped
-        mc[e] = (ColT)(out ? l : bodyBase + rk);
-        mv[e] = out ? 0.0f : v;
+      for (int kk = kk0; kk < kk1; kk += 8) {  // eight entries per batch: their 16 loads are in flight together
+        uint32_t rk[8];
+        float vv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (kk + j < kk1) { rk[j] = __ldg(a.colRank + kk + j); vv[j] = __ldg(a.val + kk + j); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (kk + j < kk1) {
+            const bool out = rk[j] == 0xffffffffu;  // an explicit zero pointing outside the body (bend stencils): dropped
+            mc[e] = (ColT)(out ? l : bodyBase + rk[j]);
+            mv[e] = out ? 0.0f : vv[j];
+            ++e;
+          }
       }
       if (a.cPtr) {
         const int c0 = a.cPtr[g], c1 = a.cPtr[g + 1];
@@ -305,7 +318,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
       if (caps.maxBlocks) {
         sLeader[l] = 0xffffu;
         if ((sl & 31u) == 0u) {  // first member of its block: claim a table entry and room for the inverse
-          const uint2 meta = a.blockMeta[sl >> 5];
+          const uint2 meta = __ldg(a.blockMeta + (sl >> 5));
           const uint32_t size = (meta.y * (meta.y + 1u) / 2u + 3u) & ~3u;
           const uint32_t idx = atomicAdd(sCtr, 1u);
           if (idx < caps.maxBlocks) {
@@ -723,7 +736,7 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   ICHECK(w.vals.reserve(nB + 1)); ICHECK(w.tmpVals.reserve(nB + 1)); ICHECK(w.heads.reserve(nB + 2));
   ICHECK(w.nodeOff.reserve(nB + 2)); ICHECK(w.posOfBody.reserve(nB + 1)); ICHECK(w.islStart.reserve(nB + 2));
   ICHECK(w.order.reserve(n + 1)); ICHECK(w.pos.reserve(n + 1)); ICHECK(w.nnzOff.reserve(n + 2));
-  ICHECK(w.tierList.reserve((size_t)(kIslandTiers + 1) * nB)); ICHECK(w.counts.reserve(16));
+  ICHECK(w.tierList.reserve((size_t)(kIslandTiers + 1) * nB)); ICHECK(w.tierDesc.reserve((size_t)(kIslandTiers + 1) * nB)); ICHECK(w.counts.reserve(16));
   ICHECK(w.blkLocal.reserve((size_t)nBlocksBound * 32 + 32)); ICHECK(w.slotIsl.reserve(n + 1));
   ICHECK(w.sortHist.reserve(sortHistBytes(nB) / 4 + 4));
   w.scanCap = std::max<uint64_t>(w.scanCap, std::max<uint64_t>(n, nB) + 2);
@@ -748,7 +761,7 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   for (int t = 0; t < kIslandTiers; ++t) tt.caps[t] = kTiers[t].caps;
   tt.enabled = tiersEnabled;
   k_isl_classify<<<gridFor(nB, kThreads), kThreads, 0, s>>>(w.counts.p, tt, w.islStart.p, w.nnzOff.p, w.order.p, slotOf, blockCount,
-                                                           nB, w.tierList.p, w.counts.p); ++L;
+                                                           nB, w.tierList.p, w.tierDesc.p, w.counts.p); ++L;
   ICHECK(cudaMemcpyAsync(w.host, w.counts.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   ICHECK(cudaEventRecord(w.ready, s));
   ICHECK(cudaEventSynchronize(w.ready));
@@ -786,7 +799,7 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
 int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const ContactLists& c, const PcgWork& pw,
                       const uint32_t* slotOf, const float4* b, float4* x, float tol, uint32_t maxIter, uint32_t statSlot) {
   IslandArgs a{};
-  a.counts = w.counts.p; a.tierList = w.tierList.p; a.listStride = w.nBodies;
+  a.counts = w.counts.p; a.tierList = w.tierList.p; a.tierDesc = w.tierDesc.p; a.listStride = w.nBodies;
   a.islStart = w.islStart.p; a.order = w.order.p; a.pos = w.pos.p; a.nnzOff = w.nnzOff.p;
   a.rowPtr = S.rowPtr; a.col = S.col; a.val = S.val; a.colRank = w.colRank.p; a.rankInBody = w.rankInBody.p;
   a.cPtr = c.nUnique ? c.cPtr : nullptr; a.cCol = c.cCol; a.cVal = c.cVal; a.cDiag = (c.nTri || c.nFloor) ? c.cDiag : nullptr;

@@ -23,6 +23,7 @@ struct IslandWork {
   // once per substep
   DevBuf<uint32_t> parent, vals, tmpVals, heads, nodeOff, posOfBody, islStart, order, pos, nnzOff, sortHist, scanScratch;
   DevBuf<uint64_t> keys, tmpKeys;
+  DevBuf<uint4> tierDesc;         // per list entry: (island, first row in island order, rows, first matrix entry)
   DevBuf<uint32_t> tierList;      // (kIslandTiers + 1) lists of nBodies entries; list kIslandTiers = islands left to the global CG
   DevBuf<uint32_t> counts;        // device: [0] islands, [1 + t] islands of tier t, [1 + kIslandTiers] left over, then nodes left over
   DevBuf<uint32_t> blkLocal;      // preconditioner block * 32 + lane -> island-local row of that member (written by every solve)

@@ -23,6 +23,7 @@ struct TetElems {
   float4* qb = nullptr;      // Qinv[4..7]
   float4* pc = nullptr;      // Qinv[8], wStrain, minStrain, maxStrain
   float4* pd = nullptr;      // wVolume, minOmega, maxOmega, unused
+  float4* rot = nullptr;     // state: 2 unit quaternions per tet (U, V of the last SVD), warm start of the next; null = cold start
   uint32_t n = 0;
 };
 

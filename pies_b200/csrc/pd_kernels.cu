@@ -49,7 +49,13 @@ __global__ void __launch_bounds__(128) k_tet_elems(TetElems e, const float4* __r
   M3 F = deformationGradient(x1, x2, x3, x4, qinv);
   M3 U, V;
   float sg[3];
-  svd3(F, U, sg, V);
+  if (e.rot) {  // warm start from the factors of the previous PD iteration (state, like the shape-matching quaternion)
+    float4 qu = e.rot[2ull * i], qv = e.rot[2ull * i + 1];
+    svd3Warm(F, qu, qv, U, sg, V);
+    e.rot[2ull * i] = qu; e.rot[2ull * i + 1] = qv;
+  } else {
+    svd3(F, U, sg, V);
+  }
   float wS = pc.y, wV = pd.x;
   float d[3] = {0.0f, 0.0f, 0.0f};
   if (wS != 0.0f) {

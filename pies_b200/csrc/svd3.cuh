@@ -74,6 +74,85 @@ __device__ __forceinline__ void swapCols(M3& U, M3& V, float (&s)[3]) {
   }
 }
 
+// Rotation matrix of a unit quaternion (x, y, z, w).
+__device__ __forceinline__ M3 quatToMat(float4 q) {
+  const float xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z;
+  const float xy = q.x * q.y, xz = q.x * q.z, yz = q.y * q.z, wx = q.w * q.x, wy = q.w * q.y, wz = q.w * q.z;
+  M3 R;
+  R.m[0][0] = 1.0f - 2.0f * (yy + zz); R.m[0][1] = 2.0f * (xy - wz);        R.m[0][2] = 2.0f * (xz + wy);
+  R.m[1][0] = 2.0f * (xy + wz);        R.m[1][1] = 1.0f - 2.0f * (xx + zz); R.m[1][2] = 2.0f * (yz - wx);
+  R.m[2][0] = 2.0f * (xz - wy);        R.m[2][1] = 2.0f * (yz + wx);        R.m[2][2] = 1.0f - 2.0f * (xx + yy);
+  return R;
+}
+
+// Unit quaternion of a proper rotation matrix (Shepperd: the largest of w, x, y, z is computed from the diagonal, the
+// others from the off-diagonal sums; normalised at the end, so orthogonality drift of the matrix does not accumulate).
+__device__ __forceinline__ float4 matToQuat(const M3& R) {
+  const float tr = R.m[0][0] + R.m[1][1] + R.m[2][2];
+  float4 q;
+  if (tr > 0.0f) {
+    q = make_float4(R.m[2][1] - R.m[1][2], R.m[0][2] - R.m[2][0], R.m[1][0] - R.m[0][1], 1.0f + tr);
+  } else if (R.m[0][0] >= R.m[1][1] && R.m[0][0] >= R.m[2][2]) {
+    q = make_float4(1.0f + R.m[0][0] - R.m[1][1] - R.m[2][2], R.m[0][1] + R.m[1][0], R.m[0][2] + R.m[2][0], R.m[2][1] - R.m[1][2]);
+  } else if (R.m[1][1] >= R.m[2][2]) {
+    q = make_float4(R.m[0][1] + R.m[1][0], 1.0f + R.m[1][1] - R.m[0][0] - R.m[2][2], R.m[1][2] + R.m[2][1], R.m[0][2] - R.m[2][0]);
+  } else {
+    q = make_float4(R.m[0][2] + R.m[2][0], R.m[1][2] + R.m[2][1], 1.0f + R.m[2][2] - R.m[0][0] - R.m[1][1], R.m[1][0] - R.m[0][1]);
+  }
+  const float inv = rsqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  return make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+}
+
+// Jacobi sweeps on A = U^T F V for given orthogonal U, V, accumulating into U and V until A is diagonal.
+__device__ __forceinline__ void jacobiSweeps(M3& A, M3& U, M3& V) {
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    float maxDiag = fmaxf(fabsf(A.m[0][0]), fmaxf(fabsf(A.m[1][1]), fabsf(A.m[2][2])));
+    float thresh = fmaxf(2.0f * 1.1920929e-7f * maxDiag, 1e-37f);  // Eigen: 2*eps*maxDiagEntry
+    bool any = jacobiPair<0, 1>(A, U, V, thresh);
+    any |= jacobiPair<0, 2>(A, U, V, thresh);
+    any |= jacobiPair<1, 2>(A, U, V, thresh);
+    if (!any) break;
+  }
+}
+
+// Eigen's conventions on the converged factors: sigma >= 0, sorted descending.
+__device__ __forceinline__ void svdFinish(const M3& A, M3& U, float (&s)[3], M3& V) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float d = A.m[i][i];
+    if (d < 0.0f) {
+      d = -d;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) U.m[k][i] = -U.m[k][i];
+    }
+    s[i] = d;
+  }
+  if (s[0] < s[1]) swapCols<0, 1>(U, V, s);
+  if (s[0] < s[2]) swapCols<0, 2>(U, V, s);
+  if (s[1] < s[2]) swapCols<1, 2>(U, V, s);
+}
+
+// Warm-started SVD: qu, qv hold the rotations the previous call converged to (identity quaternions at first); on return
+// they hold this call's.  F changes little between two PD iterations, so U0^T F V0 is nearly diagonal and one sweep
+// (plus the sweep that finds nothing left to rotate) replaces the four or five a cold start needs.
+__device__ __forceinline__ void svd3Warm(const M3& F, float4& qu, float4& qv, M3& U, float (&s)[3], M3& V) {
+  U = quatToMat(qu);
+  V = quatToMat(qv);
+  M3 T, A;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) T.m[i][j] = F.m[i][0] * V.m[0][j] + F.m[i][1] * V.m[1][j] + F.m[i][2] * V.m[2][j];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) A.m[i][j] = U.m[0][i] * T.m[0][j] + U.m[1][i] * T.m[1][j] + U.m[2][i] * T.m[2][j];
+  jacobiSweeps(A, U, V);
+  qu = matToQuat(U);   // before the sign flips / column swaps of svdFinish: both stay proper rotations
+  qv = matToQuat(V);
+  svdFinish(A, U, s, V);
+}
+
 // F = U diag(s) V^T.
 __device__ __forceinline__ void svd3(const M3& F, M3& U, float (&s)[3], M3& V) {
   M3 A = F;

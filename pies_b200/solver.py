@@ -130,6 +130,8 @@ _SIGNATURES = {
     "pies_b200_set_triangle_order": (C.c_int, [_vp, C.c_uint32, _u32p]),
     "pies_b200_set_owned_nodes": (C.c_int, [_vp, C.c_uint32, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")]),
     "pies_b200_count_owned_contacts": (C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "pies_b200_set_vertex_buffer": (C.c_int, [_vp, _vp]),
+    "pies_b200_device_vertices": (C.c_int, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
     "pies_b200_halo_unique_id": (C.c_int, [_vp]),
     "pies_b200_halo_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "pies_b200_halo_set_lists": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
@@ -213,7 +215,7 @@ class Solver:
             pass
 
     def setTuning(self, pcgTolerance=None, pcgMaxIterations=None, pcgCheckEvery=None, profilePhases=None, dataflowSweepsOnly=None,
-                  islandSolves=None, islandTiersOff=None, islandBigTier=None):
+                  islandSolves=None, islandTiersOff=None, islandBigTier=None, svdWarmStart=None):
         t = Tuning()
         lib().pies_b200_default_tuning(C.byref(t))
         cur = getattr(self, "_tuning", None)
@@ -227,6 +229,7 @@ class Solver:
         if islandSolves is not None: t.reserved = (t.reserved & ~4) | (0 if islandSolves else 4)
         if islandTiersOff is not None: t.reserved = (t.reserved & ~0xF0) | ((int(islandTiersOff) & 0xF) << 4)
         if islandBigTier is not None: t.reserved = (t.reserved & ~256) | (256 if islandBigTier else 0)
+        if svdWarmStart is not None: t.reserved = (t.reserved & ~512) | (0 if svdWarmStart else 512)
         self._tuning = t
         self._ck(lib().pies_b200_set_tuning(self.h, C.byref(t)))
 
@@ -462,6 +465,17 @@ class Solver:
     def setOwnedNodes(self, mask):
         mask = np.ascontiguousarray(mask, np.uint8)
         self._ck(lib().pies_b200_set_owned_nodes(self.h, len(mask), mask))
+
+    # -- render interop (include/pies_b200.h) --
+    def setVertexBuffer(self, device_ptr):
+        """device_ptr: a caller-owned device buffer of vertex_count x 36 bytes (e.g. an imported render buffer), or None."""
+        self._ck(lib().pies_b200_set_vertex_buffer(self.h, _vp(device_ptr) if device_ptr else None))
+
+    def deviceVertices(self):
+        """(device pointer, count) of the up-to-date Vertex array on the device; no host copy."""
+        p, n = C.c_void_p(), C.c_uint32()
+        self._ck(lib().pies_b200_device_vertices(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     # -- multi-GPU halo inside the library (include/pies_b200.h: pies_b200_halo_*) --
     @staticmethod

@@ -425,3 +425,71 @@ def test_pcg_cap_is_loud(pb):
             s.tick()
     st = s.stats()
     assert st.pcgCapHits > 0 and st.pcgWorstCapResidual > 1e-9
+
+
+def test_svd_warm_start_matches_cold_start(pb):
+    """k_tet_elems warm-starts the 3x3 Jacobi SVD of every tet from the rotations the previous PD iteration converged to
+    (two quaternions per tet, state).  Any converged SVD gives the same projection U sigma^ V^T up to rounding, so the
+    trajectory must follow the cold-started one: same contact counts, positions within the rounding-integration bound
+    (3e-5 x diagonal over 40 ticks, cf. tests/golden/sensitivity.json) through free fall, rotation-free floor contact and
+    — with a spinning, sheared body — large rotations between iterations."""
+    from pies_b200 import scenes
+
+    def make(warm):
+        s = pb.Solver(**scenes.S3_OPTIONS)
+        scenes.build_s3(s, bodies=16, nx=2, nz=2)
+        s.createTetBox((9.0, 2.0, 0.0), 1.0, (0.0, 0.0, 0.0), 1000.0, 1.0, False)
+        s.setTuning(svdWarmStart=warm)
+        return s
+    a, b = make(True), make(False)
+    # spin and shear the extra body: node velocities v = omega x (r - c) + shear
+    p = a.positions; n0 = 16 * 27
+    c = p[n0:].mean(0)
+    v = np.zeros_like(p)
+    r = p[n0:] - c
+    v[n0:] = np.cross(np.array([0.0, 0.0, 25.0], np.float32), r) + np.outer(r[:, 1], np.array([3.0, 0.0, 0.0], np.float32))
+    for s in (a, b):
+        s.setState(None, None, v)
+    diag = bbox_diag(p)
+    for t in range(1, 41):
+        a.tick(); b.tick()
+        sa, sb = a.stats(), b.stats()
+        assert (sa.triCollisions, sa.staticCollisions) == (sb.triCollisions, sb.staticCollisions), t
+        err = np.abs(a.positions - b.positions).max()
+        assert err <= 3e-5 * diag, (t, err)
+    assert np.isfinite(a.positions).all()
+
+
+def test_device_vertex_array_and_external_render_buffer(pb):
+    """Zero-copy readback: the Vertex array on the device (36 B per vertex, Solver.h:42-49) equals what getVertices()
+    returns, both in the solver's own buffer and in a caller-supplied one (standing in for an imported Vulkan / OpenGL
+    vertex buffer), with no host copy in between."""
+    import torch
+    s = pb.Solver(iterations=10)
+    two_box(s)
+    for _ in range(5):
+        s.tick()
+    ptr, n = s.deviceVertices()
+    assert n == 54 and ptr
+
+    class Raw:
+        def __init__(self, p, n):
+            self.__cuda_array_interface__ = {"shape": (n, 9), "typestr": "<f4", "data": (p, True), "version": 3, "strides": None}
+    dev = torch.as_tensor(Raw(ptr, n), device="cuda").clone().cpu().numpy()
+    host = s.getVertices()
+    assert (dev[:, :3] == host["position"]).all() and (dev[:, 3] == host["radius"]).all()
+    assert (dev[:, 4:7] == host["baseColor"]).all()
+    ext = torch.zeros((n, 9), dtype=torch.float32, device="cuda")
+    s.setVertexBuffer(ext.data_ptr())
+    s.tick()
+    p2, _ = s.deviceVertices()
+    assert p2 == ext.data_ptr()
+    torch.cuda.synchronize()
+    host = s.getVertices()
+    got = ext.cpu().numpy()
+    assert (got[:, :3] == host["position"]).all() and (got[:, 3] == host["radius"]).all() and (got[:, 4:7] == host["baseColor"]).all()
+    s.setVertexBuffer(None)
+    s.tick()
+    assert np.isfinite(s.getVertices()["position"]).all()
+    with pytest.raises(pb.PiesError):
+        s.setVertexBuffer(12345)
