@@ -291,20 +291,33 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
       const uint32_t sl = a.slotOf[g];
       slot[k] = sl;
       uint32_t e = rstart;
-      for (int kk = kk0; kk < kk1; kk += 8) {  // eight entries per batch: their 16 loads are in flight together
-        uint32_t rk[8];
-        float vv[8];
+      if (TEAM == 32) {
+        // warp tier: the island is staged by one warp whose only other work is waiting, so all 16 loads of eight entries
+        // are put in flight together (r02g: 85 -> 75 us); on the CTA tiers the same batching cost registers and 10 %
+        for (int kk = kk0; kk < kk1; kk += 8) {
+          uint32_t rk[8];
+          float vv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (kk + j < kk1) { rk[j] = __ldg(a.colRank + kk + j); vv[j] = __ldg(a.val + kk + j); }
+          for (int j = 0; j < 8; ++j)
+            if (kk + j < kk1) { rk[j] = __ldg(a.colRank + kk + j); vv[j] = __ldg(a.val + kk + j); }
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (kk + j < kk1) {
-            const bool out = rk[j] == 0xffffffffu;  // an explicit zero pointing outside the body (bend stencils): dropped
-            mc[e] = (ColT)(out ? l : bodyBase + rk[j]);
-            mv[e] = out ? 0.0f : vv[j];
-            ++e;
-          }
+          for (int j = 0; j < 8; ++j)
+            if (kk + j < kk1) {
+              const bool out = rk[j] == 0xffffffffu;  // an explicit zero pointing outside the body (bend stencils): dropped
+              mc[e] = (ColT)(out ? l : bodyBase + rk[j]);
+              mv[e] = out ? 0.0f : vv[j];
+              ++e;
+            }
+        }
+      } else {
+#pragma unroll 4
+        for (int kk = kk0; kk < kk1; ++kk, ++e) {
+          const uint32_t rk = __ldg(a.colRank + kk);
+          const float v = __ldg(a.val + kk);
+          const bool out = rk == 0xffffffffu;
+          mc[e] = (ColT)(out ? l : bodyBase + rk);
+          mv[e] = out ? 0.0f : v;
+        }
       }
       if (a.cPtr) {
         const int c0 = a.cPtr[g], c1 = a.cPtr[g + 1];
@@ -811,7 +824,8 @@ int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const C
   // Tiers 2 and 3 hold a handful of islands each of which keeps one CTA busy for a long chain of iterations: they run on
   // their own streams, beside the thousands of small islands of tiers 0 and 1 that fill the other SMs.
   const bool side = w.tierCount[3] || w.tierCount[2];
-  if (side) cudaEventRecord(w.fork, s);
+  const bool warpAside = w.tierCount[0] && w.tierCount[1];
+  if (side || warpAside) cudaEventRecord(w.fork, s);   // before anything of this solve is enqueued on s
   if (w.tierCount[3]) {
     cudaStreamWaitEvent(w.aux[0], w.fork, 0);
     const uint32_t maxNodes = kTiers[3].caps.maxNodes;
@@ -828,8 +842,16 @@ int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const C
     ++L;
   }
   if (w.tierCount[1]) { launchTier(k_island_pcg<320, 2, true>, 1, (int)std::min<uint32_t>(w.tierCount[1], 2 * kNumSMs), s, a); ++L; }
-  if (w.tierCount[0]) { launchTier(k_island_pcg<32, 1, true>, 0, (int)std::min<uint32_t>((w.tierCount[0] + 7) / 8, 3 * kNumSMs), s, a); ++L; }
-  if (w.tierCount[3]) cudaStreamWaitEvent(s, w.join[0], 0);
+  // The warp tier goes to a side stream when the 320-thread tier runs too: its CTAs fill the SMs that tier's last,
+  // partly filled wave leaves idle (3.5 waves of 296 CTAs at S3) instead of queueing behind it.
+  if (w.tierCount[0]) {
+    cudaStream_t st0 = s;
+    if (warpAside) { cudaStreamWaitEvent(w.aux[0], w.fork, 0); st0 = w.aux[0]; }
+    launchTier(k_island_pcg<32, 1, true>, 0, (int)std::min<uint32_t>((w.tierCount[0] + 7) / 8, 3 * kNumSMs), st0, a);
+    ++L;
+    if (warpAside) { cudaEventRecord(w.join[0], w.aux[0]); cudaStreamWaitEvent(s, w.join[0], 0); }
+  }
+  if (w.tierCount[3] && !warpAside) cudaStreamWaitEvent(s, w.join[0], 0);
   if (w.tierCount[2]) cudaStreamWaitEvent(s, w.join[1], 0);
   return L;
 }

@@ -474,7 +474,7 @@ def test_device_vertex_array_and_external_render_buffer(pb):
 
     class Raw:
         def __init__(self, p, n):
-            self.__cuda_array_interface__ = {"shape": (n, 9), "typestr": "<f4", "data": (p, True), "version": 3, "strides": None}
+            self.__cuda_array_interface__ = {"shape": (n, 9), "typestr": "<f4", "data": (p, False), "version": 3, "strides": None}
     dev = torch.as_tensor(Raw(ptr, n), device="cuda").clone().cpu().numpy()
     host = s.getVertices()
     assert (dev[:, :3] == host["position"]).all() and (dev[:, 3] == host["radius"]).all()
