@@ -73,6 +73,9 @@ typedef struct PiesB200Tuning {
                               * 16 << t = island tier t (0..3) disabled: its islands move to the next tier that fits;
                               * 256 = island tier 3 enabled (one 1024-thread CTA per island of up to 7 168 nodes; off by default:
                               *       such islands go to the grid-wide CG);
+                              * 1024 = PBD node-node response in colour batches instead of the reference's sequential order
+                              *       (same operation per pair and per visit, different visiting order: for scenes whose contact
+                              *       graph is one long chain, where the exact order is inherently serial; see pbd.cu);
                               * 512 = cold-start the 3x3 SVD of every tet projection (no warm start from the previous iteration's
                               *       factors: same result up to rounding, for testing) */
 } PiesB200Tuning;

@@ -57,6 +57,9 @@ struct PbdWork {
   DevBuf<uint32_t> visCnt; DevBuf<uint4> visits /* i, j, keyLo, keyHi|first<<31 */; DevBuf<uint2> visTk;
   DevBuf<uint64_t> incKeys, incTmpKeys; DevBuf<uint32_t> incVals, incTmpVals, incPtr;
   DevBuf<uint32_t> flags;   // [0] movement bound exceeded
+  // colour-batched node-node response (opt-in, PiesB200Tuning::reserved & 1024): distinct pairs, their colours
+  DevBuf<uint32_t> pairCnt; DevBuf<uint4> pairs /* a, b, applications, - */; DevBuf<uint32_t> pairColor, nodeMinPrio;
+  DevBuf<unsigned long long> nodeMask; DevBuf<uint32_t> colorStat;  // [0] pairs still uncoloured, [1] colours in use
   int* host = nullptr;      // pinned, 16 ints
   float delta = 0.0f;
   uint64_t visitsLastTick = 0;
@@ -490,6 +493,113 @@ __global__ void __launch_bounds__(kSweepThreads) k_pbd_collide(uint32_t nVis, co
 }
 
 // ------------------------------------------------------------------------------------------
+// Colour-batched node-node response (the north_star's "graph-coloured Jacobi-free batches"), opt-in.
+//
+// The reference's response is ONE sequential sweep: node i's visits modify its partners before their own turn, so on
+// a scene whose contact graph is a long chain (a coiled rope: every node touches its neighbours) the dependency chain
+// of the ordered executor above is as long as the visit list — exact, and serial (measured: seconds per tick beyond a
+// few thousand nodes).  This mode gives up the reference's ORDER, not its operation: the distinct overlapping pairs of
+// the visit list are edge-coloured (no two pairs of a colour share a node), colours run one after the other, and a
+// pair receives the reference's response (push apart by 0.85 x overlap, mass weighted, Solver.cpp:100-110) as many
+// times as the reference would have visited it (once per shared cell from either side), each time on the updated
+// positions.  Deterministic (integer atomics only, fixed priorities); results differ from the reference's like a
+// different visiting order does, so the parity tests run the ordered executor and this mode is held to
+// physical properties (tests/test_pbd_gpu.py).
+__device__ __forceinline__ uint32_t pairPriority(uint32_t p) {  // fixed pseudo-random priority: long chains colour in O(log n) rounds
+  uint32_t h = p * 2654435761u;
+  h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+  return h;
+}
+
+// distinct partners j > i of node i in its visit range, with the number of visits (shared cells)
+template <bool WRITE>
+__global__ void __launch_bounds__(kThreads) k_pbd_pairs(uint32_t n, const uint32_t* __restrict__ visOff, const uint4* __restrict__ visits,
+                                                        uint32_t* __restrict__ pairCnt /* scanned when WRITE */, uint4* __restrict__ pairs) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = visOff[i], e = visOff[i + 1];
+  uint32_t total = 0, out = WRITE ? pairCnt[i] : 0u;
+  for (uint32_t k = s; k < e; ++k) {
+    const uint32_t j = visits[k].y;
+    if (j <= i) continue;
+    bool seen = false;
+    for (uint32_t m = s; m < k && !seen; ++m) seen = visits[m].y == j;
+    if (seen) continue;
+    if (WRITE) {
+      uint32_t cnt = 1;
+      for (uint32_t m = k + 1; m < e; ++m) cnt += visits[m].y == j ? 1u : 0u;
+      pairs[out + total] = make_uint4(i, j, 2u * cnt, 0u);   // the partner visits the pair as often from its side
+    }
+    ++total;
+  }
+  if (!WRITE) pairCnt[i] = total;
+}
+
+__global__ void __launch_bounds__(kThreads) k_pbd_color_propose(uint32_t nP, const uint4* __restrict__ pairs,
+                                                                const uint32_t* __restrict__ color, uint32_t* __restrict__ nodeMinPrio) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nP || color[p] != 0xffffffffu) return;
+  const uint32_t pr = pairPriority(p);
+  atomicMin(nodeMinPrio + pairs[p].x, pr);
+  atomicMin(nodeMinPrio + pairs[p].y, pr);
+}
+
+// a pair whose priority is the smallest among the uncoloured pairs at BOTH its nodes takes the lowest colour free at both
+// (no other pair touches either node in this round, so the masks are updated without atomics)
+__global__ void __launch_bounds__(kThreads) k_pbd_color_commit(uint32_t nP, const uint4* __restrict__ pairs, uint32_t* __restrict__ color,
+                                                               const uint32_t* __restrict__ nodeMinPrio,
+                                                               unsigned long long* __restrict__ nodeMask, uint32_t* __restrict__ stat) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nP || color[p] != 0xffffffffu) return;
+  const uint32_t a = pairs[p].x, b = pairs[p].y, pr = pairPriority(p);
+  if (nodeMinPrio[a] == pr && nodeMinPrio[b] == pr) {
+    const unsigned long long used = nodeMask[a] | nodeMask[b];
+    const int c = __ffsll((long long)~used) - 1;   // -1: all 64 colours taken at these nodes (a node overlapping > 32 others)
+    if (c >= 0) {
+      color[p] = (uint32_t)c;
+      nodeMask[a] |= 1ull << c; nodeMask[b] |= 1ull << c;
+      atomicMax(stat + 1, (uint32_t)c + 1u);
+      return;
+    }
+    color[p] = 0xfffffffeu;  // left out: reported, the pass then falls back to the ordered executor
+    atomicAdd(stat + 2, 1u);
+    return;
+  }
+  atomicAdd(stat, 1u);  // still uncoloured after this round
+}
+
+__global__ void __launch_bounds__(kThreads) k_pbd_apply_color(uint32_t nP, uint32_t c, const uint4* __restrict__ pairs,
+                                                              const uint32_t* __restrict__ color, float4* __restrict__ q,
+                                                              const float4* __restrict__ prev, const float4* __restrict__ q0, float delta,
+                                                              uint32_t* __restrict__ flags) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nP || color[p] != c) return;
+  const uint4 pr = pairs[p];
+  float4 pi = q[pr.x], pj = q[pr.y];
+  const float ri = prev[pr.x].w, rj = prev[pr.y].w;
+  const float wSum = pi.w + pj.w;
+  bool moved = false;
+  for (uint32_t k = 0; k < pr.z; ++k) {  // Solver.cpp:95-110, once per visit the reference makes
+    const float dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float disp = ri + rj - dist;
+    if (!(disp > 0.0f)) break;
+    float nx = 1.0f, ny = 0.0f, nz = 0.0f;
+    if (dist > 0.00001f) { nx = dx / dist; ny = dy / dist; nz = dz / dist; }
+    const float ka = -0.85f * disp * pi.w / wSum, kb = 0.85f * disp * pj.w / wSum;
+    pi.x += ka * nx; pi.y += ka * ny; pi.z += ka * nz;
+    pj.x += kb * nx; pj.y += kb * ny; pj.z += kb * nz;
+    moved = true;
+  }
+  if (!moved) return;
+  q[pr.x] = pi; q[pr.y] = pj;
+  const float4 bi = q0[pr.x], bj = q0[pr.y];
+  const float far = fmaxf(fmaxf(fmaxf(fabsf(pi.x - bi.x), fabsf(pi.y - bi.y)), fabsf(pi.z - bi.z)),
+                          fmaxf(fmaxf(fabsf(pj.x - bj.x), fabsf(pj.y - bj.y)), fabsf(pj.z - bj.z)));
+  if (!(far <= delta)) flags[0] = 1u;   // the pair list was pruned assuming no node strays further than delta
+}
+
+// ------------------------------------------------------------------------------------------
 #define PCHECK(expr)                                                              \
   do {                                                                            \
     cudaError_t _e = (expr);                                                      \
@@ -634,6 +744,60 @@ static int collideNodes(PiesB200Solver* s, PbdWork& w) {
     PCHECK(w.scanScratch.reserve(scanScratchElems(std::max<uint64_t>(std::max<uint64_t>(nInc, nPairs) + 2, n + 3))));
     k_pbd_visits<true><<<gridFor(n, kThreads), kThreads, 0, st>>>(n, w.q0.p, s->prev.p, scale, delta, kp, w.cellKey.p, nCells,
                                                                  w.cellStart.p, w.vals.p, w.visCnt.p, w.visits.p); ++s->launches;
+    if (s->tune.reserved & 1024u) {
+      // ---- colour-batched response (see k_pbd_pairs ...): distinct pairs, edge colouring, one launch per colour
+      PCHECK(w.pairCnt.reserve(n + 2)); PCHECK(w.nodeMinPrio.reserve(n + 1)); PCHECK(w.nodeMask.reserve(n + 1)); PCHECK(w.colorStat.reserve(4));
+      PCHECK(cudaMemsetAsync(w.pairCnt.p + n, 0, 2 * sizeof(uint32_t), st));
+      k_pbd_pairs<false><<<gridFor(n, kThreads), kThreads, 0, st>>>(n, w.visCnt.p, w.visits.p, w.pairCnt.p, nullptr); ++s->launches;
+      s->launches += launchExclusiveScan(st, w.pairCnt.p, n + 1, w.scanScratch.p);
+      PCHECK(cudaMemcpyAsync(w.host + 12, w.pairCnt.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      PCHECK(cudaStreamSynchronize(st));
+      const uint32_t nP = (uint32_t)w.host[12];
+      bool fallBack = false;
+      if (nP) {
+        PCHECK(w.pairs.reserve(nP)); PCHECK(w.pairColor.reserve(nP));
+        k_pbd_pairs<true><<<gridFor(n, kThreads), kThreads, 0, st>>>(n, w.visCnt.p, w.visits.p, w.pairCnt.p, w.pairs.p); ++s->launches;
+        PCHECK(cudaMemsetAsync(w.pairColor.p, 0xff, (size_t)nP * sizeof(uint32_t), st));
+        PCHECK(cudaMemsetAsync(w.nodeMask.p, 0, (size_t)(n + 1) * sizeof(unsigned long long), st));
+        PCHECK(cudaMemsetAsync(w.colorStat.p, 0, 4 * sizeof(uint32_t), st));
+        uint32_t left = nP, colors = 0, leftOut = 0;
+        for (int batch = 0; batch < 64 && left; ++batch) {   // 16 rounds per host read; a handful of batches at most
+          for (int round = 0; round < 16; ++round) {
+            PCHECK(cudaMemsetAsync(w.nodeMinPrio.p, 0xff, (size_t)(n + 1) * sizeof(uint32_t), st));
+            PCHECK(cudaMemsetAsync(w.colorStat.p, 0, sizeof(uint32_t), st));
+            k_pbd_color_propose<<<gridFor(nP, kThreads), kThreads, 0, st>>>(nP, w.pairs.p, w.pairColor.p, w.nodeMinPrio.p);
+            k_pbd_color_commit<<<gridFor(nP, kThreads), kThreads, 0, st>>>(nP, w.pairs.p, w.pairColor.p, w.nodeMinPrio.p, w.nodeMask.p,
+                                                                          w.colorStat.p);
+            s->launches += 2;
+          }
+          PCHECK(cudaMemcpyAsync(w.host + 12, w.colorStat.p, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+          PCHECK(cudaStreamSynchronize(st));
+          left = (uint32_t)w.host[12]; colors = (uint32_t)w.host[13]; leftOut = (uint32_t)w.host[14];
+        }
+        fallBack = left != 0 || leftOut != 0;   // a node with more than 64 distinct partners: the ordered executor takes the pass
+        if (!fallBack) {
+          for (uint32_t c = 0; c < colors; ++c) {
+            k_pbd_apply_color<<<gridFor(nP, kThreads), kThreads, 0, st>>>(nP, c, w.pairs.p, w.pairColor.p, s->q.p, s->prev.p, w.q0.p,
+                                                                         delta, w.flags.p);
+            ++s->launches;
+          }
+          PCHECK(cudaMemcpyAsync(w.host + 11, w.flags.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+          PCHECK(cudaStreamSynchronize(st));
+          w.visitsLastTick += nVis;
+          if (getenv("PIES_DEBUG_PBD"))
+            std::fprintf(stderr, "[pbd] colour-batched: visits %u pairs %u colours %u delta %g attempt %d -> %s\n", nVis, nP, colors, delta,
+                         attempt, w.host[11] ? "redo" : "ok");
+          if (!w.host[11]) return PIES_B200_OK;
+          PCHECK(cudaMemcpyAsync(s->q.p, w.q0.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+          PCHECK(cudaMemsetAsync(w.flags.p, 0, sizeof(uint32_t), st));
+          w.delta *= 2.0f;
+          continue;
+        }
+      } else {
+        w.visitsLastTick += nVis;
+        return PIES_B200_OK;   // only self visits: net zero
+      }
+    }
     PCHECK(cudaMemsetAsync(w.incPtr.p, 0, (size_t)(n + 3) * sizeof(uint32_t), st));
     k_pbd_inc_emit<<<gridFor(nVis, kThreads), kThreads, 0, st>>>(nVis, n, w.visits.p, w.incKeys.p, w.incVals.p, w.incPtr.p); ++s->launches;
     s->launches += launchExclusiveScan(st, w.incPtr.p, n + 2, w.scanScratch.p);

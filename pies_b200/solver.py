@@ -215,7 +215,7 @@ class Solver:
             pass
 
     def setTuning(self, pcgTolerance=None, pcgMaxIterations=None, pcgCheckEvery=None, profilePhases=None, dataflowSweepsOnly=None,
-                  islandSolves=None, islandTiersOff=None, islandBigTier=None, svdWarmStart=None):
+                  islandSolves=None, islandTiersOff=None, islandBigTier=None, svdWarmStart=None, pbdColourBatches=None):
         t = Tuning()
         lib().pies_b200_default_tuning(C.byref(t))
         cur = getattr(self, "_tuning", None)
@@ -230,6 +230,7 @@ class Solver:
         if islandTiersOff is not None: t.reserved = (t.reserved & ~0xF0) | ((int(islandTiersOff) & 0xF) << 4)
         if islandBigTier is not None: t.reserved = (t.reserved & ~256) | (256 if islandBigTier else 0)
         if svdWarmStart is not None: t.reserved = (t.reserved & ~512) | (0 if svdWarmStart else 512)
+        if pbdColourBatches is not None: t.reserved = (t.reserved & ~1024) | (1024 if pbdColourBatches else 0)
         self._tuning = t
         self._ck(lib().pies_b200_set_tuning(self.h, C.byref(t)))
 

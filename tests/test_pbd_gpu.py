@@ -118,3 +118,69 @@ def test_pbd_with_tets_is_refused(pb):
     s.createTetBox((0, 1, 0), 1.0, (0, 0, 0), 1000.0, 1.0, False)
     with pytest.raises(pb.PiesError):
         s.tick()
+
+
+def _max_overlap(p, radius=0.25, skip_neighbours=True):
+    """Largest overlap (2r - distance) / 2r between chain nodes that are not chain neighbours, over pairs found on a grid."""
+    from collections import defaultdict
+    cells = defaultdict(list)
+    key = np.floor(p / (2 * radius)).astype(np.int64)
+    for i, k in enumerate(map(tuple, key)):
+        cells[k].append(i)
+    worst = 0.0
+    offs = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
+    for (x, y, z), members in cells.items():
+        cand = [j for o in offs for j in cells.get((x + o[0], y + o[1], z + o[2]), ())]
+        if len(cand) < 2:
+            continue
+        c = np.asarray(cand)
+        for i in members:
+            d = np.linalg.norm(p[c] - p[i], axis=1)
+            ok = c != i
+            if skip_neighbours:
+                ok &= np.abs(c - i) > 1
+            if ok.any():
+                worst = max(worst, float((2 * radius - d[ok]).max() / (2 * radius)))
+    return worst
+
+
+def test_pbd_colour_batched_contacts_small_scene(pb):
+    """The colour-batched node-node response (opt-in; the reference's operation per pair and visit, another visiting order)
+    against the ordered executor on the self-overlapping flat coil: both resolve the overlaps the coil starts with (arms
+    0.45 apart for nodes of diameter 0.5) to the same depth, and the two states stay close for the few ticks before the
+    reference's own chain instability (module docstring) takes over."""
+    a = pb.Solver(**scenes.S2_OPTIONS); b = pb.Solver(**scenes.S2_OPTIONS)
+    for s in (a, b):
+        scenes.build_rope(s, n=1500, shape="spiral", pinned=False)
+    b.setTuning(pbdColourBatches=True)
+    start = _max_overlap(a.positions)
+    assert start > 0.05
+    for _ in range(3):
+        a.tick(); b.tick()
+    pa, pbb = a.positions, b.positions
+    assert np.isfinite(pbb).all() and b.stats().collisionProjections > 0
+    oa, ob = _max_overlap(pa), _max_overlap(pbb)
+    assert ob <= max(1.5 * oa, 0.02) and ob < start, (start, oa, ob)
+    assert np.abs(pa - pbb).max() <= 0.05 * bbox_diag(pa)
+
+
+def test_pbd_colour_batched_rope_at_config2_size(pb):
+    """Config 2 at full size with active self-collisions (100 000-node flat coil, neighbouring arms overlapping): the
+    ordered executor's dependency chain is the whole visit list here (seconds per tick), the colour batches run it in
+    milliseconds.  Finite, overlaps resolved, links near rest length."""
+    import time
+    s = pb.Solver(**scenes.S2_OPTIONS)
+    n = scenes.build_rope(s, n=100000, shape="spiral", pinned=False)
+    s.setTuning(pbdColourBatches=True)
+    start = _max_overlap(s.positions[:4000])
+    t0 = time.time()
+    for _ in range(3):
+        s.tick()
+    per_tick = (time.time() - t0) / 3
+    p = s.positions
+    assert np.isfinite(p).all() and not s.simFailed
+    assert _max_overlap(p[:4000]) < start
+    d = np.linalg.norm(p[1:] - p[:-1], axis=1)
+    assert np.median(np.abs(d - 0.5)) < 0.05
+    assert s.stats().collisionProjections > n
+    assert per_tick < 2.0, per_tick
