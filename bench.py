@@ -163,6 +163,19 @@ def run_other(args, local_rank):
         s.tick()
     for _ in range(args.preroll + max(args.warmup, 3)):
         tick()
+    # The reference's PBD is unstable on chains (its distance projection moves only node 0 of a link: a self-overlapping rope
+    # diverges within ~15-25 ticks IN THE REFERENCE, tests/test_pbd_gpu.py), so the rope is put back to this state every six
+    # ticks; the 3.6 MB upload is inside the timed region.
+    reset = None
+    if args.workload == "s2":
+        reset = [torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy() for _ in range(3)]
+        reset[0][:] = s.positions; reset[1][:] = s.prevPositions; reset[2][:] = s.velocities
+        plain_tick = tick
+
+        def tick():
+            if tick_no[0] % 6 == 5:
+                s.setState(reset[0], reset[1], reset[2])
+            plain_tick()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     proj = launches = 0
     contacts = 0
@@ -255,7 +268,7 @@ def main():
                 print(json.dumps({"impl": args.impl, "unavailable": "workloads s2 / s4 run our arm on one GPU only"}))
             return 0
         if args.preroll is None or args.preroll in (60, 70):
-            args.preroll = 20
+            args.preroll = 2 if args.workload == "s2" else 20
         return run_other(args, local_rank)
     if args.workload == "s5":
         config = {"workload": "S5: %d x TetGen cube body (16 546 tets, 4 518 nodes, 6 912 boundary triangles each; one committed mesh "

@@ -286,6 +286,9 @@ int pies_b200_probe_volume_projection(uint32_t n, const float* pos, const float*
                                       float maxOmega, float* out);
 /* pointTriangleCCD (reference CollisionDetection.cpp:227-302): in 18 floats per query. */
 int pies_b200_probe_ccd(uint32_t n, const float* in18, float threshold, int32_t* hit, float* t);
+/* edgeEdgeCCD (reference CollisionDetection.cpp:304-418; never emitted by the reference's tick):
+ * in 18 floats per query (ab0 ac0 ad0 ab1 ac1 ad1). */
+int pies_b200_probe_edge_ccd(uint32_t n, const float* in18, int32_t* hit, float* t);
 /* TriCompRange / NodeCompRange (reference Solver.cpp:942-979, :877-901). */
 int pies_b200_probe_tri_range(uint32_t n, const float* pos9, const float* prev9, int64_t* mins, uint32_t* lens);
 int pies_b200_probe_node_range(uint32_t n, const float* pos3, const float* radius, float gridScale,

@@ -480,6 +480,15 @@ void pref_probe_ccd(uint32_t n, const float* in, float threshold, int32_t* hit, 
     t[i] = r ? *r : -1.0f;
   }
 }
+// edgeEdgeCCD (CollisionDetection.cpp:304-418); in = n*18 floats (ab0 ac0 ad0 ab1 ac1 ad1)
+void pref_probe_edge_ccd(uint32_t n, const float* in, int32_t* hit, float* t) {
+  for (uint32_t i = 0; i < n; ++i) {
+    const float* p = in + 18 * i;
+    std::optional<float> r = CollisionDetection::edgeEdgeCCD(V3(p), V3(p + 3), V3(p + 6), V3(p + 9), V3(p + 12), V3(p + 15));
+    hit[i] = r ? 1 : 0;
+    t[i] = r ? *r : -1.0f;
+  }
+}
 // Cell ranges: NodeCompRange (Solver.cpp:877-901) / TriCompRange (:942-979) / sweptTriRange
 // (:639-677, re-derived here through TriCompRange + the 20-cell cap because it is file-static).
 void pref_probe_node_range(uint32_t n, const float* pos, const float* radius, float gridScale,

@@ -103,6 +103,7 @@ def lib():
             "pref_probe_bend_angle": (None, [C.c_uint32, _f32p, _f32p]),
             "pref_probe_distance": (None, [C.c_uint32, _f32p, _f32p, _f32p]),
             "pref_probe_ccd": (None, [C.c_uint32, _f32p, C.c_float, _i32p, _f32p]),
+            "pref_probe_edge_ccd": (None, [C.c_uint32, _f32p, _i32p, _f32p]),
             "pref_probe_node_range": (None, [C.c_uint32, _f32p, _f32p, C.c_float, _i64p, _u32p]),
             "pref_probe_tri_range": (None, [C.c_uint32, _f32p, _f32p, _i64p, _u32p]),
             "pref_tri_occupancy_build": (C.c_uint64, [vp, C.POINTER(C.c_uint64)]),

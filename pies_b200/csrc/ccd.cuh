@@ -158,6 +158,64 @@ __device__ __forceinline__ bool pointTriangleCCD(V3 ap0, V3 ab0, V3 ac0, V3 ap1,
   return true;
 }
 
+// edgeEdgeCCD (CollisionDetection.cpp:304-418): edge (a, b) against edge (c, d), everything relative to a, positions
+// at the start (0) and end (1) of the substep.  The reference never emits edge contacts (its only call site is commented
+// out, Solver.cpp:799-823); the restatement exists so that the narrow phase is complete and checked, and it
+// reproduces the reference's behaviour INCLUDING its shadowing bug: in the non-parallel case the closest-point parameters
+// u, v are assigned to block-local variables and the outer ones stay 0, so the static proximity test is |c1 - a1| < 0.5.
+__device__ __forceinline__ float mix1(float x, float y, float a) { return add(mul(x, sub(1.0f, a)), mul(y, a)); }  // glm::mix
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+__device__ __forceinline__ bool edgeEdgeCCD(V3 ab0, V3 ac0, V3 ad0, V3 ab1, V3 ac1, V3 ad1, float& tOut) {
+  {
+    V3 cd1 = sub(ad1, ac1);
+    float abMagSq = dot3(ab1, ab1), cdMagSq = dot3(cd1, cd1), abDotCd = dot3(ab1, cd1);
+    float det = add(mul(abMagSq, -cdMagSq), mul(abDotCd, abDotCd));
+    float u = 0.0f, v = 0.0f;
+    if (det != 0.0f) {
+      // u, v of this branch are shadowed in the reference (:326-328): the outer ones keep 0
+    } else {
+      float u0 = 0.0f, u1 = 1.0f;
+      float v0 = dot3(ac1, ab1), v1 = dot3(ad1, ab1);
+      bool flip0 = false, flip1 = false;   // u0 > u1 never holds
+      if (v0 > v1) { float t = v0; v0 = v1; v1 = t; flip1 = true; }
+      if (u0 >= v1) {
+        u = flip0 ? 1.0f : 0.0f; v = flip1 ? 0.0f : 1.0f;
+      } else if (v0 >= u1) {
+        u = flip0 ? 0.0f : 1.0f; v = flip1 ? 1.0f : 0.0f;
+      } else {
+        float mid = (u0 > v0) ? mul(add(u0, v1), 0.5f) : mul(add(v0, u1), 0.5f);
+        u = (u0 == u1) ? 0.5f : div(sub(mid, u0), sub(u1, u0));
+        v = (v0 == v1) ? 0.5f : div(sub(mid, v0), sub(v1, v0));
+      }
+    }
+    u = clamp01(u); v = clamp01(v);
+    V3 q0 = V3{mix1(0.0f, ab1.x, u), mix1(0.0f, ab1.y, u), mix1(0.0f, ab1.z, u)};
+    V3 q1 = V3{mix1(ac1.x, ad1.x, v), mix1(ac1.y, ad1.y, v), mix1(ac1.z, ad1.z, v)};
+    V3 n = sub(q0, q1);
+    float dist = __fsqrt_rn(dot3(n, n));
+    if (dist < 0.5f) { tOut = 1.0f; return true; }
+  }
+  V3 abd = sub(ab1, ab0), acd = sub(ac1, ac0), add_ = sub(ad1, ad0);
+  Cubic e{0.0f, 0.0f, 0.0f, 0.0f};
+  expandTerm(ab0.x, ac0.y, ad0.z, abd.x, acd.y, add_.z, e);
+  expandTerm(-ab0.x, ad0.y, ac0.z, -abd.x, add_.y, acd.z, e);
+  expandTerm(-ac0.x, ab0.y, ad0.z, -acd.x, abd.y, add_.z, e);
+  expandTerm(ac0.x, ad0.y, ab0.z, acd.x, add_.y, abd.z, e);
+  expandTerm(ad0.x, ab0.y, ac0.z, add_.x, abd.y, acd.z, e);
+  expandTerm(-ad0.x, ac0.y, ab0.z, -add_.x, acd.y, abd.z, e);
+  float t;
+  if (!findRootInInterval(e, t)) return false;
+  V3 abt = add(ab0, scale(abd, t)), act = add(ac0, scale(acd, t)), adt = add(ad0, scale(add_, t));
+  V3 cdt = sub(adt, act);
+  V3 nt = norm3(cross3(abt, cdt));
+  float ux, uy;
+  barycentric(abt, V3{-cdt.x, -cdt.y, -cdt.z}, nt, act, ux, uy);   // inverse(mat3(abt, -cdt, nt)) * act
+  if (ux < 0.0f || ux > 1.0f || uy < 0.0f || uy > 1.0f) return false;
+  tOut = t;
+  return true;
+}
+
 // TriCompRange / sweptTriRange (Solver.cpp:942-979, :639-677): swept AABB in WORLD units
 // (gridSpacing is ignored by the reference); a side longer than `cap` cells gives
 // the empty range.  Returns false if the range is empty.

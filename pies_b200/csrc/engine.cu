@@ -391,7 +391,7 @@ PdViews pdViews(PiesB200Solver* s) {
   v.sh = ClusterElems{s->shapeOff.p, s->shapeIds.p, (uint32_t)s->scene.shapeW.size(), (uint32_t)s->scene.shapeId.size()};
   v.go = ClusterElems{s->goalOff.p, s->goalIds.p, (uint32_t)s->scene.goalW.size(), (uint32_t)s->scene.goalId.size()};
   v.A = CsrMatrix{s->rowPtr.p, s->col.p, s->val.p, s->n, (uint64_t)y.col.size(), s->sellPtr.p, s->sellRow.p, s->sellCol.p,
-                  s->sellVal.p, (uint32_t)(y.sellPtr.empty() ? 0 : y.sellPtr.size() - 1)};
+                  s->sellVal.p, (uint32_t)(y.sellPtr.empty() ? 0 : y.sellPtr.size() - 1), (uint64_t)y.sellVal.size()};
   v.pw.r = s->pr.p; v.pw.p = s->pp.p; v.pw.p2 = s->pp2.p; v.pw.z = s->pz.p; v.pw.ap = s->pap.p; v.pw.delta = s->pdelta.p;
   v.pw.partials = s->partials.p; v.pw.scalars = s->scalars.p; v.pw.flag = s->flag.p;
   if (s->blocks) {  // the contact-aware blocks of the current substep (reblock.cu)

@@ -42,6 +42,7 @@ struct CsrMatrix {
   // lane at sellPtr[s] + 32 k + lane
   uint32_t* sellPtr = nullptr; uint32_t* sellRow = nullptr; int* sellCol = nullptr; float* sellVal = nullptr;
   uint32_t nSlices = 0;
+  uint64_t sellEntries = 0;  // padded entries of the SELL copy (picks the mat-vec's tile variant)
 };
 
 // Per-substep collision lists in the reference's canonical order.

@@ -256,13 +256,17 @@ __global__ void k_pcg_check(float* __restrict__ scalars, int* __restrict__ flag,
 // CSR order: S entries, collision entries, collision diagonal.
 constexpr int kWinRows = 256;    // == HostSystem::kSellWindow
 constexpr int kWinSlices = kWinRows / 32;
-constexpr int kWinTile = 2432;   // staged S entries per window (27-node bodies: 2 336 with padding); the rest is read from global
+// Staged S entries per window, two variants: 2 432 (27-node box bodies: 2 336 entries per window with padding; three CTAs
+// per SM) and 4 096 (TetGen meshes: ~15 entries per row, 3 900 per window; two CTAs per SM).  Entries past the tile are
+// read straight from global memory by a per-lane serial loop, which is what made the mat-vec of config 5 slow (r02e: 37 %
+// of its entries took that path with the small tile).
+constexpr int kWinTileSmall = 2432, kWinTileBig = 4096;
 constexpr int kWinCTile = 512;   // staged collision entries per window (two per thread)
-constexpr int kSpmvCtasPerSm = 3;
 constexpr int kWinDescs = 64;    // windows of one CTA described per round (more: the pipeline drains and restarts)
 
 // one staging buffer; everything the window's rows need except p / ap
-struct SpmvBuf {
+template <int kWinTile>
+struct SpmvBufT {
   float4 z[kWinRows];
   int col[kWinTile]; float val[kWinTile];
   int ccol[kWinCTile]; float cval[kWinCTile];
@@ -271,8 +275,7 @@ struct SpmvBuf {
   float cDiag[kWinRows];
   uint32_t sellPtr[kWinSlices + 4];
 };
-constexpr size_t kSpmvSmem = 2 * sizeof(SpmvBuf);
-static_assert(sizeof(SpmvBuf) % 16 == 0, "buffer halves stay 16 B aligned");
+static_assert(sizeof(SpmvBufT<kWinTileSmall>) % 16 == 0 && sizeof(SpmvBufT<kWinTileBig>) % 16 == 0, "buffer halves stay 16 B aligned");
 
 struct SpmvWindow { uint32_t base, cnt; int cbase, ccnt; uint32_t win, pad; };  // S entries [base, base + cnt), collision entries [cbase, cbase + ccnt)
 
@@ -286,7 +289,8 @@ __device__ __forceinline__ void cpAsync4(void* smemDst, const void* gmemSrc) {
 // One commit group with everything of window `wdw`: S entries (16 B granules: slices are 128 B aligned), collision
 // entries (4 B: a CSR slice starts anywhere), z / sellRow / cDiag / cPtr of its rows, its slice offsets.  No register
 // ever depends on the copied words, so nothing waits before the matching cp.async.wait_group.
-__device__ __forceinline__ void stageWindow(SpmvBuf& b, const CsrMatrix& A, const ContactLists& c,
+template <int kWinTile>
+__device__ __forceinline__ void stageWindow(SpmvBufT<kWinTile>& b, const CsrMatrix& A, const ContactLists& c,
                                             const float4* __restrict__ z, const SpmvWindow& m, uint32_t wdw) {
   const uint32_t t = threadIdx.x;
   const uint32_t cnt = min(m.cnt, (uint32_t)kWinTile);
@@ -312,9 +316,11 @@ __device__ __forceinline__ void stageWindow(SpmvBuf& b, const CsrMatrix& A, cons
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+template <int kWinTile, int kSpmvCtasPerSm>
 __global__ void __launch_bounds__(kThreads, kSpmvCtasPerSm) k_pcg_spmv(CsrMatrix A, ContactLists c, PcgWork w,
                                                                        float* __restrict__ partials, int parity, int first,
                                                                        float tol2) {
+  using SpmvBuf = SpmvBufT<kWinTile>;
   extern __shared__ __align__(16) unsigned char spmvSmem[];
   __shared__ float smem[128];
   __shared__ float sPz[kWinCTile];  // z-products of the window's collision entries (x- and y-products reuse the staged slots)
@@ -569,18 +575,23 @@ int launchPcgInit(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, con
 
 // One CG iteration = two kernels.  `it` = iteration index within the solve.
 int launchPcgSpmv(cudaStream_t s, const CsrMatrix& A, const ContactLists& c, const PcgWork& w, float tol, int it) {
-  // > 48 KB of dynamic shared memory needs the opt-in (a per-device function attribute: renewed once per solve)
-  if (it == 0) cudaFuncSetAttribute(k_pcg_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmem);
   const uint32_t nWin = (A.n + kWinRows - 1) / kWinRows;
-  const int grid = (int)std::min<uint32_t>(nWin, (uint32_t)(kNumSMs * kSpmvCtasPerSm));  // fixed per topology => fixed-order reduction
-  if (grid <= 0) return 0;
+  if (!nWin) return 0;
+  // tile variant by the matrix's average padded entries per window (fixed per topology, like the grid)
+  const bool big = A.sellEntries / nWin > (uint64_t)(kWinTileSmall * 9 / 10);
+  const size_t smem = big ? 2 * sizeof(SpmvBufT<kWinTileBig>) : 2 * sizeof(SpmvBufT<kWinTileSmall>);
+  const int ctas = big ? 2 : 3;
+  auto kernel = big ? k_pcg_spmv<kWinTileBig, 2> : k_pcg_spmv<kWinTileSmall, 3>;
+  // > 48 KB of dynamic shared memory needs the opt-in (a per-device function attribute: renewed once per solve)
+  if (it == 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = (int)std::min<uint32_t>(nWin, (uint32_t)(kNumSMs * ctas));  // fixed per topology => fixed-order reduction
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSpmvSmem; cfg.stream = s;
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, k_pcg_spmv, A, c, w, w.partials, it & 1, it == 0 ? 1 : 0, tol * tol);
+  cudaLaunchKernelEx(&cfg, kernel, A, c, w, w.partials, it & 1, it == 0 ? 1 : 0, tol * tol);
   return 1;
 }
 
@@ -618,7 +629,8 @@ void preloadPcgKernels() {
   cudaFuncGetAttributes(&a, k_pcg_finish);
   cudaFuncGetAttributes(&a, k_pcg_start);
   cudaFuncGetAttributes(&a, k_pcg_check);
-  cudaFuncGetAttributes(&a, k_pcg_spmv);
+  cudaFuncGetAttributes(&a, k_pcg_spmv<kWinTileSmall, 3>);
+  cudaFuncGetAttributes(&a, k_pcg_spmv<kWinTileBig, 2>);
   cudaFuncGetAttributes(&a, k_pcg_update);
 }
 

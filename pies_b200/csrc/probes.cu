@@ -40,6 +40,17 @@ __global__ void k_probe_ccd(uint32_t n, const float* __restrict__ in, float thre
   t[i] = h ? tt : -1.0f;
 }
 
+__global__ void k_probe_edge_ccd(uint32_t n, const float* __restrict__ in, int32_t* __restrict__ hit, float* __restrict__ t) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = in + 18ull * i;
+  float tt = -1.0f;
+  bool h = ex::edgeEdgeCCD(v3(p[0], p[1], p[2]), v3(p[3], p[4], p[5]), v3(p[6], p[7], p[8]), v3(p[9], p[10], p[11]),
+                           v3(p[12], p[13], p[14]), v3(p[15], p[16], p[17]), tt);
+  hit[i] = h ? 1 : 0;
+  t[i] = h ? tt : -1.0f;
+}
+
 __global__ void k_probe_tri_range(uint32_t n, const float* __restrict__ pos, const float* __restrict__ prev,
                                   long long* __restrict__ mins, uint32_t* __restrict__ lens) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,6 +122,18 @@ int pies_b200_probe_ccd(uint32_t n, const float* in, float threshold, int32_t* h
   float* din = sc.dev<float>(18ull * n, in); int32_t* dh = sc.dev<int32_t>(n); float* dt = sc.dev<float>(n);
   if (!din || !dh || !dt) return PIES_B200_ECUDA;
   k_probe_ccd<<<(n + 127) / 128, 128>>>(n, din, threshold, dh, dt);
+  if (finish()) return PIES_B200_ECUDA;
+  cudaMemcpy(hit, dh, 4ull * n, cudaMemcpyDeviceToHost);
+  cudaMemcpy(t, dt, 4ull * n, cudaMemcpyDeviceToHost);
+  return PIES_B200_OK;
+}
+int pies_b200_probe_edge_ccd(uint32_t n, const float* in, int32_t* hit, float* t) {
+  if (!haveDevice()) return PIES_B200_ENODEV;
+  if (!n) return PIES_B200_OK;
+  Scratch sc;
+  float* din = sc.dev<float>(18ull * n, in); int32_t* dh = sc.dev<int32_t>(n); float* dt = sc.dev<float>(n);
+  if (!din || !dh || !dt) return PIES_B200_ECUDA;
+  k_probe_edge_ccd<<<(n + 127) / 128, 128>>>(n, din, dh, dt);
   if (finish()) return PIES_B200_ECUDA;
   cudaMemcpy(hit, dh, 4ull * n, cudaMemcpyDeviceToHost);
   cudaMemcpy(t, dt, 4ull * n, cudaMemcpyDeviceToHost);

@@ -143,6 +143,7 @@ _SIGNATURES = {
     "pies_b200_probe_tet_projection": (C.c_int, [C.c_uint32, _f32p, _f32p, C.c_float, C.c_float, _f32p]),
     "pies_b200_probe_volume_projection": (C.c_int, [C.c_uint32, _f32p, _f32p, C.c_float, C.c_float, _f32p]),
     "pies_b200_probe_ccd": (C.c_int, [C.c_uint32, _f32p, C.c_float, _i32p, _f32p]),
+    "pies_b200_probe_edge_ccd": (C.c_int, [C.c_uint32, _f32p, _i32p, _f32p]),
     "pies_b200_probe_tri_range": (C.c_int, [C.c_uint32, _f32p, _f32p, _i64p, _u32p]),
     "pies_b200_probe_node_range": (C.c_int, [C.c_uint32, _f32p, _f32p, C.c_float, _i64p, _u32p]),
     "pies_b200_probe_sort_pairs": (C.c_int, [C.c_uint64, _u64p, _u32p, C.c_int]),
@@ -558,6 +559,13 @@ def probe_ccd(queries, threshold):
     q = np.ascontiguousarray(queries, np.float32).reshape(-1, 18)
     hit = np.empty(len(q), np.int32); t = np.empty(len(q), np.float32)
     _ckp(lib().pies_b200_probe_ccd(len(q), q, threshold, hit, t))
+    return hit, t
+
+
+def probe_edge_ccd(queries):
+    q = np.ascontiguousarray(queries, np.float32).reshape(-1, 18)
+    hit = np.empty(len(q), np.int32); t = np.empty(len(q), np.float32)
+    _ckp(lib().pies_b200_probe_edge_ccd(len(q), q, hit, t))
     return hit, t
 
 

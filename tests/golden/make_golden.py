@@ -87,7 +87,34 @@ def ccd_and_ranges():
     rad[:8] = 200.0                                        # over the 50-cell cap
     nm = np.empty((n, 3), np.int64); nl = np.empty((n, 3), np.uint32)
     lib().pref_probe_node_range(n, pn, rad, 2.0, nm, nl)
-    save("ccd", queries=q, hit=hit, t=t)
+    # edgeEdgeCCD (dead code in the reference's tick): edges (a,b) x (c,d) relative to a; far apart at the end
+    # of the step (its static test fires below 0.5), crossing, parallel (the det == 0 branch) and degenerate ones
+    me = 6000
+    qe = rng.normal(scale=1.5, size=(me, 18)).astype(np.float32)
+    qe[:, 9:] = qe[:, :9] + 0.6 * rng.normal(size=(me, 9)).astype(np.float32)
+    qe[:1500, 9:] *= 0.2                                   # end state close together: static proximity hits
+    # c-d exactly parallel to a-b at the end state (det == 0: the only way into the reference's interval branch), c a
+    # quarter unit off the line so that overlapping ranges are static hits.  Exactly parallel at t = 1 also means coplanar
+    # at t = 1, i.e. a root of the cubic exactly at the END of the interval: when the static test does not fire, hit or
+    # miss hinges on whether the root finder lands on 1 - ulp or 1 + ulp, so those queries are excluded from the
+    # comparison (edge_compare = 0); the ones the static test decides are kept.
+    par = slice(1500, 2000)
+    qe[par, 9:12] = np.array([2.0, 0.0, 0.0], np.float32)
+    cx = rng.choice([-3.0, -1.0, 0.5, 1.0, 3.0], size=500).astype(np.float32)
+    qe[par, 12:15] = np.stack([cx, np.full(500, 0.25, np.float32), np.full(500, 0.125, np.float32)], axis=1)
+    qe[par, 15:18] = qe[par, 12:15] + np.array([1.0, 0.0, 0.0], np.float32) * rng.choice([-2.0, 0.5, 1.0, 4.0], size=(500, 1)).astype(np.float32)
+    qe[2000:2020, :] = 0.0
+    ehit = np.empty(me, np.int32); et = np.empty(me, np.float32)
+    lib().pref_probe_edge_ccd(me, qe, ehit, et)
+    compare = np.ones(me, np.int32)
+    compare[1500:2000] = ((ehit[1500:2000] == 1) & (et[1500:2000] == 1.0)).astype(np.int32)
+    # a hit at exactly t = 1 in that slice is either the static test or the boundary root; keep only those the static test
+    # explains: the closest points of the two parallel segments are at most sqrt(0.25^2 + 0.125^2) = 0.28 < 0.5 apart
+    # when their ranges along the line overlap, further than 0.5 otherwise
+    lo = np.minimum(qe[par, 12], qe[par, 15]); hi = np.maximum(qe[par, 12], qe[par, 15])
+    overlap = (hi >= 0.0) & (lo <= 2.0)
+    compare[1500:2000] &= overlap.astype(np.int32)
+    save("ccd", queries=q, hit=hit, t=t, edge_queries=qe, edge_hit=ehit, edge_t=et, edge_compare=compare)
     save("ranges", tri_pos=p, tri_prev=o, tri_min=tm, tri_len=tl, node_pos=pn, node_radius=rad, node_min=nm, node_len=nl)
 
 

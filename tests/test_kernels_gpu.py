@@ -67,6 +67,22 @@ def test_ccd_decisions_bit_exact(pb):
     assert np.abs(t[both] - g["t"][both]).max() < 1e-5
 
 
+def test_edge_edge_ccd_decisions_bit_exact(pb):
+    """edgeEdgeCCD (reference CollisionDetection.cpp:304-418, never emitted by the reference's tick: SURVEY F13) restated
+    with the reference's shadowing bug; hit/miss bit-exact on 6 000 fixture queries (static hits, crossings, parallel
+    edges, degenerate input), t to 1e-5 where the cubic is solved."""
+    g = golden("ccd")
+    hit, t = pb.probe_edge_ccd(g["edge_queries"])
+    keep = g["edge_compare"] == 1      # all but the exactly-parallel queries whose outcome is a root at the interval's end
+    assert keep.sum() > 5500 and keep[1500:2000].sum() > 20
+    assert (hit[keep] == g["edge_hit"][keep]).all(), np.flatnonzero(keep & (hit != g["edge_hit"]))[:10]
+    both = keep & (hit == 1)
+    assert both.sum() > 200 and (hit == 0).sum() > 200
+    moving = both & (g["edge_t"] != 1.0)
+    assert moving.sum() > 20
+    assert np.abs(t[both] - g["edge_t"][both]).max() < 1e-5
+
+
 def test_cell_ranges_bit_exact(pb):
     g = golden("ranges")
     mins, lens = pb.probe_tri_range(g["tri_pos"], g["tri_prev"])
