@@ -545,22 +545,35 @@ static int clusterGrid(uint32_t clusterBound) {
   return (int)std::min<uint32_t>(kNumSMs * 8, (clusterBound + kThreads / 32 - 1) / (kThreads / 32));
 }
 
+// side stream + events of the concurrent mid-cluster sweeps, created at first use; false = run everything on s
+static bool sideStream(ContactWork& w) {
+  if (w.side) return true;
+  if (cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking) != cudaSuccess) { w.side = nullptr; cudaGetLastError(); return false; }
+  if (cudaEventCreateWithFlags(&w.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&w.join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+  return true;
+}
+
 int launchStabilize(cudaStream_t s, ContactWork& w, const ContactLists& c, uint32_t n, float4* q, float4* prev,
                     const float4* snap, float thickness, uint32_t iterations) {
   int L = 0;
   if (!iterations) return 0;
   const uint8_t* cls = (c.nTri && w.haveClusters) ? w.gsClass : nullptr;
   if (cls) {
-    // small clusters: all sweeps (and their floor snaps) in one launch
-    k_gs_cluster_stabilize<<<clusterGrid(w.clusterBound), kThreads, 0, s>>>(w.view, q, prev, snap, c.floorMult, c.nFloor ? 1 : 0,
-                                                                           thickness, iterations); ++L;
     // how many mid / large clusters this substep has was copied to the host right after they were formed
     if (w.countsReady) cudaEventSynchronize(w.countsReady);
     const uint32_t nMid = w.hostCounts ? w.hostCounts[0] : 0u, nLarge = w.hostCounts ? w.hostCounts[1] : 1u;
-    if (nMid) {
-      k_gs_mid<true><<<(int)std::min<uint32_t>(nMid, kNumSMs * kMidCtasPerSm), kMidThreads, 0, s>>>(
+    const bool aside = nMid && sideStream(w);
+    if (aside) { cudaEventRecord(w.fork, s); cudaStreamWaitEvent(w.side, w.fork, 0); }
+    if (nMid) {  // mid-size clusters: one CTA each, on the side stream, beside the small clusters below
+      k_gs_mid<true><<<(int)std::min<uint32_t>(nMid, kNumSMs * kMidCtasPerSm), kMidThreads, 0, aside ? w.side : s>>>(
           w.view, w.nMidDev, c.ticket, q, prev, snap, c.floorMult, c.nFloor ? 1 : 0, thickness, 0.0f, iterations); ++L;
+      if (aside) cudaEventRecord(w.join, w.side);
     }
+    // small clusters: all sweeps (and their floor snaps) in one launch
+    k_gs_cluster_stabilize<<<clusterGrid(w.clusterBound), kThreads, 0, s>>>(w.view, q, prev, snap, c.floorMult, c.nFloor ? 1 : 0,
+                                                                           thickness, iterations); ++L;
+    if (aside) cudaStreamWaitEvent(s, w.join, 0);
     // large clusters: dataflow sweeps, floor snap of their nodes after each one
     for (uint32_t it = 0; nLarge && it < iterations; ++it) {
       L += launchSweep(s, w, c, n, StabilizeOp{q, prev, thickness});
@@ -576,13 +589,17 @@ int launchFriction(cudaStream_t s, ContactWork& w, const ContactLists& c, uint32
                    float friction, float staticThreshold) {
   int L = 0;
   if (c.nTri && w.haveClusters) {
-    k_gs_cluster_friction<<<clusterGrid(w.clusterBound), kThreads, 0, s>>>(w.view, q, vel, friction, staticThreshold); ++L;
     if (w.countsReady) cudaEventSynchronize(w.countsReady);
     const uint32_t nMid = w.hostCounts ? w.hostCounts[0] : 0u, nLarge = w.hostCounts ? w.hostCounts[1] : 1u;
+    const bool aside = nMid && sideStream(w);
+    if (aside) { cudaEventRecord(w.fork, s); cudaStreamWaitEvent(w.side, w.fork, 0); }
     if (nMid) {
-      k_gs_mid<false><<<(int)std::min<uint32_t>(nMid, kNumSMs * kMidCtasPerSm), kMidThreads, 0, s>>>(
+      k_gs_mid<false><<<(int)std::min<uint32_t>(nMid, kNumSMs * kMidCtasPerSm), kMidThreads, 0, aside ? w.side : s>>>(
           w.view, w.nMidDev, c.ticket, const_cast<float4*>(q), vel, nullptr, nullptr, 0, friction, staticThreshold, 1u); ++L;
+      if (aside) cudaEventRecord(w.join, w.side);
     }
+    k_gs_cluster_friction<<<clusterGrid(w.clusterBound), kThreads, 0, s>>>(w.view, q, vel, friction, staticThreshold); ++L;
+    if (aside) cudaStreamWaitEvent(s, w.join, 0);
     if (nLarge) L += launchSweep(s, w, c, n, FrictionOp{q, vel, friction, staticThreshold});
   }
   if (c.nFloor) { k_floor_friction<<<gridFor(n, kThreads), kThreads, 0, s>>>(n, c.floorMult, vel, friction, staticThreshold); ++L; }

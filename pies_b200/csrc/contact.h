@@ -43,6 +43,15 @@ struct ContactWork {
   cudaEvent_t countsReady = nullptr;
   uint32_t nTri = 0, sweepsUsed = 0, clusterBound = 0;
   bool haveClusters = false;
+  // the one-CTA-per-cluster sweeps of the mid-size clusters run beside the warp-per-cluster sweeps of the small ones
+  // (disjoint clusters, hence disjoint nodes): a handful of long-running CTAs next to thousands of short warps
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  ~ContactWork() {
+    if (fork) cudaEventDestroy(fork);
+    if (join) cudaEventDestroy(join);
+    if (side) cudaStreamDestroy(side);
+  }
 };
 
 // Once per substep, after detection: resets the chunk counters of the ordered sweeps.

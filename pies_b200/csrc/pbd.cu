@@ -561,8 +561,10 @@ __global__ void __launch_bounds__(kThreads) k_pbd_color_commit(uint32_t nP, cons
       atomicMax(stat + 1, (uint32_t)c + 1u);
       return;
     }
-    color[p] = 0xfffffffeu;  // left out: reported, the pass then falls back to the ordered executor
-    atomicAdd(stat + 2, 1u);
+    // all 64 colours taken at its nodes (a node overlapping dozens of others: a collapsed scene): the pair gets a colour
+    // of its own after the regular ones; the host gives up beyond 256 of them
+    const uint32_t extra = atomicAdd(stat + 2, 1u);
+    color[p] = 64u + extra;
     return;
   }
   atomicAdd(stat, 1u);  // still uncoloured after this round
@@ -774,9 +776,15 @@ static int collideNodes(PiesB200Solver* s, PbdWork& w) {
           PCHECK(cudaStreamSynchronize(st));
           left = (uint32_t)w.host[12]; colors = (uint32_t)w.host[13]; leftOut = (uint32_t)w.host[14];
         }
-        fallBack = left != 0 || leftOut != 0;   // a node with more than 64 distinct partners: the ordered executor takes the pass
+        if (left != 0 || leftOut > 256) {
+          // never silently fall back to the ordered executor here: on the scenes this mode exists for it would not return
+          s->simFailed = true;
+          return fail(s, PIES_B200_ERANGE, "PBD colour batches: the contact graph could not be coloured (a node overlaps more than 64 others: the scene has collapsed)");
+        }
+        if (leftOut) colors = 64u + leftOut;
         if (!fallBack) {
           for (uint32_t c = 0; c < colors; ++c) {
+            if (c >= (uint32_t)w.host[13] && c < 64u) continue;   // unused regular colours below the private ones
             k_pbd_apply_color<<<gridFor(nP, kThreads), kThreads, 0, st>>>(nP, c, w.pairs.p, w.pairColor.p, s->q.p, s->prev.p, w.q0.p,
                                                                          delta, w.flags.p);
             ++s->launches;
