@@ -474,6 +474,7 @@ def main():
     halo_ok = drv.check_halo(repartition=False) if drv is not None else True   # every contact partner still inside the ghost layer
 
     # ---- end-to-end run: same ticks, host buffers in and out every step ----
+    s.getVertices(copy=False)        # untimed: the first call page-locks the host mirror (once per topology)
     s.setState(snap[0], snap[1], snap[2])
     hp, hv, hq = snap
     e2e_proj = 0

@@ -523,6 +523,132 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
   }
 }
 
+// Tier 0 without staging: one warp per island that is a single preconditioner block (every free body of a multi-body
+// scene).  The block inverse is then the exact inverse of the island's matrix (contact diagonal included: such blocks are
+// re-inverted by reblock.cu), so the solve is iterative refinement rather than CG:  r = b - A x in fp64 straight from the
+// global CSR (x gathered from L2), z = Minv r, x += z, r -= A z, until the island's residual passes the tolerance — one
+// round in practice, since a round contracts the residual by ~1e-5.  Nothing is staged in shared memory (32 bytes per warp
+// for the block-lane permutation): the vectors live one row per lane and move by shuffles, the matrix rows and the
+// inverse are read where they lie, and with ~60 registers four CTAs of eight warps fit an SM, which is what a kernel
+// bound by dependent global loads needs (r02g: the staged warp tier was long-scoreboard bound at 24 warps per SM).
+__global__ void __launch_bounds__(256, 4) k_island_direct(IslandArgs a, int tier) {
+  __shared__ unsigned char sLaneOf[8][32];
+  const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
+  const uint32_t count = a.counts[1 + tier];
+  const uint4* descs = a.tierDesc + (size_t)tier * a.listStride;
+  const uint32_t stride = gridDim.x * 8u;
+  uint32_t wi = blockIdx.x * 8u + (uint32_t)warp;
+  uint4 descNext = wi < count ? __ldg(descs + wi) : make_uint4(0u, 0u, 0u, 0u);
+  for (; wi < count; wi += stride) {
+    const uint4 desc = descNext;
+    if (wi + stride < count) descNext = __ldg(descs + wi + stride);
+    const uint32_t s0 = desc.y, m = desc.z;
+    const bool act = (uint32_t)lane < m;
+    uint32_t g = 0, sl = 0, bodyBase = 0;
+    int kk0 = 0, kk1 = 0, c0 = 0, c1 = 0;
+    float4 xi = make_float4(0.0f, 0.0f, 0.0f, 0.0f), bi = xi;
+    float cd = 0.0f;
+    if (act) {
+      g = a.order[s0 + lane];
+      kk0 = a.rowPtr[g]; kk1 = a.rowPtr[g + 1];
+      xi = a.x[g]; bi = a.b[g];
+      cd = a.cDiag ? a.cDiag[g] : 0.0f;
+      sl = a.slotOf[g];
+      bodyBase = (uint32_t)lane - a.rankInBody[g];
+      if (a.cPtr) { c0 = a.cPtr[g]; c1 = a.cPtr[g + 1]; }
+    }
+    const int bl = (int)(sl & 31u);
+    // the block's inverse is indexed by block lane: which island lane holds block lane j
+    __syncwarp();
+    if (act) sLaneOf[warp][bl] = (unsigned char)lane;
+    __syncwarp();
+    const uint32_t blk = __shfl_sync(0xffffffffu, sl, 0) >> 5;
+    const uint2 meta = __ldg(a.blockMeta + blk);
+    const float* inv = a.blockInv + meta.x;
+    const int mB = (int)meta.y;
+    // ---- start residual, fp64 accumulation, x gathered where it lies
+    double y0 = (double)cd * (double)xi.x, y1 = (double)cd * (double)xi.y, y2 = (double)cd * (double)xi.z;
+    for (int kk = kk0; kk < kk1; kk += 4) {   // four entries per batch: their loads are in flight together
+      int cc[4]; float vv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (kk + j < kk1) { cc[j] = __ldg(a.col + kk + j); vv[j] = __ldg(a.val + kk + j); }
+      float4 xv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (kk + j < kk1) xv[j] = a.x[cc[j]];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (kk + j < kk1) { y0 += (double)vv[j] * (double)xv[j].x; y1 += (double)vv[j] * (double)xv[j].y; y2 += (double)vv[j] * (double)xv[j].z; }
+    }
+    for (int kk = c0; kk < c1; ++kk) {
+      const float v = a.cVal[kk];
+      const float4 xv = a.x[a.cCol[kk]];
+      y0 += (double)v * (double)xv.x; y1 += (double)v * (double)xv.y; y2 += (double)v * (double)xv.z;
+    }
+    float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+    if (act) { r0 = (float)((double)bi.x - y0); r1 = (float)((double)bi.y - y1); r2 = (float)((double)bi.z - y2); }
+    const float bb0 = warpSum(bi.x * bi.x), bb1 = warpSum(bi.y * bi.y), bb2 = warpSum(bi.z * bi.z);
+    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+    uint32_t iters = 0;
+    bool conv = false;
+    float rr0, rr1, rr2;
+    const int maxLen = __reduce_max_sync(0xffffffffu, (kk1 - kk0) + (c1 - c0));
+    while (true) {
+      rr0 = warpSum(r0 * r0); rr1 = warpSum(r1 * r1); rr2 = warpSum(r2 * r2);
+      conv = rr0 <= a.tol2 * bb0 + 1e-36f && rr1 <= a.tol2 * bb1 + 1e-36f && rr2 <= a.tol2 * bb2 + 1e-36f;
+      if (conv || iters >= a.maxIter) break;
+      // z = Minv r: lane with block lane bl owns row bl of the packed lower triangle
+      float z0 = 0.0f, z1 = 0.0f, z2 = 0.0f;
+      {
+        int off = bl * (bl + 1) / 2;
+#pragma unroll 4
+        for (int j = 0; j < mB; ++j) {
+          const float w = act ? __ldg(inv + off) : 0.0f;
+          const int src = (int)sLaneOf[warp][j];
+          const float q0 = __shfl_sync(0xffffffffu, r0, src), q1 = __shfl_sync(0xffffffffu, r1, src), q2 = __shfl_sync(0xffffffffu, r2, src);
+          z0 = fmaf(w, q0, z0); z1 = fmaf(w, q1, z1); z2 = fmaf(w, q2, z2);
+          off += j < bl ? 1 : j + 1;
+        }
+      }
+      d0 += z0; d1 += z1; d2 += z2;
+      // r -= A z: z moves by shuffles (column -> island lane through the host's rank table / the island permutation)
+      float w0 = cd * z0, w1 = cd * z1, w2 = cd * z2;
+      for (int k = 0; k < maxLen; ++k) {
+        float v = 0.0f;
+        int src = lane;
+        const int ks = kk0 + k;
+        if (ks < kk1) {
+          const uint32_t rk = __ldg(a.colRank + ks);
+          if (rk != 0xffffffffu) { v = __ldg(a.val + ks); src = (int)(bodyBase + rk); }
+        } else if (c0 + (ks - kk1) < c1) {
+          const int kc = c0 + (ks - kk1);
+          v = a.cVal[kc]; src = (int)(__ldg(a.pos + a.cCol[kc]) - s0);
+        }
+        const float q0 = __shfl_sync(0xffffffffu, z0, src), q1 = __shfl_sync(0xffffffffu, z1, src), q2 = __shfl_sync(0xffffffffu, z2, src);
+        w0 = fmaf(v, q0, w0); w1 = fmaf(v, q1, w1); w2 = fmaf(v, q2, w2);
+      }
+      r0 -= w0; r1 -= w1; r2 -= w2;
+      ++iters;
+    }
+    if (act) {
+      float4 xo = a.x[g];   // re-read (L1) instead of keeping it live through the loop
+      xo.x += d0; xo.y += d1; xo.z += d2;
+      a.x[g] = xo;
+    }
+    if (lane == 0) {
+      atomicMax(a.stats, iters);
+      atomicAdd(a.stats + 1, iters);
+      if (!conv) {
+        float rel = 0.0f;
+        if (bb0 > 0.0f) rel = fmaxf(rel, rr0 / bb0);
+        if (bb1 > 0.0f) rel = fmaxf(rel, rr1 / bb1);
+        if (bb2 > 0.0f) rel = fmaxf(rel, rr2 / bb2);
+        atomicAdd(a.stats + 2, 1u);
+        atomicMax(a.stats + 3, __float_as_uint(sqrtf(rel)));
+      }
+    }
+  }
+}
+
 // Tier 3: islands of up to a few thousand nodes (a tetrahedralised body of config 5; several toppled columns of the S3
 // stack).  One 1024-thread CTA per island; r and p (what other rows gather) live in shared memory, per-row state that only
 // its own thread touches (delta, A p, z) in global scratch in island order, the matrix in an island-local copy in global
@@ -847,7 +973,9 @@ int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const C
   if (w.tierCount[0]) {
     cudaStream_t st0 = s;
     if (warpAside) { cudaStreamWaitEvent(w.aux[0], w.fork, 0); st0 = w.aux[0]; }
-    launchTier(k_island_pcg<32, 1, true>, 0, (int)std::min<uint32_t>((w.tierCount[0] + 7) / 8, 3 * kNumSMs), st0, a);
+    static const bool staged = std::getenv("PIES_B200_WARP_TIER_STAGED") != nullptr;   // A/B switch: the staged PCG variant
+    if (staged) launchTier(k_island_pcg<32, 1, true>, 0, (int)std::min<uint32_t>((w.tierCount[0] + 7) / 8, 3 * kNumSMs), st0, a);
+    else k_island_direct<<<(int)std::min<uint32_t>((w.tierCount[0] + 7) / 8, 4 * kNumSMs), 256, 0, st0>>>(a, 0);
     ++L;
     if (warpAside) { cudaEventRecord(w.join[0], w.aux[0]); cudaStreamWaitEvent(s, w.join[0], 0); }
   }
@@ -876,6 +1004,7 @@ void preloadIslandKernels() {
   cudaFuncGetAttributes(&a, k_island_pcg<320, 2, true>);
   cudaFuncGetAttributes(&a, k_island_pcg<512, 2, true>);
   cudaFuncGetAttributes(&a, k_island_pcg_big);
+  cudaFuncGetAttributes(&a, k_island_direct);
 }
 
 }  // namespace pies
