@@ -8,9 +8,9 @@
 //      (sweptTriRange == TriCompRange except for the 20-cell cap), visiting its cells in key
 //      order (= the reference's (dx,dy,dz) order) and each cell's members in ascending index
 //      (= bucket order), three corners per candidate;
-//   4. two passes (count, scan in the reference's canonical thread-striped triangle order,
-//      write) so the output lists are in the reference's order with its multiplicities
-//       without atomics.
+//   4. hits counted per (triangle, cell) slot of the reference's canonical thread-striped triangle
+//      order, scanned, then written, so the output lists are in the reference's order with its
+//      multiplicities.
 // A conservative swept-AABB cull (margin = threshold + slop) skips candidates that cannot
 // pass pointTriangleCCD; it never changes the result.
 #include "detect.h"
@@ -156,11 +156,17 @@ __global__ void __launch_bounds__(kThreads) k_cell_starts(uint64_t nPairs, const
 // for this triangle — but only with the cheap tests: shared node, then swept corner box against the other
 // triangle's swept box (conservative: a pair that fails it cannot pass pointTriangleCCD).  Neighbouring
 // threads sit in the same cell, so the member loop reads the same records in every lane (broadcast) while
-// each lane keeps its own triangle in registers.  Candidates of pair (t, k-th cell of t) are counted into
-// slot rankOff[rank(t)] + k, i.e. directly in the reference's output order (thread-striped triangle order,
-// cells in (dx,dy,dz) order, members ascending, corners 0..2); after a scan the same kernel writes them.
-// 4b. CCD: one thread per candidate (point, triangle): the expensive swept test runs exactly once per
-// candidate, fully convergent, and a scan of the hit flags compacts the survivors in the same order.
+// each lane keeps its own triangle in registers.  The member loop runs ONCE: it counts the pair's candidates
+// and remembers which members produced any (a 64-bit mask; cells with more members redo the loop), the warp
+// reserves one contiguous chunk of the candidate buffer for all its pairs, and every thread writes its run
+// there.  The chunk order is arbitrary; the runs are found again through pairRun[j].
+// 4b. CCD: one thread per candidate (point, triangle), in the cell-sorted order of the candidate buffer
+// (neighbouring candidates share nodes and triangles): the expensive swept test runs exactly once per
+// candidate, fully convergent.
+// 4c. hits in the reference's order: the hits of pair (t, k-th cell of t) are counted into slot
+// rankOff[rank(t)] + k (thread-striped triangle order, cells in (dx,dy,dz) order); after a scan over the
+// slots the same kernel writes them (members ascending, corners 0..2 inside a run) — the output lists come
+// out in the reference's order with its multiplicities without atomics on the ordering path.
 struct NarrowParams {
   uint32_t nTri, threadCount;
   float threshold;
@@ -168,7 +174,6 @@ struct NarrowParams {
   const uint32_t* order;
 };
 
-template <bool WRITE>
 __global__ void __launch_bounds__(kThreads) k_pair_filter(NarrowParams np, KeyPack kp, uint64_t nPairs,
                                                           const uint64_t* __restrict__ keys,
                                                           const uint32_t* __restrict__ memberTri,
@@ -178,76 +183,116 @@ __global__ void __launch_bounds__(kThreads) k_pair_filter(NarrowParams np, KeyPa
                                                           const float4* __restrict__ aabbLo, const float4* __restrict__ aabbHi,
                                                           const float4* __restrict__ q, const float4* __restrict__ prev,
                                                           const uint32_t* __restrict__ rankOff,
-                                                          uint32_t* __restrict__ candCount /* canonical slots; scanned when WRITE */,
-                                                          uint2* __restrict__ cand, uint32_t candCap, int* __restrict__ failFlag) {
-  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nPairs) return;
-  uint32_t t = memberTri[j];
-  uint4 rec = triRec[t];
-  uint32_t lx = rec.w & 255u, ly = (rec.w >> 8) & 255u, lz = (rec.w >> 16) & 255u;
-  // slot of (t, this cell) in the canonical order
-  uint64_t key = keys[j];
-  int4 mn = triMin[t];
-  uint32_t dz = (uint32_t)((int)(key & ((1ull << kp.bitsZ) - 1ull)) + kp.minZ - mn.z);
-  uint32_t dy = (uint32_t)((int)((key >> kp.bitsZ) & ((1ull << kp.bitsY) - 1ull)) + kp.minY - mn.y);
-  uint32_t dx = (uint32_t)((int)(key >> (kp.bitsY + kp.bitsZ)) + kp.minX - mn.x);
-  uint32_t slot = rankOff[canonicalRank(t, np.nTri, np.threadCount, np.order)] + (dx * ly + dy) * lz + dz;
-  if (!WRITE && j == 0) candCount[nPairs] = 0;
-  if (lx > 20u || ly > 20u || lz > 20u) {  // sweptTriRange cap: inserted but queries nothing
-    if (!WRITE) candCount[slot] = 0;
-    return;
-  }
-  uint32_t cidx = cellIdx[j];
-  uint32_t s = cellStart[cidx], e = cellStart[cidx + 1];
-  if (e - s > 1000u) atomicExch(failFlag, 1);  // hang guard, Solver.cpp:751-755
-  uint32_t ia[3] = {rec.x, rec.y, rec.z};
+                                                          uint2* __restrict__ pairRun /* (first candidate, count) */,
+                                                          uint32_t* __restrict__ pairSlot /* canonical slot */,
+                                                          uint2* __restrict__ cand, uint32_t candCap,
+                                                          uint32_t* __restrict__ candTotal, int* __restrict__ failFlag) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = j < nPairs;
+  uint32_t total = 0, s = 0, e = 0, slot = 0;
+  uint64_t mask = 0;
+  uint32_t ia[3] = {0, 0, 0};
   float cLo[3][3], cHi[3][3];
+  if (live) {
+    uint32_t t = memberTri[j];
+    uint4 rec = triRec[t];
+    uint32_t lx = rec.w & 255u, ly = (rec.w >> 8) & 255u, lz = (rec.w >> 16) & 255u;
+    // slot of (t, this cell) in the canonical order
+    uint64_t key = keys[j];
+    int4 mn = triMin[t];
+    uint32_t dz = (uint32_t)((int)(key & ((1ull << kp.bitsZ) - 1ull)) + kp.minZ - mn.z);
+    uint32_t dy = (uint32_t)((int)((key >> kp.bitsZ) & ((1ull << kp.bitsY) - 1ull)) + kp.minY - mn.y);
+    uint32_t dx = (uint32_t)((int)(key >> (kp.bitsY + kp.bitsZ)) + kp.minX - mn.x);
+    slot = rankOff[canonicalRank(t, np.nTri, np.threadCount, np.order)] + (dx * ly + dy) * lz + dz;
+    if (lx <= 20u && ly <= 20u && lz <= 20u) {  // sweptTriRange cap: beyond it the triangle is inserted but queries nothing
+      uint32_t cidx = cellIdx[j];
+      s = cellStart[cidx]; e = cellStart[cidx + 1];
+      if (e - s > 1000u) atomicExch(failFlag, 1);  // hang guard, Solver.cpp:751-755
+      ia[0] = rec.x; ia[1] = rec.y; ia[2] = rec.z;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    float4 p = q[ia[i]], o = prev[ia[i]];
-    cLo[i][0] = fminf(p.x, o.x) - np.cullMargin; cHi[i][0] = fmaxf(p.x, o.x) + np.cullMargin;
-    cLo[i][1] = fminf(p.y, o.y) - np.cullMargin; cHi[i][1] = fmaxf(p.y, o.y) + np.cullMargin;
-    cLo[i][2] = fminf(p.z, o.z) - np.cullMargin; cHi[i][2] = fmaxf(p.z, o.z) + np.cullMargin;
-  }
-  // union of the three corner boxes: one test rejects most members
-  float uLo[3], uHi[3];
+      for (int i = 0; i < 3; ++i) {
+        float4 p = q[ia[i]], o = prev[ia[i]];
+        cLo[i][0] = fminf(p.x, o.x) - np.cullMargin; cHi[i][0] = fmaxf(p.x, o.x) + np.cullMargin;
+        cLo[i][1] = fminf(p.y, o.y) - np.cullMargin; cHi[i][1] = fmaxf(p.y, o.y) + np.cullMargin;
+        cLo[i][2] = fminf(p.z, o.z) - np.cullMargin; cHi[i][2] = fmaxf(p.z, o.z) + np.cullMargin;
+      }
+      // union of the three corner boxes: one test rejects most members
+      float uLo[3], uHi[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    uLo[c] = fminf(cLo[0][c], fminf(cLo[1][c], cLo[2][c]));
-    uHi[c] = fmaxf(cHi[0][c], fmaxf(cHi[1][c], cHi[2][c]));
+      for (int c = 0; c < 3; ++c) {
+        uLo[c] = fminf(cLo[0][c], fminf(cLo[1][c], cLo[2][c]));
+        uHi[c] = fmaxf(cHi[0][c], fmaxf(cHi[1][c], cHi[2][c]));
+      }
+      uint32_t oNext = memberTri[s];
+      for (uint32_t m = s; m < e; ++m) {
+        const uint32_t o = oNext;
+        if (m + 1 < e) oNext = memberTri[m + 1];
+        const uint4 ro = triRec[o];
+        const float4 lo = aabbLo[o], hi = aabbHi[o];  // issued with the record: the three loads only depend on o
+        bool common = false;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) common |= (ia[i] == ro.x) | (ia[i] == ro.y) | (ia[i] == ro.z);
+        if (common) continue;
+        if (!(uLo[0] <= hi.x && uHi[0] >= lo.x && uLo[1] <= hi.y && uHi[1] >= lo.y && uLo[2] <= hi.z && uHi[2] >= lo.z)) continue;
+        uint32_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          c += (cLo[i][0] <= hi.x && cHi[i][0] >= lo.x && cLo[i][1] <= hi.y && cHi[i][1] >= lo.y && cLo[i][2] <= hi.z &&
+                cHi[i][2] >= lo.z) ? 1u : 0u;
+        if (c) { total += c; if (m - s < 64u) mask |= 1ull << (m - s); }
+      }
+    }
   }
-  uint32_t outPos = WRITE ? candCount[slot] : 0u;
-  uint32_t total = 0;
+  // exclusive scan of the totals over the warp, one reservation per warp (no CTA barrier: the member loops of a CTA's
+  // warps differ widely in length)
+  const int lane = threadIdx.x & 31;
+  uint32_t inc = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+  uint32_t chunkBase = 0;
+  if (lane == 31 && inc) chunkBase = atomicAdd(candTotal, inc);
+  chunkBase = __shfl_sync(0xffffffffu, chunkBase, 31);
+  if (!live) return;
+  uint32_t pos = chunkBase + inc - total;
+  pairRun[j] = make_uint2(pos, total);
+  pairSlot[j] = slot;
+  if (!total) return;
+  const bool wide = e - s > 64u;
   for (uint32_t m = s; m < e; ++m) {
+    if (!wide) {
+      if (!mask) break;
+      uint32_t b = (uint32_t)__ffsll((long long)mask) - 1u;
+      mask &= mask - 1ull;
+      m = s + b;
+    }
     uint32_t o = memberTri[m];
-    uint4 ro = triRec[o];
-    bool common = false;
+    if (wide) {
+      uint4 ro = triRec[o];
+      bool common = false;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) common |= (ia[i] == ro.x) | (ia[i] == ro.y) | (ia[i] == ro.z);
-    if (common) continue;
+      for (int i = 0; i < 3; ++i) common |= (ia[i] == ro.x) | (ia[i] == ro.y) | (ia[i] == ro.z);
+      if (common) continue;
+    }
     float4 lo = aabbLo[o], hi = aabbHi[o];
-    if (!(uLo[0] <= hi.x && uHi[0] >= lo.x && uLo[1] <= hi.y && uHi[1] >= lo.y && uLo[2] <= hi.z && uHi[2] >= lo.z)) continue;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       bool ov = cLo[i][0] <= hi.x && cHi[i][0] >= lo.x && cLo[i][1] <= hi.y && cHi[i][1] >= lo.y &&
                 cLo[i][2] <= hi.z && cHi[i][2] >= lo.z;
       if (ov) {
-        if (WRITE && outPos + total < candCap) cand[outPos + total] = make_uint2(ia[i], o);
-        ++total;
+        if (pos < candCap) cand[pos] = make_uint2(ia[i], o);
+        ++pos;
       }
     }
   }
-  if (!WRITE) candCount[slot] = total;
 }
 
 __global__ void __launch_bounds__(128) k_ccd(const uint32_t* __restrict__ nCandPtr, uint32_t candCap,
                                              const uint2* __restrict__ cand, const uint4* __restrict__ triRec,
                                              const float4* __restrict__ q, const float4* __restrict__ prev,
-                                             float threshold, uint32_t* __restrict__ hit) {
+                                             float threshold, uint8_t* __restrict__ hit) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t nCand = min(*nCandPtr, candCap);
-  if (k > nCand) return;
-  if (k == nCand) { hit[k] = 0; return; }
+  if (k >= nCand) return;
   uint2 cd = cand[k];
   uint4 ro = triRec[cd.y];
   V3 pa = v3(q[cd.x]), oa = v3(prev[cd.x]);
@@ -256,38 +301,152 @@ __global__ void __launch_bounds__(128) k_ccd(const uint32_t* __restrict__ nCandP
   float tt;
   bool h = ex::pointTriangleCCD(ex::sub(oa, ob), ex::sub(oc, ob), ex::sub(od, ob), ex::sub(pa, pb), ex::sub(pc, pb),
                                 ex::sub(pd, pb), threshold, tt);
-  hit[k] = h ? 1u : 0u;
+  hit[k] = h ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(kThreads) k_compact_hits(const uint32_t* __restrict__ nCandPtr, uint32_t candCap,
-                                                           const uint2* __restrict__ cand, const uint4* __restrict__ triRec,
-                                                           const uint32_t* __restrict__ hitScan, uint4* __restrict__ outTri,
-                                                           uint32_t* __restrict__ outOther) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t nCand = min(*nCandPtr, candCap);
-  if (k >= nCand) return;
-  uint32_t pos = hitScan[k];
-  if (hitScan[k + 1] == pos) return;
-  uint2 cd = cand[k];
-  uint4 ro = triRec[cd.y];
-  outTri[pos] = make_uint4(cd.x, ro.x, ro.y, ro.z);
-  outOther[pos] = cd.y;
+// WRITE == false: hits of every pair into its canonical slot; WRITE == true (after the scan over the slots): the hits
+// themselves, in run order.
+template <bool WRITE>
+__global__ void __launch_bounds__(kThreads) k_pair_hits(uint64_t nPairs, const uint2* __restrict__ pairRun,
+                                                        const uint32_t* __restrict__ pairSlot, uint32_t candCap,
+                                                        const uint8_t* __restrict__ hit, uint32_t* __restrict__ hitCount,
+                                                        const uint2* __restrict__ cand, const uint4* __restrict__ triRec,
+                                                        uint4* __restrict__ outTri, uint32_t* __restrict__ outOther) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nPairs) return;
+  if (!WRITE && j == 0) hitCount[nPairs] = 0;
+  const uint2 run = pairRun[j];
+  const uint32_t slot = pairSlot[j];
+  const uint32_t end = min(run.x + run.y, candCap);
+  if (!WRITE) {
+    uint32_t c = 0;
+    for (uint32_t k = run.x; k < end; ++k) c += hit[k];
+    hitCount[slot] = c;
+  } else {
+    uint32_t pos = hitCount[slot];
+    if (hitCount[slot + 1] == pos) return;
+    for (uint32_t k = run.x; k < end; ++k) {
+      if (!hit[k]) continue;
+      uint2 cd = cand[k];
+      uint4 ro = triRec[cd.y];
+      outTri[pos] = make_uint4(cd.x, ro.x, ro.y, ro.z);
+      outOther[pos] = cd.y;
+      ++pos;
+    }
+  }
 }
 
 // ---- 5. node -> incident entries --------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_inc_emit(uint32_t nTriC, const uint4* __restrict__ entries,
-                                                       uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                       uint32_t* __restrict__ incCount) {
+// A counting sort by node: every (entry, slot) item takes an arrival number from its node's counter, the counters are
+// scanned into the CSR offsets and the items are placed at offset + arrival (arbitrary order inside a node).  Whatever
+// needs the node's list in ascending order then ranks the item inside its (short) list — one thread per item, the list
+// read from L1.  The result equals a stable sort by node of the items in index order, without radix passes.
+__device__ __forceinline__ uint32_t comp(const uint4& v, uint32_t s) { return s == 0u ? v.x : (s == 1u ? v.y : (s == 2u ? v.z : v.w)); }
+
+__global__ void __launch_bounds__(kThreads) k_inc_count(uint32_t nEntries, const uint32_t* __restrict__ nEntriesDev,
+                                                        const uint4* __restrict__ entries, uint32_t* __restrict__ incCount,
+                                                        uint32_t* __restrict__ arrival) {
   uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nTriC) return;
+  if (e >= nEntries || (nEntriesDev && e >= *nEntriesDev)) return;
+  uint4 v = entries[e];
+  uint32_t ids[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int s = 0; s < 4; ++s) arrival[4ull * e + s] = atomicAdd(incCount + ids[s], 1u);
+}
+
+// pointTri (optional): the triangle of the entry for its point item (slot 0), ~0 for the corner items
+__global__ void __launch_bounds__(kThreads) k_inc_place(uint32_t nEntries, const uint32_t* __restrict__ nEntriesDev,
+                                                        const uint4* __restrict__ entries, const uint32_t* __restrict__ incPtr,
+                                                        const uint32_t* __restrict__ arrival, uint32_t* __restrict__ placed,
+                                                        const uint32_t* __restrict__ otherTri, uint32_t* __restrict__ pointTri) {
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nEntries || (nEntriesDev && e >= *nEntriesDev)) return;
   uint4 v = entries[e];
   uint32_t ids[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
-    keys[4ull * e + s] = ids[s];
-    vals[4ull * e + s] = 4u * e + s;
-    atomicAdd(incCount + ids[s], 1u);
+    const uint32_t at = incPtr[ids[s]] + arrival[4ull * e + s];
+    placed[at] = 4u * e + s;
+    if (pointTri) pointTri[at] = s == 0 ? otherTri[e] : 0xffffffffu;
   }
+}
+
+// One thread per item of the FULL contact list (every copy):
+//  * ticket = its position in the node's list ordered by entry — the ordered Gauss-Seidel sweeps (contact.cu) run an
+//    entry once each of its four nodes has seen `ticket` earlier entries;
+//  * distinct contacts: the reference's list holds the same (point, triangle) once per shared cell and per triangle the
+//    point is a corner of; the ordered sweeps need every copy, but the collision MATRIX and the right-hand
+//    side only need each distinct contact with its multiplicity.  Among a node's point items the first copy of each
+//    triangle is the head: it keeps the number of copies and counts into uCount[node].
+__global__ void __launch_bounds__(kThreads) k_item_contacts(uint64_t nInc, const uint4* __restrict__ entries,
+                                                            const uint32_t* __restrict__ incPtr,
+                                                            const uint32_t* __restrict__ placed,
+                                                            const uint32_t* __restrict__ pointTri, uint32_t* __restrict__ ticket,
+                                                            uint32_t* __restrict__ headTri, uint32_t* __restrict__ uMult,
+                                                            uint32_t* __restrict__ uCount) {
+  const uint64_t at = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (at >= nInc) return;
+  const uint32_t v = placed[at];
+  const uint32_t node = comp(entries[v >> 2], v & 3u);
+  const uint32_t b = incPtr[node], k = incPtr[node + 1] - b;
+  const uint32_t tri = pointTri[at];
+  uint32_t rank = 0, mult = 0, earlier = 0;
+  if (tri == 0xffffffffu) {
+    for (uint32_t j = 0; j < k; ++j) rank += placed[b + j] < v ? 1u : 0u;
+  } else {
+    for (uint32_t j = 0; j < k; ++j) {
+      const uint32_t vj = placed[b + j];
+      const bool same = pointTri[b + j] == tri, less = vj < v;
+      rank += less ? 1u : 0u;
+      mult += same ? 1u : 0u;
+      earlier += same && less ? 1u : 0u;
+    }
+  }
+  ticket[v] = rank;
+  const bool head = tri != 0xffffffffu && earlier == 0u;
+  headTri[at] = head ? tri : 0xffffffffu;
+  uMult[at] = mult;
+  if (head) atomicAdd(uCount + node, 1u);
+}
+
+// Distinct contacts in (point, triangle) order with their weights (a head's rank among its node's heads = number of
+// smaller triangles), and the arrival numbers for THEIR incidence table.
+__global__ void __launch_bounds__(kThreads) k_uniq_write(uint64_t nInc, const uint32_t* __restrict__ placed,
+                                                         const uint32_t* __restrict__ headTri,
+                                                         const uint32_t* __restrict__ uMult,
+                                                         const uint32_t* __restrict__ incPtr,
+                                                         const uint32_t* __restrict__ uStart /* scanned uCount */,
+                                                         const uint4* __restrict__ entries, uint4* __restrict__ uTri,
+                                                         float* __restrict__ uW, uint32_t* __restrict__ uIncCount,
+                                                         uint32_t* __restrict__ uArrival) {
+  const uint64_t at = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (at >= nInc) return;
+  const uint32_t tri = headTri[at];
+  if (tri == 0xffffffffu) return;
+  const uint4 e = entries[placed[at] >> 2];
+  const uint32_t b = incPtr[e.x], k = incPtr[e.x + 1] - b;
+  uint32_t r = 0;
+  for (uint32_t j = 0; j < k; ++j) r += headTri[b + j] < tri ? 1u : 0u;
+  const uint32_t u = uStart[e.x] + r;
+  uTri[u] = e;
+  uW[u] = 10000.0f * (float)uMult[at];  // copies * PointTriangleCollisionConstraint::w (exact in fp32)
+  uint32_t ids[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+  for (int s = 0; s < 4; ++s) uArrival[4ull * u + s] = atomicAdd(uIncCount + ids[s], 1u);
+}
+
+// One thread per placed item: to its rank inside the node's list (ascending values).
+__global__ void __launch_bounds__(kThreads) k_item_sort(uint64_t nItemsBound, const uint32_t* __restrict__ nEntriesDev,
+                                                        const uint4* __restrict__ entries, const uint32_t* __restrict__ ptr,
+                                                        const uint32_t* __restrict__ placed, uint32_t* __restrict__ sorted) {
+  const uint64_t at = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (at >= nItemsBound || at >= 4ull * *nEntriesDev) return;
+  const uint32_t v = placed[at];
+  const uint32_t node = comp(entries[v >> 2], v & 3u);
+  const uint32_t b = ptr[node], k = ptr[node + 1] - b;
+  uint32_t rank = 0;
+  for (uint32_t j = 0; j < k; ++j) rank += placed[b + j] < v ? 1u : 0u;
+  sorted[b + rank] = v;
 }
 
 __global__ void __launch_bounds__(kThreads) k_floor_mult(uint32_t nFloor, const uint32_t* __restrict__ nodes,
@@ -303,31 +462,6 @@ __global__ void __launch_bounds__(kThreads) k_floor_weight(uint32_t n, const uin
   float acc = 0.0f;
   for (uint32_t k = 0; k < mult[i]; ++k) acc += 10000.0f;  // StaticCollisionConstraint::w, coeffRef += per duplicate
   w[i] = acc;
-}
-
-// ---- 6. unique contacts ---------------------------------------------------------------------
-// The reference's list holds the same (point, triangle) once per shared cell and per triangle the
-// point is a corner of; the ordered sweeps need every copy, but the collision MATRIX and
-// the right-hand side only need each distinct contact with its multiplicity (weight = copies * w).
-__global__ void __launch_bounds__(kThreads) k_uniq_keys(uint32_t nHit, const uint4* __restrict__ entries,
-                                                        const uint32_t* __restrict__ other, int bitsTri,
-                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nHit) return;
-  keys[e] = ((uint64_t)entries[e].x << bitsTri) | (uint64_t)other[e];
-  vals[e] = e;
-}
-
-__global__ void __launch_bounds__(kThreads) k_uniq_gather(const uint32_t* __restrict__ nUniquePtr,
-                                                          const uint32_t* __restrict__ start,
-                                                          const uint32_t* __restrict__ sortedEntry,
-                                                          const uint4* __restrict__ entries, uint4* __restrict__ uTri,
-                                                          float* __restrict__ uW) {
-  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= *nUniquePtr) return;
-  uint32_t j = start[u];
-  uTri[u] = entries[sortedEntry[j]];
-  uW[u] = 10000.0f * (float)(start[u + 1] - j);  // copies * PointTriangleCollisionConstraint::w (exact in fp32)
 }
 
 // ---- 7. the collision matrix in streamable form ----------------------------------------------------
@@ -374,17 +508,6 @@ __global__ void __launch_bounds__(kThreads) k_ccsr_fill(uint32_t n, const uint32
   cDiag[i] = diag;
 }
 
-// ticket of every (entry, slot): its position in the node's ordered incidence list.  The ordered
-// Gauss-Seidel sweeps (contact.cu) run an entry once each of its four nodes has seen `ticket` earlier entries.
-__global__ void __launch_bounds__(kThreads) k_inc_tickets(uint64_t nInc, const uint64_t* __restrict__ sortedNode,
-                                                          const uint32_t* __restrict__ inc,
-                                                          const uint32_t* __restrict__ incPtr,
-                                                          uint32_t* __restrict__ ticket) {
-  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nInc) return;
-  ticket[inc[k]] = (uint32_t)k - incPtr[(uint32_t)sortedNode[k]];
-}
-
 __global__ void k_init_bbox(int* bbox) {
   bbox[0] = bbox[1] = bbox[2] = 0x7fffffff;
   bbox[3] = bbox[4] = bbox[5] = (int)0x80000000;
@@ -409,7 +532,7 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
   const uint32_t T = in.threadCount ? in.threadCount : 1u;
   const float floorLimit = in.floorLimit;
   out.nTri = out.nFloor = 0;
-  w.nPairs = 0; w.nCells = 0; w.failed = false; w.badInput = false;
+  w.nPairs = 0; w.nCells = 0; w.nUnique = 0; w.failed = false; w.badInput = false;
   DCHECK(w.incPtr.reserve(n + 2));
   DCHECK(w.floorMult.reserve(n + 1));
   DCHECK(w.floorW.reserve(n + 1));
@@ -419,7 +542,7 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
   DCHECK(w.triMin.reserve(nTri)); DCHECK(w.triRec.reserve(nTri)); DCHECK(w.cnt.reserve(nTri + 2));
   DCHECK(w.cntRank.reserve(nTri + 2)); DCHECK(w.floorRank.reserve(nTri + 2));
   DCHECK(w.aabbLo.reserve(nTri)); DCHECK(w.aabbHi.reserve(nTri));
-  DCHECK(w.bbox.reserve(8));
+  DCHECK(w.bbox.reserve(12));
   DCHECK(w.scanScratch.reserve(scanScratchElems(std::max<uint64_t>(nTri + 2, w.scanCap))));
   k_init_bbox<<<1, 1, 0, s>>>(w.bbox.p); ++L;
   DCHECK(cudaMemsetAsync(w.cnt.p + nTri, 0, 2 * sizeof(uint32_t), s));
@@ -461,45 +584,40 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
     L += launchExclusiveScan(s, w.heads.p, nPairs + 1, w.scanScratch.p);
     DCHECK(cudaMemcpyAsync(w.host + 9, w.heads.p + nPairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     k_cell_starts<<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(nPairs, w.keys.p, w.heads.p, w.cellStart.p); ++L;
-    // candidate filter: count, scan, write (capacity from the previous substep; redone if it overflows)
-    k_pair_filter<false><<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p,
-                                                                       w.cellStart.p, w.triRec.p, w.triMin.p, w.aabbLo.p,
-                                                                       w.aabbHi.p, in.q, in.prev, w.cntRank.p, w.hitCount.p,
-                                                                       nullptr, 0, w.bbox.p + 7); ++L;
-    L += launchExclusiveScan(s, w.hitCount.p, nPairs + 1, w.scanScratch.p);
-    uint32_t nCand = 0;
+    // candidate filter (one pass, capacity from the previous substep; redone if it overflows), CCD, hits per slot, scan
+    DCHECK(w.pairRun.reserve(nPairs)); DCHECK(w.pairSlot.reserve(nPairs));
+    uint32_t nCand = 0, cap = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-      uint32_t cap = std::max<uint32_t>(w.candCap, 1u << 16);
-      DCHECK(w.cand.reserve(cap)); DCHECK(w.candHit.reserve((size_t)cap + 2));
-      w.scanCap = std::max<uint64_t>(w.scanCap, (uint64_t)cap + 2);
-      DCHECK(w.scanScratch.reserve(scanScratchElems(w.scanCap)));
-      k_pair_filter<true><<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p,
-                                                                        w.cellStart.p, w.triRec.p, w.triMin.p, w.aabbLo.p,
-                                                                        w.aabbHi.p, in.q, in.prev, w.cntRank.p, w.hitCount.p,
-                                                                        w.cand.p, cap, w.bbox.p + 7); ++L;
-      k_ccd<<<gridFor((uint64_t)cap + 1, 128), 128, 0, s>>>(w.hitCount.p + nPairs, cap, w.cand.p, w.triRec.p, in.q, in.prev,
-                                                          in.threshold, w.candHit.p); ++L;
-      // the scan runs over the capacity; flags past the candidate count are never read
-      DCHECK(cudaMemcpyAsync(w.host + 14, w.hitCount.p + nPairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      cap = std::max<uint32_t>(w.candCap, 1u << 16);
+      DCHECK(w.cand.reserve(cap)); DCHECK(w.candHit.reserve((size_t)cap + 16));
+      DCHECK(cudaMemsetAsync(w.bbox.p + 8, 0, sizeof(int), s));
+      k_pair_filter<<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p, w.cellStart.p,
+                                                                 w.triRec.p, w.triMin.p, w.aabbLo.p, w.aabbHi.p, in.q, in.prev,
+                                                                 w.cntRank.p, w.pairRun.p, w.pairSlot.p, w.cand.p, cap,
+                                                                 (uint32_t*)(w.bbox.p + 8), w.bbox.p + 7); ++L;
+      k_ccd<<<gridFor(cap, 128), 128, 0, s>>>((const uint32_t*)(w.bbox.p + 8), cap, w.cand.p, w.triRec.p, in.q, in.prev,
+                                             in.threshold, w.candHit.p); ++L;
+      k_pair_hits<false><<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(nPairs, w.pairRun.p, w.pairSlot.p, cap, w.candHit.p,
+                                                                      w.hitCount.p, nullptr, nullptr, nullptr, nullptr); ++L;
+      L += launchExclusiveScan(s, w.hitCount.p, nPairs + 1, w.scanScratch.p);
+      DCHECK(cudaMemcpyAsync(w.host + 14, w.bbox.p + 8, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       DCHECK(cudaMemcpyAsync(w.host + 12, w.bbox.p + 7, sizeof(int), cudaMemcpyDeviceToHost, s));
+      DCHECK(cudaMemcpyAsync(w.host + 10, w.hitCount.p + nPairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       DCHECK(cudaStreamSynchronize(s));
       nCand = (uint32_t)w.host[14];
       if (nCand <= cap) break;
+      if (attempt == 1) { w.lastError = cudaErrorUnknown; return -1; }  // the count cannot change between attempts
       w.candCap = nCand + nCand / 2;  // overflow: the list was truncated, redo with room
     }
     w.candCap = std::max<uint32_t>(w.candCap, nCand + nCand / 4 + 1024);
     w.nCells = (uint32_t)w.host[9];
     if (w.host[12]) { w.failed = true; if (launches) *launches += L; return 0; }
-    if (nCand) {
-      L += launchExclusiveScan(s, w.candHit.p, (uint64_t)nCand + 1, w.scanScratch.p);
-      DCHECK(cudaMemcpyAsync(w.host + 10, w.candHit.p + nCand, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-      DCHECK(cudaStreamSynchronize(s));
-      nHit = (uint32_t)w.host[10];
-    }
+    nHit = (uint32_t)w.host[10];
     DCHECK(w.triList.reserve(nHit + 1)); DCHECK(w.otherTri.reserve(nHit + 1));
     if (nHit) {
-      k_compact_hits<<<gridFor(nCand, kThreads), kThreads, 0, s>>>(w.hitCount.p + nPairs, w.candCap, w.cand.p, w.triRec.p,
-                                                                  w.candHit.p, w.triList.p, w.otherTri.p); ++L;
+      k_pair_hits<true><<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(nPairs, w.pairRun.p, w.pairSlot.p, cap, w.candHit.p,
+                                                                     w.hitCount.p, w.cand.p, w.triRec.p, w.triList.p,
+                                                                     w.otherTri.p); ++L;
     }
   }
   DCHECK(w.floorList.reserve(nFloor + 1));
@@ -510,40 +628,35 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
   out.tri = w.triList.p; out.floorNode = w.floorList.p; out.nTri = nHit; out.nFloor = nFloor;
   // incidence CSR + tickets + floor multiplicities
   if (nHit) {
-    uint64_t nInc = 4ull * nHit;
+    const uint64_t nInc = 4ull * nHit;
     DCHECK(cudaMemsetAsync(w.incPtr.p, 0, (n + 2) * sizeof(uint32_t), s));
-    DCHECK(w.incKeys.reserve(nInc)); DCHECK(w.incTmpKeys.reserve(nInc));
-    DCHECK(w.incVals.reserve(nInc)); DCHECK(w.incTmpVals.reserve(nInc)); DCHECK(w.ticket.reserve(nInc));
-    DCHECK(w.sortHist.reserve(sortHistBytes(nInc) / 4 + 4));
-    w.scanCap = std::max<uint64_t>(w.scanCap, std::max<uint64_t>(nInc, n) + 2);
+    DCHECK(w.arrival.reserve(nInc)); DCHECK(w.placed.reserve(nInc)); DCHECK(w.ticket.reserve(nInc));
+    DCHECK(w.pointTri.reserve(nInc)); DCHECK(w.headTri.reserve(nInc)); DCHECK(w.uMult.reserve(nInc));
+    DCHECK(w.uStart.reserve(n + 2)); DCHECK(w.uIncPtr.reserve(n + 2));
+    DCHECK(w.uTri.reserve(nHit)); DCHECK(w.uW.reserve(nHit)); DCHECK(w.uInc.reserve(nInc));
+    w.scanCap = std::max<uint64_t>(w.scanCap, (uint64_t)n + 2);
     DCHECK(w.scanScratch.reserve(scanScratchElems(w.scanCap)));
-    k_inc_emit<<<gridFor(nHit, kThreads), kThreads, 0, s>>>(nHit, w.triList.p, w.incKeys.p, w.incVals.p, w.incPtr.p); ++L;
+    k_inc_count<<<gridFor(nHit, kThreads), kThreads, 0, s>>>(nHit, nullptr, w.triList.p, w.incPtr.p, w.arrival.p); ++L;
     L += launchExclusiveScan(s, w.incPtr.p, n + 1, w.scanScratch.p);
-    L += launchSortPairs(s, nInc, w.incKeys.p, w.incVals.p, w.incTmpKeys.p, w.incTmpVals.p, w.sortHist.p, bitsFor(n));
-    k_inc_tickets<<<gridFor(nInc, kThreads), kThreads, 0, s>>>(nInc, w.incKeys.p, w.incVals.p, w.incPtr.p, w.ticket.p); ++L;
+    k_inc_place<<<gridFor(nHit, kThreads), kThreads, 0, s>>>(nHit, nullptr, w.triList.p, w.incPtr.p, w.arrival.p, w.placed.p,
+                                                            w.otherTri.p, w.pointTri.p); ++L;
+    DCHECK(cudaMemsetAsync(w.uStart.p, 0, (n + 2) * sizeof(uint32_t), s));
+    k_item_contacts<<<gridFor(nInc, kThreads), kThreads, 0, s>>>(nInc, w.triList.p, w.incPtr.p, w.placed.p, w.pointTri.p,
+                                                                w.ticket.p, w.headTri.p, w.uMult.p, w.uStart.p); ++L;
     out.ticket = reinterpret_cast<uint4*>(w.ticket.p);
-    // distinct contacts with multiplicity (sorted by (point, triangle)), then their node incidence table
-    int bitsTri = bitsFor(nTri);
-    DCHECK(w.uTri.reserve(nHit)); DCHECK(w.uW.reserve(nHit)); DCHECK(w.uStart.reserve(nHit + 2)); DCHECK(w.uHeads.reserve(nHit + 2));
-    k_uniq_keys<<<gridFor(nHit, kThreads), kThreads, 0, s>>>(nHit, w.triList.p, w.otherTri.p, bitsTri, w.incKeys.p, w.incVals.p); ++L;
-    L += launchSortPairs(s, nHit, w.incKeys.p, w.incVals.p, w.incTmpKeys.p, w.incTmpVals.p, w.sortHist.p, bitsFor(n) + bitsTri);
-    k_mark_heads<<<gridFor(nHit + 1, kThreads), kThreads, 0, s>>>(nHit, w.incKeys.p, w.uHeads.p); ++L;
-    L += launchExclusiveScan(s, w.uHeads.p, nHit + 1, w.scanScratch.p);
-    k_cell_starts<<<gridFor(nHit, kThreads), kThreads, 0, s>>>(nHit, w.incKeys.p, w.uHeads.p, w.uStart.p); ++L;
-    // uHeads[nHit] = number of distinct contacts (device); the host needs it for the incidence sort
-    k_uniq_gather<<<gridFor(nHit, kThreads), kThreads, 0, s>>>(w.uHeads.p + nHit, w.uStart.p, w.incVals.p, w.triList.p,
-                                                              w.uTri.p, w.uW.p); ++L;
-    DCHECK(cudaMemcpyAsync(w.host + 13, w.uHeads.p + nHit, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    DCHECK(cudaStreamSynchronize(s));
-    uint32_t nU = (uint32_t)w.host[13];
-    uint64_t nUInc = 4ull * nU;
-    DCHECK(w.uIncPtr.reserve(n + 2)); DCHECK(w.uInc.reserve(nUInc)); DCHECK(w.uIncNode.reserve(nUInc));
+    // distinct contacts with multiplicity (sorted by (point, triangle)), then their node incidence table; the host
+    // only learns their number at the end (everything is sized by the full list)
+    L += launchExclusiveScan(s, w.uStart.p, n + 1, w.scanScratch.p);
+    DCHECK(cudaMemcpyAsync(w.host + 13, w.uStart.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     DCHECK(cudaMemsetAsync(w.uIncPtr.p, 0, (n + 2) * sizeof(uint32_t), s));
-    k_inc_emit<<<gridFor(nU, kThreads), kThreads, 0, s>>>(nU, w.uTri.p, w.uIncNode.p, w.uInc.p, w.uIncPtr.p); ++L;
+    k_uniq_write<<<gridFor(nInc, kThreads), kThreads, 0, s>>>(nInc, w.placed.p, w.headTri.p, w.uMult.p, w.incPtr.p, w.uStart.p,
+                                                             w.triList.p, w.uTri.p, w.uW.p, w.uIncPtr.p, w.arrival.p); ++L;
     L += launchExclusiveScan(s, w.uIncPtr.p, n + 1, w.scanScratch.p);
-    L += launchSortPairs(s, nUInc, w.uIncNode.p, w.uInc.p, w.incTmpKeys.p, w.incTmpVals.p, w.sortHist.p, bitsFor(n));
-    out.uTri = w.uTri.p; out.uW = w.uW.p; out.nUnique = nU; out.incPtr = (int*)w.uIncPtr.p; out.inc = w.uInc.p;
-    w.nUnique = nU; w.nTouched = 0;
+    k_inc_place<<<gridFor(nHit, kThreads), kThreads, 0, s>>>(nHit, w.uStart.p + n, w.uTri.p, w.uIncPtr.p, w.arrival.p,
+                                                            w.placed.p, nullptr, nullptr); ++L;
+    k_item_sort<<<gridFor(nInc, kThreads), kThreads, 0, s>>>(nInc, w.uStart.p + n, w.uTri.p, w.uIncPtr.p, w.placed.p, w.uInc.p); ++L;
+    out.uTri = w.uTri.p; out.uW = w.uW.p; out.incPtr = (int*)w.uIncPtr.p; out.inc = w.uInc.p;
+    w.nTouched = 0;
   }
   if (nFloor || w.floorDirty) {
     DCHECK(cudaMemsetAsync(w.floorMult.p, 0, (n + 1) * sizeof(uint32_t), s));
@@ -553,7 +666,7 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
   }
   if (nHit || nFloor) {
     DCHECK(w.cDiag.reserve(n + 1));
-    const uint32_t nU = nHit ? w.nUnique : 0u;
+    const uint32_t nU = nHit;  // bound: the number of distinct contacts is still on its way to the host
     if (nU) {
       DCHECK(w.cPtr.reserve(n + 2)); DCHECK(w.cCol.reserve(6ull * nU + 4)); DCHECK(w.cVal.reserve(6ull * nU + 4));
       k_ccsr_count<<<gridFor(n + 1, kThreads), kThreads, 0, s>>>(n, w.uIncPtr.p, w.uInc.p, w.cPtr.p); ++L;
@@ -563,6 +676,10 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
                                                          nFloor ? w.floorW.p : nullptr, w.cCol.p, w.cVal.p, w.cDiag.p); ++L;
     out.cDiag = w.cDiag.p;
     if (nU) { out.cPtr = (int*)w.cPtr.p; out.cCol = w.cCol.p; out.cVal = w.cVal.p; }
+  }
+  if (nHit) {
+    DCHECK(cudaStreamSynchronize(s));
+    out.nUnique = w.nUnique = (uint32_t)w.host[13];
   }
   if (launches) *launches += L;
   return 0;
@@ -577,18 +694,19 @@ void preloadDetectKernels() {
   cudaFuncGetAttributes(&a, k_emit_pairs);
   cudaFuncGetAttributes(&a, k_mark_heads);
   cudaFuncGetAttributes(&a, k_cell_starts);
-  cudaFuncGetAttributes(&a, k_pair_filter<false>);
-  cudaFuncGetAttributes(&a, k_pair_filter<true>);
+  cudaFuncGetAttributes(&a, k_pair_filter);
   cudaFuncGetAttributes(&a, k_ccd);
-  cudaFuncGetAttributes(&a, k_compact_hits);
-  cudaFuncGetAttributes(&a, k_inc_emit);
+  cudaFuncGetAttributes(&a, k_pair_hits<false>);
+  cudaFuncGetAttributes(&a, k_pair_hits<true>);
+  cudaFuncGetAttributes(&a, k_inc_count);
+  cudaFuncGetAttributes(&a, k_inc_place);
+  cudaFuncGetAttributes(&a, k_item_contacts);
+  cudaFuncGetAttributes(&a, k_uniq_write);
+  cudaFuncGetAttributes(&a, k_item_sort);
   cudaFuncGetAttributes(&a, k_floor_mult);
   cudaFuncGetAttributes(&a, k_floor_weight);
-  cudaFuncGetAttributes(&a, k_uniq_keys);
-  cudaFuncGetAttributes(&a, k_uniq_gather);
   cudaFuncGetAttributes(&a, k_ccsr_count);
   cudaFuncGetAttributes(&a, k_ccsr_fill);
-  cudaFuncGetAttributes(&a, k_inc_tickets);
   cudaFuncGetAttributes(&a, k_init_bbox);
 }
 

@@ -23,14 +23,16 @@ struct DetectWork {
   DevBuf<uint32_t> cnt, cntRank, floorRank, hitCount, scanScratch;
   DevBuf<float4> aabbLo, aabbHi;
   DevBuf<int> bbox;
-  DevBuf<uint64_t> keys, tmpKeys, incKeys, incTmpKeys;
+  DevBuf<uint64_t> keys, tmpKeys;
   DevBuf<uint32_t> vals /* sorted: member triangle of every (cell, member) pair */, tmpVals, heads, cellStart, sortHist,
-      incVals, incTmpVals, ticket, nodeDone;
+      ticket, nodeDone;
+  // node incidence (counting sort): arrival numbers, placed items, per-item scratch of the distinct-contact ranking
+  DevBuf<uint32_t> arrival, placed, pointTri, headTri, uMult;
   DevBuf<uint4> triList, uTri;     // full list (canonical order) and distinct contacts
-  DevBuf<uint32_t> otherTri, uStart, uHeads, uIncPtr, uInc, candHit;
-  DevBuf<uint2> cand;               // candidate (point node, triangle) pairs of the narrow phase, canonical order
+  DevBuf<uint32_t> otherTri, uStart, uIncPtr, uInc, pairSlot;
+  DevBuf<uint8_t> candHit;
+  DevBuf<uint2> cand, pairRun;      // candidate (point node, triangle) pairs of the narrow phase (cell-sorted chunks) and every pair's run
   uint32_t candCap = 0;
-  DevBuf<uint64_t> uIncNode;
   DevBuf<float> uW;
   uint32_t nUnique = 0, nTouched = 0;
   DevBuf<uint32_t> floorList, incPtr, floorMult;

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kThreads) k_isl_nodes(uint32_t n, const uint32
   nnzOff[p] = len;
 }
 
-struct IslandTierTable { IslandCaps caps[kIslandTiers]; uint32_t enabled; };
+struct IslandTierTable { IslandCaps caps[kIslandSlots]; uint32_t enabled; };
 
 __global__ void __launch_bounds__(kThreads) k_isl_classify(const uint32_t* counts0, IslandTierTable tt,
                                                            const uint32_t* __restrict__ islStart,
@@ -127,9 +127,12 @@ __global__ void __launch_bounds__(kThreads) k_isl_classify(const uint32_t* count
   if (isl >= counts0[0]) return;
   const uint32_t s0 = islStart[isl], m = islStart[isl + 1] - s0;
   const uint32_t nnz = nnzOff[s0 + m] - nnzOff[s0];
-  int tier = kIslandTiers;
-  for (int t = 0; t < kIslandTiers; ++t) {
-    if (!((tt.enabled >> t) & 1u)) continue;
+  int tier = kIslandSlots;
+  const int tryOrder[kIslandSlots] = {0, kSmallCtaSlot, 1, 2, 3};  // smallest team first
+#pragma unroll
+  for (int o = 0; o < kIslandSlots; ++o) {
+    const int t = tryOrder[o];
+    if (!((tt.enabled >> (t == kSmallCtaSlot ? 1 : t)) & 1u)) continue;
     if (m > tt.caps[t].maxNodes || (tt.caps[t].maxNnz && nnz > tt.caps[t].maxNnz)) continue;
     if (t == 0 && blockCount[slotOf[order[s0]] >> 5] != m) continue;  // the warp tier wants the island in ONE preconditioner block
     tier = t;
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(kThreads) k_isl_classify(const uint32_t* count
   tierList[(size_t)tier * listStride + at] = isl;
   // everything a team needs to start on the island in one 16 B record (it prefetches the next one while it solves)
   tierDesc[(size_t)tier * listStride + at] = make_uint4(isl, s0, m, nnzOff[s0]);
-  if (tier == kIslandTiers) atomicAdd(counts + 2 + kIslandTiers, m);
+  if (tier == kIslandSlots) atomicAdd(counts + 2 + kIslandSlots, m);
 }
 
 // Marks the nodes of the islands left to the grid-wide CG, the 256-row windows that hold one and their preconditioner
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(kThreads) k_isl_mark_big(const uint32_t* __res
                                                            const uint32_t* __restrict__ islStart, const uint32_t* __restrict__ order,
                                                            const uint32_t* __restrict__ slotOf, uint8_t* __restrict__ big,
                                                            uint32_t* __restrict__ winFlag, uint32_t* __restrict__ blkFlag) {
-  const uint32_t nLeft = counts[1 + kIslandTiers];
+  const uint32_t nLeft = counts[1 + kIslandSlots];
   for (uint32_t k = blockIdx.x; k < nLeft; k += gridDim.x) {
     const uint32_t isl = list[k];
     const uint32_t s0 = islStart[isl], m = islStart[isl + 1] - s0;
@@ -235,7 +238,7 @@ __device__ __forceinline__ void teamReduce(float (&v)[K], float* __restrict__ sR
 }
 
 template <int TEAM, int RPT, bool MAT_SMEM>
-__global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEAM <= 320 ? 2 : 1)) k_island_pcg(IslandArgs a, IslandLayout L, IslandCaps caps, int tier) {
+__global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEAM <= 128 ? 5 : (TEAM <= 320 ? 2 : 1))) k_island_pcg(IslandArgs a, IslandLayout L, IslandCaps caps, int tier) {
   extern __shared__ __align__(16) unsigned char islSmem[];
   constexpr int kTeams = TEAM == 32 ? 8 : 1;
   using ColT = typename std::conditional<MAT_SMEM, uint16_t, int>::type;
@@ -813,11 +816,12 @@ __global__ void __launch_bounds__(kBigTeam) k_island_pcg_big(IslandArgs a, uint3
 namespace {
 struct TierConfig { int team, rpt; bool matSmem; IslandCaps caps; int ctasPerSm; };
 // caps: nodes, matrix entries, inverse floats, blocks resident in shared memory
-const TierConfig kTiers[kIslandTiers] = {
+const TierConfig kTiers[kIslandSlots] = {
     {32, 1, true, {32u, 640u, 576u, 4u}, 3},
     {320, 2, true, {640u, 6656u, 9216u, 96u}, 2},
     {512, 2, true, {1024u, 12288u, 17408u, 192u}, 1},
     {1024, 0, false, {7168u, 0u, 0u, 0u}, 1},  // k_island_pcg_big
+    {128, 2, true, {256u, 2816u, 3456u, 32u}, 5},  // kSmallCtaSlot: 43 KB of shared memory
 };
 // Test hook: PIES_B200_ISLAND_MAXBLOCKS=k shrinks the shared-memory block tables of the CTA tiers to k entries, so islands
 // with more preconditioner blocks exercise the from-global-memory path of the block-Jacobi apply.
@@ -856,7 +860,7 @@ int uploadIslandStatics(IslandWork& w, cudaStream_t s, const HostSystem& y) {
   if (!w.host) { ICHECK(cudaMallocHost(&w.host, 1024 * sizeof(uint32_t))); w.hostCap = 1024; }
   if (!w.ready) ICHECK(cudaEventCreateWithFlags(&w.ready, cudaEventDisableTiming));
   if (!w.fork) ICHECK(cudaEventCreateWithFlags(&w.fork, cudaEventDisableTiming));
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 3; ++k) {
     if (!w.aux[k]) ICHECK(cudaStreamCreateWithFlags(&w.aux[k], cudaStreamNonBlocking));
     if (!w.join[k]) ICHECK(cudaEventCreateWithFlags(&w.join[k], cudaEventDisableTiming));
   }
@@ -868,14 +872,14 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
                  int* launches) {
   int L = 0;
   const uint32_t nB = w.nBodies;
-  for (int t = 0; t < kIslandTiers; ++t) w.tierCount[t] = 0;
+  for (int t = 0; t < kIslandSlots; ++t) w.tierCount[t] = 0;
   w.nLeftIslands = 0; w.nLeftNodes = 0;
   if (!n || !nB) return 0;
   ICHECK(w.parent.reserve(nB + 1)); ICHECK(w.keys.reserve(nB + 1)); ICHECK(w.tmpKeys.reserve(nB + 1));
   ICHECK(w.vals.reserve(nB + 1)); ICHECK(w.tmpVals.reserve(nB + 1)); ICHECK(w.heads.reserve(nB + 2));
   ICHECK(w.nodeOff.reserve(nB + 2)); ICHECK(w.posOfBody.reserve(nB + 1)); ICHECK(w.islStart.reserve(nB + 2));
   ICHECK(w.order.reserve(n + 1)); ICHECK(w.pos.reserve(n + 1)); ICHECK(w.nnzOff.reserve(n + 2));
-  ICHECK(w.tierList.reserve((size_t)(kIslandTiers + 1) * nB)); ICHECK(w.tierDesc.reserve((size_t)(kIslandTiers + 1) * nB)); ICHECK(w.counts.reserve(16));
+  ICHECK(w.tierList.reserve((size_t)(kIslandSlots + 1) * nB)); ICHECK(w.tierDesc.reserve((size_t)(kIslandSlots + 1) * nB)); ICHECK(w.counts.reserve(16));
   ICHECK(w.blkLocal.reserve((size_t)nBlocksBound * 32 + 32)); ICHECK(w.slotIsl.reserve(n + 1));
   ICHECK(w.sortHist.reserve(sortHistBytes(nB) / 4 + 4));
   w.scanCap = std::max<uint64_t>(w.scanCap, std::max<uint64_t>(n, nB) + 2);
@@ -897,19 +901,21 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
                                                            c.nUnique ? c.cPtr : nullptr, w.order.p, w.pos.p, w.nnzOff.p); ++L;
   L += launchExclusiveScan(s, w.nnzOff.p, n + 1, w.scanScratch.p);
   IslandTierTable tt;
-  for (int t = 0; t < kIslandTiers; ++t) tt.caps[t] = kTiers[t].caps;
+  for (int t = 0; t < kIslandSlots; ++t) tt.caps[t] = kTiers[t].caps;
+  static const bool noSmallCta = std::getenv("PIES_B200_NO_SMALL_CTA") != nullptr;   // A/B switch: tier 1 as one 320-thread list
+  if (noSmallCta) tt.caps[kSmallCtaSlot].maxNodes = 0;
   tt.enabled = tiersEnabled;
   k_isl_classify<<<gridFor(nB, kThreads), kThreads, 0, s>>>(w.counts.p, tt, w.islStart.p, w.nnzOff.p, w.order.p, slotOf, blockCount,
                                                            nB, w.tierList.p, w.tierDesc.p, w.counts.p); ++L;
   ICHECK(cudaMemcpyAsync(w.host, w.counts.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   ICHECK(cudaEventRecord(w.ready, s));
   ICHECK(cudaEventSynchronize(w.ready));
-  for (int t = 0; t < kIslandTiers; ++t) w.tierCount[t] = w.host[1 + t];
-  w.nLeftIslands = w.host[1 + kIslandTiers];
-  w.nLeftNodes = w.host[2 + kIslandTiers];
+  for (int t = 0; t < kIslandSlots; ++t) w.tierCount[t] = w.host[1 + t];
+  w.nLeftIslands = w.host[1 + kIslandSlots];
+  w.nLeftNodes = w.host[2 + kIslandSlots];
   // Both kinds present: the grid-wide CG only has to run over the rows of the left-over islands.
   w.restricted = false;
-  const bool anyLocal = w.tierCount[0] || w.tierCount[1] || w.tierCount[2] || w.tierCount[3];
+  const bool anyLocal = w.tierCount[0] || w.tierCount[1] || w.tierCount[2] || w.tierCount[3] || w.tierCount[kSmallCtaSlot];
   if (w.nLeftIslands && anyLocal) {
     const uint32_t nWin = (n + 255u) / 256u;
     ICHECK(w.big.reserve(n + 1)); ICHECK(w.winFlag.reserve(nWin + 2)); ICHECK(w.blkFlag.reserve(nBlocksBound + 2));
@@ -920,7 +926,7 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
     ICHECK(cudaMemsetAsync(w.winFlag.p, 0, (nWin + 2) * sizeof(uint32_t), s));
     ICHECK(cudaMemsetAsync(w.blkFlag.p, 0, ((size_t)nBlocksBound + 2) * sizeof(uint32_t), s));
     k_isl_mark_big<<<(int)std::min<uint32_t>(w.nLeftIslands, 4 * kNumSMs), kThreads, 0, s>>>(
-        w.counts.p, w.tierList.p + (size_t)kIslandTiers * nB, w.islStart.p, w.order.p, slotOf, w.big.p, w.winFlag.p, w.blkFlag.p); ++L;
+        w.counts.p, w.tierList.p + (size_t)kIslandSlots * nB, w.islStart.p, w.order.p, slotOf, w.big.p, w.winFlag.p, w.blkFlag.p); ++L;
     L += launchExclusiveScan(s, w.winFlag.p, nWin + 1, w.scanScratch.p);
     k_isl_compact<<<gridFor(nWin + 1, kThreads), kThreads, 0, s>>>(nWin, w.winFlag.p, w.actWin.p, w.actCounts.p); ++L;
     L += launchExclusiveScan(s, w.blkFlag.p, (uint64_t)nBlocksBound + 1, w.scanScratch.p);
@@ -948,17 +954,19 @@ int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const C
   a.b = b; a.x = x; a.tol2 = tol * tol; a.maxIter = maxIter; a.stats = w.solveStats.p + 4ull * statSlot;
   int L = 0;
   // Tiers 2 and 3 hold a handful of islands each of which keeps one CTA busy for a long chain of iterations: they run on
-  // their own streams, beside the thousands of small islands of tiers 0 and 1 that fill the other SMs.
-  const bool side = w.tierCount[3] || w.tierCount[2];
-  const bool warpAside = w.tierCount[0] && w.tierCount[1];
-  if (side || warpAside) cudaEventRecord(w.fork, s);   // before anything of this solve is enqueued on s
+  // their own streams, beside the thousands of small islands of the other tiers that fill the other SMs.  The longest
+  // chains are enqueued first.
+  const uint32_t nSmall = w.tierCount[kSmallCtaSlot];
+  const bool wideAside = w.tierCount[1] && nSmall;                    // the 320-thread tier beside the 128-thread one
+  const bool warpAside = w.tierCount[0] && (w.tierCount[1] || nSmall);
+  const bool side = w.tierCount[3] || w.tierCount[2] || wideAside || warpAside;
+  if (side) cudaEventRecord(w.fork, s);   // before anything of this solve is enqueued on s
   if (w.tierCount[3]) {
     cudaStreamWaitEvent(w.aux[0], w.fork, 0);
     const uint32_t maxNodes = kTiers[3].caps.maxNodes;
     const size_t smem = 32ull * maxNodes + 2 * 9 * 32 * sizeof(float);
     cudaFuncSetAttribute(k_island_pcg_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_island_pcg_big<<<(int)std::min<uint32_t>(w.tierCount[3], kNumSMs), kBigTeam, smem, w.aux[0]>>>(a, maxNodes, 3);
-    cudaEventRecord(w.join[0], w.aux[0]);
     ++L;
   }
   if (w.tierCount[2]) {
@@ -967,20 +975,31 @@ int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const C
     cudaEventRecord(w.join[1], w.aux[1]);
     ++L;
   }
-  if (w.tierCount[1]) { launchTier(k_island_pcg<320, 2, true>, 1, (int)std::min<uint32_t>(w.tierCount[1], 2 * kNumSMs), s, a); ++L; }
-  // The warp tier goes to a side stream when the 320-thread tier runs too: its CTAs fill the SMs that tier's last,
-  // partly filled wave leaves idle (3.5 waves of 296 CTAs at S3) instead of queueing behind it.
+  if (w.tierCount[1]) {
+    cudaStream_t st1 = s;
+    if (wideAside) { cudaStreamWaitEvent(w.aux[2], w.fork, 0); st1 = w.aux[2]; }
+    launchTier(k_island_pcg<320, 2, true>, 1, (int)std::min<uint32_t>(w.tierCount[1], 2 * kNumSMs), st1, a);
+    if (wideAside) cudaEventRecord(w.join[2], w.aux[2]);
+    ++L;
+  }
+  if (nSmall) {
+    launchTier(k_island_pcg<128, 2, true>, kSmallCtaSlot, (int)std::min<uint32_t>(nSmall, 5 * kNumSMs), s, a);
+    ++L;
+  }
+  // The warp tier goes to a side stream when a CTA tier runs too: its CTAs fill the SMs that tier's last, partly filled
+  // wave leaves idle instead of queueing behind it.
+  bool aux0Used = w.tierCount[3] != 0;
   if (w.tierCount[0]) {
     cudaStream_t st0 = s;
-    if (warpAside) { cudaStreamWaitEvent(w.aux[0], w.fork, 0); st0 = w.aux[0]; }
+    if (warpAside) { if (!aux0Used) cudaStreamWaitEvent(w.aux[0], w.fork, 0); st0 = w.aux[0]; aux0Used = true; }
     static const bool staged = std::getenv("PIES_B200_WARP_TIER_STAGED") != nullptr;   // A/B switch: the staged PCG variant
     if (staged) launchTier(k_island_pcg<32, 1, true>, 0, (int)std::min<uint32_t>((w.tierCount[0] + 7) / 8, 3 * kNumSMs), st0, a);
     else k_island_direct<<<(int)std::min<uint32_t>((w.tierCount[0] + 7) / 8, 4 * kNumSMs), 256, 0, st0>>>(a, 0);
     ++L;
-    if (warpAside) { cudaEventRecord(w.join[0], w.aux[0]); cudaStreamWaitEvent(s, w.join[0], 0); }
   }
-  if (w.tierCount[3] && !warpAside) cudaStreamWaitEvent(s, w.join[0], 0);
+  if (aux0Used) { cudaEventRecord(w.join[0], w.aux[0]); cudaStreamWaitEvent(s, w.join[0], 0); }
   if (w.tierCount[2]) cudaStreamWaitEvent(s, w.join[1], 0);
+  if (wideAside) cudaStreamWaitEvent(s, w.join[2], 0);
   return L;
 }
 
@@ -1002,6 +1021,7 @@ void preloadIslandKernels() {
   cudaFuncGetAttributes(&a, k_isl_classify);
   cudaFuncGetAttributes(&a, k_island_pcg<32, 1, true>);
   cudaFuncGetAttributes(&a, k_island_pcg<320, 2, true>);
+  cudaFuncGetAttributes(&a, k_island_pcg<128, 2, true>);
   cudaFuncGetAttributes(&a, k_island_pcg<512, 2, true>);
   cudaFuncGetAttributes(&a, k_island_pcg_big);
   cudaFuncGetAttributes(&a, k_island_direct);

@@ -13,7 +13,12 @@ namespace pies {
 //   tier 3: one 1024-thread CTA, r and p in shared memory, the island's matrix re-indexed in a global scratch copy
 //           (L2 resident: one CTA re-reads a few hundred KB per iteration)
 // Islands above tier 3 are left to the grid-wide CG of pcg.cu.
+// Tier 1 has a second, internal list (slot 4): islands of at most 256 nodes go to a 128-thread CTA with the same
+// shared-memory layout, five CTAs per SM — at S3 the typical contact island is five bodies (~140 rows), which leaves more
+// than half of a 320-thread CTA waiting at every barrier.  The public statistics and tuning bits count it as tier 1.
 constexpr int kIslandTiers = 4;
+constexpr int kIslandSlots = kIslandTiers + 1;
+constexpr int kSmallCtaSlot = 4;
 struct IslandCaps { uint32_t maxNodes, maxNnz, maxInv, maxBlocks; };
 
 struct IslandWork {
@@ -24,8 +29,8 @@ struct IslandWork {
   DevBuf<uint32_t> parent, vals, tmpVals, heads, nodeOff, posOfBody, islStart, order, pos, nnzOff, sortHist, scanScratch;
   DevBuf<uint64_t> keys, tmpKeys;
   DevBuf<uint4> tierDesc;         // per list entry: (island, first row in island order, rows, first matrix entry)
-  DevBuf<uint32_t> tierList;      // (kIslandTiers + 1) lists of nBodies entries; list kIslandTiers = islands left to the global CG
-  DevBuf<uint32_t> counts;        // device: [0] islands, [1 + t] islands of tier t, [1 + kIslandTiers] left over, then nodes left over
+  DevBuf<uint32_t> tierList;      // (kIslandSlots + 1) lists of nBodies entries; list kIslandSlots = islands left to the global CG
+  DevBuf<uint32_t> counts;        // device: [0] islands, [1 + t] islands of list t, [1 + kIslandSlots] left over, then nodes left over
   DevBuf<uint32_t> blkLocal;      // preconditioner block * 32 + lane -> island-local row of that member (written by every solve)
   DevBuf<uint32_t> slotIsl;       // tier 3: preconditioner slot of every row, island order
   DevBuf<int> matCol;             // tier 3: island-local copy of the matrix (column = local row index), at nnzOff
@@ -39,16 +44,16 @@ struct IslandWork {
   uint32_t hostCap = 0;
   cudaEvent_t ready = nullptr;
   // the CTA tiers with few, long-running islands (2, 3) run beside the small tiers on their own streams
-  cudaStream_t aux[2] = {nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
   uint64_t scanCap = 0;
   uint32_t nLeftIslands = 0, nLeftNodes = 0;  // host copies after buildIslands
-  uint32_t tierCount[kIslandTiers] = {0, 0, 0, 0};
+  uint32_t tierCount[kIslandSlots] = {0, 0, 0, 0, 0};
   cudaError_t lastError = cudaSuccess;
   ~IslandWork() {
     if (ready) cudaEventDestroy(ready);
     if (fork) cudaEventDestroy(fork);
-    for (int k = 0; k < 2; ++k) { if (join[k]) cudaEventDestroy(join[k]); if (aux[k]) cudaStreamDestroy(aux[k]); }
+    for (int k = 0; k < 3; ++k) { if (join[k]) cudaEventDestroy(join[k]); if (aux[k]) cudaStreamDestroy(aux[k]); }
     if (host) cudaFreeHost(host);
   }
 };

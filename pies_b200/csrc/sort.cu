@@ -9,6 +9,8 @@
 // One pass = histogram (per 2048-element tile, shared-memory counters), exclusive scan of
 // the digit-major tile histogram, and a stable scatter that ranks equal digits inside a
 // tile with warp match/ballot (no atomics on the ranking path => deterministic output).
+// Sorts of at most kSortSmallTiles tiles skip the scan launches: every scatter CTA sums the
+// tile-major histogram (L2 resident, at most 160 KB) into its own digit bases.
 #include "kernels.h"
 #include "common.cuh"
 
@@ -17,6 +19,7 @@ namespace pies {
 constexpr int kSortThreads = 256;
 constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 2048
+constexpr uint32_t kSortSmallTiles = 160;               // up to 327 680 elements: two launches per pass instead of four
 constexpr int kScanItems = 4;
 constexpr int kScanTile = kThreads * kScanItems;      // 1024
 
@@ -91,6 +94,9 @@ int launchExclusiveScan(cudaStream_t s, uint32_t* data, uint64_t n, uint32_t* sc
 }
 
 // ------------------------------------------------------------------ sort -----
+// TILE_MAJOR: hist[tile][digit] (small sorts: the scatter kernel turns it into its own bases, no scan launches between);
+// otherwise hist[digit][tile], scanned in place by launchExclusiveScan.
+template <bool TILE_MAJOR>
 __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint64_t* __restrict__ keys, uint64_t n, int shift,
                                                             uint32_t* __restrict__ hist, uint32_t numTiles) {
   __shared__ uint32_t bins[256];
@@ -103,9 +109,11 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint64_t* __re
     if (i < n) atomicAdd(&bins[(uint32_t)(keys[i] >> shift) & 255u], 1u);
   }
   __syncthreads();
-  hist[(uint64_t)threadIdx.x * numTiles + blockIdx.x] = bins[threadIdx.x];
+  if (TILE_MAJOR) hist[(uint64_t)blockIdx.x * 256u + threadIdx.x] = bins[threadIdx.x];
+  else hist[(uint64_t)threadIdx.x * numTiles + blockIdx.x] = bins[threadIdx.x];
 }
 
+template <bool TILE_MAJOR>
 __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint64_t* __restrict__ keys,
                                                                const uint32_t* __restrict__ vals, uint64_t n, int shift,
                                                                const uint32_t* __restrict__ hist, uint32_t numTiles,
@@ -114,9 +122,29 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint64_t* _
   constexpr int kWarps = kSortThreads / 32;
   __shared__ uint32_t cnt[kWarps][256];
   __shared__ uint32_t digitBase[256];
+  __shared__ uint32_t warpTotals[kWarps];
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int d = threadIdx.x; d < kWarps * 256; d += kSortThreads) (&cnt[0][0])[d] = 0;
-  digitBase[threadIdx.x] = hist[(uint64_t)threadIdx.x * numTiles + blockIdx.x];
+  if (TILE_MAJOR) {
+    // this digit's count over all tiles and over the tiles before this one, then an exclusive scan over the digits
+    uint32_t total = 0, before = 0;
+    for (uint32_t t = 0; t < numTiles; ++t) {
+      uint32_t v = hist[(uint64_t)t * 256u + threadIdx.x];
+      total += v;
+      before += t < blockIdx.x ? v : 0u;
+    }
+    uint32_t inc = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) warpTotals[warp] = inc;
+    __syncthreads();
+    uint32_t prior = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) prior += w < warp ? warpTotals[w] : 0u;
+    digitBase[threadIdx.x] = prior + inc - total + before;
+  } else {
+    digitBase[threadIdx.x] = hist[(uint64_t)threadIdx.x * numTiles + blockIdx.x];
+  }
   __syncthreads();
   // warp w owns elements [w*256, (w+1)*256) of the tile, visited in 8 rounds of 32 => index order
   uint64_t warpBase = (uint64_t)blockIdx.x * kSortTile + (uint64_t)warp * (32 * kSortItems);
@@ -171,11 +199,18 @@ int launchSortPairs(cudaStream_t s, uint64_t n, uint64_t* keys, uint32_t* vals, 
   int launches = 0;
   uint64_t *srcK = keys, *dstK = tmpKeys;
   uint32_t *srcV = vals, *dstV = tmpVals;
+  const bool small = tiles <= kSortSmallTiles;
   for (int shift = 0; shift < keyBits; shift += 8) {
-    k_sort_hist<<<tiles, kSortThreads, 0, s>>>(srcK, n, shift, hist, tiles);
-    launches += 1 + launchExclusiveScan(s, hist, h, scanScratch);
-    k_sort_scatter<<<tiles, kSortThreads, 0, s>>>(srcK, srcV, n, shift, hist, tiles, dstK, dstV);
-    ++launches;
+    if (small) {
+      k_sort_hist<true><<<tiles, kSortThreads, 0, s>>>(srcK, n, shift, hist, tiles);
+      k_sort_scatter<true><<<tiles, kSortThreads, 0, s>>>(srcK, srcV, n, shift, hist, tiles, dstK, dstV);
+      launches += 2;
+    } else {
+      k_sort_hist<false><<<tiles, kSortThreads, 0, s>>>(srcK, n, shift, hist, tiles);
+      launches += 1 + launchExclusiveScan(s, hist, h, scanScratch);
+      k_sort_scatter<false><<<tiles, kSortThreads, 0, s>>>(srcK, srcV, n, shift, hist, tiles, dstK, dstV);
+      ++launches;
+    }
     uint64_t* tk = srcK; srcK = dstK; dstK = tk;
     uint32_t* tv = srcV; srcV = dstV; dstV = tv;
   }
@@ -192,8 +227,10 @@ void preloadSortKernels() {
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, k_scan_tile);
   cudaFuncGetAttributes(&a, k_scan_add);
-  cudaFuncGetAttributes(&a, k_sort_hist);
-  cudaFuncGetAttributes(&a, k_sort_scatter);
+  cudaFuncGetAttributes(&a, k_sort_hist<false>);
+  cudaFuncGetAttributes(&a, k_sort_scatter<false>);
+  cudaFuncGetAttributes(&a, k_sort_hist<true>);
+  cudaFuncGetAttributes(&a, k_sort_scatter<true>);
 }
 
 }  // namespace pies

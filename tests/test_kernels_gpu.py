@@ -93,7 +93,8 @@ def test_cell_ranges_bit_exact(pb):
     assert (mins == g["node_min"]).all() and (lens == g["node_len"]).all()
 
 
-@pytest.mark.parametrize("n,bits", [(1, 8), (31, 16), (2048, 24), (2049, 40), (100003, 64), (1 << 20, 33)])
+@pytest.mark.parametrize("n,bits", [(1, 8), (31, 16), (2048, 24), (2049, 40), (100003, 64), (327680, 17), (327681, 17),
+                                    (1 << 20, 33)])
 def test_radix_sort_is_a_stable_sort(pb, n, bits):
     rng = np.random.default_rng(n)
     mask = np.uint64((1 << bits) - 1) if bits < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
