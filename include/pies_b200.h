@@ -277,6 +277,11 @@ int pies_b200_halo_set_lists(PiesB200Solver* s, int nPeers, const int* peers, co
 int pies_b200_halo_exchange(PiesB200Solver* s, int planes);      /* explicit exchange, planes = 1 or 3 (tick() does this itself) */
 int pies_b200_halo_destroy(PiesB200Solver* s);
 
+/* Diagnostics (needs PIES_B200_ISLAND_TRACE in the environment before the first tick): the island-local solve's record
+ * of the LAST global solve for list `slot` (0 warp, 1 CTA-320, 2 CTA-512, 3 CTA-1024, 4 CTA-128): four words per island —
+ * rows, CG iterations, SM clocks, matrix entries.  *count receives the number of islands in the list. */
+int pies_b200_debug_island_trace(PiesB200Solver* s, int slot, uint32_t* out4, uint32_t cap, uint32_t* count);
+
 /* ---- [additive] per-kernel probes: run the device functions of the hot kernels on caller data ---- */
 /* Tet strain / volume projections (reference Constraints.cpp:76-128, :205-255): pos 12 floats,
  * qinv 9 floats column-major per tet; out 12 floats (projected[0..3]). */

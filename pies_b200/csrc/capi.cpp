@@ -11,6 +11,7 @@
 
 #include "engine.h"
 #include "halo.h"
+#include "islands.h"
 
 using pies::fail;
 
@@ -455,6 +456,22 @@ int pies_b200_get_collision_csr(PiesB200Solver* s, uint64_t* nnz, int32_t* cPtr,
     if (cCol && cVal && *nnz) {
       PIES_CHECK(s, cudaMemcpy(cCol, s->detect->cCol.p, *nnz * sizeof(int32_t), cudaMemcpyDeviceToHost));
       PIES_CHECK(s, cudaMemcpy(cVal, s->detect->cVal.p, *nnz * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return PIES_B200_OK;
+  });
+}
+int pies_b200_debug_island_trace(PiesB200Solver* s, int slot, uint32_t* out4, uint32_t cap, uint32_t* count) {
+  if (!s || !count || slot < 0 || slot >= pies::kIslandSlots) return PIES_B200_EINVAL;
+  return guarded(s, [&]() {
+    cudaSetDevice(s->device);
+    *count = 0;
+    if (!s->islands || !s->islands->trace.p) return fail(s, PIES_B200_EINVAL, "island trace is off: set PIES_B200_ISLAND_TRACE before the first tick");
+    const uint32_t have = s->islands->tierCount[slot];
+    *count = have;
+    const uint32_t take = std::min(have, cap);
+    if (take && out4) {
+      PIES_CHECK(s, cudaStreamSynchronize(s->stream));
+      PIES_CHECK(s, cudaMemcpy(out4, s->islands->trace.p + (size_t)slot * s->islands->nBodies, (size_t)take * sizeof(uint4), cudaMemcpyDeviceToHost));
     }
     return PIES_B200_OK;
   });

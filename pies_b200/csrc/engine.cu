@@ -491,7 +491,7 @@ int pdSubstepBegin(PiesB200Solver* s) {
       }
       s->launches += LI;
       for (int t = 0; t < kIslandTiers; ++t) s->stats.islandsTier[t] = s->islands->tierCount[t];
-      s->stats.islandsTier[1] += s->islands->tierCount[kSmallCtaSlot];
+      s->stats.islandsTier[1] += s->islands->tierCount[kSmallCtaSlot] + s->islands->tierCount[kDenseSlot];
       s->stats.islandsGlobal = s->islands->nLeftIslands;
       s->stats.islandNodesGlobal = s->islands->nLeftNodes;
     }
@@ -535,7 +535,8 @@ int pdIteration(PiesB200Solver* s) {
   bool gridWide = true;
   if (s->islands && s->blocks) {
     IslandWork& iw = *s->islands;
-    const bool any = iw.tierCount[0] || iw.tierCount[1] || iw.tierCount[2] || iw.tierCount[3] || iw.tierCount[kSmallCtaSlot];
+    bool any = false;
+    for (int t = 0; t < kIslandSlots; ++t) any = any || iw.tierCount[t];
     if (any) {
       const int spIsl = timer.begin(kPhIslandKernel);
       s->launches += launchIslandSolve(iw, st, v.A, lists, v.pw, s->blocks->slotOf.p, s->rhs.p, s->q.p, s->tune.pcgTolerance,

@@ -128,11 +128,11 @@ __global__ void __launch_bounds__(kThreads) k_isl_classify(const uint32_t* count
   const uint32_t s0 = islStart[isl], m = islStart[isl + 1] - s0;
   const uint32_t nnz = nnzOff[s0 + m] - nnzOff[s0];
   int tier = kIslandSlots;
-  const int tryOrder[kIslandSlots] = {0, kSmallCtaSlot, 1, 2, 3};  // smallest team first
+  const int tryOrder[kIslandSlots] = {0, kDenseSlot, kSmallCtaSlot, 1, 2, 3};  // smallest team first
 #pragma unroll
   for (int o = 0; o < kIslandSlots; ++o) {
     const int t = tryOrder[o];
-    if (!((tt.enabled >> (t == kSmallCtaSlot ? 1 : t)) & 1u)) continue;
+    if (!((tt.enabled >> (t >= kSmallCtaSlot ? 1 : t)) & 1u)) continue;
     if (m > tt.caps[t].maxNodes || (tt.caps[t].maxNnz && nnz > tt.caps[t].maxNnz)) continue;
     if (t == 0 && blockCount[slotOf[order[s0]] >> 5] != m) continue;  // the warp tier wants the island in ONE preconditioner block
     tier = t;
@@ -208,6 +208,7 @@ struct IslandArgs {
   float4* apScratch; float4* zScratch; uint32_t* slotIsl;  // tier 3: A p, z and the preconditioner slot per row, island order
   const float4* b; float4* x;
   float tol2; uint32_t maxIter; uint32_t* stats;
+  uint4* trace;                // diagnostics: per list entry (rows, iterations, clocks, matrix entries), or null
 };
 
 template <int TEAM>
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
     const uint4 desc = descNext;
     if (wi + stride < count) descNext = __ldg(descs + wi + stride);  // in flight while this island is solved
     const uint32_t s0 = desc.y, m = desc.z, z0 = desc.w;
+    const long long t0 = a.trace ? clock64() : 0ll;
     float* mv = MAT_SMEM ? reinterpret_cast<float*>(base + L.val) : a.matVal + z0;
     ColT* mc = MAT_SMEM ? reinterpret_cast<ColT*>(base + L.col) : reinterpret_cast<ColT*>(a.matCol + z0);
     if (tid == 0) { sCtr[0] = 0; sCtr[1] = 0; }
@@ -521,6 +523,8 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
         atomicAdd(a.stats + 2, 1u);
         atomicMax(a.stats + 3, __float_as_uint(sqrtf(rel)));
       }
+      if (a.trace)
+        a.trace[(size_t)tier * a.listStride + wi] = make_uint4(m, iters, (uint32_t)(clock64() - t0), a.nnzOff[s0 + m] - z0);
     }
     teamSync<TEAM>();  // the team's shared memory is restaged for its next island
   }
@@ -649,6 +653,243 @@ __global__ void __launch_bounds__(256, 4) k_island_direct(IslandArgs a, int tier
         atomicMax(a.stats + 3, __float_as_uint(sqrtf(rel)));
       }
     }
+  }
+}
+
+// ---- dense list (kDenseSlot): islands of at most kDenseMax nodes ---------------------------------------------------------
+// Once per substep: A^-1 of every island by in-place Gauss-Jordan without pivoting (A is SPD: M/h^2 sits on the diagonal).
+// One 256-thread CTA per island; the matrix is assembled in shared memory from the global CSR + this substep's contact
+// terms, then lives in registers (an 8 x 8 tile per thread); every elimination step broadcasts the pivot row and column
+// through two small double-buffered shared arrays, one barrier per step.  fp32 is enough: the solves refine with the
+// residual recomputed from the true matrix.
+constexpr int kInvThreads = 256;
+constexpr int kInvLd = (int)kDenseMax + 4;   // shared-memory leading dimension (floats)
+
+__global__ void __launch_bounds__(kInvThreads, 2) k_island_invert(IslandArgs a, float* __restrict__ denseInv, int slot) {
+  extern __shared__ __align__(16) unsigned char invSmem[];
+  float* sA = reinterpret_cast<float*>(invSmem);
+  float* sRow = sA + (size_t)kDenseMax * kInvLd;   // [2][kDenseMax]
+  float* sCol = sRow + 2 * kDenseMax;              // [2][kDenseMax]
+  const int tid = (int)threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const uint32_t count = a.counts[1 + slot];
+  const uint4* descs = a.tierDesc + (size_t)slot * a.listStride;
+  for (uint32_t wi = blockIdx.x; wi < count; wi += gridDim.x) {
+    const uint4 desc = __ldg(descs + wi);
+    const uint32_t s0 = desc.y, m = desc.z;
+    const int mp = (int)((m + 7u) & ~7u);
+    __syncthreads();   // the previous island's tiles are out of shared memory
+    for (int i = tid; i < mp * (kInvLd / 4); i += kInvThreads) reinterpret_cast<float4*>(sA)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    __syncthreads();
+    if ((uint32_t)tid < m) {
+      const uint32_t l = (uint32_t)tid;
+      const uint32_t g = a.order[s0 + l];
+      float* row = sA + (size_t)l * kInvLd;
+      const uint32_t bodyBase = l - a.rankInBody[g];
+      for (int kk = a.rowPtr[g]; kk < a.rowPtr[g + 1]; ++kk) {
+        const uint32_t rk = __ldg(a.colRank + kk);
+        if (rk != 0xffffffffu) row[bodyBase + rk] += __ldg(a.val + kk);
+      }
+      if (a.cPtr)
+        for (int kk = a.cPtr[g]; kk < a.cPtr[g + 1]; ++kk) row[__ldg(a.pos + __ldg(a.cCol + kk)) - s0] += __ldg(a.cVal + kk);
+      if (a.cDiag) row[l] += a.cDiag[g];
+    }
+    __syncthreads();
+    const bool mine = 8 * ty < mp && 8 * tx < mp;
+    float t[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float4 lo = mine ? *reinterpret_cast<const float4*>(sA + (size_t)(8 * ty + r) * kInvLd + 8 * tx) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      const float4 hi = mine ? *reinterpret_cast<const float4*>(sA + (size_t)(8 * ty + r) * kInvLd + 8 * tx + 4) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      t[r][0] = lo.x; t[r][1] = lo.y; t[r][2] = lo.z; t[r][3] = lo.w; t[r][4] = hi.x; t[r][5] = hi.y; t[r][6] = hi.z; t[r][7] = hi.w;
+    }
+    const int nkb = mp >> 3;
+    for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+      for (int kr = 0; kr < 8; ++kr) {
+        const int k = 8 * kb + kr;
+        if ((uint32_t)k >= m) break;   // uniform
+        float* rowBuf = sRow + (k & 1) * kDenseMax;
+        float* colBuf = sCol + (k & 1) * kDenseMax;
+        if (ty == kb && mine) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) rowBuf[8 * tx + c] = t[kr][c];
+        }
+        if (tx == kb && mine) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) colBuf[8 * ty + r] = t[r][kr];
+        }
+        __syncthreads();
+        if (mine) {
+          const float d = 1.0f / rowBuf[k];
+          float rv[8], cv[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) rv[c] = rowBuf[8 * tx + c];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) cv[r] = colBuf[8 * ty + r] * d;
+          const bool pr = ty == kb, pc = tx == kb;   // this tile holds the pivot row / column
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float v = fmaf(-cv[r], rv[c], t[r][c]);
+              if (r == kr && pr) v = rv[c] * d;
+              if (c == kr && pc) v = -cv[r];
+              if (r == kr && c == kr && pr && pc) v = d;
+              t[r][c] = v;
+            }
+          }
+        }
+      }
+    }
+    if (mine) {
+      float* out = denseInv + (size_t)wi * (kDenseMax * kDenseMax);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)(8 * ty + r) * kDenseMax + 8 * tx);
+        dst[0] = make_float4(t[r][0], t[r][1], t[r][2], t[r][3]);
+        dst[1] = make_float4(t[r][4], t[r][5], t[r][6], t[r][7]);
+      }
+    }
+  }
+}
+
+// Every global solve: iterative refinement with the island's inverse, one 128-thread CTA per island, one row per thread.
+// r = b - A x in fp64 straight from the global CSR (x gathered where it lies), then rounds of z = Ainv r (the inverse is
+// symmetric: thread l reads column l, i.e. consecutive addresses across the warp; r broadcast from shared memory),
+// x += z, r -= A z until the island's residual passes the tolerance.  A round contracts the residual by the accuracy of
+// the fp32 inverse (1e-4 .. 1e-6), so two rounds are the rule; the round limit and the statistics are the CG tiers'.
+constexpr int kDenseThreads = 128;
+
+__device__ __forceinline__ void denseSum3(float (&v)[3], float* __restrict__ sRed, int& phase, int tid) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) v[k] = warpSum(v[k]);
+  float* buf = sRed + phase * 16;
+  phase ^= 1;
+  if ((tid & 31) == 0) { buf[(tid >> 5) * 4 + 0] = v[0]; buf[(tid >> 5) * 4 + 1] = v[1]; buf[(tid >> 5) * 4 + 2] = v[2]; }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 3; ++k) v[k] = (buf[k] + buf[4 + k]) + (buf[8 + k] + buf[12 + k]);
+}
+
+__global__ void __launch_bounds__(kDenseThreads, 8) k_island_dense(IslandArgs a, const float* __restrict__ denseInv, int slot) {
+  __shared__ float4 sV[kDenseMax];
+  __shared__ float sRed[32];
+  const int tid = (int)threadIdx.x;
+  const uint32_t count = a.counts[1 + slot];
+  const uint4* descs = a.tierDesc + (size_t)slot * a.listStride;
+  int phase = 0;
+  for (uint32_t wi = blockIdx.x; wi < count; wi += gridDim.x) {
+    const uint4 desc = __ldg(descs + wi);
+    const uint32_t s0 = desc.y, m = desc.z;
+    const long long t0 = a.trace ? clock64() : 0ll;
+    const bool act = (uint32_t)tid < m;
+    uint32_t g = 0, bodyBase = 0;
+    int kk0 = 0, kk1 = 0, c0 = 0, c1 = 0;
+    float4 xi = make_float4(0.0f, 0.0f, 0.0f, 0.0f), bi = xi;
+    float cd = 0.0f;
+    if (act) {
+      g = a.order[s0 + tid];
+      kk0 = a.rowPtr[g]; kk1 = a.rowPtr[g + 1];
+      xi = a.x[g]; bi = a.b[g];
+      cd = a.cDiag ? a.cDiag[g] : 0.0f;
+      bodyBase = (uint32_t)tid - a.rankInBody[g];
+      if (a.cPtr) { c0 = a.cPtr[g]; c1 = a.cPtr[g + 1]; }
+    }
+    // ---- start residual, fp64 accumulation, x gathered where it lies
+    double y0 = (double)cd * (double)xi.x, y1 = (double)cd * (double)xi.y, y2 = (double)cd * (double)xi.z;
+    for (int kk = kk0; kk < kk1; kk += 4) {   // four entries per batch: their loads are in flight together
+      int cc[4]; float vv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (kk + j < kk1) { cc[j] = __ldg(a.col + kk + j); vv[j] = __ldg(a.val + kk + j); }
+      float4 xv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (kk + j < kk1) xv[j] = a.x[cc[j]];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (kk + j < kk1) { y0 += (double)vv[j] * (double)xv[j].x; y1 += (double)vv[j] * (double)xv[j].y; y2 += (double)vv[j] * (double)xv[j].z; }
+    }
+    for (int kk = c0; kk < c1; ++kk) {
+      const float v = a.cVal[kk];
+      const float4 xv = a.x[a.cCol[kk]];
+      y0 += (double)v * (double)xv.x; y1 += (double)v * (double)xv.y; y2 += (double)v * (double)xv.z;
+    }
+    float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+    if (act) { r0 = (float)((double)bi.x - y0); r1 = (float)((double)bi.y - y1); r2 = (float)((double)bi.z - y2); }
+    float bb[3] = {bi.x * bi.x, bi.y * bi.y, bi.z * bi.z};
+    denseSum3(bb, sRed, phase, tid);
+    const float* inv = denseInv + (size_t)wi * (kDenseMax * kDenseMax) + tid;
+    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+    uint32_t iters = 0;
+    bool conv = false;
+    float rr[3];
+    while (true) {
+      rr[0] = r0 * r0; rr[1] = r1 * r1; rr[2] = r2 * r2;
+      denseSum3(rr, sRed, phase, tid);
+      conv = rr[0] <= a.tol2 * bb[0] + 1e-36f && rr[1] <= a.tol2 * bb[1] + 1e-36f && rr[2] <= a.tol2 * bb[2] + 1e-36f;
+      if (conv || iters >= a.maxIter) break;
+      sV[tid] = make_float4(r0, r1, r2, 0.0f);
+      __syncthreads();
+      float z0 = 0.0f, z1 = 0.0f, z2 = 0.0f;
+      if (act) {
+        uint32_t j = 0;
+        for (; j + 8 <= m; j += 8) {
+          float w[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) w[u] = __ldg(inv + (size_t)(j + u) * kDenseMax);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 rj = sV[j + u];
+            z0 = fmaf(w[u], rj.x, z0); z1 = fmaf(w[u], rj.y, z1); z2 = fmaf(w[u], rj.z, z2);
+          }
+        }
+        for (; j < m; ++j) {
+          const float w = __ldg(inv + (size_t)j * kDenseMax);
+          const float4 rj = sV[j];
+          z0 = fmaf(w, rj.x, z0); z1 = fmaf(w, rj.y, z1); z2 = fmaf(w, rj.z, z2);
+        }
+      }
+      d0 += z0; d1 += z1; d2 += z2;
+      __syncthreads();   // r has been read
+      sV[tid] = make_float4(z0, z1, z2, 0.0f);
+      __syncthreads();
+      // r -= A z, columns through the host's rank table / the island permutation
+      float w0 = cd * z0, w1 = cd * z1, w2 = cd * z2;
+      for (int kk = kk0; kk < kk1; kk += 4) {
+        uint32_t rk[4]; float vv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (kk + j < kk1) { rk[j] = __ldg(a.colRank + kk + j); vv[j] = __ldg(a.val + kk + j); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (kk + j < kk1 && rk[j] != 0xffffffffu) {
+            const float4 zv = sV[bodyBase + rk[j]];
+            w0 = fmaf(vv[j], zv.x, w0); w1 = fmaf(vv[j], zv.y, w1); w2 = fmaf(vv[j], zv.z, w2);
+          }
+      }
+      for (int kk = c0; kk < c1; ++kk) {
+        const float v = a.cVal[kk];
+        const float4 zv = sV[__ldg(a.pos + a.cCol[kk]) - s0];
+        w0 = fmaf(v, zv.x, w0); w1 = fmaf(v, zv.y, w1); w2 = fmaf(v, zv.z, w2);
+      }
+      r0 -= w0; r1 -= w1; r2 -= w2;
+      ++iters;
+      // the next round's reduction barrier separates these reads of sV from its next write
+    }
+    if (act) {
+      xi.x += d0; xi.y += d1; xi.z += d2;
+      a.x[g] = xi;
+    }
+    if (tid == 0) {
+      atomicMax(a.stats, iters);
+      atomicAdd(a.stats + 1, iters * ((m + 31u) >> 5));
+      if (!conv) {
+        float rel = 0.0f;
+        for (int c = 0; c < 3; ++c) if (bb[c] > 0.0f) rel = fmaxf(rel, rr[c] / bb[c]);
+        atomicAdd(a.stats + 2, 1u);
+        atomicMax(a.stats + 3, __float_as_uint(sqrtf(rel)));
+      }
+      if (a.trace) a.trace[(size_t)slot * a.listStride + wi] = make_uint4(m, iters, (uint32_t)(clock64() - t0), a.nnzOff[s0 + m] - desc.w);
+    }
+    __syncthreads();   // sV / sRed are reused by the CTA's next island
   }
 }
 
@@ -822,6 +1063,7 @@ const TierConfig kTiers[kIslandSlots] = {
     {512, 2, true, {1024u, 12288u, 17408u, 192u}, 1},
     {1024, 0, false, {7168u, 0u, 0u, 0u}, 1},  // k_island_pcg_big
     {128, 2, true, {256u, 2816u, 3456u, 32u}, 5},  // kSmallCtaSlot: 43 KB of shared memory
+    {128, 1, false, {kDenseMax, 0u, 0u, 0u}, 8},   // kDenseSlot: k_island_invert + k_island_dense
 };
 // Test hook: PIES_B200_ISLAND_MAXBLOCKS=k shrinks the shared-memory block tables of the CTA tiers to k entries, so islands
 // with more preconditioner blocks exercise the from-global-memory path of the block-Jacobi apply.
@@ -860,7 +1102,7 @@ int uploadIslandStatics(IslandWork& w, cudaStream_t s, const HostSystem& y) {
   if (!w.host) { ICHECK(cudaMallocHost(&w.host, 1024 * sizeof(uint32_t))); w.hostCap = 1024; }
   if (!w.ready) ICHECK(cudaEventCreateWithFlags(&w.ready, cudaEventDisableTiming));
   if (!w.fork) ICHECK(cudaEventCreateWithFlags(&w.fork, cudaEventDisableTiming));
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < IslandWork::kAux; ++k) {
     if (!w.aux[k]) ICHECK(cudaStreamCreateWithFlags(&w.aux[k], cudaStreamNonBlocking));
     if (!w.join[k]) ICHECK(cudaEventCreateWithFlags(&w.join[k], cudaEventDisableTiming));
   }
@@ -881,6 +1123,8 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   ICHECK(w.order.reserve(n + 1)); ICHECK(w.pos.reserve(n + 1)); ICHECK(w.nnzOff.reserve(n + 2));
   ICHECK(w.tierList.reserve((size_t)(kIslandSlots + 1) * nB)); ICHECK(w.tierDesc.reserve((size_t)(kIslandSlots + 1) * nB)); ICHECK(w.counts.reserve(16));
   ICHECK(w.blkLocal.reserve((size_t)nBlocksBound * 32 + 32)); ICHECK(w.slotIsl.reserve(n + 1));
+  static const bool traceOn = std::getenv("PIES_B200_ISLAND_TRACE") != nullptr;
+  if (traceOn) ICHECK(w.trace.reserve((size_t)(kIslandSlots + 1) * nB));
   ICHECK(w.sortHist.reserve(sortHistBytes(nB) / 4 + 4));
   w.scanCap = std::max<uint64_t>(w.scanCap, std::max<uint64_t>(n, nB) + 2);
   ICHECK(w.scanScratch.reserve(scanScratchElems(w.scanCap)));
@@ -903,11 +1147,13 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   IslandTierTable tt;
   for (int t = 0; t < kIslandSlots; ++t) tt.caps[t] = kTiers[t].caps;
   static const bool noSmallCta = std::getenv("PIES_B200_NO_SMALL_CTA") != nullptr;   // A/B switch: tier 1 as one 320-thread list
+  static const bool noDense = std::getenv("PIES_B200_NO_DENSE") != nullptr;            // A/B switch: no dense-inverse list
   if (noSmallCta) tt.caps[kSmallCtaSlot].maxNodes = 0;
+  if (noDense) tt.caps[kDenseSlot].maxNodes = 0;
   tt.enabled = tiersEnabled;
   k_isl_classify<<<gridFor(nB, kThreads), kThreads, 0, s>>>(w.counts.p, tt, w.islStart.p, w.nnzOff.p, w.order.p, slotOf, blockCount,
                                                            nB, w.tierList.p, w.tierDesc.p, w.counts.p); ++L;
-  ICHECK(cudaMemcpyAsync(w.host, w.counts.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  ICHECK(cudaMemcpyAsync(w.host, w.counts.p, 12 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   ICHECK(cudaEventRecord(w.ready, s));
   ICHECK(cudaEventSynchronize(w.ready));
   for (int t = 0; t < kIslandSlots; ++t) w.tierCount[t] = w.host[1 + t];
@@ -915,7 +1161,8 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   w.nLeftNodes = w.host[2 + kIslandSlots];
   // Both kinds present: the grid-wide CG only has to run over the rows of the left-over islands.
   w.restricted = false;
-  const bool anyLocal = w.tierCount[0] || w.tierCount[1] || w.tierCount[2] || w.tierCount[3] || w.tierCount[kSmallCtaSlot];
+  bool anyLocal = false;
+  for (int t = 0; t < kIslandSlots; ++t) anyLocal = anyLocal || w.tierCount[t];
   if (w.nLeftIslands && anyLocal) {
     const uint32_t nWin = (n + 255u) / 256u;
     ICHECK(w.big.reserve(n + 1)); ICHECK(w.winFlag.reserve(nWin + 2)); ICHECK(w.blkFlag.reserve(nBlocksBound + 2));
@@ -937,6 +1184,17 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
     const size_t nnz = S.nnz + 6ull * c.nUnique + 16;
     ICHECK(w.matCol.reserve(nnz)); ICHECK(w.matVal.reserve(nnz));
   }
+  if (w.tierCount[kDenseSlot]) {  // the dense list: this substep's inverses
+    const uint32_t nd = w.tierCount[kDenseSlot];
+    ICHECK(w.denseInv.reserve((size_t)nd * kDenseMax * kDenseMax));
+    IslandArgs a{};
+    a.counts = w.counts.p; a.tierDesc = w.tierDesc.p; a.listStride = w.nBodies;
+    a.order = w.order.p; a.pos = w.pos.p; a.rowPtr = S.rowPtr; a.val = S.val; a.colRank = w.colRank.p; a.rankInBody = w.rankInBody.p;
+    a.cPtr = c.nUnique ? c.cPtr : nullptr; a.cCol = c.cCol; a.cVal = c.cVal; a.cDiag = (c.nTri || c.nFloor) ? c.cDiag : nullptr;
+    const size_t smem = ((size_t)kDenseMax * kInvLd + 4 * kDenseMax) * sizeof(float);
+    cudaFuncSetAttribute(k_island_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_island_invert<<<(int)std::min<uint32_t>(nd, 2 * kNumSMs), kInvThreads, smem, s>>>(a, w.denseInv.p, kDenseSlot); ++L;
+  }
   if (launches) *launches += L;
   return 0;
 }
@@ -952,54 +1210,48 @@ int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const C
   a.blkLocal = w.blkLocal.p; a.matCol = w.matCol.p; a.matVal = w.matVal.p; a.deltaScratch = pw.delta;
   a.apScratch = pw.ap; a.zScratch = pw.z; a.slotIsl = w.slotIsl.p;
   a.b = b; a.x = x; a.tol2 = tol * tol; a.maxIter = maxIter; a.stats = w.solveStats.p + 4ull * statSlot;
+  a.trace = w.trace.p;   // null unless PIES_B200_ISLAND_TRACE reserved it
   int L = 0;
-  // Tiers 2 and 3 hold a handful of islands each of which keeps one CTA busy for a long chain of iterations: they run on
-  // their own streams, beside the thousands of small islands of the other tiers that fill the other SMs.  The longest
+  // The lists of one solve are independent: the first one enqueued runs on the solver's stream, every further one on a
+  // stream of its own beside it (the handful of long-running islands of tiers 2 and 3 next to the thousands of small ones
+  // that fill the other SMs; the warp tier in the SMs a CTA tier's last, partly filled wave leaves idle).  The longest
   // chains are enqueued first.
-  const uint32_t nSmall = w.tierCount[kSmallCtaSlot];
-  const bool wideAside = w.tierCount[1] && nSmall;                    // the 320-thread tier beside the 128-thread one
-  const bool warpAside = w.tierCount[0] && (w.tierCount[1] || nSmall);
-  const bool side = w.tierCount[3] || w.tierCount[2] || wideAside || warpAside;
-  if (side) cudaEventRecord(w.fork, s);   // before anything of this solve is enqueued on s
+  int present = 0;
+  for (int t = 0; t < kIslandSlots; ++t) present += w.tierCount[t] ? 1 : 0;
+  if (present > 1) cudaEventRecord(w.fork, s);   // before anything of this solve is enqueued on s
+  int used = 0;
+  bool first = true;
+  auto nextStream = [&]() -> cudaStream_t {
+    if (first) { first = false; return s; }
+    cudaStream_t st = w.aux[used++];
+    cudaStreamWaitEvent(st, w.fork, 0);
+    return st;
+  };
   if (w.tierCount[3]) {
-    cudaStreamWaitEvent(w.aux[0], w.fork, 0);
     const uint32_t maxNodes = kTiers[3].caps.maxNodes;
     const size_t smem = 32ull * maxNodes + 2 * 9 * 32 * sizeof(float);
     cudaFuncSetAttribute(k_island_pcg_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_island_pcg_big<<<(int)std::min<uint32_t>(w.tierCount[3], kNumSMs), kBigTeam, smem, w.aux[0]>>>(a, maxNodes, 3);
+    k_island_pcg_big<<<(int)std::min<uint32_t>(w.tierCount[3], kNumSMs), kBigTeam, smem, nextStream()>>>(a, maxNodes, 3);
     ++L;
   }
-  if (w.tierCount[2]) {
-    cudaStreamWaitEvent(w.aux[1], w.fork, 0);
-    launchTier(k_island_pcg<512, 2, true>, 2, (int)std::min<uint32_t>(w.tierCount[2], kNumSMs), w.aux[1], a);
-    cudaEventRecord(w.join[1], w.aux[1]);
+  if (w.tierCount[2]) { launchTier(k_island_pcg<512, 2, true>, 2, (int)std::min<uint32_t>(w.tierCount[2], kNumSMs), nextStream(), a); ++L; }
+  if (w.tierCount[1]) { launchTier(k_island_pcg<320, 2, true>, 1, (int)std::min<uint32_t>(w.tierCount[1], 2 * kNumSMs), nextStream(), a); ++L; }
+  if (w.tierCount[kSmallCtaSlot]) {
+    launchTier(k_island_pcg<128, 2, true>, kSmallCtaSlot, (int)std::min<uint32_t>(w.tierCount[kSmallCtaSlot], 5 * kNumSMs), nextStream(), a);
     ++L;
   }
-  if (w.tierCount[1]) {
-    cudaStream_t st1 = s;
-    if (wideAside) { cudaStreamWaitEvent(w.aux[2], w.fork, 0); st1 = w.aux[2]; }
-    launchTier(k_island_pcg<320, 2, true>, 1, (int)std::min<uint32_t>(w.tierCount[1], 2 * kNumSMs), st1, a);
-    if (wideAside) cudaEventRecord(w.join[2], w.aux[2]);
+  if (w.tierCount[kDenseSlot]) {
+    k_island_dense<<<(int)std::min<uint32_t>(w.tierCount[kDenseSlot], 16 * kNumSMs), kDenseThreads, 0, nextStream()>>>(a, w.denseInv.p, kDenseSlot);
     ++L;
   }
-  if (nSmall) {
-    launchTier(k_island_pcg<128, 2, true>, kSmallCtaSlot, (int)std::min<uint32_t>(nSmall, 5 * kNumSMs), s, a);
-    ++L;
-  }
-  // The warp tier goes to a side stream when a CTA tier runs too: its CTAs fill the SMs that tier's last, partly filled
-  // wave leaves idle instead of queueing behind it.
-  bool aux0Used = w.tierCount[3] != 0;
   if (w.tierCount[0]) {
-    cudaStream_t st0 = s;
-    if (warpAside) { if (!aux0Used) cudaStreamWaitEvent(w.aux[0], w.fork, 0); st0 = w.aux[0]; aux0Used = true; }
+    cudaStream_t st0 = nextStream();
     static const bool staged = std::getenv("PIES_B200_WARP_TIER_STAGED") != nullptr;   // A/B switch: the staged PCG variant
     if (staged) launchTier(k_island_pcg<32, 1, true>, 0, (int)std::min<uint32_t>((w.tierCount[0] + 7) / 8, 3 * kNumSMs), st0, a);
     else k_island_direct<<<(int)std::min<uint32_t>((w.tierCount[0] + 7) / 8, 4 * kNumSMs), 256, 0, st0>>>(a, 0);
     ++L;
   }
-  if (aux0Used) { cudaEventRecord(w.join[0], w.aux[0]); cudaStreamWaitEvent(s, w.join[0], 0); }
-  if (w.tierCount[2]) cudaStreamWaitEvent(s, w.join[1], 0);
-  if (wideAside) cudaStreamWaitEvent(s, w.join[2], 0);
+  for (int k = 0; k < used; ++k) { cudaEventRecord(w.join[k], w.aux[k]); cudaStreamWaitEvent(s, w.join[k], 0); }
   return L;
 }
 
@@ -1025,6 +1277,8 @@ void preloadIslandKernels() {
   cudaFuncGetAttributes(&a, k_island_pcg<512, 2, true>);
   cudaFuncGetAttributes(&a, k_island_pcg_big);
   cudaFuncGetAttributes(&a, k_island_direct);
+  cudaFuncGetAttributes(&a, k_island_invert);
+  cudaFuncGetAttributes(&a, k_island_dense);
 }
 
 }  // namespace pies

@@ -16,9 +16,15 @@ namespace pies {
 // Tier 1 has a second, internal list (slot 4): islands of at most 256 nodes go to a 128-thread CTA with the same
 // shared-memory layout, five CTAs per SM — at S3 the typical contact island is five bodies (~140 rows), which leaves more
 // than half of a 320-thread CTA waiting at every barrier.  The public statistics and tuning bits count it as tier 1.
+// A third internal list (slot 5) takes the islands of at most 128 nodes that are not a single preconditioner block: their
+// matrix is inverted once per substep (dense, in-place Gauss-Jordan, one CTA per island) and every global solve of the
+// substep is then iterative refinement with that inverse — what the warp tier does with its block inverse.  At S3 every
+// contact island of the benchmark window (3-4 bodies of a column, 81-108 nodes) is of this kind.
 constexpr int kIslandTiers = 4;
-constexpr int kIslandSlots = kIslandTiers + 1;
+constexpr int kIslandSlots = kIslandTiers + 2;
 constexpr int kSmallCtaSlot = 4;
+constexpr int kDenseSlot = 5;
+constexpr uint32_t kDenseMax = 128;   // nodes; the inverse is stored with this leading dimension
 struct IslandCaps { uint32_t maxNodes, maxNnz, maxInv, maxBlocks; };
 
 struct IslandWork {
@@ -39,21 +45,24 @@ struct IslandWork {
   DevBuf<uint8_t> big;
   DevBuf<uint32_t> winFlag, blkFlag, actWin, actBlk, actCounts;
   bool restricted = false;
+  DevBuf<uint4> trace;            // diagnostics (PIES_B200_ISLAND_TRACE): per list entry (rows, iterations, SM clocks, matrix entries) of the last solve
   DevBuf<uint32_t> solveStats;    // 4 words per solve of a tick: max iterations, sum of iterations x rows, islands at the cap, worst residual
   uint32_t* host = nullptr;       // pinned copy of counts (8 words) + solveStats
   uint32_t hostCap = 0;
   cudaEvent_t ready = nullptr;
-  // the CTA tiers with few, long-running islands (2, 3) run beside the small tiers on their own streams
-  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+  // the lists of one solve run beside each other: the first on the solver's stream, the others on these
+  static constexpr int kAux = 5;
+  cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[kAux] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t scanCap = 0;
   uint32_t nLeftIslands = 0, nLeftNodes = 0;  // host copies after buildIslands
-  uint32_t tierCount[kIslandSlots] = {0, 0, 0, 0, 0};
+  uint32_t tierCount[kIslandSlots] = {0, 0, 0, 0, 0, 0};
+  DevBuf<float> denseInv;         // slot 5: kDenseMax x kDenseMax floats per list entry, inverse of the island's matrix
   cudaError_t lastError = cudaSuccess;
   ~IslandWork() {
     if (ready) cudaEventDestroy(ready);
     if (fork) cudaEventDestroy(fork);
-    for (int k = 0; k < 3; ++k) { if (join[k]) cudaEventDestroy(join[k]); if (aux[k]) cudaStreamDestroy(aux[k]); }
+    for (int k = 0; k < kAux; ++k) { if (join[k]) cudaEventDestroy(join[k]); if (aux[k]) cudaStreamDestroy(aux[k]); }
     if (host) cudaFreeHost(host);
   }
 };

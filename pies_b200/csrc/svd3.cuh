@@ -21,26 +21,37 @@ __device__ __forceinline__ float det3(const M3& a) {
 }
 
 // One Kogbetliantz step on the (P,Q) plane: L * A * J is diagonal on that 2x2 block.
+// 1/sqrt(x): SFU estimate (2 ulp) + one Newton step, ~1 ulp without the IEEE sqrt / divide sequences and their branches
+__device__ __forceinline__ float rsqrtNewton(float x) {
+  const float y = rsqrtf(x);
+  return y * fmaf(-0.5f * x, y * y, 1.5f);
+}
+
 template <int P, int Q>
 __device__ __forceinline__ bool jacobiPair(M3& A, M3& U, M3& V, float thresh) {
   float w = A.m[P][P], x = A.m[P][Q], y = A.m[Q][P], z = A.m[Q][Q];
   if (fabsf(x) <= thresh && fabsf(y) <= thresh) return false;
-  // 1) rotation R = [c s; -s c] making R*M symmetric: tan = (y - x) / (w + z)
+  // 1) rotation R = [c s; -s c] making R*M symmetric: tan = (y - x) / (w + z).
+  // Reciprocal square roots from the SFU plus a Newton step instead of IEEE sqrt + divide sequences: the kernel is bound
+  // by instruction issue (r02g); a rotation angle that is off by an ulp is corrected by the next sweep.
   float t = w + z, d = y - x;
-  float h = sqrtf(t * t + d * d);
-  float c = 1.0f, s = 0.0f;
-  if (h > 1e-30f) { float ih = 1.0f / h; c = t * ih; s = d * ih; }
+  float hh = t * t + d * d;
+  float ih = rsqrtNewton(hh);
+  const bool okR = hh > 1e-37f;
+  float c = okR ? t * ih : 1.0f, s = okR ? d * ih : 0.0f;
   float al = c * w + s * y;          // B = R*M = [al be; be ga]
   float be = c * x + s * z;
   float ga = -s * x + c * z;
-  // 2) symmetric Jacobi rotation J = [cj sj; -sj cj] diagonalising B
-  float cj = 1.0f, sj = 0.0f;
-  if (fabsf(be) > 1e-30f) {
-    float tau = (ga - al) / (2.0f * be);
-    float tt = copysignf(1.0f, tau) / (fabsf(tau) + sqrtf(1.0f + tau * tau));
-    cj = rsqrtf(1.0f + tt * tt);
-    sj = cj * tt;
-  }
+  // 2) symmetric Jacobi rotation J = [cj sj; -sj cj] diagonalising B, angle in [-pi/4, pi/4]:
+  //    tan 2a = 2 be / (ga - al); cos a = sqrt((1 + cos 2a) / 2), sin a = sin 2a / (2 cos a)
+  float dx = ga - al, dy = 2.0f * be;
+  float r2 = dx * dx + dy * dy;
+  float ir = rsqrtNewton(r2);
+  float c2 = fabsf(dx) * ir, s2 = (dx >= 0.0f ? dy : -dy) * ir;
+  float v = 0.5f + 0.5f * c2;
+  float icj = rsqrtNewton(v);
+  const bool okJ = fabsf(be) > 1e-30f && r2 > 1e-37f;
+  float cj = okJ ? v * icj : 1.0f, sj = okJ ? 0.5f * s2 * icj : 0.0f;
   // left rotation L = J^T R = [cl sl; -sl cl]
   float cl = cj * c + sj * s, sl = cj * s - sj * c;
 #pragma unroll
@@ -226,7 +237,7 @@ __device__ __forceinline__ void volumeSigma(const float (&s)[3], float lo, float
     float omega = fminf(fmaxf(product, lo), hi);
     float C = product - omega;
     float gx = sy * sz, gy = sx * sz, gz = sx * sy;
-    float k = ((gx * dx + gy * dy + gz * dz) - C) / (gx * gx + gy * gy + gz * gz);
+    float k = __fdividef((gx * dx + gy * dy + gz * dz) - C, gx * gx + gy * gy + gz * gz);
     dx = k * gx; dy = k * gy; dz = k * gz;
   }
   o[0] = s[0] + dx; o[1] = s[1] + dy; o[2] = s[2] + dz;

@@ -144,6 +144,7 @@ _SIGNATURES = {
     "pies_b200_probe_volume_projection": (C.c_int, [C.c_uint32, _f32p, _f32p, C.c_float, C.c_float, _f32p]),
     "pies_b200_probe_ccd": (C.c_int, [C.c_uint32, _f32p, C.c_float, _i32p, _f32p]),
     "pies_b200_probe_edge_ccd": (C.c_int, [C.c_uint32, _f32p, _i32p, _f32p]),
+    "pies_b200_debug_island_trace": (C.c_int, [_vp, C.c_int, _vp, C.c_uint32, C.POINTER(C.c_uint32)]),
     "pies_b200_probe_tri_range": (C.c_int, [C.c_uint32, _f32p, _f32p, _i64p, _u32p]),
     "pies_b200_probe_node_range": (C.c_int, [C.c_uint32, _f32p, _f32p, C.c_float, _i64p, _u32p]),
     "pies_b200_probe_sort_pairs": (C.c_int, [C.c_uint64, _u64p, _u32p, C.c_int]),
@@ -420,6 +421,16 @@ class Solver:
         if nnz.value:
             self._ck(lib().pies_b200_get_collision_csr(self.h, C.byref(nnz), None, p(col), p(val), None))
         return ptr, col, val, diag
+
+    def debugIslandTrace(self, slot):
+        """Diagnostics: (rows, iterations, SM clocks, matrix entries) per island of list `slot` in the last global solve
+        (PIES_B200_ISLAND_TRACE must be set in the environment before the first tick)."""
+        cnt = C.c_uint32(0)
+        self._ck(lib().pies_b200_debug_island_trace(self.h, int(slot), None, 0, C.byref(cnt)))
+        out = np.zeros((cnt.value, 4), np.uint32)
+        if cnt.value:
+            self._ck(lib().pies_b200_debug_island_trace(self.h, int(slot), out.ctypes.data_as(C.c_void_p), cnt.value, C.byref(cnt)))
+        return out
 
     def staticCollisions(self):
         out = np.empty(lib().pies_b200_static_collision_count(self.h), dtype=np.uint32)

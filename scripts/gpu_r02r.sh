@@ -1,0 +1,17 @@
+#!/bin/bash
+OUT=gpurun_out/r02r; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_solver_gpu.py tests/test_configs_gpu.py tests/test_abi.py -m gpu -q -x > $OUT/pytest.log 2>&1; echo "pytest exit $?" | tee -a $OUT/pytest.log
+timeout 240 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
+PIES_B200_NO_DENSE=1 timeout 240 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_nodense.json 2> $OUT/bench_nodense.err; echo "bench nodense exit $?"
+timeout 200 python scripts/diag_island_trace.py > $OUT/trace.log 2>&1
+SKIP=60 TICKS=1 timeout 180 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv python scripts/prof_ticks.py > $OUT/launches.log 2>&1
+python scripts/launch_summary.py $OUT/launches.csv > $OUT/launches.summary.txt 2>&1
+SKIP=60 TICKS=1 timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"k_island_invert|k_island_dense" -c 3 -f -o $OUT/prof_dense python scripts/prof_ticks.py > $OUT/prof.log 2>&1
+ls -la $OUT
+grep -v "^$" $OUT/pytest.log | tail -12; cat $OUT/trace.log | tail -14; python - <<'PY'
+import json
+for f in ("bench","bench_nodense"):
+    d=json.loads([l for l in open('gpurun_out/r02r/%s.json'%f) if l.startswith('{')][0])
+    print(f, {k:d[k] for k in ("value","ms_per_step","phase_ms_per_step","pcg_iterations_per_step")}, "e2e", d["e2e"]["ms_per_step"], "ff", d["free_fall"]["ms_per_step"], d["free_fall"]["phase_ms_per_step"])
+PY
+head -24 $OUT/launches.summary.txt

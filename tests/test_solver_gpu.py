@@ -414,6 +414,40 @@ def test_island_block_table_overflow_path(pb, monkeypatch):
     assert np.abs(a.positions - b).max() <= 1e-6 * bbox_diag(b)   # same arithmetic from another memory space
 
 
+@pytest.mark.parametrize("switch", ["PIES_B200_NO_DENSE", "PIES_B200_NO_DENSE,PIES_B200_NO_SMALL_CTA", "PIES_B200_WARP_TIER_STAGED"])
+def test_island_list_switches_agree(pb, switch):
+    """The A/B switches of the island lists (no dense-inverse list, no 128-thread list, staged warp tier) route the same
+    islands through the other kernels; all of them solve to the same tolerance, so the trajectories agree like the
+    island / grid-wide pair above (compared while the contact counts agree)."""
+    import subprocess, sys, os
+    ticks = 44
+    a = _stack(pb)
+    counts_a = []
+    for _ in range(ticks):
+        a.tick()
+        st = a.stats()
+        counts_a.append((st.triCollisions, st.staticCollisions))
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np; import pies_b200 as pb; from pies_b200 import scenes\n"
+            "s = pb.Solver(**scenes.S3_OPTIONS); scenes.build_s3(s, bodies=48, nx=2, nz=2)\n"
+            "c = []\n"
+            "for _ in range(%d):\n"
+            "    s.tick(); st = s.stats(); c.append((st.triCollisions, st.staticCollisions, st.pcgCapHits))\n"
+            "np.savez(sys.argv[1], pos=s.positions, counts=np.array(c))" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ticks))
+    out = os.path.join(os.environ.get("TMPDIR", "/tmp"), "pies_island_switch.npz")
+    env = dict(os.environ)
+    for name in switch.split(","):
+        env[name] = "1"
+    subprocess.run([sys.executable, "-c", code, out], check=True, env=env)   # the env hooks are read once per process
+    b = np.load(out)
+    assert (b["counts"][:, 2] == 0).all()
+    assert np.isfinite(b["pos"]).all()
+    if [tuple(r[:2]) for r in b["counts"]] == counts_a:
+        assert np.abs(a.positions - b["pos"]).max() <= 1e-4 * bbox_diag(b["pos"]), switch
+    else:   # a threshold contact caught by one run only: the scene diverges like the reference does from itself
+        first = next(i for i, r in enumerate(b["counts"]) if tuple(r[:2]) != counts_a[i])
+        assert first >= 30, (switch, first)
+
+
 def test_pcg_cap_is_loud(pb):
     """A solve that stops at pcgMaxIterations far from its tolerance is reported: counter, residual and an error code
     (the reference's Cholesky cannot fail this way, so silence would hide a wrong trajectory)."""
