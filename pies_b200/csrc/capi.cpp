@@ -483,11 +483,34 @@ int pies_b200_get_static_collisions(PiesB200Solver* s, uint32_t* ids) {
   PIES_CHECK(s, cudaMemcpy(ids, s->detect->floorList.p, 4ull * s->stats.staticCollisions, cudaMemcpyDeviceToHost));
   return PIES_B200_OK;
 }
+// The occupied cells are the runs of equal keys of the sorted (cell, triangle) table; counted on the host from a copy of
+// the keys (a parity readback, not a hot path), so it does not depend on which cell-start table the detection built.
+static int triOccupancyStarts(PiesB200Solver* s, std::vector<uint64_t>& keys, std::vector<uint32_t>& start) {
+  pies::DetectWork& w = *s->detect;
+  const uint64_t P = w.nPairs;
+  keys.resize(P);
+  start.clear();
+  if (!P) { start.push_back(0); return PIES_B200_OK; }
+  cudaSetDevice(s->device);
+  PIES_CHECK(s, cudaStreamSynchronize(s->stream));
+  PIES_CHECK(s, cudaMemcpy(keys.data(), w.keys.p, P * 8, cudaMemcpyDeviceToHost));
+  for (uint64_t j = 0; j < P; ++j) if (j == 0 || keys[j] != keys[j - 1]) start.push_back((uint32_t)j);
+  start.push_back((uint32_t)P);
+  return PIES_B200_OK;
+}
 int pies_b200_tri_occupancy_counts(PiesB200Solver* s, uint64_t* nCells, uint64_t* nMembers) {
   if (!s || !nCells || !nMembers) return PIES_B200_EINVAL;
-  *nCells = s->detect ? s->detect->nCells : 0;
-  *nMembers = s->detect ? s->detect->nPairs : 0;
-  return PIES_B200_OK;
+  *nCells = 0; *nMembers = 0;
+  if (!s->detect) return PIES_B200_OK;
+  return guarded(s, [&]() {
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> start;
+    int rc = triOccupancyStarts(s, keys, start);
+    if (rc) return rc;
+    *nCells = start.size() - 1;
+    *nMembers = s->detect->nPairs;
+    return PIES_B200_OK;
+  });
 }
 int pies_b200_get_tri_occupancy(PiesB200Solver* s, int64_t* cells, uint32_t* counts, uint32_t* members) {
   if (!s || !s->detect) return PIES_B200_EINVAL;
@@ -495,20 +518,20 @@ int pies_b200_get_tri_occupancy(PiesB200Solver* s, int64_t* cells, uint32_t* cou
     pies::DetectWork& w = *s->detect;
     uint64_t P = w.nPairs;
     if (!P) return PIES_B200_OK;
-    std::vector<uint64_t> keys(P);
-    std::vector<uint32_t> mem(P), start(w.nCells + 1);
-    PIES_CHECK(s, cudaMemcpy(keys.data(), w.keys.p, P * 8, cudaMemcpyDeviceToHost));
-    PIES_CHECK(s, cudaMemcpy(mem.data(), w.vals.p, P * 4, cudaMemcpyDeviceToHost));
-    PIES_CHECK(s, cudaMemcpy(start.data(), w.cellStart.p, (w.nCells + 1ull) * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> start;
+    int rc = triOccupancyStarts(s, keys, start);
+    if (rc) return rc;
+    const uint32_t nCells = (uint32_t)start.size() - 1;
+    PIES_CHECK(s, cudaMemcpy(members, w.vals.p, P * 4, cudaMemcpyDeviceToHost));
     int by = w.keyPack[3], bz = w.keyPack[4];
-    for (uint32_t c = 0; c < w.nCells; ++c) {
+    for (uint32_t c = 0; c < nCells; ++c) {
       uint64_t k = keys[start[c]];
       cells[3 * c] = (int64_t)(k >> (by + bz)) + w.keyPack[0];
       cells[3 * c + 1] = (int64_t)((k >> bz) & ((1ull << by) - 1)) + w.keyPack[1];
       cells[3 * c + 2] = (int64_t)(k & ((1ull << bz) - 1)) + w.keyPack[2];
       counts[c] = start[c + 1] - start[c];
     }
-    std::memcpy(members, mem.data(), P * 4);
     return PIES_B200_OK;
   });
 }

@@ -55,10 +55,10 @@ __global__ void __launch_bounds__(kThreads) k_floor_project(uint32_t nFloor, con
 }
 
 int launchContactProject(cudaStream_t s, const ContactLists& c, const float4* q, float thickness, float4* contribC,
-                         float4* snap) {
+                         float4* snap, bool floorToo) {
   int L = 0;
   if (c.nUnique) { k_pt_project<<<gridFor(c.nUnique, kThreads), kThreads, 0, s>>>(c.nUnique, c.uTri, c.uW, q, thickness, contribC); ++L; }
-  if (c.nFloor) { k_floor_project<<<gridFor(c.nFloor, kThreads), kThreads, 0, s>>>(c.nFloor, c.floorNode, q, snap); ++L; }
+  if (c.nFloor && floorToo) { k_floor_project<<<gridFor(c.nFloor, kThreads), kThreads, 0, s>>>(c.nFloor, c.floorNode, q, snap); ++L; }
   return L;
 }
 
@@ -83,6 +83,51 @@ __global__ void __launch_bounds__(kThreads) k_gather_contacts(uint32_t n, Contac
     for (uint32_t k = 0; k < mult; ++k) { acc.x += kFloorW * p.x; acc.y += kFloorW * p.y; acc.z += kFloorW * p.z; }
   }
   rhs[i] = acc;
+}
+
+// The whole right-hand side in one pass when there are contacts: k_gather_rhs (pd_kernels.cu), then the collision
+// contributions and the floor terms exactly as k_floor_project + k_gather_contacts add them (same values, same order, so
+// the result is bit-identical) — one launch and one read-modify-write of rhs less per PD iteration.
+__global__ void __launch_bounds__(kThreads) k_gather_rhs_contacts(uint32_t n, const float4* __restrict__ msn,
+                                                                  const int* __restrict__ incPtr,
+                                                                  const uint32_t* __restrict__ inc,
+                                                                  const float4* __restrict__ contrib, ContactLists c,
+                                                                  const float4* __restrict__ contribC,
+                                                                  const float4* __restrict__ q, float4* __restrict__ snap,
+                                                                  float4* __restrict__ rhs) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 acc = ldStream(msn + i);
+  {
+    const int beg = incPtr[i], end = incPtr[i + 1];
+    for (int k = beg; k < end; ++k) {
+      float4 cv = __ldg(contrib + inc[k]);
+      acc.x += cv.x; acc.y += cv.y; acc.z += cv.z;
+    }
+  }
+  int beg = 0, end = 0;
+  if (c.nTri) { beg = c.incPtr[i]; end = c.incPtr[i + 1]; }
+  const uint32_t mult = c.nFloor ? c.floorMult[i] : 0u;
+  for (int k = beg; k < end; ++k) {
+    float4 v = contribC[c.inc[k]];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z;
+  }
+  if (mult) {
+    float4 p = q[i];
+    if (p.y < 0.0f) p.y = 0.0f;
+    snap[i] = p;
+    for (uint32_t k = 0; k < mult; ++k) { acc.x += kFloorW * p.x; acc.y += kFloorW * p.y; acc.z += kFloorW * p.z; }
+  }
+  acc.w = 0.0f;
+  rhs[i] = acc;
+}
+
+int launchGatherRhsContacts(cudaStream_t s, uint32_t n, const float4* msn, const int* incPtr, const uint32_t* inc,
+                            const float4* contrib, const ContactLists& c, const float4* contribC, const float4* q,
+                            float4* snap, float4* rhs) {
+  if (!n) return 0;
+  k_gather_rhs_contacts<<<gridFor(n, kThreads), kThreads, 0, s>>>(n, msn, incPtr, inc, contrib, c, contribC, q, snap, rhs);
+  return 1;
 }
 
 int launchGatherContacts(cudaStream_t s, uint32_t n, const ContactLists& c, const float4* contribC, const float4* snap,
@@ -621,6 +666,7 @@ void preloadContactKernels() {
   cudaFuncGetAttributes(&a, k_gs_mid<true>);
   cudaFuncGetAttributes(&a, k_gs_mid<false>);
   cudaFuncGetAttributes(&a, k_floor_snap);
+  cudaFuncGetAttributes(&a, k_gather_rhs_contacts);
   cudaFuncGetAttributes(&a, k_floor_friction);
 }
 

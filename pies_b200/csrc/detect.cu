@@ -17,6 +17,10 @@
 
 #include "ccd.cuh"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 namespace pies {
 
 static inline int gridFor(uint64_t n, int threads) { return (int)((n + threads - 1) / threads); }
@@ -129,6 +133,42 @@ __global__ void __launch_bounds__(kThreads) k_emit_pairs(uint32_t nTri, const in
       }
 }
 
+// ---- 2b. small grids: a direct cell table instead of the radix sort --------------------------------
+// When the occupied bounding box has at most 2^22 cells the sorted table is built by counting: every pair takes an
+// arrival number from its cell's counter, the counters are scanned into the cell starts, the members are placed at
+// start + arrival (arbitrary order) and every pair then finds its rank among its cell's members (ascending triangle
+// index = the bucket order of the reference).  The cell index of a pair is its key; empty cells are empty ranges.
+__global__ void __launch_bounds__(kThreads) k_cell_count(uint64_t nPairs, const uint64_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ table, uint32_t* __restrict__ arrival) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nPairs) return;
+  arrival[i] = atomicAdd(table + (uint32_t)keys[i], 1u);
+}
+
+__global__ void __launch_bounds__(kThreads) k_cell_place(uint64_t nPairs, const uint64_t* __restrict__ keys,
+                                                         const uint32_t* __restrict__ vals, const uint32_t* __restrict__ table,
+                                                         const uint32_t* __restrict__ arrival, uint32_t* __restrict__ placed) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nPairs) return;
+  placed[table[(uint32_t)keys[i]] + arrival[i]] = vals[i];
+}
+
+__global__ void __launch_bounds__(kThreads) k_cell_rank(uint64_t nPairs, const uint64_t* __restrict__ keys,
+                                                        const uint32_t* __restrict__ vals, const uint32_t* __restrict__ table,
+                                                        const uint32_t* __restrict__ placed, uint64_t* __restrict__ outKeys,
+                                                        uint32_t* __restrict__ outVals, uint32_t* __restrict__ cellIdx) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nPairs) return;
+  const uint64_t key = keys[i];
+  const uint32_t t = vals[i];
+  const uint32_t b = table[(uint32_t)key], e = table[(uint32_t)key + 1];
+  uint32_t rank = 0;
+  for (uint32_t k = b; k < e; ++k) rank += placed[k] < t ? 1u : 0u;
+  outKeys[b + rank] = key;
+  outVals[b + rank] = t;
+  cellIdx[b + rank] = (uint32_t)key;
+}
+
 // ---- 3. cell-start table -------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_mark_heads(uint64_t nPairs, const uint64_t* __restrict__ keys,
                                                          uint32_t* __restrict__ heads) {
@@ -223,6 +263,8 @@ __global__ void __launch_bounds__(kThreads) k_pair_filter(NarrowParams np, KeyPa
         uLo[c] = fminf(cLo[0][c], fminf(cLo[1][c], cLo[2][c]));
         uHi[c] = fmaxf(cHi[0][c], fmaxf(cHi[1][c], cHi[2][c]));
       }
+      // (a software-pipelined variant — member records one iteration ahead — was measured slower, r02t: 364 vs 330 us;
+      // the registers it takes cost more occupancy than the overlap wins)
       uint32_t oNext = memberTri[s];
       for (uint32_t m = s; m < e; ++m) {
         const uint32_t o = oNext;
@@ -528,6 +570,11 @@ static int bitsFor(int64_t span) {  // bits to hold values 0..span
 
 int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, ContactLists& out, int* launches) {
   int L = 0;
+  // diagnostics: host time stamps around the three synchronisations (PIES_B200_DETECT_TRACE)
+  static const bool traceOn = std::getenv("PIES_B200_DETECT_TRACE") != nullptr;
+  double stamp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto mark = [&](int k) { if (traceOn) stamp[k] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  mark(0);
   const uint32_t nTri = in.nTri, n = in.nNodes;
   const uint32_t T = in.threadCount ? in.threadCount : 1u;
   const float floorLimit = in.floorLimit;
@@ -557,7 +604,9 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
   DCHECK(cudaMemcpyAsync(w.host, w.bbox.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
   DCHECK(cudaMemcpyAsync(w.host + 8, w.cnt.p + nTri, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   DCHECK(cudaMemcpyAsync(w.host + 11, w.floorRank.p + nTri, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  mark(1);
   DCHECK(cudaStreamSynchronize(s));
+  mark(2);
   if (w.host[6]) { w.badInput = true; return 0; }
   if (w.host[7]) { w.failed = true; if (launches) *launches += L; return 0; }  // reference latches _simFailed, lists stay empty
   uint64_t nPairs = (uint32_t)w.host[8];
@@ -578,12 +627,34 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
     DCHECK(w.sortHist.reserve(sortHistBytes(nPairs) / 4 + 4));
     w.scanCap = std::max<uint64_t>(w.scanCap, nPairs + 2);
     DCHECK(w.scanScratch.reserve(scanScratchElems(w.scanCap)));
-    k_emit_pairs<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, w.triMin.p, w.triRec.p, w.cnt.p, kp, w.keys.p, w.vals.p); ++L;
-    L += launchSortPairs(s, nPairs, w.keys.p, w.vals.p, w.tmpKeys.p, w.tmpVals.p, w.sortHist.p, bx + by + bz);
-    k_mark_heads<<<gridFor(nPairs + 1, kThreads), kThreads, 0, s>>>(nPairs, w.keys.p, w.heads.p); ++L;
-    L += launchExclusiveScan(s, w.heads.p, nPairs + 1, w.scanScratch.p);
-    DCHECK(cudaMemcpyAsync(w.host + 9, w.heads.p + nPairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    k_cell_starts<<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(nPairs, w.keys.p, w.heads.p, w.cellStart.p); ++L;
+    static const bool noCellTable = std::getenv("PIES_B200_NO_CELL_TABLE") != nullptr;   // A/B switch: always radix-sort
+    const int keyBits = bx + by + bz;
+    const bool direct = keyBits <= 22 && !noCellTable;
+    const uint32_t* cellStart = nullptr;
+    if (direct) {
+      const size_t cells = (size_t)1 << keyBits;
+      DCHECK(w.cellTable.reserve(cells + 2)); DCHECK(w.arrivalP.reserve(nPairs)); DCHECK(w.placedP.reserve(nPairs));
+      w.scanCap = std::max<uint64_t>(w.scanCap, cells + 2);
+      DCHECK(w.scanScratch.reserve(scanScratchElems(w.scanCap)));
+      DCHECK(cudaMemsetAsync(w.cellTable.p, 0, (cells + 2) * sizeof(uint32_t), s));
+      k_emit_pairs<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, w.triMin.p, w.triRec.p, w.cnt.p, kp, w.tmpKeys.p, w.tmpVals.p); ++L;
+      k_cell_count<<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(nPairs, w.tmpKeys.p, w.cellTable.p, w.arrivalP.p); ++L;
+      L += launchExclusiveScan(s, w.cellTable.p, cells + 1, w.scanScratch.p);
+      k_cell_place<<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(nPairs, w.tmpKeys.p, w.tmpVals.p, w.cellTable.p, w.arrivalP.p,
+                                                                 w.placedP.p); ++L;
+      k_cell_rank<<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(nPairs, w.tmpKeys.p, w.tmpVals.p, w.cellTable.p, w.placedP.p,
+                                                                w.keys.p, w.vals.p, w.heads.p); ++L;
+      w.host[9] = 0;
+      cellStart = w.cellTable.p;
+    } else {
+      k_emit_pairs<<<gridFor(nTri, kThreads), kThreads, 0, s>>>(nTri, w.triMin.p, w.triRec.p, w.cnt.p, kp, w.keys.p, w.vals.p); ++L;
+      L += launchSortPairs(s, nPairs, w.keys.p, w.vals.p, w.tmpKeys.p, w.tmpVals.p, w.sortHist.p, keyBits);
+      k_mark_heads<<<gridFor(nPairs + 1, kThreads), kThreads, 0, s>>>(nPairs, w.keys.p, w.heads.p); ++L;
+      L += launchExclusiveScan(s, w.heads.p, nPairs + 1, w.scanScratch.p);
+      DCHECK(cudaMemcpyAsync(w.host + 9, w.heads.p + nPairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      k_cell_starts<<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(nPairs, w.keys.p, w.heads.p, w.cellStart.p); ++L;
+      cellStart = w.cellStart.p;
+    }
     // candidate filter (one pass, capacity from the previous substep; redone if it overflows), CCD, hits per slot, scan
     DCHECK(w.pairRun.reserve(nPairs)); DCHECK(w.pairSlot.reserve(nPairs));
     uint32_t nCand = 0, cap = 0;
@@ -591,7 +662,7 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
       cap = std::max<uint32_t>(w.candCap, 1u << 16);
       DCHECK(w.cand.reserve(cap)); DCHECK(w.candHit.reserve((size_t)cap + 16));
       DCHECK(cudaMemsetAsync(w.bbox.p + 8, 0, sizeof(int), s));
-      k_pair_filter<<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p, w.cellStart.p,
+      k_pair_filter<<<gridFor(nPairs, kThreads), kThreads, 0, s>>>(np, kp, nPairs, w.keys.p, w.vals.p, w.heads.p, cellStart,
                                                                  w.triRec.p, w.triMin.p, w.aabbLo.p, w.aabbHi.p, in.q, in.prev,
                                                                  w.cntRank.p, w.pairRun.p, w.pairSlot.p, w.cand.p, cap,
                                                                  (uint32_t*)(w.bbox.p + 8), w.bbox.p + 7); ++L;
@@ -603,7 +674,9 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
       DCHECK(cudaMemcpyAsync(w.host + 14, w.bbox.p + 8, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       DCHECK(cudaMemcpyAsync(w.host + 12, w.bbox.p + 7, sizeof(int), cudaMemcpyDeviceToHost, s));
       DCHECK(cudaMemcpyAsync(w.host + 10, w.hitCount.p + nPairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      mark(3);
       DCHECK(cudaStreamSynchronize(s));
+      mark(4);
       nCand = (uint32_t)w.host[14];
       if (nCand <= cap) break;
       if (attempt == 1) { w.lastError = cudaErrorUnknown; return -1; }  // the count cannot change between attempts
@@ -678,8 +751,14 @@ int detectTriangles(DetectWork& w, cudaStream_t s, const DetectInput& in, Contac
     if (nU) { out.cPtr = (int*)w.cPtr.p; out.cCol = w.cCol.p; out.cVal = w.cVal.p; }
   }
   if (nHit) {
+    mark(5);
     DCHECK(cudaStreamSynchronize(s));
+    mark(6);
     out.nUnique = w.nUnique = (uint32_t)w.host[13];
+    if (traceOn)
+      std::fprintf(stderr, "[detect] enqueue1 %.0f us, wait1 %.0f | enqueue2 %.0f, wait2 %.0f | enqueue3 %.0f, wait3 %.0f | pairs %llu hits %u\n",
+                   stamp[1] - stamp[0], stamp[2] - stamp[1], stamp[3] - stamp[2], stamp[4] - stamp[3], stamp[5] - stamp[4],
+                   stamp[6] - stamp[5], (unsigned long long)nPairs, nHit);
   }
   if (launches) *launches += L;
   return 0;
@@ -692,6 +771,9 @@ void preloadDetectKernels() {
   cudaFuncGetAttributes(&a, k_tri_ranges);
   cudaFuncGetAttributes(&a, k_floor_write);
   cudaFuncGetAttributes(&a, k_emit_pairs);
+  cudaFuncGetAttributes(&a, k_cell_count);
+  cudaFuncGetAttributes(&a, k_cell_place);
+  cudaFuncGetAttributes(&a, k_cell_rank);
   cudaFuncGetAttributes(&a, k_mark_heads);
   cudaFuncGetAttributes(&a, k_cell_starts);
   cudaFuncGetAttributes(&a, k_pair_filter);

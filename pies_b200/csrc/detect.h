@@ -28,6 +28,8 @@ struct DetectWork {
       ticket, nodeDone;
   // node incidence (counting sort): arrival numbers, placed items, per-item scratch of the distinct-contact ranking
   DevBuf<uint32_t> arrival, placed, pointTri, headTri, uMult;
+  // small grids: direct cell table (counts -> starts), arrival numbers and unordered placement of the (cell, triangle) pairs
+  DevBuf<uint32_t> cellTable, arrivalP, placedP;
   DevBuf<uint4> triList, uTri;     // full list (canonical order) and distinct contacts
   DevBuf<uint32_t> otherTri, uStart, uIncPtr, uInc, pairSlot;
   DevBuf<uint8_t> candHit;

@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(kInvThreads, 2) k_island_invert(IslandArgs a, 
         }
         __syncthreads();
         if (mine) {
-          const float d = 1.0f / rowBuf[k];
+          const float d = __frcp_rn(rowBuf[k]);
           float rv[8], cv[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) rv[c] = rowBuf[8 * tx + c];
@@ -1076,12 +1076,14 @@ IslandCaps tierCaps(int t) {
 IslandLayout tierLayout(int t) { return islandLayout(kTiers[t].caps, kTiers[t].team, kTiers[t].matSmem); }
 size_t tierSmem(int t) { return (size_t)tierLayout(t).total * (kTiers[t].team == 32 ? 8 : 1); }
 
+// t: whose team size, shared-memory layout and capacities; list: which island list (the same unless a list is handed to
+// a larger team)
 template <typename K>
-void launchTier(K kernel, int t, int grid, cudaStream_t s, const IslandArgs& a) {
+void launchTier(K kernel, int t, int grid, cudaStream_t s, const IslandArgs& a, int list = -1) {
   const size_t smem = tierSmem(t);
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int threads = kTiers[t].team == 32 ? 256 : kTiers[t].team;
-  kernel<<<grid, threads, smem, s>>>(a, tierLayout(t), tierCaps(t), t);
+  kernel<<<grid, threads, smem, s>>>(a, tierLayout(t), tierCaps(t), list < 0 ? t : list);
 }
 }  // namespace
 
@@ -1237,7 +1239,12 @@ int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const C
   if (w.tierCount[2]) { launchTier(k_island_pcg<512, 2, true>, 2, (int)std::min<uint32_t>(w.tierCount[2], kNumSMs), nextStream(), a); ++L; }
   if (w.tierCount[1]) { launchTier(k_island_pcg<320, 2, true>, 1, (int)std::min<uint32_t>(w.tierCount[1], 2 * kNumSMs), nextStream(), a); ++L; }
   if (w.tierCount[kSmallCtaSlot]) {
-    launchTier(k_island_pcg<128, 2, true>, kSmallCtaSlot, (int)std::min<uint32_t>(w.tierCount[kSmallCtaSlot], 5 * kNumSMs), nextStream(), a);
+    // A short list is latency bound (the solve waits for its slowest island, one warp per scheduler has nothing to hide
+    // a dependent shared-memory load behind): the 320-thread team gives every row its own thread.  A long list is
+    // throughput bound: five 128-thread CTAs per SM.
+    const uint32_t ns = w.tierCount[kSmallCtaSlot];
+    if (ns <= 2u * kNumSMs) launchTier(k_island_pcg<320, 2, true>, 1, (int)ns, nextStream(), a, kSmallCtaSlot);
+    else launchTier(k_island_pcg<128, 2, true>, kSmallCtaSlot, (int)std::min<uint32_t>(ns, 5 * kNumSMs), nextStream(), a);
     ++L;
   }
   if (w.tierCount[kDenseSlot]) {

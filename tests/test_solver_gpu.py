@@ -414,10 +414,11 @@ def test_island_block_table_overflow_path(pb, monkeypatch):
     assert np.abs(a.positions - b).max() <= 1e-6 * bbox_diag(b)   # same arithmetic from another memory space
 
 
-@pytest.mark.parametrize("switch", ["PIES_B200_NO_DENSE", "PIES_B200_NO_DENSE,PIES_B200_NO_SMALL_CTA", "PIES_B200_WARP_TIER_STAGED"])
+@pytest.mark.parametrize("switch", ["PIES_B200_NO_DENSE", "PIES_B200_NO_DENSE,PIES_B200_NO_SMALL_CTA", "PIES_B200_WARP_TIER_STAGED",
+                                    "PIES_B200_NO_CELL_TABLE"])
 def test_island_list_switches_agree(pb, switch):
-    """The A/B switches of the island lists (no dense-inverse list, no 128-thread list, staged warp tier) route the same
-    islands through the other kernels; all of them solve to the same tolerance, so the trajectories agree like the
+    """The A/B switches (no dense-inverse list, no 128-thread list, staged warp tier, radix-sorted cell table) route the same
+    work through the other kernels; all of them solve to the same tolerance, so the trajectories agree like the
     island / grid-wide pair above (compared while the contact counts agree)."""
     import subprocess, sys, os
     ticks = 44
@@ -441,7 +442,10 @@ def test_island_list_switches_agree(pb, switch):
     b = np.load(out)
     assert (b["counts"][:, 2] == 0).all()
     assert np.isfinite(b["pos"]).all()
-    if [tuple(r[:2]) for r in b["counts"]] == counts_a:
+    if switch == "PIES_B200_NO_CELL_TABLE":   # radix-sorted cell table instead of the direct one: the same lists, bit for bit
+        assert [tuple(r[:2]) for r in b["counts"]] == counts_a
+        assert np.array_equal(a.positions, b["pos"])
+    elif [tuple(r[:2]) for r in b["counts"]] == counts_a:
         assert np.abs(a.positions - b["pos"]).max() <= 1e-4 * bbox_diag(b["pos"]), switch
     else:   # a threshold contact caught by one run only: the scene diverges like the reference does from itself
         first = next(i for i, r in enumerate(b["counts"]) if tuple(r[:2]) != counts_a[i])
