@@ -278,7 +278,7 @@ int pies_b200_halo_exchange(PiesB200Solver* s, int planes);      /* explicit exc
 int pies_b200_halo_destroy(PiesB200Solver* s);
 
 /* Diagnostics (needs PIES_B200_ISLAND_TRACE in the environment before the first tick): the island-local solve's record
- * of the LAST global solve for list `slot` (0 warp, 1 CTA-320, 2 CTA-512, 3 CTA-1024, 4 CTA-128): four words per island —
+ * of the LAST global solve for list `slot` (0 warp, 1 CTA-320, 2 CTA-512, 3 CTA-1024, 4 CTA-128, 5 dense <= 128 nodes, 6 dense <= 192 nodes): four words per island —
  * rows, CG iterations, SM clocks, matrix entries.  *count receives the number of islands in the list. */
 int pies_b200_debug_island_trace(PiesB200Solver* s, int slot, uint32_t* out4, uint32_t cap, uint32_t* count);
 

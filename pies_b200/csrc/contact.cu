@@ -100,7 +100,16 @@ __global__ void __launch_bounds__(kThreads) k_gather_rhs_contacts(uint32_t n, co
   float4 acc = ldStream(msn + i);
   {
     const int beg = incPtr[i], end = incPtr[i + 1];
-    for (int k = beg; k < end; ++k) {
+    int k = beg;
+    for (; k + 4 <= end; k += 4) {   // four gathers in flight; summed in list order (the result does not depend on the batching)
+      const uint32_t j0 = inc[k], j1 = inc[k + 1], j2 = inc[k + 2], j3 = inc[k + 3];
+      const float4 v0 = __ldg(contrib + j0), v1 = __ldg(contrib + j1), v2 = __ldg(contrib + j2), v3 = __ldg(contrib + j3);
+      acc.x += v0.x; acc.y += v0.y; acc.z += v0.z;
+      acc.x += v1.x; acc.y += v1.y; acc.z += v1.z;
+      acc.x += v2.x; acc.y += v2.y; acc.z += v2.z;
+      acc.x += v3.x; acc.y += v3.y; acc.z += v3.z;
+    }
+    for (; k < end; ++k) {
       float4 cv = __ldg(contrib + inc[k]);
       acc.x += cv.x; acc.y += cv.y; acc.z += cv.z;
     }

@@ -491,7 +491,7 @@ int pdSubstepBegin(PiesB200Solver* s) {
       }
       s->launches += LI;
       for (int t = 0; t < kIslandTiers; ++t) s->stats.islandsTier[t] = s->islands->tierCount[t];
-      s->stats.islandsTier[1] += s->islands->tierCount[kSmallCtaSlot] + s->islands->tierCount[kDenseSlot];
+      s->stats.islandsTier[1] += s->islands->tierCount[kSmallCtaSlot] + s->islands->tierCount[kDenseSlot] + s->islands->tierCount[kDenseSlot2];
       s->stats.islandsGlobal = s->islands->nLeftIslands;
       s->stats.islandNodesGlobal = s->islands->nLeftNodes;
     }
@@ -533,6 +533,10 @@ int pdIteration(PiesB200Solver* s) {
   timer.end(spLocal);
 
   const int spGlobal = timer.begin(kPhGlobal);
+  if (s->blocks && s->blocks->factorPending) {   // this substep's block inverses (side stream of rebuildBlocks)
+    PD_CHECK(s, cudaStreamWaitEvent(st, s->blocks->factorDone, 0));
+    s->blocks->factorPending = false;
+  }
   const uint32_t k = c->iterIndex++;
   const uint32_t solveSlot = c->solveIndex++;
   uint32_t used = 0;
@@ -615,6 +619,9 @@ int pdSubstepEnd(PiesB200Solver* s) {
   const float h = o.fixedTimestepSize / (float)o.timeSubsteps;
   PhaseTimer& timer = c->timer;
   const ContactLists& lists = c->lists;
+  // nothing of this substep's side-stream preparation may outlive it (a substep without PD iterations never waited)
+  if (s->blocks && s->blocks->factorPending) { PD_CHECK(s, cudaStreamWaitEvent(st, s->blocks->factorDone, 0)); s->blocks->factorPending = false; }
+  if (s->islands && s->islands->prepPending) { PD_CHECK(s, cudaStreamWaitEvent(st, s->islands->prepDone, 0)); s->islands->prepPending = false; }
   timer.begin(kPhContact);
   if (s->contact)
     s->launches += launchStabilize(st, *s->contact, lists, n, s->q.p, s->prev.p, s->snap.p, o.collisionThickness,

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) k_isl_classify(const uint32_t* count
   const uint32_t s0 = islStart[isl], m = islStart[isl + 1] - s0;
   const uint32_t nnz = nnzOff[s0 + m] - nnzOff[s0];
   int tier = kIslandSlots;
-  const int tryOrder[kIslandSlots] = {0, kDenseSlot, kSmallCtaSlot, 1, 2, 3};  // smallest team first
+  const int tryOrder[kIslandSlots] = {0, kDenseSlot, kDenseSlot2, kSmallCtaSlot, 1, 2, 3};  // cheapest solve first
 #pragma unroll
   for (int o = 0; o < kIslandSlots; ++o) {
     const int t = tryOrder[o];
@@ -238,13 +238,28 @@ __device__ __forceinline__ void teamReduce(float (&v)[K], float* __restrict__ sR
   }
 }
 
-template <int TEAM, int RPT, bool MAT_SMEM>
+// SPLIT > 1: every row is shared by SPLIT neighbouring lanes (matrix entries and preconditioner terms strided over them,
+// partial sums combined by shuffles) — for a short list of mid-size islands, where the solve waits for the dependent
+// shared-memory loads of its one slowest island and more, shorter instruction streams are what helps.
+template <int SPLIT>
+__device__ __forceinline__ void splitSum3(float (&v)[3]) {
+#pragma unroll
+  for (int o = SPLIT / 2; o > 0; o >>= 1) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+  }
+}
+
+template <int TEAM, int RPT, bool MAT_SMEM, int SPLIT = 1>
 __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEAM <= 128 ? 5 : (TEAM <= 320 ? 2 : 1))) k_island_pcg(IslandArgs a, IslandLayout L, IslandCaps caps, int tier) {
+  static_assert(SPLIT == 1 || (TEAM > 32 && (32 % SPLIT) == 0), "lanes of a row sit in one warp");
+  constexpr int ROWS = TEAM / SPLIT;   // rows per pass of the team
   extern __shared__ __align__(16) unsigned char islSmem[];
   constexpr int kTeams = TEAM == 32 ? 8 : 1;
   using ColT = typename std::conditional<MAT_SMEM, uint16_t, int>::type;
   const int team = TEAM == 32 ? (int)(threadIdx.x >> 5) : 0;
   const int tid = TEAM == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  const int sub = tid % SPLIT, rt = tid / SPLIT;   // lane of the row, row of the pass
   unsigned char* base = islSmem + (size_t)team * L.total;
   float4* sR = reinterpret_cast<float4*>(base + L.r);
   float4* sP = reinterpret_cast<float4*>(base + L.p);
@@ -279,7 +294,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
     float red9[9] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // r.z (3), r.r (3), b.b (3)
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
-      const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+      const uint32_t l = (uint32_t)rt + (uint32_t)k * ROWS;
       rs[k] = 0; rn[k] = 0; rb[k] = 0xffffffffu; slot[k] = 0; gid[k] = 0; cdg[k] = 0.0f;
       dl[k][0] = dl[k][1] = dl[k][2] = 0.0f;
       if (l >= m) continue;
@@ -290,8 +305,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
       const int kk0 = a.rowPtr[g], kk1 = a.rowPtr[g + 1];
       const uint32_t bodyBase = l - a.rankInBody[g];
       const float4 bi = a.b[g];
-      sP[l] = a.x[g];
-      sR[l] = bi;
+      if (sub == 0) { sP[l] = a.x[g]; sR[l] = bi; }
       cdg[k] = a.cDiag ? a.cDiag[g] : 0.0f;
       const uint32_t sl = a.slotOf[g];
       slot[k] = sl;
@@ -316,21 +330,23 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
         }
       } else {
 #pragma unroll 4
-        for (int kk = kk0; kk < kk1; ++kk, ++e) {
+        for (int kk = kk0 + sub; kk < kk1; kk += SPLIT) {
           const uint32_t rk = __ldg(a.colRank + kk);
           const float v = __ldg(a.val + kk);
           const bool out = rk == 0xffffffffu;
-          mc[e] = (ColT)(out ? l : bodyBase + rk);
-          mv[e] = out ? 0.0f : v;
+          mc[e + (kk - kk0)] = (ColT)(out ? l : bodyBase + rk);
+          mv[e + (kk - kk0)] = out ? 0.0f : v;
         }
+        e += (uint32_t)(kk1 - kk0);
       }
       if (a.cPtr) {
         const int c0 = a.cPtr[g], c1 = a.cPtr[g + 1];
-        for (int kk = c0; kk < c1; ++kk, ++e) {
-          mc[e] = (ColT)(__ldg(a.pos + __ldg(a.cCol + kk)) - s0);
-          mv[e] = __ldg(a.cVal + kk);
+        for (int kk = c0 + sub; kk < c1; kk += SPLIT) {
+          mc[e + (kk - c0)] = (ColT)(__ldg(a.pos + __ldg(a.cCol + kk)) - s0);
+          mv[e + (kk - c0)] = __ldg(a.cVal + kk);
         }
       }
+      if (sub != 0) continue;   // the row's bookkeeping below belongs to its first lane
       red9[6] += bi.x * bi.x; red9[7] += bi.y * bi.y; red9[8] += bi.z * bi.z;
       a.blkLocal[sl] = l;
       if (caps.maxBlocks) {
@@ -352,25 +368,37 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
     // agree to ~7 digits and the difference is what matters
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
-      const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
-      if (l >= m) continue;
-      const float4 xi = sP[l];
-      double y0 = (double)cdg[k] * (double)xi.x, y1 = (double)cdg[k] * (double)xi.y, y2 = (double)cdg[k] * (double)xi.z;
-      const uint32_t e1 = rs[k] + rn[k];
+      const uint32_t l = (uint32_t)rt + (uint32_t)k * ROWS;
+      const bool act = l < m;
+      if (SPLIT == 1 && !act) continue;
+      double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+      if (act) {
+        if (sub == 0) {
+          const float4 xi = sP[l];
+          y0 = (double)cdg[k] * (double)xi.x; y1 = (double)cdg[k] * (double)xi.y; y2 = (double)cdg[k] * (double)xi.z;
+        }
+        const uint32_t e1 = rs[k] + rn[k];
 #pragma unroll 4
-      for (uint32_t e = rs[k]; e < e1; ++e) {
-        const double v = (double)mv[e];
-        const float4 xv = sP[mc[e]];
-        y0 += v * (double)xv.x; y1 += v * (double)xv.y; y2 += v * (double)xv.z;
+        for (uint32_t e = rs[k] + sub; e < e1; e += SPLIT) {
+          const double v = (double)mv[e];
+          const float4 xv = sP[mc[e]];
+          y0 += v * (double)xv.x; y1 += v * (double)xv.y; y2 += v * (double)xv.z;
+        }
       }
-      const float4 bi = sR[l];
-      sR[l] = make_float4((float)((double)bi.x - y0), (float)((double)bi.y - y1), (float)((double)bi.z - y2), 0.0f);
+#pragma unroll
+      for (int o = SPLIT / 2; o > 0; o >>= 1) {
+        y0 += __shfl_xor_sync(0xffffffffu, y0, o); y1 += __shfl_xor_sync(0xffffffffu, y1, o); y2 += __shfl_xor_sync(0xffffffffu, y2, o);
+      }
+      if (act && sub == 0) {
+        const float4 bi = sR[l];
+        sR[l] = make_float4((float)((double)bi.x - y0), (float)((double)bi.y - y1), (float)((double)bi.z - y2), 0.0f);
+      }
     }
     teamSync<TEAM>();
     if (caps.maxBlocks) {
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
-        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+        const uint32_t l = (uint32_t)rt + (uint32_t)k * ROWS;
         if (l >= m) continue;
         const uint32_t lead = a.pos[a.blockNodes[(slot[k] >> 5) * 32]] - s0;
         const uint32_t idx = sLeader[lead];
@@ -398,13 +426,23 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
         const int lane = (int)(rb[k] & 31u), mB = (int)sBlkM[idx];
         const float* inv = sInv + sBlkOff[idx];
         const uint16_t* mem = sMem + idx * 32;
-        int off = lane * (lane + 1) / 2;
+        if (SPLIT == 1) {
+          int off = lane * (lane + 1) / 2;
 #pragma unroll 3
-        for (int j = 0; j < mB; ++j) {
-          const float w = inv[off];
-          const float4 rj = sR[mem[j]];
-          z[0] = fmaf(w, rj.x, z[0]); z[1] = fmaf(w, rj.y, z[1]); z[2] = fmaf(w, rj.z, z[2]);
-          off += j < lane ? 1 : j + 1;
+          for (int j = 0; j < mB; ++j) {
+            const float w = inv[off];
+            const float4 rj = sR[mem[j]];
+            z[0] = fmaf(w, rj.x, z[0]); z[1] = fmaf(w, rj.y, z[1]); z[2] = fmaf(w, rj.z, z[2]);
+            off += j < lane ? 1 : j + 1;
+          }
+        } else {   // this lane's share of the row: terms sub, sub + SPLIT, ...
+          const int tri = lane * (lane + 1) / 2;
+#pragma unroll 2
+          for (int j = sub; j < mB; j += SPLIT) {
+            const float w = inv[j < lane ? tri + j : j * (j + 1) / 2 + lane];
+            const float4 rj = sR[mem[j]];
+            z[0] = fmaf(w, rj.x, z[0]); z[1] = fmaf(w, rj.y, z[1]); z[2] = fmaf(w, rj.z, z[2]);
+          }
         }
       } else {  // block not resident (tier 3, or the island has more blocks than the tier's table): same sum from global memory
         const uint32_t b = slot[k] >> 5;
@@ -412,12 +450,11 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
         const uint2 meta = a.blockMeta[b];
         const float* inv = a.blockInv + meta.x;
         const uint32_t* loc = a.blkLocal + (size_t)b * 32;
-        int off = lane * (lane + 1) / 2;
-        for (int j = 0; j < (int)meta.y; ++j) {
-          const float w = __ldg(inv + off);
+        const int tri = lane * (lane + 1) / 2;
+        for (int j = sub; j < (int)meta.y; j += SPLIT) {
+          const float w = __ldg(inv + (j < lane ? tri + j : j * (j + 1) / 2 + lane));
           const float4 rj = sR[loc[j]];
           z[0] = fmaf(w, rj.x, z[0]); z[1] = fmaf(w, rj.y, z[1]); z[2] = fmaf(w, rj.z, z[2]);
-          off += j < lane ? 1 : j + 1;
         }
       }
     };
@@ -428,9 +465,13 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
     float zz[RPT][3];
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
-      const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
-      if (l >= m) continue;
-      precond(k, zz[k]);
+      const uint32_t l = (uint32_t)rt + (uint32_t)k * ROWS;
+      const bool act = l < m;
+      if (SPLIT == 1 && !act) continue;
+      zz[k][0] = zz[k][1] = zz[k][2] = 0.0f;
+      if (act) precond(k, zz[k]);
+      splitSum3<SPLIT>(zz[k]);
+      if (!act || sub != 0) continue;
       const float4 r = sR[l];
       red9[0] += r.x * zz[k][0]; red9[1] += r.y * zz[k][1]; red9[2] += r.z * zz[k][2];
       red9[3] += r.x * r.x; red9[4] += r.y * r.y; red9[5] += r.z * r.z;
@@ -451,16 +492,21 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
       float pap[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
-        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
+        const uint32_t l = (uint32_t)rt + (uint32_t)k * ROWS;
         ap[k][0] = ap[k][1] = ap[k][2] = 0.0f;
-        if (l >= m) continue;
-        const uint32_t e1 = rs[k] + rn[k];
+        const bool act = l < m;
+        if (SPLIT == 1 && !act) continue;
+        if (act) {
+          const uint32_t e1 = rs[k] + rn[k];
 #pragma unroll 4
-        for (uint32_t e = rs[k]; e < e1; ++e) {
-          const float v = mv[e];
-          const float4 pv = sP[mc[e]];
-          ap[k][0] = fmaf(v, pv.x, ap[k][0]); ap[k][1] = fmaf(v, pv.y, ap[k][1]); ap[k][2] = fmaf(v, pv.z, ap[k][2]);
+          for (uint32_t e = rs[k] + sub; e < e1; e += SPLIT) {
+            const float v = mv[e];
+            const float4 pv = sP[mc[e]];
+            ap[k][0] = fmaf(v, pv.x, ap[k][0]); ap[k][1] = fmaf(v, pv.y, ap[k][1]); ap[k][2] = fmaf(v, pv.z, ap[k][2]);
+          }
         }
+        splitSum3<SPLIT>(ap[k]);
+        if (!act || sub != 0) continue;
         const float4 pl = sP[l];
         ap[k][0] = fmaf(cdg[k], pl.x, ap[k][0]); ap[k][1] = fmaf(cdg[k], pl.y, ap[k][1]); ap[k][2] = fmaf(cdg[k], pl.z, ap[k][2]);
         pap[0] += pl.x * ap[k][0]; pap[1] += pl.y * ap[k][1]; pap[2] += pl.z * ap[k][2];
@@ -472,8 +518,8 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
       float rl[RPT][3];
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
-        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
-        if (l >= m) continue;
+        const uint32_t l = (uint32_t)rt + (uint32_t)k * ROWS;
+        if (l >= m || sub != 0) continue;
         const float4 pl = sP[l];
         dl[k][0] = fmaf(alpha[0], pl.x, dl[k][0]); dl[k][1] = fmaf(alpha[1], pl.y, dl[k][1]); dl[k][2] = fmaf(alpha[2], pl.z, dl[k][2]);
         const float4 r = sR[l];
@@ -484,9 +530,13 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
       float red6[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
-        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
-        if (l >= m) continue;
-        precond(k, zz[k]);
+        const uint32_t l = (uint32_t)rt + (uint32_t)k * ROWS;
+        const bool act = l < m;
+        if (SPLIT == 1 && !act) continue;
+        zz[k][0] = zz[k][1] = zz[k][2] = 0.0f;
+        if (act) precond(k, zz[k]);
+        splitSum3<SPLIT>(zz[k]);
+        if (!act || sub != 0) continue;
         red6[0] += rl[k][0] * zz[k][0]; red6[1] += rl[k][1] * zz[k][1]; red6[2] += rl[k][2] * zz[k][2];
         red6[3] += rl[k][0] * rl[k][0]; red6[4] += rl[k][1] * rl[k][1]; red6[5] += rl[k][2] * rl[k][2];
       }
@@ -499,8 +549,8 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
       if (conv) break;
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
-        const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
-        if (l >= m) continue;
+        const uint32_t l = (uint32_t)rt + (uint32_t)k * ROWS;
+        if (l >= m || sub != 0) continue;
         const float4 pl = sP[l];
         sP[l] = make_float4(fmaf(beta[0], pl.x, zz[k][0]), fmaf(beta[1], pl.y, zz[k][1]), fmaf(beta[2], pl.z, zz[k][2]), 0.0f);
       }
@@ -508,8 +558,8 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
     }
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
-      const uint32_t l = (uint32_t)tid + (uint32_t)k * TEAM;
-      if (l >= m) continue;
+      const uint32_t l = (uint32_t)rt + (uint32_t)k * ROWS;
+      if (l >= m || sub != 0) continue;
       float4 xv = a.x[gid[k]];
       xv.x += dl[k][0]; xv.y += dl[k][1]; xv.z += dl[k][2];
       a.x[gid[k]] = xv;
@@ -532,13 +582,15 @@ __global__ void __launch_bounds__(TEAM == 32 ? 256 : TEAM, TEAM == 32 ? 3 : (TEA
 
 // Tier 0 without staging: one warp per island that is a single preconditioner block (every free body of a multi-body
 // scene).  The block inverse is then the exact inverse of the island's matrix (contact diagonal included: such blocks are
-// re-inverted by reblock.cu), so the solve is iterative refinement rather than CG:  r = b - A x in fp64 straight from the
-// global CSR (x gathered from L2), z = Minv r, x += z, r -= A z, until the island's residual passes the tolerance — one
-// round in practice, since a round contracts the residual by ~1e-5.  Nothing is staged in shared memory (32 bytes per warp
-// for the block-lane permutation): the vectors live one row per lane and move by shuffles, the matrix rows and the
-// inverse are read where they lie, and with ~60 registers four CTAs of eight warps fit an SM, which is what a kernel
-// bound by dependent global loads needs (r02g: the staged warp tier was long-scoreboard bound at 24 warps per SM).
+// re-inverted by reblock.cu), so the solve is iterative refinement rather than CG:  r = b - A x in fp64, z = Minv r,
+// x += z, r -= A z, until the island's residual passes the tolerance (a round contracts the residual by ~1e-5).  The
+// vectors live one row per lane and move by shuffles — every column of an island row lies in the island, so nothing is
+// gathered from global memory — the matrix rows are read where they lie, the block's packed inverse travels to shared
+// memory with cp.async while the start residual is computed, and with 64 registers four CTAs of eight warps fit an SM,
+// which is what a kernel bound by dependent global loads needs (r02g: the staged warp tier was long-scoreboard bound at
+// 24 warps per SM).
 __global__ void __launch_bounds__(256, 4) k_island_direct(IslandArgs a, int tier) {
+  __shared__ __align__(16) float sInv[8][528];   // the block's packed inverse (at most 32 * 33 / 2 floats), one per warp
   __shared__ unsigned char sLaneOf[8][32];
   const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
   const uint32_t count = a.counts[1 + tier];
@@ -568,28 +620,43 @@ __global__ void __launch_bounds__(256, 4) k_island_direct(IslandArgs a, int tier
     // the block's inverse is indexed by block lane: which island lane holds block lane j
     __syncwarp();
     if (act) sLaneOf[warp][bl] = (unsigned char)lane;
-    __syncwarp();
     const uint32_t blk = __shfl_sync(0xffffffffu, sl, 0) >> 5;
     const uint2 meta = __ldg(a.blockMeta + blk);
-    const float* inv = a.blockInv + meta.x;
     const int mB = (int)meta.y;
-    // ---- start residual, fp64 accumulation, x gathered where it lies
-    double y0 = (double)cd * (double)xi.x, y1 = (double)cd * (double)xi.y, y2 = (double)cd * (double)xi.z;
-    for (int kk = kk0; kk < kk1; kk += 4) {   // four entries per batch: their loads are in flight together
-      int cc[4]; float vv[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (kk + j < kk1) { cc[j] = __ldg(a.col + kk + j); vv[j] = __ldg(a.val + kk + j); }
-      float4 xv[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (kk + j < kk1) xv[j] = a.x[cc[j]];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (kk + j < kk1) { y0 += (double)vv[j] * (double)xv[j].x; y1 += (double)vv[j] * (double)xv[j].y; y2 += (double)vv[j] * (double)xv[j].z; }
+    {  // the inverse travels to shared memory asynchronously while the start residual is computed
+      const uint32_t n4 = ((uint32_t)(mB * (mB + 1) / 2) + 3u) >> 2;
+      const float4* src = reinterpret_cast<const float4*>(a.blockInv + meta.x);
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sInv[warp][0]);
+      for (uint32_t t = (uint32_t)lane; t < n4; t += 32u)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * t), "l"(src + t) : "memory");
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
-    for (int kk = c0; kk < c1; ++kk) {
-      const float v = a.cVal[kk];
-      const float4 xv = a.x[a.cCol[kk]];
-      y0 += (double)v * (double)xv.x; y1 += (double)v * (double)xv.y; y2 += (double)v * (double)xv.z;
+    // ---- the row's entries as (value, island lane of the column): every column of an island row lies in the island, so
+    //      vectors move by shuffles and nothing is gathered from global memory.  Entry k of the row: S entries through
+    //      the host's rank table (an explicit zero pointing outside the body is dropped), then this substep's contacts.
+    const int maxLen = __reduce_max_sync(0xffffffffu, (kk1 - kk0) + (c1 - c0));
+    auto entry = [&](int k, float& v, int& src) {
+      v = 0.0f; src = lane;
+      const int ks = kk0 + k;
+      if (ks < kk1) {
+        const uint32_t rk = __ldg(a.colRank + ks);
+        if (rk != 0xffffffffu) { v = __ldg(a.val + ks); src = (int)(bodyBase + rk); }
+      } else if (c0 + (ks - kk1) < c1) {
+        const int kc = c0 + (ks - kk1);
+        v = a.cVal[kc]; src = (int)(__ldg(a.pos + a.cCol[kc]) - s0);
+      }
+    };
+    // ---- start residual, fp64 accumulation
+    double y0 = (double)cd * (double)xi.x, y1 = (double)cd * (double)xi.y, y2 = (double)cd * (double)xi.z;
+    for (int k = 0; k < maxLen; k += 2) {   // two entries per step: their loads are in flight together
+      float v[2]; int src[2];
+      entry(k, v[0], src[0]);
+      if (k + 1 < maxLen) entry(k + 1, v[1], src[1]); else { v[1] = 0.0f; src[1] = lane; }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float q0 = __shfl_sync(0xffffffffu, xi.x, src[u]), q1 = __shfl_sync(0xffffffffu, xi.y, src[u]), q2 = __shfl_sync(0xffffffffu, xi.z, src[u]);
+        y0 += (double)v[u] * (double)q0; y1 += (double)v[u] * (double)q1; y2 += (double)v[u] * (double)q2;
+      }
     }
     float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
     if (act) { r0 = (float)((double)bi.x - y0); r1 = (float)((double)bi.y - y1); r2 = (float)((double)bi.z - y2); }
@@ -598,7 +665,9 @@ __global__ void __launch_bounds__(256, 4) k_island_direct(IslandArgs a, int tier
     uint32_t iters = 0;
     bool conv = false;
     float rr0, rr1, rr2;
-    const int maxLen = __reduce_max_sync(0xffffffffu, (kk1 - kk0) + (c1 - c0));
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncwarp();
+    const float* inv = &sInv[warp][0];
     while (true) {
       rr0 = warpSum(r0 * r0); rr1 = warpSum(r1 * r1); rr2 = warpSum(r2 * r2);
       conv = rr0 <= a.tol2 * bb0 + 1e-36f && rr1 <= a.tol2 * bb1 + 1e-36f && rr2 <= a.tol2 * bb2 + 1e-36f;
@@ -609,7 +678,7 @@ __global__ void __launch_bounds__(256, 4) k_island_direct(IslandArgs a, int tier
         int off = bl * (bl + 1) / 2;
 #pragma unroll 4
         for (int j = 0; j < mB; ++j) {
-          const float w = act ? __ldg(inv + off) : 0.0f;
+          const float w = act ? inv[off] : 0.0f;
           const int src = (int)sLaneOf[warp][j];
           const float q0 = __shfl_sync(0xffffffffu, r0, src), q1 = __shfl_sync(0xffffffffu, r1, src), q2 = __shfl_sync(0xffffffffu, r2, src);
           z0 = fmaf(w, q0, z0); z1 = fmaf(w, q1, z1); z2 = fmaf(w, q2, z2);
@@ -617,19 +686,11 @@ __global__ void __launch_bounds__(256, 4) k_island_direct(IslandArgs a, int tier
         }
       }
       d0 += z0; d1 += z1; d2 += z2;
-      // r -= A z: z moves by shuffles (column -> island lane through the host's rank table / the island permutation)
+      // r -= A z
       float w0 = cd * z0, w1 = cd * z1, w2 = cd * z2;
       for (int k = 0; k < maxLen; ++k) {
-        float v = 0.0f;
-        int src = lane;
-        const int ks = kk0 + k;
-        if (ks < kk1) {
-          const uint32_t rk = __ldg(a.colRank + ks);
-          if (rk != 0xffffffffu) { v = __ldg(a.val + ks); src = (int)(bodyBase + rk); }
-        } else if (c0 + (ks - kk1) < c1) {
-          const int kc = c0 + (ks - kk1);
-          v = a.cVal[kc]; src = (int)(__ldg(a.pos + a.cCol[kc]) - s0);
-        }
+        float v; int src;
+        entry(k, v, src);
         const float q0 = __shfl_sync(0xffffffffu, z0, src), q1 = __shfl_sync(0xffffffffu, z1, src), q2 = __shfl_sync(0xffffffffu, z2, src);
         w0 = fmaf(v, q0, w0); w1 = fmaf(v, q1, w1); w2 = fmaf(v, q2, w2);
       }
@@ -637,9 +698,8 @@ __global__ void __launch_bounds__(256, 4) k_island_direct(IslandArgs a, int tier
       ++iters;
     }
     if (act) {
-      float4 xo = a.x[g];   // re-read (L1) instead of keeping it live through the loop
-      xo.x += d0; xo.y += d1; xo.z += d2;
-      a.x[g] = xo;
+      xi.x += d0; xi.y += d1; xi.z += d2;
+      a.x[g] = xi;
     }
     if (lane == 0) {
       atomicMax(a.stats, iters);
@@ -652,7 +712,9 @@ __global__ void __launch_bounds__(256, 4) k_island_direct(IslandArgs a, int tier
         atomicAdd(a.stats + 2, 1u);
         atomicMax(a.stats + 3, __float_as_uint(sqrtf(rel)));
       }
+      if (a.trace) a.trace[(size_t)tier * a.listStride + wi] = make_uint4(m, iters, 0u, 0u);
     }
+    __syncwarp();   // sInv / sLaneOf of this warp are rewritten for its next island
   }
 }
 
@@ -662,15 +724,17 @@ __global__ void __launch_bounds__(256, 4) k_island_direct(IslandArgs a, int tier
 // terms, then lives in registers (an 8 x 8 tile per thread); every elimination step broadcasts the pivot row and column
 // through two small double-buffered shared arrays, one barrier per step.  fp32 is enough: the solves refine with the
 // residual recomputed from the true matrix.
-constexpr int kInvThreads = 256;
-constexpr int kInvLd = (int)kDenseMax + 4;   // shared-memory leading dimension (floats)
-
-__global__ void __launch_bounds__(kInvThreads, 2) k_island_invert(IslandArgs a, float* __restrict__ denseInv, int slot) {
+// N: largest island (128: 256 threads, two CTAs per SM; 192: 576 threads, one CTA per SM)
+template <int N>
+__global__ void __launch_bounds__((N / 8) * (N / 8), N <= 128 ? 2 : 1) k_island_invert(IslandArgs a, float* __restrict__ denseInv, int slot) {
+  constexpr int kInvThreads = (N / 8) * (N / 8);
+  constexpr int kInvLd = N + 4;                    // shared-memory leading dimension (floats)
+  constexpr int kDenseMax = N;                     // shadows the namespace constant inside this kernel
   extern __shared__ __align__(16) unsigned char invSmem[];
   float* sA = reinterpret_cast<float*>(invSmem);
-  float* sRow = sA + (size_t)kDenseMax * kInvLd;   // [2][kDenseMax]
-  float* sCol = sRow + 2 * kDenseMax;              // [2][kDenseMax]
-  const int tid = (int)threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  float* sRow = sA + (size_t)kDenseMax * kInvLd;   // [2][N]
+  float* sCol = sRow + 2 * kDenseMax;              // [2][N]
+  const int tid = (int)threadIdx.x, ty = tid / (N / 8), tx = tid % (N / 8);
   const uint32_t count = a.counts[1 + slot];
   const uint4* descs = a.tierDesc + (size_t)slot * a.listStride;
   for (uint32_t wi = blockIdx.x; wi < count; wi += gridDim.x) {
@@ -758,22 +822,29 @@ __global__ void __launch_bounds__(kInvThreads, 2) k_island_invert(IslandArgs a, 
 // symmetric: thread l reads column l, i.e. consecutive addresses across the warp; r broadcast from shared memory),
 // x += z, r -= A z until the island's residual passes the tolerance.  A round contracts the residual by the accuracy of
 // the fp32 inverse (1e-4 .. 1e-6), so two rounds are the rule; the round limit and the statistics are the CG tiers'.
-constexpr int kDenseThreads = 128;
-
+template <int WARPS>
 __device__ __forceinline__ void denseSum3(float (&v)[3], float* __restrict__ sRed, int& phase, int tid) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) v[k] = warpSum(v[k]);
-  float* buf = sRed + phase * 16;
+  float* buf = sRed + phase * (4 * WARPS);
   phase ^= 1;
   if ((tid & 31) == 0) { buf[(tid >> 5) * 4 + 0] = v[0]; buf[(tid >> 5) * 4 + 1] = v[1]; buf[(tid >> 5) * 4 + 2] = v[2]; }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < 3; ++k) v[k] = (buf[k] + buf[4 + k]) + (buf[8 + k] + buf[12 + k]);
+  for (int k = 0; k < 3; ++k) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) t += buf[4 * w + k];   // fixed order
+    v[k] = t;
+  }
 }
 
-__global__ void __launch_bounds__(kDenseThreads, 8) k_island_dense(IslandArgs a, const float* __restrict__ denseInv, int slot) {
-  __shared__ float4 sV[kDenseMax];
-  __shared__ float sRed[32];
+// N: largest island = threads per CTA (128 or 192)
+template <int N>
+__global__ void __launch_bounds__(N, N <= 128 ? 8 : 5) k_island_dense(IslandArgs a, const float* __restrict__ denseInv, int slot) {
+  constexpr int kDenseMax = N;   // shadows the namespace constant inside this kernel
+  __shared__ float4 sV[N];
+  __shared__ float sRed[2 * 4 * (N / 32)];
   const int tid = (int)threadIdx.x;
   const uint32_t count = a.counts[1 + slot];
   const uint4* descs = a.tierDesc + (size_t)slot * a.listStride;
@@ -795,28 +866,31 @@ __global__ void __launch_bounds__(kDenseThreads, 8) k_island_dense(IslandArgs a,
       bodyBase = (uint32_t)tid - a.rankInBody[g];
       if (a.cPtr) { c0 = a.cPtr[g]; c1 = a.cPtr[g + 1]; }
     }
-    // ---- start residual, fp64 accumulation, x gathered where it lies
+    // ---- start residual, fp64 accumulation; x of the island through shared memory (every column of an island row lies in
+    //      the island: local column = body base + rank of the column, contact columns through the island permutation)
+    sV[tid] = xi;
+    __syncthreads();
     double y0 = (double)cd * (double)xi.x, y1 = (double)cd * (double)xi.y, y2 = (double)cd * (double)xi.z;
     for (int kk = kk0; kk < kk1; kk += 4) {   // four entries per batch: their loads are in flight together
-      int cc[4]; float vv[4];
+      uint32_t rk[4]; float vv[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (kk + j < kk1) { cc[j] = __ldg(a.col + kk + j); vv[j] = __ldg(a.val + kk + j); }
-      float4 xv[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (kk + j < kk1) xv[j] = a.x[cc[j]];
+      for (int j = 0; j < 4; ++j) if (kk + j < kk1) { rk[j] = __ldg(a.colRank + kk + j); vv[j] = __ldg(a.val + kk + j); }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (kk + j < kk1) { y0 += (double)vv[j] * (double)xv[j].x; y1 += (double)vv[j] * (double)xv[j].y; y2 += (double)vv[j] * (double)xv[j].z; }
+        if (kk + j < kk1 && rk[j] != 0xffffffffu) {
+          const float4 xv = sV[bodyBase + rk[j]];
+          y0 += (double)vv[j] * (double)xv.x; y1 += (double)vv[j] * (double)xv.y; y2 += (double)vv[j] * (double)xv.z;
+        }
     }
     for (int kk = c0; kk < c1; ++kk) {
       const float v = a.cVal[kk];
-      const float4 xv = a.x[a.cCol[kk]];
+      const float4 xv = sV[__ldg(a.pos + a.cCol[kk]) - s0];
       y0 += (double)v * (double)xv.x; y1 += (double)v * (double)xv.y; y2 += (double)v * (double)xv.z;
     }
     float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
     if (act) { r0 = (float)((double)bi.x - y0); r1 = (float)((double)bi.y - y1); r2 = (float)((double)bi.z - y2); }
     float bb[3] = {bi.x * bi.x, bi.y * bi.y, bi.z * bi.z};
-    denseSum3(bb, sRed, phase, tid);
+    denseSum3<N / 32>(bb, sRed, phase, tid);
     const float* inv = denseInv + (size_t)wi * (kDenseMax * kDenseMax) + tid;
     float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
     uint32_t iters = 0;
@@ -824,7 +898,7 @@ __global__ void __launch_bounds__(kDenseThreads, 8) k_island_dense(IslandArgs a,
     float rr[3];
     while (true) {
       rr[0] = r0 * r0; rr[1] = r1 * r1; rr[2] = r2 * r2;
-      denseSum3(rr, sRed, phase, tid);
+      denseSum3<N / 32>(rr, sRed, phase, tid);
       conv = rr[0] <= a.tol2 * bb[0] + 1e-36f && rr[1] <= a.tol2 * bb[1] + 1e-36f && rr[2] <= a.tol2 * bb[2] + 1e-36f;
       if (conv || iters >= a.maxIter) break;
       sV[tid] = make_float4(r0, r1, r2, 0.0f);
@@ -1063,7 +1137,8 @@ const TierConfig kTiers[kIslandSlots] = {
     {512, 2, true, {1024u, 12288u, 17408u, 192u}, 1},
     {1024, 0, false, {7168u, 0u, 0u, 0u}, 1},  // k_island_pcg_big
     {128, 2, true, {256u, 2816u, 3456u, 32u}, 5},  // kSmallCtaSlot: 43 KB of shared memory
-    {128, 1, false, {kDenseMax, 0u, 0u, 0u}, 8},   // kDenseSlot: k_island_invert + k_island_dense
+    {128, 1, false, {kDenseMax, 0u, 0u, 0u}, 8},   // kDenseSlot: k_island_invert<128> + k_island_dense<128>
+    {192, 1, false, {kDenseMax2, 0u, 0u, 0u}, 5},  // kDenseSlot2: the same with N = 192
 };
 // Test hook: PIES_B200_ISLAND_MAXBLOCKS=k shrinks the shared-memory block tables of the CTA tiers to k entries, so islands
 // with more preconditioner blocks exercise the from-global-memory path of the block-Jacobi apply.
@@ -1079,10 +1154,11 @@ size_t tierSmem(int t) { return (size_t)tierLayout(t).total * (kTiers[t].team ==
 // t: whose team size, shared-memory layout and capacities; list: which island list (the same unless a list is handed to
 // a larger team)
 template <typename K>
-void launchTier(K kernel, int t, int grid, cudaStream_t s, const IslandArgs& a, int list = -1) {
-  const size_t smem = tierSmem(t);
+void launchTier(K kernel, int t, int grid, cudaStream_t s, const IslandArgs& a, int list = -1, int teamThreads = 0,
+                size_t smemAtLeast = 0) {
+  const size_t smem = std::max(tierSmem(t), smemAtLeast);
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int threads = kTiers[t].team == 32 ? 256 : kTiers[t].team;
+  const int threads = teamThreads ? teamThreads : (kTiers[t].team == 32 ? 256 : kTiers[t].team);
   kernel<<<grid, threads, smem, s>>>(a, tierLayout(t), tierCaps(t), list < 0 ? t : list);
 }
 }  // namespace
@@ -1104,6 +1180,11 @@ int uploadIslandStatics(IslandWork& w, cudaStream_t s, const HostSystem& y) {
   if (!w.host) { ICHECK(cudaMallocHost(&w.host, 1024 * sizeof(uint32_t))); w.hostCap = 1024; }
   if (!w.ready) ICHECK(cudaEventCreateWithFlags(&w.ready, cudaEventDisableTiming));
   if (!w.fork) ICHECK(cudaEventCreateWithFlags(&w.fork, cudaEventDisableTiming));
+  if (!w.prep) {
+    ICHECK(cudaStreamCreateWithFlags(&w.prep, cudaStreamNonBlocking));
+    ICHECK(cudaEventCreateWithFlags(&w.prepFork, cudaEventDisableTiming));
+    ICHECK(cudaEventCreateWithFlags(&w.prepDone, cudaEventDisableTiming));
+  }
   for (int k = 0; k < IslandWork::kAux; ++k) {
     if (!w.aux[k]) ICHECK(cudaStreamCreateWithFlags(&w.aux[k], cudaStreamNonBlocking));
     if (!w.join[k]) ICHECK(cudaEventCreateWithFlags(&w.join[k], cudaEventDisableTiming));
@@ -1118,6 +1199,7 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   const uint32_t nB = w.nBodies;
   for (int t = 0; t < kIslandSlots; ++t) w.tierCount[t] = 0;
   w.nLeftIslands = 0; w.nLeftNodes = 0;
+  if (w.prepPending) { ICHECK(cudaStreamWaitEvent(s, w.prepDone, 0)); w.prepPending = false; }  // an aborted substep's inversions
   if (!n || !nB) return 0;
   ICHECK(w.parent.reserve(nB + 1)); ICHECK(w.keys.reserve(nB + 1)); ICHECK(w.tmpKeys.reserve(nB + 1));
   ICHECK(w.vals.reserve(nB + 1)); ICHECK(w.tmpVals.reserve(nB + 1)); ICHECK(w.heads.reserve(nB + 2));
@@ -1151,7 +1233,9 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   static const bool noSmallCta = std::getenv("PIES_B200_NO_SMALL_CTA") != nullptr;   // A/B switch: tier 1 as one 320-thread list
   static const bool noDense = std::getenv("PIES_B200_NO_DENSE") != nullptr;            // A/B switch: no dense-inverse list
   if (noSmallCta) tt.caps[kSmallCtaSlot].maxNodes = 0;
-  if (noDense) tt.caps[kDenseSlot].maxNodes = 0;
+  static const bool noDense2 = std::getenv("PIES_B200_NO_DENSE2") != nullptr;          // A/B switch: dense list only up to 128 nodes
+  if (noDense) { tt.caps[kDenseSlot].maxNodes = 0; tt.caps[kDenseSlot2].maxNodes = 0; }
+  if (noDense2) tt.caps[kDenseSlot2].maxNodes = 0;
   tt.enabled = tiersEnabled;
   k_isl_classify<<<gridFor(nB, kThreads), kThreads, 0, s>>>(w.counts.p, tt, w.islStart.p, w.nnzOff.p, w.order.p, slotOf, blockCount,
                                                            nB, w.tierList.p, w.tierDesc.p, w.counts.p); ++L;
@@ -1186,16 +1270,29 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
     const size_t nnz = S.nnz + 6ull * c.nUnique + 16;
     ICHECK(w.matCol.reserve(nnz)); ICHECK(w.matVal.reserve(nnz));
   }
-  if (w.tierCount[kDenseSlot]) {  // the dense list: this substep's inverses
-    const uint32_t nd = w.tierCount[kDenseSlot];
-    ICHECK(w.denseInv.reserve((size_t)nd * kDenseMax * kDenseMax));
+  if (w.tierCount[kDenseSlot] || w.tierCount[kDenseSlot2]) {  // the dense lists: this substep's inverses, on the side stream
     IslandArgs a{};
     a.counts = w.counts.p; a.tierDesc = w.tierDesc.p; a.listStride = w.nBodies;
     a.order = w.order.p; a.pos = w.pos.p; a.rowPtr = S.rowPtr; a.val = S.val; a.colRank = w.colRank.p; a.rankInBody = w.rankInBody.p;
     a.cPtr = c.nUnique ? c.cPtr : nullptr; a.cCol = c.cCol; a.cVal = c.cVal; a.cDiag = (c.nTri || c.nFloor) ? c.cDiag : nullptr;
-    const size_t smem = ((size_t)kDenseMax * kInvLd + 4 * kDenseMax) * sizeof(float);
-    cudaFuncSetAttribute(k_island_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_island_invert<<<(int)std::min<uint32_t>(nd, 2 * kNumSMs), kInvThreads, smem, s>>>(a, w.denseInv.p, kDenseSlot); ++L;
+    if (w.tierCount[kDenseSlot]) ICHECK(w.denseInv.reserve((size_t)w.tierCount[kDenseSlot] * kDenseMax * kDenseMax));
+    if (w.tierCount[kDenseSlot2]) ICHECK(w.denseInv2.reserve((size_t)w.tierCount[kDenseSlot2] * kDenseMax2 * kDenseMax2));
+    ICHECK(cudaEventRecord(w.prepFork, s));
+    ICHECK(cudaStreamWaitEvent(w.prep, w.prepFork, 0));
+    if (w.tierCount[kDenseSlot2]) {   // the longer inversions first
+      const uint32_t nd = w.tierCount[kDenseSlot2];
+      const size_t smem = ((size_t)kDenseMax2 * (kDenseMax2 + 4) + 4 * kDenseMax2) * sizeof(float);
+      cudaFuncSetAttribute(k_island_invert<(int)kDenseMax2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k_island_invert<(int)kDenseMax2><<<(int)std::min<uint32_t>(nd, kNumSMs), (kDenseMax2 / 8) * (kDenseMax2 / 8), smem, w.prep>>>(a, w.denseInv2.p, kDenseSlot2); ++L;
+    }
+    if (w.tierCount[kDenseSlot]) {
+      const uint32_t nd = w.tierCount[kDenseSlot];
+      const size_t smem = ((size_t)kDenseMax * (kDenseMax + 4) + 4 * kDenseMax) * sizeof(float);
+      cudaFuncSetAttribute(k_island_invert<(int)kDenseMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k_island_invert<(int)kDenseMax><<<(int)std::min<uint32_t>(nd, 2 * kNumSMs), (kDenseMax / 8) * (kDenseMax / 8), smem, w.prep>>>(a, w.denseInv.p, kDenseSlot); ++L;
+    }
+    ICHECK(cudaEventRecord(w.prepDone, w.prep));
+    w.prepPending = true;
   }
   if (launches) *launches += L;
   return 0;
@@ -1218,6 +1315,7 @@ int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const C
   // stream of its own beside it (the handful of long-running islands of tiers 2 and 3 next to the thousands of small ones
   // that fill the other SMs; the warp tier in the SMs a CTA tier's last, partly filled wave leaves idle).  The longest
   // chains are enqueued first.
+  if (w.prepPending) { cudaStreamWaitEvent(s, w.prepDone, 0); w.prepPending = false; }   // this substep's dense inverses
   int present = 0;
   for (int t = 0; t < kIslandSlots; ++t) present += w.tierCount[t] ? 1 : 0;
   if (present > 1) cudaEventRecord(w.fork, s);   // before anything of this solve is enqueued on s
@@ -1243,12 +1341,22 @@ int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const C
     // a dependent shared-memory load behind): the 320-thread team gives every row its own thread.  A long list is
     // throughput bound: five 128-thread CTAs per SM.
     const uint32_t ns = w.tierCount[kSmallCtaSlot];
-    if (ns <= 2u * kNumSMs) launchTier(k_island_pcg<320, 2, true>, 1, (int)ns, nextStream(), a, kSmallCtaSlot);
+    // (measured, r02v/r02w: sharing a row between four lanes of a 1024-thread CTA is NOT faster — 10.8 k clocks per
+    // iteration against 8.9 k; the extra shuffles and reductions saturate the same shared-memory / shuffle pipe.  The
+    // variant stays reachable for experiments.)
+    static const bool split = std::getenv("PIES_B200_SPLIT_ROWS") != nullptr;
+    if (ns <= (uint32_t)kNumSMs && split)
+      launchTier(k_island_pcg<1024, 1, true, 4>, 1, (int)ns, nextStream(), a, kSmallCtaSlot, 1024);
+    else if (ns <= 2u * kNumSMs) launchTier(k_island_pcg<320, 2, true>, 1, (int)ns, nextStream(), a, kSmallCtaSlot);
     else launchTier(k_island_pcg<128, 2, true>, kSmallCtaSlot, (int)std::min<uint32_t>(ns, 5 * kNumSMs), nextStream(), a);
     ++L;
   }
+  if (w.tierCount[kDenseSlot2]) {
+    k_island_dense<(int)kDenseMax2><<<(int)std::min<uint32_t>(w.tierCount[kDenseSlot2], 10 * kNumSMs), (int)kDenseMax2, 0, nextStream()>>>(a, w.denseInv2.p, kDenseSlot2);
+    ++L;
+  }
   if (w.tierCount[kDenseSlot]) {
-    k_island_dense<<<(int)std::min<uint32_t>(w.tierCount[kDenseSlot], 16 * kNumSMs), kDenseThreads, 0, nextStream()>>>(a, w.denseInv.p, kDenseSlot);
+    k_island_dense<(int)kDenseMax><<<(int)std::min<uint32_t>(w.tierCount[kDenseSlot], 16 * kNumSMs), (int)kDenseMax, 0, nextStream()>>>(a, w.denseInv.p, kDenseSlot);
     ++L;
   }
   if (w.tierCount[0]) {
@@ -1281,11 +1389,14 @@ void preloadIslandKernels() {
   cudaFuncGetAttributes(&a, k_island_pcg<32, 1, true>);
   cudaFuncGetAttributes(&a, k_island_pcg<320, 2, true>);
   cudaFuncGetAttributes(&a, k_island_pcg<128, 2, true>);
+  cudaFuncGetAttributes(&a, k_island_pcg<1024, 1, true, 4>);
   cudaFuncGetAttributes(&a, k_island_pcg<512, 2, true>);
   cudaFuncGetAttributes(&a, k_island_pcg_big);
   cudaFuncGetAttributes(&a, k_island_direct);
-  cudaFuncGetAttributes(&a, k_island_invert);
-  cudaFuncGetAttributes(&a, k_island_dense);
+  cudaFuncGetAttributes(&a, k_island_invert<(int)kDenseMax>);
+  cudaFuncGetAttributes(&a, k_island_invert<(int)kDenseMax2>);
+  cudaFuncGetAttributes(&a, k_island_dense<(int)kDenseMax>);
+  cudaFuncGetAttributes(&a, k_island_dense<(int)kDenseMax2>);
 }
 
 }  // namespace pies

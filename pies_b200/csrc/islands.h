@@ -21,10 +21,14 @@ namespace pies {
 // substep is then iterative refinement with that inverse — what the warp tier does with its block inverse.  At S3 every
 // contact island of the benchmark window (3-4 bodies of a column, 81-108 nodes) is of this kind.
 constexpr int kIslandTiers = 4;
-constexpr int kIslandSlots = kIslandTiers + 2;
+// A second dense list (slot 6) does the same for islands of 129..192 nodes with a 576-thread inversion CTA (a column of
+// 5-7 bodies: S3 ticks 79..100); beyond that the m^3 of the inversion and the m^2 of every apply lose to the CG.
+constexpr int kIslandSlots = kIslandTiers + 3;
 constexpr int kSmallCtaSlot = 4;
-constexpr int kDenseSlot = 5;
+constexpr int kDenseSlot = 5;         // <= kDenseMax nodes
+constexpr int kDenseSlot2 = 6;        // <= kDenseMax2 nodes
 constexpr uint32_t kDenseMax = 128;   // nodes; the inverse is stored with this leading dimension
+constexpr uint32_t kDenseMax2 = 192;
 struct IslandCaps { uint32_t maxNodes, maxNnz, maxInv, maxBlocks; };
 
 struct IslandWork {
@@ -51,17 +55,24 @@ struct IslandWork {
   uint32_t hostCap = 0;
   cudaEvent_t ready = nullptr;
   // the lists of one solve run beside each other: the first on the solver's stream, the others on these
-  static constexpr int kAux = 5;
-  cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join[kAux] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kAux = 6;
+  cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[kAux] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // the once-per-substep inversions of the dense list run on their own stream beside the first local step
+  cudaStream_t prep = nullptr;
+  cudaEvent_t prepFork = nullptr, prepDone = nullptr;
+  bool prepPending = false;
   uint64_t scanCap = 0;
   uint32_t nLeftIslands = 0, nLeftNodes = 0;  // host copies after buildIslands
-  uint32_t tierCount[kIslandSlots] = {0, 0, 0, 0, 0, 0};
-  DevBuf<float> denseInv;         // slot 5: kDenseMax x kDenseMax floats per list entry, inverse of the island's matrix
+  uint32_t tierCount[kIslandSlots] = {0, 0, 0, 0, 0, 0, 0};
+  DevBuf<float> denseInv, denseInv2;   // slots 5 / 6: N x N floats per list entry (N = kDenseMax / kDenseMax2), inverse of the island's matrix
   cudaError_t lastError = cudaSuccess;
   ~IslandWork() {
     if (ready) cudaEventDestroy(ready);
     if (fork) cudaEventDestroy(fork);
+    if (prepFork) cudaEventDestroy(prepFork);
+    if (prepDone) cudaEventDestroy(prepDone);
+    if (prep) cudaStreamDestroy(prep);
     for (int k = 0; k < kAux; ++k) { if (join[k]) cudaEventDestroy(join[k]); if (aux[k]) cudaStreamDestroy(aux[k]); }
     if (host) cudaFreeHost(host);
   }

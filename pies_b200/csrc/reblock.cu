@@ -300,6 +300,7 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
                   const float* staticInv, uint32_t nStatic, const ContactLists& c, const float4* q, PcgWork& pw,
                   int* launches) {
   int L = 0;
+  if (w.factorPending) { RCHECK(cudaStreamWaitEvent(s, w.factorDone, 0)); w.factorPending = false; }  // an aborted substep's inversions
   RCHECK(w.nBlocksDev.reserve(4));
   RCHECK(w.flag.reserve(n + 2)); RCHECK(w.parent.reserve(n + 1)); RCHECK(w.slotOf.reserve(n + 1));
   RCHECK(w.dirty.reserve(nStatic + 1));
@@ -359,9 +360,18 @@ int rebuildBlocks(BlockWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   RCHECK(cudaEventRecord(w.countsReady, s));
   k_block_sizes<<<gridFor(bound + 1, kThreads), kThreads, 0, s>>>(bound, w.nBlocksDev.p, w.blockCount.p, w.blockOff.p); ++L;
   L += launchExclusiveScan(s, w.blockOff.p, bound + 1, w.scanScratch.p);
-  k_block_factor<<<gridFor(bound, kFactorWarps), kFactorWarps * 32, 0, s>>>(nStatic, w.nBlocksDev.p, S, c, w.blockNodes.p,
-                                                                           w.slotOf.p, w.dirty.p, w.blockOff.p, staticInv,
-                                                                           w.blockInv.p, w.blockMeta.p); ++L;
+  if (!w.side) {
+    RCHECK(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
+    RCHECK(cudaEventCreateWithFlags(&w.factorFork, cudaEventDisableTiming));
+    RCHECK(cudaEventCreateWithFlags(&w.factorDone, cudaEventDisableTiming));
+  }
+  RCHECK(cudaEventRecord(w.factorFork, s));
+  RCHECK(cudaStreamWaitEvent(w.side, w.factorFork, 0));
+  k_block_factor<<<gridFor(bound, kFactorWarps), kFactorWarps * 32, 0, w.side>>>(nStatic, w.nBlocksDev.p, S, c, w.blockNodes.p,
+                                                                                w.slotOf.p, w.dirty.p, w.blockOff.p, staticInv,
+                                                                                w.blockInv.p, w.blockMeta.p); ++L;
+  RCHECK(cudaEventRecord(w.factorDone, w.side));
+  w.factorPending = true;
   pw.blockNodes = w.blockNodes.p; pw.blockInv = w.blockInv.p; pw.blockMeta = w.blockMeta.p; pw.nBlocks = bound;
   pw.nBlocksDev = w.nBlocksDev.p;
   w.nTouched = nT;

@@ -24,7 +24,17 @@ struct BlockWork {
   // [0] = mid clusters, [1] = clusters larger than that (dataflow sweeps); host copy in host[1..2] once countsReady fired
   DevBuf<uint32_t> midList, midCount;
   cudaEvent_t countsReady = nullptr;
-  ~BlockWork() { if (countsReady) cudaEventDestroy(countsReady); }
+  // the dense inversions of the touched blocks (k_block_factor) run on a side stream beside the cluster and island
+  // bookkeeping that follows (dozens of tiny launches); whoever applies the inverses first waits for factorDone
+  cudaStream_t side = nullptr;
+  cudaEvent_t factorFork = nullptr, factorDone = nullptr;
+  bool factorPending = false;
+  ~BlockWork() {
+    if (countsReady) cudaEventDestroy(countsReady);
+    if (factorFork) cudaEventDestroy(factorFork);
+    if (factorDone) cudaEventDestroy(factorDone);
+    if (side) cudaStreamDestroy(side);
+  }
   uint32_t midClusterMax = kMidClusterMax;  // tuning: 0 sends every cluster above 32 nodes to the dataflow sweeps
   uint32_t* host = nullptr;      // pinned, 4 words
   uint32_t nBlocksBound = 0, nTouched = 0;

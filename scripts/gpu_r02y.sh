@@ -1,0 +1,11 @@
+#!/bin/bash
+OUT=gpurun_out/r02y; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_solver_gpu.py tests/test_configs_gpu.py tests/test_abi.py -m gpu -q -x > $OUT/pytest.log 2>&1; echo "pytest exit $?" | tee -a $OUT/pytest.log
+timeout 240 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
+FROM=60 TO=108 EVERY=4 timeout 300 python scripts/diag_island_lists.py > $OUT/lists.log 2>&1
+grep -v "^$" $OUT/pytest.log | tail -12; cat $OUT/lists.log | cut -c1-330; python - <<'PY'
+import json
+for f in ("bench",):
+    d=json.loads([l for l in open('gpurun_out/r02y/%s.json'%f) if l.startswith('{')][0])
+    print(f, {k:d[k] for k in ("value","ms_per_step","phase_ms_per_step","pcg_iterations_per_step")}, "e2e", d["e2e"]["ms_per_step"], "ff", d["free_fall"]["ms_per_step"], d["free_fall"]["phase_ms_per_step"], "isl", d["roofline"]["avg_launch_ms"])
+PY
