@@ -520,8 +520,9 @@ def main():
                  "gather": "k_gather_rhs (CSR gather of the contributions into the right-hand side)",
                  "spmv": "k_pcg_spmv (A z over SELL-32 windows staged by cp.async, with p / Ap recurrences)",
                  "update": "k_pcg_update (x, r update + packed block-Jacobi apply; the preconditioner stream is not in the SURVEY model)",
-                 "island": "k_island_pcg<*> (one global solve = every island's whole PCG in shared memory, all tiers; bytes = the SURVEY "
-                           "CG model x the iterations each island ran, so on-chip reuse can put this above the HBM peak)"}
+                 "island": "island solve: k_island_direct + k_island_dense<*> + k_island_pcg<*> side by side (one global solve = every "
+                           "island's refinement rounds / CG iterations; bytes = the SURVEY CG model x the rounds or iterations each "
+                           "island ran, so on-chip reuse can put this above the HBM peak and the dense applies are not in it)"}
         traffic = {}
         traffic_file = os.path.join(ROOT, "profiles", "kernel_traffic.json")
         if os.path.exists(traffic_file):
@@ -568,7 +569,7 @@ def main():
             "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
             "pcg_iterations_per_step": pcg_iters / args.steps,
             "pcg_cap_hits": int(cap_hits),
-            "islands_last_tick": {"warp": int(st.islandsTier[0]), "cta320": int(st.islandsTier[1]), "cta512": int(st.islandsTier[2]),
+            "islands_last_tick": {"warp": int(st.islandsTier[0]), "dense_cta128_cta320": int(st.islandsTier[1]), "cta512": int(st.islandsTier[2]),
                                   "cta1024": int(st.islandsTier[3]), "grid_wide": int(st.islandsGlobal),
                                   "grid_wide_nodes": int(st.islandNodesGlobal)},
             "tick_window": [args.preroll + warmup, args.preroll + warmup + args.steps],

@@ -621,7 +621,6 @@ int pdSubstepEnd(PiesB200Solver* s) {
   const ContactLists& lists = c->lists;
   // nothing of this substep's side-stream preparation may outlive it (a substep without PD iterations never waited)
   if (s->blocks && s->blocks->factorPending) { PD_CHECK(s, cudaStreamWaitEvent(st, s->blocks->factorDone, 0)); s->blocks->factorPending = false; }
-  if (s->islands && s->islands->prepPending) { PD_CHECK(s, cudaStreamWaitEvent(st, s->islands->prepDone, 0)); s->islands->prepPending = false; }
   timer.begin(kPhContact);
   if (s->contact)
     s->launches += launchStabilize(st, *s->contact, lists, n, s->q.p, s->prev.p, s->snap.p, o.collisionThickness,

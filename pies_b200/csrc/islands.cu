@@ -1180,11 +1180,6 @@ int uploadIslandStatics(IslandWork& w, cudaStream_t s, const HostSystem& y) {
   if (!w.host) { ICHECK(cudaMallocHost(&w.host, 1024 * sizeof(uint32_t))); w.hostCap = 1024; }
   if (!w.ready) ICHECK(cudaEventCreateWithFlags(&w.ready, cudaEventDisableTiming));
   if (!w.fork) ICHECK(cudaEventCreateWithFlags(&w.fork, cudaEventDisableTiming));
-  if (!w.prep) {
-    ICHECK(cudaStreamCreateWithFlags(&w.prep, cudaStreamNonBlocking));
-    ICHECK(cudaEventCreateWithFlags(&w.prepFork, cudaEventDisableTiming));
-    ICHECK(cudaEventCreateWithFlags(&w.prepDone, cudaEventDisableTiming));
-  }
   for (int k = 0; k < IslandWork::kAux; ++k) {
     if (!w.aux[k]) ICHECK(cudaStreamCreateWithFlags(&w.aux[k], cudaStreamNonBlocking));
     if (!w.join[k]) ICHECK(cudaEventCreateWithFlags(&w.join[k], cudaEventDisableTiming));
@@ -1199,7 +1194,6 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   const uint32_t nB = w.nBodies;
   for (int t = 0; t < kIslandSlots; ++t) w.tierCount[t] = 0;
   w.nLeftIslands = 0; w.nLeftNodes = 0;
-  if (w.prepPending) { ICHECK(cudaStreamWaitEvent(s, w.prepDone, 0)); w.prepPending = false; }  // an aborted substep's inversions
   if (!n || !nB) return 0;
   ICHECK(w.parent.reserve(nB + 1)); ICHECK(w.keys.reserve(nB + 1)); ICHECK(w.tmpKeys.reserve(nB + 1));
   ICHECK(w.vals.reserve(nB + 1)); ICHECK(w.tmpVals.reserve(nB + 1)); ICHECK(w.heads.reserve(nB + 2));
@@ -1270,29 +1264,27 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
     const size_t nnz = S.nnz + 6ull * c.nUnique + 16;
     ICHECK(w.matCol.reserve(nnz)); ICHECK(w.matVal.reserve(nnz));
   }
-  if (w.tierCount[kDenseSlot] || w.tierCount[kDenseSlot2]) {  // the dense lists: this substep's inverses, on the side stream
+  if (w.tierCount[kDenseSlot] || w.tierCount[kDenseSlot2]) {  // the dense lists: this substep's inverses
     IslandArgs a{};
     a.counts = w.counts.p; a.tierDesc = w.tierDesc.p; a.listStride = w.nBodies;
     a.order = w.order.p; a.pos = w.pos.p; a.rowPtr = S.rowPtr; a.val = S.val; a.colRank = w.colRank.p; a.rankInBody = w.rankInBody.p;
     a.cPtr = c.nUnique ? c.cPtr : nullptr; a.cCol = c.cCol; a.cVal = c.cVal; a.cDiag = (c.nTri || c.nFloor) ? c.cDiag : nullptr;
     if (w.tierCount[kDenseSlot]) ICHECK(w.denseInv.reserve((size_t)w.tierCount[kDenseSlot] * kDenseMax * kDenseMax));
     if (w.tierCount[kDenseSlot2]) ICHECK(w.denseInv2.reserve((size_t)w.tierCount[kDenseSlot2] * kDenseMax2 * kDenseMax2));
-    ICHECK(cudaEventRecord(w.prepFork, s));
-    ICHECK(cudaStreamWaitEvent(w.prep, w.prepFork, 0));
+    // On the solver's stream: run beside the first local step on a side stream (r02x) they only moved their time from one
+    // phase to the other — both want every SM — and blurred the per-kernel timings of that step.
     if (w.tierCount[kDenseSlot2]) {   // the longer inversions first
       const uint32_t nd = w.tierCount[kDenseSlot2];
       const size_t smem = ((size_t)kDenseMax2 * (kDenseMax2 + 4) + 4 * kDenseMax2) * sizeof(float);
       cudaFuncSetAttribute(k_island_invert<(int)kDenseMax2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k_island_invert<(int)kDenseMax2><<<(int)std::min<uint32_t>(nd, kNumSMs), (kDenseMax2 / 8) * (kDenseMax2 / 8), smem, w.prep>>>(a, w.denseInv2.p, kDenseSlot2); ++L;
+      k_island_invert<(int)kDenseMax2><<<(int)std::min<uint32_t>(nd, kNumSMs), (kDenseMax2 / 8) * (kDenseMax2 / 8), smem, s>>>(a, w.denseInv2.p, kDenseSlot2); ++L;
     }
     if (w.tierCount[kDenseSlot]) {
       const uint32_t nd = w.tierCount[kDenseSlot];
       const size_t smem = ((size_t)kDenseMax * (kDenseMax + 4) + 4 * kDenseMax) * sizeof(float);
       cudaFuncSetAttribute(k_island_invert<(int)kDenseMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k_island_invert<(int)kDenseMax><<<(int)std::min<uint32_t>(nd, 2 * kNumSMs), (kDenseMax / 8) * (kDenseMax / 8), smem, w.prep>>>(a, w.denseInv.p, kDenseSlot); ++L;
+      k_island_invert<(int)kDenseMax><<<(int)std::min<uint32_t>(nd, 2 * kNumSMs), (kDenseMax / 8) * (kDenseMax / 8), smem, s>>>(a, w.denseInv.p, kDenseSlot); ++L;
     }
-    ICHECK(cudaEventRecord(w.prepDone, w.prep));
-    w.prepPending = true;
   }
   if (launches) *launches += L;
   return 0;
@@ -1315,7 +1307,6 @@ int launchIslandSolve(IslandWork& w, cudaStream_t s, const CsrMatrix& S, const C
   // stream of its own beside it (the handful of long-running islands of tiers 2 and 3 next to the thousands of small ones
   // that fill the other SMs; the warp tier in the SMs a CTA tier's last, partly filled wave leaves idle).  The longest
   // chains are enqueued first.
-  if (w.prepPending) { cudaStreamWaitEvent(s, w.prepDone, 0); w.prepPending = false; }   // this substep's dense inverses
   int present = 0;
   for (int t = 0; t < kIslandSlots; ++t) present += w.tierCount[t] ? 1 : 0;
   if (present > 1) cudaEventRecord(w.fork, s);   // before anything of this solve is enqueued on s

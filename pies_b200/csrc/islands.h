@@ -58,10 +58,6 @@ struct IslandWork {
   static constexpr int kAux = 6;
   cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[kAux] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  // the once-per-substep inversions of the dense list run on their own stream beside the first local step
-  cudaStream_t prep = nullptr;
-  cudaEvent_t prepFork = nullptr, prepDone = nullptr;
-  bool prepPending = false;
   uint64_t scanCap = 0;
   uint32_t nLeftIslands = 0, nLeftNodes = 0;  // host copies after buildIslands
   uint32_t tierCount[kIslandSlots] = {0, 0, 0, 0, 0, 0, 0};
@@ -70,9 +66,6 @@ struct IslandWork {
   ~IslandWork() {
     if (ready) cudaEventDestroy(ready);
     if (fork) cudaEventDestroy(fork);
-    if (prepFork) cudaEventDestroy(prepFork);
-    if (prepDone) cudaEventDestroy(prepDone);
-    if (prep) cudaStreamDestroy(prep);
     for (int k = 0; k < kAux; ++k) { if (join[k]) cudaEventDestroy(join[k]); if (aux[k]) cudaStreamDestroy(aux[k]); }
     if (host) cudaFreeHost(host);
   }
