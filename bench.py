@@ -434,6 +434,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern = {k: [0.0, 0] for k in ("tet", "gather", "spmv", "update", "island")}
     island_row_iters = 0
+    island_inv_floats = 0
     cap_hits = 0
     phases = {"local": 0.0, "global": 0.0, "detect": 0.0, "contact": 0.0, "other": 0.0, "halo": 0.0}
     proj = launches = pcg_iters = 0
@@ -455,6 +456,7 @@ def main():
         kern["update"][0] += st.msUpdateKernel; kern["update"][1] += st.updateKernelLaunches
         kern["island"][0] += st.msIslandKernels; kern["island"][1] += st.islandKernelLaunches
         island_row_iters += st.pcgIslandRowIterations
+        island_inv_floats += int(st.islandInverseFloats)
         cap_hits += st.pcgCapHits
         phases["local"] += st.msLocal; phases["global"] += st.msGlobal; phases["detect"] += st.msDetect
         phases["contact"] += st.msContact; phases["other"] += st.msOther; phases["halo"] += st.msHalo
@@ -511,18 +513,19 @@ def main():
         # Algorithmic bytes per launch (the split of the 176 B per tet-type projection between the
         # kernel that writes the contributions and the gather that re-reads them is stated in DESIGN.md section 4).
         local_proj = int(st.staticProjections)
-        # island solves: a CG iteration of the SURVEY model costs 8 B per non-zero + 136 B per node; the island kernels ran
-        # island_row_iters x 32 row-iterations in kern["island"][1] solves (iterations differ per island)
-        isl_solves = max(1, kern["island"][1])
+        # One island solve has to move, once: the rows of S + C_t (8 B per non-zero), x in and out, b and the per-row
+        # tables (76 B per node), and the inverses its lists apply (packed block inverse of every single-block island,
+        # dense inverse of every island of the dense lists, packed block inverses of the CG lists) — everything else
+        # (refinement rounds, CG iterations) runs out of registers / shared memory.  Average over the timed ticks.
         alg = {"tet": 112 * local_proj, "gather": 64 * local_proj + 40 * n, "spmv": 8 * nnz + 64 * n, "update": 72 * n,
-               "island": int(32 * island_row_iters * (8.0 * nnz / n + 136.0) / isl_solves)}
+               "island": int(8 * nnz + 76 * n + 4.0 * island_inv_floats / max(1, args.steps))}
         names = {"tet": "k_tet_elems (fused tet strain+volume projection: ids, Qinv, parameters in; 4 contributions out)",
-                 "gather": "k_gather_rhs (CSR gather of the contributions into the right-hand side)",
+                 "gather": "k_gather_rhs / k_gather_rhs_contacts (CSR gather of the contributions, with contacts also the collision and floor terms, into the right-hand side)",
                  "spmv": "k_pcg_spmv (A z over SELL-32 windows staged by cp.async, with p / Ap recurrences)",
                  "update": "k_pcg_update (x, r update + packed block-Jacobi apply; the preconditioner stream is not in the SURVEY model)",
-                 "island": "island solve: k_island_direct + k_island_dense<*> + k_island_pcg<*> side by side (one global solve = every "
-                           "island's refinement rounds / CG iterations; bytes = the SURVEY CG model x the rounds or iterations each "
-                           "island ran, so on-chip reuse can put this above the HBM peak and the dense applies are not in it)"}
+                 "island": "island solve: k_island_direct + k_island_dense<*> + k_island_pcg<*> side by side (one global solve; bytes "
+                           "= what a solve has to read once: 8 B per non-zero of S, 76 B per node of vectors and row tables, and "
+                           "the block / dense inverses its lists apply; rounds and iterations run on chip)"}
         traffic = {}
         traffic_file = os.path.join(ROOT, "profiles", "kernel_traffic.json")
         if os.path.exists(traffic_file):

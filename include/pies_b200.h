@@ -127,7 +127,7 @@ typedef struct PiesB200Stats {
   float msHalo;
   uint64_t systemNonZeros;     /* non-zeros of S = M/h^2 + sum w A^T A (both triangles), for the CG byte model */
   uint32_t staticBodies;       /* connected components of S */
-  uint32_t reserved2;
+  uint32_t islandInverseFloats; /* floats of block / dense inverse one global solve of the island lists reads (last substep) */
 } PiesB200Stats;
 
 typedef struct PiesB200Solver PiesB200Solver;

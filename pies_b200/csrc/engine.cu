@@ -493,6 +493,7 @@ int pdSubstepBegin(PiesB200Solver* s) {
       for (int t = 0; t < kIslandTiers; ++t) s->stats.islandsTier[t] = s->islands->tierCount[t];
       s->stats.islandsTier[1] += s->islands->tierCount[kSmallCtaSlot] + s->islands->tierCount[kDenseSlot] + s->islands->tierCount[kDenseSlot2];
       s->stats.islandsGlobal = s->islands->nLeftIslands;
+      s->stats.islandInverseFloats = s->islands->inverseFloats;
       s->stats.islandNodesGlobal = s->islands->nLeftNodes;
     }
   }

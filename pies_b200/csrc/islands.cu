@@ -143,6 +143,9 @@ __global__ void __launch_bounds__(kThreads) k_isl_classify(const uint32_t* count
   // everything a team needs to start on the island in one 16 B record (it prefetches the next one while it solves)
   tierDesc[(size_t)tier * listStride + at] = make_uint4(isl, s0, m, nnzOff[s0]);
   if (tier == kIslandSlots) atomicAdd(counts + 2 + kIslandSlots, m);
+  // floats of inverse the island's solve has to read: the packed block inverse (warp list), the dense inverse (dense
+  // lists), the packed inverses of its blocks (CG lists: at most 16.5 per node, taken as 14 = a 27-node block)
+  else atomicAdd(counts + 3 + kIslandSlots, tier == 0 ? m * (m + 1u) / 2u : ((tier == kDenseSlot || tier == kDenseSlot2) ? m * m : 14u * m));
 }
 
 // Marks the nodes of the islands left to the grid-wide CG, the 256-row windows that hold one and their preconditioner
@@ -1239,6 +1242,7 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   for (int t = 0; t < kIslandSlots; ++t) w.tierCount[t] = w.host[1 + t];
   w.nLeftIslands = w.host[1 + kIslandSlots];
   w.nLeftNodes = w.host[2 + kIslandSlots];
+  w.inverseFloats = w.host[3 + kIslandSlots];
   // Both kinds present: the grid-wide CG only has to run over the rows of the left-over islands.
   w.restricted = false;
   bool anyLocal = false;

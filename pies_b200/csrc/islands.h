@@ -60,6 +60,7 @@ struct IslandWork {
   cudaEvent_t fork = nullptr, join[kAux] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t scanCap = 0;
   uint32_t nLeftIslands = 0, nLeftNodes = 0;  // host copies after buildIslands
+  uint32_t inverseFloats = 0;                 // floats of inverse (block, dense) one global solve of the island lists reads
   uint32_t tierCount[kIslandSlots] = {0, 0, 0, 0, 0, 0, 0};
   DevBuf<float> denseInv, denseInv2;   // slots 5 / 6: N x N floats per list entry (N = kDenseMax / kDenseMax2), inverse of the island's matrix
   cudaError_t lastError = cudaSuccess;

@@ -55,7 +55,7 @@ class Stats(C.Structure):
         ("msIslandKernels", C.c_float), ("islandKernelLaunches", C.c_uint32),
         ("pcgIslandRowIterations", C.c_uint64),
         ("haloBytesLastTick", C.c_uint64), ("haloExchangesLastTick", C.c_uint32), ("msHalo", C.c_float),
-        ("systemNonZeros", C.c_uint64), ("staticBodies", C.c_uint32), ("reserved2", C.c_uint32),
+        ("systemNonZeros", C.c_uint64), ("staticBodies", C.c_uint32), ("islandInverseFloats", C.c_uint32),
     ]
 
 
