@@ -452,6 +452,38 @@ def test_island_list_switches_agree(pb, switch):
         assert first >= 30, (switch, first)
 
 
+def test_island_trace_and_lists(pb):
+    """Diagnostics entry point: the per-island record of the last global solve (rows, rounds / iterations, SM clocks,
+    matrix entries) for every list, read in a process that has PIES_B200_ISLAND_TRACE set.  On the 4 x 12 stack at tick 46
+    the dense-inverse lists hold the stacked columns (refinement: a handful of rounds), the warp list the free bodies."""
+    import subprocess, sys, os, json
+    code = ("import sys, json; sys.path.insert(0, %r); import numpy as np; import pies_b200 as pb; from pies_b200 import scenes\n"
+            "s = pb.Solver(**scenes.S3_OPTIONS); scenes.build_s3(s, bodies=48, nx=2, nz=2)\n"
+            "[s.tick() for _ in range(46)]\n"
+            "st = s.stats()\n"
+            "out = {'tiers': list(st.islandsTier), 'inv': int(st.islandInverseFloats), 'lists': {}}\n"
+            "for slot in range(7):\n"
+            "    tr = s.debugIslandTrace(slot)\n"
+            "    out['lists'][str(slot)] = tr.tolist()\n"
+            "print(json.dumps(out))" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, PIES_B200_ISLAND_TRACE="1")
+    res = subprocess.run([sys.executable, "-c", code], check=True, env=env, capture_output=True, text=True)
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    lists = {int(k): np.array(v, dtype=np.int64).reshape(-1, 4) for k, v in out["lists"].items()}
+    n_islands = sum(len(v) for v in lists.values())
+    assert n_islands == sum(out["tiers"]) and n_islands > 0
+    assert len(lists[1]) + len(lists[4]) + len(lists[5]) + len(lists[6]) == out["tiers"][1]
+    rows = sum(int(v[:, 0].sum()) for v in lists.values())
+    assert rows == 48 * 27                                       # every node is in exactly one island
+    dense = np.concatenate([lists[5], lists[6]])
+    assert len(dense) > 0 and dense[:, 0].max() <= 192 and (lists[5][:, 0] <= 128).all()
+    assert (dense[:, 1] >= 1).all() and (dense[:, 1] <= 8).all()   # refinement rounds, not CG iterations
+    assert (lists[0][:, 0] <= 32).all()
+    expected_inv = sum(int(m) * (int(m) + 1) // 2 for m in lists[0][:, 0]) + sum(int(m) ** 2 for m in dense[:, 0]) \
+        + sum(14 * int(m) for k in (1, 2, 3, 4) for m in lists[k][:, 0])
+    assert out["inv"] == expected_inv
+
+
 def test_pcg_cap_is_loud(pb):
     """A solve that stops at pcgMaxIterations far from its tolerance is reported: counter, residual and an error code
     (the reference's Cholesky cannot fail this way, so silence would hide a wrong trajectory)."""
