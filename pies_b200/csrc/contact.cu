@@ -42,52 +42,18 @@ __global__ void __launch_bounds__(kThreads) k_pt_project(uint32_t nTri, const ui
   contribC[4ull * e + 3] = f4(kPtW * ((-1.0f) * pA + D), 0.0f);
 }
 
-// projectedPosition of every floor contact (CollisionConstraint.cpp:447-455): position with y<0 -> 0.
-// Duplicates of a node all carry the same value, so it is stored per node.
-__global__ void __launch_bounds__(kThreads) k_floor_project(uint32_t nFloor, const uint32_t* __restrict__ nodes,
-                                                            const float4* __restrict__ q, float4* __restrict__ snap) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nFloor) return;
-  uint32_t node = nodes[i];
-  float4 p = q[node];
-  if (p.y < 0.0f) p.y = 0.0f;
-  snap[node] = p;
-}
-
-int launchContactProject(cudaStream_t s, const ContactLists& c, const float4* q, float thickness, float4* contribC,
-                         float4* snap, bool floorToo) {
+// (the floor contacts' projectedPosition — CollisionConstraint.cpp:447-455: the position with y < 0 -> 0, the same for
+// every duplicate of a node — is computed and stored per node by k_gather_rhs_contacts)
+int launchContactProject(cudaStream_t s, const ContactLists& c, const float4* q, float thickness, float4* contribC) {
   int L = 0;
   if (c.nUnique) { k_pt_project<<<gridFor(c.nUnique, kThreads), kThreads, 0, s>>>(c.nUnique, c.uTri, c.uW, q, thickness, contribC); ++L; }
-  if (c.nFloor && floorToo) { k_floor_project<<<gridFor(c.nFloor, kThreads), kThreads, 0, s>>>(c.nFloor, c.floorNode, q, snap); ++L; }
   return L;
 }
 
-// rhs_i += sum of collision contributions (list order) + per floor duplicate w * projectedPosition
-// (Solver.cpp:337-349).
-__global__ void __launch_bounds__(kThreads) k_gather_contacts(uint32_t n, ContactLists c,
-                                                              const float4* __restrict__ contribC,
-                                                              const float4* __restrict__ snap, float4* __restrict__ rhs) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int beg = 0, end = 0;
-  if (c.nTri) { beg = c.incPtr[i]; end = c.incPtr[i + 1]; }
-  uint32_t mult = c.nFloor ? c.floorMult[i] : 0u;
-  if (beg == end && !mult) return;
-  float4 acc = rhs[i];
-  for (int k = beg; k < end; ++k) {
-    float4 v = contribC[c.inc[k]];
-    acc.x += v.x; acc.y += v.y; acc.z += v.z;
-  }
-  if (mult) {
-    float4 p = snap[i];
-    for (uint32_t k = 0; k < mult; ++k) { acc.x += kFloorW * p.x; acc.y += kFloorW * p.y; acc.z += kFloorW * p.z; }
-  }
-  rhs[i] = acc;
-}
-
-// The whole right-hand side in one pass when there are contacts: k_gather_rhs (pd_kernels.cu), then the collision
-// contributions and the floor terms exactly as k_floor_project + k_gather_contacts add them (same values, same order, so
-// the result is bit-identical) — one launch and one read-modify-write of rhs less per PD iteration.
+// The whole right-hand side in one pass when there are contacts: the constraint gather of k_gather_rhs (pd_kernels.cu),
+// then rhs_i += sum of the collision contributions (list order) + per floor duplicate w * projectedPosition
+// (Solver.cpp:337-349), in that order; the floor contacts' projectedPosition (the position with y < 0 -> 0) is written to
+// `snap` for the stabilisation sweeps.
 __global__ void __launch_bounds__(kThreads) k_gather_rhs_contacts(uint32_t n, const float4* __restrict__ msn,
                                                                   const int* __restrict__ incPtr,
                                                                   const uint32_t* __restrict__ inc,
@@ -136,13 +102,6 @@ int launchGatherRhsContacts(cudaStream_t s, uint32_t n, const float4* msn, const
                             float4* snap, float4* rhs) {
   if (!n) return 0;
   k_gather_rhs_contacts<<<gridFor(n, kThreads), kThreads, 0, s>>>(n, msn, incPtr, inc, contrib, c, contribC, q, snap, rhs);
-  return 1;
-}
-
-int launchGatherContacts(cudaStream_t s, uint32_t n, const ContactLists& c, const float4* contribC, const float4* snap,
-                         float4* rhs) {
-  if (!c.nTri && !c.nFloor) return 0;
-  k_gather_contacts<<<gridFor(n, kThreads), kThreads, 0, s>>>(n, c, contribC, snap, rhs);
   return 1;
 }
 
@@ -665,8 +624,6 @@ int launchFriction(cudaStream_t s, ContactWork& w, const ContactLists& c, uint32
 void preloadContactKernels() {
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, k_pt_project);
-  cudaFuncGetAttributes(&a, k_floor_project);
-  cudaFuncGetAttributes(&a, k_gather_contacts);
   cudaFuncGetAttributes(&a, k_gs_dataflow<StabilizeOp>);
   cudaFuncGetAttributes(&a, k_gs_dataflow<FrictionOp>);
   cudaFuncGetAttributes(&a, k_entry_keys);

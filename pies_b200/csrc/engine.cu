@@ -523,7 +523,7 @@ int pdIteration(PiesB200Solver* s) {
   s->launches += launchShape(st, v.sh, s->shapeMat.p, s->shapeQinv.p, s->shapeQuat.p, s->shapeW.p, s->q.p, s->contrib.p + y.baseShape);
   s->launches += launchGoal(st, v.go, s->goalMat.p, s->goalXform.p, s->goalW.p, s->contrib.p + y.baseGoal);
   const bool anyContact = lists.nTri || lists.nFloor;
-  s->launches += launchContactProject(st, lists, s->q.p, s->opt.collisionThickness, contribC, s->snap.p, /*floorToo=*/false);
+  s->launches += launchContactProject(st, lists, s->q.p, s->opt.collisionThickness, contribC);
   const int spGather = timer.begin(kPhGatherKernel);
   if (anyContact)   // constraints + collision + floor terms in one pass over the nodes (it also writes the floor snap)
     s->launches += launchGatherRhsContacts(st, n, s->msn.p, s->incPtr.p, s->inc.p, s->contrib.p, lists, contribC, s->q.p,
