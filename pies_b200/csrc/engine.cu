@@ -764,9 +764,13 @@ int tickPD(PiesB200Solver* s, bool refreshMirror) {
   for (uint32_t sub = 0; sub < s->opt.timeSubsteps; ++sub) {
     if (multi && (rc = tickHalo(s, 3))) return rc;
     if (!failed && (rc = pdSubstepBegin(s))) { pdAbort(s); failed = rc; if (!multi) return rc; }
+    // No island mixes owned and ghost rows on any rank (agreed collectively): the owned rows do not see the ghost rows
+    // for the rest of the substep, so the exchange after every PD iteration is skipped.
+    bool mixed = true;
+    if (multi && (rc = haloMixedIslands(s, !failed, &mixed))) return rc;
     for (uint32_t it = 0; it < s->opt.iterations; ++it) {
       if (!failed && (rc = pdIteration(s))) { pdAbort(s); failed = rc; if (!multi) return rc; }
-      if (multi && (rc = tickHalo(s, 1))) return rc;
+      if (multi && mixed && (rc = tickHalo(s, 1))) return rc;
     }
     if (!failed && (rc = pdSubstepEnd(s))) { pdAbort(s); failed = rc; if (!multi) return rc; }
   }

@@ -15,6 +15,10 @@
 // haloInit fails loudly; nothing falls back to host staging.
 #include "halo.h"
 
+#include <cstdlib>
+
+#include "islands.h"
+
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -112,6 +116,20 @@ __global__ void __launch_bounds__(kThreads) k_halo_unpack(uint32_t n, const uint
     vel[row] = make_float4(a.x, a.y, a.z, 0.0f);
   }
 }
+// island root of every row's body: which kinds of rows (owned / ghost) its island holds
+__global__ void __launch_bounds__(kThreads) k_halo_mix_mark(uint32_t n, const uint32_t* __restrict__ bodyOf,
+                                                            const uint32_t* __restrict__ parent, const uint8_t* __restrict__ ghost,
+                                                            uint32_t* __restrict__ bodyMix) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x = bodyOf[i], p = parent[x];
+  while (p != x) { x = p; p = parent[x]; }
+  atomicOr(bodyMix + x, ghost[i] ? 2u : 1u);
+}
+__global__ void __launch_bounds__(kThreads) k_halo_mix_any(uint32_t nB, const uint32_t* __restrict__ bodyMix, int* __restrict__ flag) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nB && bodyMix[b] == 3u) *flag = 1;
+}
 }  // namespace
 
 HaloWork::~HaloWork() {
@@ -184,6 +202,11 @@ int haloSetLists(PiesB200Solver* s, int nPeers, const int* peers, const uint32_t
   };
   PIES_CHECK(s, upload(h->sendIdx, sendIdx, h->sendOff));
   PIES_CHECK(s, upload(h->recvIdx, recvIdx, h->recvOff));
+  {
+    std::vector<uint8_t> g(s->n, 0);
+    for (uint32_t i = 0; i < nR; ++i) g[recvIdx[i]] = 1;
+    PIES_CHECK(s, h->ghost.upload(g.data(), g.size(), s->stream));
+  }
   PIES_CHECK(s, h->sendBuf.reserve(3ull * nS + 1));
   PIES_CHECK(s, h->recvBuf.reserve(3ull * nR + 1));
   PIES_CHECK(s, cudaStreamSynchronize(s->stream));
@@ -221,6 +244,31 @@ int haloExchange(PiesB200Solver* s, int planes) {
   }
   h->bytesLastTick += 16ull * planes * ((uint64_t)nS + nR);
   ++h->exchangesLastTick;
+  return PIES_B200_OK;
+}
+
+int haloMixedIslands(PiesB200Solver* s, bool localOk, bool* anyMixed) {
+  HaloWork* h = s->halo;
+  *anyMixed = true;
+  if (!h || h->world == 1) { *anyMixed = false; return PIES_B200_OK; }
+  static const bool always = std::getenv("PIES_B200_HALO_EVERY_ITERATION") != nullptr;   // A/B switch: never skip
+  NcclApi& a = nccl();
+  cudaStream_t st = s->stream;
+  IslandWork* w = s->islands;
+  const bool canTell = localOk && !always && h->listsSet && w && w->nBodies && h->ghost.cap >= s->n;
+  h->hostStatus[2] = canTell ? 0 : 1;
+  PIES_CHECK(s, cudaMemcpyAsync(h->status.p + 2, h->hostStatus + 2, sizeof(int), cudaMemcpyHostToDevice, st));
+  if (canTell && w->united) {   // without contacts every body is its own island, and a body is owned or ghost as a whole
+    PIES_CHECK(s, h->bodyMix.reserve(w->nBodies));
+    PIES_CHECK(s, cudaMemsetAsync(h->bodyMix.p, 0, (size_t)w->nBodies * sizeof(uint32_t), st));
+    k_halo_mix_mark<<<(s->n + kThreads - 1) / kThreads, kThreads, 0, st>>>(s->n, w->bodyOf.p, w->parent.p, h->ghost.p, h->bodyMix.p);
+    k_halo_mix_any<<<(w->nBodies + kThreads - 1) / kThreads, kThreads, 0, st>>>(w->nBodies, h->bodyMix.p, h->status.p + 2);
+    s->launches += 2;
+  }
+  NCHECK(s, a.AllReduce(h->status.p + 2, h->status.p + 3, 1, ncclInt, ncclMax, static_cast<ncclComm_t>(h->comm), st));
+  PIES_CHECK(s, cudaMemcpyAsync(h->hostStatus + 3, h->status.p + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PIES_CHECK(s, cudaStreamSynchronize(st));
+  *anyMixed = h->hostStatus[3] != 0;
   return PIES_B200_OK;
 }
 

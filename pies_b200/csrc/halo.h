@@ -16,7 +16,10 @@ struct HaloWork {
   std::vector<uint32_t> sendOff, recvOff;
   DevBuf<uint32_t> sendIdx, recvIdx;
   DevBuf<float4> sendBuf, recvBuf;   // three planes per row, peer segments back to back
-  DevBuf<int> status;                // [0] this rank's failure flag for the all-reduce, [1] the reduced flag
+  DevBuf<int> status;                // [0] this rank's failure flag for the all-reduce, [1] the reduced flag,
+                                     // [2] / [3] the same for "an island mixes owned and ghost rows"
+  DevBuf<uint8_t> ghost;             // per local row: 1 = ghost (owned by a neighbour)
+  DevBuf<uint32_t> bodyMix;          // per body (island root): bit 0 an owned row, bit 1 a ghost row in its island
   int* hostStatus = nullptr;         // pinned
   uint64_t bytesLastTick = 0, exchangesLastTick = 0;
   bool listsSet = false;
@@ -32,6 +35,12 @@ int haloSetLists(PiesB200Solver* s, int nPeers, const int* peers, const uint32_t
 int haloExchange(PiesB200Solver* s, int planes);
 // Collective over all ranks: true if any rank's simulation has failed (so they all stop together instead of hanging).
 int haloAnyFailed(PiesB200Solver* s, bool mine, bool* any);
+// Collective, once per substep after the islands are built: true if on any rank an island (a connected component of
+// S + C_t) contains both owned and ghost rows.  If none does, the owned rows of every rank are independent of the ghost
+// rows for the rest of the substep (ghost bodies are complete islands of their own, simulated redundantly) and the
+// per-iteration exchanges can be skipped: the next substep's three-plane exchange refreshes the ghosts.  localOk = false
+// (this rank's substep failed) counts as mixed.
+int haloMixedIslands(PiesB200Solver* s, bool localOk, bool* anyMixed);
 void haloDestroy(PiesB200Solver* s);
 
 }  // namespace pies

@@ -1196,7 +1196,7 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   int L = 0;
   const uint32_t nB = w.nBodies;
   for (int t = 0; t < kIslandSlots; ++t) w.tierCount[t] = 0;
-  w.nLeftIslands = 0; w.nLeftNodes = 0;
+  w.nLeftIslands = 0; w.nLeftNodes = 0; w.united = false;
   if (!n || !nB) return 0;
   ICHECK(w.parent.reserve(nB + 1)); ICHECK(w.keys.reserve(nB + 1)); ICHECK(w.tmpKeys.reserve(nB + 1));
   ICHECK(w.vals.reserve(nB + 1)); ICHECK(w.tmpVals.reserve(nB + 1)); ICHECK(w.heads.reserve(nB + 2));
@@ -1211,6 +1211,7 @@ int buildIslands(IslandWork& w, cudaStream_t s, uint32_t n, const CsrMatrix& S, 
   ICHECK(w.scanScratch.reserve(scanScratchElems(w.scanCap)));
   ICHECK(cudaMemsetAsync(w.counts.p, 0, 16 * sizeof(uint32_t), s));
   const int united = c.nUnique ? 1 : 0;
+  w.united = united != 0;
   if (united) {
     k_isl_init<<<gridFor(nB, kThreads), kThreads, 0, s>>>(nB, w.parent.p); ++L;
     k_isl_unite<<<gridFor(c.nUnique, kThreads), kThreads, 0, s>>>(c.nUnique, c.uTri, w.bodyOf.p, w.parent.p); ++L;

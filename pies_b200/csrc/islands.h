@@ -49,6 +49,7 @@ struct IslandWork {
   DevBuf<uint8_t> big;
   DevBuf<uint32_t> winFlag, blkFlag, actWin, actBlk, actCounts;
   bool restricted = false;
+  bool united = false;            // this substep's islands were built from contacts (parent holds the forest over bodies)
   DevBuf<uint4> trace;            // diagnostics (PIES_B200_ISLAND_TRACE): per list entry (rows, iterations, SM clocks, matrix entries) of the last solve
   DevBuf<uint32_t> solveStats;    // 4 words per solve of a tick: max iterations, sum of iterations x rows, islands at the cap, worst residual
   uint32_t* host = nullptr;       // pinned copy of counts (8 words) + solveStats

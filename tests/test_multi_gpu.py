@@ -153,15 +153,18 @@ def test_lockstep_with_tetgen_bodies(pb):
     assert ref[10][2] > 0
 
 
-def _nccl_worker(rank, world, port, out, native=True):
+def _nccl_worker(rank, world, port, out, native=True, pitch=2.05):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
+    if native == "every":   # A/B switch of the library (read once per process): never skip the per-iteration exchanges
+        os.environ["PIES_B200_HALO_EVERY_ITERATION"] = "1"
+        native = True
     from pies_b200 import multigpu as mg
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    specs = row_specs(columns=6)
+    specs = row_specs(columns=6, pitch=pitch)
     s = mg.SlabSolver(specs, rank=rank, world=world, halo=3.2, device=rank, dist=dist, snap=0.5, check_every=4,
                       native_halo=native, **OPTS)
     assert s.native_halo == native
@@ -177,23 +180,28 @@ def _nccl_worker(rank, world, port, out, native=True):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("native", [True, False])
-def test_nccl_two_ranks_match_single_solver(pb, native):
+@pytest.mark.parametrize("native,pitch", [(True, 2.05), (True, 3.0), ("every", 3.0), (False, 2.05)])
+def test_nccl_two_ranks_match_single_solver(pb, native, pitch):
     """native: the halo exchange inside libpies_b200.so (ncclSend / ncclRecv from pies_b200_tick, csrc/halo.cu);
-    otherwise the same lists through torch.distributed point-to-point ops between the phases of the tick."""
+    otherwise the same lists through torch.distributed point-to-point ops between the phases of the tick.
+    pitch 2.05: neighbouring columns touch, so islands mix owned and ghost rows and every PD iteration exchanges;
+    pitch 3.0: columns apart — the ranks agree collectively that no island mixes and skip the per-iteration exchanges
+    ("every" forces them: same positions either way)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     import torch.multiprocessing as mp
-    specs = row_specs(columns=6)
+    specs = row_specs(columns=6, pitch=pitch)
     ref = _single(pb, specs, (10,))
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_nccl_worker, args=(2, _free_port(), out, native), nprocs=2, join=True)
+    mp.spawn(_nccl_worker, args=(2, _free_port(), out, native, pitch), nprocs=2, join=True)
     diag = bbox_diag(ref[10][0])
     assert float(np.abs(out["pos"] - ref[10][0]).max()) <= 1e-4 * diag
     assert out["halo_bytes"] > 0
-    if native:
+    if native is True and pitch > 2.5:
+        assert out["exchanges"] == 1       # only the three-plane exchange of the substep
+    elif native is not False:
         assert out["exchanges"] == 11      # one 3-plane exchange per substep + one per PD iteration
 
 
